@@ -1,0 +1,150 @@
+/*
+ * ref_harness.cpp -- thin driver around the UNMODIFIED reference library
+ * (RabbitSketch, compiled from /root/reference by oracle/Makefile into oracle/_ref/).
+ * TEST / BASELINE INFRASTRUCTURE ONLY: used to validate oracle/tclust_oracle.c, to
+ * generate tests/golden/, and as the "reference" CPU baseline timed by bench.py.
+ * It contains no reference source; it only calls the reference's public API
+ * (Sketch::MinHash, RabbitSketch/src/Sketch.h:55-164).
+ *
+ *   ref_harness sketch <k> <s> <fasta[.gz]>...      one sketch per FILE (as sketchFiles,
+ *                                                   src/SketchInfo.cpp:865-992); binary out:
+ *                                                   per file  u64 n, u64 h[n]
+ *   ref_harness pairs <hash.sketch> <threads> <nmax> [contain]
+ *                                                   all-pairs MinHash::distance (semantic B,
+ *                                                   MinHash.cpp:1125-1153) over the first nmax
+ *                                                   sketches; prints JSON with pairs/s
+ *   ref_harness update <k> <s> <threads> <len> <ngenomes>
+ *                                                   time MinHash::update on synthetic genomes
+ *   ref_harness dist <hash.sketch> <i> <j>          jaccard/distance of one pair (semantic B)
+ */
+#include "Sketch.h"
+#include <zlib.h>
+#include "kseq.h"
+#include <omp.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+KSEQ_INIT(gzFile, gzread)
+
+static double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct Folder { int func_id, k; bool contain; int param; std::vector<std::vector<uint64_t>> sk; };
+
+static bool load_hash_sketch(const char *path, size_t nmax, Folder &f)
+{
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return false;
+    if (fread(&f.func_id, 4, 1, fp) != 1 || fread(&f.k, 4, 1, fp) != 1 ||
+        fread(&f.contain, 1, 1, fp) != 1 || fread(&f.param, 4, 1, fp) != 1) { fclose(fp); return false; }
+    size_t n;
+    while (f.sk.size() < nmax && fread(&n, sizeof(size_t), 1, fp) == 1) {
+        std::vector<uint64_t> h(n);
+        if (n && fread(h.data(), 8, n, fp) != n) break;
+        f.sk.push_back(std::move(h));
+    }
+    fclose(fp);
+    return true;
+}
+
+static int cmd_sketch(int argc, char **argv)
+{
+    int k = atoi(argv[2]), s = atoi(argv[3]);
+    for (int a = 4; a < argc; a++) {
+        gzFile fp = gzopen(argv[a], "r");
+        if (!fp) { fprintf(stderr, "cannot open %s\n", argv[a]); return 1; }
+        kseq_t *ks = kseq_init(fp);
+        Sketch::MinHash mh(k, s);
+        while (kseq_read(ks) >= 0) mh.update(ks->seq.s);
+        std::vector<uint64_t> h = mh.storeMinHashes();
+        uint64_t n = h.size();
+        fwrite(&n, 8, 1, stdout);
+        fwrite(h.data(), 8, n, stdout);
+        kseq_destroy(ks);
+        gzclose(fp);
+    }
+    return 0;
+}
+
+static int cmd_pairs(int argc, char **argv)
+{
+    Folder f;
+    int threads = atoi(argv[3]);
+    size_t nmax = strtoull(argv[4], 0, 10);
+    bool contain = argc > 5 && !strcmp(argv[5], "contain");
+    if (!load_hash_sketch(argv[2], nmax, f)) { fprintf(stderr, "cannot read %s\n", argv[2]); return 1; }
+    size_t N = f.sk.size();
+    std::vector<Sketch::MinHash *> mh(N);
+    for (size_t i = 0; i < N; i++) {
+        mh[i] = new Sketch::MinHash(f.k, f.param);
+        mh[i]->loadMinHashes(f.sk[i]);
+        mh[i]->getSketchSize();
+    }
+    double sum = 0;
+    double t0 = now_s();
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 8) reduction(+ : sum)
+    for (long i = 0; i < (long)N; i++)
+        for (size_t j = 0; j < (size_t)i; j++)
+            sum += contain ? mh[i]->containDistance(mh[j]) : mh[i]->distance(mh[j]);
+    double t1 = now_s();
+    double pairs = (double)N * (N - 1) / 2;
+    printf("{\"n\": %zu, \"pairs\": %.0f, \"seconds\": %.6f, \"pairs_per_s\": %.1f, \"threads\": %d, \"dist_sum\": %.10f}\n",
+           N, pairs, t1 - t0, pairs / (t1 - t0), threads, sum);
+    return 0;
+}
+
+static int cmd_update(int argc, char **argv)
+{
+    int k = atoi(argv[2]), s = atoi(argv[3]), threads = atoi(argv[4]);
+    size_t len = strtoull(argv[5], 0, 10);
+    int ng = atoi(argv[6]);
+    std::vector<std::string> g(ng);
+    for (int i = 0; i < ng; i++) {
+        uint64_t x = 0x9E3779B97F4A7C15ULL * (i + 1);
+        g[i].resize(len);
+        for (size_t p = 0; p < len; p++) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            g[i][p] = "ACGT"[x & 3];
+        }
+    }
+    uint64_t chk = 0;
+    double t0 = now_s();
+#pragma omp parallel for num_threads(threads) schedule(dynamic) reduction(^ : chk)
+    for (int i = 0; i < ng; i++) {
+        Sketch::MinHash mh(k, s);
+        mh.update(&g[i][0]);
+        std::vector<uint64_t> h = mh.storeMinHashes();
+        for (uint64_t v : h) chk ^= v;
+    }
+    double t1 = now_s();
+    printf("{\"genomes\": %d, \"len\": %zu, \"seconds\": %.6f, \"genomes_per_s\": %.3f, \"mbp_per_s\": %.3f, \"threads\": %d, \"chk\": %llu}\n",
+           ng, len, t1 - t0, ng / (t1 - t0), ng * (double)len / 1e6 / (t1 - t0), threads, (unsigned long long)chk);
+    return 0;
+}
+
+static int cmd_dist(int argc, char **argv)
+{
+    Folder f;
+    if (!load_hash_sketch(argv[2], (size_t)-1, f)) return 1;
+    int i = atoi(argv[3]), j = atoi(argv[4]);
+    Sketch::MinHash a(f.k, f.param), b(f.k, f.param);
+    a.loadMinHashes(f.sk[i]); b.loadMinHashes(f.sk[j]);
+    printf("%.17g %.17g %.17g\n", a.jaccard(&b), a.distance(&b), a.containDistance(&b));
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc >= 5 && !strcmp(argv[1], "sketch")) return cmd_sketch(argc, argv);
+    if (argc >= 5 && !strcmp(argv[1], "pairs")) return cmd_pairs(argc, argv);
+    if (argc >= 7 && !strcmp(argv[1], "update")) return cmd_update(argc, argv);
+    if (argc >= 5 && !strcmp(argv[1], "dist")) return cmd_dist(argc, argv);
+    fprintf(stderr, "usage: see header of ref_harness.cpp\n");
+    return 2;
+}

@@ -1,0 +1,454 @@
+/*
+ * tclust_oracle.c -- CPU restatement of the RabbitTClust hot paths (plain C).
+ * TEST INFRASTRUCTURE ONLY -- see tclust_oracle.h.  Not linked by the product.
+ * Citations are relative to /root/reference.
+ */
+#include "tclust_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ Murmur3 */
+static inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+static inline uint64_t fmix64(uint64_t k) {           /* MurmurHash3.cpp fmix64 */
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33; return k;
+}
+
+/* RabbitSketch/src/MurmurHash3.cpp:259-336 (public-domain MurmurHash3_x64_128). */
+uint64_t oc_murmur3_x64_128_h1(const uint8_t *data, int len, uint32_t seed)
+{
+    const int nblocks = len / 16;
+    uint64_t h1 = seed, h2 = seed;
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    for (int i = 0; i < nblocks; i++) {
+        uint64_t k1, k2;
+        memcpy(&k1, data + 16 * i, 8);
+        memcpy(&k2, data + 16 * i + 8, 8);
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    const uint8_t *tail = data + nblocks * 16;
+    uint64_t k1 = 0, k2 = 0;
+    int rem = len & 15;
+    for (int i = rem - 1; i >= 8; i--) k2 |= (uint64_t)tail[i] << (8 * (i - 8));
+    if (rem > 8) { k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+    for (int i = (rem > 8 ? 7 : rem - 1); i >= 0; i--) k1 |= (uint64_t)tail[i] << (8 * i);
+    if (rem > 0) { k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1; }
+    h1 ^= (uint64_t)len; h2 ^= (uint64_t)len;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2; /* h2 += h1; */
+    return h1;
+}
+
+/* RabbitSketch/src/MinHash.cpp:1185-1195 */
+void oc_revcomp(const uint8_t *src, uint8_t *dst, size_t n)
+{
+    static const uint8_t table[4] = {'T', 'G', 'A', 'C'};
+    for (size_t i = 0; i < n; i++) dst[n - 1 - i] = table[(src[i] >> 1) & 3];
+}
+
+/* ------------------------------------------------------- bottom-s selection */
+static int cmp_u64(const void *a, const void *b)
+{
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : x > y;
+}
+typedef struct { uint64_t *buf; size_t n, cap, s; uint64_t tau; } bottom_s;
+
+/* sort + unique + truncate to s; tau = s-th smallest once s distinct values exist.
+ * Equivalent to MinHashHeap::tryInsert's "s smallest distinct" (MinHash.cpp:287-348). */
+static void bs_compact(bottom_s *b)
+{
+    qsort(b->buf, b->n, 8, cmp_u64);
+    size_t m = 0;
+    for (size_t i = 0; i < b->n; i++)
+        if (m == 0 || b->buf[i] != b->buf[m - 1]) b->buf[m++] = b->buf[i];
+    if (m > b->s) m = b->s;
+    b->n = m;
+    if (m == b->s && m > 0) b->tau = b->buf[m - 1];
+}
+static inline void bs_push(bottom_s *b, uint64_t h)
+{
+    if (h > b->tau) return;           /* cannot be among the s smallest distinct */
+    if (b->n == b->cap) bs_compact(b);
+    b->buf[b->n++] = h;
+}
+
+/* AVX-512 build's strand choice, MinHash.cpp:396-402 (min512) + 555-571: lanes of
+ * 8 bytes of the zero-padded k-mer, highest lane first, signed 64-bit compare. */
+static int fwd_is_min512(const uint8_t *f, const uint8_t *r, int k)
+{
+    uint8_t a[64], b[64];
+    memset(a, 0, 64); memset(b, 0, 64);
+    memcpy(a, f, k); memcpy(b, r, k);
+    for (int lane = 7; lane >= 0; lane--) {
+        int64_t x, y;
+        memcpy(&x, a + 8 * lane, 8); memcpy(&y, b + 8 * lane, 8);
+        if (x < y) return 1;
+        if (x > y) return 0;
+    }
+    return 0;
+}
+
+/* MinHash::update (MinHash.cpp:465-747) over every record, then heapToList
+ * (756-810). */
+size_t oc_minhash_sketch(const uint8_t *seq, const uint64_t *rec_off, int nrec,
+                         int k, size_t s, uint32_t seed, int rule, uint64_t *out)
+{
+    bottom_s b;
+    b.s = s; b.cap = 4 * s + 1024; b.n = 0; b.tau = UINT64_MAX;
+    b.buf = (uint64_t *)malloc(b.cap * 8);
+    for (int r = 0; r < nrec; r++) {
+        size_t len = (size_t)(rec_off[r + 1] - rec_off[r]);
+        if (len < (size_t)k) continue;
+        uint8_t *fw = (uint8_t *)malloc(len), *rc = (uint8_t *)malloc(len);
+        memcpy(fw, seq + rec_off[r], len);
+        for (size_t i = 0; i < len; i++)                 /* MinHash.cpp:472-479 */
+            if (fw[i] > 96 && fw[i] < 123) fw[i] -= 32;
+        oc_revcomp(fw, rc, len);
+        size_t n = len - k + 1, body16 = (n / 16) * 16;
+        for (size_t i = 0; i < n; i++) {
+            const uint8_t *f = fw + i, *v = rc + len - i - k;
+            int use_fwd;
+            if (rule == 1 && i < body16) use_fwd = fwd_is_min512(f, v, k);
+            else use_fwd = memcmp(f, v, k) <= 0;          /* MinHash.cpp:667-670,696 */
+            bs_push(&b, oc_murmur3_x64_128_h1(use_fwd ? f : v, k, seed));
+        }
+        free(fw); free(rc);
+    }
+    bs_compact(&b);
+    memcpy(out, b.buf, b.n * 8);
+    size_t n = b.n;
+    free(b.buf);
+    return n;
+}
+
+/* --------------------------------------------------------------------- KSSD */
+static void oc_shuffle(int32_t *arr, int length, unsigned seed)  /* SketchInfo.cpp:60-78 */
+{
+    srand(seed);
+    for (int i = length - 1; i > 0; i--) {
+        int j = rand() % (i + 1);
+        int32_t t = arr[i]; arr[i] = arr[j]; arr[j] = t;
+    }
+}
+void oc_kssd_shuffled_dim(int half_subk, int32_t *out)          /* SketchInfo.cpp:80-102 */
+{
+    int n = 1 << (4 * half_subk);
+    for (int i = 0; i < n; i++) out[i] = i;
+    oc_shuffle(out, n, 23);
+    oc_shuffle(out, n, 348842630u);
+}
+
+size_t oc_kssd_sketch(const uint8_t *seq, const uint64_t *rec_off, int nrec,
+                      int kmer_size, int drlevel, const int32_t *shuffled_dim,
+                      uint64_t *out, size_t out_cap)
+{
+    /* constants: SketchInfo.cpp:1019-1048 */
+    int half_k = (kmer_size + 1) / 2;
+    int kmer = half_k * 2;
+    int use64 = half_k - drlevel > 8;
+    int half_subk = 6 - drlevel >= 2 ? 6 : drlevel + 2;
+    int dim_end = 1 << (4 * (half_subk - drlevel));
+    int comp_bittl = 64 - 4 * half_k;
+    int half_outctx_len = half_k - half_subk;
+    int rev_add_move = 4 * half_k - 2;
+    uint64_t tupmask = UINT64_MAX >> comp_bittl;
+    uint64_t domask = (tupmask >> (4 * half_outctx_len)) << (2 * half_outctx_len);
+    uint64_t undomask = (tupmask ^ domask) & tupmask;
+    uint64_t undomask1 = undomask & (tupmask >> ((half_k + half_subk) * 2));
+    uint64_t undomask0 = undomask ^ undomask1;
+    size_t n = 0, cap = 1 << 16;
+    uint64_t *buf = (uint64_t *)malloc(cap * 8);
+    for (int r = 0; r < nrec; r++) {
+        uint64_t tuple = 0, rvs = 0;
+        int base = 1;
+        for (uint64_t p = rec_off[r]; p < rec_off[r + 1]; p++) {   /* :1126-1165 */
+            int bn;
+            switch (seq[p]) {
+                case 'A': case 'a': bn = 0; break;
+                case 'C': case 'c': bn = 1; break;
+                case 'G': case 'g': bn = 2; break;
+                case 'T': case 't': bn = 3; break;
+                default: bn = -1;
+            }
+            if (bn < 0) { base = 1; tuple = 0; rvs = 0; continue; }
+            tuple = ((tuple << 2) | (uint64_t)bn) & tupmask;
+            rvs = (rvs >> 2) + (((uint64_t)bn ^ 3ULL) << rev_add_move);
+            base++;
+            if (base > kmer) {
+                uint64_t uni = tuple < rvs ? tuple : rvs;
+                uint32_t dim_id = (uint32_t)((uni & domask) >> (half_outctx_len * 2));
+                int pf = shuffled_dim[dim_id];
+                if (pf >= dim_end) continue;
+                uint64_t dr = (((uni & undomask0) |
+                                ((uni & undomask1) << (kmer * 2 - half_outctx_len * 4)))
+                               >> (drlevel * 4)) | (uint64_t)pf;
+                if (!use64) dr &= 0xffffffffULL;
+                if (n == cap) { cap *= 2; buf = (uint64_t *)realloc(buf, cap * 8); }
+                buf[n++] = dr;
+            }
+        }
+    }
+    qsort(buf, n, 8, cmp_u64);                                     /* :1180-1193 */
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++)
+        if (m == 0 || buf[i] != buf[m - 1]) buf[m++] = buf[i];
+    if (m > out_cap) m = out_cap;
+    memcpy(out, buf, m * 8);
+    free(buf);
+    return m;
+}
+
+/* --------------------------------------------------------------- distances */
+uint32_t oc_intersect_u64(const uint64_t *a, size_t na, const uint64_t *b, size_t nb,
+                          uint32_t *first_hit)
+{
+    size_t i = 0, j = 0; uint32_t c = 0, fh = UINT32_MAX;
+    while (i < na && j < nb) {
+        if (a[i] < b[j]) i++;
+        else if (a[i] > b[j]) j++;
+        else { if (!c) fh = (uint32_t)i; c++; i++; j++; }
+    }
+    if (first_hit) *first_hit = fh;
+    return c;
+}
+
+double oc_jaccard_B(const uint64_t *a, size_t na, const uint64_t *b, size_t nb,
+                    uint64_t sketch_size)                 /* MinHash.cpp:1058-1100 */
+{
+    uint64_t i = 0, j = 0, common = 0, denom = 0;
+    while (denom < sketch_size && i < na && j < nb) {
+        if (a[i] < b[j]) i++;
+        else if (b[j] < a[i]) j++;
+        else { i++; j++; common++; }
+        denom++;
+    }
+    if (denom < sketch_size) {
+        if (i < na) denom += na - i;
+        if (j < nb) denom += nb - j;
+        if (denom > sketch_size) denom = sketch_size;
+    }
+    return (double)common / (double)denom;
+}
+
+double oc_distance_B(double jaccard, int k)               /* MinHash.cpp:1125-1153 */
+{
+    if (jaccard == 1.0) return 0;
+    double d = -log(2 * jaccard / (1. + jaccard)) / k;
+    if (d > 1) d = 1;
+    return d;
+}
+
+int oc_radio(double threshold, int kmer_size)             /* MST.cpp:26-37,1292 */
+{
+    return (int)(2.0 * exp(threshold * (kmer_size - 1)) - 1.0);
+}
+
+double oc_mash_dist_A(int common, int size0, int size1, int k)   /* MST.cpp:1489-1503 */
+{
+    const double inv_k = 1.0 / k;
+    int denom = size0 + size1 - common;
+    double jaccard = denom == 0 ? 0.0 : (double)common / denom;
+    if (jaccard == 1.0) return 0.0;
+    if (jaccard == 0.0) return 1.0;
+    double ratio = (2.0 * jaccard) / (1.0 + jaccard);
+    return -inv_k * log(ratio);
+}
+
+double oc_aaf_dist_mst(int common, int size0, int size1, int k)  /* MST.cpp:1504-1515 */
+{
+    const double inv_k = 1.0 / k;
+    int denom = size0 < size1 ? size0 : size1;
+    double c = denom == 0 ? 0.0 : (double)common / denom;
+    if (c == 1.0) return 0.0;
+    if (c == 0.0) return 1.0;
+    return -inv_k * log(c);
+}
+
+double oc_greedy_dist(int common, int size_ref, int size_qry, int containment, int k)
+{                                                          /* greedy.cpp:1245-1274 */
+    double dist;
+    if (containment) {
+        int mn = size_ref < size_qry ? size_ref : size_qry;
+        if (mn == 0) return 1.0;
+        double j = (double)common / mn;
+        if (j >= 1.0) dist = 0.0;
+        else if (j <= 0.0) dist = 1.0;
+        else { dist = -log(2.0 * j / (1.0 + j)) / k; if (dist > 1.0) dist = 1.0; }
+    } else {
+        int denom = size_ref + size_qry - common;
+        if (denom == 0) return 0.0;
+        double j = (double)common / denom;
+        if (j >= 1.0) dist = 0.0;
+        else if (j <= 0.0) dist = 1.0;
+        else { dist = -log(2.0 * j / (1.0 + j)) / k; if (dist > 1.0) dist = 1.0; }
+    }
+    return dist;
+}
+
+int oc_greedy_common_min(double threshold, int k, int size_ref, int size_qry, int containment)
+{                                                          /* greedy.cpp:1107-1113,1211-1219 */
+    double x = exp(-threshold * k);
+    double jmin = x / (2.0 - x);
+    if (containment) {
+        int mn = size_ref < size_qry ? size_ref : size_qry;
+        return (int)ceil(jmin * mn);
+    }
+    return (int)ceil(jmin * (size_ref + size_qry) / (1.0 + jmin));
+}
+
+/* ---------------------------------------------------------------------- MST */
+static int uf_find(int *p, int x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; }
+
+static int cmp_edge(const void *a, const void *b)
+{
+    const oc_edge *x = (const oc_edge *)a, *y = (const oc_edge *)b;
+    if (x->dist < y->dist) return -1;
+    if (x->dist > y->dist) return 1;
+    if (x->pre != y->pre) return x->pre < y->pre ? -1 : 1;
+    return x->suf < y->suf ? -1 : x->suf > y->suf;
+}
+
+size_t oc_mst(const uint64_t *hashes, const uint64_t *off, int N, int k,
+              int containment, double threshold, oc_edge *out)
+{
+    int radio = oc_radio(threshold, k);
+    size_t cap = 1 << 16, n = 0;
+    oc_edge *g = (oc_edge *)malloc(cap * sizeof(oc_edge));
+    for (int i = 0; i < N; i++) {
+        int size0 = (int)(off[i + 1] - off[i]);
+        if (size0 == 0) continue;                              /* MST.cpp:1404 */
+        for (int j = 0; j < i; j++) {
+            int size1 = (int)(off[j + 1] - off[j]);
+            if (size1 == 0) continue;
+            int common = (int)oc_intersect_u64(hashes + off[i], size0, hashes + off[j], size1, NULL);
+            if (common == 0) continue;        /* only index hits are candidates, :1409-1435 */
+            int mn = size0 < size1 ? size0 : size1, mx = size0 > size1 ? size0 : size1;
+            if (mx > radio * mn) continue;                     /* :1481-1487 */
+            double d = containment ? oc_aaf_dist_mst(common, size0, size1, k)
+                                   : oc_mash_dist_A(common, size0, size1, k);
+            if (n == cap) { cap *= 2; g = (oc_edge *)realloc(g, cap * sizeof(oc_edge)); }
+            g[n].pre = i; g[n].suf = j; g[n].dist = d; n++;
+        }
+    }
+    qsort(g, n, sizeof(oc_edge), cmp_edge);                    /* :1721 */
+    int *p = (int *)malloc(sizeof(int) * (N > 0 ? N : 1));
+    for (int i = 0; i < N; i++) p[i] = i;
+    size_t m = 0;
+    for (size_t e = 0; e < n; e++) {                           /* kruskalAlgorithm :59-75 */
+        int a = uf_find(p, g[e].pre), b = uf_find(p, g[e].suf);
+        if (a != b) { p[a] = b; out[m++] = g[e]; }
+    }
+    free(p); free(g);
+    return m;
+}
+
+void oc_common_matrix(const uint64_t *hashes, const uint64_t *off, int N, uint32_t *out)
+{
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++)
+            out[(size_t)i * N + j] = oc_intersect_u64(hashes + off[i], off[i + 1] - off[i],
+                                                      hashes + off[j], off[j + 1] - off[j], NULL);
+}
+
+int oc_clusters_from_mst(const oc_edge *mst, size_t n_edges, int N, double threshold,
+                         int32_t *labels, int32_t *order)
+{
+    /* generateForest (MST.cpp:77-85) + generateClusterWithBfs (:109-142) */
+    int *deg = (int *)calloc(N + 1, sizeof(int));
+    for (size_t e = 0; e < n_edges; e++)
+        if (mst[e].dist <= threshold) { deg[mst[e].pre]++; deg[mst[e].suf]++; }
+    int *start = (int *)malloc(sizeof(int) * (N + 1));
+    start[0] = 0;
+    for (int i = 0; i < N; i++) start[i + 1] = start[i] + deg[i];
+    int *adj = (int *)malloc(sizeof(int) * (start[N] + 1));
+    int *fill = (int *)calloc(N + 1, sizeof(int));
+    for (size_t e = 0; e < n_edges; e++)
+        if (mst[e].dist <= threshold) {
+            int u = mst[e].pre, v = mst[e].suf;
+            adj[start[u] + fill[u]++] = v;
+            adj[start[v] + fill[v]++] = u;
+        }
+    char *vis = (char *)calloc(N + 1, 1);
+    int *q = (int *)malloc(sizeof(int) * (N + 1));
+    int nclust = 0, pos = 0;
+    for (int i = 0; i < N; i++) {
+        if (vis[i]) continue;
+        vis[i] = 1;
+        int qh = 0, qt = 0;
+        q[qt++] = i; labels[i] = nclust; order[pos++] = i;
+        while (qh < qt) {
+            int u = q[qh++];
+            for (int t = start[u]; t < start[u + 1]; t++) {
+                int v = adj[t];
+                if (vis[v]) continue;
+                vis[v] = 1; q[qt++] = v; labels[v] = nclust; order[pos++] = v;
+            }
+        }
+        nclust++;
+    }
+    free(deg); free(start); free(adj); free(fill); free(vis); free(q);
+    return nclust;
+}
+
+/* ------------------------------------------------------------------- greedy */
+typedef struct { uint32_t first_hit; int order; int rep; int common; } touched_t;
+static int cmp_touched(const void *a, const void *b)
+{
+    const touched_t *x = (const touched_t *)a, *y = (const touched_t *)b;
+    if (x->first_hit != y->first_hit) return x->first_hit < y->first_hit ? -1 : 1;
+    return x->order < y->order ? -1 : x->order > y->order;
+}
+
+int oc_greedy_inverted(const uint64_t *hashes, const uint64_t *off, int N, int k,
+                       int containment, double threshold, int32_t *rep_of)
+{
+    if (N == 0) return 0;
+    int *reps = (int *)malloc(sizeof(int) * N), nrep = 0;
+    touched_t *tc = (touched_t *)malloc(sizeof(touched_t) * N);
+    /* fixed-size fast path detection over the first 100 sketches, greedy.cpp:1092-1103 */
+    int fixed_size = (int)(off[1] - off[0]);
+    int all_fixed = !containment;
+    for (int i = 1; i < (N < 100 ? N : 100); i++)
+        if (containment || (int)(off[i + 1] - off[i]) != fixed_size) { all_fixed = 0; break; }
+    int fixed_common_min = 0;
+    if (all_fixed) fixed_common_min = oc_greedy_common_min(threshold, k, fixed_size, fixed_size, 0);
+    reps[nrep++] = 0; rep_of[0] = 0;
+    for (int j = 1; j < N; j++) {
+        const uint64_t *q = hashes + off[j];
+        int size_ref = (int)(off[j + 1] - off[j]);
+        int nt = 0;
+        for (int r = 0; r < nrep; r++) {                       /* index probe :1148-1164 */
+            int id = reps[r];
+            uint32_t fh;
+            int c = (int)oc_intersect_u64(q, size_ref, hashes + off[id], off[id + 1] - off[id], &fh);
+            if (c > 0) { tc[nt].first_hit = fh; tc[nt].order = r; tc[nt].rep = id; tc[nt].common = c; nt++; }
+        }
+        qsort(tc, nt, sizeof(touched_t), cmp_touched);         /* touched order, 8a-G */
+        int best_common = -1, best_rep = -1;
+        double best_dist = 1.7976931348623157e308;
+        for (int t = 0; t < nt; t++) {                         /* :1198-1285 with one thread */
+            int id = tc[t].rep, common = tc[t].common;
+            int size_qry = (int)(off[id + 1] - off[id]);
+            int cmin = all_fixed ? fixed_common_min
+                                 : oc_greedy_common_min(threshold, k, size_ref, size_qry, containment);
+            if (common < cmin) continue;
+            if (all_fixed) {
+                if (common > best_common) { best_common = common; best_rep = id; }
+            } else {
+                double d = oc_greedy_dist(common, size_ref, size_qry, containment, k);
+                if (d <= threshold && d < best_dist) { best_dist = d; best_common = common; best_rep = id; }
+            }
+        }
+        if (best_rep != -1) rep_of[j] = best_rep;
+        else { reps[nrep++] = j; rep_of[j] = j; }
+    }
+    free(reps); free(tc);
+    return nrep;
+}
