@@ -1,0 +1,160 @@
+/*
+ * tclust.h -- C ABI of libtclust_cuda.so: the B200 (sm_100a) implementation of the two
+ * data-parallel hot paths of RabbitTClust.
+ *
+ * The reference has no FFI layer; the hot paths sit behind the library API its callers
+ * use.  Each entry point below names the reference interface it stands
+ * in for (paths relative to the reference root).  INTEGRATION.md shows the call sites a
+ * maintainer would change.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (message via
+ * tc_last_error(), thread-local).  The caller owns all host buffers.  Device memory is
+ * owned by the opaque tc_ctx (one per process per GPU, single caller thread).  Pointers
+ * named *_dev are CUDA device pointers on the context's device; all others are host
+ * pointers.  There is NO CPU fallback: without a CUDA device tc_ctx_create fails.
+ *
+ * Results are integers (hashes, intersection sizes, ids).  Distances are produced on the
+ * host by tc_*_dist below with the reference's exact expression order and glibc log(), so
+ * they are bit-identical to the reference's doubles.
+ */
+#ifndef TCLUST_H
+#define TCLUST_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TC_VERSION 100
+typedef struct tc_ctx tc_ctx;
+
+/* src/MST.h:17-21 EdgeInfo {int preNode; int sufNode; double dist;} (edge.mst record,
+ * src/MST_IO.cpp:200-217). */
+typedef struct { int32_t pre, suf; double dist; } tc_edge;
+
+/* one candidate edge of the semantic-A graph: pair (i, j<i) with common >= 1 */
+typedef struct { uint32_t i, j, common; } tc_pair;
+
+int         tc_version(void);
+const char *tc_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------ */
+int  tc_ctx_create(int device, tc_ctx **out);
+void tc_ctx_destroy(tc_ctx *ctx);
+/* number of kernels of this library launched on the context so far (bench accounting) */
+uint64_t tc_kernel_launches(const tc_ctx *ctx);
+/* CUDA stream (cudaStream_t) the context launches on, for event timing by the caller */
+void *tc_stream(const tc_ctx *ctx);
+
+/* ---- HP-1: sketch construction ------------------------------------------------------- */
+/*
+ * MinHash bottom-s sketches of `ngenomes` genomes.  Replaces, per genome,
+ *   Sketch::MinHash mh(k, size, seed=42); for each record: mh.update(seq); mh.storeMinHashes()
+ * (RabbitSketch/src/Sketch.h:60-101, MinHash.cpp:465-747, 287-348, 756-843; driver
+ * src/SketchInfo.cpp:918-948).
+ * seqs: concatenated record bytes (any case, any byte; upper-cased on device as
+ * MinHash.cpp:472-479); record r = seqs[rec_off[r] .. rec_off[r+1]); rec2genome[r] = genome
+ * of record r (non-decreasing).  k <= 32.  sketch_size[g] = s of genome g.
+ * out_hashes: ngenomes rows of out_stride u64 (out_stride >= max sketch_size); row g holds
+ * out_n[g] <= sketch_size[g] hashes ascending (the s smallest distinct).
+ */
+int tc_sketch_minhash(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off,
+                      const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes, int k,
+                      const uint32_t *sketch_size, uint32_t seed,
+                      uint64_t *out_hashes, uint64_t out_stride, uint32_t *out_n);
+/* same with all buffers already resident on the device (timed "value" leg of bench.py);
+ * seqs_dev must be readable 16 bytes past its end. */
+int tc_sketch_minhash_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const uint64_t *rec_off,
+                          const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes, int k,
+                          const uint32_t *sketch_size, uint32_t seed,
+                          uint64_t *out_hashes_dev, uint64_t out_stride, uint32_t *out_n_dev);
+
+/*
+ * KSSD (--fast) sketches, list mode.  Replaces the hot loop of sketchFileWithKssd
+ * (src/SketchInfo.cpp:1019-1048 constants, 1126-1165 loop, 1180-1193 sort).
+ * shuffled_dim: host table of 1<<(4*half_subk) ints (generate_shuffle_dim,
+ * SketchInfo.cpp:60-102; glibc rand() -- host-only by construction).
+ * out: ngenomes rows of out_stride u64, ascending, distinct; out_n[g] = count (an error is
+ * returned if a genome yields more than out_stride hashes).
+ */
+int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off,
+                   const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes,
+                   int kmer_size, int drlevel, const int32_t *shuffled_dim,
+                   uint64_t *out_hashes, uint64_t out_stride, uint32_t *out_n);
+
+/* ---- HP-2: all-pairs sorted-sketch intersection -------------------------------------- */
+/*
+ * Make N sorted, duplicate-free sketches resident on the device (what compute_minhash_mst
+ * caches at src/MST.cpp:1311-1322 and greedy.cpp:1138).  sketch g = hashes[off[g]..off[g+1]).
+ * Replaces any previously uploaded set.
+ */
+int tc_sketches_upload(tc_ctx *ctx, const uint64_t *hashes, const uint64_t *off, uint32_t n);
+int tc_sketches_upload_dev(tc_ctx *ctx, const uint64_t *hashes_dev, const uint64_t *off, uint32_t n);
+
+/* validation: common[i-i0][j-j0] = |sketch_i n sketch_j| for i in [i0,i1), j in [j0,j1)
+ * (semantic A: the counts of src/MST.cpp:1409-1435).  impl 0 = tiled production kernel,
+ * 1 = independent u64 global-memory merge kernel. */
+int tc_pair_common(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1,
+                   int impl, uint32_t *out);
+
+/*
+ * One dense pass over all pairs j < i of the uploaded sketches, restricted to the tiles
+ * owned by `part` of `nparts` (multi-GPU sharding; 0/1 = everything).  Emits the candidate
+ * edges of compute_minhash_mst: common >= 1 and max(size) <= radio*min(size)
+ * (src/MST.cpp:1470,1481-1487).  Edges stay on the device for tc_mst_*; n_pairs / n_edges
+ * (may be NULL) receive the pairs evaluated and edges kept by this call.
+ */
+int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts,
+                     uint64_t *n_pairs, uint64_t *n_edges);
+/* copy the candidate edges kept so far to the host (cap entries at most; *n = total) */
+int tc_edges_download(tc_ctx *ctx, tc_pair *out, uint64_t cap, uint64_t *n);
+
+/*
+ * Boruvka over the device-resident candidate edges.  One round: per current component
+ * (comp[v], host array of N labels) the minimum-weight outgoing edge under the total order
+ * (distance asc == similarity key desc, then (i,j) asc).  Two reductions per round so that
+ * ranks can all-reduce(min) between them:
+ *   phase 1: best_key[c]  = min over outgoing edges of key      (N u64, device buffer)
+ *   phase 2: best_edge[c] = min (i<<32|j) among edges whose key == best_key[c]
+ * key = ~bits(J) with J = (double)common/denom exactly as src/MST.cpp:1489-1492 (Mash) or
+ * :1505-1507 (containment) computes it, so the host can turn it into the reference's
+ * distance.  The *_dev buffers are caller-provided (e.g. torch tensors that NCCL reduces).
+ */
+int tc_boruvka_upload_comp(tc_ctx *ctx, const int32_t *comp, uint32_t n);
+int tc_boruvka_phase1(tc_ctx *ctx, int containment, uint64_t *best_key_dev);
+int tc_boruvka_phase2(tc_ctx *ctx, int containment, const uint64_t *best_key_dev,
+                      uint64_t *best_edge_dev);
+
+/*
+ * Whole single-GPU MST build = compute_minhash_mst (src/MST.cpp:1290-1737): dense pass +
+ * Boruvka rounds + host distances.  out: up to n-1 forest edges {i, j<i, dist} sorted by
+ * (dist, i, j); *n_out = count.  The sorted multiset of weights and the partition at any
+ * threshold equal the reference's.
+ */
+int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double threshold,
+           tc_edge *out, uint64_t *n_out);
+
+/*
+ * Greedy representative scan (K5).  For queries q in [q0,q1) against representatives
+ * rep_ids[0..nrep): common[(q-q0)*nrep + r] and first_hit (index in the query sketch of the
+ * first shared hash, UINT32_MAX if none) -- what greedy.cpp:1148-1164 accumulates in
+ * cnt[]/touched[].
+ */
+int tc_greedy_scan(tc_ctx *ctx, uint32_t q0, uint32_t q1, const uint32_t *rep_ids,
+                   uint32_t nrep, uint32_t *common, uint32_t *first_hit);
+/* full MinHashGreedyClusterWithInvertedIndex with one thread (greedy.cpp:986-1399):
+ * rep_of[j] = representative of genome j.  Returns #clusters in *n_clusters. */
+int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, double threshold,
+                      int32_t *rep_of, uint32_t *n_clusters);
+
+/* ---- host-side exact distance helpers (glibc log; reference expression order) --------- */
+double tc_mash_dist(int common, int size0, int size1, int kmer_size);     /* MST.cpp:1489-1503 */
+double tc_aaf_dist(int common, int size0, int size1, int kmer_size);      /* MST.cpp:1504-1515 */
+double tc_dist_from_key(uint64_t key, int containment, int kmer_size);    /* J bits -> dist */
+int    tc_radio(double threshold, int kmer_size);                         /* MST.cpp:26-37,1292 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

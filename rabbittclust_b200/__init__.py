@@ -1,0 +1,236 @@
+"""rabbittclust_b200 -- host-side Python binding of libtclust_cuda.so (include/tclust.h).
+
+The library is the product: hand-written sm_100a CUDA behind a C ABI.  This module only
+marshals numpy arrays into it (ctypes) for the tests, bench.py and the Python tools.  There
+is no CPU fallback: importing works without a GPU (so the symbol-export tests can run), but
+every compute call needs a CUDA device and raises TclustError otherwise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtclust_cuda.so")
+
+EDGE_DTYPE = np.dtype([("pre", "<i4"), ("suf", "<i4"), ("dist", "<f8")])
+PAIR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("common", "<u4")])
+
+# every symbol include/tclust.h declares (tests check the built library exports all of them)
+SYMBOLS = [
+    "tc_version", "tc_last_error", "tc_ctx_create", "tc_ctx_destroy", "tc_kernel_launches", "tc_stream",
+    "tc_sketch_minhash", "tc_sketch_minhash_dev", "tc_sketch_kssd",
+    "tc_sketches_upload", "tc_sketches_upload_dev", "tc_pair_common", "tc_allpairs_pass",
+    "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_mst",
+    "tc_greedy_scan", "tc_greedy_cluster",
+    "tc_mash_dist", "tc_aaf_dist", "tc_dist_from_key", "tc_radio",
+]
+
+
+class TclustError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libtclust_cuda.so; fail loudly if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TclustError(f"{LIB_PATH} is missing: build it with `python -m rabbittclust_b200.build` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u8p, u32p, u64p, i32p = (C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32),
+                                 C.POINTER(C.c_uint64), C.POINTER(C.c_int32))
+    L.tc_version.restype = C.c_int
+    L.tc_last_error.restype = C.c_char_p
+    L.tc_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.tc_ctx_destroy.argtypes = [vp]
+    L.tc_ctx_destroy.restype = None
+    L.tc_kernel_launches.argtypes = [vp]
+    L.tc_kernel_launches.restype = C.c_uint64
+    L.tc_stream.argtypes = [vp]
+    L.tc_stream.restype = vp
+    sk = [vp, vp, u64p, u32p, C.c_uint64, C.c_uint32, C.c_int, u32p, C.c_uint32, vp, C.c_uint64, vp]
+    L.tc_sketch_minhash.argtypes = sk
+    L.tc_sketch_minhash_dev.argtypes = sk
+    L.tc_sketch_kssd.argtypes = [vp, vp, u64p, u32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, i32p,
+                                 vp, C.c_uint64, vp]
+    L.tc_sketches_upload.argtypes = [vp, vp, u64p, C.c_uint32]
+    L.tc_sketches_upload_dev.argtypes = [vp, vp, u64p, C.c_uint32]
+    L.tc_pair_common.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u32p]
+    L.tc_allpairs_pass.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, u64p, u64p]
+    L.tc_edges_download.argtypes = [vp, vp, C.c_uint64, u64p]
+    L.tc_boruvka_upload_comp.argtypes = [vp, i32p, C.c_uint32]
+    L.tc_boruvka_phase1.argtypes = [vp, C.c_int, vp]
+    L.tc_boruvka_phase2.argtypes = [vp, C.c_int, vp, vp]
+    L.tc_mst.argtypes = [vp, C.c_int, C.c_int, C.c_double, vp, u64p]
+    L.tc_greedy_scan.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, C.c_uint32, u32p, u32p]
+    L.tc_greedy_cluster.argtypes = [vp, C.c_int, C.c_int, C.c_double, i32p, u32p]
+    for f in (L.tc_mash_dist, L.tc_aaf_dist):
+        f.argtypes = [C.c_int] * 4
+        f.restype = C.c_double
+    L.tc_dist_from_key.argtypes = [C.c_uint64, C.c_int, C.c_int]
+    L.tc_dist_from_key.restype = C.c_double
+    L.tc_radio.argtypes = [C.c_double, C.c_int]
+    L.tc_radio.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _chk(rc):
+    if rc != 0:
+        raise TclustError(lib().tc_last_error().decode())
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def pack_records(genomes):
+    """genomes: list (one per genome) of lists of bytes records -> (seq u8, rec_off u64, rec2genome u32)."""
+    recs, r2g = [], []
+    for g, rs in enumerate(genomes):
+        for r in rs:
+            recs.append(r if isinstance(r, (bytes, bytearray)) else r.encode())
+            r2g.append(g)
+    off = np.zeros(len(recs) + 1, np.uint64)
+    if recs:
+        off[1:] = np.cumsum([len(r) for r in recs], dtype=np.uint64)
+    seq = np.frombuffer(b"".join(recs) + b"\0" * 32, np.uint8).copy()
+    return seq, off, np.asarray(r2g, np.uint32)
+
+
+def pack_sketches(sketches):
+    off = np.zeros(len(sketches) + 1, np.uint64)
+    off[1:] = np.cumsum([len(s) for s in sketches], dtype=np.uint64)
+    parts = [np.asarray(s, np.uint64) for s in sketches] + [np.zeros(1, np.uint64)]
+    return np.ascontiguousarray(np.concatenate(parts)), off
+
+
+class Context:
+    """One tc_ctx (one GPU).  Mirrors how the reference's callers use Sketch::MinHash and
+    compute_minhash_mst / MinHashGreedyClusterWithInvertedIndex (see include/tclust.h)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _chk(lib().tc_ctx_create(device, C.byref(self._h)))
+        self.n = 0
+        self.sizes = None
+
+    def close(self):
+        if self._h:
+            lib().tc_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(lib().tc_kernel_launches(self._h))
+
+    @property
+    def stream(self):
+        return int(lib().tc_stream(self._h) or 0)
+
+    # ---- HP-1 ----
+    def sketch_minhash(self, genomes, k=21, s=1000, seed=42):
+        """genomes: list of lists of records (bytes).  s: int or per-genome sequence.
+        Returns list of sorted np.uint64 arrays (Sketch::MinHash::storeMinHashes per genome)."""
+        seq, off, r2g = pack_records(genomes)
+        ng = len(genomes)
+        ss = np.full(ng, s, np.uint32) if np.isscalar(s) else np.asarray(s, np.uint32)
+        stride = int(ss.max()) if ng else 1
+        out = np.zeros((ng, stride), np.uint64)
+        out_n = np.zeros(ng, np.uint32)
+        _chk(lib().tc_sketch_minhash(self._h, seq.ctypes.data, _p(off, C.c_uint64), _p(r2g, C.c_uint32),
+                                     len(off) - 1, ng, k, _p(ss, C.c_uint32), seed,
+                                     out.ctypes.data, stride, out_n.ctypes.data))
+        return [out[g, :out_n[g]].copy() for g in range(ng)]
+
+    def sketch_kssd(self, genomes, kmer_size, drlevel, shuffled_dim, max_hashes=None):
+        seq, off, r2g = pack_records(genomes)
+        ng = len(genomes)
+        if max_hashes is None:
+            longest = max((sum(len(r) for r in g) for g in genomes), default=0)
+            max_hashes = max(1024, longest // 64)
+        out = np.zeros((ng, max_hashes), np.uint64)
+        out_n = np.zeros(ng, np.uint32)
+        sd = np.ascontiguousarray(shuffled_dim, np.int32)
+        _chk(lib().tc_sketch_kssd(self._h, seq.ctypes.data, _p(off, C.c_uint64), _p(r2g, C.c_uint32),
+                                  len(off) - 1, ng, kmer_size, drlevel, _p(sd, C.c_int32),
+                                  out.ctypes.data, max_hashes, out_n.ctypes.data))
+        return [out[g, :out_n[g]].copy() for g in range(ng)]
+
+    # ---- HP-2 ----
+    def upload(self, sketches=None, hashes=None, off=None):
+        if sketches is not None:
+            hashes, off = pack_sketches(sketches)
+        hashes = np.ascontiguousarray(hashes, np.uint64)
+        off = np.ascontiguousarray(off, np.uint64)
+        self.n = len(off) - 1
+        self.sizes = np.diff(off).astype(np.int64)
+        _chk(lib().tc_sketches_upload(self._h, hashes.ctypes.data, _p(off, C.c_uint64), self.n))
+
+    def pair_common(self, i0, i1, j0, j1, impl=0):
+        out = np.zeros((i1 - i0, j1 - j0), np.uint32)
+        _chk(lib().tc_pair_common(self._h, i0, i1, j0, j1, impl, _p(out, C.c_uint32)))
+        return out
+
+    def allpairs_pass(self, radio, part=0, nparts=1):
+        npairs, nedges = C.c_uint64(0), C.c_uint64(0)
+        _chk(lib().tc_allpairs_pass(self._h, radio, part, nparts, C.byref(npairs), C.byref(nedges)))
+        return int(npairs.value), int(nedges.value)
+
+    def edges(self):
+        n = C.c_uint64(0)
+        _chk(lib().tc_edges_download(self._h, None, 0, C.byref(n)))
+        out = np.zeros(int(n.value), PAIR_DTYPE)
+        if n.value:
+            _chk(lib().tc_edges_download(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def mst(self, k, threshold, containment=False):
+        out = np.zeros(max(self.n, 1), EDGE_DTYPE)
+        m = C.c_uint64(0)
+        _chk(lib().tc_mst(self._h, k, int(containment), threshold, out.ctypes.data, C.byref(m)))
+        return out[:int(m.value)].copy()
+
+    def greedy_scan(self, q0, q1, rep_ids):
+        reps = np.ascontiguousarray(rep_ids, np.uint32)
+        common = np.zeros((q1 - q0, len(reps)), np.uint32)
+        first = np.zeros((q1 - q0, len(reps)), np.uint32)
+        _chk(lib().tc_greedy_scan(self._h, q0, q1, _p(reps, C.c_uint32), len(reps),
+                                  _p(common, C.c_uint32), _p(first, C.c_uint32)))
+        return common, first
+
+    def greedy_cluster(self, k, threshold, containment=False):
+        rep = np.zeros(max(self.n, 1), np.int32)
+        nc = C.c_uint32(0)
+        _chk(lib().tc_greedy_cluster(self._h, k, int(containment), threshold, _p(rep, C.c_int32), C.byref(nc)))
+        return int(nc.value), rep[:self.n].copy()
+
+
+def mash_dist(common, size0, size1, k):
+    return float(lib().tc_mash_dist(common, size0, size1, k))
+
+
+def aaf_dist(common, size0, size1, k):
+    return float(lib().tc_aaf_dist(common, size0, size1, k))
+
+
+def radio(threshold, k):
+    return int(lib().tc_radio(threshold, k))

@@ -1,0 +1,67 @@
+// tc_common.cuh -- context object and helpers shared by the kernels of libtclust_cuda.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/tclust.h"
+
+void tc_set_error(const char *fmt, ...);
+
+#define TC_CUDA(call)                                                                  \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            tc_set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return 1;                                                                  \
+        }                                                                              \
+    } while (0)
+
+#define TC_CHECK(cond, ...)                                                            \
+    do {                                                                               \
+        if (!(cond)) { tc_set_error(__VA_ARGS__); return 1; }                          \
+    } while (0)
+
+constexpr uint32_t TC_GROUP = 32;            // sketches per interleaved group (= warp width)
+constexpr uint32_t TC_SENT_A = 0xFFFFFFFFu;  // end-of-window sentinel, row streams
+constexpr uint32_t TC_SENT_B = 0xFFFFFFFEu;  // end-of-window sentinel, column streams
+constexpr uint32_t TC_RANK_MAX = 0xFFFFFFFDu;
+
+struct tc_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+
+    // resident sketches (HP-2)
+    uint32_t n = 0;               // number of sketches
+    uint64_t total = 0;           // total hashes
+    uint64_t *d_hashes = nullptr; // original u64 hashes, ragged row-major (validation kernel, greedy first-hit)
+    uint64_t *d_off = nullptr;    // n+1 offsets
+    uint32_t *d_size = nullptr;   // n sizes
+    uint32_t *d_ranks = nullptr;  // order-preserving dense u32 ranks of the hashes, same layout as d_hashes
+    uint32_t ngroups = 0;
+    uint32_t *d_gt = nullptr;     // group-interleaved ranks: [group][row][lane]
+    uint64_t *d_goff = nullptr;   // ngroups+1 element offsets into d_gt
+    std::vector<uint64_t> h_off;
+    std::vector<uint32_t> h_size;
+
+    // candidate edges (semantic-A graph) produced by the dense pass
+    tc_pair *d_edges = nullptr;
+    uint64_t edge_cap = 0;
+    unsigned long long *d_edge_count = nullptr;  // [0] = count, [1] = overflow flag, [2] = tile counter
+    uint64_t n_edges = 0;
+    int32_t *d_comp = nullptr;
+
+    // scratch
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+int tc_scratch(tc_ctx *ctx, size_t bytes, void **out);
+
+// tile-kernel entry points (k3_tile.cu)
+int tc_launch_tiles_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
+int tc_launch_tiles_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts);
+int tc_launch_pair_common_ref(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);

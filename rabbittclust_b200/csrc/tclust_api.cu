@@ -1,0 +1,487 @@
+// tclust_api.cu -- C ABI (include/tclust.h): context, sketch residency (rank transform +
+// group interleave), validation entry points, dense pass driver, Boruvka MST driver.
+#include "tc_common.cuh"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+static thread_local std::string g_err;
+void tc_set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+extern "C" const char *tc_last_error(void) { return g_err.c_str(); }
+extern "C" int tc_version(void) { return TC_VERSION; }
+
+int tc_scratch(tc_ctx *ctx, size_t bytes, void **out)
+{
+    if (bytes > ctx->scratch_bytes) {
+        if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+        ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+        TC_CUDA(cudaMalloc(&ctx->d_scratch, bytes));
+        ctx->scratch_bytes = bytes;
+    }
+    *out = ctx->d_scratch;
+    return 0;
+}
+
+extern "C" int tc_ctx_create(int device, tc_ctx **out)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        tc_set_error("tc_ctx_create: no CUDA device (%s); libtclust_cuda has no CPU fallback",
+                     cudaGetErrorString(e));
+        return 1;
+    }
+    TC_CHECK(device >= 0 && device < ndev, "tc_ctx_create: device %d out of range (%d devices)", device, ndev);
+    TC_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TC_CUDA(cudaGetDeviceProperties(&prop, device));
+    TC_CHECK(prop.major >= 10, "tc_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+             device, prop.major, prop.minor);
+    tc_ctx *ctx = new tc_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    TC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    TC_CUDA(cudaMalloc(&ctx->d_edge_count, 4 * sizeof(unsigned long long)));
+    TC_CUDA(cudaMemset(ctx->d_edge_count, 0, 4 * sizeof(unsigned long long)));
+    *out = ctx;
+    return 0;
+}
+
+static void free_sketches(tc_ctx *ctx)
+{
+    cudaFree(ctx->d_hashes); cudaFree(ctx->d_off); cudaFree(ctx->d_size); cudaFree(ctx->d_ranks);
+    cudaFree(ctx->d_gt); cudaFree(ctx->d_goff); cudaFree(ctx->d_edges); cudaFree(ctx->d_comp);
+    ctx->d_hashes = nullptr; ctx->d_off = nullptr; ctx->d_size = nullptr; ctx->d_ranks = nullptr;
+    ctx->d_gt = nullptr; ctx->d_goff = nullptr; ctx->d_edges = nullptr; ctx->d_comp = nullptr;
+    ctx->edge_cap = 0; ctx->n_edges = 0; ctx->n = 0; ctx->total = 0; ctx->ngroups = 0;
+}
+
+extern "C" void tc_ctx_destroy(tc_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_sketches(ctx);
+    cudaFree(ctx->d_edge_count);
+    cudaFree(ctx->d_scratch);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" uint64_t tc_kernel_launches(const tc_ctx *ctx) { return ctx->launches; }
+extern "C" void *tc_stream(const tc_ctx *ctx) { return (void *)ctx->stream; }
+
+// ------------------------------------------------------------------ rank transform kernels
+__global__ void iota_kernel(uint32_t *p, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+__global__ void head_flag_kernel(const uint64_t *keys, uint32_t *flag, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+__global__ void scatter_rank_kernel(const uint32_t *scan, const uint32_t *perm, uint32_t *ranks, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ranks[perm[i]] = scan[i] - 1u;  // inclusive scan of head flags, 0-based dense rank
+}
+__global__ void sizes_kernel(const unsigned long long *off, uint32_t *size, uint32_t n)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) size[i] = (uint32_t)(off[i + 1] - off[i]);
+}
+// gt[goff[g] + row*32 + lane] = rank `row` of sketch g*32+lane (TC_SENT_A padding)
+__global__ void interleave_kernel(const uint32_t *ranks, const unsigned long long *off, const unsigned long long *goff,
+                                  uint32_t n, uint32_t ngroups, uint32_t *gt)
+{
+    const uint32_t g = blockIdx.y;
+    const unsigned long long rows = (goff[g + 1] - goff[g]) / TC_GROUP;
+    const unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * TC_GROUP) return;
+    const uint32_t lane = (uint32_t)(e & 31), row = (uint32_t)(e >> 5);
+    const uint32_t sk = g * TC_GROUP + lane;
+    uint32_t v = TC_SENT_A;
+    if (sk < n) {
+        const unsigned long long o = off[sk], len = off[sk + 1] - o;
+        if (row < len) v = ranks[o + row];
+    }
+    gt[goff[g] + e] = v;
+}
+
+static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_device, const uint64_t *off, uint32_t n)
+{
+    TC_CUDA(cudaSetDevice(ctx->device));
+    free_sketches(ctx);
+    TC_CHECK(n > 0, "tc_sketches_upload: n == 0");
+    const uint64_t total = off[n];
+    TC_CHECK(total < 0xFFFFFFF0ull, "tc_sketches_upload: %llu hashes exceed the u32 rank space",
+             (unsigned long long)total);
+    ctx->n = n; ctx->total = total;
+    ctx->h_off.assign(off, off + n + 1);
+    ctx->h_size.resize(n);
+    uint32_t max_size = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        TC_CHECK(off[i + 1] >= off[i], "tc_sketches_upload: offsets not monotone at %u", i);
+        ctx->h_size[i] = (uint32_t)(off[i + 1] - off[i]);
+        max_size = std::max(max_size, ctx->h_size[i]);
+    }
+    cudaStream_t st = ctx->stream;
+    const uint64_t tot1 = std::max<uint64_t>(total, 1);
+    TC_CUDA(cudaMalloc(&ctx->d_hashes, tot1 * 8));
+    TC_CUDA(cudaMalloc(&ctx->d_off, (size_t)(n + 1) * 8));
+    TC_CUDA(cudaMalloc(&ctx->d_size, (size_t)n * 4));
+    TC_CUDA(cudaMalloc(&ctx->d_ranks, tot1 * 4));
+    TC_CUDA(cudaMemcpyAsync(ctx->d_hashes, hashes, total * 8,
+                            hashes_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    TC_CUDA(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    sizes_kernel<<<nblk(n, 256), 256, 0, st>>>(reinterpret_cast<unsigned long long *>(ctx->d_off), ctx->d_size, n);
+    ctx->launches++;
+
+    // ---- order-preserving dense rank transform: u64 hash -> u32 rank (equal hash <=> equal rank)
+    if (total > 0) {
+        uint64_t *k_in = nullptr, *k_out = nullptr;
+        uint32_t *v_in = nullptr, *v_out = nullptr;
+        TC_CUDA(cudaMalloc(&k_in, total * 8)); TC_CUDA(cudaMalloc(&k_out, total * 8));
+        TC_CUDA(cudaMalloc(&v_in, total * 4)); TC_CUDA(cudaMalloc(&v_out, total * 4));
+        TC_CUDA(cudaMemcpyAsync(k_in, ctx->d_hashes, total * 8, cudaMemcpyDeviceToDevice, st));
+        iota_kernel<<<nblk(total, 256), 256, 0, st>>>(v_in, total);
+        cub::DoubleBuffer<uint64_t> kb(k_in, k_out);
+        cub::DoubleBuffer<uint32_t> vb(v_in, v_out);
+        size_t tmp_bytes = 0;
+        TC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)total, 0, 64, st));
+        void *tmp = nullptr;
+        TC_CUDA(cudaMalloc(&tmp, tmp_bytes));
+        TC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kb, vb, (int)total, 0, 64, st));
+        uint32_t *flag = vb.Alternate();  // reuse the spare value buffer
+        head_flag_kernel<<<nblk(total, 256), 256, 0, st>>>(kb.Current(), flag, total);
+        size_t tmp2 = 0;
+        TC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp2, flag, flag, (int)total, st));
+        if (tmp2 > tmp_bytes) { cudaFree(tmp); TC_CUDA(cudaMalloc(&tmp, tmp2)); tmp_bytes = tmp2; }
+        TC_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp2, flag, flag, (int)total, st));
+        scatter_rank_kernel<<<nblk(total, 256), 256, 0, st>>>(flag, vb.Current(), ctx->d_ranks, total);
+        ctx->launches += 12;  // iota, sort passes (cub), flags, scan, scatter (approximate; cub internals)
+        TC_CUDA(cudaStreamSynchronize(st));
+        cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out); cudaFree(tmp);
+    }
+
+    // ---- group-interleaved layout
+    ctx->ngroups = (n + TC_GROUP - 1) / TC_GROUP;
+    std::vector<uint64_t> goff(ctx->ngroups + 1, 0);
+    uint64_t max_rows = 0;
+    for (uint32_t g = 0; g < ctx->ngroups; g++) {
+        uint32_t rows = 0;
+        for (uint32_t l = 0; l < TC_GROUP && g * TC_GROUP + l < n; l++) rows = std::max(rows, ctx->h_size[g * TC_GROUP + l]);
+        goff[g + 1] = goff[g] + (uint64_t)rows * TC_GROUP;
+        max_rows = std::max<uint64_t>(max_rows, rows);
+    }
+    TC_CUDA(cudaMalloc(&ctx->d_goff, (size_t)(ctx->ngroups + 1) * 8));
+    TC_CUDA(cudaMemcpyAsync(ctx->d_goff, goff.data(), (size_t)(ctx->ngroups + 1) * 8, cudaMemcpyHostToDevice, st));
+    TC_CUDA(cudaMalloc(&ctx->d_gt, std::max<uint64_t>(goff[ctx->ngroups], 1) * 4));
+    if (max_rows > 0) {
+        dim3 grid(nblk(max_rows * TC_GROUP, 256), ctx->ngroups);
+        interleave_kernel<<<grid, 256, 0, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
+                                                reinterpret_cast<unsigned long long *>(ctx->d_goff), n, ctx->ngroups,
+                                                ctx->d_gt);
+        ctx->launches++;
+    }
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int tc_sketches_upload(tc_ctx *ctx, const uint64_t *hashes, const uint64_t *off, uint32_t n)
+{
+    return upload_common(ctx, hashes, false, off, n);
+}
+extern "C" int tc_sketches_upload_dev(tc_ctx *ctx, const uint64_t *hashes_dev, const uint64_t *off, uint32_t n)
+{
+    return upload_common(ctx, hashes_dev, true, off, n);
+}
+
+extern "C" int tc_pair_common(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, int impl,
+                              uint32_t *out)
+{
+    TC_CUDA(cudaSetDevice(ctx->device));
+    TC_CHECK(ctx->n > 0, "tc_pair_common: no sketches uploaded");
+    TC_CHECK(i0 <= i1 && i1 <= ctx->n && j0 <= j1 && j1 <= ctx->n, "tc_pair_common: range out of bounds");
+    const size_t cells = (size_t)(i1 - i0) * (j1 - j0);
+    if (!cells) return 0;
+    uint32_t *d_out = nullptr;
+    TC_CUDA(cudaMalloc(&d_out, cells * 4));
+    int rc = impl == 0 ? tc_launch_tiles_matrix(ctx, i0, i1, j0, j1, d_out)
+                       : tc_launch_pair_common_ref(ctx, i0, i1, j0, j1, d_out);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { tc_set_error("tc_pair_common: %s", cudaGetErrorString(e)); rc = 1; }
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------ dense pass
+static int ensure_edges(tc_ctx *ctx)
+{
+    if (ctx->d_edges) return 0;
+    uint64_t cap = (uint64_t)ctx->n * (ctx->n - 1) / 2;
+    uint64_t lim = 1ull << 28;  // 268M edges = 3.2 GB
+    if (const char *s = getenv("TCLUST_EDGE_CAP")) lim = strtoull(s, nullptr, 10);
+    cap = std::max<uint64_t>(std::min(cap, lim), 1);
+    TC_CUDA(cudaMalloc(&ctx->d_edges, cap * sizeof(tc_pair)));
+    ctx->edge_cap = cap;
+    TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    ctx->n_edges = 0;
+    return 0;
+}
+
+extern "C" int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint64_t *n_pairs,
+                                uint64_t *n_edges)
+{
+    TC_CUDA(cudaSetDevice(ctx->device));
+    TC_CHECK(ctx->n > 0, "tc_allpairs_pass: no sketches uploaded");
+    if (nparts == 0) nparts = 1;
+    TC_CHECK(part < nparts, "tc_allpairs_pass: part %u >= nparts %u", part, nparts);
+    if (ensure_edges(ctx)) return 1;
+    // a pass restarts the candidate list
+    TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (tc_launch_tiles_edges(ctx, radio, part, nparts)) return 1;
+    unsigned long long cnt[2];
+    TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    TC_CHECK(cnt[1] == 0 && cnt[0] <= ctx->edge_cap,
+             "tc_allpairs_pass: %llu candidate edges exceed the device edge buffer (%llu); raise TCLUST_EDGE_CAP",
+             cnt[0], (unsigned long long)ctx->edge_cap);
+    ctx->n_edges = cnt[0];
+    if (n_edges) *n_edges = cnt[0];
+    if (n_pairs) {
+        // pairs j<i inside the tiles owned by this part
+        const uint64_t G = ctx->ngroups;
+        if (nparts == 1) *n_pairs = (uint64_t)ctx->n * (ctx->n - 1) / 2;
+        else {
+            uint64_t p = 0, t = 0;
+            for (uint64_t r = 0; r < G; r++)
+                for (uint64_t c = 0; c <= r; c++, t++) {
+                    if (t % nparts != part) continue;
+                    const uint64_t nr = std::min<uint64_t>(TC_GROUP, ctx->n - r * TC_GROUP);
+                    const uint64_t nc = std::min<uint64_t>(TC_GROUP, ctx->n - c * TC_GROUP);
+                    p += r == c ? nr * (nr - 1) / 2 : nr * nc;
+                }
+            *n_pairs = p;
+        }
+    }
+    return 0;
+}
+
+extern "C" int tc_edges_download(tc_ctx *ctx, tc_pair *out, uint64_t cap, uint64_t *n)
+{
+    TC_CUDA(cudaSetDevice(ctx->device));
+    if (n) *n = ctx->n_edges;
+    const uint64_t m = std::min(cap, ctx->n_edges);
+    if (m) {
+        TC_CUDA(cudaMemcpyAsync(out, ctx->d_edges, m * sizeof(tc_pair), cudaMemcpyDeviceToHost, ctx->stream));
+        TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------- Boruvka
+// similarity key: ~bits(J); J computed exactly as the reference's host code does
+// (MST.cpp:1489-1492: (double)common / (size0+size1-common); :1505-1507: / min(size0,size1)).
+__device__ __forceinline__ unsigned long long edge_key(const tc_pair &e, const uint32_t *size, int containment)
+{
+    const uint32_t s0 = size[e.i], s1 = size[e.j];
+    const uint32_t denom = containment ? min(s0, s1) : (s0 + s1 - e.common);
+    const double J = denom == 0 ? 0.0 : __ddiv_rn((double)e.common, (double)denom);
+    return ~(unsigned long long)__double_as_longlong(J);
+}
+
+__global__ void boruvka_phase1_kernel(const tc_pair *edges, unsigned long long n_edges, const uint32_t *size,
+                                      const int32_t *comp, int containment, unsigned long long *best_key)
+{
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges;
+         e += (unsigned long long)gridDim.x * blockDim.x) {
+        const tc_pair p = edges[e];
+        const int32_t ci = comp[p.i], cj = comp[p.j];
+        if (ci == cj) continue;
+        const unsigned long long k = edge_key(p, size, containment);
+        atomicMin(&best_key[ci], k);
+        atomicMin(&best_key[cj], k);
+    }
+}
+__global__ void boruvka_phase2_kernel(const tc_pair *edges, unsigned long long n_edges, const uint32_t *size,
+                                      const int32_t *comp, int containment, const unsigned long long *best_key,
+                                      unsigned long long *best_edge)
+{
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges;
+         e += (unsigned long long)gridDim.x * blockDim.x) {
+        const tc_pair p = edges[e];
+        const int32_t ci = comp[p.i], cj = comp[p.j];
+        if (ci == cj) continue;
+        const unsigned long long k = edge_key(p, size, containment);
+        const unsigned long long id = ((unsigned long long)p.i << 32) | p.j;
+        if (k == best_key[ci]) atomicMin(&best_edge[ci], id);
+        if (k == best_key[cj]) atomicMin(&best_edge[cj], id);
+    }
+}
+
+extern "C" int tc_boruvka_upload_comp(tc_ctx *ctx, const int32_t *comp, uint32_t n)
+{
+    TC_CUDA(cudaSetDevice(ctx->device));
+    TC_CHECK(n == ctx->n, "tc_boruvka_upload_comp: n mismatch");
+    if (!ctx->d_comp) TC_CUDA(cudaMalloc(&ctx->d_comp, (size_t)n * 4));
+    TC_CUDA(cudaMemcpyAsync(ctx->d_comp, comp, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+static int boruvka_grid(tc_ctx *ctx)
+{
+    uint64_t b = (ctx->n_edges + 255) / 256;
+    uint64_t cap = (uint64_t)ctx->num_sms * 8;
+    return (int)std::max<uint64_t>(1, std::min(b, cap));
+}
+
+extern "C" int tc_boruvka_phase1(tc_ctx *ctx, int containment, uint64_t *best_key_dev)
+{
+    TC_CUDA(cudaSetDevice(ctx->device));
+    TC_CHECK(ctx->d_comp, "tc_boruvka_phase1: component labels not uploaded");
+    TC_CUDA(cudaMemsetAsync(best_key_dev, 0xFF, (size_t)ctx->n * 8, ctx->stream));
+    if (ctx->n_edges) {
+        boruvka_phase1_kernel<<<boruvka_grid(ctx), 256, 0, ctx->stream>>>(
+            ctx->d_edges, ctx->n_edges, ctx->d_size, ctx->d_comp, containment,
+            reinterpret_cast<unsigned long long *>(best_key_dev));
+        ctx->launches++;
+    }
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int tc_boruvka_phase2(tc_ctx *ctx, int containment, const uint64_t *best_key_dev, uint64_t *best_edge_dev)
+{
+    TC_CUDA(cudaSetDevice(ctx->device));
+    TC_CHECK(ctx->d_comp, "tc_boruvka_phase2: component labels not uploaded");
+    TC_CUDA(cudaMemsetAsync(best_edge_dev, 0xFF, (size_t)ctx->n * 8, ctx->stream));
+    if (ctx->n_edges) {
+        boruvka_phase2_kernel<<<boruvka_grid(ctx), 256, 0, ctx->stream>>>(
+            ctx->d_edges, ctx->n_edges, ctx->d_size, ctx->d_comp, containment,
+            reinterpret_cast<const unsigned long long *>(best_key_dev),
+            reinterpret_cast<unsigned long long *>(best_edge_dev));
+        ctx->launches++;
+    }
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ host distance helpers
+extern "C" int tc_radio(double threshold, int kmer_size)
+{
+    return (int)(2.0 * std::exp(threshold * (kmer_size - 1)) - 1.0);  // calr(threshold, k-1) truncated
+}
+extern "C" double tc_mash_dist(int common, int size0, int size1, int kmer_size)
+{
+    const double inv_kmer_size = 1.0 / kmer_size;
+    int denom = size0 + size1 - common;
+    double jaccard = denom == 0 ? 0.0 : (double)common / denom;
+    if (jaccard == 1.0) return 0.0;
+    if (jaccard == 0.0) return 1.0;
+    double ratio = (2.0 * jaccard) / (1.0 + jaccard);
+    return -inv_kmer_size * std::log(ratio);
+}
+extern "C" double tc_aaf_dist(int common, int size0, int size1, int kmer_size)
+{
+    const double inv_kmer_size = 1.0 / kmer_size;
+    int denom = size0 < size1 ? size0 : size1;
+    double containment = denom == 0 ? 0.0 : (double)common / denom;
+    if (containment == 1.0) return 0.0;
+    if (containment == 0.0) return 1.0;
+    return -inv_kmer_size * std::log(containment);
+}
+extern "C" double tc_dist_from_key(uint64_t key, int containment, int kmer_size)
+{
+    const uint64_t bits = ~key;
+    double J;
+    memcpy(&J, &bits, 8);
+    const double inv_kmer_size = 1.0 / kmer_size;
+    if (J == 1.0) return 0.0;
+    if (J == 0.0) return 1.0;
+    if (containment) return -inv_kmer_size * std::log(J);
+    double ratio = (2.0 * J) / (1.0 + J);
+    return -inv_kmer_size * std::log(ratio);
+}
+
+// ------------------------------------------------------------------- single-GPU MST driver
+namespace {
+struct HostUF {
+    std::vector<int32_t> p;
+    explicit HostUF(uint32_t n) : p(n) { std::iota(p.begin(), p.end(), 0); }
+    int32_t find(int32_t x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; }
+};
+}  // namespace
+
+extern "C" int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double threshold, tc_edge *out, uint64_t *n_out)
+{
+    TC_CUDA(cudaSetDevice(ctx->device));
+    TC_CHECK(ctx->n > 0, "tc_mst: no sketches uploaded");
+    const uint32_t n = ctx->n;
+    const int radio = tc_radio(threshold, kmer_size);
+    if (tc_allpairs_pass(ctx, radio, 0, 1, nullptr, nullptr)) return 1;
+    uint64_t *d_key = nullptr, *d_edge = nullptr;
+    TC_CUDA(cudaMalloc(&d_key, (size_t)n * 8));
+    TC_CUDA(cudaMalloc(&d_edge, (size_t)n * 8));
+    std::vector<uint64_t> key(n), edge(n);
+    std::vector<int32_t> comp(n);
+    HostUF uf(n);
+    std::vector<tc_edge> mst;
+    mst.reserve(n);
+    int rc = 0;
+    for (int round = 0; round < 64 && !rc; round++) {
+        for (uint32_t v = 0; v < n; v++) comp[v] = uf.find((int32_t)v);
+        if ((rc = tc_boruvka_upload_comp(ctx, comp.data(), n))) break;
+        if ((rc = tc_boruvka_phase1(ctx, containment, d_key))) break;
+        if ((rc = tc_boruvka_phase2(ctx, containment, d_key, d_edge))) break;
+        if (cudaMemcpy(key.data(), d_key, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(edge.data(), d_edge, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            tc_set_error("tc_mst: device-to-host copy failed");
+            rc = 1;
+            break;
+        }
+        uint64_t merged = 0;
+        for (uint32_t c = 0; c < n; c++) {
+            if (edge[c] == UINT64_MAX) continue;
+            const int32_t i = (int32_t)(edge[c] >> 32), j = (int32_t)(edge[c] & 0xffffffffu);
+            const int32_t a = uf.find(i), b = uf.find(j);
+            if (a == b) continue;
+            uf.p[a] = b;
+            mst.push_back(tc_edge{i, j, tc_dist_from_key(key[c], containment, kmer_size)});
+            merged++;
+        }
+        if (!merged) break;
+    }
+    cudaFree(d_key); cudaFree(d_edge);
+    if (rc) return rc;
+    std::sort(mst.begin(), mst.end(), [](const tc_edge &x, const tc_edge &y) {
+        if (x.dist != y.dist) return x.dist < y.dist;
+        if (x.pre != y.pre) return x.pre < y.pre;
+        return x.suf < y.suf;
+    });
+    if (out) std::copy(mst.begin(), mst.end(), out);
+    if (n_out) *n_out = mst.size();
+    return 0;
+}

@@ -1,0 +1,100 @@
+"""GPU parity of the all-pairs intersection (K3), the dense pass and the MST build against the
+CPU oracle (oracle/tclust_oracle.c, pinned to the reference)."""
+import numpy as np
+import pytest
+
+from rabbittclust_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_matrix(ctx, oracle, sketches):
+    ctx.upload(sketches)
+    n = len(sketches)
+    want = oracle.common_matrix(sketches)
+    got_ref = ctx.pair_common(0, n, 0, n, impl=1)
+    got = ctx.pair_common(0, n, 0, n, impl=0)
+    assert np.array_equal(got_ref, want), "u64 global-merge kernel differs from oracle"
+    assert np.array_equal(got, want), "tiled kernel differs from oracle"
+
+
+def test_common_fixed_size(ctx, oracle):
+    _check_matrix(ctx, oracle, synth.family_sketches(6, 17, s=1000, seed=1))
+
+
+def test_common_small_and_odd_sizes(ctx, oracle):
+    rng = np.random.default_rng(3)
+    sk = [np.unique(rng.integers(0, 5000, int(sz), dtype=np.uint64)) for sz in rng.integers(0, 300, 70)]
+    sk[5] = np.zeros(0, np.uint64)             # empty sketch
+    sk[6] = sk[7].copy()                        # identical pair
+    sk[8] = np.array([2**64 - 1, ], np.uint64)  # extreme value
+    sk[9] = np.array([0, 2**64 - 1], np.uint64)
+    _check_matrix(ctx, oracle, sk)
+
+
+def test_common_ragged_multichunk(ctx, oracle):
+    # sizes 100..6000: several value chunks per tile, very different value ranges per sketch
+    rng = np.random.default_rng(5)
+    sk = []
+    for t in range(40):
+        size = int(np.exp(rng.uniform(np.log(100), np.log(6000))))
+        hi = 2**64 - 1 if t % 3 else 2**40           # some sketches live in a tiny value range
+        sk.append(np.unique(rng.integers(0, hi, size, dtype=np.uint64)))
+    sk += synth.family_sketches(2, 6, s=3000, seed=9)
+    _check_matrix(ctx, oracle, sk)
+
+
+def test_common_subrange(ctx, oracle):
+    sk = synth.family_sketches(4, 25, s=500, seed=11)
+    ctx.upload(sk)
+    want = oracle.common_matrix(sk)
+    got = ctx.pair_common(37, 91, 3, 66, impl=0)
+    assert np.array_equal(got, want[37:91, 3:66])
+
+
+@pytest.mark.parametrize("containment", [False, True])
+def test_dense_pass_edges_and_mst(ctx, oracle, tc, containment):
+    k, thr = 21, 0.05
+    if containment:
+        sk = synth.family_sketches(8, 12, seed=21, ragged=(100, 2000))
+    else:
+        sk = synth.family_sketches(10, 13, s=1000, seed=20)
+    n = len(sk)
+    ctx.upload(sk)
+    radio = tc.radio(thr, k)
+    assert radio == oracle.lib().oc_radio(thr, k)
+    npairs, nedges = ctx.allpairs_pass(radio)
+    assert npairs == n * (n - 1) // 2
+    e = ctx.edges()
+    assert len(e) == nedges
+    want = oracle.common_matrix(sk)
+    sizes = np.array([len(s) for s in sk])
+    exp = {}
+    for i in range(n):
+        for j in range(i):
+            c = int(want[i, j])
+            mn, mx = min(sizes[i], sizes[j]), max(sizes[i], sizes[j])
+            if c >= 1 and mn > 0 and not mx > radio * mn:
+                exp[(i, j)] = c
+    got = {(int(r["i"]), int(r["j"])): int(r["common"]) for r in e}
+    assert got == exp
+    mst = ctx.mst(k, thr, containment)
+    ref = oracle.mst(sk, k, thr, containment)
+    assert len(mst) == len(ref)
+    assert np.array_equal(np.sort(mst["dist"]), np.sort(ref["dist"])), "MST weight multiset differs (bit-exact)"
+    nc_g, lab_g, _ = oracle.clusters_from_mst(mst, n, thr)
+    nc_r, lab_r, _ = oracle.clusters_from_mst(ref, n, thr)
+    assert nc_g == nc_r
+    part = lambda lab: sorted(sorted(np.nonzero(lab == c)[0].tolist()) for c in range(lab.max() + 1))
+    assert part(lab_g) == part(lab_r)
+
+
+def test_larger_block_against_u64_kernel(ctx):
+    # 1500 sketches: the tiled kernel against the independent u64 kernel on a full matrix
+    h, off = synth.family_sketches_fast(30, 50, s=1000, seed=4)
+    ctx.upload(hashes=h, off=off)
+    a = ctx.pair_common(0, 1500, 0, 1500, impl=0)
+    b = ctx.pair_common(0, 1500, 0, 1500, impl=1)
+    assert np.array_equal(a, b)
+    assert (np.diag(a) == 1000).all()
+    assert a[0, 1] >= 250 and a[0, 60] == 0
