@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 hot paths (contract: task brief, section 4).
+
+Headline (default, --workload pairs): ONE dense all-pairs pass (K3 + candidate-edge epilogue +
+Boruvka round 1) over N=100,000 pre-sketched s=1000 MinHash sketches (BASELINE.json configs[2],
+the configuration the north-star's pairs/s target is quoted on; it fits one GPU).
+    value  = pairwise sketch distances / s, sketches resident in HBM (CUDA events)
+    e2e    = same through the C ABI with HOST buffers: H2D upload + rank transform + pass + D2H edges
+--workload sketch: MinHash sketch construction, synthetic 5 Mbp genomes k=21 s=1000 (configs[1]).
+--impl reference: the reference's own CPU path (oracle/_ref/ref_harness, AVX2 build of RabbitSketch)
+on a bounded sample of the same workload, all host threads.
+
+Multi-GPU: one process per GPU (torchrun); sketches replicated, the tile space of the fixed
+N=100k problem is dealt round-robin to the ranks ("strong" scaling); per step one
+all-reduce(min) pair of the Boruvka round-1 keys over NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PAIR_BYTES = 16000.0   # algorithmic operand bytes per pair: 8*(|A|+|B|) at s=1000
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock/throttle sampling during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------- reference arm
+def ref_pairs(n_sample, threads, hashes, off, k=21, s=1000):
+    """Time the reference's MinHash::distance all-pairs (oracle/_ref/ref_harness) on n_sample sketches."""
+    import tempfile
+    from rabbittclust_b200 import sketch_io
+    from oracle import pyoracle
+    exe = pyoracle.ref_bin("ref_harness")
+    if exe is None:
+        return None
+    with tempfile.TemporaryDirectory() as d:
+        sk = [hashes[int(off[i]):int(off[i + 1])] for i in range(n_sample)]
+        sketch_io.write_minhash_folder(d, sk, ["g%06d" % i for i in range(n_sample)], k=k, sketch_size=s)
+        out = subprocess.check_output([exe, "pairs", os.path.join(d, "hash.sketch"), str(threads), str(n_sample)])
+    return json.loads(out)
+
+
+def port_pairs(n_sample, hashes, off):
+    """Scalar oracle port (full-intersection merge), single thread."""
+    from oracle import pyoracle
+    sk = [hashes[int(off[i]):int(off[i + 1])] for i in range(n_sample)]
+    t0 = time.time()
+    pyoracle.common_matrix(sk)
+    dt = time.time() - t0
+    return {"pairs": n_sample * n_sample, "seconds": dt, "pairs_per_s": n_sample * n_sample / dt, "threads": 1}
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from rabbittclust_b200 import synth
+    threads = os.cpu_count() or 1
+    if args.workload == "pairs":
+        n_sample = args.ref_sample
+        h, off = synth.family_sketches_fast(max(n_sample // 100, 1), 100, 1000, seed=7)
+        n_sample = len(off) - 1
+        vals = []
+        kind = "reference"
+        for it in range(args.warmup + args.steps):
+            r = ref_pairs(n_sample, threads, h, off)
+            if r is None:
+                r = port_pairs(min(n_sample, 600), h, off)
+                kind = "port"
+            if it >= args.warmup:
+                vals.append(r)
+        pairs = sum(v["pairs"] for v in vals)
+        secs = sum(v["seconds"] for v in vals)
+        value = pairs / secs
+        line = {"impl": "reference", "metric": "pairwise sketch distances/sec", "value": value, "unit": "pairs/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * secs / len(vals), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": "clust-mst all-pairs on 100,000 pre-sketched s=1000 k=21 sketches "
+                                       "(BASELINE.json configs[2])",
+                           "note": "CPU arm: MinHash::distance (AVX2 build) over a bounded sample"},
+                "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": vals[0].get("threads", 1), "kind": kind,
+                                 "sample": "%d sketches of the same synthetic model = %d pairs per step" %
+                                           (n_sample, vals[0]["pairs"])},
+                "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    else:
+        from oracle import pyoracle
+        exe = pyoracle.ref_bin("ref_harness")
+        ng, L = max(threads, 8), args.genome_len
+        vals, kind = [], "reference"
+        for it in range(args.warmup + args.steps):
+            if exe:
+                r = json.loads(subprocess.check_output([exe, "update", "21", "1000", str(threads), str(L), str(ng)]))
+            else:
+                kind = "port"
+                rng = np.random.default_rng(1)
+                g = synth.random_genome(L, rng)
+                t0 = time.time(); pyoracle.minhash_sketch([g], 21, 1000); dt = time.time() - t0
+                r = {"genomes": 1, "seconds": dt, "threads": 1}
+            if it >= args.warmup:
+                vals.append(r)
+        secs = sum(v["seconds"] for v in vals)
+        value = sum(v["genomes"] for v in vals) / secs
+        line = {"impl": "reference", "metric": "genomes sketched/sec", "value": value, "unit": "genomes/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * secs / len(vals), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": "sketch-only synthetic %d bp genomes k=21 s=1000 (BASELINE.json configs[1])" % L},
+                "cpu_baseline": {"value": value, "unit": "genomes/s", "cores": vals[0].get("threads", 1), "kind": kind,
+                                 "sample": "%d genomes of %d bp per step" % (vals[0]["genomes"], L)},
+                "e2e": {"value": value, "unit": "genomes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_pairs(args):
+    import torch
+    import rabbittclust_b200 as T
+    from rabbittclust_b200 import synth
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.n
+    per_fam = 100
+    h, off = synth.family_sketches_fast(max(n // per_fam, 1), per_fam, 1000, seed=7)
+    n = len(off) - 1
+    k, thr = 21, 0.05
+    radio = T.radio(thr, k)
+    ctx = T.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    h_pin = torch.from_numpy(h).pin_memory()
+    hp = h_pin.numpy()
+    best_key = torch.empty(n, dtype=torch.int64, device="cuda")
+    best_edge = torch.empty(n, dtype=torch.int64, device="cuda")
+    comp = np.arange(n, dtype=np.int32)
+    L = T.lib()
+    import ctypes as C
+
+    def device_step():
+        npairs, nedges = ctx.allpairs_pass(radio, rank, world)
+        T._chk(L.tc_boruvka_upload_comp(ctx._h, comp.ctypes.data_as(C.POINTER(C.c_int32)), n))
+        T._chk(L.tc_boruvka_phase1(ctx._h, 0, best_key.data_ptr()))
+        if dist is not None:
+            # keys are u64 bit patterns < 2^63 is NOT guaranteed: reduce as unsigned via the sign flip
+            best_key.bitwise_xor_(-2**63); dist.all_reduce(best_key, op=dist.ReduceOp.MIN); best_key.bitwise_xor_(-2**63)
+        T._chk(L.tc_boruvka_phase2(ctx._h, 0, best_key.data_ptr(), best_edge.data_ptr()))
+        if dist is not None:
+            best_edge.bitwise_xor_(-2**63); dist.all_reduce(best_edge, op=dist.ReduceOp.MIN); best_edge.bitwise_xor_(-2**63)
+        return npairs, nedges
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx.upload(hashes=hp, off=off)
+    for _ in range(args.warmup):
+        device_step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k3_ms, pairs_mine, nedges = 0.0, 0, 0
+    with torch.cuda.stream(stream):
+        ev0.record()
+    t_wall0 = time.time()
+    for _ in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            a.record()
+        npairs, nedges = ctx.allpairs_pass(radio, rank, world)
+        with torch.cuda.stream(stream):
+            b.record()
+        b.synchronize()
+        k3_ms += a.elapsed_time(b)
+        pairs_mine += npairs
+        T._chk(L.tc_boruvka_upload_comp(ctx._h, comp.ctypes.data_as(C.POINTER(C.c_int32)), n))
+        T._chk(L.tc_boruvka_phase1(ctx._h, 0, best_key.data_ptr()))
+        if dist is not None:
+            best_key.bitwise_xor_(-2**63); dist.all_reduce(best_key, op=dist.ReduceOp.MIN); best_key.bitwise_xor_(-2**63)
+        T._chk(L.tc_boruvka_phase2(ctx._h, 0, best_key.data_ptr(), best_edge.data_ptr()))
+        if dist is not None:
+            best_edge.bitwise_xor_(-2**63); dist.all_reduce(best_edge, op=dist.ReduceOp.MIN); best_edge.bitwise_xor_(-2**63)
+    with torch.cuda.stream(stream):
+        ev1.record()
+    sync_all()
+    ev1.synchronize()
+    dev_ms = ev0.elapsed_time(ev1)
+    wall_ms = (time.time() - t_wall0) * 1e3
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host buffers -> upload (H2D + rank transform) -> pass -> edges D2H
+    e2e_steps = max(1, min(args.steps, 3))
+    sync_all()
+    t0 = time.time()
+    d2h = 0
+    for _ in range(e2e_steps):
+        ctx.upload(hashes=hp, off=off)
+        ctx.allpairs_pass(radio, rank, world)
+        e = ctx.edges()
+        d2h = e.nbytes
+    sync_all()
+    e2e_ms = (time.time() - t0) * 1e3 / e2e_steps
+
+    t = torch.tensor([dev_ms, e2e_ms, k3_ms, float(pairs_mine), float(launches)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms = float(tmax[0]), float(tmax[1])
+        total_pairs, launches = float(tsum[3]), int(tsum[4])
+    else:
+        total_pairs = float(pairs_mine)
+    if rank == 0:
+        peak, how = measured_peak()
+        pairs_per_step_all = n * (n - 1) / 2
+        value = total_pairs / (dev_ms / 1e3)
+        k3_avg_s = k3_ms / 1e3 / args.steps
+        achieved = (pairs_mine / args.steps) * PAIR_BYTES / k3_avg_s / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "k3_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "pairwise sketch distances/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 ranks of u64 hashes",
+            "data": "synthetic",
+            "config": {"workload": "clust-mst dense all-pairs pass on %d pre-sketched s=1000 k=21 sketches, "
+                                   "1000-per-family model (BASELINE.json configs[2])" % n,
+                       "n_sketches": n, "sketch_size": 1000, "pairs_per_step": pairs_per_step_all,
+                       "candidate_edges": int(nedges), "parallelism": "tile-sharded x%d, sketches replicated" % world,
+                       "l2": "input 0.4 GB of u32 ranks (+0.8 GB u64) per GPU > 126 MB L2"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": how,
+                         "kernel": "k3_tile_kernel", "kernel_ms": 1e3 * k3_avg_s,
+                         "note": "algorithmic bytes = 16000 B/pair x pairs per launch (SURVEY 8d); tiles are reused "
+                                 "from shared memory so this effective operand bandwidth exceeds HBM peak; the binding "
+                                 "unit is the shared-memory/issue pipe (DESIGN.md K3)"},
+            "e2e": {"value": (pairs_per_step_all) / (e2e_ms / 1e3), "unit": "pairs/s",
+                    "h2d_bytes_per_step": int(h.nbytes + off.nbytes) * world, "d2h_bytes_per_step": int(d2h) * world,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
+        }
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            r = ref_pairs(min(args.ref_sample, n), threads, h, off)
+            kind = "reference"
+            if r is None:
+                r, kind = port_pairs(min(600, n), h, off), "port"
+            line["cpu_baseline"] = {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r.get("threads", 1),
+                                    "kind": kind, "sample": "all pairs of the first %d sketches (%d pairs), "
+                                    "MinHash::distance AVX2 build" % (min(args.ref_sample, n), r["pairs"])}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pairs", choices=["pairs", "sketch"])
+    ap.add_argument("--n", type=int, default=100000, help="number of sketches (pairs workload)")
+    ap.add_argument("--genomes", type=int, default=2048, help="genomes per step (sketch workload)")
+    ap.add_argument("--genome-len", type=int, default=5000000)
+    ap.add_argument("--ref-sample", type=int, default=4000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.workload == "pairs":
+        return run_pairs(args)
+    from bench_sketch import run_sketch
+    return run_sketch(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,116 @@
+"""On-disk formats of the reference (the drop-in boundary b-1 of SURVEY.md), Python side.
+
+Layouts follow the reference byte for byte (native little-endian, no padding, no magic):
+  hash.sketch  src/Sketch_IO.cpp:192-206 (write), :297-349 (read)
+  info.sketch  src/Sketch_IO.cpp:96-131 (write), :477-560 (read)
+  edge.mst     src/MST_IO.cpp:200-217 (write), :47-70 (read); info.mst == info.sketch layout
+  cluster file src/MST_IO.cpp:136-179
+The C++ host (rabbittclust_b200/host/) implements the same formats for the CLI; this module serves
+the tests, bench.py and the tools.
+"""
+import os
+import struct
+
+import numpy as np
+
+EDGE_DTYPE = np.dtype([("pre", "<i4"), ("suf", "<i4"), ("dist", "<f8")])
+
+
+def write_minhash_folder(folder, sketches, names, k, sketch_size=1000, containment=False, contain_compress=1000,
+                         total_len=None, comments=None, by_file=True):
+    """Write hash.sketch + info.sketch accepted by the reference's --presketched."""
+    os.makedirs(folder, exist_ok=True)
+    n = len(sketches)
+    if total_len is None:
+        total_len = [1_000_000] * n
+    if comments is None:
+        comments = ["synthetic"] * n
+    with open(os.path.join(folder, "hash.sketch"), "wb") as fh:
+        fh.write(struct.pack("<ii?i", 0, k, bool(containment), contain_compress if containment else sketch_size))
+        for h in sketches:
+            h = np.ascontiguousarray(h, "<u8")
+            fh.write(struct.pack("<Q", len(h)))
+            fh.write(h.tobytes())
+    with open(os.path.join(folder, "info.sketch"), "wb") as fi:
+        fi.write(struct.pack("<?Q", bool(by_file), n))
+        for nm, ln, cm in zip(names, total_len, comments):
+            sn, cb = nm.encode(), cm.encode()
+            if by_file:
+                fn = (nm + ".fna").encode()
+                fi.write(struct.pack("<iiiiQ", len(fn), len(sn), len(cb), 0, int(ln)))
+                fi.write(fn + sn + cb)
+            else:
+                fi.write(struct.pack("<iiii", len(sn), len(cb), 0, int(ln)))
+                fi.write(sn + cb)
+
+
+def read_hash_sketch(path):
+    """-> dict(func_id, k, containment, param, sketches=[np.uint64...])."""
+    with open(path, "rb") as f:
+        data = f.read()
+    func_id, k, cont, param = struct.unpack_from("<ii?i", data, 0)
+    pos = struct.calcsize("<ii?i")
+    sk = []
+    while pos < len(data):
+        (m,) = struct.unpack_from("<Q", data, pos)
+        pos += 8
+        sk.append(np.frombuffer(data, "<u8", m, pos).copy())
+        pos += 8 * m
+    return {"func_id": func_id, "k": k, "containment": bool(cont), "param": param, "sketches": sk}
+
+
+def read_info_sketch(path):
+    """-> (by_file, [dict(file, name, comment, strand, length)])."""
+    with open(path, "rb") as f:
+        data = f.read()
+    by_file, n = struct.unpack_from("<?Q", data, 0)
+    pos = 9
+    out = []
+    for _ in range(n):
+        if by_file:
+            lf, ls, lc, strand, tot = struct.unpack_from("<iiiiQ", data, pos)
+            pos += 24
+            fn = data[pos:pos + lf]; pos += lf
+            sn = data[pos:pos + ls]; pos += ls
+            cm = data[pos:pos + lc]; pos += lc
+            out.append({"file": fn.decode(), "name": sn.decode(), "comment": cm.decode(), "strand": strand,
+                        "length": tot})
+        else:
+            ls, lc, strand, length = struct.unpack_from("<iiii", data, pos)
+            pos += 16
+            sn = data[pos:pos + ls]; pos += ls
+            cm = data[pos:pos + lc]; pos += lc
+            out.append({"file": "", "name": sn.decode(), "comment": cm.decode(), "strand": strand, "length": length})
+    return bool(by_file), out
+
+
+def read_edge_mst(path):
+    with open(path, "rb") as f:
+        data = f.read()
+    (n,) = struct.unpack_from("<Q", data, 0)
+    return np.frombuffer(data, EDGE_DTYPE, n, 8).copy()
+
+
+def write_edge_mst(path, edges):
+    e = np.ascontiguousarray(edges, EDGE_DTYPE)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<Q", len(e)))
+        f.write(e.tobytes())
+
+
+def parse_cluster_file(path):
+    """Cluster text (MST_IO.cpp:136-179) -> list of clusters, each a list of (global_id, name) tuples."""
+    clusters, cur = [], None
+    for line in open(path):
+        if line.startswith("#"):
+            continue
+        if line.startswith("the cluster"):
+            cur = []
+            clusters.append(cur)
+        elif line.startswith("\t") and cur is not None:
+            f = line.rstrip("\n").split("\t")
+            # list mode: '', idx, gid, len, file, name, comment ; single-file mode: '', idx, gid, len, name, comment
+            gid = int(f[2])
+            name = f[5].strip() if len(f) >= 7 else f[4].strip()
+            cur.append((gid, name))
+    return clusters

@@ -1,0 +1,47 @@
+"""The C-ABI shared library builds for sm_100a, loads without a GPU and exports every symbol that
+include/tclust.h declares; compute entry points fail loudly when no CUDA device is present."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "tclust.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree(tc):
+    assert declared_symbols() == sorted(tc.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(tc):
+    from rabbittclust_b200 import build
+    build.build()
+    L = ctypes.CDLL(tc.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(L, s), s
+    assert tc.lib().tc_version() == 100
+
+
+def test_host_distance_helpers_match_oracle(tc, oracle):
+    L = oracle.lib()
+    for (c, s0, s1, k) in [(581, 1000, 1000, 21), (1000, 1000, 1000, 21), (1, 1000, 997, 17), (350, 1000, 1000, 21),
+                           (77, 100, 9000, 19), (100, 100, 9000, 19)]:
+        assert tc.mash_dist(c, s0, s1, k) == L.oc_mash_dist_A(c, s0, s1, k)
+        assert tc.aaf_dist(c, s0, s1, k) == L.oc_aaf_dist_mst(c, s0, s1, k)
+    assert tc.mash_dist(581, 1000, 1000, 21) == 0.02585735819667742      # SURVEY.md 8c known answer
+    assert tc.radio(0.05, 21) == 4 == L.oc_radio(0.05, 21)
+    assert L.oc_greedy_common_min(0.05, 21, 1000, 1000, 0) == 350           # SURVEY.md 8a-15 known answer
+
+
+def test_no_silent_cpu_fallback(tc):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(tc.TclustError):
+        tc.Context(0)

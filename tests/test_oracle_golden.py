@@ -1,0 +1,161 @@
+"""Pin the CPU oracle (oracle/tclust_oracle.c) to the reference: golden vectors produced by the
+unmodified reference binaries (tools/make_golden.py), plus live comparisons against oracle/_ref
+when those binaries are present.  CPU only."""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from rabbittclust_b200 import fasta, sketch_io, synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def genome_records(name):
+    for d in ("genomes", "ecoli", "mst_genomes"):
+        for p in glob.glob(os.path.join(GOLD, d, name + "*.fa.gz")):
+            return [r[2] for r in fasta.read_fasta(p)]
+    raise FileNotFoundError(name)
+
+
+def partition(clusters):
+    return sorted(sorted(n for _, n in c) for c in clusters)
+
+
+def test_murmur_known_answers(oracle):
+    # MurmurHash3_x64_128 reference vectors (seed 0 empty = 0; published test values) + Mash-style k-mer
+    assert oracle.murmur_h1(b"", 0) == 0
+    assert oracle.murmur_h1(b"hello", 0) == 0xcbd8a7b341bd9b02
+    assert oracle.murmur_h1(b"The quick brown fox jumps over the lazy dog", 0) == 0xe34bbc7bbc071b6c
+
+
+@pytest.mark.parametrize("k,s", [(21, 1000), (15, 200), (32, 64), (17, 1000)])
+def test_sketch_matches_reference_golden(oracle, k, s):
+    gold = np.load(os.path.join(GOLD, "sketches.npz"))
+    names = sorted({key.split("_k")[0] for key in gold.files})
+    assert len(names) == 8
+    for nm in names:
+        want = gold["%s_k%d_s%d" % (nm, k, s)]
+        got = oracle.minhash_sketch(genome_records(nm), k, s)
+        assert np.array_equal(got, want), (nm, k, s)
+
+
+def test_ecoli_known_answer_from_survey(oracle):
+    # SURVEY.md 8c pins the full genomes; the 150 kb slices are pinned by the golden file, and the
+    # slice sketches of K-12 strains 1 and 3 share almost everything while O157:H7 does not.
+    gold = np.load(os.path.join(GOLD, "sketches.npz"))
+    a, b, c = (gold["ecoli%d_k21_s1000" % i] for i in (1, 2, 3))
+    c12, _ = oracle.intersect(a, b)
+    c13, _ = oracle.intersect(a, c)
+    assert c13 > c12
+    assert len(a) == 1000 and (np.diff(a.astype(object)) > 0).all()
+
+
+def test_mst_list_golden(oracle):
+    d = os.path.join(GOLD, "mst_list")
+    hs = sketch_io.read_hash_sketch(os.path.join(d, "hash.sketch"))
+    by_file, info = sketch_io.read_info_sketch(os.path.join(d, "info.sketch"))
+    assert by_file and hs["k"] == 15 and not hs["containment"] and hs["param"] == 1000
+    # sketches in the folder == oracle sketches of the genomes named in info.sketch
+    for rec, sk in zip(info, hs["sketches"]):
+        got = oracle.minhash_sketch(genome_records(rec["name"]), 15, 1000)
+        assert np.array_equal(got, sk), rec["name"]
+    ref_mst = sketch_io.read_edge_mst(os.path.join(d, "edge.mst"))
+    mst = oracle.mst(hs["sketches"], 15, 0.05)
+    assert np.array_equal(np.sort(mst["dist"]), np.sort(ref_mst["dist"]))
+    n = len(info)
+    _, labels, _ = oracle.clusters_from_mst(mst, n, 0.05)
+    mine = sorted(sorted(info[i]["name"] for i in np.nonzero(labels == c)[0]) for c in range(labels.max() + 1))
+    assert mine == partition(sketch_io.parse_cluster_file(os.path.join(d, "clusters.txt")))
+
+
+@pytest.mark.parametrize("tag,contain", [("greedy_list_s", False), ("greedy_list_c", True)])
+def test_greedy_list_golden(oracle, tag, contain):
+    d = os.path.join(GOLD, tag)
+    hs = sketch_io.read_hash_sketch(os.path.join(d, "hash.sketch"))
+    _, info = sketch_io.read_info_sketch(os.path.join(d, "info.sketch"))
+    assert hs["containment"] == contain
+    for rec, sk in zip(info, hs["sketches"]):
+        # -c 100: sketch size = max(fileBytes/100, 100) with the gz trailer's uncompressed size
+        s = len(sk) if contain else 1000
+        got = oracle.minhash_sketch(genome_records(rec["name"]), 15, s)
+        assert np.array_equal(got, sk), rec["name"]
+    nc, rep = oracle.greedy(hs["sketches"], 15, 0.05, contain)
+    ref = sketch_io.parse_cluster_file(os.path.join(d, "clusters.txt"))
+    # reference order: clusters in representative-creation order, members in arrival order
+    mine = [[info[r]["name"]] + [info[j]["name"] for j in range(len(rep)) if rep[j] == r and j != r]
+            for r in sorted(set(rep.tolist()))]
+    assert mine == [[n for _, n in c] for c in ref]
+    assert nc == len(ref)
+
+
+@pytest.mark.parametrize("mode,contain", [("mash", False), ("contain", True)])
+def test_presketched_golden(oracle, mode, contain):
+    d = os.path.join(GOLD, "presketched", mode)
+    hs = sketch_io.read_hash_sketch(os.path.join(d, "hash.sketch"))
+    _, info = sketch_io.read_info_sketch(os.path.join(d, "info.sketch"))
+    n = len(info)
+    mst = oracle.mst(hs["sketches"], hs["k"], 0.05, contain)
+    _, labels, order = oracle.clusters_from_mst(mst, n, 0.05)
+    mine = sorted(sorted(info[i]["name"] for i in np.nonzero(labels == c)[0]) for c in range(labels.max() + 1))
+    assert mine == partition(sketch_io.parse_cluster_file(os.path.join(d, "clust-mst.clusters.txt")))
+    # greedy --presketched sorts by (totalSeqLength desc, id asc) first (sub_command.cpp:2657-2660)
+    order = sorted(range(n), key=lambda i: (-info[i]["length"], i))
+    sk = [hs["sketches"][i] for i in order]
+    nc, rep = oracle.greedy(sk, hs["k"], 0.05, contain)
+    ref = sketch_io.parse_cluster_file(os.path.join(d, "clust-greedy.clusters.txt"))
+    mine = [[info[order[r]]["name"]] + [info[order[j]]["name"] for j in range(n) if rep[j] == r and j != r]
+            for r in sorted(set(rep.tolist()))]
+    assert mine == [[nm for _, nm in c] for c in ref]
+
+
+def test_kssd_golden(oracle):
+    import struct
+    d = os.path.join(GOLD, "kssd")
+    data = open(os.path.join(d, "kssd.hash.sketch"), "rb").read()
+    pid, half_k, half_subk, drlevel, ngen = struct.unpack_from("<iiiii", data, 0)
+    assert (half_subk, drlevel, ngen) == (6, 3, 16)
+    pos, sk = 20, []
+    for _ in range(ngen):
+        (m,) = struct.unpack_from("<Q", data, pos); pos += 8
+        sk.append(np.frombuffer(data, "<u4", m, pos).astype(np.uint64)); pos += 4 * m
+    assert pos == len(data)
+    for i, want in enumerate(sk):
+        got = oracle.kssd_sketch(genome_records("g%02d" % i), 2 * half_k, drlevel)
+        assert np.array_equal(got, want), i
+    ref_mst = sketch_io.read_edge_mst(os.path.join(d, "edge.mst"))
+    mst = oracle.mst(sk, 2 * half_k, 0.05)   # KSSD distance = semantic A with k = 2*half_k (MST.cpp:219)
+    assert np.array_equal(np.sort(mst["dist"]), np.sort(ref_mst["dist"]))
+
+
+def test_semantic_B_against_reference_binary(oracle, tmp_path):
+    exe = oracle.ref_bin("ref_harness")
+    if exe is None:
+        pytest.skip("oracle/_ref not built")
+    sk = synth.family_sketches(3, 4, s=400, seed=8)
+    sketch_io.write_minhash_folder(str(tmp_path), sk, ["x%d" % i for i in range(len(sk))], k=21, sketch_size=400)
+    for i, j in [(0, 1), (0, 5), (2, 3), (7, 7)]:
+        out = subprocess.check_output([exe, "dist", str(tmp_path / "hash.sketch"), str(i), str(j)]).split()
+        jac, dist = float(out[0]), float(out[1])
+        mine = oracle.jaccard_B(sk[i], sk[j], 400)
+        assert mine == jac
+        assert float(oracle.lib().oc_distance_B(mine, 21)) == dist
+
+
+def test_reference_cli_accepts_our_folder_live(oracle, tmp_path):
+    exe = oracle.ref_bin("clust-mst")
+    if exe is None:
+        pytest.skip("oracle/_ref not built")
+    sk = synth.family_sketches(5, 5, s=200, seed=31)
+    names = ["n%02d" % i for i in range(len(sk))]
+    folder = tmp_path / "sk"
+    sketch_io.write_minhash_folder(str(folder), sk, names, k=21, sketch_size=200)
+    subprocess.run([exe, "-t", "1", "--presketched", str(folder), "-d", "0.05", "-o", "out.txt"], cwd=tmp_path,
+                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    ref = partition(sketch_io.parse_cluster_file(str(tmp_path / "out.txt")))
+    mst = oracle.mst(sk, 21, 0.05)
+    _, labels, _ = oracle.clusters_from_mst(mst, len(sk), 0.05)
+    mine = sorted(sorted(names[i] for i in np.nonzero(labels == c)[0]) for c in range(labels.max() + 1))
+    assert mine == ref
