@@ -1,12 +1,6 @@
 // k_pending.cu -- entry points declared in include/tclust.h whose kernels are not built yet.
 // They fail loudly (no CPU fallback).
 #include "tc_common.cuh"
-extern "C" int tc_sketch_minhash(tc_ctx *, const uint8_t *, const uint64_t *, const uint32_t *, uint64_t, uint32_t, int,
-                                 const uint32_t *, uint32_t, uint64_t *, uint64_t, uint32_t *)
-{ tc_set_error("tc_sketch_minhash: not implemented"); return 2; }
-extern "C" int tc_sketch_minhash_dev(tc_ctx *, const uint8_t *, const uint64_t *, const uint32_t *, uint64_t, uint32_t, int,
-                                     const uint32_t *, uint32_t, uint64_t *, uint64_t, uint32_t *)
-{ tc_set_error("tc_sketch_minhash_dev: not implemented"); return 2; }
 extern "C" int tc_sketch_kssd(tc_ctx *, const uint8_t *, const uint64_t *, const uint32_t *, uint64_t, uint32_t, int, int,
                               const int32_t *, uint64_t *, uint64_t, uint32_t *)
 { tc_set_error("tc_sketch_kssd: not implemented"); return 2; }

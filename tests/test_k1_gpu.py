@@ -1,0 +1,91 @@
+"""GPU parity of MinHash sketch construction (K1) against the reference's golden sketches and the
+CPU oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from rabbittclust_b200 import fasta, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_genomes():
+    out = {}
+    for d in ("genomes", "ecoli"):
+        for p in sorted(glob.glob(os.path.join(GOLD, d, "*.fa.gz"))):
+            nm = os.path.basename(p).split(".")[0].replace("_150k", "")
+            out[nm] = [r[2] for r in fasta.read_fasta(p)]
+    return out
+
+
+@pytest.mark.parametrize("k,s", [(21, 1000), (15, 200), (32, 64), (17, 1000)])
+def test_sketch_matches_reference_golden(ctx, k, s):
+    gold = np.load(os.path.join(GOLD, "sketches.npz"))
+    gen = golden_genomes()
+    names = sorted(gen)
+    got = ctx.sketch_minhash([gen[n] for n in names], k=k, s=s)     # one batch, 8 genomes
+    for nm, h in zip(names, got):
+        assert np.array_equal(h, gold["%s_k%d_s%d" % (nm, k, s)]), (nm, k, s)
+
+
+@pytest.mark.parametrize("k", [8, 11, 16, 19, 24, 25, 31])
+def test_sketch_all_word_counts_vs_oracle(ctx, oracle, k):
+    rng = np.random.default_rng(k)
+    g = [[synth.random_genome(7000, rng)], [synth.random_genome(3000, rng).lower(), b"ACGTNNRYKMacgtn" * 30]]
+    got = ctx.sketch_minhash(g, k=k, s=150)
+    for recs, h in zip(g, got):
+        assert np.array_equal(h, oracle.minhash_sketch(recs, k, 150))
+
+
+def test_sketch_edge_cases(ctx, oracle):
+    rng = np.random.default_rng(77)
+    g = [
+        [b"ACGT"],                                             # shorter than k: empty sketch
+        [synth.random_genome(21, rng)],                        # exactly one window
+        [b"A" * 5000],                                         # one distinct k-mer repeated
+        [synth.random_genome(200, rng)] * 5,                   # identical records: duplicates across records
+        [bytes(rng.integers(0, 256, 4000, dtype=np.uint8).tolist()).replace(b"\0", b"x")],   # arbitrary bytes
+        [synth.random_genome(100000, rng)],                    # several segments, merged
+        [synth.random_genome(40, rng), b"", synth.random_genome(25, rng)],
+    ]
+    got = ctx.sketch_minhash(g, k=21, s=1000)
+    for recs, h in zip(g, got):
+        want = oracle.minhash_sketch(recs, 21, 1000)
+        assert np.array_equal(h, want), (len(h), len(want))
+    assert len(got[0]) == 0 and len(got[1]) == 1 and len(got[2]) == 1
+
+
+def test_sketch_variable_and_large_sizes(ctx, oracle):
+    # containment mode: sketch size per genome = max(bytes/compress, 100); includes a size that needs
+    # the global-memory candidate buffer
+    rng = np.random.default_rng(5)
+    lens = [12000, 150000, 600000, 60000]
+    sizes = [100, 3000, 30000, 120]
+    g = [[synth.random_genome(L, rng)] for L in lens]
+    got = ctx.sketch_minhash(g, k=19, s=sizes)
+    for recs, h, s in zip(g, got, sizes):
+        assert np.array_equal(h, oracle.minhash_sketch(recs, 19, s))
+
+
+def test_sketch_then_cluster_matches_reference_run(ctx, oracle):
+    """config-1 shape in miniature: the reference's own clust-mst run on tests/golden/mst_genomes."""
+    from rabbittclust_b200 import sketch_io
+    d = os.path.join(GOLD, "mst_list")
+    hs = sketch_io.read_hash_sketch(os.path.join(d, "hash.sketch"))
+    _, info = sketch_io.read_info_sketch(os.path.join(d, "info.sketch"))
+    genomes = [[r[2] for r in fasta.read_fasta(os.path.join(GOLD, "mst_genomes", rec["name"] + ".fa.gz"))]
+               for rec in info]
+    got = ctx.sketch_minhash(genomes, k=15, s=1000)
+    for a, b in zip(got, hs["sketches"]):
+        assert np.array_equal(a, b)
+    ctx.upload(got)
+    mst = ctx.mst(15, 0.05)
+    ref = sketch_io.read_edge_mst(os.path.join(d, "edge.mst"))
+    assert np.array_equal(np.sort(mst["dist"]), np.sort(ref["dist"]))
+    _, labels, _ = oracle.clusters_from_mst(mst, len(info), 0.05)
+    mine = sorted(sorted(info[i]["name"] for i in np.nonzero(labels == c)[0]) for c in range(labels.max() + 1))
+    ref_c = sketch_io.parse_cluster_file(os.path.join(d, "clusters.txt"))
+    assert mine == sorted(sorted(n for _, n in c) for c in ref_c)
