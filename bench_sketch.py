@@ -1,0 +1,171 @@
+"""bench_sketch.py -- HP-1 leg of bench.py: MinHash sketch construction (K1) on synthetic genomes of
+the BASELINE.json configs[1] shape (5 Mbp, single record, k=21, s=1000), generated ON THE DEVICE
+(50,000 x 5 Mbp does not fit host RAM/disk, so a step sketches one HBM-resident batch).
+
+value = genomes/s with the batch resident in HBM (CUDA events on the library's stream);
+e2e   = genomes/s through tc_sketch_minhash with HOST (pinned) sequence buffers: H2D of the bases,
+        kernels, D2H of the sketches inside the timed region.
+"""
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def device_genomes(torch, n, length, seed, device):
+    """n genomes of `length` iid uniform ACGT bases as one uint8 device tensor (+64 B tail pad)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    total = n * length
+    buf = torch.zeros(total + 64, dtype=torch.uint8, device=device)
+    step = 1 << 28
+    for o in range(0, total, step):
+        m = min(step, total - o)
+        c = torch.randint(0, 4, (m,), dtype=torch.uint8, device=device, generator=g)
+        # 0,1,2,3 -> 'A','C','G','T' (65,67,71,84)
+        buf[o:o + m] = 65 + 2 * c + 2 * (c >= 2).to(torch.uint8) + 11 * (c == 3).to(torch.uint8)
+        del c
+    return buf
+
+
+def measure(args, local_rank=0, rank=0, world=1, dist=None):
+    """Returns a dict with the sketch-leg numbers of this rank's batch (genomes are independent units:
+    every rank sketches its own batch, no collective -> weak scaling)."""
+    import torch
+    import rabbittclust_b200 as T
+    L = T.lib()
+    dev = torch.device("cuda", local_rank)
+    ng, glen, k, s = args.genomes, args.genome_len, 21, 1000
+    ctx = T.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    seq = device_genomes(torch, ng, glen, 1234 + rank, dev)
+    rec_off = (np.arange(ng + 1, dtype=np.uint64) * np.uint64(glen))
+    r2g = np.arange(ng, dtype=np.uint32)
+    ss = np.full(ng, s, np.uint32)
+    out = torch.zeros((ng, s), dtype=torch.int64, device=dev)
+    out_n = torch.zeros(ng, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        T._chk(L.tc_sketch_minhash_dev(ctx._h, seq.data_ptr(), T._p(rec_off, C.c_uint64), T._p(r2g, C.c_uint32),
+                                       ng, ng, k, T._p(ss, C.c_uint32), 42, out.data_ptr(), s, out_n.data_ptr()))
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+    for _ in range(args.steps):
+        step()
+    with torch.cuda.stream(stream):
+        e1.record()
+    e1.synchronize()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / args.steps
+    launches = ctx.launches - l0
+    # size-independent property at full size: every sketch has exactly s strictly ascending hashes
+    o = out.cpu().numpy().view(np.uint64)
+    assert (out_n.cpu().numpy() == s).all(), "sketch count"
+    assert (o[:, 1:] > o[:, :-1]).all(), "sketches not strictly ascending"
+
+    # ---- e2e: host pinned bases -> tc_sketch_minhash -> host sketches
+    ne = max(1, min(ng, args.e2e_genomes))
+    h_seq = torch.empty(ne * glen + 64, dtype=torch.uint8).pin_memory()
+    h_seq[:ne * glen].copy_(seq[:ne * glen])
+    h_seq[ne * glen:] = 0
+    h_out = torch.zeros((ne, s), dtype=torch.int64).pin_memory()
+    h_n = torch.zeros(ne, dtype=torch.int32).pin_memory()
+    ro, rg, sz = rec_off[:ne + 1].copy(), r2g[:ne].copy(), ss[:ne].copy()
+
+    def e2e_step():
+        T._chk(L.tc_sketch_minhash(ctx._h, h_seq.data_ptr(), T._p(ro, C.c_uint64), T._p(rg, C.c_uint32),
+                                   ne, ne, k, T._p(sz, C.c_uint32), 42, h_out.data_ptr(), s, h_n.data_ptr()))
+
+    e2e_step()
+    torch.cuda.synchronize()
+    n_e2e = max(1, min(args.steps, 3))
+    t0 = time.time()
+    for _ in range(n_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.time() - t0) * 1e3 / n_e2e
+    assert np.array_equal(h_out.numpy().view(np.uint64), o[:ne]), "host-buffer path differs from device path"
+    ctx.close()
+    del seq
+    return {"genomes": ng, "genome_len": glen, "k": k, "s": s, "ms_per_step": dev_ms,
+            "genomes_per_s": ng / (dev_ms / 1e3), "gbp_per_s": ng * glen / (dev_ms / 1e3) / 1e9,
+            "launches": int(launches), "e2e_genomes": ne, "e2e_ms_per_step": e2e_ms,
+            "e2e_genomes_per_s": ne / (e2e_ms / 1e3), "h2d_bytes": ne * glen, "d2h_bytes": ne * s * 8 + ne * 4}
+
+
+def cpu_update(args, threads):
+    """The reference's MinHash::update (oracle/_ref/ref_harness, AVX2 build) on a bounded sample."""
+    import subprocess
+    from oracle import pyoracle
+    exe = pyoracle.ref_bin("ref_harness")
+    if exe is None:
+        return None
+    ng = max(threads, 8)
+    r = json.loads(subprocess.check_output([exe, "update", "21", "1000", str(threads), str(args.genome_len), str(ng)]))
+    return r
+
+
+def run_sketch(args):
+    """--workload sketch: the sketch leg as the main JSON line."""
+    import torch
+    from bench import ClockSampler, dist_env, measured_peak
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    m = measure(args, local_rank, rank, world, dist)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([m["ms_per_step"], m["e2e_ms_per_step"], float(m["launches"])], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        m["ms_per_step"], m["e2e_ms_per_step"], m["launches"] = float(tm[0]), float(tm[1]), int(ts[2])
+    if rank == 0:
+        peak, how = measured_peak()
+        ng, glen, s = m["genomes"], m["genome_len"], m["s"]
+        value = world * ng / (m["ms_per_step"] / 1e3)
+        alg_bytes = ng * (glen + 8 * s)
+        achieved = alg_bytes / (m["ms_per_step"] / 1e3) / 1e9
+        line = {"metric": "genomes sketched/sec", "value": value, "unit": "genomes/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": "sketch-only: %d synthetic %d bp genomes per GPU and step, k=21 s=1000 "
+                                       "(BASELINE.json configs[1] shape, device-generated)" % (ng, glen),
+                           "l2": "input %.1f GB per step > 126 MB L2" % (ng * glen / 1e9),
+                           "gbp_per_s": world * m["gbp_per_s"]},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": how, "kernel": "k1_sketch_segment_kernel",
+                             "note": "algorithmic bytes = L + 8s per genome (SURVEY 8d); K1 is INT32-ALU bound "
+                                     "(Murmur3 64-bit multiplies), see DESIGN.md K1"},
+                "e2e": {"value": world * m["e2e_genomes_per_s"], "unit": "genomes/s",
+                        "h2d_bytes_per_step": m["h2d_bytes"] * world, "d2h_bytes_per_step": m["d2h_bytes"] * world,
+                        "genomes_per_step": m["e2e_genomes"] * world},
+                "gpu_launches": m["launches"], "clocks": clocks}
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            r = cpu_update(args, threads)
+            if r:
+                line["cpu_baseline"] = {"value": r["genomes_per_s"], "unit": "genomes/s", "cores": r["threads"],
+                                        "kind": "reference", "sample": "%d genomes of %d bp, MinHash::update AVX2 build"
+                                        % (r["genomes"], r["len"])}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
