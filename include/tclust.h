@@ -36,6 +36,11 @@ typedef struct { int32_t pre, suf; double dist; } tc_edge;
 /* one candidate edge of the semantic-A graph: pair (i, j<i) with common >= 1 */
 typedef struct { uint32_t i, j, common; } tc_pair;
 
+/* one candidate of the greedy representative scan: query genome, representative genome, shared
+ * hashes, and the index in the query sketch of the first shared hash (what greedy.cpp:1148-1164
+ * accumulates in cnt[] / the position of the representative in touched[]) */
+typedef struct { uint32_t query, rep, common, first_hit; } tc_cand;
+
 int         tc_version(void);
 const char *tc_last_error(void);
 
@@ -82,6 +87,12 @@ int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off,
                    const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes,
                    int kmer_size, int drlevel, const int32_t *shuffled_dim,
                    uint64_t *out_hashes, uint64_t out_stride, uint32_t *out_n);
+/* same with sequence and outputs resident on the device (shuffled_dim stays a host pointer; the
+ * table is uploaded once per context and pointer) */
+int tc_sketch_kssd_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const uint64_t *rec_off,
+                       const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes,
+                       int kmer_size, int drlevel, const int32_t *shuffled_dim,
+                       uint64_t *out_hashes_dev, uint64_t out_stride, uint32_t *out_n_dev);
 
 /* ---- HP-2: all-pairs sorted-sketch intersection -------------------------------------- */
 /*
@@ -152,6 +163,10 @@ int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, double thresh
 double tc_mash_dist(int common, int size0, int size1, int kmer_size);     /* MST.cpp:1489-1503 */
 double tc_aaf_dist(int common, int size0, int size1, int kmer_size);      /* MST.cpp:1504-1515 */
 double tc_dist_from_key(uint64_t key, int containment, int kmer_size);    /* J bits -> dist */
+int    tc_greedy_common_min(double threshold, int kmer_size, int size_ref, int size_qry,
+                            int containment);                             /* greedy.cpp:1107-1113,1211-1219 */
+double tc_greedy_dist(int common, int size_ref, int size_qry, int containment,
+                      int kmer_size);                                     /* greedy.cpp:1245-1274 */
 int    tc_radio(double threshold, int kmer_size);                         /* MST.cpp:26-37,1292 */
 
 #ifdef __cplusplus

@@ -116,7 +116,7 @@ def kssd_sketch(records, kmer_size, drlevel=3):
     seq, off, n = _pack_records(records)
     _, half_subk, _ = kssd_params(kmer_size, drlevel)
     sd = kssd_shuffled_dim(half_subk)
-    cap = max(1024, int(off[-1]) // 256 + 1024)
+    cap = max(1024, int(off[-1]) // 8 + 1024)
     out = np.zeros(cap, np.uint64)
     m = lib().oc_kssd_sketch(_p(seq, C.c_uint8), _p(off, C.c_uint64), n, kmer_size, drlevel,
                              _p(sd, C.c_int32), _p(out, C.c_uint64), cap)

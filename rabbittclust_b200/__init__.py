@@ -19,11 +19,11 @@ PAIR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("common", "<u4")])
 # every symbol include/tclust.h declares (tests check the built library exports all of them)
 SYMBOLS = [
     "tc_version", "tc_last_error", "tc_ctx_create", "tc_ctx_destroy", "tc_kernel_launches", "tc_stream",
-    "tc_sketch_minhash", "tc_sketch_minhash_dev", "tc_sketch_kssd",
+    "tc_sketch_minhash", "tc_sketch_minhash_dev", "tc_sketch_kssd", "tc_sketch_kssd_dev",
     "tc_sketches_upload", "tc_sketches_upload_dev", "tc_pair_common", "tc_allpairs_pass",
     "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_mst",
     "tc_greedy_scan", "tc_greedy_cluster",
-    "tc_mash_dist", "tc_aaf_dist", "tc_dist_from_key", "tc_radio",
+    "tc_mash_dist", "tc_aaf_dist", "tc_dist_from_key", "tc_radio", "tc_greedy_common_min", "tc_greedy_dist",
 ]
 
 
@@ -59,6 +59,7 @@ def lib():
     L.tc_sketch_minhash_dev.argtypes = sk
     L.tc_sketch_kssd.argtypes = [vp, vp, u64p, u32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, i32p,
                                  vp, C.c_uint64, vp]
+    L.tc_sketch_kssd_dev.argtypes = L.tc_sketch_kssd.argtypes
     L.tc_sketches_upload.argtypes = [vp, vp, u64p, C.c_uint32]
     L.tc_sketches_upload_dev.argtypes = [vp, vp, u64p, C.c_uint32]
     L.tc_pair_common.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u32p]
@@ -75,6 +76,10 @@ def lib():
         f.restype = C.c_double
     L.tc_dist_from_key.argtypes = [C.c_uint64, C.c_int, C.c_int]
     L.tc_dist_from_key.restype = C.c_double
+    L.tc_greedy_common_min.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.tc_greedy_common_min.restype = C.c_int
+    L.tc_greedy_dist.argtypes = [C.c_int] * 5
+    L.tc_greedy_dist.restype = C.c_double
     L.tc_radio.argtypes = [C.c_double, C.c_int]
     L.tc_radio.restype = C.c_int
     _lib = L

@@ -39,24 +39,34 @@ struct K3Meta {
 };
 constexpr size_t K3_SMEM = (size_t)2 * K3_ROWS * 32 * 4 + sizeof(K3Meta);
 
-enum { K3_MODE_MATRIX = 0, K3_MODE_EDGES = 1 };
+enum { K3_MODE_MATRIX = 0, K3_MODE_EDGES = 1, K3_MODE_CAND = 2 };
+
+// a set of sketches in the group-interleaved layout: member m = group*32 + lane
+struct K3Set {
+    const uint32_t *gt;              // interleaved ranks
+    const unsigned long long *goff;  // ngroups+1 element offsets into gt
+    const uint32_t *len;             // length of member m
+    const uint32_t *ids;             // global sketch id of member m (nullptr: identity)
+    uint32_t n, ngroups;
+};
 
 struct K3Args {
-    const uint32_t *gt;
-    const unsigned long long *goff;
-    const uint32_t *size;
-    uint32_t n, ngroups;
-    int mode;
+    K3Set row, col;
     // tile space: row groups [rg0, rg1), col groups [cg0, cg1); triangular => only cg <= rg
     uint32_t rg0, rg1, cg0, cg1;
     int triangular;
     long long ntiles;
     uint32_t part, nparts;
-    unsigned long long *counters;  // [0] edge count, [1] overflow, [2] tile counter
-    // matrix mode
-    uint32_t *out; uint32_t i0, i1, j0, j1;
-    // edge mode
+    unsigned long long *counters;  // [0] edge/candidate count, [1] overflow, [2] tile counter
+    // matrix mode (validation): common (and first_hit when FH) for rows [i0,i1) x col members [j0,j1)
+    uint32_t *out; uint32_t *out_fh; uint32_t i0, i1, j0, j1;
+    // edge mode (MST candidate graph)
     tc_pair *edges; unsigned long long edge_cap; int radio;
+    // candidate mode (greedy representative scan): emit (query, rep, common, first_hit) when
+    // common >= 1 and common + 1 >= common_min(pair)  (host applies the exact rule)
+    tc_cand *cands; int lower_only;   // lower_only: emit only col id < row id (intra-batch tiles)
+    int cmin_fixed;                   // >= 0: fixed-size Mash mode; < 0: per-pair rule below
+    int containment; double jmin, one_plus_jmin;
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
@@ -82,6 +92,7 @@ __device__ __forceinline__ void tile_to_rc(const K3Args &a, long long t, uint32_
     }
 }
 
+template <int MODE, bool FH>
 __global__ void __launch_bounds__(K3_THREADS, 1) k3_tile_kernel(const K3Args a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -111,21 +122,23 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_tile_kernel(const K3Args a)
         uint32_t rg, cg;
         tile_to_rc(a, t, rg, cg);
         if (tid < 64) {
+            const K3Set &S = tid < 32 ? a.row : a.col;
             const uint32_t g = tid < 32 ? rg : cg;
             const uint32_t sk = g * TC_GROUP + (tid & 31);
-            m->len[tid] = (g < a.ngroups && sk < a.n) ? a.size[sk] : 0u;
+            m->len[tid] = (g < S.ngroups && sk < S.n) ? S.len[sk] : 0u;
             m->pos[tid] = 0;
-            m->gbase[tid] = (g < a.ngroups ? a.goff[g] : 0ULL) + (tid & 31);
+            m->gbase[tid] = (g < S.ngroups ? S.goff[g] : 0ULL) + (tid & 31);
         }
         uint32_t acc = 0;
+        uint32_t first_hit = 0xFFFFFFFFu;   // FH: index in the row sketch of the first shared element
         __syncthreads();
 
         for (;;) {  // ---- value-range chunks ----
             {   // load: warp w fills rows w, w+32, ... of both regions; lane = stream
                 const uint32_t pA = m->pos[lane], lA = m->len[lane];
                 const uint32_t pB = m->pos[32 + lane], lB = m->len[32 + lane];
-                const uint32_t *gA = a.gt + m->gbase[lane];
-                const uint32_t *gB = a.gt + m->gbase[32 + lane];
+                const uint32_t *gA = a.row.gt + m->gbase[lane];
+                const uint32_t *gB = a.col.gt + m->gbase[32 + lane];
 #pragma unroll 4
                 for (int r = warp; r < K3_CAP; r += 32) {
                     const uint32_t eA = pA + r, eB = pB + r;
@@ -164,10 +177,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_tile_kernel(const K3Args a)
                 uint32_t pa = pa0, pb = pb0;
                 uint32_t va = lds_u32(pa), vb = lds_u32(pb);
                 uint32_t nblk = 0;
+                uint32_t fh_addr = 0xFFFFFFFFu;
                 while (max(va, vb) < TC_SENT_B) {
 #pragma unroll
                     for (int u = 0; u < K3_U; u++) {
                         const bool le = va <= vb, ge = va >= vb;
+                        if (FH) { if (le && ge) fh_addr = min(fh_addr, pa); }
                         if (le) pa += 128;
                         if (ge) pb += 128;
                         va = lds_u32(pa);
@@ -176,6 +191,10 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_tile_kernel(const K3Args a)
                     nblk++;
                 }
                 acc += (((pa - pa0) + (pb - pb0)) >> 7) - nblk * K3_U;
+                if (FH) {
+                    if (first_hit == 0xFFFFFFFFu && fh_addr != 0xFFFFFFFFu)
+                        first_hit = m->pos[prow] + ((fh_addr - pa0) >> 7);
+                }
             }
             const uint32_t more = m->more;
             __syncthreads();
@@ -185,17 +204,35 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_tile_kernel(const K3Args a)
         }
 
         // ---- epilogue ----
-        const uint32_t i = rg * TC_GROUP + prow, j = cg * TC_GROUP + pcol;
-        if (a.mode == K3_MODE_MATRIX) {
-            if (i >= a.i0 && i < a.i1 && j >= a.j0 && j < a.j1)
-                a.out[(size_t)(i - a.i0) * (a.j1 - a.j0) + (j - a.j0)] = acc;
+        const uint32_t i = rg * TC_GROUP + prow, jm = cg * TC_GROUP + pcol;   // member indices
+        if (MODE == K3_MODE_MATRIX) {
+            if (i >= a.i0 && i < a.i1 && jm >= a.j0 && jm < a.j1) {
+                const size_t o = (size_t)(i - a.i0) * (a.j1 - a.j0) + (jm - a.j0);
+                a.out[o] = acc;
+                if (FH) a.out_fh[o] = first_hit;
+            }
         } else {
             bool keep = false;
-            if (i < a.n && j < i && acc >= 1u) {
-                const uint32_t s0 = a.size[i], s1 = a.size[j];
-                const uint32_t mn = min(s0, s1), mx = max(s0, s1);
-                // reference: skip if max_size > radio * min_size (int arithmetic), MST.cpp:1481-1487
-                keep = mn > 0 && !((long long)mx > (long long)a.radio * (long long)mn);
+            const uint32_t s0 = m->len[prow], s1 = m->len[32 + pcol];
+            uint32_t j = jm;
+            if (MODE == K3_MODE_EDGES) {
+                if (i < a.row.n && j < i && acc >= 1u) {
+                    const uint32_t mn = min(s0, s1), mx = max(s0, s1);
+                    // reference: skip if max_size > radio * min_size (int arithmetic), MST.cpp:1481-1487
+                    keep = mn > 0 && !((long long)mx > (long long)a.radio * (long long)mn);
+                }
+            } else {
+                if (i < a.row.n && jm < a.col.n && acc >= 1u) {
+                    if (a.col.ids) j = a.col.ids[jm];
+                    int cmin = a.cmin_fixed;
+                    if (cmin < 0) {   // greedy.cpp:1211-1219, IEEE-exact operations in the host's order
+                        const double t = a.containment
+                            ? __dmul_rn(a.jmin, (double)min(s0, s1))
+                            : __ddiv_rn(__dmul_rn(a.jmin, (double)(s0 + s1)), a.one_plus_jmin);
+                        cmin = (int)ceil(t);
+                    }
+                    keep = (long long)acc + 1 >= (long long)cmin && (!a.lower_only || j < i);
+                }
             }
             const unsigned ballot = __ballot_sync(0xffffffffu, keep);
             if (ballot) {
@@ -205,8 +242,13 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_tile_kernel(const K3Args a)
                 if (keep) {
                     const unsigned long long idx = base + __popc(ballot & ((1u << lane) - 1));
                     if (idx < a.edge_cap) {
-                        tc_pair e; e.i = i; e.j = j; e.common = acc;
-                        a.edges[idx] = e;
+                        if (MODE == K3_MODE_EDGES) {
+                            tc_pair e; e.i = i; e.j = j; e.common = acc;
+                            a.edges[idx] = e;
+                        } else {
+                            tc_cand c; c.query = i; c.rep = j; c.common = acc; c.first_hit = first_hit;
+                            a.cands[idx] = c;
+                        }
                     } else {
                         a.counters[1] = 1ULL;
                     }
@@ -237,24 +279,46 @@ __global__ void pair_common_ref_kernel(const uint64_t *hashes, const unsigned lo
     out[idx] = c;
 }
 
-int k3_launch(tc_ctx *ctx, K3Args &a)
+template <int MODE, bool FH>
+int k3_launch_t(tc_ctx *ctx, const K3Args &a, int grid)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        TC_CUDA(cudaFuncSetAttribute(k3_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM));
+        TC_CUDA(cudaFuncSetAttribute(k3_tile_kernel<MODE, FH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM));
         attr_set = true;
     }
-    a.gt = ctx->d_gt;
-    a.goff = reinterpret_cast<const unsigned long long *>(ctx->d_goff);
-    a.size = ctx->d_size;
-    a.n = ctx->n;
-    a.ngroups = ctx->ngroups;
+    k3_tile_kernel<MODE, FH><<<grid, K3_THREADS, K3_SMEM, ctx->stream>>>(a);
+    return 0;
+}
+
+K3Set main_set(const tc_ctx *ctx)
+{
+    K3Set s{};
+    s.gt = ctx->d_gt; s.goff = reinterpret_cast<const unsigned long long *>(ctx->d_goff);
+    s.len = ctx->d_size; s.ids = nullptr; s.n = ctx->n; s.ngroups = ctx->ngroups;
+    return s;
+}
+
+K3Set rep_set(const tc_ctx *ctx)
+{
+    K3Set s{};
+    s.gt = ctx->d_rep_gt; s.goff = reinterpret_cast<const unsigned long long *>(ctx->d_rep_goff);
+    s.len = ctx->d_rep_len; s.ids = ctx->d_rep_ids; s.n = ctx->nrep; s.ngroups = (ctx->nrep + TC_GROUP - 1) / TC_GROUP;
+    return s;
+}
+
+int k3_launch(tc_ctx *ctx, K3Args &a, int mode, bool fh)
+{
     a.counters = ctx->d_edge_count;
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count + 2, 0, sizeof(unsigned long long), ctx->stream));
     long long my_tiles = (a.ntiles - a.part + a.nparts - 1) / a.nparts;
     if (my_tiles <= 0) return 0;
     int grid = (int)(my_tiles < ctx->num_sms ? my_tiles : ctx->num_sms);
-    k3_tile_kernel<<<grid, K3_THREADS, K3_SMEM, ctx->stream>>>(a);
+    int rc;
+    if (mode == K3_MODE_MATRIX) rc = fh ? k3_launch_t<K3_MODE_MATRIX, true>(ctx, a, grid) : k3_launch_t<K3_MODE_MATRIX, false>(ctx, a, grid);
+    else if (mode == K3_MODE_EDGES) rc = k3_launch_t<K3_MODE_EDGES, false>(ctx, a, grid);
+    else rc = k3_launch_t<K3_MODE_CAND, true>(ctx, a, grid);
+    if (rc) return rc;
     ctx->launches++;
     TC_CUDA(cudaGetLastError());
     return 0;
@@ -265,26 +329,65 @@ int k3_launch(tc_ctx *ctx, K3Args &a)
 int tc_launch_tiles_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out)
 {
     K3Args a{};
-    a.mode = K3_MODE_MATRIX;
+    a.row = main_set(ctx); a.col = main_set(ctx);
     a.rg0 = i0 / TC_GROUP; a.rg1 = (i1 + TC_GROUP - 1) / TC_GROUP;
     a.cg0 = j0 / TC_GROUP; a.cg1 = (j1 + TC_GROUP - 1) / TC_GROUP;
     a.triangular = 0;
     a.ntiles = (long long)(a.rg1 - a.rg0) * (a.cg1 - a.cg0);
     a.part = 0; a.nparts = 1;
     a.out = d_out; a.i0 = i0; a.i1 = i1; a.j0 = j0; a.j1 = j1;
-    return k3_launch(ctx, a);
+    return k3_launch(ctx, a, K3_MODE_MATRIX, false);
+}
+
+// queries [q0,q1) of the main set against the representative table: common and first_hit matrices
+int tc_launch_tiles_rep_matrix(tc_ctx *ctx, uint32_t q0, uint32_t q1, uint32_t *d_common, uint32_t *d_first_hit)
+{
+    K3Args a{};
+    a.row = main_set(ctx); a.col = rep_set(ctx);
+    a.rg0 = q0 / TC_GROUP; a.rg1 = (q1 + TC_GROUP - 1) / TC_GROUP;
+    a.cg0 = 0; a.cg1 = a.col.ngroups;
+    a.triangular = 0;
+    a.ntiles = (long long)(a.rg1 - a.rg0) * (a.cg1 - a.cg0);
+    a.part = 0; a.nparts = 1;
+    a.out = d_common; a.out_fh = d_first_hit; a.i0 = q0; a.i1 = q1; a.j0 = 0; a.j1 = ctx->nrep;
+    return k3_launch(ctx, a, K3_MODE_MATRIX, true);
 }
 
 int tc_launch_tiles_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts)
 {
     K3Args a{};
-    a.mode = K3_MODE_EDGES;
+    a.row = main_set(ctx); a.col = main_set(ctx);
     a.rg0 = 0; a.rg1 = ctx->ngroups; a.cg0 = 0; a.cg1 = ctx->ngroups;
     a.triangular = 1;
     a.ntiles = (long long)ctx->ngroups * (ctx->ngroups + 1) / 2;
     a.part = part; a.nparts = nparts ? nparts : 1;
     a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
-    return k3_launch(ctx, a);
+    return k3_launch(ctx, a, K3_MODE_EDGES, false);
+}
+
+// greedy candidates of the query batch [q0,q1) (q0 multiple of 32): vs_reps = against the representative
+// table, else the batch against itself (col id < row id).  Appends to ctx->d_cands.
+int tc_launch_tiles_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment,
+                          double jmin, uint32_t part, uint32_t nparts)
+{
+    K3Args a{};
+    a.row = main_set(ctx);
+    a.rg0 = q0 / TC_GROUP; a.rg1 = (q1 + TC_GROUP - 1) / TC_GROUP;
+    if (vs_reps) {
+        a.col = rep_set(ctx);
+        a.cg0 = 0; a.cg1 = a.col.ngroups; a.triangular = 0; a.lower_only = 0;
+        a.ntiles = (long long)(a.rg1 - a.rg0) * (a.cg1 - a.cg0);
+    } else {
+        a.col = main_set(ctx);
+        a.cg0 = a.rg0; a.cg1 = a.rg1; a.triangular = 1; a.lower_only = 1;
+        const long long g = a.rg1 - a.rg0;
+        a.ntiles = g * (g + 1) / 2;
+    }
+    a.part = part; a.nparts = nparts ? nparts : 1;
+    a.cands = ctx->d_cands; a.edge_cap = ctx->cand_cap;
+    a.cmin_fixed = cmin_fixed; a.containment = containment; a.jmin = jmin; a.one_plus_jmin = 1.0 + jmin;
+    a.counters = ctx->d_edge_count;
+    return k3_launch(ctx, a, K3_MODE_CAND, true);
 }
 
 int tc_launch_pair_common_ref(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out)

@@ -1,0 +1,283 @@
+// k5_greedy.cu -- K5: greedy representative scan (clust-greedy), host driver + representative table.
+//
+// Replaces MinHashGreedyClusterWithInvertedIndex (reference src/greedy.cpp:986-1399).  The reference
+// walks the genomes serially; genome j probes a dynamic hash -> representative-ids index, counts the
+// shared hashes per touched representative (:1148-1164), filters by common_min (:1107-1113,
+// :1211-1219), picks the best representative (:1198-1309) or becomes a new one (:1321-1336).
+//
+// B200 design (DESIGN.md "K5"): genomes are processed in batches.  For a batch the K3 tile kernel
+// (candidate mode, first-hit tracking) computes  batch x current-representatives  and  batch x batch
+// (earlier member only) and emits the sparse list of candidates (query, rep, common, first_hit) that
+// can pass the common_min filter.  The host then replays the reference's serial decision per query in
+// genome order -- candidates sorted in the reference's `touched` order: (index of the first shared
+// hash in the query sketch, representative creation order) -- so the result is exactly the reference's
+// with one thread.  Genomes that become representatives are appended to a device
+// table kept in the same 32-interleaved layout as the main sketch set.
+#include "tc_common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+
+namespace {
+
+// gt[goff[g] + row*32 + lane] = rank `row` of sketch ids[g*32+lane] (TC_SENT_A padding)
+__global__ void interleave_gather_kernel(const uint32_t *ranks, const unsigned long long *off, const uint32_t *ids,
+                                         uint32_t nmembers, const unsigned long long *goff, uint32_t g0, uint32_t *gt)
+{
+    const uint32_t g = g0 + blockIdx.y;
+    const unsigned long long rows = (goff[g + 1] - goff[g]) / TC_GROUP;
+    const unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * TC_GROUP) return;
+    const uint32_t lane = (uint32_t)(e & 31), row = (uint32_t)(e >> 5);
+    const uint32_t mem = g * TC_GROUP + lane;
+    uint32_t v = TC_SENT_A;
+    if (mem < nmembers) {
+        const uint32_t id = ids[mem];
+        const unsigned long long o = off[id], len = off[id + 1] - o;
+        if (row < len) v = ranks[o + row];
+    }
+    gt[goff[g] + e] = v;
+}
+
+template <typename T>
+int grow(T **p, uint64_t *cap, uint64_t need, uint64_t keep, cudaStream_t st)
+{
+    if (need <= *cap) return 0;
+    uint64_t ncap = std::max<uint64_t>(need, *cap * 2);
+    ncap = std::max<uint64_t>(ncap, 1024);
+    T *q = nullptr;
+    TC_CUDA(cudaMalloc(&q, ncap * sizeof(T)));
+    if (*p && keep) TC_CUDA(cudaMemcpyAsync(q, *p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    TC_CUDA(cudaStreamSynchronize(st));
+    cudaFree(*p);
+    *p = q; *cap = ncap;
+    return 0;
+}
+
+}  // namespace
+
+void tc_rep_table_free(tc_ctx *ctx)
+{
+    cudaFree(ctx->d_rep_gt); cudaFree(ctx->d_rep_goff); cudaFree(ctx->d_rep_len); cudaFree(ctx->d_rep_ids);
+    cudaFree(ctx->d_cands);
+    ctx->d_rep_gt = nullptr; ctx->d_rep_goff = nullptr; ctx->d_rep_len = nullptr; ctx->d_rep_ids = nullptr;
+    ctx->d_cands = nullptr; ctx->cand_cap = 0;
+    ctx->rep_gt_cap = ctx->rep_goff_cap = ctx->rep_len_cap = ctx->rep_ids_cap = 0;
+    ctx->nrep = 0; ctx->h_rep_ids.clear(); ctx->h_rep_goff.assign(1, 0);
+}
+
+void tc_rep_table_reset(tc_ctx *ctx)
+{
+    ctx->nrep = 0; ctx->h_rep_ids.clear(); ctx->h_rep_goff.assign(1, 0);
+}
+
+// append representatives (global sketch ids, in creation order) to the device table
+int tc_rep_table_append(tc_ctx *ctx, const uint32_t *ids, uint32_t count)
+{
+    if (!count) return 0;
+    cudaStream_t st = ctx->stream;
+    const uint32_t old_n = ctx->nrep, new_n = old_n + count;
+    const uint32_t g_first = old_n / TC_GROUP;                       // first group whose content changes
+    const uint32_t ng_new = (new_n + TC_GROUP - 1) / TC_GROUP;
+    for (uint32_t i = 0; i < count; i++) {
+        TC_CHECK(ids[i] < ctx->n, "rep table: sketch id %u out of range", ids[i]);
+        ctx->h_rep_ids.push_back(ids[i]);
+    }
+    ctx->h_rep_goff.resize(ng_new + 1);
+    uint64_t max_rows = 0;
+    for (uint32_t g = g_first; g < ng_new; g++) {
+        uint32_t rows = 0;
+        for (uint32_t l = 0; l < TC_GROUP && g * TC_GROUP + l < new_n; l++)
+            rows = std::max(rows, ctx->h_size[ctx->h_rep_ids[g * TC_GROUP + l]]);
+        ctx->h_rep_goff[g + 1] = ctx->h_rep_goff[g] + (uint64_t)rows * TC_GROUP;
+        max_rows = std::max<uint64_t>(max_rows, rows);
+    }
+    if (grow(&ctx->d_rep_gt, &ctx->rep_gt_cap, ctx->h_rep_goff[ng_new] + 1, ctx->h_rep_goff[g_first], st)) return 1;
+    if (grow(&ctx->d_rep_goff, &ctx->rep_goff_cap, (uint64_t)ng_new + 1, (uint64_t)g_first + 1, st)) return 1;
+    if (grow(&ctx->d_rep_len, &ctx->rep_len_cap, (uint64_t)ng_new * TC_GROUP, old_n, st)) return 1;
+    if (grow(&ctx->d_rep_ids, &ctx->rep_ids_cap, (uint64_t)ng_new * TC_GROUP, old_n, st)) return 1;
+    std::vector<uint32_t> len(count);
+    for (uint32_t i = 0; i < count; i++) len[i] = ctx->h_size[ids[i]];
+    TC_CUDA(cudaMemcpyAsync(ctx->d_rep_goff + g_first, ctx->h_rep_goff.data() + g_first,
+                            (size_t)(ng_new + 1 - g_first) * 8, cudaMemcpyHostToDevice, st));
+    TC_CUDA(cudaMemcpyAsync(ctx->d_rep_ids + old_n, ids, (size_t)count * 4, cudaMemcpyHostToDevice, st));
+    TC_CUDA(cudaMemcpyAsync(ctx->d_rep_len + old_n, len.data(), (size_t)count * 4, cudaMemcpyHostToDevice, st));
+    ctx->nrep = new_n;
+    if (max_rows > 0) {
+        dim3 grid((unsigned)((max_rows * TC_GROUP + 255) / 256), ng_new - g_first);
+        interleave_gather_kernel<<<grid, 256, 0, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
+                                                       ctx->d_rep_ids, new_n,
+                                                       reinterpret_cast<unsigned long long *>(ctx->d_rep_goff), g_first,
+                                                       ctx->d_rep_gt);
+        ctx->launches++;
+        TC_CUDA(cudaGetLastError());
+    }
+    // the host staging vectors (len) must outlive the async copies
+    TC_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------ host formulas (exact)
+extern "C" int tc_greedy_common_min(double threshold, int kmer_size, int size_ref, int size_qry, int containment)
+{
+    // greedy.cpp:1107-1113 (fixed size: size_ref == size_qry) and :1211-1219
+    const double x = std::exp(-threshold * kmer_size);
+    const double jaccard_min = x / (2.0 - x);
+    if (containment) return (int)std::ceil(jaccard_min * std::min(size_ref, size_qry));
+    return (int)std::ceil(jaccard_min * (size_ref + size_qry) / (1.0 + jaccard_min));
+}
+
+extern "C" double tc_greedy_dist(int common, int size_ref, int size_qry, int containment, int kmer_size)
+{
+    // greedy.cpp:1245-1274
+    double jaccard;
+    if (containment) {
+        const int min_size = std::min(size_ref, size_qry);
+        if (min_size == 0) return 1.0;
+        jaccard = (double)common / min_size;
+    } else {
+        const int denom = size_ref + size_qry - common;
+        if (denom == 0) return 0.0;
+        jaccard = (double)common / denom;
+    }
+    if (jaccard >= 1.0) return 0.0;
+    if (jaccard <= 0.0) return 1.0;
+    double dist = -std::log(2.0 * jaccard / (1.0 + jaccard)) / kmer_size;
+    if (dist > 1.0) dist = 1.0;
+    return dist;
+}
+
+// ------------------------------------------------------------------------- validation entry
+extern "C" int tc_greedy_scan(tc_ctx *ctx, uint32_t q0, uint32_t q1, const uint32_t *rep_ids, uint32_t nrep,
+                              uint32_t *common, uint32_t *first_hit)
+{
+    TC_CUDA(cudaSetDevice(ctx->device));
+    TC_CHECK(ctx->n > 0, "tc_greedy_scan: no sketches uploaded");
+    TC_CHECK(q0 <= q1 && q1 <= ctx->n, "tc_greedy_scan: query range out of bounds");
+    const size_t cells = (size_t)(q1 - q0) * nrep;
+    if (!cells) return 0;
+    tc_rep_table_reset(ctx);
+    if (tc_rep_table_append(ctx, rep_ids, nrep)) return 1;
+    uint32_t *d_c = nullptr, *d_f = nullptr;
+    TC_CUDA(cudaMalloc(&d_c, cells * 4));
+    int rc = 1;
+    do {
+        if (cudaMalloc(&d_f, cells * 4) != cudaSuccess) { tc_set_error("tc_greedy_scan: out of device memory"); break; }
+        if (tc_launch_tiles_rep_matrix(ctx, q0, q1, d_c, d_f)) break;
+        if (cudaMemcpyAsync(common, d_c, cells * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(first_hit, d_f, cells * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            tc_set_error("tc_greedy_scan: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        rc = 0;
+    } while (0);
+    cudaFree(d_c); cudaFree(d_f);
+    return rc;
+}
+
+// --------------------------------------------------------------------- full greedy clustering
+extern "C" int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, double threshold, int32_t *rep_of,
+                                 uint32_t *n_clusters)
+{
+    TC_CUDA(cudaSetDevice(ctx->device));
+    TC_CHECK(ctx->n > 0, "tc_greedy_cluster: no sketches uploaded");
+    const uint32_t n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    // fixed-size fast path detection over the first 100 sketches (greedy.cpp:1092-1103)
+    const int fixed_size = (int)ctx->h_size[0];
+    bool all_fixed = !containment;
+    for (uint32_t i = 1; i < std::min<uint32_t>(100, n) && all_fixed; i++)
+        if ((int)ctx->h_size[i] != fixed_size) all_fixed = false;
+    const int cmin_fixed = all_fixed ? tc_greedy_common_min(threshold, kmer_size, fixed_size, fixed_size, 0) : -1;
+    const double x = std::exp(-threshold * kmer_size);
+    const double jmin = x / (2.0 - x);
+
+    uint64_t cap = 1ull << 24;
+    if (const char *s = getenv("TCLUST_CAND_CAP")) cap = std::max<uint64_t>(strtoull(s, nullptr, 10), 1024);
+    if (ctx->cand_cap < cap) {
+        cudaFree(ctx->d_cands); ctx->d_cands = nullptr; ctx->cand_cap = 0;
+        TC_CUDA(cudaMalloc(&ctx->d_cands, cap * sizeof(tc_cand)));
+        ctx->cand_cap = cap;
+    }
+    uint32_t batch = 4096;
+    if (const char *s = getenv("TCLUST_GREEDY_BATCH")) batch = (uint32_t)std::max<long>(atol(s), 32);
+    batch = (batch + TC_GROUP - 1) / TC_GROUP * TC_GROUP;
+
+    tc_rep_table_reset(ctx);
+    std::vector<int32_t> order_of(n, -1);      // representative creation order, -1 = not a representative
+    std::vector<tc_cand> cands;
+    std::vector<uint32_t> start;
+    std::vector<tc_cand> sorted;
+    std::vector<uint32_t> new_reps;
+    uint32_t nrep_total = 0;
+
+    for (uint32_t b0 = 0; b0 < n;) {
+        const uint32_t b1 = std::min<uint64_t>(n, (uint64_t)b0 + batch);
+        TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), st));
+        if (ctx->nrep > 0 && tc_launch_tiles_cands(ctx, b0, b1, 1, cmin_fixed, containment, jmin, 0, 1)) return 1;
+        if (tc_launch_tiles_cands(ctx, b0, b1, 0, cmin_fixed, containment, jmin, 0, 1)) return 1;
+        unsigned long long cnt[2];
+        TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, st));
+        TC_CUDA(cudaStreamSynchronize(st));
+        if (cnt[1] != 0 || cnt[0] > ctx->cand_cap) {
+            TC_CHECK(batch > TC_GROUP, "tc_greedy_cluster: %llu candidates of one 32-genome batch exceed the buffer "
+                     "(%llu); raise TCLUST_CAND_CAP", cnt[0], (unsigned long long)ctx->cand_cap);
+            batch = std::max<uint32_t>(TC_GROUP, batch / 2 / TC_GROUP * TC_GROUP);
+            continue;                                           // redo this batch with a smaller one
+        }
+        cands.resize(cnt[0]);
+        if (cnt[0]) {
+            TC_CUDA(cudaMemcpyAsync(cands.data(), ctx->d_cands, cnt[0] * sizeof(tc_cand), cudaMemcpyDeviceToHost, st));
+            TC_CUDA(cudaStreamSynchronize(st));
+        }
+        // bucket by query (counting sort)
+        const uint32_t nb = b1 - b0;
+        start.assign(nb + 1, 0);
+        for (const tc_cand &c : cands) start[c.query - b0 + 1]++;
+        for (uint32_t i = 0; i < nb; i++) start[i + 1] += start[i];
+        sorted.resize(cands.size());
+        {
+            std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+            for (const tc_cand &c : cands) sorted[fill[c.query - b0]++] = c;
+        }
+        new_reps.clear();
+        for (uint32_t q = b0; q < b1; q++) {
+            tc_cand *lo = sorted.data() + start[q - b0], *hi = sorted.data() + start[q - b0 + 1];
+            // keep candidates that are representatives by now; `touched` order = (first shared query hash,
+            // representative creation order)  -- greedy.cpp:1148-1164
+            tc_cand *end = std::remove_if(lo, hi, [&](const tc_cand &c) { return order_of[c.rep] < 0; });
+            std::sort(lo, end, [&](const tc_cand &a, const tc_cand &b) {
+                if (a.first_hit != b.first_hit) return a.first_hit < b.first_hit;
+                return order_of[a.rep] < order_of[b.rep];
+            });
+            const int size_ref = (int)ctx->h_size[q];
+            int best_common = -1, best_rep = -1;
+            double best_dist = std::numeric_limits<double>::max();
+            for (tc_cand *c = lo; c < end; c++) {
+                const int common = (int)c->common, size_qry = (int)ctx->h_size[c->rep];
+                const int common_min = all_fixed ? cmin_fixed
+                                                 : tc_greedy_common_min(threshold, kmer_size, size_ref, size_qry, containment);
+                if (common < common_min) continue;
+                if (all_fixed) {
+                    if (common > best_common) { best_common = common; best_rep = (int)c->rep; }
+                } else {
+                    const double dist = tc_greedy_dist(common, size_ref, size_qry, containment, kmer_size);
+                    if (dist <= threshold && dist < best_dist) { best_dist = dist; best_common = common; best_rep = (int)c->rep; }
+                }
+            }
+            if (best_rep != -1) {
+                rep_of[q] = best_rep;
+            } else {
+                rep_of[q] = (int32_t)q;
+                order_of[q] = (int32_t)nrep_total++;
+                new_reps.push_back(q);
+            }
+        }
+        if (tc_rep_table_append(ctx, new_reps.data(), (uint32_t)new_reps.size())) return 1;
+        b0 = b1;
+    }
+    if (n_clusters) *n_clusters = nrep_total;
+    return 0;
+}

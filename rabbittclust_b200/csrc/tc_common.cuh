@@ -54,6 +54,22 @@ struct tc_ctx {
     uint64_t n_edges = 0;
     int32_t *d_comp = nullptr;
 
+    // representative table of the greedy scan (K5): same interleaved layout, members in creation order
+    uint32_t nrep = 0;
+    uint32_t *d_rep_gt = nullptr;   uint64_t rep_gt_cap = 0;
+    uint64_t *d_rep_goff = nullptr; uint64_t rep_goff_cap = 0;
+    uint32_t *d_rep_len = nullptr;  uint64_t rep_len_cap = 0;
+    uint32_t *d_rep_ids = nullptr;  uint64_t rep_ids_cap = 0;
+    std::vector<uint32_t> h_rep_ids;
+    std::vector<uint64_t> h_rep_goff = std::vector<uint64_t>(1, 0);
+    tc_cand *d_cands = nullptr;
+    uint64_t cand_cap = 0;
+
+    // KSSD shuffled_dim table (K2), resident once uploaded
+    int32_t *d_kssd_dim = nullptr;
+    const int32_t *kssd_dim_host = nullptr;
+    size_t kssd_dim_n = 0;
+
     // scratch
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -64,4 +80,11 @@ int tc_scratch(tc_ctx *ctx, size_t bytes, void **out);
 // tile-kernel entry points (k3_tile.cu)
 int tc_launch_tiles_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
 int tc_launch_tiles_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts);
+int tc_launch_tiles_rep_matrix(tc_ctx *ctx, uint32_t q0, uint32_t q1, uint32_t *d_common, uint32_t *d_first_hit);
+int tc_launch_tiles_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment,
+                          double jmin, uint32_t part, uint32_t nparts);
+// representative table (k5_greedy.cu)
+void tc_rep_table_free(tc_ctx *ctx);
+void tc_rep_table_reset(tc_ctx *ctx);
+int tc_rep_table_append(tc_ctx *ctx, const uint32_t *ids, uint32_t count);
 int tc_launch_pair_common_ref(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);

@@ -66,6 +66,7 @@ static void free_sketches(tc_ctx *ctx)
     ctx->d_hashes = nullptr; ctx->d_off = nullptr; ctx->d_size = nullptr; ctx->d_ranks = nullptr;
     ctx->d_gt = nullptr; ctx->d_goff = nullptr; ctx->d_edges = nullptr; ctx->d_comp = nullptr;
     ctx->edge_cap = 0; ctx->n_edges = 0; ctx->n = 0; ctx->total = 0; ctx->ngroups = 0;
+    tc_rep_table_reset(ctx);
 }
 
 extern "C" void tc_ctx_destroy(tc_ctx *ctx)
@@ -74,8 +75,10 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_sketches(ctx);
+    tc_rep_table_free(ctx);
     cudaFree(ctx->d_edge_count);
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_kssd_dim);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

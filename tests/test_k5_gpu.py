@@ -1,0 +1,112 @@
+"""GPU parity of the greedy representative scan (K5) against the CPU oracle (oc_greedy_inverted,
+pinned to the reference's clust-greedy -t 1 golden runs) and against those golden runs directly."""
+import os
+
+import numpy as np
+import pytest
+
+from rabbittclust_b200 import sketch_io, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_scan_common_and_first_hit(ctx, oracle):
+    sk = synth.family_sketches(5, 20, s=700, seed=13)
+    sk += synth.family_sketches(3, 10, seed=14, ragged=(50, 3000))
+    sk.append(np.zeros(0, np.uint64))
+    n = len(sk)
+    ctx.upload(sk)
+    reps = [0, 3, 21, 40, 41, 99, 100, 115, 129, n - 1, 7]          # arbitrary order, not sorted
+    common, first = ctx.greedy_scan(10, n, reps)
+    for qi, q in enumerate(range(10, n)):
+        for ri, r in enumerate(reps):
+            c, fh = oracle.intersect(sk[q], sk[r])
+            assert common[qi, ri] == c, (q, r)
+            assert first[qi, ri] == (fh if c else 0xFFFFFFFF), (q, r)
+
+
+def _check_greedy(ctx, oracle, sk, k, thr, contain):
+    ctx.upload(sk)
+    nc, rep = ctx.greedy_cluster(k, thr, contain)
+    nc_o, rep_o = oracle.greedy(sk, k, thr, contain)
+    assert nc == nc_o
+    assert np.array_equal(rep, rep_o)
+    return nc
+
+
+@pytest.mark.parametrize("batch", ["32", "96", "4096"])
+def test_greedy_fixed_size_vs_oracle(ctx, oracle, monkeypatch, batch):
+    monkeypatch.setenv("TCLUST_GREEDY_BATCH", batch)
+    # keep 30-100 % of the pool: some members fall below common_min and found their own clusters
+    sk = synth.family_sketches(12, 25, s=1000, seed=5, keep_lo=0.3, keep_hi=1.0)
+    rng = np.random.default_rng(1)
+    sk = [sk[i] for i in rng.permutation(len(sk))]
+    nc = _check_greedy(ctx, oracle, sk, 21, 0.05, False)
+    assert 12 <= nc < len(sk)
+
+
+@pytest.mark.parametrize("contain", [False, True])
+@pytest.mark.parametrize("batch", ["64", "4096"])
+def test_greedy_ragged_vs_oracle(ctx, oracle, monkeypatch, contain, batch):
+    monkeypatch.setenv("TCLUST_GREEDY_BATCH", batch)
+    sk = synth.family_sketches(10, 20, seed=8, ragged=(100, 4000), keep_lo=0.3, keep_hi=1.0)
+    # greedy --presketched order: size descending (sub_command.cpp:2657-2660)
+    sk = sorted(sk, key=lambda s: -len(s))
+    _check_greedy(ctx, oracle, sk, 21, 0.05, contain)
+
+
+def test_greedy_ties_follow_touched_order(ctx, oracle, monkeypatch):
+    # many exact ties: identical sketches and representatives that share the same number of hashes
+    monkeypatch.setenv("TCLUST_GREEDY_BATCH", "32")
+    rng = np.random.default_rng(3)
+    pool = np.unique(rng.integers(0, 2**62, 3000, dtype=np.uint64))[:2400]
+    a, b, c = pool[:800], pool[800:1600], pool[1600:2400]
+    mk = lambda *parts: np.sort(np.concatenate(parts))
+    sk = [mk(a[:400], b[:400]), mk(a[400:], c[:400]), mk(b[400:], c[400:])]       # three unrelated reps
+    for _ in range(40):
+        x, y = rng.choice(3, 2, replace=False)
+        srcs = [sk[x], sk[y]]
+        sk.append(mk(rng.choice(srcs[0], 400, replace=False), rng.choice(srcs[1], 400, replace=False)))
+        sk.append(sk[-1].copy())
+    _check_greedy(ctx, oracle, sk, 21, 0.05, False)
+    _check_greedy(ctx, oracle, sk, 21, 0.05, True)
+
+
+@pytest.mark.parametrize("tag,contain", [("greedy_list_s", False), ("greedy_list_c", True)])
+def test_greedy_matches_reference_run(ctx, tag, contain):
+    d = os.path.join(GOLD, tag)
+    hs = sketch_io.read_hash_sketch(os.path.join(d, "hash.sketch"))
+    _, info = sketch_io.read_info_sketch(os.path.join(d, "info.sketch"))
+    ctx.upload(hs["sketches"])
+    nc, rep = ctx.greedy_cluster(15, 0.05, contain)
+    ref = sketch_io.parse_cluster_file(os.path.join(d, "clusters.txt"))
+    mine = [[info[r]["name"]] + [info[j]["name"] for j in range(len(rep)) if rep[j] == r and j != r]
+            for r in sorted(set(rep.tolist()))]
+    assert mine == [[n for _, n in c] for c in ref]
+    assert nc == len(ref)
+
+
+@pytest.mark.parametrize("mode,contain", [("mash", False), ("contain", True)])
+def test_greedy_presketched_matches_reference_run(ctx, mode, contain):
+    d = os.path.join(GOLD, "presketched", mode)
+    hs = sketch_io.read_hash_sketch(os.path.join(d, "hash.sketch"))
+    _, info = sketch_io.read_info_sketch(os.path.join(d, "info.sketch"))
+    n = len(info)
+    order = sorted(range(n), key=lambda i: (-info[i]["length"], i))
+    ctx.upload([hs["sketches"][i] for i in order])
+    nc, rep = ctx.greedy_cluster(hs["k"], 0.05, contain)
+    ref = sketch_io.parse_cluster_file(os.path.join(d, "clust-greedy.clusters.txt"))
+    mine = [[info[order[r]]["name"]] + [info[order[j]]["name"] for j in range(n) if rep[j] == r and j != r]
+            for r in sorted(set(rep.tolist()))]
+    assert mine == [[nm for _, nm in c] for c in ref]
+
+
+def test_greedy_large_vs_oracle(ctx, oracle):
+    # 3000 genomes, default batch: several batches, representative table grows across groups
+    h, off = synth.family_sketches_fast(60, 50, s=1000, seed=17)
+    rng = np.random.default_rng(4)
+    perm = rng.permutation(3000)
+    sk = [h[int(off[i]):int(off[i + 1])] for i in perm]
+    nc = _check_greedy(ctx, oracle, sk, 21, 0.05, False)
+    assert nc >= 60
