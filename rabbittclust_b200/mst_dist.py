@@ -1,0 +1,125 @@
+"""Multi-GPU MST build: the tile space of the dense pass is sharded over the ranks of one box and the
+only exchange is the Boruvka min-edge reduction (two all-reduce(MIN) of N u64 words per round).
+
+Replaces compute_minhash_mst / compute_kssd_mst (reference src/MST.cpp:1290-1737, 216-807) for
+world_size > 1.  One process per GPU (torchrun); torch.distributed is plumbing only: the dense pass and
+both reduction phases are the CUDA kernels behind include/tclust.h.  Every rank ends with the same MST.
+
+The per-rank compute is injected (`ops`) so that the host-side logic here -- tile ownership, the
+two-phase min reduction, component relabelling, distance conversion -- is testable on CPU with the gloo
+backend (tests/test_dist_cpu.py supplies an oracle-backed `ops`).
+"""
+import ctypes as C
+
+import numpy as np
+
+U64_MAX = np.uint64(0xFFFFFFFFFFFFFFFF)
+_SIGN = np.int64(-2**63)
+
+
+def tile_owner(t, nparts):
+    """Rank that owns tile t of the row-major lower-triangular 32x32-group tile order (the rule of
+    k3_tile_kernel: the k-th tile a rank fetches is k*nparts + part)."""
+    return t % nparts
+
+
+def owned_pairs(n, part, nparts, group=32):
+    """Number of pairs j<i inside the tiles owned by `part` (mirror of tc_allpairs_pass's n_pairs)."""
+    g = (n + group - 1) // group
+    total, t = 0, 0
+    for r in range(g):
+        nr = min(group, n - r * group)
+        for c in range(r + 1):
+            if t % nparts == part:
+                nc = min(group, n - c * group)
+                total += nr * (nr - 1) // 2 if r == c else nr * nc
+            t += 1
+    return total
+
+
+def allreduce_min_u64(arr, dist=None, device=None):
+    """Element-wise unsigned-64 minimum over all ranks.  NCCL/gloo reduce signed int64, so the sign bit
+    is flipped around the reduction (order-preserving map u64 -> i64)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return arr
+    import torch
+    t = torch.from_numpy((arr.view(np.int64) ^ _SIGN).copy())
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return (t.cpu().numpy() ^ _SIGN).view(np.uint64)
+
+
+class GpuOps:
+    """Boruvka reduction phases of one rank on its GPU (tc_boruvka_* over the rank's candidate edges)."""
+
+    def __init__(self, ctx, containment):
+        import torch
+        import rabbittclust_b200 as T
+        self.T, self.torch, self.ctx, self.containment = T, torch, ctx, int(containment)
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.key = torch.empty(ctx.n, dtype=torch.int64, device=self.dev)
+        self.edge = torch.empty(ctx.n, dtype=torch.int64, device=self.dev)
+
+    def phase1(self, comp):
+        L, T = self.T.lib(), self.T
+        T._chk(L.tc_boruvka_upload_comp(self.ctx._h, comp.ctypes.data_as(C.POINTER(C.c_int32)), len(comp)))
+        T._chk(L.tc_boruvka_phase1(self.ctx._h, self.containment, self.key.data_ptr()))
+        return self.key.cpu().numpy().view(np.uint64)
+
+    def phase2(self, comp, key):
+        L, T = self.T.lib(), self.T
+        self.key.copy_(self.torch.from_numpy(key.view(np.int64)))
+        T._chk(L.tc_boruvka_phase2(self.ctx._h, self.containment, self.key.data_ptr(), self.edge.data_ptr()))
+        return self.edge.cpu().numpy().view(np.uint64)
+
+
+def boruvka(n, ops, dist_from_key, dist=None, device=None, max_rounds=64):
+    """Boruvka over the union of all ranks' candidate edges.  ops.phase1(comp) -> best key per component
+    (u64, U64_MAX = none); ops.phase2(comp, key) -> smallest (i<<32|j) among the edges with that key.
+    Returns the forest as a structured array sorted by (dist, pre, suf) -- identical on every rank."""
+    from . import EDGE_DTYPE
+    parent = np.arange(n, dtype=np.int64)
+
+    def find_all():
+        p = parent
+        while True:
+            q = p[p]
+            if np.array_equal(q, p):
+                return p
+            p = q
+
+    out = []
+    for _ in range(max_rounds):
+        parent[:] = find_all()
+        comp = parent.astype(np.int32)
+        key = allreduce_min_u64(ops.phase1(comp), dist, device)
+        edge = allreduce_min_u64(ops.phase2(comp, key), dist, device)
+        merged = 0
+        for c in np.nonzero(edge != U64_MAX)[0]:
+            i, j = int(edge[c] >> np.uint64(32)), int(edge[c] & np.uint64(0xFFFFFFFF))
+            a, b = i, j
+            while parent[a] != a:
+                a = parent[a]
+            while parent[b] != b:
+                b = parent[b]
+            if a == b:
+                continue
+            parent[a] = b
+            out.append((i, j, dist_from_key(int(key[c]))))
+            merged += 1
+        if not merged:
+            break
+    mst = np.array(out, dtype=EDGE_DTYPE) if out else np.zeros(0, EDGE_DTYPE)
+    return mst[np.lexsort((mst["suf"], mst["pre"], mst["dist"]))]
+
+
+def distributed_mst(ctx, k, threshold, containment=False, dist=None):
+    """Full multi-GPU MST of the sketches uploaded (replicated) on every rank's ctx."""
+    import rabbittclust_b200 as T
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    ctx.allpairs_pass(T.radio(threshold, k), rank, world)
+    ops = GpuOps(ctx, containment)
+    L = T.lib()
+    return boruvka(ctx.n, ops, lambda key: float(L.tc_dist_from_key(key, int(containment), k)), dist, ops.dev)

@@ -1,0 +1,54 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU MST host logic: tile ownership, two-phase all-reduce(MIN)
+Boruvka, host distances.  The per-rank CUDA reductions are replaced by a numpy restatement
+(tests/_dist_worker.py); the result must equal the oracle's MST of the whole set on every rank."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from rabbittclust_b200 import mst_dist, synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("containment", [0, 1])
+def test_two_rank_boruvka_matches_oracle(oracle, tmp_path, containment):
+    port = _free_port()
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "_dist_worker.py"), str(r), "2", str(port),
+                               str(containment), str(tmp_path)]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    if containment:
+        sk = synth.family_sketches(6, 15, seed=21, ragged=(100, 1500))
+    else:
+        sk = synth.family_sketches(7, 14, s=600, seed=20)
+    n = len(sk)
+    ref = oracle.mst(sk, 21, 0.05, bool(containment))
+    m0, m1 = (np.load(tmp_path / ("mst_%d.npy" % r)) for r in range(2))
+    assert np.array_equal(m0, m1), "ranks disagree"
+    assert len(m0) == len(ref)
+    assert np.array_equal(np.sort(m0["dist"]), np.sort(ref["dist"])), "MST weight multiset differs (bit-exact)"
+    nc0, lab0, _ = oracle.clusters_from_mst(m0, n, 0.05)
+    nc1, lab1, _ = oracle.clusters_from_mst(ref, n, 0.05)
+    part = lambda lab: sorted(sorted(np.nonzero(lab == c)[0].tolist()) for c in range(lab.max() + 1))
+    assert nc0 == nc1 and part(lab0) == part(lab1)
+    p0, p1 = (np.load(tmp_path / ("pairs_%d.npy" % r)) for r in range(2))
+    assert p0[0] + p1[0] == n * (n - 1) // 2          # the shards tile the pair space exactly
+    assert p0[1] > 0 and p1[1] > 0
+
+
+def test_owned_pairs_partition():
+    for n in (1, 31, 32, 33, 100, 257):
+        for world in (1, 2, 3, 8):
+            assert sum(mst_dist.owned_pairs(n, r, world) for r in range(world)) == n * (n - 1) // 2

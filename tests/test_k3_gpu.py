@@ -98,3 +98,48 @@ def test_larger_block_against_u64_kernel(ctx):
     assert np.array_equal(a, b)
     assert (np.diag(a) == 1000).all()
     assert a[0, 1] >= 250 and a[0, 60] == 0
+
+
+@pytest.mark.parametrize("containment", [False, True])
+def test_sharded_pass_two_parts_equals_oracle(tc, oracle, containment):
+    """The multi-GPU split on one GPU: two contexts own the tiles of part 0 and part 1; the element-wise
+    minimum of their Boruvka reductions (what the NCCL all-reduce(MIN) computes) yields the reference MST."""
+    from rabbittclust_b200 import mst_dist
+    k, thr = 21, 0.05
+    sk = (synth.family_sketches(8, 12, seed=31, ragged=(100, 2000)) if containment
+          else synth.family_sketches(9, 15, s=800, seed=30))
+    n = len(sk)
+    radio = tc.radio(thr, k)
+    ctxs = [tc.Context(0), tc.Context(0)]
+    try:
+        tot_pairs = 0
+        for part, c in enumerate(ctxs):
+            c.upload(sk)
+            npairs, _ = c.allpairs_pass(radio, part, 2)
+            assert npairs == mst_dist.owned_pairs(n, part, 2)
+            tot_pairs += npairs
+        assert tot_pairs == n * (n - 1) // 2
+        ops = [mst_dist.GpuOps(c, containment) for c in ctxs]
+
+        class Both:
+            def phase1(self, comp):
+                return np.minimum(ops[0].phase1(comp), ops[1].phase1(comp))
+
+            def phase2(self, comp, key):
+                return np.minimum(ops[0].phase2(comp, key), ops[1].phase2(comp, key))
+
+        L = tc.lib()
+        mst = mst_dist.boruvka(n, Both(), lambda key: float(L.tc_dist_from_key(key, int(containment), k)))
+    finally:
+        for c in ctxs:
+            c.close()
+    ref = oracle.mst(sk, k, thr, containment)
+    assert len(mst) == len(ref)
+    assert np.array_equal(np.sort(mst["dist"]), np.sort(ref["dist"]))
+    single = tc.Context(0)
+    try:
+        single.upload(sk)
+        one = mst_dist.distributed_mst(single, k, thr, containment)
+        assert np.array_equal(np.sort(one["dist"]), np.sort(ref["dist"]))
+    finally:
+        single.close()
