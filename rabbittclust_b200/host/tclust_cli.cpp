@@ -1,0 +1,645 @@
+// tclust_cli.cpp -- host side of the drop-in: `clust-mst` and `clust-greedy` (-DGREEDY_CLUST) with the
+// reference's in-scope flags, parameter tuning, on-disk formats and cluster-file output, calling the CUDA
+// hot paths through the C ABI of include/tclust.h.  There is no CPU implementation of the hot paths here.
+//
+// Reference behaviour mirrored (paths relative to the reference root):
+//   options / dispatch        src/main.cpp:75-129,200,255-289,639-671
+//   calSize, tune_parameters  src/SketchInfo.cpp:438-552, src/sub_command.cpp:2383-2467
+//   sketchFiles (list mode)   src/SketchInfo.cpp:865-992      (-c size rule :892-921, -m filter :963)
+//   sketchSequences (-i file) src/SketchInfo.cpp:205-272,741-763; RabbitFX/io/Formater.cpp:87-129
+//   saveSketches/loadSketches src/Sketch_IO.cpp:88-226,284-353,477-560
+//   saveMST/loadMST           src/MST_IO.cpp:47-70,200-217
+//   forest / BFS clusters     src/MST.cpp:77-85,109-142
+//   printResult               src/MST_IO.cpp:136-179
+//   greedy cluster order      src/greedy.cpp:1321-1336,1358-1367
+// Out of scope: --append/--db/--save-rep, tree/linkage output, --dense, dbscan/leiden.
+#include "../../include/tclust.h"
+#include <zlib.h>
+#include <sys/stat.h>
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <queue>
+#include <string>
+#include <thread>
+#include <vector>
+#include <atomic>
+
+using std::cerr;
+using std::endl;
+using std::string;
+using std::vector;
+
+bool path_is_gz(const string &p) { return p.size() >= 2 && p.compare(p.size() - 2, 2, "gz") == 0; }
+
+namespace {
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct Genome {          // SketchInfo (src/SketchInfo.h:23-36) without the owning sketch pointers
+    string file_name;    // list mode
+    string name, comment;  // first record (list mode) or the record (single-file mode)
+    int strand = 0;
+    uint64_t total_len = 0;   // list mode: sum of record lengths; single-file mode: record length
+    vector<uint64_t> hashes;
+    int id = 0;
+};
+
+struct Options {
+    string input = "genome.fna", output = "result.out", folder;
+    int threads = (int)std::thread::hardware_concurrency();
+    bool by_file = false, containment = false, jaccard = false, set_kmer = false, no_save = false, fast = false;
+    bool has_output = false, has_input = false, presketched = false, premsted = false, has_threshold = false;
+    double threshold = 0.05;
+    int kmer = 19, sketch_size = 1000, compress = 1000, drlevel = 3, device = 0;
+    uint64_t min_len = 10000;
+};
+
+[[noreturn]] void die(const string &msg) { cerr << "ERROR: " << msg << endl; exit(1); }
+void tc_or_die(int rc, const char *where) { if (rc) die(string(where) + ", " + tc_last_error()); }
+
+// ------------------------------------------------------------------------------------ FASTA
+struct Record { string name, comment; bool has_comment = false; uint64_t begin = 0, end = 0; };
+
+bool read_whole_gz(const string &path, string &out)
+{
+    gzFile fp = gzopen(path.c_str(), "r");
+    if (!fp) return false;
+    gzbuffer(fp, 1 << 20);
+    out.clear();
+    char buf[1 << 16];
+    int n;
+    while ((n = gzread(fp, buf, sizeof buf)) > 0) out.append(buf, n);
+    gzclose(fp);
+    return true;
+}
+
+// Parse FASTA text; sequence bytes (line breaks removed) are appended to `seq`, records to `recs`.
+// kseq_mode: name ends at the first whitespace, comment = rest of the header line (kseq.h);
+// otherwise RabbitFX's rule: name ends at the first ' ' (Formater.cpp:104-106).
+void parse_fasta(const string &text, bool kseq_mode, vector<uint8_t> &seq, vector<Record> &recs)
+{
+    size_t p = 0, n = text.size();
+    while (p < n && text[p] != '>') {                      // skip anything before the first header
+        const char *nl = (const char *)memchr(text.data() + p, '\n', n - p);
+        if (!nl) return;
+        p = nl - text.data() + 1;
+    }
+    while (p < n) {
+        size_t eol = p;
+        { const char *nl = (const char *)memchr(text.data() + p, '\n', n - p); eol = nl ? (size_t)(nl - text.data()) : n; }
+        size_t hend = eol;
+        if (hend > p && text[hend - 1] == '\r') hend--;
+        Record r;
+        size_t q = p + 1;
+        if (kseq_mode) {
+            while (q < hend && !isspace((unsigned char)text[q])) q++;
+            r.name.assign(text, p + 1, q - p - 1);
+            if (q < hend) { r.comment.assign(text, q + 1, hend - q - 1); r.has_comment = true; }
+        } else {
+            while (q < hend && text[q] != ' ') q++;
+            r.name.assign(text, p + 1, q - p - 1);
+            if (q < hend) { r.comment.assign(text, q + 1, hend - q - 1); r.has_comment = true; }
+        }
+        r.begin = seq.size();
+        p = eol < n ? eol + 1 : n;
+        while (p < n && text[p] != '>') {
+            const char *nl = (const char *)memchr(text.data() + p, '\n', n - p);
+            size_t le = nl ? (size_t)(nl - text.data()) : n;
+            size_t e = le;
+            if (e > p && text[e - 1] == '\r') e--;
+            seq.insert(seq.end(), text.begin() + p, text.begin() + e);
+            p = le < n ? le + 1 : n;
+        }
+        r.end = seq.size();
+        recs.push_back(std::move(r));
+    }
+}
+
+// size of the genome file as the reference sees it (SketchInfo.cpp:453-470,892-915): gz trailer or file bytes
+bool file_size_like_reference(const string &path, uint64_t &size_u64, int &size_int)
+{
+    FILE *fp = fopen(path.c_str(), "r");
+    if (!fp) return false;
+    if (path.size() >= 2 && path.compare(path.size() - 2, 2, "gz") == 0) {
+        int v = 0;
+        fseek(fp, -4, SEEK_END);
+        if (fread(&v, sizeof(int), 1, fp) != 1) v = 0;
+        size_int = v; size_u64 = (uint64_t)(int64_t)v;
+    } else {
+        fseek(fp, 0, SEEK_END);
+        long v = ftell(fp);
+        size_int = (int)v; size_u64 = (uint64_t)v;
+    }
+    fclose(fp);
+    return true;
+}
+
+vector<string> read_list(const string &path)
+{
+    std::ifstream ifs(path);
+    if (!ifs) die("cannot open the inputFile: " + path);
+    vector<string> v;
+    string line;
+    while (getline(ifs, line)) v.push_back(line);
+    return v;
+}
+
+// ------------------------------------------------------------------------ parameter tuning
+void cal_size(const Options &o, uint64_t &max_size, uint64_t &min_size, uint64_t &avg_size)
+{
+    max_size = 0; min_size = (uint64_t)(int64_t)(int)(1u << 31); avg_size = 0;   // reference: `1 << 31` as int
+    uint64_t total = 0; int number = 0, bad = 0;
+    if (o.by_file) {
+        for (const string &line : read_list(o.input)) {
+            uint64_t cur = 0; int dummy = 0;
+            if (path_is_gz(line)) file_size_like_reference(line, cur, dummy);
+            else { struct stat sb; cur = stat(line.c_str(), &sb) == 0 ? (uint64_t)sb.st_size : 0; }
+            if (cur < o.min_len) { bad++; continue; }
+            max_size = std::max(max_size, cur); min_size = std::min(min_size, cur); total += cur; number++;
+        }
+    } else {
+        string text;
+        if (!read_whole_gz(o.input, text)) die("cannot open the genome file, " + o.input);
+        vector<uint8_t> seq; vector<Record> recs;
+        parse_fasta(text, false, seq, recs);
+        max_size = 1;                                        // reference consumer init (SketchInfo.cpp:487)
+        for (const Record &r : recs) {
+            uint64_t len = r.end - r.begin;
+            if (len < o.min_len) { bad++; continue; }
+            max_size = std::max(max_size, len); min_size = std::min(min_size, len); total += len; number++;
+        }
+    }
+    if (number == 0) die("calSize(), no genome passes the minimum length filter");
+    avg_size = total / number;
+    int total_number = number + bad;
+    cerr << "\t===the genome number for clustering is: " << number << endl;
+    cerr << "\t===the genome number below the minimum genome length threshold is: " << bad << endl;
+    cerr << "\t===the total genome number is: " << total_number << endl;
+    if ((double)bad / total_number >= 0.2)
+        fprintf(stderr, "Warning: there are %d poor quality (length < %ld) genome assemblies in the total %d genome assemblied.\n",
+                bad, (long)o.min_len, total_number);
+    cerr << "\t===the totalSize is: " << total << endl;
+    cerr << "\t===the maxSize is: " << max_size << endl;
+    cerr << "\t===the minSize is: " << min_size << endl;
+    cerr << "\t===the averageSize is: " << avg_size << endl;
+}
+
+bool tune_parameters(Options &o)
+{
+    uint64_t max_size, min_size, avg_size;
+    cal_size(o, max_size, min_size, avg_size);
+    if (o.containment && o.jaccard) {
+        cerr << "ERROR: tune_parameters(), conflict distance measurement of Mash distance (fixed-sketch-size) and AAF distance (variable-sketch-size) " << endl;
+        return false;
+    }
+#ifdef GREEDY_CLUST
+    if (!o.containment && !o.jaccard) { o.compress = avg_size / 1000; o.containment = true; }
+    else if (o.containment && avg_size / o.compress < 10) {
+        cerr << "the containCompress " << o.compress << " is too large and the sketch size is too small" << endl;
+        o.compress = avg_size / 1000;
+        cerr << "set the containCompress to: " << o.compress << endl;
+    }
+#endif
+    const double warning_rate = 0.01, recommend_rate = 0.0001;
+    int recommended = ceil(log(max_size * (1 - recommend_rate) / recommend_rate) / log(4));
+    int warning = ceil(log(max_size * (1 - warning_rate) / warning_rate) / log(4));
+    if (!o.set_kmer) o.kmer = recommended;
+    else if (o.kmer < warning) {
+        cerr << "the kmerSize " << o.kmer << " is too small for the maximum genome size of " << max_size << endl;
+        cerr << "replace the kmerSize to the: " << recommended << " for reducing the random collision of kmers" << endl;
+        o.kmer = recommended;
+    } else if (o.kmer > recommended + 3) {
+        cerr << "the kmerSize " << o.kmer << " maybe too large for the maximum genome size of " << max_size << endl;
+        cerr << "replace the kmerSize to the " << recommended << " for increasing the sensitivity of genome comparison" << endl;
+        o.kmer = recommended;
+    }
+    double min_jaccard = !o.containment ? 1.0 / o.sketch_size : 1.0 / (min_size / o.compress);
+    double max_dist = min_jaccard >= 1.0 ? 1.0 : -1.0 / o.kmer * log(2 * min_jaccard / (1.0 + min_jaccard));
+    cerr << "-----the max recommand distance threshold is: " << max_dist << endl;
+    if (o.threshold > max_dist) {
+        cerr << "ERROR: tune_parameters(), the threshold: " << o.threshold << " is out of the valid distance range estimated by Mash distance or AAF distance" << endl;
+        cerr << "Please set a distance threshold with -d option" << endl;
+        return false;
+    }
+    cerr << (o.by_file ? "-----sketch by file!" : "-----sketch by sequence!") << endl;
+    cerr << "-----the kmerSize is: " << o.kmer << endl;
+    cerr << "-----the thread number is: " << o.threads << endl;
+    cerr << "-----the threshold is: " << o.threshold << endl;
+    if (o.containment) cerr << "-----use the AAF distance (variable-sketch-size), the sketchSize is in proportion with 1/" << o.compress << endl;
+    else cerr << "-----use the Mash distance (fixed-sketch-size), the sketchSize is: " << o.sketch_size << endl;
+    return true;
+}
+
+// ---------------------------------------------------------------------------- sketching
+struct Batch {
+    vector<uint8_t> seq; vector<uint64_t> rec_off{0}; vector<uint32_t> rec2genome, ssize;
+    vector<Genome> genomes;
+    void clear() { seq.clear(); rec_off.assign(1, 0); rec2genome.clear(); ssize.clear(); genomes.clear(); }
+};
+
+void flush_batch(tc_ctx *ctx, const Options &o, Batch &b, vector<Genome> &out)
+{
+    if (b.genomes.empty()) return;
+    const uint32_t ng = (uint32_t)b.genomes.size();
+    uint32_t smax = 1;
+    for (uint32_t s : b.ssize) smax = std::max(smax, s);
+    b.seq.resize(b.seq.size() + 64, 0);
+    vector<uint64_t> hashes((size_t)ng * smax);
+    vector<uint32_t> out_n(ng);
+    tc_or_die(tc_sketch_minhash(ctx, b.seq.data(), b.rec_off.data(), b.rec2genome.data(), b.rec2genome.size(), ng, o.kmer,
+                                b.ssize.data(), 42, hashes.data(), smax, out_n.data()), "sketch generation");
+    for (uint32_t g = 0; g < ng; g++) {
+        b.genomes[g].hashes.assign(hashes.begin() + (size_t)g * smax, hashes.begin() + (size_t)g * smax + out_n[g]);
+        out.push_back(std::move(b.genomes[g]));
+    }
+    b.clear();
+}
+
+// list mode: one genome per file (sketchFiles)
+void sketch_files(tc_ctx *ctx, const Options &o, vector<Genome> &out)
+{
+    fprintf(stderr, "-----input fileList, sketch by file\n");
+    vector<string> files = read_list(o.input);
+    const size_t nfiles = files.size();
+    const uint64_t batch_bytes = 1ull << 30;
+    struct Parsed { vector<uint8_t> seq; vector<Record> recs; int file_len = 0; bool ok = false; };
+    size_t next = 0;
+    Batch b;
+    while (next < nfiles) {
+        // read + parse a window of files on the host threads, then append them in list order
+        const size_t win = std::min(nfiles - next, (size_t)std::max(o.threads * 4, 16));
+        vector<Parsed> parsed(win);
+        std::atomic<size_t> cursor{0};
+        auto worker = [&]() {
+            for (;;) {
+                size_t i = cursor.fetch_add(1);
+                if (i >= win) break;
+                string text;
+                if (!read_whole_gz(files[next + i], text)) continue;
+                parse_fasta(text, true, parsed[i].seq, parsed[i].recs);
+                if (o.containment) { uint64_t u; file_size_like_reference(files[next + i], u, parsed[i].file_len); }
+                parsed[i].ok = true;
+            }
+        };
+        vector<std::thread> th;
+        for (int t = 0; t < std::max(1, std::min<int>(o.threads, (int)win)); t++) th.emplace_back(worker);
+        for (auto &t : th) t.join();
+        for (size_t i = 0; i < win; i++) {
+            Parsed &p = parsed[i];
+            if (!p.ok) { fprintf(stderr, "cannot open the genome file: %s\n", files[next + i].c_str()); exit(1); }
+            uint64_t total_len = 0;
+            for (const Record &r : p.recs) total_len += r.end - r.begin;
+            if (total_len < o.min_len) continue;                       // SketchInfo.cpp:963
+            Genome g;
+            g.file_name = files[next + i];
+            g.name = "noName"; g.comment = "noName";                    // :934-939
+            if (!p.recs.empty()) { g.name = p.recs[0].name; if (p.recs[0].has_comment) g.comment = p.recs[0].comment; }
+            g.total_len = total_len;
+            const uint32_t gi = (uint32_t)b.genomes.size();
+            const uint64_t base = b.seq.size();
+            b.seq.insert(b.seq.end(), p.seq.begin(), p.seq.end());
+            for (const Record &r : p.recs) { b.rec_off.push_back(base + r.end); b.rec2genome.push_back(gi); }
+            b.ssize.push_back(o.containment ? (uint32_t)std::max(p.file_len / o.compress, 100) : (uint32_t)o.sketch_size);
+            b.genomes.push_back(std::move(g));
+            if (b.seq.size() >= batch_bytes) flush_batch(ctx, o, b, out);
+        }
+        next += win;
+    }
+    flush_batch(ctx, o, b, out);
+    for (size_t i = 0; i < out.size(); i++) out[i].id = (int)i;
+}
+
+// single-file mode: one genome per record (sketchSequences with the RabbitFX reader)
+void sketch_sequences(tc_ctx *ctx, const Options &o, vector<Genome> &out)
+{
+    fprintf(stderr, "-----input one file, sketch by sequence: \n");
+    string text;
+    if (!read_whole_gz(o.input, text)) die("cannot open the genome file, " + o.input);
+    vector<uint8_t> seq; vector<Record> recs;
+    parse_fasta(text, false, seq, recs);
+    text.clear(); text.shrink_to_fit();
+    Batch b;
+    for (const Record &r : recs) {
+        const uint64_t len = r.end - r.begin;
+        if (len < o.min_len) continue;                                   // SketchInfo.cpp:217
+        Genome g;
+        g.name = r.name; g.comment = r.comment; g.total_len = len;
+        const uint32_t gi = (uint32_t)b.genomes.size();
+        b.seq.insert(b.seq.end(), seq.begin() + r.begin, seq.begin() + r.end);
+        b.rec_off.push_back(b.seq.size()); b.rec2genome.push_back(gi);
+        b.ssize.push_back(o.containment ? (uint32_t)std::max((int)len / o.compress, 100) : (uint32_t)o.sketch_size);
+        b.genomes.push_back(std::move(g));
+        if (b.seq.size() >= (1ull << 30)) flush_batch(ctx, o, b, out);
+    }
+    flush_batch(ctx, o, b, out);
+    for (size_t i = 0; i < out.size(); i++) out[i].id = (int)i;
+}
+
+// ---------------------------------------------------------------------------- on-disk formats
+string current_date_time()
+{
+    time_t now = time(0);
+    struct tm t = *localtime(&now);
+    char buf[80];
+    strftime(buf, sizeof buf, "%Y_%m_%d_%H-%M-%S", &t);
+    return buf;
+}
+
+template <typename T> void wr(FILE *fp, const T &v) { fwrite(&v, sizeof(T), 1, fp); }
+template <typename T> bool rd(FILE *fp, T &v) { return fread(&v, sizeof(T), 1, fp) == 1; }
+
+void save_genome_info(const vector<Genome> &g, const string &folder, const char *type, bool by_file)
+{
+    string path = folder + "/info." + type;
+    FILE *fp = fopen(path.c_str(), "w+");
+    if (!fp) die("save_genome_info(), cannot open the file: " + path);
+    wr(fp, by_file);
+    wr(fp, (size_t)g.size());
+    for (const Genome &x : g) {
+        if (by_file) {
+            wr(fp, (int)x.file_name.size()); wr(fp, (int)x.name.size()); wr(fp, (int)x.comment.size()); wr(fp, x.strand);
+            wr(fp, (uint64_t)x.total_len);
+            fwrite(x.file_name.data(), 1, x.file_name.size(), fp); fwrite(x.name.data(), 1, x.name.size(), fp);
+            fwrite(x.comment.data(), 1, x.comment.size(), fp);
+        } else {
+            wr(fp, (int)x.name.size()); wr(fp, (int)x.comment.size()); wr(fp, x.strand); wr(fp, (int)x.total_len);
+            fwrite(x.name.data(), 1, x.name.size(), fp); fwrite(x.comment.data(), 1, x.comment.size(), fp);
+        }
+    }
+    fclose(fp);
+}
+
+bool load_genome_info(vector<Genome> &g, const string &folder, const char *type)
+{
+    string path = folder + "/info." + type;
+    FILE *fp = fopen(path.c_str(), "r");
+    if (!fp) die("load_genome_info(), cannot open the file: " + path);
+    bool by_file = false; size_t n = 0;
+    if (!rd(fp, by_file) || !rd(fp, n)) die("load_genome_info(), truncated file: " + path);
+    g.resize(n);
+    auto rs = [&](string &s, int len) { s.resize(len); if (len && fread(&s[0], 1, len, fp) != (size_t)len) die("truncated " + path); };
+    for (size_t i = 0; i < n; i++) {
+        Genome &x = g[i];
+        x.id = (int)i;
+        if (by_file) {
+            int lf, ls, lc; uint64_t tot;
+            if (!rd(fp, lf) || !rd(fp, ls) || !rd(fp, lc) || !rd(fp, x.strand) || !rd(fp, tot)) die("truncated " + path);
+            x.total_len = tot; rs(x.file_name, lf); rs(x.name, ls); rs(x.comment, lc);
+        } else {
+            int ls, lc, len;
+            if (!rd(fp, ls) || !rd(fp, lc) || !rd(fp, x.strand) || !rd(fp, len)) die("truncated " + path);
+            x.total_len = (uint64_t)len; rs(x.name, ls); rs(x.comment, lc);
+        }
+    }
+    fclose(fp);
+    return by_file;
+}
+
+void save_sketches(const vector<Genome> &g, const string &folder, const Options &o)
+{
+    save_genome_info(g, folder, "sketch", o.by_file);
+    string path = folder + "/hash.sketch";
+    FILE *fp = fopen(path.c_str(), "w+");
+    if (!fp) die("saveSketch(), cannot open the file: " + path);
+    wr(fp, (int)0); wr(fp, o.kmer); wr(fp, o.containment); wr(fp, o.containment ? o.compress : o.sketch_size);
+    for (const Genome &x : g) { wr(fp, (size_t)x.hashes.size()); fwrite(x.hashes.data(), 8, x.hashes.size(), fp); }
+    fclose(fp);
+    cerr << "-----save the sketches into: " << folder << endl;
+}
+
+bool load_sketches(vector<Genome> &g, const string &folder, Options &o)
+{
+    bool by_file = load_genome_info(g, folder, "sketch");
+    string path = folder + "/hash.sketch";
+    FILE *fp = fopen(path.c_str(), "r");
+    if (!fp) die("loadSketches(), cannot open the file: " + path);
+    int func_id = 0, param = 0;
+    if (!rd(fp, func_id) || func_id != 0) die("loadSketches(), " + path + " does not hold MinHash sketches");
+    if (!rd(fp, o.kmer) || !rd(fp, o.containment) || !rd(fp, param)) die("loadSketches(), truncated " + path);
+    if (o.containment) o.compress = param; else o.sketch_size = param;
+    for (Genome &x : g) {
+        size_t n = 0;
+        if (!rd(fp, n)) die("loadSketches(), truncated " + path);
+        x.hashes.resize(n);
+        if (n && fread(x.hashes.data(), 8, n, fp) != n) die("loadSketches(), truncated " + path);
+    }
+    fclose(fp);
+    return by_file;
+}
+
+void save_mst(const vector<Genome> &g, const vector<tc_edge> &mst, const string &folder, bool by_file)
+{
+    save_genome_info(g, folder, "mst", by_file);
+    string path = folder + "/edge.mst";
+    FILE *fp = fopen(path.c_str(), "w+");
+    if (!fp) die("saveMST(), cannot open the file: " + path);
+    wr(fp, (size_t)mst.size());
+    for (const tc_edge &e : mst) { wr(fp, e.pre); wr(fp, e.suf); wr(fp, e.dist); }
+    fclose(fp);
+    cerr << "-----save the mst into: " << folder << endl;
+}
+
+bool load_mst(vector<Genome> &g, vector<tc_edge> &mst, const string &folder)
+{
+    bool by_file = load_genome_info(g, folder, "mst");
+    string path = folder + "/edge.mst";
+    FILE *fp = fopen(path.c_str(), "r");
+    if (!fp) die("loadMST(), cannot open the file: " + path);
+    size_t n = 0;
+    if (!rd(fp, n)) die("loadMST(), truncated " + path);
+    mst.resize(n);
+    for (tc_edge &e : mst) if (!rd(fp, e.pre) || !rd(fp, e.suf) || !rd(fp, e.dist)) die("loadMST(), truncated " + path);
+    fclose(fp);
+    return by_file;
+}
+
+void print_result(const vector<vector<int>> &cluster, const vector<Genome> &g, bool by_file, const string &out, double threshold)
+{
+    FILE *fp = fopen(out.c_str(), "w");
+    if (!fp) { cerr << "Error in printResult(), cannot open file: " << out << endl; exit(1); }
+    if (threshold >= 0.0) {
+        fprintf(fp, "# Clustering threshold: %.6f\n", threshold);
+        fprintf(fp, "# Total clusters: %zu\n", cluster.size());
+        fprintf(fp, "#\n");
+    }
+    for (size_t i = 0; i < cluster.size(); i++) {
+        fprintf(fp, "the cluster %d is: \n", (int)i);
+        for (size_t j = 0; j < cluster[i].size(); j++) {
+            const int id = cluster[i][j];
+            if (by_file)
+                fprintf(fp, "\t%5d\t%6d\t%12dnt\t%20s\t%20s\t%s\n", (int)j, id, (int)g[id].total_len, g[id].file_name.c_str(),
+                        g[id].name.c_str(), g[id].comment.c_str());
+            else
+                fprintf(fp, "\t%6d\t%6d\t%12dnt\t%20s\t%s\n", (int)j, id, (int)g[id].total_len, g[id].name.c_str(),
+                        g[id].comment.c_str());
+        }
+        fprintf(fp, "\n");
+    }
+    fclose(fp);
+}
+
+// ------------------------------------------------------------------------------- clustering
+void upload(tc_ctx *ctx, const vector<Genome> &g)
+{
+    vector<uint64_t> off(g.size() + 1, 0);
+    for (size_t i = 0; i < g.size(); i++) off[i + 1] = off[i] + g[i].hashes.size();
+    vector<uint64_t> hashes(off.back() + 1);
+    for (size_t i = 0; i < g.size(); i++) std::copy(g[i].hashes.begin(), g[i].hashes.end(), hashes.begin() + off[i]);
+    tc_or_die(tc_sketches_upload(ctx, hashes.data(), off.data(), (uint32_t)g.size()), "sketch upload");
+}
+
+vector<vector<int>> clusters_from_forest(const vector<tc_edge> &mst, double threshold, int vertices)
+{
+    vector<vector<int>> adj(vertices);
+    for (const tc_edge &e : mst)
+        if (e.dist <= threshold) { adj[e.pre].push_back(e.suf); adj[e.suf].push_back(e.pre); }   // generateForest
+    vector<char> visited(vertices, 0);
+    vector<vector<int>> res;
+    for (int i = 0; i < vertices; i++) {                                                        // generateClusterWithBfs
+        if (visited[i]) continue;
+        visited[i] = 1;
+        std::queue<int> q;
+        q.push(i);
+        vector<int> c{i};
+        while (!q.empty()) {
+            int k = q.front(); q.pop();
+            for (int v : adj[k]) if (!visited[v]) { visited[v] = 1; q.push(v); c.push_back(v); }
+        }
+        res.push_back(std::move(c));
+    }
+    return res;
+}
+
+void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_file, bool save, const string &folder)
+{
+    if (g.empty()) die("no sketches to cluster");
+    double t2 = now_s();
+    upload(ctx, g);
+#ifdef GREEDY_CLUST
+    vector<int32_t> rep_of(g.size());
+    uint32_t nclust = 0;
+    tc_or_die(tc_greedy_cluster(ctx, o.kmer, o.containment, o.threshold, rep_of.data(), &nclust), "greedy clustering");
+    vector<vector<int>> cluster;
+    vector<int> cid(g.size(), -1);
+    for (int j = 0; j < (int)g.size(); j++) {
+        if (rep_of[j] == j) { cid[j] = (int)cluster.size(); cluster.push_back({j}); }
+        else cluster[cid[rep_of[j]]].push_back(j);
+    }
+    print_result(cluster, g, by_file, o.output, -1.0);
+    cerr << "-----write the cluster result into: " << o.output << endl;
+    cerr << "-----the cluster number of " << o.output << " is: " << cluster.size() << endl;
+    cerr << "========time of greedyCluster is: " << now_s() - t2 << "========" << endl;
+    (void)save; (void)folder;
+#else
+    vector<tc_edge> mst(g.size());
+    uint64_t m = 0;
+    tc_or_die(tc_mst(ctx, o.kmer, o.containment, o.threshold, mst.data(), &m), "MST generation");
+    mst.resize(m);
+    double t3 = now_s();
+    cerr << "========time of generateMST is: " << t3 - t2 << "========" << endl;
+    if (save) save_mst(g, mst, folder, by_file);
+    vector<vector<int>> cluster = clusters_from_forest(mst, o.threshold, (int)g.size());
+    print_result(cluster, g, by_file, o.output, o.threshold);
+    cerr << "-----write the cluster result into: " << o.output << endl;
+    cerr << "-----the cluster number of: " << o.output << " is: " << cluster.size() << endl;
+#endif
+}
+
+void usage(const char *prog)
+{
+    fprintf(stderr,
+            "usage: %s [-t threads] [-m minLen] [-c containCompress | -s sketchSize] [-k kmerSize] [-l] [-e]\n"
+            "          [-d threshold] -o output (-i input | --presketched DIR"
+#ifndef GREEDY_CLUST
+            " | --premsted DIR"
+#endif
+            ") [--device N]\n", prog);
+}
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    Options o;
+    if (o.threads < 1) o.threads = 1;
+    for (int a = 1; a < argc; a++) {
+        string f = argv[a];
+        auto need = [&](const char *what) -> const char * { if (a + 1 >= argc) die(string("option ") + what + " needs a value"); return argv[++a]; };
+        if (f == "-t" || f == "--threads") o.threads = atoi(need("-t"));
+        else if (f == "-m" || f == "--min-length") { o.min_len = strtoull(need("-m"), nullptr, 10); fprintf(stderr, "-----set the filter minimum length: %ld\n", (long)o.min_len); }
+        else if (f == "-c" || f == "--containment") { o.compress = atoi(need("-c")); o.containment = true;
+            fprintf(stderr, "-----use AAF distance with containment coefficient, the sketch size is in porportion with 1/%d\n", o.compress); }
+        else if (f == "-k" || f == "--kmer-size") { o.kmer = atoi(need("-k")); o.set_kmer = true; fprintf(stderr, "-----set kmerSize: %d\n", o.kmer); }
+        else if (f == "-s" || f == "--sketch-size") { o.sketch_size = atoi(need("-s")); o.jaccard = true; fprintf(stderr, "-----set sketchSize:  %d\n", o.sketch_size); }
+        else if (f == "-l" || f == "--list") o.by_file = true;
+        else if (f == "-e" || f == "--no-save") o.no_save = true;
+        else if (f == "-d" || f == "--threshold") { o.threshold = atof(need("-d")); o.has_threshold = true; fprintf(stderr, "-----set threshold:  %g\n", o.threshold); }
+        else if (f == "-o" || f == "--output") { o.output = need("-o"); o.has_output = true; }
+        else if (f == "-i" || f == "--input") { o.input = need("-i"); o.has_input = true; }
+        else if (f == "--presketched") { o.folder = need("--presketched"); o.presketched = true; }
+#ifndef GREEDY_CLUST
+        else if (f == "--premsted") { o.folder = need("--premsted"); o.premsted = true; }
+#endif
+        else if (f == "--device") o.device = atoi(need("--device"));
+        else if (f == "-h" || f == "--help") { usage(argv[0]); return 0; }
+        else { usage(argv[0]); die("unsupported option " + f + " (see DESIGN.md: out of scope for the B200 hot-path build)"); }
+    }
+    if (!o.has_output) { cerr << "ERROR: option -o/--output is required (unless --buildDB or --stats is used)" << endl; return 1; }
+    if (o.threads < 1) { fprintf(stderr, "-----Invalid thread number %d\n", o.threads); return 1; }
+    fprintf(stderr, "-----set the thread number %d\n", o.threads);
+    if (!o.has_threshold) cerr << "-----use default threshold: " << o.threshold << endl;
+
+#ifndef GREEDY_CLUST
+    if (o.premsted) {                       // clust_from_mst: host only, no GPU needed
+        vector<Genome> g; vector<tc_edge> mst;
+        bool by_file = load_mst(g, mst, o.folder);
+        vector<vector<int>> cluster = clusters_from_forest(mst, o.threshold, (int)g.size());
+        print_result(cluster, g, by_file, o.output, o.threshold);
+        cerr << "-----write the cluster result into: " << o.output << endl;
+        cerr << "-----the cluster number of: " << o.output << " is: " << cluster.size() << endl;
+        return 0;
+    }
+#endif
+    tc_ctx *ctx = nullptr;
+    tc_or_die(tc_ctx_create(o.device, &ctx), "tc_ctx_create");
+    vector<Genome> g;
+    if (o.presketched) {                    // clust_from_sketches (sub_command.cpp:2647-2856)
+        double t0 = now_s();
+        bool by_file = load_sketches(g, o.folder, o);
+        cerr << "-----the size of sketches is: " << g.size() << endl;
+#ifdef GREEDY_CLUST
+        std::sort(g.begin(), g.end(), [](const Genome &a, const Genome &b) {      // cmpGenomeSize / cmpSeqSize
+            if (a.total_len != b.total_len) return a.total_len > b.total_len;
+            return a.id < b.id;
+        });
+#endif
+        cerr << "========time of load genome Infos and sketch Infos is: " << now_s() - t0 << endl;
+        run_clustering(ctx, g, o, by_file, false, o.folder);
+    } else {
+        if (!o.has_input) { usage(argv[0]); die("option -i/--input or --presketched is required"); }
+        if (!tune_parameters(o)) return 1;
+        double t0 = now_s();
+        if (o.by_file) sketch_files(ctx, o, g); else sketch_sequences(ctx, o, g);
+        cerr << "-----the size of sketches (number of genomes or sequences) is: " << g.size() << endl;
+        double t1 = now_s();
+        cerr << "========time of computing sketch is: " << t1 - t0 << "========" << endl;
+        string folder = current_date_time();
+        const bool save = !o.no_save;
+        if (save) {
+            string cmd = "mkdir -p " + folder;
+            if (system(cmd.c_str()) != 0) die("cannot create " + folder);
+            save_sketches(g, folder, o);
+            cerr << "========time of saveSketches is: " << now_s() - t1 << "========" << endl;
+        }
+        run_clustering(ctx, g, o, o.by_file, save, folder);
+    }
+    tc_ctx_destroy(ctx);
+    return 0;
+}

@@ -1,0 +1,130 @@
+"""End-to-end drop-in check: our C++ host binaries (rabbittclust_b200/host/bin/clust-mst, clust-greedy;
+CUDA hot paths through the C ABI) against the UNMODIFIED reference binaries (oracle/_ref, run with -t 1)
+on the same synthetic genome files: sketch folder byte-identical, MST weights bit-identical, same
+partition / same greedy cluster file."""
+import glob
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from rabbittclust_b200 import sketch_io, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "rabbittclust_b200", "host", "bin")
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _need_bins():
+    for p in (os.path.join(OURS, "clust-mst"), os.path.join(OURS, "clust-greedy")):
+        if not os.path.exists(p):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "rabbittclust_b200", "host")])
+    if not os.path.exists(os.path.join(REF, "clust-mst")):
+        pytest.skip("oracle/_ref not built")
+
+
+def _write_fasta(path, records, width=80):
+    op = gzip.open if path.endswith(".gz") else open
+    with op(path, "wb") as f:
+        for name, seq in records:
+            f.write(b">" + name.encode() + b"\n")
+            for i in range(0, len(seq), width):
+                f.write(seq[i:i + width] + b"\n")
+
+
+def _make_genomes(d, n_fam=5, per_fam=6, length=120000, seed=12345):
+    gen = synth.genome_families(n_fam, per_fam, length, seed=seed)
+    rng = np.random.default_rng(seed)
+    files = []
+    for i, g in enumerate(gen):
+        fam, mem = divmod(i, per_fam)
+        # some genomes in two records, some gz, one with lower case and N runs, one without a comment
+        cut = int(rng.integers(length // 3, 2 * length // 3))
+        if i % 3 == 0:
+            recs = [("g%04d_%03d synthetic family %d member %d" % (fam, mem, fam, mem), g[:cut]), ("ctg2 second contig", g[cut:])]
+        elif i % 3 == 1:
+            recs = [("g%04d_%03d" % (fam, mem), g)]
+        else:
+            b = bytearray(g.lower() if i % 2 else g)
+            b[1000:1040] = b"N" * 40
+            recs = [("g%04d_%03d\tfamily %d" % (fam, mem, fam), bytes(b))]
+        p = os.path.join(d, "g%04d_%03d.fna%s" % (fam, mem, ".gz" if i % 4 == 1 else ""))
+        _write_fasta(p, recs)
+        files.append(p)
+    lst = os.path.join(d, "list.txt")
+    open(lst, "w").write("\n".join(files) + "\n")
+    multi = os.path.join(d, "all.fna")
+    _write_fasta(multi, [("seq%d len=%d" % (i, len(g)), g) for i, g in enumerate(gen)])
+    return lst, multi
+
+
+def _run(exe, args, cwd):
+    os.makedirs(cwd, exist_ok=True)
+    r = subprocess.run([exe] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    folders = [p for p in glob.glob(os.path.join(cwd, "20*")) if os.path.isdir(p)]
+    return folders[0] if folders else None, r.stderr.decode()
+
+
+def _partition(path):
+    return sorted(sorted(n for _, n in c) for c in sketch_io.parse_cluster_file(path))
+
+
+def _same_bytes(a, b):
+    return open(a, "rb").read() == open(b, "rb").read()
+
+
+@pytest.fixture(scope="module")
+def genomes(tmp_path_factory):
+    _need_bins()
+    d = str(tmp_path_factory.mktemp("genomes"))
+    return _make_genomes(d)
+
+
+@pytest.mark.parametrize("mode", ["list", "single"])
+@pytest.mark.parametrize("extra", [["-s", "1000"], ["-c", "100"]])
+def test_clust_mst_matches_reference(genomes, tmp_path, mode, extra):
+    lst, multi = genomes
+    inp = ["-l", "-i", lst] if mode == "list" else ["-i", multi]
+    args = inp + ["-k", "21", "-d", "0.05", "-o", "out.txt"] + extra
+    rf, rerr = _run(os.path.join(REF, "clust-mst"), ["-t", "1"] + args, str(tmp_path / "ref"))
+    of, oerr = _run(os.path.join(OURS, "clust-mst"), args, str(tmp_path / "ours"))
+    assert "replace the kmerSize" in rerr and "replace the kmerSize" in oerr          # k override
+    assert _same_bytes(os.path.join(rf, "hash.sketch"), os.path.join(of, "hash.sketch"))
+    assert _same_bytes(os.path.join(rf, "info.sketch"), os.path.join(of, "info.sketch"))
+    assert _same_bytes(os.path.join(rf, "info.mst"), os.path.join(of, "info.mst"))
+    a = sketch_io.read_edge_mst(os.path.join(rf, "edge.mst"))
+    b = sketch_io.read_edge_mst(os.path.join(of, "edge.mst"))
+    assert np.array_equal(np.sort(a["dist"]), np.sort(b["dist"]))
+    ref_out, our_out = str(tmp_path / "ref" / "out.txt"), str(tmp_path / "ours" / "out.txt")
+    assert open(ref_out).read().splitlines()[:3] == open(our_out).read().splitlines()[:3]   # header lines
+    assert _partition(ref_out) == _partition(our_out)
+    # cluster order (by smallest member id) is tree-independent
+    first = lambda p: [c[0][0] for c in sketch_io.parse_cluster_file(p)]
+    assert first(ref_out) == first(our_out)
+    # --presketched and --premsted on the folder the reference wrote
+    _run(os.path.join(OURS, "clust-mst"), ["--presketched", rf, "-d", "0.05", "-o", "pre.txt"], str(tmp_path / "ours"))
+    assert _partition(str(tmp_path / "ours" / "pre.txt")) == _partition(ref_out)
+    _run(os.path.join(OURS, "clust-mst"), ["--premsted", rf, "-d", "0.05", "-o", "mst.txt"], str(tmp_path / "ours"))
+    assert open(str(tmp_path / "ours" / "mst.txt")).read() == open(ref_out).read()   # same tree -> same bytes
+
+
+@pytest.mark.parametrize("mode", ["list", "single"])
+@pytest.mark.parametrize("extra", [["-s", "1000"], ["-c", "100"], []])
+def test_clust_greedy_matches_reference(genomes, tmp_path, mode, extra):
+    lst, multi = genomes
+    inp = ["-l", "-i", lst] if mode == "list" else ["-i", multi]
+    args = inp + ["-k", "21", "-d", "0.05", "-o", "out.txt"] + extra
+    rf, _ = _run(os.path.join(REF, "clust-greedy"), ["-t", "1"] + args, str(tmp_path / "ref"))
+    of, _ = _run(os.path.join(OURS, "clust-greedy"), args, str(tmp_path / "ours"))
+    assert _same_bytes(os.path.join(rf, "hash.sketch"), os.path.join(of, "hash.sketch"))
+    assert _same_bytes(os.path.join(rf, "info.sketch"), os.path.join(of, "info.sketch"))
+    ref_out, our_out = str(tmp_path / "ref" / "out.txt"), str(tmp_path / "ours" / "out.txt")
+    assert open(ref_out).read() == open(our_out).read()          # -t 1 greedy output is fully deterministic
+    # --presketched: both sort by (length desc, id asc) first
+    _run(os.path.join(REF, "clust-greedy"), ["-t", "1", "--presketched", rf, "-d", "0.05", "-o", "pre.txt"], str(tmp_path / "ref"))
+    _run(os.path.join(OURS, "clust-greedy"), ["--presketched", rf, "-d", "0.05", "-o", "pre.txt"], str(tmp_path / "ours"))
+    assert open(str(tmp_path / "ref" / "pre.txt")).read() == open(str(tmp_path / "ours" / "pre.txt")).read()
