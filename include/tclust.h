@@ -104,8 +104,8 @@ int tc_sketches_upload(tc_ctx *ctx, const uint64_t *hashes, const uint64_t *off,
 int tc_sketches_upload_dev(tc_ctx *ctx, const uint64_t *hashes_dev, const uint64_t *off, uint32_t n);
 
 /* validation: common[i-i0][j-j0] = |sketch_i n sketch_j| for i in [i0,i1), j in [j0,j1)
- * (semantic A: the counts of src/MST.cpp:1409-1435).  impl 0 = tiled production kernel,
- * 1 = independent u64 global-memory merge kernel. */
+ * (semantic A: the counts of src/MST.cpp:1409-1435).  impl 0 = tiled merge kernel (k3_tile.cu),
+ * 1 = independent u64 global-memory merge kernel, 2 = hash-join kernel (k3h_join.cu). */
 int tc_pair_common(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1,
                    int impl, uint32_t *out);
 

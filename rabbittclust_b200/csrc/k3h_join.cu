@@ -1,0 +1,342 @@
+// k3h_join.cu -- K3H: all-pairs sketch intersection as a tile-level hash join (HP-2, second
+// generation of the dense pass; same results as k3_tile.cu, several times fewer instructions per pair).
+//
+// Replaces the same reference code as K3 (candidate loop of compute_minhash_mst, src/MST.cpp:1409-1435,
+// 1467-1533, and the pairwise merges of RabbitSketch/src/MinHash.cpp:1199-1643): for every pair (i, j)
+// the exact |A_i n A_j| (semantic A).  The reference's own default path is an inverted index
+// (hash -> genome ids, src/SketchInfo.h:95-161); this kernel is the dense, data-independent GPU form of
+// that idea: an inverted index of only 32 sketches at a time, held in shared memory.
+//
+// Design (DESIGN.md "K3H"):
+//  * a work unit is a row block of 32 sketches x a segment of up to 4096 column sketches.  One persistent
+//    CTA (1024 threads) per SM takes units from an atomic counter; unit u belongs to rank u % nparts.
+//  * the 32 row sketches are cut into P value ranges ("partitions") of at most ~8000 elements each
+//    (pivots = equal-count quantiles of the row block, computed once per upload by k3h_pivot_kernel).
+//    Per partition the CTA builds, in shared memory, an open-addressing table  rank -> 32-bit mask of the
+//    row sketches that contain it  (16384 slots, load <= 0.5) plus a 128-Kbit presence filter.
+//  * the column sketches stream through the table: one warp per column, 32 consecutive elements per step
+//    (one coalesced 128-byte load from the row-major u32 ranks); a lane whose element misses the presence
+//    filter is done after one LDS; hits fetch the mask from the table.  Lane r accumulates count(row r,
+//    column): masks are redistributed with shuffles (few hits) or 32 ballots (many hits).
+//  * between partitions the per-column state (32 counts + stream position) lives in a per-CTA scratch in
+//    global memory (4096 x 33 words = 540 KB per CTA, L2 resident); after the last partition the epilogue
+//    emits the candidate edge / matrix cell.
+//  Units are ordered segment-major, so at any moment all CTAs stream the same 16 MB of column data: the
+//  column stream is served by L2, not HBM.
+#include "tc_common.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int KH_THREADS = 1024;
+constexpr uint32_t KH_SLOTS = 16384;          // table slots (key, mask), 128 KB
+constexpr uint32_t KH_KCAP = 8000;            // max elements of the row block per partition
+constexpr uint32_t KH_FBITS = 17;             // presence filter: 2^17 bits = 16 KB
+constexpr uint32_t KH_FWORDS = (1u << KH_FBITS) / 32;
+constexpr uint32_t KH_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t KH_CSEG = 4096;            // columns per unit
+constexpr uint32_t KH_STATE = 33;             // words of state per column: 32 counts + position
+constexpr size_t KH_SMEM = (size_t)KH_SLOTS * 8 + (size_t)KH_FWORDS * 4;
+
+enum { KH_MODE_MATRIX = 0, KH_MODE_EDGES = 1 };
+
+struct KHArgs {
+    const uint32_t *ranks;
+    const unsigned long long *off;
+    const uint32_t *size;
+    uint32_t n;
+    const uint32_t *pivots;         // interior pivots of row block rb: pivots[pivoff[rb] .. pivoff[rb+1])
+    const uint32_t *pivoff;
+    const tc_kh_unit *units;
+    uint32_t nunits, part, nparts;
+    unsigned long long *counters;   // [0] edge count, [1] overflow, [2] unit counter
+    uint32_t *state;                // gridDim.x * KH_CSEG * KH_STATE words
+    int mode;
+    uint32_t *out; uint32_t i0, i1, j0, j1;
+    tc_pair *edges; unsigned long long edge_cap; int radio;
+};
+
+__device__ __forceinline__ uint32_t kh_fbit(uint32_t x) { return (x * 0x9E3779B1u) >> (32 - KH_FBITS); }
+__device__ __forceinline__ uint32_t kh_slot(uint32_t x) { return (x * 0x85EBCA6Bu) >> 18; }   // 14 bits
+
+// number of elements of the sorted array a[0..len) that are < v, searching from `from`
+__device__ __forceinline__ uint32_t kh_lower_bound(const uint32_t *a, uint32_t from, uint32_t len, uint32_t v)
+{
+    uint32_t lo = from, hi = len;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- pivots: one warp per row block; interior pivot q = smallest v with #(elements < v) >= q*total/P
+__global__ void k3h_pivot_kernel(const uint32_t *ranks, const unsigned long long *off, const uint32_t *size, uint32_t n,
+                                 const uint32_t *pivoff, uint32_t nrb, uint32_t *pivots)
+{
+    const uint32_t rb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (rb >= nrb) return;
+    const uint32_t np = pivoff[rb + 1] - pivoff[rb];
+    if (np == 0) return;
+    const uint32_t id = rb * 32 + lane;
+    const uint32_t len = id < n ? size[id] : 0u;
+    const uint32_t *a = ranks + (id < n ? off[id] : 0ULL);
+    unsigned long long total = len;
+    for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    for (uint32_t q = 1; q <= np; q++) {
+        const unsigned long long target = total * q / (np + 1);
+        uint32_t lo = 0, hi = 0xFFFFFFFEu;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            uint32_t c = kh_lower_bound(a, 0, len, mid);
+            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (c >= target) hi = mid; else lo = mid + 1;
+        }
+        if (lane == 0) pivots[pivoff[rb] + q - 1] = lo;
+    }
+}
+
+__global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
+{
+    extern __shared__ __align__(16) uint8_t kh_smem[];
+    uint2 *table = reinterpret_cast<uint2 *>(kh_smem);
+    uint32_t *filter = reinterpret_cast<uint32_t *>(kh_smem + (size_t)KH_SLOTS * 8);
+    __shared__ uint32_t s_unit, s_next;
+    __shared__ uint32_t s_lo[32], s_hi[32], s_len[32];
+    __shared__ unsigned long long s_base[32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *state = a.state + (size_t)blockIdx.x * KH_CSEG * KH_STATE;
+
+    for (;;) {
+        if (tid == 0) s_unit = (uint32_t)(atomicAdd(&a.counters[2], 1ULL) * a.nparts + a.part);
+        __syncthreads();
+        const uint32_t u = s_unit;
+        if (u >= a.nunits) break;
+        const tc_kh_unit unit = a.units[u];
+        const uint32_t rb = unit.rb, c0 = unit.c0, c1 = unit.c1;
+        const uint32_t piv0 = a.pivoff[rb];
+        const uint32_t P = a.pivoff[rb + 1] - piv0 + 1;
+        if (tid < 32) {
+            const uint32_t id = rb * 32 + tid;
+            s_len[tid] = id < a.n ? a.size[id] : 0u;
+            s_base[tid] = id < a.n ? a.off[id] : 0ULL;
+            s_lo[tid] = 0;
+        }
+        __syncthreads();
+
+        for (uint32_t p = 0; p < P; p++) {
+            const uint32_t piv_hi = (p + 1 == P) ? 0xFFFFFFFFu : a.pivots[piv0 + p];
+            // ---- clear table + filter, find this partition's end in every row
+            {
+                uint4 *t4 = reinterpret_cast<uint4 *>(kh_smem);
+                const uint4 e = make_uint4(KH_EMPTY, 0u, KH_EMPTY, 0u);
+                for (uint32_t i = tid; i < KH_SLOTS / 2; i += KH_THREADS) t4[i] = e;
+                for (uint32_t i = tid; i < KH_FWORDS; i += KH_THREADS) filter[i] = 0u;
+                if (tid < 32) {
+                    const uint32_t *row = a.ranks + s_base[tid];
+                    s_hi[tid] = (p + 1 == P) ? s_len[tid] : kh_lower_bound(row, s_lo[tid], s_len[tid], piv_hi);
+                }
+                if (tid == 0) s_next = c0;
+            }
+            __syncthreads();
+            // ---- build: warp w inserts the partition's elements of row w
+            {
+                const uint32_t *row = a.ranks + s_base[warp];
+                const uint32_t bit = 1u << warp;
+                for (uint32_t e = s_lo[warp] + lane; e < s_hi[warp]; e += 32) {
+                    const uint32_t x = __ldg(row + e);
+                    const uint32_t fb = kh_fbit(x);
+                    atomicOr(&filter[fb >> 5], 1u << (fb & 31));
+                    uint32_t slot = kh_slot(x);
+                    for (;;) {
+                        const uint32_t old = atomicCAS(&table[slot].x, KH_EMPTY, x);
+                        if (old == KH_EMPTY || old == x) { atomicOr(&table[slot].y, bit); break; }
+                        slot = (slot + 1) & (KH_SLOTS - 1);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- stream the columns of the segment through the table, one warp per column
+            for (;;) {
+                uint32_t c = 0;
+                if (lane == 0) c = atomicAdd(&s_next, 1u);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= c1) break;
+                const uint32_t clen = a.size[c];
+                const uint32_t *col = a.ranks + a.off[c];
+                uint32_t *st = state + (size_t)(c - c0) * KH_STATE;
+                uint32_t pos = 0, cnt = 0;
+                if (p > 0) { pos = st[32]; cnt = st[lane]; }
+                uint32_t x = (pos + lane < clen) ? __ldg(col + pos + lane) : 0xFFFFFFFFu;
+                for (;;) {
+                    // speculative next batch (used when this one is consumed completely)
+                    const uint32_t xn = (pos + 32 + lane < clen) ? __ldg(col + pos + 32 + lane) : 0xFFFFFFFFu;
+                    const bool act = x < piv_hi;
+                    uint32_t mask = 0;
+                    if (act) {
+                        const uint32_t fb = kh_fbit(x);
+                        if ((filter[fb >> 5] >> (fb & 31)) & 1u) {
+                            uint32_t slot = kh_slot(x);
+                            for (;;) {
+                                const uint2 e = table[slot];
+                                if (e.x == x) { mask = e.y; break; }
+                                if (e.x == KH_EMPTY) break;
+                                slot = (slot + 1) & (KH_SLOTS - 1);
+                            }
+                        }
+                    }
+                    unsigned hit = __ballot_sync(0xffffffffu, mask != 0u);
+                    if (hit) {
+                        if (__popc(hit) <= 16) {
+                            while (hit) {
+                                const int src = __ffs(hit) - 1;
+                                const uint32_t m = __shfl_sync(0xffffffffu, mask, src);
+                                cnt += (m >> lane) & 1u;
+                                hit &= hit - 1;
+                            }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 32; r++) {
+                                const unsigned b = __ballot_sync(0xffffffffu, (mask >> r) & 1u);
+                                if (lane == r) cnt += __popc(b);
+                            }
+                        }
+                    }
+                    const uint32_t nact = __popc(__ballot_sync(0xffffffffu, act));
+                    pos += nact;
+                    if (nact < 32) break;
+                    x = xn;
+                }
+                if (p + 1 < P) {
+                    st[lane] = cnt;
+                    if (lane == 0) st[32] = pos;
+                } else {
+                    // ---- epilogue: lane r holds |row r n column c|
+                    const uint32_t i = rb * 32 + lane, j = c;
+                    if (a.mode == KH_MODE_MATRIX) {
+                        if (i >= a.i0 && i < a.i1 && j >= a.j0 && j < a.j1)
+                            a.out[(size_t)(i - a.i0) * (a.j1 - a.j0) + (j - a.j0)] = cnt;
+                    } else {
+                        bool keep = false;
+                        if (i < a.n && j < i && cnt >= 1u) {
+                            const uint32_t s0 = s_len[lane], s1 = clen;
+                            const uint32_t mn = min(s0, s1), mx = max(s0, s1);
+                            // reference: skip if max_size > radio * min_size (int arithmetic), MST.cpp:1481-1487
+                            keep = mn > 0 && !((long long)mx > (long long)a.radio * (long long)mn);
+                        }
+                        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+                        if (ballot) {
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)__popc(ballot));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (keep) {
+                                const unsigned long long idx = base + __popc(ballot & ((1u << lane) - 1));
+                                if (idx < a.edge_cap) {
+                                    tc_pair e; e.i = i; e.j = j; e.common = cnt;
+                                    a.edges[idx] = e;
+                                } else {
+                                    a.counters[1] = 1ULL;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < 32) s_lo[tid] = s_hi[tid];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+// ---- per-upload setup: partition pivots of every row block
+int tc_kh_prepare(tc_ctx *ctx)
+{
+    cudaFree(ctx->d_kh_pivots); cudaFree(ctx->d_kh_pivoff);
+    ctx->d_kh_pivots = nullptr; ctx->d_kh_pivoff = nullptr;
+    const uint32_t nrb = (ctx->n + 31) / 32;
+    std::vector<uint32_t> pivoff(nrb + 1, 0);
+    for (uint32_t rb = 0; rb < nrb; rb++) {
+        uint64_t total = 0;
+        for (uint32_t l = 0; l < 32 && rb * 32 + l < ctx->n; l++) total += ctx->h_size[rb * 32 + l];
+        const uint32_t P = (uint32_t)std::max<uint64_t>(1, (total + (KH_KCAP - 64) - 1) / (KH_KCAP - 64));
+        pivoff[rb + 1] = pivoff[rb] + (P - 1);
+    }
+    TC_CUDA(cudaMalloc(&ctx->d_kh_pivoff, (size_t)(nrb + 1) * 4));
+    TC_CUDA(cudaMalloc(&ctx->d_kh_pivots, std::max<size_t>(pivoff[nrb], 1) * 4));
+    TC_CUDA(cudaMemcpyAsync(ctx->d_kh_pivoff, pivoff.data(), (size_t)(nrb + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (pivoff[nrb] > 0) {
+        const unsigned blocks = (unsigned)(((uint64_t)nrb * 32 + 255) / 256);
+        k3h_pivot_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
+                                                          ctx->d_size, ctx->n, ctx->d_kh_pivoff, nrb, ctx->d_kh_pivots);
+        ctx->launches++;
+        TC_CUDA(cudaGetLastError());
+    }
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));   // pivoff (host vector) must outlive the copy
+    return 0;
+}
+
+static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &units)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        TC_CUDA(cudaFuncSetAttribute(k3h_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KH_SMEM));
+        attr_set = true;
+    }
+    if (units.empty()) return 0;
+    if (units.size() > ctx->kh_units_cap) {
+        cudaFree(ctx->d_kh_units); ctx->d_kh_units = nullptr; ctx->kh_units_cap = 0;
+        TC_CUDA(cudaMalloc(&ctx->d_kh_units, units.size() * sizeof(tc_kh_unit)));
+        ctx->kh_units_cap = units.size();
+    }
+    TC_CUDA(cudaMemcpyAsync(ctx->d_kh_units, units.data(), units.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice,
+                            ctx->stream));
+    const long long mine = ((long long)units.size() - a.part + a.nparts - 1) / a.nparts;
+    if (mine <= 0) { TC_CUDA(cudaStreamSynchronize(ctx->stream)); return 0; }
+    const int grid = (int)std::min<long long>(mine, ctx->num_sms);
+    if (!ctx->d_kh_state) TC_CUDA(cudaMalloc(&ctx->d_kh_state, (size_t)ctx->num_sms * KH_CSEG * KH_STATE * 4));
+    a.ranks = ctx->d_ranks; a.off = reinterpret_cast<const unsigned long long *>(ctx->d_off); a.size = ctx->d_size;
+    a.n = ctx->n; a.pivots = ctx->d_kh_pivots; a.pivoff = ctx->d_kh_pivoff;
+    a.units = ctx->d_kh_units; a.nunits = (uint32_t)units.size();
+    a.counters = ctx->d_edge_count; a.state = ctx->d_kh_state;
+    TC_CUDA(cudaMemsetAsync(ctx->d_edge_count + 2, 0, sizeof(unsigned long long), ctx->stream));
+    k3h_join_kernel<<<grid, KH_THREADS, KH_SMEM, ctx->stream>>>(a);
+    ctx->launches++;
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));   // `units` (host) must outlive the copy
+    return 0;
+}
+
+int tc_launch_join_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out)
+{
+    std::vector<tc_kh_unit> units;
+    for (uint32_t c0 = j0; c0 < j1; c0 += KH_CSEG)
+        for (uint32_t rb = i0 / 32; rb * 32 < i1; rb++) units.push_back(tc_kh_unit{rb, c0, std::min(j1, c0 + KH_CSEG)});
+    KHArgs a{};
+    a.mode = KH_MODE_MATRIX; a.part = 0; a.nparts = 1;
+    a.out = d_out; a.i0 = i0; a.i1 = i1; a.j0 = j0; a.j1 = j1;
+    return kh_launch(ctx, a, units);
+}
+
+int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts)
+{
+    // pairs (i, j < i): row block rb needs the columns [0, rb*32+31); units segment-major so that all CTAs
+    // stream the same column segment at the same time (L2 reuse)
+    const uint32_t n = ctx->n, nrb = (n + 31) / 32;
+    if (ctx->kh_edge_units_n != n) {
+        ctx->kh_edge_units.clear();
+        for (uint32_t c0 = 0; c0 < n; c0 += KH_CSEG)
+            for (uint32_t rb = c0 / 32; rb < nrb; rb++) {
+                const uint32_t c1 = std::min<uint32_t>(std::min(n, c0 + KH_CSEG), rb * 32 + 31);
+                if (c1 > c0) ctx->kh_edge_units.push_back(tc_kh_unit{rb, c0, c1});
+            }
+        ctx->kh_edge_units_n = n;
+    }
+    KHArgs a{};
+    a.mode = KH_MODE_EDGES; a.part = part; a.nparts = nparts ? nparts : 1;
+    a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
+    return kh_launch(ctx, a, ctx->kh_edge_units);
+}

@@ -28,6 +28,8 @@ constexpr uint32_t TC_SENT_A = 0xFFFFFFFFu;  // end-of-window sentinel, row stre
 constexpr uint32_t TC_SENT_B = 0xFFFFFFFEu;  // end-of-window sentinel, column streams
 constexpr uint32_t TC_RANK_MAX = 0xFFFFFFFDu;
 
+struct tc_kh_unit { uint32_t rb, c0, c1; };   // K3H work unit: row block x column segment [c0, c1)
+
 struct tc_ctx {
     int device = 0;
     int num_sms = 0;
@@ -65,6 +67,13 @@ struct tc_ctx {
     tc_cand *d_cands = nullptr;
     uint64_t cand_cap = 0;
 
+    // hash-join pass (K3H): partition pivots per row block, unit list, per-CTA column state
+    uint32_t *d_kh_pivots = nullptr, *d_kh_pivoff = nullptr, *d_kh_state = nullptr;
+    tc_kh_unit *d_kh_units = nullptr;
+    size_t kh_units_cap = 0;
+    std::vector<tc_kh_unit> kh_edge_units;
+    uint32_t kh_edge_units_n = 0;
+
     // KSSD shuffled_dim table (K2), resident once uploaded
     int32_t *d_kssd_dim = nullptr;
     const int32_t *kssd_dim_host = nullptr;
@@ -83,6 +92,10 @@ int tc_launch_tiles_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts
 int tc_launch_tiles_rep_matrix(tc_ctx *ctx, uint32_t q0, uint32_t q1, uint32_t *d_common, uint32_t *d_first_hit);
 int tc_launch_tiles_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment,
                           double jmin, uint32_t part, uint32_t nparts);
+// hash-join pass (k3h_join.cu)
+int tc_kh_prepare(tc_ctx *ctx);
+int tc_launch_join_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
+int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts);
 // representative table (k5_greedy.cu)
 void tc_rep_table_free(tc_ctx *ctx);
 void tc_rep_table_reset(tc_ctx *ctx);

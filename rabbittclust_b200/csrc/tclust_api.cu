@@ -63,6 +63,8 @@ static void free_sketches(tc_ctx *ctx)
 {
     cudaFree(ctx->d_hashes); cudaFree(ctx->d_off); cudaFree(ctx->d_size); cudaFree(ctx->d_ranks);
     cudaFree(ctx->d_gt); cudaFree(ctx->d_goff); cudaFree(ctx->d_edges); cudaFree(ctx->d_comp);
+    cudaFree(ctx->d_kh_pivots); cudaFree(ctx->d_kh_pivoff);
+    ctx->d_kh_pivots = nullptr; ctx->d_kh_pivoff = nullptr; ctx->kh_edge_units.clear(); ctx->kh_edge_units_n = 0;
     ctx->d_hashes = nullptr; ctx->d_off = nullptr; ctx->d_size = nullptr; ctx->d_ranks = nullptr;
     ctx->d_gt = nullptr; ctx->d_goff = nullptr; ctx->d_edges = nullptr; ctx->d_comp = nullptr;
     ctx->edge_cap = 0; ctx->n_edges = 0; ctx->n = 0; ctx->total = 0; ctx->ngroups = 0;
@@ -79,6 +81,7 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     cudaFree(ctx->d_edge_count);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_kssd_dim);
+    cudaFree(ctx->d_kh_state); cudaFree(ctx->d_kh_units);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -205,7 +208,7 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     }
     TC_CUDA(cudaGetLastError());
     TC_CUDA(cudaStreamSynchronize(st));
-    return 0;
+    return tc_kh_prepare(ctx);
 }
 
 extern "C" int tc_sketches_upload(tc_ctx *ctx, const uint64_t *hashes, const uint64_t *off, uint32_t n)
@@ -228,6 +231,7 @@ extern "C" int tc_pair_common(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0
     uint32_t *d_out = nullptr;
     TC_CUDA(cudaMalloc(&d_out, cells * 4));
     int rc = impl == 0 ? tc_launch_tiles_matrix(ctx, i0, i1, j0, j1, d_out)
+           : impl == 2 ? tc_launch_join_matrix(ctx, i0, i1, j0, j1, d_out)
                        : tc_launch_pair_common_ref(ctx, i0, i1, j0, j1, d_out);
     if (!rc) {
         cudaError_t e = cudaMemcpyAsync(out, d_out, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -263,7 +267,10 @@ extern "C" int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t 
     if (ensure_edges(ctx)) return 1;
     // a pass restarts the candidate list
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    if (tc_launch_tiles_edges(ctx, radio, part, nparts)) return 1;
+    // TCLUST_PASS_IMPL=merge selects the first-generation tiled merge kernel (k3_tile.cu)
+    const char *impl = getenv("TCLUST_PASS_IMPL");
+    const bool use_merge = impl && !strcmp(impl, "merge");
+    if (use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts) : tc_launch_join_edges(ctx, radio, part, nparts)) return 1;
     unsigned long long cnt[2];
     TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -273,10 +280,10 @@ extern "C" int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t 
     ctx->n_edges = cnt[0];
     if (n_edges) *n_edges = cnt[0];
     if (n_pairs) {
-        // pairs j<i inside the tiles owned by this part
-        const uint64_t G = ctx->ngroups;
         if (nparts == 1) *n_pairs = (uint64_t)ctx->n * (ctx->n - 1) / 2;
-        else {
+        else if (use_merge) {
+            // pairs j<i inside the tiles owned by this part
+            const uint64_t G = ctx->ngroups;
             uint64_t p = 0, t = 0;
             for (uint64_t r = 0; r < G; r++)
                 for (uint64_t c = 0; c <= r; c++, t++) {
@@ -285,6 +292,17 @@ extern "C" int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t 
                     const uint64_t nc = std::min<uint64_t>(TC_GROUP, ctx->n - c * TC_GROUP);
                     p += r == c ? nr * (nr - 1) / 2 : nr * nc;
                 }
+            *n_pairs = p;
+        } else {
+            // pairs j<i inside the (row block x column segment) units owned by this part
+            uint64_t p = 0;
+            for (size_t u = part; u < ctx->kh_edge_units.size(); u += nparts) {
+                const tc_kh_unit &un = ctx->kh_edge_units[u];
+                for (uint64_t i = (uint64_t)un.rb * 32; i < std::min<uint64_t>(ctx->n, (uint64_t)un.rb * 32 + 32); i++) {
+                    const uint64_t hi = std::min<uint64_t>(un.c1, i);
+                    if (hi > un.c0) p += hi - un.c0;
+                }
+            }
             *n_pairs = p;
         }
     }

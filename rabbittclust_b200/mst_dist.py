@@ -23,10 +23,32 @@ def tile_owner(t, nparts):
     return t % nparts
 
 
-def owned_pairs(n, part, nparts, group=32):
-    """Number of pairs j<i inside the tiles owned by `part` (mirror of tc_allpairs_pass's n_pairs)."""
+def join_units(n, cseg=4096):
+    """Work units of the hash-join dense pass (k3h_join.cu: tc_launch_join_edges): row block rb x column
+    segment [c0, c1), segment-major.  Unit u belongs to rank u % nparts."""
+    nrb = (n + 31) // 32
+    units = []
+    for c0 in range(0, n, cseg):
+        for rb in range(c0 // 32, nrb):
+            c1 = min(n, c0 + cseg, rb * 32 + 31)
+            if c1 > c0:
+                units.append((rb, c0, c1))
+    return units
+
+
+def owned_pairs(n, part, nparts, impl="join", group=32):
+    """Number of pairs j<i owned by `part` (mirror of tc_allpairs_pass's n_pairs) for the hash-join pass
+    (units) or the first-generation merge pass (32x32 tiles, TCLUST_PASS_IMPL=merge)."""
+    total = 0
+    if impl == "join":
+        for u, (rb, c0, c1) in enumerate(join_units(n)):
+            if u % nparts != part:
+                continue
+            for i in range(rb * 32, min(n, rb * 32 + 32)):
+                total += max(0, min(c1, i) - c0)
+        return total
     g = (n + group - 1) // group
-    total, t = 0, 0
+    t = 0
     for r in range(g):
         nr = min(group, n - r * group)
         for c in range(r + 1):

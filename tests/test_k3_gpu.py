@@ -14,8 +14,10 @@ def _check_matrix(ctx, oracle, sketches):
     want = oracle.common_matrix(sketches)
     got_ref = ctx.pair_common(0, n, 0, n, impl=1)
     got = ctx.pair_common(0, n, 0, n, impl=0)
+    got_join = ctx.pair_common(0, n, 0, n, impl=2)
     assert np.array_equal(got_ref, want), "u64 global-merge kernel differs from oracle"
-    assert np.array_equal(got, want), "tiled kernel differs from oracle"
+    assert np.array_equal(got, want), "tiled merge kernel differs from oracle"
+    assert np.array_equal(got_join, want), "hash-join kernel differs from oracle"
 
 
 def test_common_fixed_size(ctx, oracle):
@@ -48,12 +50,30 @@ def test_common_subrange(ctx, oracle):
     sk = synth.family_sketches(4, 25, s=500, seed=11)
     ctx.upload(sk)
     want = oracle.common_matrix(sk)
-    got = ctx.pair_common(37, 91, 3, 66, impl=0)
-    assert np.array_equal(got, want[37:91, 3:66])
+    for impl in (0, 2):
+        got = ctx.pair_common(37, 91, 3, 66, impl=impl)
+        assert np.array_equal(got, want[37:91, 3:66]), impl
 
 
+def test_join_many_segments_and_partitions(ctx):
+    """9000 sketches: three column segments per row block; ragged sizes up to 20000 give row blocks with
+    dozens of table partitions.  Hash-join kernel against the independent u64 kernel."""
+    rng = np.random.default_rng(12)
+    h, off = synth.family_sketches_fast(180, 50, s=300, seed=6)
+    sk = [h[int(off[i]):int(off[i + 1])] for i in range(9000)]
+    for i in rng.integers(0, 9000, 40):
+        sk[i] = np.unique(np.concatenate([sk[i], rng.integers(0, 2**64 - 4, int(rng.integers(2000, 20000)), dtype=np.uint64)]))
+    ctx.upload(sk)
+    for (i0, i1, j0, j1) in [(0, 64, 0, 9000), (4000, 4100, 3000, 9000), (8950, 9000, 0, 9000)]:
+        a = ctx.pair_common(i0, i1, j0, j1, impl=2)
+        b = ctx.pair_common(i0, i1, j0, j1, impl=1)
+        assert np.array_equal(a, b), (i0, i1, j0, j1)
+
+
+@pytest.mark.parametrize("pass_impl", ["join", "merge"])
 @pytest.mark.parametrize("containment", [False, True])
-def test_dense_pass_edges_and_mst(ctx, oracle, tc, containment):
+def test_dense_pass_edges_and_mst(ctx, oracle, tc, containment, pass_impl, monkeypatch):
+    monkeypatch.setenv("TCLUST_PASS_IMPL", pass_impl)
     k, thr = 21, 0.05
     if containment:
         sk = synth.family_sketches(8, 12, seed=21, ragged=(100, 2000))
@@ -95,7 +115,9 @@ def test_larger_block_against_u64_kernel(ctx):
     ctx.upload(hashes=h, off=off)
     a = ctx.pair_common(0, 1500, 0, 1500, impl=0)
     b = ctx.pair_common(0, 1500, 0, 1500, impl=1)
+    c = ctx.pair_common(0, 1500, 0, 1500, impl=2)
     assert np.array_equal(a, b)
+    assert np.array_equal(c, b)
     assert (np.diag(a) == 1000).all()
     assert a[0, 1] >= 250 and a[0, 60] == 0
 
@@ -116,7 +138,7 @@ def test_sharded_pass_two_parts_equals_oracle(tc, oracle, containment):
         for part, c in enumerate(ctxs):
             c.upload(sk)
             npairs, _ = c.allpairs_pass(radio, part, 2)
-            assert npairs == mst_dist.owned_pairs(n, part, 2)
+            assert npairs == mst_dist.owned_pairs(n, part, 2, impl="join")
             tot_pairs += npairs
         assert tot_pairs == n * (n - 1) // 2
         ops = [mst_dist.GpuOps(c, containment) for c in ctxs]
