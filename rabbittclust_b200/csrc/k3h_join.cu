@@ -30,7 +30,7 @@ namespace {
 
 constexpr int KH_THREADS = 1024;
 constexpr uint32_t KH_SLOTS = 16384;          // table slots (key, mask), 128 KB
-constexpr uint32_t KH_KCAP = 8000;            // max elements of the row block per partition
+constexpr uint32_t KH_KCAP = 8256;            // max elements of the row block per partition (32 x 1000 -> 4 partitions)
 constexpr uint32_t KH_FBITS = 17;             // presence filter: 2^17 bits = 16 KB
 constexpr uint32_t KH_FWORDS = (1u << KH_FBITS) / 32;
 constexpr uint32_t KH_EMPTY = 0xFFFFFFFFu;
@@ -58,6 +58,18 @@ struct KHArgs {
 
 __device__ __forceinline__ uint32_t kh_fbit(uint32_t x) { return (x * 0x9E3779B1u) >> (32 - KH_FBITS); }
 __device__ __forceinline__ uint32_t kh_slot(uint32_t x) { return (x * 0x85EBCA6Bu) >> 18; }   // 14 bits
+__device__ __forceinline__ uint32_t kh_lds(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 kh_lds2(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
 
 // number of elements of the sorted array a[0..len) that are < v, searching from `from`
 __device__ __forceinline__ uint32_t kh_lower_bound(const uint32_t *a, uint32_t from, uint32_t len, uint32_t v)
@@ -106,6 +118,8 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
     __shared__ unsigned long long s_base[32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(table);
+    const uint32_t filt_addr = (uint32_t)__cvta_generic_to_shared(filter);
     uint32_t *state = a.state + (size_t)blockIdx.x * KH_CSEG * KH_STATE;
 
     for (;;) {
@@ -157,7 +171,8 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                 }
             }
             __syncthreads();
-            // ---- stream the columns of the segment through the table, one warp per column
+            // ---- stream the columns of the segment through the table, one warp per column, 128 elements
+            //      (4 coalesced 128-byte loads) per step; the next step's loads are issued before the probes
             for (;;) {
                 uint32_t c = 0;
                 if (lane == 0) c = atomicAdd(&s_next, 1u);
@@ -168,45 +183,76 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                 uint32_t *st = state + (size_t)(c - c0) * KH_STATE;
                 uint32_t pos = 0, cnt = 0;
                 if (p > 0) { pos = st[32]; cnt = st[lane]; }
-                uint32_t x = (pos + lane < clen) ? __ldg(col + pos + lane) : 0xFFFFFFFFu;
-                for (;;) {
-                    // speculative next batch (used when this one is consumed completely)
-                    const uint32_t xn = (pos + 32 + lane < clen) ? __ldg(col + pos + 32 + lane) : 0xFFFFFFFFu;
-                    const bool act = x < piv_hi;
-                    uint32_t mask = 0;
-                    if (act) {
-                        const uint32_t fb = kh_fbit(x);
-                        if ((filter[fb >> 5] >> (fb & 31)) & 1u) {
-                            uint32_t slot = kh_slot(x);
-                            for (;;) {
-                                const uint2 e = table[slot];
-                                if (e.x == x) { mask = e.y; break; }
-                                if (e.x == KH_EMPTY) break;
-                                slot = (slot + 1) & (KH_SLOTS - 1);
-                            }
-                        }
-                    }
-                    unsigned hit = __ballot_sync(0xffffffffu, mask != 0u);
-                    if (hit) {
-                        if (__popc(hit) <= 16) {
-                            while (hit) {
-                                const int src = __ffs(hit) - 1;
-                                const uint32_t m = __shfl_sync(0xffffffffu, mask, src);
-                                cnt += (m >> lane) & 1u;
-                                hit &= hit - 1;
-                            }
-                        } else {
+                uint32_t x[4], xn[4];
 #pragma unroll
-                            for (int r = 0; r < 32; r++) {
-                                const unsigned b = __ballot_sync(0xffffffffu, (mask >> r) & 1u);
-                                if (lane == r) cnt += __popc(b);
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t idx = pos + lane + 32 * k;
+                    x[k] = idx < clen ? __ldg(col + idx) : 0xFFFFFFFFu;
+                }
+                for (;;) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t idx = pos + 128 + lane + 32 * k;
+                        xn[k] = idx < clen ? __ldg(col + idx) : 0xFFFFFFFFu;
+                    }
+                    uint32_t mask[4];
+                    uint32_t fw[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {              // presence filter: 4 independent LDS
+                        const uint32_t fb = kh_fbit(x[k]);
+                        fw[k] = kh_lds(filt_addr + ((fb >> 5) << 2)) >> (fb & 31);
+                    }
+                    bool maybe = false;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        mask[k] = 0u;
+                        fw[k] = (fw[k] & 1u) && x[k] < piv_hi;
+                        maybe |= fw[k] != 0u;
+                    }
+                    if (maybe) {                               // table lookups for the filter hits
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            if (fw[k]) {
+                                uint32_t slot = kh_slot(x[k]);
+                                for (;;) {
+                                    const uint2 e = kh_lds2(tab_addr + slot * 8);
+                                    if (e.x == x[k]) { mask[k] = e.y; break; }
+                                    if (e.x == KH_EMPTY) break;
+                                    slot = (slot + 1) & (KH_SLOTS - 1);
+                                }
                             }
                         }
                     }
-                    const uint32_t nact = __popc(__ballot_sync(0xffffffffu, act));
-                    pos += nact;
-                    if (nact < 32) break;
-                    x = xn;
+                    if (__ballot_sync(0xffffffffu, (mask[0] | mask[1] | mask[2] | mask[3]) != 0u)) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            unsigned hit = __ballot_sync(0xffffffffu, mask[k] != 0u);
+                            if (__popc(hit) <= 16) {
+                                while (hit) {
+                                    const int src = __ffs(hit) - 1;
+                                    const uint32_t m = __shfl_sync(0xffffffffu, mask[k], src);
+                                    cnt += (m >> lane) & 1u;
+                                    hit &= hit - 1;
+                                }
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < 32; r++) {
+                                    const unsigned b = __ballot_sync(0xffffffffu, (mask[k] >> r) & 1u);
+                                    if (lane == r) cnt += __popc(b);
+                                }
+                            }
+                        }
+                    }
+                    // sorted stream: the step is consumed completely iff its last element is in the partition
+                    if (__shfl_sync(0xffffffffu, x[3], 31) < piv_hi) {
+                        pos += 128;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) x[k] = xn[k];
+                        continue;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) pos += __popc(__ballot_sync(0xffffffffu, x[k] < piv_hi));
+                    break;
                 }
                 if (p + 1 < P) {
                     st[lane] = cnt;
