@@ -31,7 +31,7 @@ namespace {
 constexpr int KH_THREADS = 1024;
 constexpr uint32_t KH_SLOTS = 16384;          // table slots (key, mask), 128 KB
 constexpr uint32_t KH_KCAP = 8256;            // max elements of the row block per partition (32 x 1000 -> 4 partitions)
-constexpr uint32_t KH_FBITS = 17;             // presence filter: 2^17 bits = 16 KB
+constexpr uint32_t KH_FBITS = 18;             // presence filter: 2^18 bits = 32 KB, 2 bits per key in one word
 constexpr uint32_t KH_FWORDS = (1u << KH_FBITS) / 32;
 constexpr uint32_t KH_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t KH_CSEG = 4096;            // columns per unit
@@ -56,7 +56,9 @@ struct KHArgs {
     tc_pair *edges; unsigned long long edge_cap; int radio;
 };
 
-__device__ __forceinline__ uint32_t kh_fbit(uint32_t x) { return (x * 0x9E3779B1u) >> (32 - KH_FBITS); }
+// presence filter: word = top (KH_FBITS-5) bits of h = x * golden, the two bit positions = low 10 bits of h
+__device__ __forceinline__ uint32_t kh_fword(uint32_t h) { return h >> (32 - (KH_FBITS - 5)); }
+__device__ __forceinline__ uint32_t kh_fmask(uint32_t h) { return (1u << (h & 31)) | (1u << ((h >> 5) & 31)); }
 __device__ __forceinline__ uint32_t kh_slot(uint32_t x) { return (x * 0x85EBCA6Bu) >> 18; }   // 14 bits
 __device__ __forceinline__ uint32_t kh_lds(uint32_t addr)
 {
@@ -117,9 +119,13 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
     __shared__ uint32_t s_lo[32], s_hi[32], s_len[32];
     __shared__ unsigned long long s_base[32];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(table);
-    const uint32_t filt_addr = (uint32_t)__cvta_generic_to_shared(filter);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint32_t lane = tid & 31;
+    asm volatile("" : "+r"(lane));
+    uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(table);
+    asm volatile("" : "+r"(tab_addr));
+    uint32_t filt_addr = (uint32_t)__cvta_generic_to_shared(filter);
+    asm volatile("" : "+r"(filt_addr));      // keep the shared-window addresses in registers (no rematerialisation)
     uint32_t *state = a.state + (size_t)blockIdx.x * KH_CSEG * KH_STATE;
 
     for (;;) {
@@ -160,8 +166,8 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                 const uint32_t bit = 1u << warp;
                 for (uint32_t e = s_lo[warp] + lane; e < s_hi[warp]; e += 32) {
                     const uint32_t x = __ldg(row + e);
-                    const uint32_t fb = kh_fbit(x);
-                    atomicOr(&filter[fb >> 5], 1u << (fb & 31));
+                    const uint32_t h = x * 0x9E3779B1u;
+                    atomicOr(&filter[kh_fword(h)], kh_fmask(h));
                     uint32_t slot = kh_slot(x);
                     for (;;) {
                         const uint32_t old = atomicCAS(&table[slot].x, KH_EMPTY, x);
@@ -179,36 +185,32 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                 c = __shfl_sync(0xffffffffu, c, 0);
                 if (c >= c1) break;
                 const uint32_t clen = a.size[c];
-                const uint32_t *col = a.ranks + a.off[c];
                 uint32_t *st = state + (size_t)(c - c0) * KH_STATE;
                 uint32_t pos = 0, cnt = 0;
                 if (p > 0) { pos = st[32]; cnt = st[lane]; }
+                const uint32_t *pc = a.ranks + a.off[c] + pos + lane;   // this lane's element of the current step
+                uint32_t rem = clen - pos;                               // elements left from the step's start
                 uint32_t x[4], xn[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t idx = pos + lane + 32 * k;
-                    x[k] = idx < clen ? __ldg(col + idx) : 0xFFFFFFFFu;
-                }
+                for (int k = 0; k < 4; k++) x[k] = (lane + 32 * k < rem) ? __ldg(pc + 32 * k) : 0xFFFFFFFFu;
                 for (;;) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const uint32_t idx = pos + 128 + lane + 32 * k;
-                        xn[k] = idx < clen ? __ldg(col + idx) : 0xFFFFFFFFu;
-                    }
-                    uint32_t mask[4];
-                    uint32_t fw[4];
+                    for (int k = 0; k < 4; k++) xn[k] = (lane + 128 + 32 * k < rem) ? __ldg(pc + 128 + 32 * k) : 0xFFFFFFFFu;
+                    // presence filter (blocked Bloom, 2 bits in one word): 4 independent LDS per lane
+                    uint32_t fw[4], fm[4];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {              // presence filter: 4 independent LDS
-                        const uint32_t fb = kh_fbit(x[k]);
-                        fw[k] = kh_lds(filt_addr + ((fb >> 5) << 2)) >> (fb & 31);
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t h = x[k] * 0x9E3779B1u;
+                        fw[k] = kh_lds(filt_addr + ((h >> (30 - KH_FBITS + 5)) & ((KH_FWORDS - 1) << 2)));
+                        fm[k] = kh_fmask(h);
                     }
                     bool maybe = false;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        mask[k] = 0u;
-                        fw[k] = (fw[k] & 1u) && x[k] < piv_hi;
+                        fw[k] = ((~fw[k] & fm[k]) == 0u) && x[k] < piv_hi;
                         maybe |= fw[k] != 0u;
                     }
+                    uint32_t mask[4] = {0u, 0u, 0u, 0u};
                     if (maybe) {                               // table lookups for the filter hits
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
@@ -224,20 +226,21 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                         }
                     }
                     if (__ballot_sync(0xffffffffu, (mask[0] | mask[1] | mask[2] | mask[3]) != 0u)) {
-#pragma unroll
+#pragma unroll 1
                         for (int k = 0; k < 4; k++) {
-                            unsigned hit = __ballot_sync(0xffffffffu, mask[k] != 0u);
+                            const uint32_t mk = k == 0 ? mask[0] : k == 1 ? mask[1] : k == 2 ? mask[2] : mask[3];
+                            unsigned hit = __ballot_sync(0xffffffffu, mk != 0u);
                             if (__popc(hit) <= 16) {
                                 while (hit) {
                                     const int src = __ffs(hit) - 1;
-                                    const uint32_t m = __shfl_sync(0xffffffffu, mask[k], src);
+                                    const uint32_t m = __shfl_sync(0xffffffffu, mk, src);
                                     cnt += (m >> lane) & 1u;
                                     hit &= hit - 1;
                                 }
                             } else {
 #pragma unroll
                                 for (int r = 0; r < 32; r++) {
-                                    const unsigned b = __ballot_sync(0xffffffffu, (mask[k] >> r) & 1u);
+                                    const unsigned b = __ballot_sync(0xffffffffu, (mk >> r) & 1u);
                                     if (lane == r) cnt += __popc(b);
                                 }
                             }
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                     }
                     // sorted stream: the step is consumed completely iff its last element is in the partition
                     if (__shfl_sync(0xffffffffu, x[3], 31) < piv_hi) {
-                        pos += 128;
+                        pos += 128; pc += 128; rem -= 128;
 #pragma unroll
                         for (int k = 0; k < 4; k++) x[k] = xn[k];
                         continue;
