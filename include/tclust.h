@@ -109,6 +109,13 @@ int tc_sketches_upload_dev(tc_ctx *ctx, const uint64_t *hashes_dev, const uint64
 int tc_pair_common(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1,
                    int impl, uint32_t *out);
 
+/* semantic B validation: out[i-i0][j-j0] = number of shared hashes among the first `sketch_size` elements of the
+ * sorted union of sketch_i and sketch_j -- the `common` of Sketch::MinHash::jaccard
+ * (RabbitSketch/src/MinHash.cpp:982-1101; stop rule u64_intersect_scalar_stop :1199-1229, to which the AVX2
+ * kernel :1579-1643 is equivalent).  Its denominator is min(sketch_size, |A|+|B|-common) (tc_jaccard_b). */
+int tc_pair_common_b(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1,
+                     uint32_t sketch_size, uint32_t *out);
+
 /*
  * One dense pass over all pairs j < i of the uploaded sketches, restricted to the tiles
  * owned by `part` of `nparts` (multi-GPU sharding; 0/1 = everything).  Emits the candidate
@@ -118,6 +125,10 @@ int tc_pair_common(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t 
  */
 int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts,
                      uint64_t *n_pairs, uint64_t *n_edges);
+/* the same pass with semantic-B counts (the all-pairs loop of modifyMST, src/MST.cpp:851-868): edges are the
+ * pairs with common_B >= 1, no size-ratio filter; the remaining pairs have distance exactly 1. */
+int tc_allpairs_pass_b(tc_ctx *ctx, uint32_t sketch_size, uint32_t part, uint32_t nparts,
+                       uint64_t *n_pairs, uint64_t *n_edges);
 /* copy the candidate edges kept so far to the host (cap entries at most; *n = total) */
 int tc_edges_download(tc_ctx *ctx, tc_pair *out, uint64_t cap, uint64_t *n);
 
@@ -131,7 +142,13 @@ int tc_edges_download(tc_ctx *ctx, tc_pair *out, uint64_t cap, uint64_t *n);
  * key = ~bits(J) with J = (double)common/denom exactly as src/MST.cpp:1489-1492 (Mash) or
  * :1505-1507 (containment) computes it, so the host can turn it into the reference's
  * distance.  The *_dev buffers are caller-provided (e.g. torch tensors that NCCL reduces).
+ * `containment` is the distance mode TC_DIST_*: 0/1 as above; TC_DIST_MASH_B after tc_allpairs_pass_b
+ * (J = common_B / min(sketchSize, union)); TC_DIST_CONTAIN_B = containDistance (J = common / min size).
  */
+#define TC_DIST_MASH_A    0   /* src/MST.cpp:1489-1503 */
+#define TC_DIST_AAF       1   /* src/MST.cpp:1504-1515 */
+#define TC_DIST_MASH_B    2   /* RabbitSketch/src/MinHash.cpp:1125-1153 MinHash::distance */
+#define TC_DIST_CONTAIN_B 3   /* RabbitSketch/src/MinHash.cpp:1102-1123 MinHash::containDistance */
 int tc_boruvka_upload_comp(tc_ctx *ctx, const int32_t *comp, uint32_t n);
 int tc_boruvka_phase1(tc_ctx *ctx, int containment, uint64_t *best_key_dev);
 int tc_boruvka_phase2(tc_ctx *ctx, int containment, const uint64_t *best_key_dev,
@@ -147,6 +164,15 @@ int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double threshold,
            tc_edge *out, uint64_t *n_out);
 
 /*
+ * Brute-force MST = modifyMST (src/MST.cpp:809-1018): every pair gets MinHash::distance (semantic B with
+ * `sketch_size`; containment != 0: containDistance) and the MST of the COMPLETE graph is returned: n-1 edges
+ * {i, j<i, dist} sorted by (dist, i, j).  Pairs without a shared hash have distance exactly 1; they are not
+ * enumerated but enter as the weight-1 edges that join the remaining components.
+ */
+int tc_mst_bruteforce(tc_ctx *ctx, int kmer_size, uint32_t sketch_size, int containment,
+                      tc_edge *out, uint64_t *n_out);
+
+/*
  * Greedy representative scan (K5).  For queries q in [q0,q1) against representatives
  * rep_ids[0..nrep): common[(q-q0)*nrep + r] and first_hit (index in the query sketch of the
  * first shared hash, UINT32_MAX if none) -- what greedy.cpp:1148-1164 accumulates in
@@ -159,10 +185,20 @@ int tc_greedy_scan(tc_ctx *ctx, uint32_t q0, uint32_t q1, const uint32_t *rep_id
 int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, double threshold,
                       int32_t *rep_of, uint32_t *n_clusters);
 
+/* brute-force greedyCluster (src/greedy.cpp:285-351) with one thread: genome j joins the nearest representative
+ * with MinHash::distance (containment: containDistance) <= threshold, ties -> the earliest-created one; else it
+ * becomes a representative.  threshold < 1. */
+int tc_greedy_cluster_bruteforce(tc_ctx *ctx, int kmer_size, uint32_t sketch_size, int containment,
+                                 double threshold, int32_t *rep_of, uint32_t *n_clusters);
+
 /* ---- host-side exact distance helpers (glibc log; reference expression order) --------- */
 double tc_mash_dist(int common, int size0, int size1, int kmer_size);     /* MST.cpp:1489-1503 */
 double tc_aaf_dist(int common, int size0, int size1, int kmer_size);      /* MST.cpp:1504-1515 */
-double tc_dist_from_key(uint64_t key, int containment, int kmer_size);    /* J bits -> dist */
+double tc_dist_from_key(uint64_t key, int containment, int kmer_size);    /* J bits -> dist, mode TC_DIST_* */
+double tc_jaccard_b(int common_b, int size0, int size1, int sketch_size); /* MinHash.cpp:1079-1100 */
+double tc_distance_b(int common_b, int size0, int size1, int sketch_size,
+                     int kmer_size);                                      /* MinHash.cpp:1125-1153 */
+double tc_contain_distance(int common, int size0, int size1, int kmer_size); /* MinHash.cpp:908-979,1102-1123 */
 int    tc_greedy_common_min(double threshold, int kmer_size, int size_ref, int size_qry,
                             int containment);                             /* greedy.cpp:1107-1113,1211-1219 */
 double tc_greedy_dist(int common, int size_ref, int size_qry, int containment,

@@ -65,6 +65,14 @@ def lib():
         L.oc_clusters_from_mst.argtypes = [C.POINTER(Edge), C.c_size_t, C.c_int, C.c_double, i32p, i32p]
         L.oc_greedy_inverted.restype = C.c_int
         L.oc_greedy_inverted.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_int, C.c_double, i32p]
+        L.oc_common_B.restype = C.c_uint32
+        L.oc_common_B.argtypes = [u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint64, u32p]
+        L.oc_contain_distance.restype = C.c_double
+        L.oc_contain_distance.argtypes = [u64p, C.c_size_t, u64p, C.c_size_t, C.c_int]
+        L.oc_mst_bruteforce.restype = C.c_size_t
+        L.oc_mst_bruteforce.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(Edge)]
+        L.oc_greedy_bruteforce.restype = C.c_int
+        L.oc_greedy_bruteforce.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_double, i32p]
         _LIB = L
     return _LIB
 
@@ -140,6 +148,50 @@ def intersect(a, b):
 def jaccard_B(a, b, sketch_size):
     a = np.ascontiguousarray(a, np.uint64); b = np.ascontiguousarray(b, np.uint64)
     return float(lib().oc_jaccard_B(_p(a, C.c_uint64), len(a), _p(b, C.c_uint64), len(b), sketch_size))
+
+
+def common_B(a, b, sketch_size):
+    """-> (common, denom) of MinHash::jaccard (semantic B)."""
+    a = np.ascontiguousarray(a, np.uint64); b = np.ascontiguousarray(b, np.uint64)
+    d = C.c_uint32(0)
+    c = lib().oc_common_B(_p(a, C.c_uint64), len(a), _p(b, C.c_uint64), len(b), sketch_size, C.byref(d))
+    return int(c), int(d.value)
+
+
+def common_B_matrix(sketches, sketch_size):
+    n = len(sketches)
+    out = np.zeros((n, n), np.uint32)
+    for i in range(n):
+        for j in range(n):
+            out[i, j] = common_B(sketches[i], sketches[j], sketch_size)[0]
+    return out
+
+
+def distance_B(a, b, sketch_size, k):
+    return float(lib().oc_distance_B(jaccard_B(a, b, sketch_size), k))
+
+
+def contain_distance(a, b, k):
+    a = np.ascontiguousarray(a, np.uint64); b = np.ascontiguousarray(b, np.uint64)
+    return float(lib().oc_contain_distance(_p(a, C.c_uint64), len(a), _p(b, C.c_uint64), len(b), k))
+
+
+def mst_bruteforce(sketches, k, sketch_size, containment=False):
+    h, off = pack_sketches(sketches)
+    n = len(sketches)
+    out = np.zeros(max(n, 1), EDGE_DTYPE)
+    m = lib().oc_mst_bruteforce(_p(h, C.c_uint64), _p(off, C.c_uint64), n, k, sketch_size, int(containment),
+                                out.ctypes.data_as(C.POINTER(Edge)))
+    return out[:m].copy()
+
+
+def greedy_bruteforce(sketches, k, sketch_size, threshold, containment=False):
+    h, off = pack_sketches(sketches)
+    n = len(sketches)
+    rep = np.zeros(max(n, 1), np.int32)
+    nc = lib().oc_greedy_bruteforce(_p(h, C.c_uint64), _p(off, C.c_uint64), n, k, sketch_size, int(containment),
+                                    threshold, _p(rep, C.c_int32))
+    return nc, rep[:n]
 
 
 def common_matrix(sketches):

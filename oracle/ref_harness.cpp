@@ -16,8 +16,18 @@
  *   ref_harness update <k> <s> <threads> <len> <ngenomes>
  *                                                   time MinHash::update on synthetic genomes
  *   ref_harness dist <hash.sketch> <i> <j>          jaccard/distance of one pair (semantic B)
+ *   ref_harness pairsdump <hash.sketch> <nmax>      binary: for i, for j<i: double jaccard(), distance(),
+ *                                                   containDistance()  (MinHash.cpp:982-1153, 908-979)
+ *   ref_harness mstb <hash.sketch> <nmax> <threads> [contain]
+ *                                                   the reference's brute-force MST modifyMST
+ *                                                   (src/MST.cpp:809-1018); binary: u64 n, {i32,i32,f64}[n]
+ *   ref_harness greedyb <hash.sketch> <nmax> <threads> <threshold> [contain]
+ *                                                   the reference's brute-force greedyCluster
+ *                                                   (src/greedy.cpp:285-351); text: one cluster per line
  */
 #include "Sketch.h"
+#include "MST.h"
+#include "greedy.h"
 #include <zlib.h>
 #include "kseq.h"
 #include <omp.h>
@@ -139,8 +149,71 @@ static int cmd_dist(int argc, char **argv)
     return 0;
 }
 
+static int cmd_pairsdump(int argc, char **argv)
+{
+    Folder f;
+    if (!load_hash_sketch(argv[2], strtoull(argv[3], 0, 10), f)) return 1;
+    size_t N = f.sk.size();
+    std::vector<Sketch::MinHash *> mh(N);
+    for (size_t i = 0; i < N; i++) { mh[i] = new Sketch::MinHash(f.k, f.param); mh[i]->loadMinHashes(f.sk[i]); }
+    for (size_t i = 0; i < N; i++)
+        for (size_t j = 0; j < i; j++) {
+            double v[3] = {mh[i]->jaccard(mh[j]), mh[i]->distance(mh[j]), mh[i]->containDistance(mh[j])};
+            fwrite(v, 8, 3, stdout);
+        }
+    return 0;
+}
+
+static void make_infos(const Folder &f, bool contain, std::vector<SketchInfo> &v)
+{
+    v.resize(f.sk.size());
+    for (size_t i = 0; i < f.sk.size(); i++) {
+        v[i].id = (int)i;
+        v[i].isContainment = contain;
+        v[i].totalSeqLength = 0;
+        v[i].minHash = new Sketch::MinHash(f.k, f.param);
+        v[i].minHash->loadMinHashes(const_cast<std::vector<uint64_t> &>(f.sk[i]));
+    }
+}
+
+static int cmd_mstb(int argc, char **argv)
+{
+    Folder f;
+    if (!load_hash_sketch(argv[2], strtoull(argv[3], 0, 10), f)) return 1;
+    int threads = atoi(argv[4]);
+    bool contain = argc > 5 && !strcmp(argv[5], "contain");
+    std::vector<SketchInfo> v;
+    make_infos(f, contain, v);
+    int **dense = nullptr; uint64_t *ani = nullptr;
+    std::vector<EdgeInfo> mst = modifyMST(v, 0, 0, threads, true, dense, 0, ani);
+    uint64_t n = mst.size();
+    fwrite(&n, 8, 1, stdout);
+    for (const EdgeInfo &e : mst) { fwrite(&e.preNode, 4, 1, stdout); fwrite(&e.sufNode, 4, 1, stdout); fwrite(&e.dist, 8, 1, stdout); }
+    return 0;
+}
+
+static int cmd_greedyb(int argc, char **argv)
+{
+    Folder f;
+    if (!load_hash_sketch(argv[2], strtoull(argv[3], 0, 10), f)) return 1;
+    int threads = atoi(argv[4]);
+    double thr = atof(argv[5]);
+    bool contain = argc > 6 && !strcmp(argv[6], "contain");
+    std::vector<SketchInfo> v;
+    make_infos(f, contain, v);
+    std::vector<std::vector<int>> cl = greedyCluster(v, 0, thr, threads);
+    for (const auto &c : cl) {
+        for (size_t i = 0; i < c.size(); i++) printf(i ? " %d" : "%d", c[i]);
+        printf("\n");
+    }
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc >= 4 && !strcmp(argv[1], "pairsdump")) return cmd_pairsdump(argc, argv);
+    if (argc >= 5 && !strcmp(argv[1], "mstb")) return cmd_mstb(argc, argv);
+    if (argc >= 6 && !strcmp(argv[1], "greedyb")) return cmd_greedyb(argc, argv);
     if (argc >= 5 && !strcmp(argv[1], "sketch")) return cmd_sketch(argc, argv);
     if (argc >= 5 && !strcmp(argv[1], "pairs")) return cmd_pairs(argc, argv);
     if (argc >= 7 && !strcmp(argv[1], "update")) return cmd_update(argc, argv);

@@ -452,3 +452,93 @@ int oc_greedy_inverted(const uint64_t *hashes, const uint64_t *off, int N, int k
     free(reps); free(tc);
     return nrep;
 }
+
+/* ------------------------------------------------- semantic B brute-force callers */
+/* MinHash::jaccard as integers: common among the first sketch_size union elements and the
+ * completed denominator (MinHash.cpp:982-1101, scalar form :1199-1229). */
+uint32_t oc_common_B(const uint64_t *a, size_t na, const uint64_t *b, size_t nb,
+                     uint64_t sketch_size, uint32_t *denom_out)
+{
+    uint64_t i = 0, j = 0, common = 0, denom = 0;
+    while (denom < sketch_size && i < na && j < nb) {
+        if (a[i] < b[j]) i++;
+        else if (b[j] < a[i]) j++;
+        else { i++; j++; common++; }
+        denom++;
+    }
+    if (denom < sketch_size) {
+        if (i < na) denom += na - i;
+        if (j < nb) denom += nb - j;
+        if (denom > sketch_size) denom = sketch_size;
+    }
+    if (denom_out) *denom_out = (uint32_t)denom;
+    return (uint32_t)common;
+}
+
+/* MinHash::containDistance (MinHash.cpp:1102-1123) over containJaccard (:908-979) */
+double oc_contain_distance(const uint64_t *a, size_t na, const uint64_t *b, size_t nb, int k)
+{
+    uint32_t common = oc_intersect_u64(a, na, b, nb, NULL);
+    double j = (double)common / (double)(na < nb ? na : nb);
+    if (j == 1.0) return 0;
+    double d = -log(2 * j / (1. + j)) / k;
+    if (d > 1) d = 1;
+    return d;
+}
+
+static double pair_dist_B(const uint64_t *hashes, const uint64_t *off, int i, int j, int k,
+                          uint64_t sketch_size, int containment)
+{
+    const uint64_t *a = hashes + off[i], *b = hashes + off[j];
+    size_t na = off[i + 1] - off[i], nb = off[j + 1] - off[j];
+    if (containment) return oc_contain_distance(a, na, b, nb, k);
+    return oc_distance_B(oc_jaccard_B(a, na, b, nb, sketch_size), k);
+}
+
+/* modifyMST (MST.cpp:809-1018): every pair i<j gets MinHash::distance / containDistance, then
+ * sort + Kruskal over the complete graph.  Returns N-1 edges. */
+size_t oc_mst_bruteforce(const uint64_t *hashes, const uint64_t *off, int N, int k,
+                         uint64_t sketch_size, int containment, oc_edge *out)
+{
+    size_t n = 0, cap = (size_t)N * (N > 0 ? N - 1 : 0) / 2 + 1;
+    oc_edge *g = (oc_edge *)malloc(cap * sizeof(oc_edge));
+    for (int i = 0; i < N; i++)
+        for (int j = i + 1; j < N; j++) {
+            g[n].pre = i; g[n].suf = j;
+            g[n].dist = pair_dist_B(hashes, off, i, j, k, sketch_size, containment);
+            n++;
+        }
+    qsort(g, n, sizeof(oc_edge), cmp_edge);
+    int *p = (int *)malloc(sizeof(int) * (N > 0 ? N : 1));
+    for (int i = 0; i < N; i++) p[i] = i;
+    size_t m = 0;
+    for (size_t e = 0; e < n; e++) {
+        int a = uf_find(p, g[e].pre), b = uf_find(p, g[e].suf);
+        if (a != b) { p[a] = b; out[m++] = g[e]; }
+    }
+    free(p); free(g);
+    return m;
+}
+
+/* greedyCluster (greedy.cpp:285-351) with one thread: genome j joins the nearest
+ * representative with dist <= threshold (std::map<double,int>::insert keeps the FIRST rep
+ * inserted for equal distances = earliest-created), else becomes a representative. */
+int oc_greedy_bruteforce(const uint64_t *hashes, const uint64_t *off, int N, int k,
+                         uint64_t sketch_size, int containment, double threshold, int32_t *rep_of)
+{
+    if (N == 0) return 0;
+    int *reps = (int *)malloc(sizeof(int) * N), nrep = 0;
+    reps[nrep++] = 0; rep_of[0] = 0;
+    for (int j = 1; j < N; j++) {
+        int best = -1;
+        double best_d = 0;
+        for (int r = 0; r < nrep; r++) {
+            double d = pair_dist_B(hashes, off, reps[r], j, k, sketch_size, containment);
+            if (d <= threshold && (best < 0 || d < best_d)) { best = reps[r]; best_d = d; }
+        }
+        if (best >= 0) rep_of[j] = best;
+        else { reps[nrep++] = j; rep_of[j] = j; }
+    }
+    free(reps);
+    return nrep;
+}

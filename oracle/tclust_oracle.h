@@ -87,6 +87,21 @@ int oc_clusters_from_mst(const oc_edge *mst, size_t n_edges, int N, double thres
 int oc_greedy_inverted(const uint64_t *hashes, const uint64_t *off, int N, int k,
                        int containment, double threshold, int32_t *rep_of);
 
+/* ---- semantic B (the brute-force fallbacks) ---------------------------------------- */
+/* integer form of MinHash::jaccard (MinHash.cpp:982-1101): common among the first
+ * sketch_size union elements; *denom_out = completed/capped denominator. */
+uint32_t oc_common_B(const uint64_t *a, size_t na, const uint64_t *b, size_t nb,
+                     uint64_t sketch_size, uint32_t *denom_out);
+/* MinHash::containDistance (MinHash.cpp:1102-1123, containJaccard :908-979) */
+double oc_contain_distance(const uint64_t *a, size_t na, const uint64_t *b, size_t nb, int k);
+/* modifyMST (src/MST.cpp:809-1018) + Kruskal: brute-force all pairs with MinHash::distance
+ * (containment: containDistance); N-1 edges {i, j>i, dist} in Kruskal order. */
+size_t oc_mst_bruteforce(const uint64_t *hashes, const uint64_t *off, int N, int k,
+                         uint64_t sketch_size, int containment, oc_edge *out);
+/* greedyCluster (src/greedy.cpp:285-351) with one thread. rep_of[j] = centre of genome j. */
+int oc_greedy_bruteforce(const uint64_t *hashes, const uint64_t *off, int N, int k,
+                         uint64_t sketch_size, int containment, double threshold, int32_t *rep_of);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,8 @@ SYMBOLS = [
     "tc_sketches_upload", "tc_sketches_upload_dev", "tc_pair_common", "tc_allpairs_pass",
     "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_mst",
     "tc_greedy_scan", "tc_greedy_cluster",
+    "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce",
+    "tc_jaccard_b", "tc_distance_b", "tc_contain_distance",
     "tc_mash_dist", "tc_aaf_dist", "tc_dist_from_key", "tc_radio", "tc_greedy_common_min", "tc_greedy_dist",
 ]
 
@@ -71,6 +73,16 @@ def lib():
     L.tc_mst.argtypes = [vp, C.c_int, C.c_int, C.c_double, vp, u64p]
     L.tc_greedy_scan.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, C.c_uint32, u32p, u32p]
     L.tc_greedy_cluster.argtypes = [vp, C.c_int, C.c_int, C.c_double, i32p, u32p]
+    L.tc_pair_common_b.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
+    L.tc_allpairs_pass_b.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u64p]
+    L.tc_mst_bruteforce.argtypes = [vp, C.c_int, C.c_uint32, C.c_int, vp, u64p]
+    L.tc_greedy_cluster_bruteforce.argtypes = [vp, C.c_int, C.c_uint32, C.c_int, C.c_double, i32p, u32p]
+    L.tc_jaccard_b.argtypes = [C.c_int] * 4
+    L.tc_jaccard_b.restype = C.c_double
+    L.tc_distance_b.argtypes = [C.c_int] * 5
+    L.tc_distance_b.restype = C.c_double
+    L.tc_contain_distance.argtypes = [C.c_int] * 4
+    L.tc_contain_distance.restype = C.c_double
     for f in (L.tc_mash_dist, L.tc_aaf_dist):
         f.argtypes = [C.c_int] * 4
         f.restype = C.c_double
@@ -195,6 +207,31 @@ class Context:
         _chk(lib().tc_pair_common(self._h, i0, i1, j0, j1, impl, _p(out, C.c_uint32)))
         return out
 
+    def pair_common_b(self, i0, i1, j0, j1, sketch_size):
+        """semantic B (MinHash::jaccard): shared hashes among the first sketch_size union elements."""
+        out = np.zeros((i1 - i0, j1 - j0), np.uint32)
+        _chk(lib().tc_pair_common_b(self._h, i0, i1, j0, j1, sketch_size, _p(out, C.c_uint32)))
+        return out
+
+    def allpairs_pass_b(self, sketch_size, part=0, nparts=1):
+        npairs, nedges = C.c_uint64(0), C.c_uint64(0)
+        _chk(lib().tc_allpairs_pass_b(self._h, sketch_size, part, nparts, C.byref(npairs), C.byref(nedges)))
+        return int(npairs.value), int(nedges.value)
+
+    def mst_bruteforce(self, k, sketch_size, containment=False):
+        """modifyMST: MST of the complete graph under MinHash::distance / containDistance."""
+        out = np.zeros(max(self.n, 1), EDGE_DTYPE)
+        m = C.c_uint64(0)
+        _chk(lib().tc_mst_bruteforce(self._h, k, sketch_size, int(containment), out.ctypes.data, C.byref(m)))
+        return out[:int(m.value)].copy()
+
+    def greedy_cluster_bruteforce(self, k, sketch_size, threshold, containment=False):
+        rep = np.zeros(max(self.n, 1), np.int32)
+        nc = C.c_uint32(0)
+        _chk(lib().tc_greedy_cluster_bruteforce(self._h, k, sketch_size, int(containment), threshold,
+                                                _p(rep, C.c_int32), C.byref(nc)))
+        return int(nc.value), rep[:self.n].copy()
+
     def allpairs_pass(self, radio, part=0, nparts=1):
         npairs, nedges = C.c_uint64(0), C.c_uint64(0)
         _chk(lib().tc_allpairs_pass(self._h, radio, part, nparts, C.byref(npairs), C.byref(nedges)))
@@ -235,6 +272,14 @@ def mash_dist(common, size0, size1, k):
 
 def aaf_dist(common, size0, size1, k):
     return float(lib().tc_aaf_dist(common, size0, size1, k))
+
+
+def distance_b(common_b, size0, size1, sketch_size, k):
+    return float(lib().tc_distance_b(common_b, size0, size1, sketch_size, k))
+
+
+def contain_distance(common, size0, size1, k):
+    return float(lib().tc_contain_distance(common, size0, size1, k))
 
 
 def radio(threshold, k):

@@ -67,6 +67,9 @@ struct K3Args {
     tc_cand *cands; int lower_only;   // lower_only: emit only col id < row id (intra-batch tiles)
     int cmin_fixed;                   // >= 0: fixed-size Mash mode; < 0: per-pair rule below
     int containment; double jmin, one_plus_jmin;
+    // semantic B (SEMB kernels): the merge of a pair stops after semb_size union elements
+    // (MinHash::jaccard, RabbitSketch/src/MinHash.cpp:982-1101; scalar form :1199-1229)
+    uint32_t semb_size;
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
@@ -92,7 +95,7 @@ __device__ __forceinline__ void tile_to_rc(const K3Args &a, long long t, uint32_
     }
 }
 
-template <int MODE, bool FH>
+template <int MODE, bool FH, bool SEMB>
 __global__ void __launch_bounds__(K3_THREADS, 1) k3_tile_kernel(const K3Args a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -131,6 +134,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_tile_kernel(const K3Args a)
         }
         uint32_t acc = 0;
         uint32_t first_hit = 0xFFFFFFFFu;   // FH: index in the row sketch of the first shared element
+        uint32_t budget = SEMB ? a.semb_size : 0u;   // SEMB: union elements this pair may still consume
         __syncthreads();
 
         for (;;) {  // ---- value-range chunks ----
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_tile_kernel(const K3Args a)
                 if (m->pos[tid] + lo < m->len[tid]) atomicOr(&m->more, tid < 32 ? 1u : 2u);
             }
             __syncthreads();
-            {   // ---- branch-free two-pointer merge, one pair per thread ----
+            if (!SEMB) {   // ---- branch-free two-pointer merge, one pair per thread ----
                 const uint32_t pa0 = sA_addr + prow * 4, pb0 = sB_addr + pcol * 4;
                 uint32_t pa = pa0, pb = pb0;
                 uint32_t va = lds_u32(pa), vb = lds_u32(pb);
@@ -195,6 +199,38 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_tile_kernel(const K3Args a)
                     if (first_hit == 0xFFFFFFFFu && fh_addr != 0xFFFFFFFFu)
                         first_hit = m->pos[prow] + ((fh_addr - pa0) >> 7);
                 }
+            } else {
+                // ---- semantic B: the same merge with a step budget.  Every active step consumes exactly one
+                // element of the union in ascending order (steps taken when both streams sit on their
+                // sentinels are spurious: they advance pb and the step counter alike and end the chunk).
+                const uint32_t pa0 = sA_addr + prow * 4, pb0 = sB_addr + pcol * 4;
+                uint32_t pa = pa0, pb = pb0;
+                uint32_t va = lds_u32(pa), vb = lds_u32(pb);
+                uint32_t steps = 0, left = budget;
+                while (max(va, vb) < TC_SENT_B && left > 0) {
+#pragma unroll
+                    for (int u = 0; u < K3_U; u++) {
+                        const bool act = (uint32_t)u < left;
+                        const bool le = act && va <= vb, ge = act && va >= vb;
+                        if (le) pa += 128;
+                        if (ge) pb += 128;
+                        va = lds_u32(pa);
+                        vb = lds_u32(pb);
+                    }
+                    const uint32_t d = min(left, (uint32_t)K3_U);
+                    steps += d;
+                    left -= d;
+                }
+                const uint32_t cc = (((pa - pa0) + (pb - pb0)) >> 7) - steps;
+                acc += cc;
+                if (max(va, vb) >= TC_SENT_B) {
+                    // one stream of this value range is used up: the rest of the other stream (all <= pivot)
+                    // precedes the next chunk in the union, so the whole chunk counts against the budget
+                    const uint32_t used = m->cut[prow] + m->cut[32 + pcol] - cc;
+                    budget = budget > used ? budget - used : 0u;
+                } else {
+                    budget = 0;      // stopped inside the chunk: sketch_size union elements consumed
+                }
             }
             const uint32_t more = m->more;
             __syncthreads();
@@ -216,7 +252,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_tile_kernel(const K3Args a)
             const uint32_t s0 = m->len[prow], s1 = m->len[32 + pcol];
             uint32_t j = jm;
             if (MODE == K3_MODE_EDGES) {
-                if (i < a.row.n && j < i && acc >= 1u) {
+                if (SEMB) {
+                    keep = i < a.row.n && j < i && acc >= 1u;   // modifyMST: no size-ratio filter
+                } else if (i < a.row.n && j < i && acc >= 1u) {
                     const uint32_t mn = min(s0, s1), mx = max(s0, s1);
                     // reference: skip if max_size > radio * min_size (int arithmetic), MST.cpp:1481-1487
                     keep = mn > 0 && !((long long)mx > (long long)a.radio * (long long)mn);
@@ -225,7 +263,11 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k3_tile_kernel(const K3Args a)
                 if (i < a.row.n && jm < a.col.n && acc >= 1u) {
                     if (a.col.ids) j = a.col.ids[jm];
                     int cmin = a.cmin_fixed;
-                    if (cmin < 0) {   // greedy.cpp:1211-1219, IEEE-exact operations in the host's order
+                    if (SEMB) {
+                        // J_B = common / min(S, |A u B|) <= common / min(S, max size): conservative bound,
+                        // the host applies MinHash::distance exactly
+                        cmin = (int)ceil(__dmul_rn(a.jmin, (double)min(a.semb_size, max(s0, s1))));
+                    } else if (cmin < 0) {   // greedy.cpp:1211-1219, IEEE-exact operations in the host's order
                         const double t = a.containment
                             ? __dmul_rn(a.jmin, (double)min(s0, s1))
                             : __ddiv_rn(__dmul_rn(a.jmin, (double)(s0 + s1)), a.one_plus_jmin);
@@ -279,15 +321,15 @@ __global__ void pair_common_ref_kernel(const uint64_t *hashes, const unsigned lo
     out[idx] = c;
 }
 
-template <int MODE, bool FH>
+template <int MODE, bool FH, bool SEMB>
 int k3_launch_t(tc_ctx *ctx, const K3Args &a, int grid)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        TC_CUDA(cudaFuncSetAttribute(k3_tile_kernel<MODE, FH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM));
+        TC_CUDA(cudaFuncSetAttribute(k3_tile_kernel<MODE, FH, SEMB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM));
         attr_set = true;
     }
-    k3_tile_kernel<MODE, FH><<<grid, K3_THREADS, K3_SMEM, ctx->stream>>>(a);
+    k3_tile_kernel<MODE, FH, SEMB><<<grid, K3_THREADS, K3_SMEM, ctx->stream>>>(a);
     return 0;
 }
 
@@ -315,9 +357,15 @@ int k3_launch(tc_ctx *ctx, K3Args &a, int mode, bool fh)
     if (my_tiles <= 0) return 0;
     int grid = (int)(my_tiles < ctx->num_sms ? my_tiles : ctx->num_sms);
     int rc;
-    if (mode == K3_MODE_MATRIX) rc = fh ? k3_launch_t<K3_MODE_MATRIX, true>(ctx, a, grid) : k3_launch_t<K3_MODE_MATRIX, false>(ctx, a, grid);
-    else if (mode == K3_MODE_EDGES) rc = k3_launch_t<K3_MODE_EDGES, false>(ctx, a, grid);
-    else rc = k3_launch_t<K3_MODE_CAND, true>(ctx, a, grid);
+    const bool semb = a.semb_size > 0;
+    if (mode == K3_MODE_MATRIX)
+        rc = semb ? k3_launch_t<K3_MODE_MATRIX, false, true>(ctx, a, grid)
+           : fh   ? k3_launch_t<K3_MODE_MATRIX, true, false>(ctx, a, grid)
+                  : k3_launch_t<K3_MODE_MATRIX, false, false>(ctx, a, grid);
+    else if (mode == K3_MODE_EDGES)
+        rc = semb ? k3_launch_t<K3_MODE_EDGES, false, true>(ctx, a, grid) : k3_launch_t<K3_MODE_EDGES, false, false>(ctx, a, grid);
+    else
+        rc = semb ? k3_launch_t<K3_MODE_CAND, false, true>(ctx, a, grid) : k3_launch_t<K3_MODE_CAND, true, false>(ctx, a, grid);
     if (rc) return rc;
     ctx->launches++;
     TC_CUDA(cudaGetLastError());
@@ -326,9 +374,11 @@ int k3_launch(tc_ctx *ctx, K3Args &a, int mode, bool fh)
 
 }  // namespace
 
-int tc_launch_tiles_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out)
+int tc_launch_tiles_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out,
+                           uint32_t semb_size)
 {
     K3Args a{};
+    a.semb_size = semb_size;
     a.row = main_set(ctx); a.col = main_set(ctx);
     a.rg0 = i0 / TC_GROUP; a.rg1 = (i1 + TC_GROUP - 1) / TC_GROUP;
     a.cg0 = j0 / TC_GROUP; a.cg1 = (j1 + TC_GROUP - 1) / TC_GROUP;
@@ -353,9 +403,10 @@ int tc_launch_tiles_rep_matrix(tc_ctx *ctx, uint32_t q0, uint32_t q1, uint32_t *
     return k3_launch(ctx, a, K3_MODE_MATRIX, true);
 }
 
-int tc_launch_tiles_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts)
+int tc_launch_tiles_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t semb_size)
 {
     K3Args a{};
+    a.semb_size = semb_size;
     a.row = main_set(ctx); a.col = main_set(ctx);
     a.rg0 = 0; a.rg1 = ctx->ngroups; a.cg0 = 0; a.cg1 = ctx->ngroups;
     a.triangular = 1;
@@ -368,9 +419,10 @@ int tc_launch_tiles_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts
 // greedy candidates of the query batch [q0,q1) (q0 multiple of 32): vs_reps = against the representative
 // table, else the batch against itself (col id < row id).  Appends to ctx->d_cands.
 int tc_launch_tiles_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment,
-                          double jmin, uint32_t part, uint32_t nparts)
+                          double jmin, uint32_t part, uint32_t nparts, uint32_t semb_size)
 {
     K3Args a{};
+    a.semb_size = semb_size;
     a.row = main_set(ctx);
     a.rg0 = q0 / TC_GROUP; a.rg1 = (q1 + TC_GROUP - 1) / TC_GROUP;
     if (vs_reps) {

@@ -178,8 +178,12 @@ extern "C" int tc_greedy_scan(tc_ctx *ctx, uint32_t q0, uint32_t q1, const uint3
 }
 
 // --------------------------------------------------------------------- full greedy clustering
-extern "C" int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, double threshold, int32_t *rep_of,
-                                 uint32_t *n_clusters)
+// brute = false: MinHashGreedyClusterWithInvertedIndex (greedy.cpp:986-1399), semantic A, `touched` tie order.
+// brute = true : greedyCluster (greedy.cpp:285-351): MinHash::distance (semantic B with sketchSize semb_size) or
+//                containDistance of the query against every representative; nearest wins, ties -> earliest-created
+//                representative (std::map<double,int>::insert keeps the first key, one thread).
+static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double threshold, bool brute, uint32_t semb_size,
+                       int32_t *rep_of, uint32_t *n_clusters)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0, "tc_greedy_cluster: no sketches uploaded");
@@ -187,7 +191,8 @@ extern "C" int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, do
     cudaStream_t st = ctx->stream;
     // fixed-size fast path detection over the first 100 sketches (greedy.cpp:1092-1103)
     const int fixed_size = (int)ctx->h_size[0];
-    bool all_fixed = !containment;
+    bool all_fixed = !containment && !brute;
+    if (brute && containment) semb_size = 0;   // containDistance counts the full intersection
     for (uint32_t i = 1; i < std::min<uint32_t>(100, n) && all_fixed; i++)
         if ((int)ctx->h_size[i] != fixed_size) all_fixed = false;
     const int cmin_fixed = all_fixed ? tc_greedy_common_min(threshold, kmer_size, fixed_size, fixed_size, 0) : -1;
@@ -216,8 +221,8 @@ extern "C" int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, do
     for (uint32_t b0 = 0; b0 < n;) {
         const uint32_t b1 = std::min<uint64_t>(n, (uint64_t)b0 + batch);
         TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), st));
-        if (ctx->nrep > 0 && tc_launch_tiles_cands(ctx, b0, b1, 1, cmin_fixed, containment, jmin, 0, 1)) return 1;
-        if (tc_launch_tiles_cands(ctx, b0, b1, 0, cmin_fixed, containment, jmin, 0, 1)) return 1;
+        if (ctx->nrep > 0 && tc_launch_tiles_cands(ctx, b0, b1, 1, cmin_fixed, containment, jmin, 0, 1, semb_size)) return 1;
+        if (tc_launch_tiles_cands(ctx, b0, b1, 0, cmin_fixed, containment, jmin, 0, 1, semb_size)) return 1;
         unsigned long long cnt[2];
         TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, st));
         TC_CUDA(cudaStreamSynchronize(st));
@@ -249,7 +254,7 @@ extern "C" int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, do
             // representative creation order)  -- greedy.cpp:1148-1164
             tc_cand *end = std::remove_if(lo, hi, [&](const tc_cand &c) { return order_of[c.rep] < 0; });
             std::sort(lo, end, [&](const tc_cand &a, const tc_cand &b) {
-                if (a.first_hit != b.first_hit) return a.first_hit < b.first_hit;
+                if (!brute && a.first_hit != b.first_hit) return a.first_hit < b.first_hit;
                 return order_of[a.rep] < order_of[b.rep];
             });
             const int size_ref = (int)ctx->h_size[q];
@@ -257,6 +262,12 @@ extern "C" int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, do
             double best_dist = std::numeric_limits<double>::max();
             for (tc_cand *c = lo; c < end; c++) {
                 const int common = (int)c->common, size_qry = (int)ctx->h_size[c->rep];
+                if (brute) {   // greedy.cpp:297-334: dist <= threshold, smallest distance, first inserted wins
+                    const double dist = containment ? tc_contain_distance(common, size_qry, size_ref, kmer_size)
+                                                    : tc_distance_b(common, size_qry, size_ref, (int)semb_size, kmer_size);
+                    if (dist <= threshold && dist < best_dist) { best_dist = dist; best_rep = (int)c->rep; }
+                    continue;
+                }
                 const int common_min = all_fixed ? cmin_fixed
                                                  : tc_greedy_common_min(threshold, kmer_size, size_ref, size_qry, containment);
                 if (common < common_min) continue;
@@ -280,4 +291,19 @@ extern "C" int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, do
     }
     if (n_clusters) *n_clusters = nrep_total;
     return 0;
+}
+
+extern "C" int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, double threshold, int32_t *rep_of,
+                                 uint32_t *n_clusters)
+{
+    return greedy_impl(ctx, kmer_size, containment, threshold, false, 0, rep_of, n_clusters);
+}
+
+extern "C" int tc_greedy_cluster_bruteforce(tc_ctx *ctx, int kmer_size, uint32_t sketch_size, int containment,
+                                            double threshold, int32_t *rep_of, uint32_t *n_clusters)
+{
+    TC_CHECK(containment || sketch_size > 0, "tc_greedy_cluster_bruteforce: sketch_size == 0");
+    TC_CHECK(threshold < 1.0, "tc_greedy_cluster_bruteforce: threshold must be < 1 (pairs without a shared hash "
+             "have distance 1 and are never candidates)");
+    return greedy_impl(ctx, kmer_size, containment, threshold, true, sketch_size, rep_of, n_clusters);
 }

@@ -54,6 +54,7 @@ struct tc_ctx {
     uint64_t edge_cap = 0;
     unsigned long long *d_edge_count = nullptr;  // [0] = count, [1] = overflow flag, [2] = tile counter
     uint64_t n_edges = 0;
+    uint32_t edges_semb_size = 0;     // > 0: the edges carry semantic-B counts taken with this sketchSize
     int32_t *d_comp = nullptr;
 
     // representative table of the greedy scan (K5): same interleaved layout, members in creation order
@@ -87,11 +88,13 @@ struct tc_ctx {
 int tc_scratch(tc_ctx *ctx, size_t bytes, void **out);
 
 // tile-kernel entry points (k3_tile.cu)
-int tc_launch_tiles_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
-int tc_launch_tiles_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts);
+// semb_size > 0 selects semantic B (Mash union-limited merge, MinHash.cpp:982-1101) with that sketchSize
+int tc_launch_tiles_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out,
+                           uint32_t semb_size = 0);
+int tc_launch_tiles_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t semb_size = 0);
 int tc_launch_tiles_rep_matrix(tc_ctx *ctx, uint32_t q0, uint32_t q1, uint32_t *d_common, uint32_t *d_first_hit);
 int tc_launch_tiles_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment,
-                          double jmin, uint32_t part, uint32_t nparts);
+                          double jmin, uint32_t part, uint32_t nparts, uint32_t semb_size = 0);
 // hash-join pass (k3h_join.cu)
 int tc_kh_prepare(tc_ctx *ctx);
 int tc_launch_join_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);

@@ -242,6 +242,27 @@ extern "C" int tc_pair_common(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0
     return rc;
 }
 
+extern "C" int tc_pair_common_b(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1,
+                                uint32_t sketch_size, uint32_t *out)
+{
+    TC_CUDA(cudaSetDevice(ctx->device));
+    TC_CHECK(ctx->n > 0, "tc_pair_common_b: no sketches uploaded");
+    TC_CHECK(sketch_size > 0, "tc_pair_common_b: sketch_size == 0");
+    TC_CHECK(i0 <= i1 && i1 <= ctx->n && j0 <= j1 && j1 <= ctx->n, "tc_pair_common_b: range out of bounds");
+    const size_t cells = (size_t)(i1 - i0) * (j1 - j0);
+    if (!cells) return 0;
+    uint32_t *d_out = nullptr;
+    TC_CUDA(cudaMalloc(&d_out, cells * 4));
+    int rc = tc_launch_tiles_matrix(ctx, i0, i1, j0, j1, d_out, sketch_size);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { tc_set_error("tc_pair_common_b: %s", cudaGetErrorString(e)); rc = 1; }
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------ dense pass
 static int ensure_edges(tc_ctx *ctx)
 {
@@ -257,8 +278,8 @@ static int ensure_edges(tc_ctx *ctx)
     return 0;
 }
 
-extern "C" int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint64_t *n_pairs,
-                                uint64_t *n_edges)
+static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32_t part, uint32_t nparts,
+                              uint64_t *n_pairs, uint64_t *n_edges)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0, "tc_allpairs_pass: no sketches uploaded");
@@ -269,8 +290,10 @@ extern "C" int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t 
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), ctx->stream));
     // TCLUST_PASS_IMPL=merge selects the first-generation tiled merge kernel (k3_tile.cu)
     const char *impl = getenv("TCLUST_PASS_IMPL");
-    const bool use_merge = impl && !strcmp(impl, "merge");
-    if (use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts) : tc_launch_join_edges(ctx, radio, part, nparts)) return 1;
+    // semantic B needs the ordered merge (the stop rule depends on the union order): merge kernel only
+    const bool use_merge = semb_size > 0 || (impl && !strcmp(impl, "merge"));
+    ctx->edges_semb_size = semb_size;
+    if (use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts, semb_size) : tc_launch_join_edges(ctx, radio, part, nparts)) return 1;
     unsigned long long cnt[2];
     TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -309,6 +332,19 @@ extern "C" int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t 
     return 0;
 }
 
+extern "C" int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint64_t *n_pairs,
+                                uint64_t *n_edges)
+{
+    return allpairs_pass_impl(ctx, radio, 0, part, nparts, n_pairs, n_edges);
+}
+
+extern "C" int tc_allpairs_pass_b(tc_ctx *ctx, uint32_t sketch_size, uint32_t part, uint32_t nparts,
+                                  uint64_t *n_pairs, uint64_t *n_edges)
+{
+    TC_CHECK(sketch_size > 0, "tc_allpairs_pass_b: sketch_size == 0");
+    return allpairs_pass_impl(ctx, 0, sketch_size, part, nparts, n_pairs, n_edges);
+}
+
 extern "C" int tc_edges_download(tc_ctx *ctx, tc_pair *out, uint64_t cap, uint64_t *n)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
@@ -324,37 +360,41 @@ extern "C" int tc_edges_download(tc_ctx *ctx, tc_pair *out, uint64_t cap, uint64
 // -------------------------------------------------------------------------------- Boruvka
 // similarity key: ~bits(J); J computed exactly as the reference's host code does
 // (MST.cpp:1489-1492: (double)common / (size0+size1-common); :1505-1507: / min(size0,size1)).
-__device__ __forceinline__ unsigned long long edge_key(const tc_pair &e, const uint32_t *size, int containment)
+// mode: TC_DIST_MASH_A (0) denom = |A|+|B|-common; TC_DIST_AAF (1) / TC_DIST_CONTAIN_B (3) denom = min size;
+// TC_DIST_MASH_B (2) denom = min(sketchSize, |A|+|B|-common_B)  (MinHash.cpp:1079-1097)
+__device__ __forceinline__ unsigned long long edge_key(const tc_pair &e, const uint32_t *size, int mode, uint32_t semb)
 {
     const uint32_t s0 = size[e.i], s1 = size[e.j];
-    const uint32_t denom = containment ? min(s0, s1) : (s0 + s1 - e.common);
+    const uint32_t uni = s0 + s1 - e.common;
+    const uint32_t denom = (mode == 1 || mode == 3) ? min(s0, s1) : mode == 2 ? min(semb, uni) : uni;
     const double J = denom == 0 ? 0.0 : __ddiv_rn((double)e.common, (double)denom);
     return ~(unsigned long long)__double_as_longlong(J);
 }
 
 __global__ void boruvka_phase1_kernel(const tc_pair *edges, unsigned long long n_edges, const uint32_t *size,
-                                      const int32_t *comp, int containment, unsigned long long *best_key)
+                                      const int32_t *comp, int containment, uint32_t semb,
+                                      unsigned long long *best_key)
 {
     for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges;
          e += (unsigned long long)gridDim.x * blockDim.x) {
         const tc_pair p = edges[e];
         const int32_t ci = comp[p.i], cj = comp[p.j];
         if (ci == cj) continue;
-        const unsigned long long k = edge_key(p, size, containment);
+        const unsigned long long k = edge_key(p, size, containment, semb);
         atomicMin(&best_key[ci], k);
         atomicMin(&best_key[cj], k);
     }
 }
 __global__ void boruvka_phase2_kernel(const tc_pair *edges, unsigned long long n_edges, const uint32_t *size,
-                                      const int32_t *comp, int containment, const unsigned long long *best_key,
-                                      unsigned long long *best_edge)
+                                      const int32_t *comp, int containment, uint32_t semb,
+                                      const unsigned long long *best_key, unsigned long long *best_edge)
 {
     for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges;
          e += (unsigned long long)gridDim.x * blockDim.x) {
         const tc_pair p = edges[e];
         const int32_t ci = comp[p.i], cj = comp[p.j];
         if (ci == cj) continue;
-        const unsigned long long k = edge_key(p, size, containment);
+        const unsigned long long k = edge_key(p, size, containment, semb);
         const unsigned long long id = ((unsigned long long)p.i << 32) | p.j;
         if (k == best_key[ci]) atomicMin(&best_edge[ci], id);
         if (k == best_key[cj]) atomicMin(&best_edge[cj], id);
@@ -381,10 +421,13 @@ extern "C" int tc_boruvka_phase1(tc_ctx *ctx, int containment, uint64_t *best_ke
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->d_comp, "tc_boruvka_phase1: component labels not uploaded");
+    TC_CHECK(containment >= 0 && containment <= 3, "tc_boruvka_phase1: distance mode %d unknown", containment);
+    TC_CHECK((containment == TC_DIST_MASH_B) == (ctx->edges_semb_size > 0),
+             "tc_boruvka_phase1: distance mode %d does not match the pass that produced the edges", containment);
     TC_CUDA(cudaMemsetAsync(best_key_dev, 0xFF, (size_t)ctx->n * 8, ctx->stream));
     if (ctx->n_edges) {
         boruvka_phase1_kernel<<<boruvka_grid(ctx), 256, 0, ctx->stream>>>(
-            ctx->d_edges, ctx->n_edges, ctx->d_size, ctx->d_comp, containment,
+            ctx->d_edges, ctx->n_edges, ctx->d_size, ctx->d_comp, containment, ctx->edges_semb_size,
             reinterpret_cast<unsigned long long *>(best_key_dev));
         ctx->launches++;
     }
@@ -400,7 +443,7 @@ extern "C" int tc_boruvka_phase2(tc_ctx *ctx, int containment, const uint64_t *b
     TC_CUDA(cudaMemsetAsync(best_edge_dev, 0xFF, (size_t)ctx->n * 8, ctx->stream));
     if (ctx->n_edges) {
         boruvka_phase2_kernel<<<boruvka_grid(ctx), 256, 0, ctx->stream>>>(
-            ctx->d_edges, ctx->n_edges, ctx->d_size, ctx->d_comp, containment,
+            ctx->d_edges, ctx->n_edges, ctx->d_size, ctx->d_comp, containment, ctx->edges_semb_size,
             reinterpret_cast<const unsigned long long *>(best_key_dev),
             reinterpret_cast<unsigned long long *>(best_edge_dev));
         ctx->launches++;
@@ -440,11 +483,43 @@ extern "C" double tc_dist_from_key(uint64_t key, int containment, int kmer_size)
     double J;
     memcpy(&J, &bits, 8);
     const double inv_kmer_size = 1.0 / kmer_size;
+    if (containment == TC_DIST_MASH_B || containment == TC_DIST_CONTAIN_B) {
+        // MinHash::distance / containDistance (MinHash.cpp:1102-1153): divide by k, clamp at 1
+        if (J == 1.0) return 0.0;
+        double d = -std::log(2 * J / (1. + J)) / kmer_size;
+        if (d > 1) d = 1;
+        return d;
+    }
     if (J == 1.0) return 0.0;
     if (J == 0.0) return 1.0;
     if (containment) return -inv_kmer_size * std::log(J);
     double ratio = (2.0 * J) / (1.0 + J);
     return -inv_kmer_size * std::log(ratio);
+}
+extern "C" double tc_jaccard_b(int common_b, int size0, int size1, int sketch_size)
+{
+    // MinHash::jaccard (MinHash.cpp:1079-1100): denom = union consumed, completed and capped at sketchSize
+    long long denom = (long long)size0 + size1 - common_b;
+    if (denom > sketch_size) denom = sketch_size;
+    return (double)common_b / (double)denom;
+}
+extern "C" double tc_distance_b(int common_b, int size0, int size1, int sketch_size, int kmer_size)
+{
+    // MinHash::distance (MinHash.cpp:1125-1153)
+    const double jaccard_ = tc_jaccard_b(common_b, size0, size1, sketch_size);
+    if (jaccard_ == 1.0) return 0;
+    double distance = -std::log(2 * jaccard_ / (1. + jaccard_)) / kmer_size;
+    if (distance > 1) distance = 1;
+    return distance;
+}
+extern "C" double tc_contain_distance(int common, int size0, int size1, int kmer_size)
+{
+    // MinHash::containDistance over containJaccard (MinHash.cpp:908-979, 1102-1123)
+    const double jaccard_ = (double)common / (double)std::min(size0, size1);
+    if (jaccard_ == 1.0) return 0;
+    double distance = -std::log(2 * jaccard_ / (1. + jaccard_)) / kmer_size;
+    if (distance > 1) distance = 1;
+    return distance;
 }
 
 // ------------------------------------------------------------------- single-GPU MST driver
@@ -456,13 +531,16 @@ struct HostUF {
 };
 }  // namespace
 
-extern "C" int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double threshold, tc_edge *out, uint64_t *n_out)
+// mode = distance mode of the Boruvka keys; complete = add weight-1 edges between the components that share no
+// hash (the brute-force reference builds the MST of the complete graph)
+static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t semb_size, bool complete,
+                    tc_edge *out, uint64_t *n_out)
 {
+    const int containment = mode;
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0, "tc_mst: no sketches uploaded");
     const uint32_t n = ctx->n;
-    const int radio = tc_radio(threshold, kmer_size);
-    if (tc_allpairs_pass(ctx, radio, 0, 1, nullptr, nullptr)) return 1;
+    if (allpairs_pass_impl(ctx, radio, semb_size, 0, 1, nullptr, nullptr)) return 1;
     uint64_t *d_key = nullptr, *d_edge = nullptr;
     TC_CUDA(cudaMalloc(&d_key, (size_t)n * 8));
     TC_CUDA(cudaMalloc(&d_edge, (size_t)n * 8));
@@ -497,6 +575,17 @@ extern "C" int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double thresh
     }
     cudaFree(d_key); cudaFree(d_edge);
     if (rc) return rc;
+    if (complete) {
+        // pairs without a shared hash have distance exactly 1 (J = 0): chain the remaining components
+        int32_t first_root = -1, first_v = -1;
+        for (uint32_t v = 0; v < n; v++) {
+            const int32_t r = uf.find((int32_t)v);
+            if (first_root < 0) { first_root = r; first_v = (int32_t)v; continue; }
+            if (r == first_root) continue;
+            uf.p[r] = first_root;
+            mst.push_back(tc_edge{(int32_t)v, first_v, 1.0});
+        }
+    }
     std::sort(mst.begin(), mst.end(), [](const tc_edge &x, const tc_edge &y) {
         if (x.dist != y.dist) return x.dist < y.dist;
         if (x.pre != y.pre) return x.pre < y.pre;
@@ -505,4 +594,19 @@ extern "C" int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double thresh
     if (out) std::copy(mst.begin(), mst.end(), out);
     if (n_out) *n_out = mst.size();
     return 0;
+}
+
+extern "C" int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double threshold, tc_edge *out, uint64_t *n_out)
+{
+    TC_CHECK(containment == 0 || containment == 1, "tc_mst: containment must be 0 or 1");
+    return mst_impl(ctx, kmer_size, containment, tc_radio(threshold, kmer_size), 0, false, out, n_out);
+}
+
+extern "C" int tc_mst_bruteforce(tc_ctx *ctx, int kmer_size, uint32_t sketch_size, int containment, tc_edge *out,
+                                 uint64_t *n_out)
+{
+    if (containment)   // containDistance: full intersection / min size, no size-ratio filter
+        return mst_impl(ctx, kmer_size, TC_DIST_CONTAIN_B, 0x7fffffff, 0, true, out, n_out);
+    TC_CHECK(sketch_size > 0, "tc_mst_bruteforce: sketch_size == 0");
+    return mst_impl(ctx, kmer_size, TC_DIST_MASH_B, 0, sketch_size, true, out, n_out);
 }

@@ -159,3 +159,35 @@ def test_reference_cli_accepts_our_folder_live(oracle, tmp_path):
     _, labels, _ = oracle.clusters_from_mst(mst, len(sk), 0.05)
     mine = sorted(sorted(names[i] for i in np.nonzero(labels == c)[0]) for c in range(labels.max() + 1))
     assert mine == ref
+
+
+SEMB_CASES = ["eq200", "rag200", "rag64", "eq1000"]
+
+
+def semb_case(name):
+    z = np.load(os.path.join(GOLD, "semb", "semb.npz"))
+    off = z[name + "_off"].astype(np.int64)
+    sk = [z[name + "_hashes"][off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    s, k, thr6 = (int(x) for x in z[name + "_param"])
+    return z, sk, s, k, thr6 / 1e6
+
+
+@pytest.mark.parametrize("name", SEMB_CASES)
+def test_semantic_B_golden(oracle, name):
+    """a-11/a-12/a-16: MinHash::jaccard/distance/containDistance, modifyMST and greedyCluster of the unmodified
+    reference (tools/make_golden_semb.py) vs the oracle restatement."""
+    z, sk, s, k, thr = semb_case(name)
+    pairs = z[name + "_pairs"]
+    idx = 0
+    for i in range(len(sk)):
+        for j in range(i):
+            c, den = oracle.common_B(sk[i], sk[j], s)
+            assert c / den == pairs[idx, 0]
+            assert oracle.distance_B(sk[i], sk[j], s, k) == pairs[idx, 1]
+            assert oracle.contain_distance(sk[i], sk[j], k) == pairs[idx, 2]
+            idx += 1
+    for tag, contain in (("", False), ("_contain", True)):
+        mst = oracle.mst_bruteforce(sk, k, s, contain)
+        assert np.array_equal(np.sort(mst["dist"]), z[name + "_mst_w" + tag])
+        _, rep = oracle.greedy_bruteforce(sk, k, s, thr, contain)
+        assert np.array_equal(rep, z[name + "_rep" + tag])

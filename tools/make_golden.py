@@ -16,6 +16,8 @@ Fixtures:
   presketched/               synthetic sketch folder written by sketch_io + the reference's cluster text
                              for clust-mst and clust-greedy --presketched
   kssd/                      clust-mst --fast -l run: kssd.hash.sketch + cluster text
+  semb/                      semantic-B vectors (tools/make_golden_semb.py): MinHash::jaccard/distance/
+                             containDistance of all pairs, modifyMST weights, greedyCluster centres
 """
 import glob
 import gzip
@@ -166,6 +168,10 @@ def main():
                 shutil.copy(os.path.join(d, fn), out)
         shutil.copy(os.path.join(tmp, "clusters.txt"), out)
         meta["kssd"] = {"cmd": " ".join(cmd[1:]), "stderr_tail": p.stderr.decode()[-600:]}
+    # ---- 5. semantic-B brute-force paths (MinHash::distance, modifyMST, greedyCluster)
+    import make_golden_semb
+    make_golden_semb.main()
+    meta["semb"] = {"cmd": "oracle/_ref/ref_harness pairsdump|mstb|greedyb (tools/make_golden_semb.py)"}
     json.dump(meta, open(os.path.join(GOLD, "MANIFEST.json"), "w"), indent=1)
     subprocess.call(["du", "-sh", GOLD])
 
