@@ -330,8 +330,16 @@ def run_pairs(args):
             line["cpu_baseline"] = {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r.get("threads", 1),
                                     "kind": kind, "sample": "all pairs of the first %d sketches (%d pairs), "
                                     "MinHash::distance AVX2 build" % (min(args.ref_sample, n), r["pairs"])}
-        print(json.dumps(line), flush=True)
     ctx.close()
+    # ---- second half of BASELINE.json's metric: genomes sketched/sec (configs[1] shape), same JSON line
+    if not args.no_sketch:
+        import bench_sketch
+        sargs = argparse.Namespace(**vars(args))
+        m = bench_sketch.reduce_ranks(torch, dist, bench_sketch.measure(sargs, local_rank, rank, world, dist))
+        if rank == 0:
+            line["sketch"] = bench_sketch.sketch_block(sargs, m, world, None, with_cpu=(world == 1 and not args.no_cpu))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -339,7 +347,7 @@ def run_pairs(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pairs", choices=["pairs", "sketch"])
@@ -349,6 +357,7 @@ def main():
     ap.add_argument("--e2e-genomes", type=int, default=128, help="genomes per e2e step (sketch workload)")
     ap.add_argument("--ref-sample", type=int, default=4000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sketch", action="store_true", help="pairs workload: skip the sketch leg of the line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -118,10 +118,53 @@ def cpu_update(args, threads):
     return r
 
 
+def sketch_block(args, m, world, clocks=None, with_cpu=True):
+    """The sketch-leg numbers as a JSON-able dict (same keys as a bench line)."""
+    from bench import measured_peak
+    peak, how = measured_peak()
+    ng, glen, s = m["genomes"], m["genome_len"], m["s"]
+    value = world * ng / (m["ms_per_step"] / 1e3)
+    alg_bytes = ng * (glen + 8 * s)
+    achieved = alg_bytes / (m["ms_per_step"] / 1e3) / 1e9
+    blk = {"metric": "genomes sketched/sec", "value": value, "unit": "genomes/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": "sketch-only: %d synthetic %d bp genomes per GPU and step, k=21 s=1000 "
+                                  "(BASELINE.json configs[1] shape, device-generated)" % (ng, glen),
+                      "l2": "input %.1f GB per step > 126 MB L2" % (ng * glen / 1e9),
+                      "gbp_per_s": world * m["gbp_per_s"]},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": None, "peak_source": how, "kernel": "k1_sketch_segment_kernel",
+                        "note": "algorithmic bytes = L + 8s per genome (SURVEY 8d); K1 is integer-issue bound "
+                                "(Murmur3 = ten 64-bit multiplies per window), not HBM bound: see DESIGN.md K1"},
+           "e2e": {"value": world * m["e2e_genomes_per_s"], "unit": "genomes/s",
+                   "h2d_bytes_per_step": m["h2d_bytes"] * world, "d2h_bytes_per_step": m["d2h_bytes"] * world,
+                   "genomes_per_step": m["e2e_genomes"] * world, "ms_per_step": m["e2e_ms_per_step"]},
+           "gpu_launches": m["launches"]}
+    if clocks is not None:
+        blk["clocks"] = clocks
+    tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tp):
+        try:
+            prof = json.load(open(tp))
+            blk["roofline"]["traffic"] = prof.get("dram_bytes_per_launch_at_bench_size")
+            blk["roofline"]["binding_units"] = {k: prof[k] for k in prof if k.endswith("_pct")}
+        except Exception:
+            pass
+    if with_cpu:
+        threads = os.cpu_count() or 1
+        r = cpu_update(args, threads)
+        if r:
+            blk["cpu_baseline"] = {"value": r["genomes_per_s"], "unit": "genomes/s", "cores": r["threads"],
+                                   "kind": "reference", "sample": "%d genomes of %d bp, MinHash::update AVX2 build"
+                                   % (r["genomes"], r["len"])}
+    return blk
+
+
 def run_sketch(args):
     """--workload sketch: the sketch leg as the main JSON line."""
     import torch
-    from bench import ClockSampler, dist_env, measured_peak
+    from bench import ClockSampler, dist_env
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
     dist = None
@@ -133,39 +176,23 @@ def run_sketch(args):
         sampler.start()
     m = measure(args, local_rank, rank, world, dist)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([m["ms_per_step"], m["e2e_ms_per_step"], float(m["launches"])], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        m["ms_per_step"], m["e2e_ms_per_step"], m["launches"] = float(tm[0]), float(tm[1]), int(ts[2])
+    m = reduce_ranks(torch, dist, m)
     if rank == 0:
-        peak, how = measured_peak()
-        ng, glen, s = m["genomes"], m["genome_len"], m["s"]
-        value = world * ng / (m["ms_per_step"] / 1e3)
-        alg_bytes = ng * (glen + 8 * s)
-        achieved = alg_bytes / (m["ms_per_step"] / 1e3) / 1e9
-        line = {"metric": "genomes sketched/sec", "value": value, "unit": "genomes/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "config": {"workload": "sketch-only: %d synthetic %d bp genomes per GPU and step, k=21 s=1000 "
-                                       "(BASELINE.json configs[1] shape, device-generated)" % (ng, glen),
-                           "l2": "input %.1f GB per step > 126 MB L2" % (ng * glen / 1e9),
-                           "gbp_per_s": world * m["gbp_per_s"]},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": how, "kernel": "k1_sketch_segment_kernel",
-                             "note": "algorithmic bytes = L + 8s per genome (SURVEY 8d); K1 is INT32-ALU bound "
-                                     "(Murmur3 64-bit multiplies), see DESIGN.md K1"},
-                "e2e": {"value": world * m["e2e_genomes_per_s"], "unit": "genomes/s",
-                        "h2d_bytes_per_step": m["h2d_bytes"] * world, "d2h_bytes_per_step": m["d2h_bytes"] * world,
-                        "genomes_per_step": m["e2e_genomes"] * world},
-                "gpu_launches": m["launches"], "clocks": clocks}
-        if world == 1 and not args.no_cpu:
-            threads = os.cpu_count() or 1
-            r = cpu_update(args, threads)
-            if r:
-                line["cpu_baseline"] = {"value": r["genomes_per_s"], "unit": "genomes/s", "cores": r["threads"],
-                                        "kind": "reference", "sample": "%d genomes of %d bp, MinHash::update AVX2 build"
-                                        % (r["genomes"], r["len"])}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(sketch_block(args, m, world, clocks, with_cpu=(world == 1 and not args.no_cpu))), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def reduce_ranks(torch, dist, m):
+    """max of the times over the ranks, sum of the launches"""
+    if dist is None:
+        return m
+    t = torch.tensor([m["ms_per_step"], m["e2e_ms_per_step"], float(m["launches"])], dtype=torch.float64, device="cuda")
+    tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+    m = dict(m)
+    m["ms_per_step"], m["e2e_ms_per_step"], m["launches"] = float(tm[0]), float(tm[1]), int(ts[2])
+    m["e2e_genomes_per_s"] = m["e2e_genomes"] / (m["e2e_ms_per_step"] / 1e3)
+    m["genomes_per_s"] = m["genomes"] / (m["ms_per_step"] / 1e3)
+    m["gbp_per_s"] = m["genomes"] * m["genome_len"] / (m["ms_per_step"] / 1e3) / 1e9
+    return m

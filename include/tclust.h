@@ -52,6 +52,11 @@ uint64_t tc_kernel_launches(const tc_ctx *ctx);
 /* CUDA stream (cudaStream_t) the context launches on, for event timing by the caller */
 void *tc_stream(const tc_ctx *ctx);
 
+/* page-locked host memory for sequence buffers handed to tc_sketch_* (the FASTA feeder parses straight into
+ * it): copies from it overlap the kernels; pageable buffers work too, only slower. */
+void *tc_host_alloc(size_t bytes);
+void  tc_host_free(void *p);
+
 /* ---- HP-1: sketch construction ------------------------------------------------------- */
 /*
  * MinHash bottom-s sketches of `ngenomes` genomes.  Replaces, per genome,
@@ -63,6 +68,8 @@ void *tc_stream(const tc_ctx *ctx);
  * of record r (non-decreasing).  k <= 32.  sketch_size[g] = s of genome g.
  * out_hashes: ngenomes rows of out_stride u64 (out_stride >= max sketch_size); row g holds
  * out_n[g] <= sketch_size[g] hashes ascending (the s smallest distinct).
+ * The call pipelines batches of whole genomes (about TCLUST_SKETCH_CHUNK_MB = 64 MB of sequence each) over
+ * two device staging buffers: the H2D copy of batch c+1 overlaps the kernels of batch c.
  */
 int tc_sketch_minhash(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off,
                       const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes, int k,

@@ -19,7 +19,7 @@ PAIR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("common", "<u4")])
 # every symbol include/tclust.h declares (tests check the built library exports all of them)
 SYMBOLS = [
     "tc_version", "tc_last_error", "tc_ctx_create", "tc_ctx_destroy", "tc_kernel_launches", "tc_stream",
-    "tc_sketch_minhash", "tc_sketch_minhash_dev", "tc_sketch_kssd", "tc_sketch_kssd_dev",
+    "tc_host_alloc", "tc_host_free", "tc_sketch_minhash", "tc_sketch_minhash_dev", "tc_sketch_kssd", "tc_sketch_kssd_dev",
     "tc_sketches_upload", "tc_sketches_upload_dev", "tc_pair_common", "tc_allpairs_pass",
     "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_mst",
     "tc_greedy_scan", "tc_greedy_cluster",
@@ -56,6 +56,10 @@ def lib():
     L.tc_kernel_launches.restype = C.c_uint64
     L.tc_stream.argtypes = [vp]
     L.tc_stream.restype = vp
+    L.tc_host_alloc.argtypes = [C.c_size_t]
+    L.tc_host_alloc.restype = vp
+    L.tc_host_free.argtypes = [vp]
+    L.tc_host_free.restype = None
     sk = [vp, vp, u64p, u32p, C.c_uint64, C.c_uint32, C.c_int, u32p, C.c_uint32, vp, C.c_uint64, vp]
     L.tc_sketch_minhash.argtypes = sk
     L.tc_sketch_minhash_dev.argtypes = sk

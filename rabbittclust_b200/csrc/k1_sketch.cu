@@ -23,6 +23,8 @@
 #include "tc_common.cuh"
 #include "k_sort.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -130,17 +132,50 @@ __device__ __noinline__ unsigned long long k1_compact_step(uint64_t *buf, uint32
     return *s_tau;
 }
 
+// complement of 4 packed bytes: "TGAC"[(c>>1)&3] per byte (MinHash.cpp:1185-1195), two PRMT table look-ups
+__device__ __forceinline__ uint32_t comp4(uint32_t v)
+{
+    const uint32_t idx = (v >> 1) & 0x03030303u;           // byte t = 2-bit table index of base t
+    const uint32_t t = idx | (idx >> 4);                    // byte0 = i0 | i1<<4, byte2 = i2 | i3<<4
+    const uint32_t sel = __byte_perm(t, 0u, 0x4420);        // selector nibbles i0, i1, i2, i3
+    return __byte_perm(0x43414754u, 0u, sel);               // table bytes 'T','G','A','C'
+}
+__device__ __forceinline__ uint64_t comp8(uint64_t x)
+{
+    return ((uint64_t)comp4((uint32_t)(x >> 32)) << 32) | comp4((uint32_t)x);
+}
+// bytes [8i+u, 8i+u+8) of a little-endian word array (u compile-time after unrolling)
+template <int N>
+__device__ __forceinline__ uint64_t ext_word(const uint64_t (&b)[N], int i, int u)
+{
+    return u == 0 ? b[i] : (b[i] >> (8 * u)) | (b[i + 1] << (64 - 8 * u));
+}
+
+// Inner loop (second generation).  A thread keeps the next 8*(NW+1) bases of its run in registers twice:
+//   fb[]  the upper-cased bytes in memory order (little-endian words): the forward k-mer of the window at
+//         byte offset u is the byte range [u, u+k) -- already the word layout Murmur3 reads;
+//   cb[]  the complemented bytes, stored shifted by r-8 bytes (r = k - 8*(NW-1) = bytes in the last k-mer
+//         word), so that the reverse-complement k-mer, read BACKWARDS, is the byte range [u, u+8*NW) of cb:
+//         word NW-1-i of that range is word i of the reverse-complement strand in BIG-endian byte order.
+// Big-endian words compare like memcmp, so the canonical-strand test is one 64-bit compare of
+// bswap(forward word 0) with the top cb word (later words only when the first 8 bytes tie); the words of the
+// chosen strand are produced by one PRMT per 32-bit half (identity on the forward half or byte-reversal of
+// the cb half, selected by the permute control).  All byte offsets inside the 8-window step are
+// compile-time constants; k enters only through two masks and one funnel shift per 8 loaded bases.
 template <int NW>
 __global__ void __launch_bounds__(K1_THREADS) k1_sketch_segment_kernel(const K1Args a)
 {
+    constexpr int NB = NW + 1;
     extern __shared__ __align__(16) uint8_t k1_smem[];
     __shared__ uint32_t s_count, s_seg;
     __shared__ unsigned long long s_tau;
     __shared__ __align__(8) uint32_t s_scratch[40];
     uint64_t *buf = a.use_global ? a.gscratch + (size_t)blockIdx.x * a.cap : reinterpret_cast<uint64_t *>(k1_smem);
     const int k = a.k;
-    const int last_shift = 56 - 8 * ((k - 1) & 7);                 // bit position of byte k-1 in its BE word
-    const uint64_t last_mask = ~0ULL << last_shift;                 // keeps bytes 0..(k-1)%8 of the last word
+    const int r = k - 8 * (NW - 1);                                  // 1..8 bytes in the last k-mer word
+    const uint64_t lomask = r == 8 ? ~0ULL : ((1ULL << (8 * r)) - 1ULL);   // forward last word: low r bytes
+    const int csh = 8 * (8 - r);                                     // cb is stored csh bits "late"
+    const uint64_t himask = ~0ULL << csh;                            // reverse last word: high r bytes
 
     for (;;) {
         if (threadIdx.x == 0) s_seg = atomicAdd(a.seg_counter, 1u);
@@ -157,50 +192,68 @@ __global__ void __launch_bounds__(K1_THREADS) k1_sketch_segment_kernel(const K1A
         R = (R + K1_STEP - 1) / K1_STEP * K1_STEP;
         const uint32_t w0 = threadIdx.x * R;
         const uint32_t nwin_t = w0 < seg.nwin ? min(R, seg.nwin - w0) : 0u;
-        const uint32_t nbases = R + (uint32_t)k - 1;               // bases every thread steps through (uniform)
-        const unsigned long long p0 = seg.seq_start + w0;          // first base of this thread
+        const uint32_t nbytes_t = nwin_t ? nwin_t + (uint32_t)k - 1 : 0u;   // bytes this thread may touch
+        const unsigned long long p0 = seg.seq_start + w0;                    // first base of this thread
         const uint64_t *wp = reinterpret_cast<const uint64_t *>(a.seq + (p0 & ~7ULL));
         const int mis = (int)(p0 & 7ULL) * 8;
-        // does this thread have anything to read? (threads beyond the segment must not touch memory)
-        const bool active = nwin_t > 0;
-        uint64_t cur = active ? __ldg(wp) : 0;
+        uint64_t cur = nbytes_t ? __ldg(wp) : 0;
+        uint32_t jw = 0;                                                     // next 8-byte word of the run
+        // bytes [p0+8*jw, +8), upper-cased; zero when the thread needs none of them
+        auto next_word = [&]() -> uint64_t {
+            const bool need = 8u * jw < nbytes_t;
+            const uint64_t nxt = need ? __ldg(wp + jw + 1) : 0;
+            const uint64_t w = mis ? ((cur >> mis) | (nxt << (64 - mis))) : cur;
+            cur = nxt;
+            jw++;
+            return need ? upper8(w) : 0;
+        };
 
-        uint64_t F[NW], Rv[NW];
+        uint64_t fb[NB], cb[NB];
+        uint64_t cprev = 0;
 #pragma unroll
-        for (int i = 0; i < NW; i++) { F[i] = 0; Rv[i] = 0; }
+        for (int i = 0; i < NB; i++) {
+            fb[i] = next_word();
+            const uint64_t c = comp8(fb[i]);
+            cb[i] = (c << csh) | ((cprev >> 1) >> (63 - csh));
+            cprev = c;
+        }
         unsigned long long tau = s_tau;
 
-        for (uint32_t b0 = 0; b0 < nbases; b0 += K1_STEP) {
-            // next 8 bases of this thread: bytes [p0+b0, p0+b0+8) assembled from two aligned words
-            const bool need = active && (b0 < nwin_t + (uint32_t)k - 1);
-            const uint64_t nxt = need ? __ldg(wp + (b0 >> 3) + 1) : 0;
-            uint64_t eight = mis ? ((cur >> mis) | (nxt << (64 - mis))) : cur;
-            cur = nxt;
-            eight = upper8(eight);
+        for (uint32_t g0 = 0; g0 < R; g0 += K1_STEP) {
 #pragma unroll
             for (int half = 0; half < K1_STEP / K1_VOTE; half++) {
 #pragma unroll
                 for (int jj = 0; jj < K1_VOTE; jj++) {
-                    const int j = half * K1_VOTE + jj;
-                    const uint32_t c = (uint32_t)(eight >> (8 * j)) & 0xffu;
-                    const uint32_t comp = __byte_perm(0x43414754u, 0u, ((c >> 1) & 3u) | 0x4440u);   // "TGAC"[(c>>1)&3]
-                    // forward strand: drop byte 0, append c at byte k-1
+                    const int u = half * K1_VOTE + jj;
+                    if (g0 + u < nwin_t) {
+                        uint64_t fw[NW], rx[NW];
 #pragma unroll
-                    for (int i = 0; i < NW - 1; i++) F[i] = (F[i] << 8) | (F[i + 1] >> 56);
-                    F[NW - 1] = (F[NW - 1] << 8) | ((uint64_t)c << last_shift);
-                    // reverse-complement strand: prepend comp(c), drop byte k-1
+                        for (int i = 0; i < NW; i++) fw[i] = ext_word<NB>(fb, i, u);
+                        fw[NW - 1] &= lomask;
 #pragma unroll
-                    for (int i = NW - 1; i > 0; i--) Rv[i] = (Rv[i] >> 8) | (Rv[i - 1] << 56);
-                    Rv[0] = (Rv[0] >> 8) | ((uint64_t)comp << 56);
-                    Rv[NW - 1] &= last_mask;
-                    const uint32_t bi = b0 + j;                         // base index just consumed
-                    if (bi >= (uint32_t)k - 1 && bi - ((uint32_t)k - 1) < nwin_t) {
-                        bool fwd = true;                                // memcmp(fwd, rev, k) <= 0
+                        for (int i = 0; i < NW - 1; i++) rx[i] = ext_word<NB>(cb, NW - 1 - i, u);
+                        rx[NW - 1] = ext_word<NB>(cb, 0, u) & himask;
+                        // memcmp(forward, reverse, k) <= 0 on big-endian words
+                        bool fwd = true;
+                        {
+                            const uint64_t f0 = bswap64(fw[0]);
+                            if (f0 != rx[0]) fwd = f0 < rx[0];
+                            else {
 #pragma unroll
-                        for (int i = NW - 1; i >= 0; i--) fwd = (F[i] != Rv[i]) ? (F[i] < Rv[i]) : fwd;
+                                for (int i = NW - 1; i >= 1; i--) {
+                                    const uint64_t fi = bswap64(fw[i]);
+                                    fwd = (fi != rx[i]) ? (fi < rx[i]) : fwd;
+                                }
+                            }
+                        }
+                        const uint32_t sel = fwd ? 0x3210u : 0x4567u;   // identity on a / byte reversal of b
                         uint64_t w[NW];
 #pragma unroll
-                        for (int i = 0; i < NW; i++) w[i] = bswap64(fwd ? F[i] : Rv[i]);
+                        for (int i = 0; i < NW; i++) {
+                            const uint32_t lo = __byte_perm((uint32_t)fw[i], (uint32_t)(rx[i] >> 32), sel);
+                            const uint32_t hi = __byte_perm((uint32_t)(fw[i] >> 32), (uint32_t)rx[i], sel);
+                            w[i] = ((uint64_t)hi << 32) | lo;
+                        }
                         const uint64_t h = murmur_h1<NW>(w, k, a.seed);
                         if (h <= tau) {
                             const uint32_t pos = atomicAdd(&s_count, 1u);
@@ -215,6 +268,13 @@ __global__ void __launch_bounds__(K1_THREADS) k1_sketch_segment_kernel(const K1A
                     tau = k1_compact_step(buf, a.cap, s, s_scratch, &s_count, &s_tau, &a.tau[seg.genome]);
                 }
             }
+            // slide the register window by one word (8 bases)
+#pragma unroll
+            for (int i = 0; i < NB - 1; i++) { fb[i] = fb[i + 1]; cb[i] = cb[i + 1]; }
+            fb[NB - 1] = next_word();
+            const uint64_t c = comp8(fb[NB - 1]);
+            cb[NB - 1] = (c << csh) | ((cprev >> 1) >> (63 - csh));
+            cprev = c;
         }
         __syncthreads();
         {   // final compaction of this segment and write-out of the partial sketch
@@ -247,7 +307,6 @@ __global__ void __launch_bounds__(K1_THREADS) k1_merge_kernel(const K1MergeArgs 
 {
     extern __shared__ __align__(16) uint8_t k1_smem[];
     __shared__ __align__(8) uint32_t s_scratch[40];
-    __shared__ uint32_t s_total;
     const uint32_t g = blockIdx.x;
     uint64_t *buf = a.use_global ? a.gscratch + (size_t)g * a.cap : reinterpret_cast<uint64_t *>(k1_smem);
     const uint32_t sb = a.genome_seg_begin[g], se = a.genome_seg_begin[g + 1];
@@ -263,27 +322,185 @@ __global__ void __launch_bounds__(K1_THREADS) k1_merge_kernel(const K1MergeArgs 
     uint32_t m = total;
     if (se - sb > 1) m = cta_compact(buf, total, a.cap, s, s_scratch, &dummy);
     else if (m > s) m = s;
-    if (threadIdx.x == 0) { a.out_n[g] = m; s_total = m; }
+    if (threadIdx.x == 0) a.out_n[g] = m;
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) a.out[(size_t)g * a.out_stride + i] = buf[i];
 }
 
 uint32_t next_pow2(uint64_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
 
 template <int NW>
-int launch_segments(tc_ctx *ctx, const K1Args &a, int grid, size_t smem)
+int launch_segments(tc_ctx *ctx, cudaStream_t st, const K1Args &a, int grid, size_t smem)
 {
     if (smem > 48 * 1024)
         TC_CUDA(cudaFuncSetAttribute(k1_sketch_segment_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k1_sketch_segment_kernel<NW><<<grid, K1_THREADS, smem, ctx->stream>>>(a);
+    k1_sketch_segment_kernel<NW><<<grid, K1_THREADS, smem, st>>>(a);
     ctx->launches++;
     TC_CUDA(cudaGetLastError());
     return 0;
 }
 
-// seq_dev: sequence bytes on the device (readable 16 B past the end). Everything else host.
-int sketch_minhash_impl(tc_ctx *ctx, const uint8_t *seq_dev, const uint64_t *rec_off, const uint32_t *rec2genome,
-                        uint64_t nrec, uint32_t ngenomes, int k, const uint32_t *sketch_size, uint32_t seed,
-                        uint64_t *out_dev, uint64_t out_stride, uint32_t *out_n_dev)
+// ------------------------------------------------------------------------------ host driver
+// A batch (whole genomes) is planned on the host (segments), its metadata goes through a pinned staging
+// buffer, and two kernels are enqueued.  Nothing here synchronises: the host-buffer entry point pipelines
+// batches over two slots so that the H2D copy of batch c+1 (copy stream) overlaps the kernels of batch c.
+struct K1Slot {
+    uint8_t *d_seq = nullptr;  size_t seq_cap = 0;      // staged sequence bytes (host-buffer path only)
+    uint8_t *h_meta = nullptr; size_t h_meta_cap = 0;   // pinned: segments, genome->segment ranges, sketch sizes
+    uint8_t *d_meta = nullptr; size_t d_meta_cap = 0;   // the same on the device + partial sketches, counters
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool used = false;
+};
+struct K1Workspace {
+    K1Slot slot[2];
+    cudaStream_t copy_stream = nullptr;
+    uint64_t *d_out = nullptr; size_t out_cap = 0;      // staged outputs (host-buffer path)
+    uint32_t *d_n = nullptr;   size_t n_cap = 0;
+};
+
+K1Workspace *k1_ws(tc_ctx *ctx)
+{
+    if (!ctx->k1_ws) {
+        K1Workspace *w = new K1Workspace();
+        if (cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete w; return nullptr; }
+        for (K1Slot &sl : w->slot) {
+            cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+        }
+        ctx->k1_ws = w;
+    }
+    return static_cast<K1Workspace *>(ctx->k1_ws);
+}
+
+struct K1Plan {
+    std::vector<K1Seg> segs;
+    std::vector<uint32_t> gbegin;
+    uint64_t out_off = 0, max_merge = 1;
+    uint32_t smax = 0;
+};
+
+inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// records [r0, r1) = genomes [g0, g1); sequence byte x of the input lives at seq_dev[x - base_off]
+void k1_plan(const tc_ctx *ctx, const uint64_t *rec_off, const uint32_t *rec2genome, uint64_t r0, uint64_t r1,
+             uint32_t g0, uint32_t g1, int k, const uint32_t *sketch_size, uint64_t base_off, K1Plan &pl)
+{
+    const uint32_t ngl = g1 - g0;
+    uint64_t total_win = 0;
+    for (uint64_t r = r0; r < r1; r++) {
+        const uint64_t len = rec_off[r + 1] - rec_off[r];
+        if (len >= (uint64_t)k) total_win += len - k + 1;
+    }
+    const uint64_t want_ctas = (uint64_t)ctx->num_sms * 24;
+    uint64_t segw = std::min<uint64_t>(std::max<uint64_t>(total_win / std::max<uint64_t>(want_ctas, 1), 1u << 15), 1u << 20);
+    segw = (segw + K1_THREADS * K1_STEP - 1) / (K1_THREADS * K1_STEP) * (K1_THREADS * K1_STEP);
+    pl.segs.clear();
+    pl.gbegin.assign(ngl + 1, 0);
+    pl.out_off = 0; pl.max_merge = 1; pl.smax = 0;
+    uint64_t r = r0;
+    for (uint32_t g = g0; g < g1; g++) {
+        pl.gbegin[g - g0] = (uint32_t)pl.segs.size();
+        pl.smax = std::max(pl.smax, sketch_size[g]);
+        for (; r < r1 && rec2genome[r] == g; r++) {
+            const uint64_t len = rec_off[r + 1] - rec_off[r];
+            if (len < (uint64_t)k) continue;
+            const uint64_t nwin = len - k + 1;
+            for (uint64_t w = 0; w < nwin; w += segw) {
+                K1Seg sg;
+                sg.seq_start = rec_off[r] - base_off + w;
+                sg.nwin = (uint32_t)std::min<uint64_t>(segw, nwin - w);
+                sg.genome = g - g0;
+                sg.out_off = pl.out_off;
+                pl.out_off += sketch_size[g];
+                pl.segs.push_back(sg);
+            }
+        }
+        const uint32_t nsg = (uint32_t)pl.segs.size() - pl.gbegin[g - g0];
+        pl.max_merge = std::max<uint64_t>(pl.max_merge, (uint64_t)nsg * sketch_size[g]);
+    }
+    pl.gbegin[ngl] = (uint32_t)pl.segs.size();
+}
+
+// enqueue the two kernels of one planned batch on `st`; out_dev / out_n_dev / sketch_size point at genome g0
+int k1_enqueue(tc_ctx *ctx, K1Slot &sl, cudaStream_t st, const uint8_t *seq_dev, const K1Plan &pl, uint32_t ngl, int k,
+               uint32_t seed, const uint32_t *sketch_size, uint64_t *out_dev, uint64_t out_stride, uint32_t *out_n_dev)
+{
+    const uint32_t nseg = (uint32_t)pl.segs.size();
+    // ---- layout of the metadata block
+    const size_t o_segs = 0;
+    const size_t o_gbegin = al16(o_segs + std::max<size_t>(nseg, 1) * sizeof(K1Seg));
+    const size_t o_ss = al16(o_gbegin + (size_t)(ngl + 1) * 4);
+    const size_t host_bytes = al16(o_ss + (size_t)ngl * 4);           // uploaded part
+    const size_t o_pn = host_bytes;
+    const size_t o_tau = al16(o_pn + std::max<size_t>(nseg, 1) * 4);
+    const size_t o_counter = al16(o_tau + (size_t)ngl * 8);
+    const size_t o_partial = al16(o_counter + 16);
+    size_t total = al16(o_partial + std::max<uint64_t>(pl.out_off, 1) * 8);
+
+    K1Args a{};
+    a.cap = std::max<uint32_t>(next_pow2((uint64_t)pl.smax + 2 * K1_STEP_CAND + 1), 4096);
+    size_t smem1 = (size_t)a.cap * 8;
+    a.use_global = smem1 > 160 * 1024;
+    const int per_sm = a.use_global ? 4 : (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (smem1 + 1024)));
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(nseg, (uint64_t)ctx->num_sms * per_sm));
+    size_t o_scr1 = 0, o_scr2 = 0;
+    if (a.use_global) { o_scr1 = total; total = al16(total + (size_t)grid * a.cap * 8); smem1 = 0; }
+    K1MergeArgs m{};
+    m.cap = std::max<uint32_t>(next_pow2(pl.max_merge), 2);
+    size_t smem2 = (size_t)m.cap * 8;
+    m.use_global = smem2 > 160 * 1024;
+    if (m.use_global) { o_scr2 = total; total = al16(total + (size_t)ngl * m.cap * 8); smem2 = 0; }
+
+    // ---- capacity (grows only; the caller guarantees the slot is idle)
+    if (host_bytes > sl.h_meta_cap) {
+        if (sl.h_meta) cudaFreeHost(sl.h_meta);
+        sl.h_meta = nullptr; sl.h_meta_cap = 0;
+        TC_CUDA(cudaMallocHost(&sl.h_meta, host_bytes * 2));
+        sl.h_meta_cap = host_bytes * 2;
+    }
+    if (total > sl.d_meta_cap) {
+        if (sl.d_meta) cudaFree(sl.d_meta);
+        sl.d_meta = nullptr; sl.d_meta_cap = 0;
+        TC_CUDA(cudaMalloc(&sl.d_meta, total + total / 4));
+        sl.d_meta_cap = total + total / 4;
+    }
+    if (nseg) memcpy(sl.h_meta + o_segs, pl.segs.data(), (size_t)nseg * sizeof(K1Seg));
+    memcpy(sl.h_meta + o_gbegin, pl.gbegin.data(), (size_t)(ngl + 1) * 4);
+    memcpy(sl.h_meta + o_ss, sketch_size, (size_t)ngl * 4);
+    TC_CUDA(cudaMemcpyAsync(sl.d_meta, sl.h_meta, host_bytes, cudaMemcpyHostToDevice, st));
+    TC_CUDA(cudaMemsetAsync(sl.d_meta + o_pn, 0, o_tau - o_pn, st));
+    TC_CUDA(cudaMemsetAsync(sl.d_meta + o_tau, 0xFF, (size_t)ngl * 8, st));
+    TC_CUDA(cudaMemsetAsync(sl.d_meta + o_counter, 0, 16, st));
+
+    const K1Seg *d_segs = reinterpret_cast<const K1Seg *>(sl.d_meta + o_segs);
+    const uint32_t *d_ss = reinterpret_cast<const uint32_t *>(sl.d_meta + o_ss);
+    uint32_t *d_pn = reinterpret_cast<uint32_t *>(sl.d_meta + o_pn);
+    uint64_t *d_partial = reinterpret_cast<uint64_t *>(sl.d_meta + o_partial);
+    if (nseg > 0) {
+        a.seq = seq_dev; a.segs = d_segs; a.nseg = nseg; a.k = k; a.seed = seed; a.sketch_size = d_ss;
+        a.tau = reinterpret_cast<unsigned long long *>(sl.d_meta + o_tau);
+        a.partial = d_partial; a.partial_n = d_pn;
+        a.seg_counter = reinterpret_cast<unsigned int *>(sl.d_meta + o_counter);
+        a.gscratch = a.use_global ? reinterpret_cast<uint64_t *>(sl.d_meta + o_scr1) : nullptr;
+        const int nw = (k + 7) / 8;
+        const int rc = nw == 1 ? launch_segments<1>(ctx, st, a, grid, smem1) : nw == 2 ? launch_segments<2>(ctx, st, a, grid, smem1)
+                     : nw == 3 ? launch_segments<3>(ctx, st, a, grid, smem1) : launch_segments<4>(ctx, st, a, grid, smem1);
+        if (rc) return rc;
+    }
+    m.partial = d_partial; m.partial_n = d_pn; m.segs = d_segs;
+    m.genome_seg_begin = reinterpret_cast<const uint32_t *>(sl.d_meta + o_gbegin); m.sketch_size = d_ss;
+    m.out = out_dev; m.out_stride = out_stride; m.out_n = out_n_dev;
+    m.gscratch = m.use_global ? reinterpret_cast<uint64_t *>(sl.d_meta + o_scr2) : nullptr;
+    if (smem2 > 48 * 1024)
+        TC_CUDA(cudaFuncSetAttribute(k1_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k1_merge_kernel<<<ngl, K1_THREADS, smem2, st>>>(m);
+    ctx->launches++;
+    TC_CUDA(cudaGetLastError());
+    sl.used = true;
+    return 0;
+}
+
+int k1_validate(const uint64_t *rec_off, const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes, int k,
+                const uint32_t *sketch_size, uint64_t out_stride)
 {
     TC_CHECK(k >= 1 && k <= 32, "tc_sketch_minhash: k=%d unsupported (1..32, as the reference's AVX2 path)", k);
     TC_CHECK(ngenomes > 0, "tc_sketch_minhash: no genomes");
@@ -294,118 +511,42 @@ int sketch_minhash_impl(tc_ctx *ctx, const uint8_t *seq_dev, const uint64_t *rec
     }
     TC_CHECK(out_stride >= smax, "tc_sketch_minhash: out_stride %llu < max sketch size %u",
              (unsigned long long)out_stride, smax);
-    // ---- segments
-    uint64_t total_win = 0;
     for (uint64_t r = 0; r < nrec; r++) {
         TC_CHECK(rec_off[r + 1] >= rec_off[r], "tc_sketch_minhash: record offsets not monotone");
         TC_CHECK(r == 0 || rec2genome[r] >= rec2genome[r - 1], "tc_sketch_minhash: rec2genome must be non-decreasing");
         TC_CHECK(rec2genome[r] < ngenomes, "tc_sketch_minhash: rec2genome[%llu] out of range", (unsigned long long)r);
-        const uint64_t len = rec_off[r + 1] - rec_off[r];
-        if (len >= (uint64_t)k) total_win += len - k + 1;
     }
-    const uint64_t want_ctas = (uint64_t)ctx->num_sms * 24;
-    uint64_t segw = std::min<uint64_t>(std::max<uint64_t>(total_win / std::max<uint64_t>(want_ctas, 1), 1u << 15), 1u << 20);
-    segw = (segw + K1_THREADS * K1_STEP - 1) / (K1_THREADS * K1_STEP) * (K1_THREADS * K1_STEP);
-    std::vector<K1Seg> segs;
-    std::vector<uint32_t> gbegin(ngenomes + 1, 0);
-    uint64_t out_off = 0;
-    {
-        uint64_t r = 0;
-        for (uint32_t g = 0; g < ngenomes; g++) {
-            gbegin[g] = (uint32_t)segs.size();
-            for (; r < nrec && rec2genome[r] == g; r++) {
-                const uint64_t len = rec_off[r + 1] - rec_off[r];
-                if (len < (uint64_t)k) continue;
-                const uint64_t nwin = len - k + 1;
-                for (uint64_t w = 0; w < nwin; w += segw) {
-                    K1Seg s;
-                    s.seq_start = rec_off[r] + w;
-                    s.nwin = (uint32_t)std::min<uint64_t>(segw, nwin - w);
-                    s.genome = g;
-                    s.out_off = out_off;
-                    out_off += sketch_size[g];
-                    segs.push_back(s);
-                }
-            }
-        }
-        gbegin[ngenomes] = (uint32_t)segs.size();
-    }
-    const uint32_t nseg = (uint32_t)segs.size();
-    uint32_t max_seg_per_genome = 1;
-    uint64_t max_merge = 1;
-    for (uint32_t g = 0; g < ngenomes; g++) {
-        max_seg_per_genome = std::max(max_seg_per_genome, gbegin[g + 1] - gbegin[g]);
-        max_merge = std::max<uint64_t>(max_merge, (uint64_t)(gbegin[g + 1] - gbegin[g]) * sketch_size[g]);
-    }
-    cudaStream_t st = ctx->stream;
-    // ---- device metadata
-    K1Seg *d_segs = nullptr; uint32_t *d_gbegin = nullptr, *d_ss = nullptr, *d_pn = nullptr;
-    unsigned long long *d_tau = nullptr; uint64_t *d_partial = nullptr; unsigned int *d_counter = nullptr;
-    uint64_t *d_scr1 = nullptr, *d_scr2 = nullptr;
-    int rc = 0;
-    auto cleanup = [&]() {
-        cudaFree(d_segs); cudaFree(d_gbegin); cudaFree(d_ss); cudaFree(d_pn); cudaFree(d_tau); cudaFree(d_partial);
-        cudaFree(d_counter); cudaFree(d_scr1); cudaFree(d_scr2);
-    };
-#define K1_TRY(x) do { if ((x) != cudaSuccess) { tc_set_error("tc_sketch_minhash: %s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); cleanup(); return 1; } } while (0)
-    K1_TRY(cudaMalloc(&d_segs, std::max<size_t>(nseg, 1) * sizeof(K1Seg)));
-    K1_TRY(cudaMalloc(&d_gbegin, (size_t)(ngenomes + 1) * 4));
-    K1_TRY(cudaMalloc(&d_ss, (size_t)ngenomes * 4));
-    K1_TRY(cudaMalloc(&d_pn, std::max<size_t>(nseg, 1) * 4));
-    K1_TRY(cudaMalloc(&d_tau, (size_t)ngenomes * 8));
-    K1_TRY(cudaMalloc(&d_partial, std::max<uint64_t>(out_off, 1) * 8));
-    K1_TRY(cudaMalloc(&d_counter, 4));
-    K1_TRY(cudaMemcpyAsync(d_segs, segs.data(), nseg * sizeof(K1Seg), cudaMemcpyHostToDevice, st));
-    K1_TRY(cudaMemcpyAsync(d_gbegin, gbegin.data(), (size_t)(ngenomes + 1) * 4, cudaMemcpyHostToDevice, st));
-    K1_TRY(cudaMemcpyAsync(d_ss, sketch_size, (size_t)ngenomes * 4, cudaMemcpyHostToDevice, st));
-    K1_TRY(cudaMemsetAsync(d_tau, 0xFF, (size_t)ngenomes * 8, st));
-    K1_TRY(cudaMemsetAsync(d_counter, 0, 4, st));
-    K1_TRY(cudaMemsetAsync(d_pn, 0, std::max<size_t>(nseg, 1) * 4, st));
-
-    if (nseg > 0) {
-        K1Args a{};
-        a.seq = seq_dev; a.segs = d_segs; a.nseg = nseg; a.k = k; a.seed = seed; a.sketch_size = d_ss; a.tau = d_tau;
-        a.partial = d_partial; a.partial_n = d_pn; a.seg_counter = d_counter;
-        a.cap = std::max<uint32_t>(next_pow2((uint64_t)smax + 2 * K1_STEP_CAND + 1), 4096);
-        size_t smem = (size_t)a.cap * 8;
-        a.use_global = smem > 160 * 1024;
-        int per_sm = a.use_global ? 4 : (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (smem + 1024)));
-        int grid = (int)std::min<uint64_t>(nseg, (uint64_t)ctx->num_sms * per_sm);
-        if (a.use_global) {
-            K1_TRY(cudaMalloc(&d_scr1, (size_t)grid * a.cap * 8));
-            a.gscratch = d_scr1;
-            smem = 0;
-        }
-        const int nw = (k + 7) / 8;
-        rc = nw == 1 ? launch_segments<1>(ctx, a, grid, smem) : nw == 2 ? launch_segments<2>(ctx, a, grid, smem)
-           : nw == 3 ? launch_segments<3>(ctx, a, grid, smem) : launch_segments<4>(ctx, a, grid, smem);
-        if (rc) { cleanup(); return rc; }
-    }
-    {
-        K1MergeArgs m{};
-        m.partial = d_partial; m.partial_n = d_pn; m.segs = d_segs; m.genome_seg_begin = d_gbegin; m.sketch_size = d_ss;
-        m.out = out_dev; m.out_stride = out_stride; m.out_n = out_n_dev;
-        m.cap = std::max<uint32_t>(next_pow2(max_merge), 2);
-        size_t smem = (size_t)m.cap * 8;
-        m.use_global = smem > 160 * 1024;
-        if (m.use_global) {
-            K1_TRY(cudaMalloc(&d_scr2, (size_t)ngenomes * m.cap * 8));
-            m.gscratch = d_scr2;
-            smem = 0;
-        }
-        if (smem > 48 * 1024)
-            K1_TRY(cudaFuncSetAttribute(k1_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k1_merge_kernel<<<ngenomes, K1_THREADS, smem, st>>>(m);
-        ctx->launches++;
-        K1_TRY(cudaGetLastError());
-    }
-    K1_TRY(cudaStreamSynchronize(st));
-#undef K1_TRY
-    cleanup();
     return 0;
 }
 
 }  // namespace
+
+void tc_k1_free(tc_ctx *ctx)
+{
+    K1Workspace *w = static_cast<K1Workspace *>(ctx->k1_ws);
+    if (!w) return;
+    for (K1Slot &sl : w->slot) {
+        cudaFree(sl.d_seq); cudaFree(sl.d_meta);
+        if (sl.h_meta) cudaFreeHost(sl.h_meta);
+        if (sl.copied) cudaEventDestroy(sl.copied);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    cudaFree(w->d_out); cudaFree(w->d_n);
+    if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
+    delete w;
+    ctx->k1_ws = nullptr;
+}
+
+extern "C" void *tc_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        tc_set_error("tc_host_alloc: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void tc_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" int tc_sketch_minhash_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const uint64_t *rec_off,
                                      const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes, int k,
@@ -413,8 +554,15 @@ extern "C" int tc_sketch_minhash_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const
                                      uint64_t out_stride, uint32_t *out_n_dev)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
-    return sketch_minhash_impl(ctx, seqs_dev, rec_off, rec2genome, nrec, ngenomes, k, sketch_size, seed,
-                               out_hashes_dev, out_stride, out_n_dev);
+    if (k1_validate(rec_off, rec2genome, nrec, ngenomes, k, sketch_size, out_stride)) return 1;
+    K1Workspace *ws = k1_ws(ctx);
+    TC_CHECK(ws, "tc_sketch_minhash: cannot create the workspace");
+    K1Plan pl;
+    k1_plan(ctx, rec_off, rec2genome, 0, nrec, 0, ngenomes, k, sketch_size, 0, pl);
+    if (k1_enqueue(ctx, ws->slot[0], ctx->stream, seqs_dev, pl, ngenomes, k, seed, sketch_size, out_hashes_dev,
+                   out_stride, out_n_dev)) return 1;
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 extern "C" int tc_sketch_minhash(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off, const uint32_t *rec2genome,
@@ -422,31 +570,75 @@ extern "C" int tc_sketch_minhash(tc_ctx *ctx, const uint8_t *seqs, const uint64_
                                  uint64_t *out_hashes, uint64_t out_stride, uint32_t *out_n)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
-    const uint64_t nbytes = nrec ? rec_off[nrec] : 0;
-    uint8_t *d_seq = nullptr; uint64_t *d_out = nullptr; uint32_t *d_n = nullptr;
-    TC_CUDA(cudaMalloc(&d_seq, nbytes + 64));
-    int rc = 1;
-    do {
-        if (cudaMalloc(&d_out, std::max<uint64_t>((uint64_t)ngenomes * out_stride, 1) * 8) != cudaSuccess ||
-            cudaMalloc(&d_n, std::max<uint32_t>(ngenomes, 1) * 4) != cudaSuccess) {
-            tc_set_error("tc_sketch_minhash: out of device memory");
-            break;
+    if (k1_validate(rec_off, rec2genome, nrec, ngenomes, k, sketch_size, out_stride)) return 1;
+    K1Workspace *ws = k1_ws(ctx);
+    TC_CHECK(ws, "tc_sketch_minhash: cannot create the workspace");
+    cudaStream_t st = ctx->stream, cs = ws->copy_stream;
+    // staged outputs
+    const size_t out_elems = std::max<uint64_t>((uint64_t)ngenomes * out_stride, 1);
+    if (out_elems > ws->out_cap) {
+        cudaFree(ws->d_out); ws->d_out = nullptr; ws->out_cap = 0;
+        TC_CUDA(cudaMalloc(&ws->d_out, out_elems * 8));
+        ws->out_cap = out_elems;
+    }
+    if (ngenomes > ws->n_cap) {
+        cudaFree(ws->d_n); ws->d_n = nullptr; ws->n_cap = 0;
+        TC_CUDA(cudaMalloc(&ws->d_n, (size_t)ngenomes * 4));
+        ws->n_cap = ngenomes;
+    }
+    // ---- batches of whole genomes, about TCLUST_SKETCH_CHUNK_MB (default 64) of sequence each
+    uint64_t chunk_bytes = 64ull << 20;
+    if (const char *e = getenv("TCLUST_SKETCH_CHUNK_MB")) chunk_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 1) << 20;
+    K1Plan pl;
+    uint64_t r0 = 0;
+    uint32_t g0 = 0, batch = 0;
+    int rc = 0;
+    while (g0 < ngenomes && !rc) {
+        // records of genomes [g0, g1)
+        uint32_t g1 = g0;
+        uint64_t r1 = r0;
+        const uint64_t b0 = r0 < nrec ? rec_off[r0] : (nrec ? rec_off[nrec] : 0);
+        for (;;) {
+            while (r1 < nrec && rec2genome[r1] == g1) r1++;
+            g1++;
+            const uint64_t b1 = r1 < nrec ? rec_off[r1] : (nrec ? rec_off[nrec] : 0);
+            if (g1 >= ngenomes || b1 - b0 >= chunk_bytes) break;
         }
-        if (cudaMemcpyAsync(d_seq, seqs, nbytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
-            cudaMemsetAsync(d_seq + nbytes, 0, 64, ctx->stream) != cudaSuccess) {
-            tc_set_error("tc_sketch_minhash: H2D copy failed");
-            break;
+        const uint64_t b1 = r1 < nrec ? rec_off[r1] : (nrec ? rec_off[nrec] : 0);
+        const uint64_t base = b0 & ~15ull;                       // keep the 8-byte alignment of the offsets
+        const size_t nbytes = (size_t)(b1 - base);
+        K1Slot &sl = ws->slot[batch & 1];
+        if (sl.used) {                                           // previous batch of this slot must be finished
+            if (cudaEventSynchronize(sl.done) != cudaSuccess) { tc_set_error("tc_sketch_minhash: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; break; }
         }
-        rc = sketch_minhash_impl(ctx, d_seq, rec_off, rec2genome, nrec, ngenomes, k, sketch_size, seed, d_out,
-                                 out_stride, d_n);
-        if (rc) break;
-        if (cudaMemcpyAsync(out_hashes, d_out, (uint64_t)ngenomes * out_stride * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-            cudaMemcpyAsync(out_n, d_n, (size_t)ngenomes * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        if (nbytes + 64 > sl.seq_cap) {
+            cudaFree(sl.d_seq); sl.d_seq = nullptr; sl.seq_cap = 0;
+            if (cudaMalloc(&sl.d_seq, nbytes + 64 + nbytes / 8) != cudaSuccess) { tc_set_error("tc_sketch_minhash: out of device memory (%zu bytes of sequence per batch)", nbytes); rc = 1; break; }
+            sl.seq_cap = nbytes + 64 + nbytes / 8;
+        }
+        if ((nbytes && cudaMemcpyAsync(sl.d_seq, seqs + base, nbytes, cudaMemcpyHostToDevice, cs) != cudaSuccess) ||
+            cudaMemsetAsync(sl.d_seq + nbytes, 0, 64, cs) != cudaSuccess ||
+            cudaEventRecord(sl.copied, cs) != cudaSuccess || cudaStreamWaitEvent(st, sl.copied, 0) != cudaSuccess) {
+            tc_set_error("tc_sketch_minhash: H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = 1; break;
+        }
+        k1_plan(ctx, rec_off, rec2genome, r0, r1, g0, g1, k, sketch_size, base, pl);
+        rc = k1_enqueue(ctx, sl, st, sl.d_seq, pl, g1 - g0, k, seed, sketch_size + g0, ws->d_out + (size_t)g0 * out_stride,
+                        out_stride, ws->d_n + g0);
+        if (!rc && cudaEventRecord(sl.done, st) != cudaSuccess) { tc_set_error("tc_sketch_minhash: event record failed"); rc = 1; }
+        g0 = g1; r0 = r1; batch++;
+    }
+    if (!rc) {
+        if (cudaMemcpyAsync(out_hashes, ws->d_out, (size_t)ngenomes * out_stride * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(out_n, ws->d_n, (size_t)ngenomes * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
             tc_set_error("tc_sketch_minhash: D2H copy failed");
             rc = 1;
         }
-    } while (0);
-    cudaFree(d_seq); cudaFree(d_out); cudaFree(d_n);
+    }
+    const cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(st);
+    if (!rc && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+        tc_set_error("tc_sketch_minhash: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        rc = 1;
+    }
     return rc;
 }

@@ -80,12 +80,16 @@ struct tc_ctx {
     const int32_t *kssd_dim_host = nullptr;
     size_t kssd_dim_n = 0;
 
+    // K1 pipeline workspace (k1_sketch.cu): staging slots, copy stream
+    void *k1_ws = nullptr;
+
     // scratch
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
 };
 
 int tc_scratch(tc_ctx *ctx, size_t bytes, void **out);
+void tc_k1_free(tc_ctx *ctx);
 
 // tile-kernel entry points (k3_tile.cu)
 // semb_size > 0 selects semantic B (Mash union-limited merge, MinHash.cpp:982-1101) with that sketchSize

@@ -78,6 +78,7 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     free_sketches(ctx);
     tc_rep_table_free(ctx);
+    tc_k1_free(ctx);
     cudaFree(ctx->d_edge_count);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_kssd_dim);

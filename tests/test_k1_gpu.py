@@ -89,3 +89,20 @@ def test_sketch_then_cluster_matches_reference_run(ctx, oracle):
     mine = sorted(sorted(info[i]["name"] for i in np.nonzero(labels == c)[0]) for c in range(labels.max() + 1))
     ref_c = sketch_io.parse_cluster_file(os.path.join(d, "clusters.txt"))
     assert mine == sorted(sorted(n for _, n in c) for c in ref_c)
+
+
+def test_sketch_pipelined_batches(ctx, oracle, monkeypatch):
+    """host-buffer entry point with 1 MB batches: 9 genomes of odd lengths -> several batches over the two staging
+    slots (copy of batch c+1 overlaps the kernels of batch c); offsets deliberately not 16-byte aligned"""
+    monkeypatch.setenv("TCLUST_SKETCH_CHUNK_MB", "1")
+    rng = np.random.default_rng(123)
+    lens = [400003, 700001, 5, 1300007, 250000, 999, 1048577, 31, 610001]
+    g = [[synth.random_genome(L, rng)] if L > 1000 else [synth.random_genome(L, rng), synth.random_genome(77, rng)]
+         for L in lens]
+    got = ctx.sketch_minhash(g, k=21, s=500)
+    for recs, h in zip(g, got):
+        assert np.array_equal(h, oracle.minhash_sketch(recs, 21, 500))
+    # the same input in one batch gives the same sketches
+    monkeypatch.setenv("TCLUST_SKETCH_CHUNK_MB", "4096")
+    again = ctx.sketch_minhash(g, k=21, s=500)
+    assert all(np.array_equal(a, b) for a, b in zip(got, again))
