@@ -68,7 +68,7 @@ void  tc_host_free(void *p);
  * of record r (non-decreasing).  k <= 32.  sketch_size[g] = s of genome g.
  * out_hashes: ngenomes rows of out_stride u64 (out_stride >= max sketch_size); row g holds
  * out_n[g] <= sketch_size[g] hashes ascending (the s smallest distinct).
- * The call pipelines batches of whole genomes (about TCLUST_SKETCH_CHUNK_MB = 64 MB of sequence each) over
+ * The call pipelines batches of whole genomes (about TCLUST_SKETCH_CHUNK_MB = 128 MB of sequence each) over
  * two device staging buffers: the H2D copy of batch c+1 overlaps the kernels of batch c.
  */
 int tc_sketch_minhash(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off,

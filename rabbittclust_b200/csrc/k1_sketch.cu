@@ -291,7 +291,11 @@ __global__ void __launch_bounds__(K1_THREADS) k1_sketch_segment_kernel(const K1A
     }
 }
 
-// merge the partial sketches of one genome: concat, sort, unique, truncate
+// merge the partial sketches of one genome.  The partials are sorted and distinct; they are appended to the
+// buffer segment by segment, cut at the running threshold tau (the s-th smallest distinct value merged so far;
+// binary search on the sorted partial), and the buffer is sorted/deduplicated/truncated whenever the next prefix
+// does not fit.  tau tightens after every compaction, so a genome with hundreds of segments needs only a few of
+// them; repeated k-mers shared by many segments just cost more compactions.
 struct K1MergeArgs {
     const uint64_t *partial;
     const uint32_t *partial_n;
@@ -299,7 +303,7 @@ struct K1MergeArgs {
     const uint32_t *genome_seg_begin;   // ngenomes+1
     const uint32_t *sketch_size;
     uint64_t *out; unsigned long long out_stride; uint32_t *out_n;
-    uint32_t cap;                       // buffer capacity (power of two)
+    uint32_t cap;                       // buffer capacity (power of two, >= 2 * largest sketch size)
     uint64_t *gscratch; int use_global;
 };
 
@@ -311,19 +315,37 @@ __global__ void __launch_bounds__(K1_THREADS) k1_merge_kernel(const K1MergeArgs 
     uint64_t *buf = a.use_global ? a.gscratch + (size_t)g * a.cap : reinterpret_cast<uint64_t *>(k1_smem);
     const uint32_t sb = a.genome_seg_begin[g], se = a.genome_seg_begin[g + 1];
     const uint32_t s = a.sketch_size[g];
-    uint32_t total = 0;
+    uint32_t count = 0, nsrc = 0;                 // block-uniform
+    unsigned long long tau = ~0ULL;
     for (uint32_t sg = sb; sg < se; sg++) {
-        const uint32_t m = a.partial_n[sg];
-        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) buf[total + i] = a.partial[a.segs[sg].out_off + i];
-        total += m;
+        const uint32_t n = a.partial_n[sg];
+        const uint64_t *p = a.partial + a.segs[sg].out_off;
+        auto prefix_len = [&]() {                 // #values <= tau (every thread runs the same search)
+            uint32_t lo = 0, hi = n;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (p[mid] <= tau) lo = mid + 1; else hi = mid;
+            }
+            return lo;
+        };
+        uint32_t m = prefix_len();
+        if (m == 0) continue;
+        if (count + m > a.cap) {
+            __syncthreads();
+            count = cta_compact(buf, count, a.cap, s, s_scratch, &tau);
+            __syncthreads();
+            m = prefix_len();
+            if (m == 0) continue;
+        }
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) buf[count + i] = p[i];
+        count += m;
+        nsrc++;
     }
     __syncthreads();
-    unsigned long long dummy = 0;
-    uint32_t m = total;
-    if (se - sb > 1) m = cta_compact(buf, total, a.cap, s, s_scratch, &dummy);
-    else if (m > s) m = s;
-    if (threadIdx.x == 0) a.out_n[g] = m;
-    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) a.out[(size_t)g * a.out_stride + i] = buf[i];
+    if (nsrc > 1) count = cta_compact(buf, count, a.cap, s, s_scratch, &tau);
+    else if (count > s) count = s;
+    if (threadIdx.x == 0) a.out_n[g] = count;
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) a.out[(size_t)g * a.out_stride + i] = buf[i];
 }
 
 uint32_t next_pow2(uint64_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
@@ -390,8 +412,11 @@ void k1_plan(const tc_ctx *ctx, const uint64_t *rec_off, const uint32_t *rec2gen
         const uint64_t len = rec_off[r + 1] - rec_off[r];
         if (len >= (uint64_t)k) total_win += len - k + 1;
     }
-    const uint64_t want_ctas = (uint64_t)ctx->num_sms * 24;
-    uint64_t segw = std::min<uint64_t>(std::max<uint64_t>(total_win / std::max<uint64_t>(want_ctas, 1), 1u << 15), 1u << 20);
+    // segments of 128 Ki .. 1 Mi windows: a segment re-discovers the bottom-s set on its own (about
+    // s*(1+ln(windows/s)) candidates pass its filter), so shorter segments spend more time sorting than hashing
+    // one wave of resident CTAs (6 per SM at s = 1000) when the batch is small enough for that
+    const uint64_t want_ctas = (uint64_t)ctx->num_sms * 6;
+    uint64_t segw = std::min<uint64_t>(std::max<uint64_t>(total_win / std::max<uint64_t>(want_ctas, 1), 1u << 17), 1u << 20);
     segw = (segw + K1_THREADS * K1_STEP - 1) / (K1_THREADS * K1_STEP) * (K1_THREADS * K1_STEP);
     pl.segs.clear();
     pl.gbegin.assign(ngl + 1, 0);
@@ -445,7 +470,7 @@ int k1_enqueue(tc_ctx *ctx, K1Slot &sl, cudaStream_t st, const uint8_t *seq_dev,
     size_t o_scr1 = 0, o_scr2 = 0;
     if (a.use_global) { o_scr1 = total; total = al16(total + (size_t)grid * a.cap * 8); smem1 = 0; }
     K1MergeArgs m{};
-    m.cap = std::max<uint32_t>(next_pow2(pl.max_merge), 2);
+    m.cap = std::max<uint32_t>(next_pow2(2ull * pl.smax), 4096);
     size_t smem2 = (size_t)m.cap * 8;
     m.use_global = smem2 > 160 * 1024;
     if (m.use_global) { o_scr2 = total; total = al16(total + (size_t)ngl * m.cap * 8); smem2 = 0; }
@@ -586,8 +611,8 @@ extern "C" int tc_sketch_minhash(tc_ctx *ctx, const uint8_t *seqs, const uint64_
         TC_CUDA(cudaMalloc(&ws->d_n, (size_t)ngenomes * 4));
         ws->n_cap = ngenomes;
     }
-    // ---- batches of whole genomes, about TCLUST_SKETCH_CHUNK_MB (default 64) of sequence each
-    uint64_t chunk_bytes = 64ull << 20;
+    // ---- batches of whole genomes, about TCLUST_SKETCH_CHUNK_MB (default 128) of sequence each
+    uint64_t chunk_bytes = 128ull << 20;
     if (const char *e = getenv("TCLUST_SKETCH_CHUNK_MB")) chunk_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 1) << 20;
     K1Plan pl;
     uint64_t r0 = 0;
