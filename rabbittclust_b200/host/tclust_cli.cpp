@@ -12,7 +12,16 @@
 //   forest / BFS clusters     src/MST.cpp:77-85,109-142
 //   printResult               src/MST_IO.cpp:136-179
 //   greedy cluster order      src/greedy.cpp:1321-1336,1358-1367
-// Out of scope: --append/--db/--save-rep, tree/linkage output, --dense, dbscan/leiden.
+//   --fast (KSSD, clust-mst)  src/main.cpp:603-636, src/sub_command.cpp:1934-2010,2317-2382 (tuning),
+//                             src/SketchInfo.cpp:994-1252 (list-mode driver), 60-102 (shuffled_dim),
+//                             src/Sketch_IO.cpp:36-86,136-167,228-282 (kssd.*.sketch), src/SketchInfo.cpp:1379-1467
+//                             (kssd.sketch.index/.dict), src/MST_IO.cpp:181-198 (kssd.info.mst + edge.mst)
+// FASTA feeder: files are decompressed/parsed on host threads into page-locked batch buffers
+// (tc_host_alloc); a batch is sketched by a background thread (tc_sketch_* pipelines its H2D copies) while the
+// next batch is being parsed.
+// Out of scope: --append/--db/--save-rep, tree/linkage output, --dense, dbscan/leiden,
+// clust-greedy --fast, --fast with a single multi-FASTA input (the reference's -i KSSD consumer is the
+// quirky variant).
 #include "../../include/tclust.h"
 #include <zlib.h>
 #include <sys/stat.h>
@@ -237,30 +246,140 @@ bool tune_parameters(Options &o)
     return true;
 }
 
+struct KssdParams { int id = 0, half_k = 0, half_subk = 0, drlevel = 0, genome_number = 0; };   // SketchInfo.h:52-58
+KssdParams g_kssd;                       // set by sketch_files when o.fast
+vector<int32_t> g_shuffled_dim;          // generate_shuffle_dim table (host only: glibc rand)
+
+// tune_kssd_parameters (src/sub_command.cpp:2317-2382)
+bool tune_kssd_parameters(Options &o)
+{
+    uint64_t max_size, min_size, avg_size;
+    cal_size(o, max_size, min_size, avg_size);
+    const int compression = 1 << (4 * o.drlevel);
+    const int sketch_size = avg_size / compression;
+    const double warning_rate = 0.01, recommend_rate = 0.0001;
+    int recommended = ceil(log(max_size * (1 - recommend_rate) / recommend_rate) / log(4));
+    int warning = ceil(log(max_size * (1 - warning_rate) / warning_rate) / log(4));
+    if (!o.set_kmer) o.kmer = recommended;
+    else if (o.kmer < warning) {
+        cerr << "the kmerSize " << o.kmer << " is too small for the maximum genome size of " << max_size << endl;
+        cerr << "replace the kmerSize to the: " << recommended << " for reducing the random collision of kmers" << endl;
+        o.kmer = recommended;
+    } else if (o.kmer > recommended + 3) {
+        cerr << "the kmerSize " << o.kmer << " maybe too large for the maximum genome size of " << max_size << endl;
+        cerr << "replace the kmerSize to the " << recommended << " for increasing the sensitivity of genome comparison" << endl;
+        o.kmer = recommended;
+    }
+    double min_jaccard = !o.containment ? 1.0 / sketch_size : 1.0 / (min_size / compression);
+    double max_dist = min_jaccard >= 1.0 ? 1.0 : -1.0 / o.kmer * log(2 * min_jaccard / (1.0 + min_jaccard));
+    cerr << "-----the max recommand distance threshold is: " << max_dist << endl;
+    if (o.threshold > max_dist) {
+        cerr << "ERROR: tune_parameters(), the threshold: " << o.threshold << " is out of the valid distance range estimated by Mash distance or AAF distance" << endl;
+        cerr << "Please set a distance threshold with -d option" << endl;
+        return false;
+    }
+    cerr << (o.by_file ? "-----sketch by file!" : "-----sketch by sequence!") << endl;
+    cerr << "-----the kmerSize is: " << o.kmer << endl;
+    cerr << "-----the thread number is: " << o.threads << endl;
+    cerr << "-----the threshold is: " << o.threshold << endl;
+    if (o.containment) cerr << "-----use the AAF distance, the sketchSize is approximately in proportion with 1/" << compression << endl;
+    else cerr << "-----use the Mash distance, the sketchSize is about: " << sketch_size << endl;
+    return true;
+}
+
+// generate_shuffle_dim (src/SketchInfo.cpp:60-102): identity permutation of 16^half_subk slots, Fisher-Yates
+// with glibc srand(23)/rand(), then again with srand(348842630).  glibc's rand() stream is part of the
+// reference's definition of the KSSD sketch, hence host-only.
+void shuffle_in_place(vector<int32_t> &arr, unsigned seed)
+{
+    srand(seed);
+    for (int i = (int)arr.size() - 1; i > 0; i--) std::swap(arr[i], arr[rand() % (i + 1)]);
+}
+void make_shuffled_dim(int half_subk)
+{
+    g_shuffled_dim.resize((size_t)1 << (4 * half_subk));
+    for (size_t i = 0; i < g_shuffled_dim.size(); i++) g_shuffled_dim[i] = (int32_t)i;
+    shuffle_in_place(g_shuffled_dim, 23);
+    shuffle_in_place(g_shuffled_dim, 348842630u);
+}
+
 // ---------------------------------------------------------------------------- sketching
+// page-locked, growable byte buffer (the H2D copies of tc_sketch_* overlap the kernels only from pinned memory)
+struct PinnedBuf {
+    uint8_t *p = nullptr; size_t cap = 0, len = 0;
+    void reserve(size_t need)
+    {
+        if (need <= cap) return;
+        const size_t nc = std::max<size_t>(need + need / 4, (size_t)64 << 20);
+        uint8_t *q = (uint8_t *)tc_host_alloc(nc);
+        if (!q) { cerr << "ERROR: cannot allocate " << nc << " bytes of page-locked memory, " << tc_last_error() << endl; exit(1); }
+        if (len) memcpy(q, p, len);
+        tc_host_free(p);
+        p = q; cap = nc;
+    }
+    void append(const uint8_t *src, size_t n) { reserve(len + n + 64); memcpy(p + len, src, n); len += n; }
+    size_t size() const { return len; }
+    ~PinnedBuf() { tc_host_free(p); }
+};
+
 struct Batch {
-    vector<uint8_t> seq; vector<uint64_t> rec_off{0}; vector<uint32_t> rec2genome, ssize;
+    PinnedBuf seq; vector<uint64_t> rec_off{0}; vector<uint32_t> rec2genome, ssize;
     vector<Genome> genomes;
-    void clear() { seq.clear(); rec_off.assign(1, 0); rec2genome.clear(); ssize.clear(); genomes.clear(); }
+    uint64_t longest = 0;
+    void clear() { seq.len = 0; rec_off.assign(1, 0); rec2genome.clear(); ssize.clear(); genomes.clear(); longest = 0; }
 };
 
 void flush_batch(tc_ctx *ctx, const Options &o, Batch &b, vector<Genome> &out)
 {
     if (b.genomes.empty()) return;
     const uint32_t ng = (uint32_t)b.genomes.size();
-    uint32_t smax = 1;
-    for (uint32_t s : b.ssize) smax = std::max(smax, s);
-    b.seq.resize(b.seq.size() + 64, 0);
-    vector<uint64_t> hashes((size_t)ng * smax);
+    b.seq.reserve(b.seq.len + 64);
+    memset(b.seq.p + b.seq.len, 0, 64);
+    vector<uint64_t> hashes;
     vector<uint32_t> out_n(ng);
-    tc_or_die(tc_sketch_minhash(ctx, b.seq.data(), b.rec_off.data(), b.rec2genome.data(), b.rec2genome.size(), ng, o.kmer,
-                                b.ssize.data(), 42, hashes.data(), smax, out_n.data()), "sketch generation");
+    uint64_t stride = 1;
+    if (o.fast) {
+        // survivors of the dimension filter: about L / 16^drlevel per genome; a repetitive genome can exceed any
+        // estimate (the row holds them before deduplication), so the call is retried with a longer row
+        stride = std::max<uint64_t>(1024, (b.longest >> (4 * o.drlevel)) * 2 + 1024);
+        for (;;) {
+            hashes.assign((size_t)ng * stride, 0);
+            const int rc = tc_sketch_kssd(ctx, b.seq.p, b.rec_off.data(), b.rec2genome.data(), b.rec2genome.size(), ng, o.kmer,
+                                          o.drlevel, g_shuffled_dim.data(), hashes.data(), stride, out_n.data());
+            if (!rc) break;
+            if (strstr(tc_last_error(), "more than out_stride") && stride < b.longest + 1024) { stride = std::min<uint64_t>(stride * 8, b.longest + 1024); continue; }
+            tc_or_die(rc, "kssd sketch generation");
+        }
+    } else {
+        for (uint32_t s : b.ssize) stride = std::max<uint64_t>(stride, s);
+        hashes.resize((size_t)ng * stride);
+        tc_or_die(tc_sketch_minhash(ctx, b.seq.p, b.rec_off.data(), b.rec2genome.data(), b.rec2genome.size(), ng, o.kmer,
+                                    b.ssize.data(), 42, hashes.data(), stride, out_n.data()), "sketch generation");
+    }
     for (uint32_t g = 0; g < ng; g++) {
-        b.genomes[g].hashes.assign(hashes.begin() + (size_t)g * smax, hashes.begin() + (size_t)g * smax + out_n[g]);
+        b.genomes[g].hashes.assign(hashes.begin() + (size_t)g * stride, hashes.begin() + (size_t)g * stride + out_n[g]);
         out.push_back(std::move(b.genomes[g]));
     }
     b.clear();
 }
+
+// two batches: one is being filled by the parser while the other is sketched by a background thread
+struct Feeder {
+    tc_ctx *ctx; const Options &o; vector<Genome> &out;
+    Batch batch[2]; int cur = 0; std::thread worker; bool running = false;
+    Feeder(tc_ctx *c, const Options &opt, vector<Genome> &dst) : ctx(c), o(opt), out(dst) {}
+    Batch &fill() { return batch[cur]; }
+    void wait() { if (running) { worker.join(); running = false; } }
+    void submit()                      // hand the filled batch to the GPU, continue in the other one
+    {
+        wait();                        // results are appended in submission order
+        Batch *b = &batch[cur];
+        worker = std::thread([this, b]() { flush_batch(ctx, o, *b, out); });
+        running = true;
+        cur ^= 1;
+    }
+    void finish() { submit(); wait(); }
+};
 
 // list mode: one genome per file (sketchFiles)
 void sketch_files(tc_ctx *ctx, const Options &o, vector<Genome> &out)
@@ -268,10 +387,19 @@ void sketch_files(tc_ctx *ctx, const Options &o, vector<Genome> &out)
     fprintf(stderr, "-----input fileList, sketch by file\n");
     vector<string> files = read_list(o.input);
     const size_t nfiles = files.size();
-    const uint64_t batch_bytes = 1ull << 30;
+    if (o.fast) {                                          // SketchInfo.cpp:1019-1031
+        const int half_k = (o.kmer + 1) / 2;
+        g_kssd.half_k = half_k;
+        g_kssd.half_subk = 6 - o.drlevel >= 2 ? 6 : o.drlevel + 2;
+        g_kssd.drlevel = o.drlevel;
+        g_kssd.id = (half_k << 8) + (g_kssd.half_subk << 4) + o.drlevel;
+        g_kssd.genome_number = (int)nfiles;
+        make_shuffled_dim(g_kssd.half_subk);
+    }
+    const uint64_t batch_bytes = 1ull << 29;
     struct Parsed { vector<uint8_t> seq; vector<Record> recs; int file_len = 0; bool ok = false; };
     size_t next = 0;
-    Batch b;
+    Feeder feeder(ctx, o, out);
     while (next < nfiles) {
         // read + parse a window of files on the host threads, then append them in list order
         const size_t win = std::min(nfiles - next, (size_t)std::max(o.threads * 4, 16));
@@ -284,7 +412,7 @@ void sketch_files(tc_ctx *ctx, const Options &o, vector<Genome> &out)
                 string text;
                 if (!read_whole_gz(files[next + i], text)) continue;
                 parse_fasta(text, true, parsed[i].seq, parsed[i].recs);
-                if (o.containment) { uint64_t u; file_size_like_reference(files[next + i], u, parsed[i].file_len); }
+                if (o.containment && !o.fast) { uint64_t u; file_size_like_reference(files[next + i], u, parsed[i].file_len); }
                 parsed[i].ok = true;
             }
         };
@@ -302,17 +430,19 @@ void sketch_files(tc_ctx *ctx, const Options &o, vector<Genome> &out)
             g.name = "noName"; g.comment = "noName";                    // :934-939
             if (!p.recs.empty()) { g.name = p.recs[0].name; if (p.recs[0].has_comment) g.comment = p.recs[0].comment; }
             g.total_len = total_len;
+            Batch &b = feeder.fill();
             const uint32_t gi = (uint32_t)b.genomes.size();
             const uint64_t base = b.seq.size();
-            b.seq.insert(b.seq.end(), p.seq.begin(), p.seq.end());
+            b.seq.append(p.seq.data(), p.seq.size());
             for (const Record &r : p.recs) { b.rec_off.push_back(base + r.end); b.rec2genome.push_back(gi); }
             b.ssize.push_back(o.containment ? (uint32_t)std::max(p.file_len / o.compress, 100) : (uint32_t)o.sketch_size);
+            b.longest = std::max<uint64_t>(b.longest, total_len);
             b.genomes.push_back(std::move(g));
-            if (b.seq.size() >= batch_bytes) flush_batch(ctx, o, b, out);
+            if (b.seq.size() >= batch_bytes) feeder.submit();
         }
         next += win;
     }
-    flush_batch(ctx, o, b, out);
+    feeder.finish();
     for (size_t i = 0; i < out.size(); i++) out[i].id = (int)i;
 }
 
@@ -325,20 +455,22 @@ void sketch_sequences(tc_ctx *ctx, const Options &o, vector<Genome> &out)
     vector<uint8_t> seq; vector<Record> recs;
     parse_fasta(text, false, seq, recs);
     text.clear(); text.shrink_to_fit();
-    Batch b;
+    Feeder feeder(ctx, o, out);
     for (const Record &r : recs) {
         const uint64_t len = r.end - r.begin;
         if (len < o.min_len) continue;                                   // SketchInfo.cpp:217
         Genome g;
         g.name = r.name; g.comment = r.comment; g.total_len = len;
+        Batch &b = feeder.fill();
         const uint32_t gi = (uint32_t)b.genomes.size();
-        b.seq.insert(b.seq.end(), seq.begin() + r.begin, seq.begin() + r.end);
+        b.seq.append(seq.data() + r.begin, len);
         b.rec_off.push_back(b.seq.size()); b.rec2genome.push_back(gi);
         b.ssize.push_back(o.containment ? (uint32_t)std::max((int)len / o.compress, 100) : (uint32_t)o.sketch_size);
+        b.longest = std::max<uint64_t>(b.longest, len);
         b.genomes.push_back(std::move(g));
-        if (b.seq.size() >= (1ull << 30)) flush_batch(ctx, o, b, out);
+        if (b.seq.size() >= (1ull << 29)) feeder.submit();
     }
-    flush_batch(ctx, o, b, out);
+    feeder.finish();
     for (size_t i = 0; i < out.size(); i++) out[i].id = (int)i;
 }
 
@@ -434,21 +566,148 @@ bool load_sketches(vector<Genome> &g, const string &folder, Options &o)
     return by_file;
 }
 
-void save_mst(const vector<Genome> &g, const vector<tc_edge> &mst, const string &folder, bool by_file)
+// ---- KSSD folder (src/Sketch_IO.cpp:36-86,136-167,228-282; index/dict src/SketchInfo.cpp:1379-1467)
+bool kssd_use64(const KssdParams &k) { return k.half_k - k.drlevel > 8; }
+
+void save_kssd_genome_info(const vector<Genome> &g, const string &folder, const char *type, bool by_file, bool use64)
 {
-    save_genome_info(g, folder, "mst", by_file);
+    string path = folder + "/kssd.info." + type;
+    FILE *fp = fopen(path.c_str(), "w+");
+    if (!fp) die("save_genome_info(), cannot open the file: " + path);
+    wr(fp, by_file);
+    wr(fp, (size_t)g.size());
+    for (const Genome &x : g) {
+        if (by_file) {
+            wr(fp, (int)x.file_name.size()); wr(fp, (int)x.name.size()); wr(fp, (int)x.comment.size()); wr(fp, x.strand);
+            wr(fp, (uint64_t)x.total_len);
+            fwrite(x.file_name.data(), 1, x.file_name.size(), fp); fwrite(x.name.data(), 1, x.name.size(), fp);
+            fwrite(x.comment.data(), 1, x.comment.size(), fp);
+        } else {
+            wr(fp, (int)x.name.size()); wr(fp, (int)x.comment.size()); wr(fp, x.strand); wr(fp, (int)x.total_len);
+            fwrite(x.name.data(), 1, x.name.size(), fp); fwrite(x.comment.data(), 1, x.comment.size(), fp);
+        }
+        wr(fp, use64);
+    }
+    fclose(fp);
+}
+
+bool load_kssd_genome_info(vector<Genome> &g, const string &folder, const char *type)
+{
+    string path = folder + "/kssd.info." + type;
+    FILE *fp = fopen(path.c_str(), "r");
+    if (!fp) die("load_kssd_genome_info(), cannot open the file: " + path);
+    bool by_file = false; size_t n = 0;
+    if (!rd(fp, by_file) || !rd(fp, n)) die("load_kssd_genome_info(), truncated file: " + path);
+    g.resize(n);
+    auto rs = [&](string &s, int len) { s.resize(len); if (len && fread(&s[0], 1, len, fp) != (size_t)len) die("truncated " + path); };
+    for (size_t i = 0; i < n; i++) {
+        Genome &x = g[i];
+        x.id = (int)i;
+        bool use64 = false;
+        if (by_file) {
+            int lf, ls, lc; uint64_t tot;
+            if (!rd(fp, lf) || !rd(fp, ls) || !rd(fp, lc) || !rd(fp, x.strand) || !rd(fp, tot)) die("truncated " + path);
+            x.total_len = tot; rs(x.file_name, lf); rs(x.name, ls); rs(x.comment, lc);
+        } else {
+            int ls, lc, len;
+            if (!rd(fp, ls) || !rd(fp, lc) || !rd(fp, x.strand) || !rd(fp, len)) die("truncated " + path);
+            x.total_len = (uint64_t)len; rs(x.name, ls); rs(x.comment, lc);
+        }
+        if (!rd(fp, use64)) die("truncated " + path);
+    }
+    fclose(fp);
+    return by_file;
+}
+
+void save_kssd_sketches(const vector<Genome> &g, const string &folder, bool by_file)
+{
+    const bool use64 = kssd_use64(g_kssd);
+    save_kssd_genome_info(g, folder, "sketch", by_file, use64);
+    string path = folder + "/kssd.hash.sketch";
+    FILE *fp = fopen(path.c_str(), "w+");
+    if (!fp) die("saveSketch(), cannot open the file: " + path);
+    wr(fp, g_kssd.id); wr(fp, g_kssd.half_k); wr(fp, g_kssd.half_subk); wr(fp, g_kssd.drlevel); wr(fp, g_kssd.genome_number);
+    vector<uint32_t> tmp;
+    for (const Genome &x : g) {
+        wr(fp, (size_t)x.hashes.size());
+        if (use64) fwrite(x.hashes.data(), 8, x.hashes.size(), fp);
+        else { tmp.assign(x.hashes.begin(), x.hashes.end()); fwrite(tmp.data(), 4, tmp.size(), fp); }
+    }
+    fclose(fp);
+    cerr << "-----save the kssd sketches into: " << folder << endl;
+    // kssd.sketch.index / kssd.sketch.dict: hash -> genome ids.  The reference's --fast --presketched reader has
+    // no rebuild path and exits without them (src/MST.cpp:242-337), so a folder we write carries both.  Entries
+    // are written in ascending hash order (the reference's order is its hash-map iteration order; the reader
+    // only builds a map from them).
+    vector<std::pair<uint64_t, uint32_t>> post;
+    for (size_t i = 0; i < g.size(); i++) for (uint64_t h : g[i].hashes) post.emplace_back(h, (uint32_t)i);
+    std::sort(post.begin(), post.end());
+    vector<uint64_t> keys; vector<uint32_t> sizes, ids;
+    for (size_t a = 0; a < post.size();) {
+        size_t b = a;
+        while (b < post.size() && post[b].first == post[a].first) ids.push_back(post[b++].second);
+        keys.push_back(post[a].first); sizes.push_back((uint32_t)(b - a));
+        a = b;
+    }
+    FILE *fd = fopen((folder + "/kssd.sketch.dict").c_str(), "w+");
+    if (!fd) die("cannot open " + folder + "/kssd.sketch.dict");
+    fwrite(ids.data(), 4, ids.size(), fd);
+    fclose(fd);
+    FILE *fi = fopen((folder + "/kssd.sketch.index").c_str(), "w+");
+    if (!fi) die("cannot open " + folder + "/kssd.sketch.index");
+    wr(fi, (size_t)keys.size());
+    if (use64) fwrite(keys.data(), 8, keys.size(), fi);
+    else { tmp.assign(keys.begin(), keys.end()); fwrite(tmp.data(), 4, tmp.size(), fi); }
+    fwrite(sizes.data(), 4, sizes.size(), fi);
+    fclose(fi);
+}
+
+bool load_kssd_sketches(vector<Genome> &g, const string &folder)
+{
+    string path = folder + "/kssd.hash.sketch";
+    FILE *fp = fopen(path.c_str(), "r");
+    if (!fp) {
+        cerr << "ERROR: loadKssdSketches(), cannot open the file: " << path << endl;
+        FILE *t = fopen((folder + "/hash.sketch").c_str(), "r");
+        if (t) { cerr << "Do you want to load the minHash sketches directory? Try again without '--fast' option" << endl; fclose(t); }
+        exit(1);
+    }
+    if (!rd(fp, g_kssd.id) || !rd(fp, g_kssd.half_k) || !rd(fp, g_kssd.half_subk) || !rd(fp, g_kssd.drlevel) ||
+        !rd(fp, g_kssd.genome_number)) die("loadKssdSketches(), truncated " + path);
+    const bool by_file = load_kssd_genome_info(g, folder, "sketch");
+    const bool use64 = kssd_use64(g_kssd);
+    vector<uint32_t> tmp;
+    for (Genome &x : g) {
+        size_t n = 0;
+        if (!rd(fp, n)) die("loadKssdSketches(), truncated " + path);
+        x.hashes.resize(n);
+        if (use64) { if (n && fread(x.hashes.data(), 8, n, fp) != n) die("loadKssdSketches(), truncated " + path); }
+        else {
+            tmp.resize(n);
+            if (n && fread(tmp.data(), 4, n, fp) != n) die("loadKssdSketches(), truncated " + path);
+            std::copy(tmp.begin(), tmp.end(), x.hashes.begin());
+        }
+    }
+    fclose(fp);
+    return by_file;
+}
+
+void save_mst(const vector<Genome> &g, const vector<tc_edge> &mst, const string &folder, bool by_file, bool fast)
+{
+    if (fast) save_kssd_genome_info(g, folder, "mst", by_file, kssd_use64(g_kssd));      // saveKssdMST, MST_IO.cpp:181-198
+    else save_genome_info(g, folder, "mst", by_file);
     string path = folder + "/edge.mst";
     FILE *fp = fopen(path.c_str(), "w+");
     if (!fp) die("saveMST(), cannot open the file: " + path);
     wr(fp, (size_t)mst.size());
     for (const tc_edge &e : mst) { wr(fp, e.pre); wr(fp, e.suf); wr(fp, e.dist); }
     fclose(fp);
-    cerr << "-----save the mst into: " << folder << endl;
+    cerr << (fast ? "-----save the kssd mst into: " : "-----save the mst into: ") << folder << endl;
 }
 
-bool load_mst(vector<Genome> &g, vector<tc_edge> &mst, const string &folder)
+bool load_mst(vector<Genome> &g, vector<tc_edge> &mst, const string &folder, bool fast)
 {
-    bool by_file = load_genome_info(g, folder, "mst");
+    bool by_file = fast ? load_kssd_genome_info(g, folder, "mst") : load_genome_info(g, folder, "mst");
     string path = folder + "/edge.mst";
     FILE *fp = fopen(path.c_str(), "r");
     if (!fp) die("loadMST(), cannot open the file: " + path);
@@ -544,7 +803,7 @@ void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_fi
     mst.resize(m);
     double t3 = now_s();
     cerr << "========time of generateMST is: " << t3 - t2 << "========" << endl;
-    if (save) save_mst(g, mst, folder, by_file);
+    if (save) save_mst(g, mst, folder, by_file, o.fast);
     vector<vector<int>> cluster = clusters_from_forest(mst, o.threshold, (int)g.size());
     print_result(cluster, g, by_file, o.output, o.threshold);
     cerr << "-----write the cluster result into: " << o.output << endl;
@@ -560,7 +819,7 @@ void usage(const char *prog)
 #ifndef GREEDY_CLUST
             " | --premsted DIR"
 #endif
-            ") [--device N]\n", prog);
+            ") [--fast [--drlevel N]] [--device N]\n", prog);
 }
 
 }  // namespace
@@ -587,6 +846,8 @@ int main(int argc, char **argv)
 #ifndef GREEDY_CLUST
         else if (f == "--premsted") { o.folder = need("--premsted"); o.premsted = true; }
 #endif
+        else if (f == "--fast") o.fast = true;
+        else if (f == "--drlevel") o.drlevel = atoi(need("--drlevel"));
         else if (f == "--device") o.device = atoi(need("--device"));
         else if (f == "-h" || f == "--help") { usage(argv[0]); return 0; }
         else { usage(argv[0]); die("unsupported option " + f + " (see DESIGN.md: out of scope for the B200 hot-path build)"); }
@@ -595,11 +856,15 @@ int main(int argc, char **argv)
     if (o.threads < 1) { fprintf(stderr, "-----Invalid thread number %d\n", o.threads); return 1; }
     fprintf(stderr, "-----set the thread number %d\n", o.threads);
     if (!o.has_threshold) cerr << "-----use default threshold: " << o.threshold << endl;
+#ifdef GREEDY_CLUST
+    if (o.fast) die("clust-greedy --fast is not part of this build (SURVEY.md 8f-2); use clust-mst --fast or clust-greedy without --fast");
+#endif
+    if (o.fast && (o.drlevel < 0 || o.drlevel > 8)) { cerr << "ERROR: invalid drlevel " << o.drlevel << ", should be in [0, 8]" << endl; return 1; }
 
 #ifndef GREEDY_CLUST
     if (o.premsted) {                       // clust_from_mst: host only, no GPU needed
         vector<Genome> g; vector<tc_edge> mst;
-        bool by_file = load_mst(g, mst, o.folder);
+        bool by_file = load_mst(g, mst, o.folder, o.fast);
         vector<vector<int>> cluster = clusters_from_forest(mst, o.threshold, (int)g.size());
         print_result(cluster, g, by_file, o.output, o.threshold);
         cerr << "-----write the cluster result into: " << o.output << endl;
@@ -612,7 +877,9 @@ int main(int argc, char **argv)
     vector<Genome> g;
     if (o.presketched) {                    // clust_from_sketches (sub_command.cpp:2647-2856)
         double t0 = now_s();
-        bool by_file = load_sketches(g, o.folder, o);
+        bool by_file;
+        if (o.fast) { by_file = load_kssd_sketches(g, o.folder); o.kmer = 2 * g_kssd.half_k; }   // sub_command.cpp: kmer_size = half_k * 2
+        else by_file = load_sketches(g, o.folder, o);
         cerr << "-----the size of sketches is: " << g.size() << endl;
 #ifdef GREEDY_CLUST
         std::sort(g.begin(), g.end(), [](const Genome &a, const Genome &b) {      // cmpGenomeSize / cmpSeqSize
@@ -624,9 +891,13 @@ int main(int argc, char **argv)
         run_clustering(ctx, g, o, by_file, false, o.folder);
     } else {
         if (!o.has_input) { usage(argv[0]); die("option -i/--input or --presketched is required"); }
-        if (!tune_parameters(o)) return 1;
+        if (o.fast && !o.by_file)
+            die("--fast needs -l/--list in this build: the reference's single-file KSSD consumer is a different variant "
+                "(SURVEY.md 8a-9) and is out of scope");
+        if (!(o.fast ? tune_kssd_parameters(o) : tune_parameters(o))) return 1;
         double t0 = now_s();
         if (o.by_file) sketch_files(ctx, o, g); else sketch_sequences(ctx, o, g);
+        if (o.fast) o.kmer = 2 * g_kssd.half_k;                          // SketchInfo.cpp:1019-1020, MST.cpp:219
         cerr << "-----the size of sketches (number of genomes or sequences) is: " << g.size() << endl;
         double t1 = now_s();
         cerr << "========time of computing sketch is: " << t1 - t0 << "========" << endl;
@@ -635,7 +906,7 @@ int main(int argc, char **argv)
         if (save) {
             string cmd = "mkdir -p " + folder;
             if (system(cmd.c_str()) != 0) die("cannot create " + folder);
-            save_sketches(g, folder, o);
+            if (o.fast) save_kssd_sketches(g, folder, o.by_file); else save_sketches(g, folder, o);
             cerr << "========time of saveSketches is: " << now_s() - t1 << "========" << endl;
         }
         run_clustering(ctx, g, o, o.by_file, save, folder);

@@ -128,3 +128,49 @@ def test_clust_greedy_matches_reference(genomes, tmp_path, mode, extra):
     _run(os.path.join(REF, "clust-greedy"), ["-t", "1", "--presketched", rf, "-d", "0.05", "-o", "pre.txt"], str(tmp_path / "ref"))
     _run(os.path.join(OURS, "clust-greedy"), ["--presketched", rf, "-d", "0.05", "-o", "pre.txt"], str(tmp_path / "ours"))
     assert open(str(tmp_path / "ref" / "pre.txt")).read() == open(str(tmp_path / "ours" / "pre.txt")).read()
+
+
+def test_clust_mst_fast_matches_reference(genomes, tmp_path):
+    """--fast (KSSD) list mode: sketch folder byte-identical to the reference's, same MST weights and partition;
+    the reference reads the folder we wrote (incl. kssd.sketch.index/.dict) and we read the reference's."""
+    lst, _ = genomes
+    args = ["--fast", "-l", "-i", lst, "-d", "0.05", "-o", "out.txt"]
+    rf, _ = _run(os.path.join(REF, "clust-mst"), ["-t", "1"] + args, str(tmp_path / "ref"))
+    of, _ = _run(os.path.join(OURS, "clust-mst"), args, str(tmp_path / "ours"))
+    for fn in ("kssd.hash.sketch", "kssd.info.sketch", "kssd.info.mst"):
+        assert _same_bytes(os.path.join(rf, fn), os.path.join(of, fn)), fn
+    a = sketch_io.read_edge_mst(os.path.join(rf, "edge.mst"))
+    b = sketch_io.read_edge_mst(os.path.join(of, "edge.mst"))
+    assert np.array_equal(np.sort(a["dist"]), np.sort(b["dist"]))
+    ref_out, our_out = str(tmp_path / "ref" / "out.txt"), str(tmp_path / "ours" / "out.txt")
+    assert open(ref_out).read().splitlines()[:3] == open(our_out).read().splitlines()[:3]
+    assert _partition(ref_out) == _partition(our_out)
+    # cross-reading of the folders
+    _run(os.path.join(REF, "clust-mst"), ["-t", "1", "--fast", "--presketched", of, "-d", "0.05", "-o", "x.txt"], str(tmp_path / "ref"))
+    assert _partition(str(tmp_path / "ref" / "x.txt")) == _partition(ref_out)
+    _run(os.path.join(OURS, "clust-mst"), ["--fast", "--presketched", rf, "-d", "0.05", "-o", "pre.txt"], str(tmp_path / "ours"))
+    assert _partition(str(tmp_path / "ours" / "pre.txt")) == _partition(ref_out)
+    _run(os.path.join(OURS, "clust-mst"), ["--fast", "--premsted", rf, "-d", "0.05", "-o", "mst.txt"], str(tmp_path / "ours"))
+    assert open(str(tmp_path / "ours" / "mst.txt")).read() == open(ref_out).read()
+    # explicit k and a different reduction level
+    args2 = ["--fast", "-l", "-i", lst, "-k", "20", "--drlevel", "2", "-d", "0.05", "-o", "out2.txt"]
+    rf2, _ = _run(os.path.join(REF, "clust-mst"), ["-t", "1"] + args2, str(tmp_path / "ref2"))
+    of2, _ = _run(os.path.join(OURS, "clust-mst"), args2, str(tmp_path / "ours2"))
+    assert _same_bytes(os.path.join(rf2, "kssd.hash.sketch"), os.path.join(of2, "kssd.hash.sketch"))
+    assert _partition(str(tmp_path / "ref2" / "out2.txt")) == _partition(str(tmp_path / "ours2" / "out2.txt"))
+
+
+def test_clust_mst_fast_golden_folder(tmp_path):
+    """the committed reference run (tests/golden/kssd): our binary reproduces its kssd.hash.sketch from the same
+    genome files without needing the reference binary"""
+    _need_bins()
+    os.symlink(os.path.join(ROOT, "tests"), str(tmp_path / "tests"))
+    of, _ = _run(os.path.join(OURS, "clust-mst"), ["--fast", "-l", "-i", "tests/golden/mst_genomes/list.txt", "-d", "0.05",
+                                                    "-o", "clusters.txt"], str(tmp_path))
+    gold = os.path.join(ROOT, "tests", "golden", "kssd")
+    assert _same_bytes(os.path.join(gold, "kssd.hash.sketch"), os.path.join(of, "kssd.hash.sketch"))
+    assert _same_bytes(os.path.join(gold, "kssd.info.sketch"), os.path.join(of, "kssd.info.sketch"))
+    a = sketch_io.read_edge_mst(os.path.join(gold, "edge.mst"))
+    b = sketch_io.read_edge_mst(os.path.join(of, "edge.mst"))
+    assert np.array_equal(np.sort(a["dist"]), np.sort(b["dist"]))
+    assert _partition(os.path.join(gold, "clusters.txt")) == _partition(str(tmp_path / "clusters.txt"))
