@@ -47,11 +47,14 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.period_ms = int(os.environ.get("TCLUST_BENCH_SAMPLER_MS", "200"))
 
     def start(self):
+        if self.period_ms <= 0:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -267,6 +270,20 @@ def run_pairs(args):
     sync_all()
     e2e_ms = (time.time() - t0) * 1e3 / e2e_steps
 
+    # ---- semantic B (MinHash::distance, the computation the CPU arm times): one pass of the step-budget merge kernel
+    semb_ms, semb_pairs = None, 0
+    if not args.no_semb:
+        sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            a.record()
+        semb_pairs, _ = ctx.allpairs_pass_b(1000, rank, world)
+        with torch.cuda.stream(stream):
+            b.record()
+        b.synchronize()
+        semb_ms = a.elapsed_time(b)
+        sync_all()
+
     t = torch.tensor([dev_ms, e2e_ms, k3_ms, float(pairs_mine), float(launches)], dtype=torch.float64, device="cuda")
     if dist is not None:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -321,6 +338,12 @@ def run_pairs(args):
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
         }
+        if semb_ms is not None:
+            line["semantic_b"] = {"what": "the same pass with Mash union-limited counts (MinHash::jaccard stop rule, "
+                                          "sketchSize 1000) on the step-budget merge kernel k3_tile_kernel<EDGES,SEMB>; "
+                                          "this is the computation the cpu_baseline runs; rank 0's share",
+                                  "value": semb_pairs / (semb_ms / 1e3), "unit": "pairs/s", "ms": semb_ms,
+                                  "pairs": int(semb_pairs)}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             r = ref_pairs(min(args.ref_sample, n), threads, h, off)
@@ -358,6 +381,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=4000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sketch", action="store_true", help="pairs workload: skip the sketch leg of the line")
+    ap.add_argument("--no-semb", action="store_true", help="pairs workload: skip the semantic-B pass")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

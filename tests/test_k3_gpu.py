@@ -165,3 +165,27 @@ def test_sharded_pass_two_parts_equals_oracle(tc, oracle, containment):
         assert np.array_equal(np.sort(one["dist"]), np.sort(ref["dist"]))
     finally:
         single.close()
+
+
+def test_full_size_pass_properties(ctx):
+    """BASELINE configs[2] at full size (N = 100,000, s = 1000; 5.0e9 pairs): the oracle cannot run this, so the dense
+    pass is checked through properties of the generator -- pool hashes are even and private ones odd, hence a pair
+    shares hashes iff it lies inside a family: exactly 1000 * C(100,2) candidate edges, every edge in-family, and
+    `common` equal to the exact intersection recomputed on the host for a sample of edges."""
+    h, off = synth.family_sketches_fast(1000, 100, 1000, seed=7)
+    n = len(off) - 1
+    ctx.upload(hashes=h, off=off)
+    npairs, nedges = ctx.allpairs_pass(4)
+    assert npairs == n * (n - 1) // 2
+    assert nedges == 1000 * (100 * 99 // 2)
+    e = ctx.edges()
+    assert (e["j"] < e["i"]).all() and (e["i"] // 100 == e["j"] // 100).all()
+    rows = h.reshape(n, 1000)
+    rng = np.random.default_rng(0)
+    for t in rng.integers(0, len(e), 300):
+        i, j, c = int(e["i"][t]), int(e["j"][t]), int(e["common"][t])
+        assert c == len(np.intersect1d(rows[i], rows[j], assume_unique=True))
+    # idempotence: a second pass yields the same edge multiset
+    ctx.allpairs_pass(4)
+    e2 = ctx.edges()
+    assert np.array_equal(np.sort(e, order=["i", "j"]), np.sort(e2, order=["i", "j"]))
