@@ -210,6 +210,9 @@ def run_pairs(args):
         T._chk(L.tc_boruvka_phase2(ctx._h, 0, best_key.data_ptr(), best_edge.data_ptr()))
         if dist is not None:
             best_edge.bitwise_xor_(-2**63); dist.all_reduce(best_edge, op=dist.ReduceOp.MIN); best_edge.bitwise_xor_(-2**63)
+            # a Boruvka round ends with the reduced edges on every rank (the host unions the components next):
+            # the collectives must be complete before the next pass starts, they are not left to overlap it
+            torch.cuda.current_stream().synchronize()
         return npairs, nedges
 
     def sync_all():
@@ -248,6 +251,7 @@ def run_pairs(args):
         T._chk(L.tc_boruvka_phase2(ctx._h, 0, best_key.data_ptr(), best_edge.data_ptr()))
         if dist is not None:
             best_edge.bitwise_xor_(-2**63); dist.all_reduce(best_edge, op=dist.ReduceOp.MIN); best_edge.bitwise_xor_(-2**63)
+            torch.cuda.current_stream().synchronize()      # round complete on this rank (see device_step)
     with torch.cuda.stream(stream):
         ev1.record()
     sync_all()
