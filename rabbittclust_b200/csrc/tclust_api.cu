@@ -269,7 +269,13 @@ static int ensure_edges(tc_ctx *ctx)
 {
     if (ctx->d_edges) return 0;
     uint64_t cap = (uint64_t)ctx->n * (ctx->n - 1) / 2;
-    uint64_t lim = 1ull << 28;  // 268M edges = 3.2 GB
+    // default: up to 2^28 edges (3.2 GB), or -- for sets whose candidate graph is denser, e.g. KSSD sketches in a
+    // 2^24 hash space at N = 500k (BASELINE configs[4]: ~1.4 % of all pairs share a hash) -- up to half of the
+    // free HBM; TCLUST_EDGE_CAP overrides
+    uint64_t lim = 1ull << 28;
+    size_t free_b = 0, total_b = 0;
+    if (cap > lim && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+        lim = std::max<uint64_t>(lim, std::min<uint64_t>(cap / 16, free_b / 2 / sizeof(tc_pair)));
     if (const char *s = getenv("TCLUST_EDGE_CAP")) lim = strtoull(s, nullptr, 10);
     cap = std::max<uint64_t>(std::min(cap, lim), 1);
     TC_CUDA(cudaMalloc(&ctx->d_edges, cap * sizeof(tc_pair)));

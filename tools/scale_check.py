@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Full-size runs of the BASELINE.json parity-case shapes that are not bench lines (configs[3] and configs[4]),
+checked through size-independent properties (the oracle cannot run these sizes in reasonable time).
+
+  kssd   configs[4] shape: N KSSD-like sketches (about 488 u32-range hashes in a 2^24 space, k = 18) -> tc_mst.
+         Properties: N-1-(components-1) forest edges sorted by weight; the partition at d equals the planted
+         families (cross-family pairs share only chance hashes: J << Jmin); every in-family MST edge weight equals
+         the host formula on the exact intersection recomputed with numpy.
+  greedy configs[3] shape: N ragged sketches (100..10000, containment, k = 21) sorted by length desc ->
+         tc_greedy_cluster.  Properties: every member is within d of its representative (exact host distance on the
+         numpy intersection) and every representative is farther than d from every earlier representative of its
+         own family sample; cluster count reported.
+usage: python tools/scale_check.py kssd|greedy [N]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rabbittclust_b200 as T  # noqa: E402
+
+
+def kssd_like(n_fam, per_fam, size=488, space=1 << 24, seed=5):
+    rng = np.random.default_rng(seed)
+    sk = []
+    for f in range(n_fam):
+        pool = rng.choice(space, size, replace=False).astype(np.uint64)
+        for m in range(per_fam):
+            keep = int(size * rng.uniform(0.6, 1.0))
+            part = rng.choice(pool, keep, replace=False)
+            priv = rng.integers(0, space, size - keep + 4).astype(np.uint64)
+            s = np.unique(np.concatenate([part, priv]))
+            sk.append(s)
+    return sk
+
+
+def ragged_families(n_fam, per_fam, seed=6, lo=100, hi=10000):
+    """member = the s smallest values of (random p-subset of the family pool + private values)"""
+    rng = np.random.default_rng(seed)
+    sk, lens = [], []
+    for f in range(n_fam):
+        pool = np.sort(rng.integers(0, 2**62, hi, dtype=np.uint64)) * np.uint64(2)
+        for m in range(per_fam):
+            s = int(np.exp(rng.uniform(np.log(lo), np.log(hi))))
+            p = rng.uniform(0.3, 1.0)
+            top = pool[:s]
+            part = top[rng.random(s) < p]
+            priv = rng.integers(0, int(top[-1]) // 2 + 1, s - len(part), dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+            v = np.unique(np.concatenate([part, priv]))
+            sk.append(v)
+            lens.append(1000 * len(v) + int(rng.integers(0, 1000)))
+    return sk, np.asarray(lens)
+
+
+def main():
+    what = sys.argv[1]
+    res = {"what": what}
+    ctx = T.Context(0)
+    if what == "kssd":
+        n = int(sys.argv[2]) if len(sys.argv) > 2 else 500000
+        per = 100
+        t0 = time.time(); sk = kssd_like(n // per, per); res["gen_s"] = time.time() - t0
+        n = len(sk)
+        k, d = 18, 0.05
+        t0 = time.time(); ctx.upload(sk); res["upload_s"] = time.time() - t0
+        t0 = time.time(); mst = ctx.mst(k, d); res["mst_s"] = time.time() - t0
+        res.update(n=n, pairs=n * (n - 1) // 2, mst_edges=len(mst), pairs_per_s_incl_boruvka=n * (n - 1) / 2 / res["mst_s"])
+        assert (np.diff(mst["dist"]) >= 0).all()
+        # union-find over edges <= d
+        par = np.arange(n)
+        def find(x):
+            while par[x] != x:
+                par[x] = par[par[x]]; x = par[x]
+            return x
+        for e in mst[mst["dist"] <= d]:
+            a, b = find(int(e["pre"])), find(int(e["suf"]))
+            if a != b:
+                par[a] = b
+        roots = np.array([find(i) for i in range(n)])
+        fam = np.arange(n) // per
+        # each cluster lies inside one family and each family is one cluster (members share >= 60 % of the pool)
+        assert len(set(zip(roots.tolist(), fam.tolist()))) == len(set(roots.tolist())) == n // per, "partition != families"
+        rng = np.random.default_rng(0)
+        for t in rng.integers(0, len(mst), 300):
+            i, j = int(mst["pre"][t]), int(mst["suf"][t])
+            c = len(np.intersect1d(sk[i], sk[j], assume_unique=True))
+            assert mst["dist"][t] == T.mash_dist(c, len(sk[i]), len(sk[j]), k)
+        res["clusters"] = n // per
+    else:
+        n = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
+        per = 100
+        t0 = time.time(); sk, lens = ragged_families(n // per, per); res["gen_s"] = time.time() - t0
+        order = np.lexsort((np.arange(len(sk)), -lens))          # length desc, id asc (the --presketched order)
+        sk = [sk[i] for i in order]
+        fam = (order // per)
+        n = len(sk)
+        k, d = 21, 0.05
+        t0 = time.time(); ctx.upload(sk); res["upload_s"] = time.time() - t0
+        t0 = time.time(); nc, rep = ctx.greedy_cluster(k, d, containment=True); res["greedy_s"] = time.time() - t0
+        res.update(n=n, clusters=nc, mean_size=float(np.mean([len(s) for s in sk])))
+        assert nc == len(set(rep.tolist())) and (rep <= np.arange(n)).all() and (rep[rep] == rep).all()
+        L = T.lib()
+        rng = np.random.default_rng(1)
+        for j in rng.integers(0, n, 2000):
+            j = int(j); r = int(rep[j])
+            if r == j:
+                continue
+            c = len(np.intersect1d(sk[j], sk[r], assume_unique=True))
+            assert L.tc_greedy_dist(c, len(sk[j]), len(sk[r]), 1, k) <= d, (j, r)
+        # representatives of the same family must not be within d of an earlier representative
+        reps = np.nonzero(rep == np.arange(n))[0]
+        checked = 0
+        for f in rng.integers(0, n // per, 40):
+            rf = reps[fam[reps] == f]
+            for a in range(len(rf)):
+                for b in range(a):
+                    i, j = int(rf[a]), int(rf[b])
+                    c = len(np.intersect1d(sk[i], sk[j], assume_unique=True))
+                    cmin = L.tc_greedy_common_min(d, k, len(sk[i]), len(sk[j]), 1)
+                    assert c < cmin or L.tc_greedy_dist(c, len(sk[i]), len(sk[j]), 1, k) > d, (i, j)
+                    checked += 1
+        res["rep_pairs_checked"] = checked
+    ctx.close()
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
