@@ -377,7 +377,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="pairs", choices=["pairs", "sketch"])
+    ap.add_argument("--workload", default="pairs", choices=["pairs", "sketch", "kssd"])
     ap.add_argument("--n", type=int, default=100000, help="number of sketches (pairs workload)")
     ap.add_argument("--genomes", type=int, default=2048, help="genomes per step (sketch workload)")
     ap.add_argument("--genome-len", type=int, default=5000000)

@@ -106,6 +106,75 @@ def measure(args, local_rank=0, rank=0, world=1, dist=None):
             "e2e_genomes_per_s": ne / (e2e_ms / 1e3), "h2d_bytes": ne * glen, "d2h_bytes": ne * s * 8 + ne * 4}
 
 
+def measure_kssd(args, local_rank=0, rank=0):
+    """KSSD (--fast) sketch leg, BASELINE configs[4] shape: 2 Mbp genomes, k=18 (half_k 9), drlevel 3."""
+    import torch
+    import rabbittclust_b200 as T
+    L = T.lib()
+    dev = torch.device("cuda", local_rank)
+    ng, glen, k, drl, stride = args.genomes, 2000000, 18, 3, 2048
+    ctx = T.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    seq = device_genomes(torch, ng, glen, 4321 + rank, dev)
+    rec_off = (np.arange(ng + 1, dtype=np.uint64) * np.uint64(glen))
+    r2g = np.arange(ng, dtype=np.uint32)
+    sd = T.kssd_shuffled_dim(6)
+    out = torch.zeros((ng, stride), dtype=torch.int64, device=dev)
+    out_n = torch.zeros(ng, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        T._chk(L.tc_sketch_kssd_dev(ctx._h, seq.data_ptr(), T._p(rec_off, C.c_uint64), T._p(r2g, C.c_uint32), ng, ng, k, drl,
+                                    T._p(sd, C.c_int32), out.data_ptr(), stride, out_n.data_ptr()))
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+    for _ in range(args.steps):
+        step()
+    with torch.cuda.stream(stream):
+        e1.record()
+    e1.synchronize()
+    dev_ms = e0.elapsed_time(e1) / args.steps
+    launches = ctx.launches - l0
+    n = out_n.cpu().numpy()
+    o = out.cpu().numpy().view(np.uint64)
+    assert (n > 300).all() and (n < 700).all(), "KSSD sketch sizes out of the expected range"   # ~ L / 4096 = 488
+    for g in range(0, ng, max(1, ng // 64)):
+        assert (o[g, 1:n[g]] > o[g, :n[g] - 1]).all(), "KSSD sketch not strictly ascending"
+    ne = max(1, min(ng, args.e2e_genomes * 2))
+    h_seq = torch.empty(ne * glen + 64, dtype=torch.uint8).pin_memory()
+    h_seq[:ne * glen].copy_(seq[:ne * glen]); h_seq[ne * glen:] = 0
+    h_out = torch.zeros((ne, stride), dtype=torch.int64).pin_memory()
+    h_n = torch.zeros(ne, dtype=torch.int32).pin_memory()
+    ro, rg = rec_off[:ne + 1].copy(), r2g[:ne].copy()
+
+    def e2e_step():
+        T._chk(L.tc_sketch_kssd(ctx._h, h_seq.data_ptr(), T._p(ro, C.c_uint64), T._p(rg, C.c_uint32), ne, ne, k, drl,
+                                T._p(sd, C.c_int32), h_out.data_ptr(), stride, h_n.data_ptr()))
+
+    e2e_step()
+    torch.cuda.synchronize()
+    n_e2e = max(1, min(args.steps, 3))
+    t0 = time.time()
+    for _ in range(n_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.time() - t0) * 1e3 / n_e2e
+    assert np.array_equal(h_n.numpy(), n[:ne]) and np.array_equal(h_out.numpy().view(np.uint64)[:, :256], o[:ne, :256])
+    ctx.close()
+    return {"metric": "genomes sketched/sec (KSSD --fast)", "value": ng / (dev_ms / 1e3), "unit": "genomes/s",
+            "ms_per_step": dev_ms, "gbp_per_s": ng * glen / (dev_ms / 1e3) / 1e9, "gpu_launches": int(launches),
+            "config": {"workload": "KSSD sketch: %d synthetic %d bp genomes, k=18 drlevel=3 (BASELINE.json configs[4] shape)"
+                                   % (ng, glen), "mean_sketch_size": float(n.mean())},
+            "e2e": {"value": ne / (e2e_ms / 1e3), "unit": "genomes/s", "h2d_bytes_per_step": ne * glen,
+                    "d2h_bytes_per_step": ne * stride * 8 + ne * 4, "genomes_per_step": ne, "ms_per_step": e2e_ms}}
+
+
 def cpu_update(args, threads):
     """The reference's MinHash::update (oracle/_ref/ref_harness, AVX2 build) on a bounded sample."""
     import subprocess
@@ -167,6 +236,9 @@ def run_sketch(args):
     from bench import ClockSampler, dist_env
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
+    if args.workload == "kssd":
+        print(json.dumps(measure_kssd(args, local_rank, rank)), flush=True)
+        return
     dist = None
     if world > 1:
         import torch.distributed as dist

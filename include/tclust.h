@@ -86,10 +86,12 @@ int tc_sketch_minhash_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const uint64_t *
  * KSSD (--fast) sketches, list mode.  Replaces the hot loop of sketchFileWithKssd
  * (src/SketchInfo.cpp:1019-1048 constants, 1126-1165 loop, 1180-1193 sort).
  * shuffled_dim: host table of 1<<(4*half_subk) ints (generate_shuffle_dim,
- * SketchInfo.cpp:60-102; glibc rand() -- host-only by construction).
+ * SketchInfo.cpp:60-102; glibc rand() -- host-only by construction; tc_kssd_shuffled_dim
+ * builds it, half_subk = 6 unless drlevel > 4, SketchInfo.cpp:1022).
  * out: ngenomes rows of out_stride u64, ascending, distinct; out_n[g] = count (an error is
  * returned if a genome yields more than out_stride hashes).
  */
+int tc_kssd_shuffled_dim(int half_subk, int32_t *out /* 1 << (4*half_subk) ints */);
 int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off,
                    const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes,
                    int kmer_size, int drlevel, const int32_t *shuffled_dim,

@@ -19,7 +19,7 @@ PAIR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("common", "<u4")])
 # every symbol include/tclust.h declares (tests check the built library exports all of them)
 SYMBOLS = [
     "tc_version", "tc_last_error", "tc_ctx_create", "tc_ctx_destroy", "tc_kernel_launches", "tc_stream",
-    "tc_host_alloc", "tc_host_free", "tc_sketch_minhash", "tc_sketch_minhash_dev", "tc_sketch_kssd", "tc_sketch_kssd_dev",
+    "tc_host_alloc", "tc_host_free", "tc_sketch_minhash", "tc_sketch_minhash_dev", "tc_kssd_shuffled_dim", "tc_sketch_kssd", "tc_sketch_kssd_dev",
     "tc_sketches_upload", "tc_sketches_upload_dev", "tc_pair_common", "tc_allpairs_pass",
     "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_mst",
     "tc_greedy_scan", "tc_greedy_cluster",
@@ -63,6 +63,7 @@ def lib():
     sk = [vp, vp, u64p, u32p, C.c_uint64, C.c_uint32, C.c_int, u32p, C.c_uint32, vp, C.c_uint64, vp]
     L.tc_sketch_minhash.argtypes = sk
     L.tc_sketch_minhash_dev.argtypes = sk
+    L.tc_kssd_shuffled_dim.argtypes = [C.c_int, i32p]
     L.tc_sketch_kssd.argtypes = [vp, vp, u64p, u32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, i32p,
                                  vp, C.c_uint64, vp]
     L.tc_sketch_kssd_dev.argtypes = L.tc_sketch_kssd.argtypes
@@ -284,6 +285,18 @@ def distance_b(common_b, size0, size1, sketch_size, k):
 
 def contain_distance(common, size0, size1, k):
     return float(lib().tc_contain_distance(common, size0, size1, k))
+
+
+_SHUF = {}
+
+
+def kssd_shuffled_dim(half_subk=6):
+    """generate_shuffle_dim table of the reference (host, glibc rand), cached per half_subk."""
+    if half_subk not in _SHUF:
+        a = np.zeros(1 << (4 * half_subk), np.int32)
+        _chk(lib().tc_kssd_shuffled_dim(half_subk, _p(a, C.c_int32)))
+        _SHUF[half_subk] = a
+    return _SHUF[half_subk]
 
 
 def radio(threshold, k):

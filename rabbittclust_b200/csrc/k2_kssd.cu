@@ -17,6 +17,8 @@
 #include "tc_common.cuh"
 #include "k_sort.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -123,21 +125,53 @@ __global__ void __launch_bounds__(K2_THREADS) k2_sort_kernel(const K2SortArgs a)
 
 uint32_t pow2_at_least(uint64_t x) { uint32_t p = 2; while (p < x) p <<= 1; return p; }
 
-int sketch_kssd_impl(tc_ctx *ctx, const uint8_t *seq_dev, const uint64_t *rec_off, const uint32_t *rec2genome,
-                     uint64_t nrec, uint32_t ngenomes, int kmer_size, int drlevel, const int32_t *shuffled_dim,
-                     uint64_t *out_dev, uint64_t out_stride, uint32_t *out_n_dev)
+// ------------------------------------------------------------------------------ host driver
+// Same scheme as K1 (k1_sketch.cu): a batch of whole genomes is planned on the host, its metadata goes through a
+// pinned staging buffer, two kernels are enqueued without synchronising; the host-buffer entry point alternates
+// batches over two slots so that the H2D copy of batch c+1 overlaps the kernels of batch c.
+struct K2Slot {
+    uint8_t *d_seq = nullptr;  size_t seq_cap = 0;
+    uint8_t *h_meta = nullptr; size_t h_meta_cap = 0;   // pinned: segments
+    uint8_t *d_meta = nullptr; size_t d_meta_cap = 0;   // segments, per-genome counters, segment counter, scratch
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool used = false;
+};
+struct K2Workspace {
+    K2Slot slot[2];
+    cudaStream_t copy_stream = nullptr;
+    uint64_t *d_out = nullptr; size_t out_cap = 0;
+    uint32_t *d_n = nullptr;   size_t n_cap = 0;
+    unsigned int *d_overflow = nullptr;                  // max pre-deduplication row length seen in a call
+};
+
+K2Workspace *k2_ws(tc_ctx *ctx)
 {
-    TC_CHECK(ngenomes > 0, "tc_sketch_kssd: no genomes");
+    if (!ctx->k2_ws) {
+        K2Workspace *w = new K2Workspace();
+        if (cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMalloc(&w->d_overflow, 4) != cudaSuccess) { delete w; return nullptr; }
+        for (K2Slot &sl : w->slot) {
+            cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+        }
+        ctx->k2_ws = w;
+    }
+    return static_cast<K2Workspace *>(ctx->k2_ws);
+}
+
+inline size_t k2_al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// constants of the scheme (SketchInfo.cpp:1019-1048) + the resident shuffled_dim table
+int k2_setup(tc_ctx *ctx, int kmer_size, int drlevel, const int32_t *shuffled_dim, uint64_t out_stride, K2Args &a)
+{
     TC_CHECK(kmer_size >= 2 && kmer_size <= 32, "tc_sketch_kssd: kmer_size=%d unsupported (2..32)", kmer_size);
     TC_CHECK(out_stride > 0 && out_stride < (1ull << 31), "tc_sketch_kssd: bad out_stride");
-    // constants, SketchInfo.cpp:1019-1048
     const int half_k = (kmer_size + 1) / 2;
     const int kmer = half_k * 2;
     const int half_subk = 6 - drlevel >= 2 ? 6 : drlevel + 2;
     TC_CHECK(drlevel >= 0 && half_k > half_subk, "tc_sketch_kssd: half_k=%d must exceed half_subk=%d", half_k, half_subk);
     const int half_outctx_len = half_k - half_subk;
     const int comp_bittl = 64 - 4 * half_k;
-    K2Args a{};
     a.kmer = kmer; a.drlevel = drlevel; a.half_outctx_len = half_outctx_len;
     a.dim_end = 1 << (4 * (half_subk - drlevel));
     a.use64 = half_k - drlevel > 8;
@@ -147,83 +181,150 @@ int sketch_kssd_impl(tc_ctx *ctx, const uint8_t *seq_dev, const uint64_t *rec_of
     const unsigned long long undomask = (a.tupmask ^ a.domask) & a.tupmask;
     a.undomask1 = undomask & (a.tupmask >> ((half_k + half_subk) * 2));
     a.undomask0 = undomask ^ a.undomask1;
-
     // shuffled_dim table: resident per context (the reference generates it once per process)
     const size_t dim_n = (size_t)1 << (4 * half_subk);
     if (ctx->kssd_dim_host != shuffled_dim || ctx->kssd_dim_n != dim_n) {
         cudaFree(ctx->d_kssd_dim); ctx->d_kssd_dim = nullptr; ctx->kssd_dim_host = nullptr;
         TC_CUDA(cudaMalloc(&ctx->d_kssd_dim, dim_n * 4));
-        TC_CUDA(cudaMemcpyAsync(ctx->d_kssd_dim, shuffled_dim, dim_n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TC_CUDA(cudaMemcpy(ctx->d_kssd_dim, shuffled_dim, dim_n * 4, cudaMemcpyHostToDevice));
         ctx->kssd_dim_host = shuffled_dim; ctx->kssd_dim_n = dim_n;
     }
     a.shuffled_dim = ctx->d_kssd_dim;
+    return 0;
+}
 
-    // ---- segments of end-positions
-    uint64_t total = 0;
+int k2_validate(const uint64_t *rec_off, const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes)
+{
+    TC_CHECK(ngenomes > 0, "tc_sketch_kssd: no genomes");
     for (uint64_t r = 0; r < nrec; r++) {
         TC_CHECK(rec_off[r + 1] >= rec_off[r], "tc_sketch_kssd: record offsets not monotone");
+        TC_CHECK(r == 0 || rec2genome[r] >= rec2genome[r - 1], "tc_sketch_kssd: rec2genome must be non-decreasing");
         TC_CHECK(rec2genome[r] < ngenomes, "tc_sketch_kssd: rec2genome[%llu] out of range", (unsigned long long)r);
+    }
+    return 0;
+}
+
+// enqueue one batch: records [r0, r1) = genomes [g0, g0+ngl); byte x of the input lives at seq_dev[x - base_off];
+// out_dev / out_n_dev point at genome g0
+int k2_enqueue(tc_ctx *ctx, K2Workspace *ws, K2Slot &sl, cudaStream_t st, K2Args a, const uint8_t *seq_dev,
+               const uint64_t *rec_off, const uint32_t *rec2genome, uint64_t r0, uint64_t r1, uint32_t g0, uint32_t ngl,
+               uint64_t base_off, uint64_t *out_dev, uint64_t out_stride, uint32_t *out_n_dev)
+{
+    uint64_t total = 0;
+    for (uint64_t r = r0; r < r1; r++) {
         const uint64_t len = rec_off[r + 1] - rec_off[r];
-        if (len >= (uint64_t)kmer) total += len - kmer + 1;
+        if (len >= (uint64_t)a.kmer) total += len - a.kmer + 1;
     }
     const uint64_t want_ctas = (uint64_t)ctx->num_sms * 32;
     uint64_t segw = std::min<uint64_t>(std::max<uint64_t>(total / std::max<uint64_t>(want_ctas, 1), 1u << 14), 1u << 20);
     segw = (segw + K2_THREADS * 8 - 1) / (K2_THREADS * 8) * (K2_THREADS * 8);
     std::vector<K2Seg> segs;
-    for (uint64_t r = 0; r < nrec; r++) {
+    for (uint64_t r = r0; r < r1; r++) {
         const uint64_t len = rec_off[r + 1] - rec_off[r];
-        if (len < (uint64_t)kmer) continue;
-        const uint64_t first = rec_off[r] + kmer - 1, last = rec_off[r + 1];   // end-positions [first, last)
+        if (len < (uint64_t)a.kmer) continue;
+        const uint64_t start = rec_off[r] - base_off;
+        const uint64_t first = start + a.kmer - 1, last = start + len;      // end-positions [first, last)
         for (uint64_t e = first; e < last; e += segw) {
-            K2Seg s{};
-            s.rec_start = rec_off[r]; s.emit_begin = e; s.emit_end = std::min(e + segw, last); s.genome = rec2genome[r];
-            segs.push_back(s);
+            K2Seg sg{};
+            sg.rec_start = start; sg.emit_begin = e; sg.emit_end = std::min(e + segw, last); sg.genome = rec2genome[r] - g0;
+            segs.push_back(sg);
         }
     }
     const uint32_t nseg = (uint32_t)segs.size();
-    cudaStream_t st = ctx->stream;
-    K2Seg *d_segs = nullptr; uint32_t *d_cnt = nullptr; unsigned int *d_ctr = nullptr; uint64_t *d_scr = nullptr;
-    auto cleanup = [&]() { cudaFree(d_segs); cudaFree(d_cnt); cudaFree(d_ctr); cudaFree(d_scr); };
-#define K2_TRY(x) do { if ((x) != cudaSuccess) { tc_set_error("tc_sketch_kssd: %s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); cleanup(); return 1; } } while (0)
-    K2_TRY(cudaMalloc(&d_segs, std::max<size_t>(nseg, 1) * sizeof(K2Seg)));
-    K2_TRY(cudaMalloc(&d_cnt, (size_t)ngenomes * 4));
-    K2_TRY(cudaMalloc(&d_ctr, 8));
-    K2_TRY(cudaMemcpyAsync(d_segs, segs.data(), nseg * sizeof(K2Seg), cudaMemcpyHostToDevice, st));
-    K2_TRY(cudaMemsetAsync(d_cnt, 0, (size_t)ngenomes * 4, st));
-    K2_TRY(cudaMemsetAsync(d_ctr, 0, 8, st));
-    a.seq = seq_dev; a.segs = d_segs; a.nseg = nseg; a.seg_counter = d_ctr;
+    K2SortArgs s{};
+    s.cap = pow2_at_least(out_stride);
+    size_t smem = (size_t)s.cap * 8;
+    s.use_global = smem > 160 * 1024;
+    const size_t host_bytes = k2_al16(std::max<size_t>(nseg, 1) * sizeof(K2Seg));
+    const size_t o_cnt = host_bytes;
+    const size_t o_ctr = k2_al16(o_cnt + (size_t)ngl * 4);
+    size_t total_bytes = k2_al16(o_ctr + 16);
+    size_t o_scr = 0;
+    if (s.use_global) { o_scr = total_bytes; total_bytes = k2_al16(total_bytes + (size_t)ngl * s.cap * 8); smem = 0; }
+    if (host_bytes > sl.h_meta_cap) {
+        if (sl.h_meta) cudaFreeHost(sl.h_meta);
+        sl.h_meta = nullptr; sl.h_meta_cap = 0;
+        TC_CUDA(cudaMallocHost(&sl.h_meta, host_bytes * 2));
+        sl.h_meta_cap = host_bytes * 2;
+    }
+    if (total_bytes > sl.d_meta_cap) {
+        if (sl.d_meta) cudaFree(sl.d_meta);
+        sl.d_meta = nullptr; sl.d_meta_cap = 0;
+        TC_CUDA(cudaMalloc(&sl.d_meta, total_bytes + total_bytes / 4));
+        sl.d_meta_cap = total_bytes + total_bytes / 4;
+    }
+    if (nseg) memcpy(sl.h_meta, segs.data(), (size_t)nseg * sizeof(K2Seg));
+    TC_CUDA(cudaMemcpyAsync(sl.d_meta, sl.h_meta, host_bytes, cudaMemcpyHostToDevice, st));
+    TC_CUDA(cudaMemsetAsync(sl.d_meta + o_cnt, 0, o_ctr + 16 - o_cnt, st));
+    uint32_t *d_cnt = reinterpret_cast<uint32_t *>(sl.d_meta + o_cnt);
+    a.seq = seq_dev; a.segs = reinterpret_cast<const K2Seg *>(sl.d_meta); a.nseg = nseg;
+    a.seg_counter = reinterpret_cast<unsigned int *>(sl.d_meta + o_ctr);
     a.out = out_dev; a.out_stride = out_stride; a.cnt = d_cnt;
     if (nseg) {
         const int grid = (int)std::min<uint64_t>(nseg, (uint64_t)ctx->num_sms * 8);
         k2_kssd_kernel<<<grid, K2_THREADS, 0, st>>>(a);
         ctx->launches++;
-        K2_TRY(cudaGetLastError());
+        TC_CUDA(cudaGetLastError());
     }
-    K2SortArgs s{};
-    s.out = out_dev; s.out_stride = out_stride; s.cnt = d_cnt; s.out_n = out_n_dev; s.overflow = d_ctr + 1;
-    s.cap = pow2_at_least(out_stride);
-    size_t smem = (size_t)s.cap * 8;
-    s.use_global = smem > 160 * 1024;
-    if (s.use_global) {
-        K2_TRY(cudaMalloc(&d_scr, (size_t)ngenomes * s.cap * 8));
-        s.gscratch = d_scr; smem = 0;
-    }
+    s.out = out_dev; s.out_stride = out_stride; s.cnt = d_cnt; s.out_n = out_n_dev; s.overflow = ws->d_overflow;
+    s.gscratch = s.use_global ? reinterpret_cast<uint64_t *>(sl.d_meta + o_scr) : nullptr;
     if (smem > 48 * 1024)
-        K2_TRY(cudaFuncSetAttribute(k2_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k2_sort_kernel<<<ngenomes, K2_THREADS, smem, st>>>(s);
+        TC_CUDA(cudaFuncSetAttribute(k2_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k2_sort_kernel<<<ngl, K2_THREADS, smem, st>>>(s);
     ctx->launches++;
-    K2_TRY(cudaGetLastError());
-    unsigned int ovf[2] = {0, 0};
-    K2_TRY(cudaMemcpyAsync(ovf, d_ctr, 8, cudaMemcpyDeviceToHost, st));
-    K2_TRY(cudaStreamSynchronize(st));
-#undef K2_TRY
-    cleanup();
-    TC_CHECK(ovf[1] == 0, "tc_sketch_kssd: a genome produced %u hashes, more than out_stride=%llu", ovf[1],
+    TC_CUDA(cudaGetLastError());
+    sl.used = true;
+    return 0;
+}
+
+int k2_check_overflow(K2Workspace *ws, cudaStream_t st, uint64_t out_stride)
+{
+    unsigned int ovf = 0;
+    TC_CUDA(cudaMemcpyAsync(&ovf, ws->d_overflow, 4, cudaMemcpyDeviceToHost, st));
+    TC_CUDA(cudaStreamSynchronize(st));
+    TC_CHECK(ovf == 0, "tc_sketch_kssd: a genome produced %u hashes, more than out_stride=%llu", ovf,
              (unsigned long long)out_stride);
     return 0;
 }
 
 }  // namespace
+
+void tc_k2_free(tc_ctx *ctx)
+{
+    K2Workspace *w = static_cast<K2Workspace *>(ctx->k2_ws);
+    if (!w) return;
+    for (K2Slot &sl : w->slot) {
+        cudaFree(sl.d_seq); cudaFree(sl.d_meta);
+        if (sl.h_meta) cudaFreeHost(sl.h_meta);
+        if (sl.copied) cudaEventDestroy(sl.copied);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    cudaFree(w->d_out); cudaFree(w->d_n); cudaFree(w->d_overflow);
+    if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
+    delete w;
+    ctx->k2_ws = nullptr;
+}
+
+// generate_shuffle_dim (reference src/SketchInfo.cpp:60-102): identity permutation of 16^half_subk slots,
+// Fisher-Yates driven by glibc srand(23)/rand(), then again by srand(348842630).  The glibc rand() stream is part
+// of the reference's definition of a KSSD sketch, so this stays on the host.
+static void kssd_shuffle(int32_t *arr, int length, unsigned seed)
+{
+    srand(seed);
+    for (int i = length - 1; i > 0; i--) {
+        const int j = rand() % (i + 1);
+        const int32_t tmp = arr[i]; arr[i] = arr[j]; arr[j] = tmp;
+    }
+}
+extern "C" int tc_kssd_shuffled_dim(int half_subk, int32_t *out)
+{
+    TC_CHECK(half_subk >= 1 && half_subk <= 7, "tc_kssd_shuffled_dim: half_subk=%d out of range (1..7)", half_subk);
+    const int n = 1 << (4 * half_subk);
+    for (int i = 0; i < n; i++) out[i] = i;
+    kssd_shuffle(out, n, 23);
+    kssd_shuffle(out, n, 348842630u);
+    return 0;
+}
 
 extern "C" int tc_sketch_kssd_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const uint64_t *rec_off, const uint32_t *rec2genome,
                                   uint64_t nrec, uint32_t ngenomes, int kmer_size, int drlevel,
@@ -231,8 +332,15 @@ extern "C" int tc_sketch_kssd_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const ui
                                   uint32_t *out_n_dev)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
-    return sketch_kssd_impl(ctx, seqs_dev, rec_off, rec2genome, nrec, ngenomes, kmer_size, drlevel, shuffled_dim,
-                            out_hashes_dev, out_stride, out_n_dev);
+    if (k2_validate(rec_off, rec2genome, nrec, ngenomes)) return 1;
+    K2Workspace *ws = k2_ws(ctx);
+    TC_CHECK(ws, "tc_sketch_kssd: cannot create the workspace");
+    K2Args a{};
+    if (k2_setup(ctx, kmer_size, drlevel, shuffled_dim, out_stride, a)) return 1;
+    TC_CUDA(cudaMemsetAsync(ws->d_overflow, 0, 4, ctx->stream));
+    if (k2_enqueue(ctx, ws, ws->slot[0], ctx->stream, a, seqs_dev, rec_off, rec2genome, 0, nrec, 0, ngenomes, 0,
+                   out_hashes_dev, out_stride, out_n_dev)) return 1;
+    return k2_check_overflow(ws, ctx->stream, out_stride);
 }
 
 extern "C" int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off, const uint32_t *rec2genome,
@@ -240,31 +348,71 @@ extern "C" int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *
                               uint64_t *out_hashes, uint64_t out_stride, uint32_t *out_n)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
-    const uint64_t nbytes = nrec ? rec_off[nrec] : 0;
-    uint8_t *d_seq = nullptr; uint64_t *d_out = nullptr; uint32_t *d_n = nullptr;
-    TC_CUDA(cudaMalloc(&d_seq, nbytes + 64));
-    int rc = 1;
-    do {
-        if (cudaMalloc(&d_out, std::max<uint64_t>((uint64_t)ngenomes * out_stride, 1) * 8) != cudaSuccess ||
-            cudaMalloc(&d_n, std::max<uint32_t>(ngenomes, 1) * 4) != cudaSuccess) {
-            tc_set_error("tc_sketch_kssd: out of device memory");
-            break;
+    if (k2_validate(rec_off, rec2genome, nrec, ngenomes)) return 1;
+    K2Workspace *ws = k2_ws(ctx);
+    TC_CHECK(ws, "tc_sketch_kssd: cannot create the workspace");
+    K2Args a{};
+    if (k2_setup(ctx, kmer_size, drlevel, shuffled_dim, out_stride, a)) return 1;
+    cudaStream_t st = ctx->stream, cs = ws->copy_stream;
+    const size_t out_elems = std::max<uint64_t>((uint64_t)ngenomes * out_stride, 1);
+    if (out_elems > ws->out_cap) {
+        cudaFree(ws->d_out); ws->d_out = nullptr; ws->out_cap = 0;
+        TC_CUDA(cudaMalloc(&ws->d_out, out_elems * 8));
+        ws->out_cap = out_elems;
+    }
+    if (ngenomes > ws->n_cap) {
+        cudaFree(ws->d_n); ws->d_n = nullptr; ws->n_cap = 0;
+        TC_CUDA(cudaMalloc(&ws->d_n, (size_t)ngenomes * 4));
+        ws->n_cap = ngenomes;
+    }
+    TC_CUDA(cudaMemsetAsync(ws->d_overflow, 0, 4, st));
+    uint64_t chunk_bytes = 128ull << 20;
+    if (const char *e = getenv("TCLUST_SKETCH_CHUNK_MB")) chunk_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 1) << 20;
+    const uint64_t end_off = nrec ? rec_off[nrec] : 0;
+    uint64_t r0 = 0;
+    uint32_t g0 = 0, batch = 0;
+    int rc = 0;
+    while (g0 < ngenomes && !rc) {
+        uint32_t g1 = g0;
+        uint64_t r1 = r0;
+        const uint64_t b0 = r0 < nrec ? rec_off[r0] : end_off;
+        for (;;) {
+            while (r1 < nrec && rec2genome[r1] == g1) r1++;
+            g1++;
+            const uint64_t b1 = r1 < nrec ? rec_off[r1] : end_off;
+            if (g1 >= ngenomes || b1 - b0 >= chunk_bytes) break;
         }
-        if (cudaMemcpyAsync(d_seq, seqs, nbytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
-            cudaMemsetAsync(d_seq + nbytes, 0, 64, ctx->stream) != cudaSuccess) {
-            tc_set_error("tc_sketch_kssd: H2D copy failed");
-            break;
+        const uint64_t b1 = r1 < nrec ? rec_off[r1] : end_off;
+        const uint64_t base = b0 & ~15ull;
+        const size_t nbytes = (size_t)(b1 - base);
+        K2Slot &sl = ws->slot[batch & 1];
+        if (sl.used && cudaEventSynchronize(sl.done) != cudaSuccess) { tc_set_error("tc_sketch_kssd: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; break; }
+        if (nbytes + 64 > sl.seq_cap) {
+            cudaFree(sl.d_seq); sl.d_seq = nullptr; sl.seq_cap = 0;
+            if (cudaMalloc(&sl.d_seq, nbytes + 64 + nbytes / 8) != cudaSuccess) { tc_set_error("tc_sketch_kssd: out of device memory (%zu bytes of sequence per batch)", nbytes); rc = 1; break; }
+            sl.seq_cap = nbytes + 64 + nbytes / 8;
         }
-        rc = sketch_kssd_impl(ctx, d_seq, rec_off, rec2genome, nrec, ngenomes, kmer_size, drlevel, shuffled_dim, d_out,
-                              out_stride, d_n);
-        if (rc) break;
-        if (cudaMemcpyAsync(out_hashes, d_out, (uint64_t)ngenomes * out_stride * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-            cudaMemcpyAsync(out_n, d_n, (size_t)ngenomes * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        if ((nbytes && cudaMemcpyAsync(sl.d_seq, seqs + base, nbytes, cudaMemcpyHostToDevice, cs) != cudaSuccess) ||
+            cudaMemsetAsync(sl.d_seq + nbytes, 0, 64, cs) != cudaSuccess ||
+            cudaEventRecord(sl.copied, cs) != cudaSuccess || cudaStreamWaitEvent(st, sl.copied, 0) != cudaSuccess) {
+            tc_set_error("tc_sketch_kssd: H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = 1; break;
+        }
+        rc = k2_enqueue(ctx, ws, sl, st, a, sl.d_seq, rec_off, rec2genome, r0, r1, g0, g1 - g0, base,
+                        ws->d_out + (size_t)g0 * out_stride, out_stride, ws->d_n + g0);
+        if (!rc && cudaEventRecord(sl.done, st) != cudaSuccess) { tc_set_error("tc_sketch_kssd: event record failed"); rc = 1; }
+        g0 = g1; r0 = r1; batch++;
+    }
+    if (!rc) {
+        if (cudaMemcpyAsync(out_hashes, ws->d_out, (size_t)ngenomes * out_stride * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(out_n, ws->d_n, (size_t)ngenomes * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
             tc_set_error("tc_sketch_kssd: D2H copy failed");
             rc = 1;
         }
-    } while (0);
-    cudaFree(d_seq); cudaFree(d_out); cudaFree(d_n);
+    }
+    const cudaError_t e1 = cudaStreamSynchronize(cs);
+    if (!rc) rc = k2_check_overflow(ws, st, out_stride);
+    else cudaStreamSynchronize(st);
+    if (!rc && e1 != cudaSuccess) { tc_set_error("tc_sketch_kssd: %s", cudaGetErrorString(e1)); rc = 1; }
     return rc;
 }

@@ -82,6 +82,7 @@ struct tc_ctx {
 
     // K1 pipeline workspace (k1_sketch.cu): staging slots, copy stream
     void *k1_ws = nullptr;
+    void *k2_ws = nullptr;       // K2 (KSSD) pipeline workspace (k2_kssd.cu)
 
     // scratch
     void *d_scratch = nullptr;
@@ -90,6 +91,7 @@ struct tc_ctx {
 
 int tc_scratch(tc_ctx *ctx, size_t bytes, void **out);
 void tc_k1_free(tc_ctx *ctx);
+void tc_k2_free(tc_ctx *ctx);
 
 // tile-kernel entry points (k3_tile.cu)
 // semb_size > 0 selects semantic B (Mash union-limited merge, MinHash.cpp:982-1101) with that sketchSize

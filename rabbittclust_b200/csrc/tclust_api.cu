@@ -79,6 +79,7 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     free_sketches(ctx);
     tc_rep_table_free(ctx);
     tc_k1_free(ctx);
+    tc_k2_free(ctx);
     cudaFree(ctx->d_edge_count);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_kssd_dim);

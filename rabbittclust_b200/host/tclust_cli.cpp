@@ -287,20 +287,11 @@ bool tune_kssd_parameters(Options &o)
     return true;
 }
 
-// generate_shuffle_dim (src/SketchInfo.cpp:60-102): identity permutation of 16^half_subk slots, Fisher-Yates
-// with glibc srand(23)/rand(), then again with srand(348842630).  glibc's rand() stream is part of the
-// reference's definition of the KSSD sketch, hence host-only.
-void shuffle_in_place(vector<int32_t> &arr, unsigned seed)
-{
-    srand(seed);
-    for (int i = (int)arr.size() - 1; i > 0; i--) std::swap(arr[i], arr[rand() % (i + 1)]);
-}
+// generate_shuffle_dim (src/SketchInfo.cpp:60-102) lives behind the ABI (host-only: glibc rand stream)
 void make_shuffled_dim(int half_subk)
 {
     g_shuffled_dim.resize((size_t)1 << (4 * half_subk));
-    for (size_t i = 0; i < g_shuffled_dim.size(); i++) g_shuffled_dim[i] = (int32_t)i;
-    shuffle_in_place(g_shuffled_dim, 23);
-    shuffle_in_place(g_shuffled_dim, 348842630u);
+    tc_or_die(tc_kssd_shuffled_dim(half_subk, g_shuffled_dim.data()), "shuffled_dim");
 }
 
 // ---------------------------------------------------------------------------- sketching
