@@ -23,6 +23,12 @@
 namespace {
 
 constexpr int K2_THREADS = 256;
+// presence filter of the dimension test.  Only 16^(half_subk-drlevel) of the 16^half_subk slots pass
+// (4096 of 16.7 M at the defaults); testing every window against the 64 MB table makes the kernel L2-sector bound
+// (one random 32 B sector per base).  A 2^18-bit bitmap in shared memory (bit = slot id mod 2^18) answers
+// "cannot pass" for 98.4 % of the windows; only the rest read the table.
+constexpr int K2_FILTER_BITS = 1 << 18;
+constexpr int K2_FILTER_WORDS = K2_FILTER_BITS / 32;
 
 struct K2Seg {
     unsigned long long rec_start;   // first byte of the record
@@ -38,6 +44,7 @@ struct K2Args {
     uint32_t nseg;
     unsigned int *seg_counter;
     const int32_t *shuffled_dim;
+    const uint32_t *dim_filter;     // K2_FILTER_BITS-bit presence bitmap of the slots that pass (see k2_setup)
     int kmer, drlevel, half_outctx_len, dim_end, use64, rev_add_move;
     unsigned long long tupmask, domask, undomask0, undomask1;
     uint64_t *out; unsigned long long out_stride; uint32_t *cnt;
@@ -46,6 +53,9 @@ struct K2Args {
 __global__ void __launch_bounds__(K2_THREADS) k2_kssd_kernel(const K2Args a)
 {
     __shared__ uint32_t s_seg;
+    __shared__ uint32_t s_filter[K2_FILTER_WORDS];
+    for (int i = threadIdx.x; i < K2_FILTER_WORDS; i += K2_THREADS) s_filter[i] = __ldg(a.dim_filter + i);
+    __syncthreads();
     for (;;) {
         if (threadIdx.x == 0) s_seg = atomicAdd(a.seg_counter, 1u);
         __syncthreads();
@@ -82,7 +92,9 @@ __global__ void __launch_bounds__(K2_THREADS) k2_kssd_kernel(const K2Args a)
             if (run >= a.kmer && pos >= e0) {
                 const unsigned long long uni = tuple < rvs ? tuple : rvs;
                 const uint32_t dim_id = (uint32_t)((uni & a.domask) >> (a.half_outctx_len * 2));
-                const int pf = __ldg(a.shuffled_dim + dim_id);
+                const uint32_t fb = dim_id & (K2_FILTER_BITS - 1);
+                const bool maybe = (s_filter[fb >> 5] >> (fb & 31u)) & 1u;
+                const int pf = maybe ? __ldg(a.shuffled_dim + dim_id) : a.dim_end;
                 if (pf < a.dim_end) {
                     unsigned long long dr = (((uni & a.undomask0) |
                                               ((uni & a.undomask1) << (a.kmer * 2 - a.half_outctx_len * 4)))
@@ -183,13 +195,20 @@ int k2_setup(tc_ctx *ctx, int kmer_size, int drlevel, const int32_t *shuffled_di
     a.undomask0 = undomask ^ a.undomask1;
     // shuffled_dim table: resident per context (the reference generates it once per process)
     const size_t dim_n = (size_t)1 << (4 * half_subk);
-    if (ctx->kssd_dim_host != shuffled_dim || ctx->kssd_dim_n != dim_n) {
+    if (ctx->kssd_dim_host != shuffled_dim || ctx->kssd_dim_n != dim_n || ctx->kssd_dim_end != a.dim_end) {
         cudaFree(ctx->d_kssd_dim); ctx->d_kssd_dim = nullptr; ctx->kssd_dim_host = nullptr;
+        cudaFree(ctx->d_kssd_filter); ctx->d_kssd_filter = nullptr;
         TC_CUDA(cudaMalloc(&ctx->d_kssd_dim, dim_n * 4));
+        TC_CUDA(cudaMalloc(&ctx->d_kssd_filter, K2_FILTER_WORDS * 4));
         TC_CUDA(cudaMemcpy(ctx->d_kssd_dim, shuffled_dim, dim_n * 4, cudaMemcpyHostToDevice));
-        ctx->kssd_dim_host = shuffled_dim; ctx->kssd_dim_n = dim_n;
+        std::vector<uint32_t> filt(K2_FILTER_WORDS, 0u);
+        for (size_t t = 0; t < dim_n; t++)
+            if (shuffled_dim[t] < a.dim_end) { const uint32_t fb = (uint32_t)t & (K2_FILTER_BITS - 1); filt[fb >> 5] |= 1u << (fb & 31u); }
+        TC_CUDA(cudaMemcpy(ctx->d_kssd_filter, filt.data(), K2_FILTER_WORDS * 4, cudaMemcpyHostToDevice));
+        ctx->kssd_dim_host = shuffled_dim; ctx->kssd_dim_n = dim_n; ctx->kssd_dim_end = a.dim_end;
     }
     a.shuffled_dim = ctx->d_kssd_dim;
+    a.dim_filter = ctx->d_kssd_filter;
     return 0;
 }
 
@@ -261,7 +280,7 @@ int k2_enqueue(tc_ctx *ctx, K2Workspace *ws, K2Slot &sl, cudaStream_t st, K2Args
     a.seg_counter = reinterpret_cast<unsigned int *>(sl.d_meta + o_ctr);
     a.out = out_dev; a.out_stride = out_stride; a.cnt = d_cnt;
     if (nseg) {
-        const int grid = (int)std::min<uint64_t>(nseg, (uint64_t)ctx->num_sms * 8);
+        const int grid = (int)std::min<uint64_t>(nseg, (uint64_t)ctx->num_sms * 6);   // 6 CTAs x 32 KB filter per SM
         k2_kssd_kernel<<<grid, K2_THREADS, 0, st>>>(a);
         ctx->launches++;
         TC_CUDA(cudaGetLastError());

@@ -77,6 +77,8 @@ struct tc_ctx {
 
     // KSSD shuffled_dim table (K2), resident once uploaded
     int32_t *d_kssd_dim = nullptr;
+    uint32_t *d_kssd_filter = nullptr;   // presence bitmap of the passing slots (k2_kssd.cu)
+    int kssd_dim_end = -1;
     const int32_t *kssd_dim_host = nullptr;
     size_t kssd_dim_n = 0;
 

@@ -82,7 +82,7 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     tc_k2_free(ctx);
     cudaFree(ctx->d_edge_count);
     cudaFree(ctx->d_scratch);
-    cudaFree(ctx->d_kssd_dim);
+    cudaFree(ctx->d_kssd_dim); cudaFree(ctx->d_kssd_filter);
     cudaFree(ctx->d_kh_state); cudaFree(ctx->d_kh_units);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
