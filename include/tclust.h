@@ -194,6 +194,11 @@ int tc_greedy_scan(tc_ctx *ctx, uint32_t q0, uint32_t q1, const uint32_t *rep_id
 int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, double threshold,
                       int32_t *rep_of, uint32_t *n_clusters);
 
+/* KssdGreedyClusterWithInvertedIndex (src/greedy.cpp:566-899) with one thread, for sketches the caller has already
+ * put in the reference's processing order (hash count descending, the reference's std::sort; see the CLI):
+ * per-pair common_min, the representative with the largest Jaccard wins, ties -> first in `touched` order. */
+int tc_greedy_cluster_kssd(tc_ctx *ctx, int kmer_size, double threshold, int32_t *rep_of, uint32_t *n_clusters);
+
 /* brute-force greedyCluster (src/greedy.cpp:285-351) with one thread: genome j joins the nearest representative
  * with MinHash::distance (containment: containDistance) <= threshold, ties -> the earliest-created one; else it
  * becomes a representative.  threshold < 1. */

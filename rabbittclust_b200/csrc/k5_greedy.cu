@@ -182,8 +182,10 @@ extern "C" int tc_greedy_scan(tc_ctx *ctx, uint32_t q0, uint32_t q1, const uint3
 // brute = true : greedyCluster (greedy.cpp:285-351): MinHash::distance (semantic B with sketchSize semb_size) or
 //                containDistance of the query against every representative; nearest wins, ties -> earliest-created
 //                representative (std::map<double,int>::insert keeps the first key, one thread).
+// kssd = true  : KssdGreedyClusterWithInvertedIndex (greedy.cpp:566-899) with one thread: per-pair common_min,
+//                best = largest Jaccard (strict >) in `touched` order, no distance test beyond common_min.
 static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double threshold, bool brute, uint32_t semb_size,
-                       int32_t *rep_of, uint32_t *n_clusters)
+                       int32_t *rep_of, uint32_t *n_clusters, bool kssd = false)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0, "tc_greedy_cluster: no sketches uploaded");
@@ -191,7 +193,7 @@ static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double thres
     cudaStream_t st = ctx->stream;
     // fixed-size fast path detection over the first 100 sketches (greedy.cpp:1092-1103)
     const int fixed_size = (int)ctx->h_size[0];
-    bool all_fixed = !containment && !brute;
+    bool all_fixed = !containment && !brute && !kssd;
     if (brute && containment) semb_size = 0;   // containDistance counts the full intersection
     for (uint32_t i = 1; i < std::min<uint32_t>(100, n) && all_fixed; i++)
         if ((int)ctx->h_size[i] != fixed_size) all_fixed = false;
@@ -259,7 +261,7 @@ static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double thres
             });
             const int size_ref = (int)ctx->h_size[q];
             int best_common = -1, best_rep = -1;
-            double best_dist = std::numeric_limits<double>::max();
+            double best_dist = std::numeric_limits<double>::max(), best_jaccard = -1.0;
             for (tc_cand *c = lo; c < end; c++) {
                 const int common = (int)c->common, size_qry = (int)ctx->h_size[c->rep];
                 if (brute) {   // greedy.cpp:297-334: dist <= threshold, smallest distance, first inserted wins
@@ -271,6 +273,12 @@ static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double thres
                 const int common_min = all_fixed ? cmin_fixed
                                                  : tc_greedy_common_min(threshold, kmer_size, size_ref, size_qry, containment);
                 if (common < common_min) continue;
+                if (kssd) {   // greedy.cpp:783-794: compare Jaccard directly, larger wins, first in touched order on ties
+                    const int denom = size_ref + size_qry - common;
+                    const double jaccard = denom == 0 ? 1.0 : (double)common / denom;
+                    if (jaccard > best_jaccard) { best_jaccard = jaccard; best_rep = (int)c->rep; }
+                    continue;
+                }
                 if (all_fixed) {
                     if (common > best_common) { best_common = common; best_rep = (int)c->rep; }
                 } else {
@@ -297,6 +305,11 @@ extern "C" int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, do
                                  uint32_t *n_clusters)
 {
     return greedy_impl(ctx, kmer_size, containment, threshold, false, 0, rep_of, n_clusters);
+}
+
+extern "C" int tc_greedy_cluster_kssd(tc_ctx *ctx, int kmer_size, double threshold, int32_t *rep_of, uint32_t *n_clusters)
+{
+    return greedy_impl(ctx, kmer_size, 0, threshold, false, 0, rep_of, n_clusters, true);
 }
 
 extern "C" int tc_greedy_cluster_bruteforce(tc_ctx *ctx, int kmer_size, uint32_t sketch_size, int containment,

@@ -20,7 +20,7 @@
 // (tc_host_alloc); a batch is sketched by a background thread (tc_sketch_* pipelines its H2D copies) while the
 // next batch is being parsed.
 // Out of scope: --append/--db/--save-rep, tree/linkage output, --dense, dbscan/leiden,
-// clust-greedy --fast, --fast with a single multi-FASTA input (the reference's -i KSSD consumer is the
+// --fast with a single multi-FASTA input (the reference's -i KSSD consumer is the
 // quirky variant).
 #include "../../include/tclust.h"
 #include <zlib.h>
@@ -626,6 +626,9 @@ void save_kssd_sketches(const vector<Genome> &g, const string &folder, bool by_f
     }
     fclose(fp);
     cerr << "-----save the kssd sketches into: " << folder << endl;
+#ifdef GREEDY_CLUST
+    return;     // clust-greedy writes no index files (sub_command.cpp:1943-1947)
+#endif
     // kssd.sketch.index / kssd.sketch.dict: hash -> genome ids.  The reference's --fast --presketched reader has
     // no rebuild path and exits without them (src/MST.cpp:242-337), so a folder we write carries both.  Entries
     // are written in ascending hash order (the reference's order is its hash-map iteration order; the reader
@@ -771,11 +774,18 @@ void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_fi
 {
     if (g.empty()) die("no sketches to cluster");
     double t2 = now_s();
+#ifdef GREEDY_CLUST
+    // KssdGreedyClusterWithInvertedIndex (greedy.cpp:592-599): std::sort by hash count, descending.  The sort is not
+    // stable; the same libstdc++ algorithm on the same key sequence yields the same permutation, which is what
+    // makes the cluster file comparable with the reference's.
+    if (o.fast) std::sort(g.begin(), g.end(), [](const Genome &a, const Genome &b) { return a.hashes.size() > b.hashes.size(); });
+#endif
     upload(ctx, g);
 #ifdef GREEDY_CLUST
     vector<int32_t> rep_of(g.size());
     uint32_t nclust = 0;
-    tc_or_die(tc_greedy_cluster(ctx, o.kmer, o.containment, o.threshold, rep_of.data(), &nclust), "greedy clustering");
+    if (o.fast) tc_or_die(tc_greedy_cluster_kssd(ctx, o.kmer, o.threshold, rep_of.data(), &nclust), "greedy clustering");
+    else tc_or_die(tc_greedy_cluster(ctx, o.kmer, o.containment, o.threshold, rep_of.data(), &nclust), "greedy clustering");
     vector<vector<int>> cluster;
     vector<int> cid(g.size(), -1);
     for (int j = 0; j < (int)g.size(); j++) {
@@ -847,9 +857,6 @@ int main(int argc, char **argv)
     if (o.threads < 1) { fprintf(stderr, "-----Invalid thread number %d\n", o.threads); return 1; }
     fprintf(stderr, "-----set the thread number %d\n", o.threads);
     if (!o.has_threshold) cerr << "-----use default threshold: " << o.threshold << endl;
-#ifdef GREEDY_CLUST
-    if (o.fast) die("clust-greedy --fast is not part of this build (SURVEY.md 8f-2); use clust-mst --fast or clust-greedy without --fast");
-#endif
     if (o.fast && (o.drlevel < 0 || o.drlevel > 8)) { cerr << "ERROR: invalid drlevel " << o.drlevel << ", should be in [0, 8]" << endl; return 1; }
 
 #ifndef GREEDY_CLUST
@@ -873,6 +880,7 @@ int main(int argc, char **argv)
         else by_file = load_sketches(g, o.folder, o);
         cerr << "-----the size of sketches is: " << g.size() << endl;
 #ifdef GREEDY_CLUST
+        if (!o.fast)
         std::sort(g.begin(), g.end(), [](const Genome &a, const Genome &b) {      // cmpGenomeSize / cmpSeqSize
             if (a.total_len != b.total_len) return a.total_len > b.total_len;
             return a.id < b.id;

@@ -174,3 +174,18 @@ def test_clust_mst_fast_golden_folder(tmp_path):
     b = sketch_io.read_edge_mst(os.path.join(of, "edge.mst"))
     assert np.array_equal(np.sort(a["dist"]), np.sort(b["dist"]))
     assert _partition(os.path.join(gold, "clusters.txt")) == _partition(str(tmp_path / "clusters.txt"))
+
+
+def test_clust_greedy_fast_matches_reference(genomes, tmp_path):
+    """clust-greedy --fast (KssdGreedyClusterWithInvertedIndex): same sketch folder, byte-identical cluster
+    file with -t 1 (the size sort is the same std::sort on the same key sequence), also from --presketched"""
+    lst, _ = genomes
+    args = ["--fast", "-l", "-i", lst, "-d", "0.05", "-o", "out.txt"]
+    rf, _ = _run(os.path.join(REF, "clust-greedy"), ["-t", "1"] + args, str(tmp_path / "ref"))
+    of, _ = _run(os.path.join(OURS, "clust-greedy"), args, str(tmp_path / "ours"))
+    for fn in ("kssd.hash.sketch", "kssd.info.sketch"):
+        assert _same_bytes(os.path.join(rf, fn), os.path.join(of, fn)), fn
+    assert open(str(tmp_path / "ref" / "out.txt")).read() == open(str(tmp_path / "ours" / "out.txt")).read()
+    _run(os.path.join(REF, "clust-greedy"), ["-t", "1", "--fast", "--presketched", rf, "-d", "0.02", "-o", "pre.txt"], str(tmp_path / "ref"))
+    _run(os.path.join(OURS, "clust-greedy"), ["--fast", "--presketched", rf, "-d", "0.02", "-o", "pre.txt"], str(tmp_path / "ours"))
+    assert open(str(tmp_path / "ref" / "pre.txt")).read() == open(str(tmp_path / "ours" / "pre.txt")).read()

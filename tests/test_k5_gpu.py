@@ -110,3 +110,55 @@ def test_greedy_large_vs_oracle(ctx, oracle):
     sk = [h[int(off[i]):int(off[i + 1])] for i in perm]
     nc = _check_greedy(ctx, oracle, sk, 21, 0.05, False)
     assert nc >= 60
+
+
+def test_greedy_kssd_rule_live_against_reference(ctx, oracle, tmp_path):
+    """KssdGreedyClusterWithInvertedIndex of the unmodified reference (clust-greedy --fast --presketched, -t 1) on a
+    synthetic KSSD folder with many equal-size ties vs tc_greedy_cluster_kssd on the same processing order."""
+    import struct
+    import subprocess
+    from rabbittclust_b200 import sketch_io
+    exe = oracle.ref_bin("clust-greedy")
+    if exe is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(3)
+    sk = []
+    for f in range(12):
+        pool = rng.choice(1 << 24, 480, replace=False)
+        for m in range(10):
+            keep = rng.choice(pool, int(480 * rng.uniform(0.5, 1.0)), replace=False)
+            priv = rng.integers(0, 1 << 24, int(rng.integers(0, 60)))
+            sk.append(np.unique(np.concatenate([keep, priv])).astype(np.uint64))
+    n = len(sk)
+    d = tmp_path / "kssd"
+    d.mkdir()
+    half_k, half_subk, drlevel = 9, 6, 3
+    with open(d / "kssd.hash.sketch", "wb") as f:
+        f.write(struct.pack("<iiiii", (half_k << 8) + (half_subk << 4) + drlevel, half_k, half_subk, drlevel, n))
+        for h in sk:
+            f.write(struct.pack("<Q", len(h))); f.write(h.astype("<u4").tobytes())
+    with open(d / "kssd.info.sketch", "wb") as f:
+        f.write(struct.pack("<?Q", True, n))
+        for i in range(n):
+            fn, nm, cm = b"f%03d.fna" % i, b"s%03d" % i, b"c"
+            f.write(struct.pack("<iiiiQ", len(fn), len(nm), len(cm), 0, 2000000)); f.write(fn + nm + cm); f.write(struct.pack("<?", False))
+    subprocess.run([exe, "-t", "1", "--fast", "--presketched", str(d), "-d", "0.05", "-o", "out.txt"], cwd=tmp_path, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    # the cluster file carries (position in the reference's processing order, name): recover that order (its
+    # std::sort by size is not stable) and replay exactly the same sequence on the GPU path
+    ref = sketch_io.parse_cluster_file(str(tmp_path / "out.txt"))
+    pos_of = {}
+    for c in ref:
+        for gid, nm in c:
+            pos_of[gid] = int(nm[1:])
+    assert sorted(pos_of) == list(range(n))
+    order = [pos_of[p] for p in range(n)]
+    assert all(len(sk[order[i]]) >= len(sk[order[i + 1]]) for i in range(n - 1))
+    ctx.upload([sk[i] for i in order])
+    nc, rep = ctx.greedy_cluster_kssd(18, 0.05)
+    want = np.zeros(n, np.int32)
+    for c in ref:
+        for gid, _ in c:
+            want[gid] = c[0][0]
+    assert nc == len(ref)
+    assert np.array_equal(rep, want)
