@@ -101,6 +101,11 @@ def ref_pairs(n_sample, threads, hashes, off, k=21, s=1000):
     return json.loads(out)
 
 
+def pyoracle_ref_harness():
+    from oracle import pyoracle
+    return pyoracle.ref_bin("ref_harness")
+
+
 def port_pairs(n_sample, hashes, off):
     """Scalar oracle port (full-intersection merge), single thread."""
     from oracle import pyoracle
@@ -144,6 +149,17 @@ def run_reference(args):
                                  "sample": "%d sketches of the same synthetic model = %d pairs per step" %
                                            (n_sample, vals[0]["pairs"])},
                 "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        # the sketch half of the metric on the same arm: MinHash::update of the reference on all host threads
+        exe = pyoracle_ref_harness()
+        if exe and not args.no_sketch:
+            ng = max(threads, 8)
+            r = json.loads(subprocess.check_output([exe, "update", "21", "1000", str(threads), str(args.genome_len), str(ng)]))
+            line["sketch"] = {"metric": "genomes sketched/sec", "value": r["genomes_per_s"], "unit": "genomes/s",
+                              "cpu_baseline": {"value": r["genomes_per_s"], "unit": "genomes/s", "cores": r["threads"],
+                                               "kind": "reference", "sample": "%d genomes of %d bp, MinHash::update AVX2 build"
+                                               % (r["genomes"], r["len"])},
+                              "e2e": {"value": r["genomes_per_s"], "unit": "genomes/s", "h2d_bytes_per_step": 0,
+                                      "d2h_bytes_per_step": 0}}
     else:
         from oracle import pyoracle
         exe = pyoracle.ref_bin("ref_harness")
