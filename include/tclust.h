@@ -173,6 +173,15 @@ int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double threshold,
            tc_edge *out, uint64_t *n_out);
 
 /*
+ * --dense epilogue of compute_minhash_mst / compute_kssd_mst (src/MST.cpp:1517-1530, 1702-1712) over the candidate
+ * pairs of the last tc_allpairs_pass / tc_mst on this context: dense[t*n + v] = number of candidate neighbours of
+ * genome v with distance <= t/dense_span (lower_bound bucketing made cumulative over t, the layout of mst.dense,
+ * src/MST_IO.cpp:219-233); ani[b], b = (int)((1-dist)*100) clamped to 100 (mst.ani, :235-250).  Bit-exact: bins are
+ * decided on exact J = common/denom against host-computed thresholds of the reference's glibc expression.
+ */
+int tc_dense_ani(tc_ctx *ctx, int kmer_size, int containment, int dense_span, int32_t *dense, uint64_t *ani);
+
+/*
  * Brute-force MST = modifyMST (src/MST.cpp:809-1018): every pair gets MinHash::distance (semantic B with
  * `sketch_size`; containment != 0: containDistance) and the MST of the COMPLETE graph is returned: n-1 edges
  * {i, j<i, dist} sorted by (dist, i, j).  Pairs without a shared hash have distance exactly 1; they are not

@@ -73,6 +73,10 @@ def lib():
         L.oc_mst_bruteforce.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(Edge)]
         L.oc_greedy_bruteforce.restype = C.c_int
         L.oc_greedy_bruteforce.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_double, i32p]
+        L.oc_dense_ani.restype = None
+        L.oc_dense_ani.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, i32p, u64p]
+        L.oc_remove_noise_clusters.restype = C.c_int
+        L.oc_remove_noise_clusters.argtypes = [C.POINTER(Edge), C.c_size_t, C.c_int, C.c_double, i32p, C.c_int, i32p, i32p]
         _LIB = L
     return _LIB
 
@@ -192,6 +196,25 @@ def greedy_bruteforce(sketches, k, sketch_size, threshold, containment=False):
     nc = lib().oc_greedy_bruteforce(_p(h, C.c_uint64), _p(off, C.c_uint64), n, k, sketch_size, int(containment),
                                     threshold, _p(rep, C.c_int32))
     return nc, rep[:n]
+
+
+def dense_ani(sketches, k, threshold, containment=False, span=100):
+    h, off = pack_sketches(sketches)
+    n = len(sketches)
+    dense = np.zeros((span, max(n, 1)), np.int32)
+    ani = np.zeros(101, np.uint64)
+    lib().oc_dense_ani(_p(h, C.c_uint64), _p(off, C.c_uint64), n, k, int(containment), threshold, span,
+                       _p(dense, C.c_int32), _p(ani, C.c_uint64))
+    return dense, ani
+
+
+def remove_noise_clusters(edges, n, threshold, dense):
+    e = np.ascontiguousarray(edges, EDGE_DTYPE)
+    d = np.ascontiguousarray(dense, np.int32)
+    labels = np.zeros(max(n, 1), np.int32); order = np.zeros(max(n, 1), np.int32)
+    nc = lib().oc_remove_noise_clusters(e.ctypes.data_as(C.POINTER(Edge)), len(e), n, threshold, _p(d, C.c_int32),
+                                        d.shape[0], _p(labels, C.c_int32), _p(order, C.c_int32))
+    return nc, labels[:n], order[:n]
 
 
 def common_matrix(sketches):

@@ -542,3 +542,81 @@ int oc_greedy_bruteforce(const uint64_t *hashes, const uint64_t *off, int N, int
     free(reps);
     return nrep;
 }
+
+/* ------------------------------------------------------------------ --dense epilogue */
+/* the `if(!no_dense)` block of compute_minhash_mst (MST.cpp:1517-1530) over the candidate pairs
+ * (common >= 1, size-ratio filter), then the cumulative pass (:1702-1712).  dense: span x N ints,
+ * ani: 101 counters. */
+void oc_dense_ani(const uint64_t *hashes, const uint64_t *off, int N, int k, int containment,
+                  double threshold, int span, int32_t *dense, uint64_t *ani)
+{
+    int radio = oc_radio(threshold, k);
+    double step = 1.0 / span;
+    double *radius = (double *)malloc(sizeof(double) * span);
+    for (int t = 0; t < span; t++) radius[t] = step * (double)t;
+    memset(dense, 0, sizeof(int32_t) * (size_t)span * N);
+    memset(ani, 0, sizeof(uint64_t) * 101);
+    for (int i = 0; i < N; i++) {
+        int size0 = (int)(off[i + 1] - off[i]);
+        if (size0 == 0) continue;
+        for (int j = 0; j < i; j++) {
+            int size1 = (int)(off[j + 1] - off[j]);
+            if (size1 == 0) continue;
+            int common = (int)oc_intersect_u64(hashes + off[i], size0, hashes + off[j], size1, NULL);
+            if (common == 0) continue;
+            int mn = size0 < size1 ? size0 : size1, mx = size0 > size1 ? size0 : size1;
+            if (mx > radio * mn) continue;
+            double d = containment ? oc_aaf_dist_mst(common, size0, size1, k) : oc_mash_dist_A(common, size0, size1, k);
+            int t0 = 0;                                   /* std::lower_bound(distRadius, ..., d) */
+            while (t0 < span && radius[t0] < d) t0++;
+            if (t0 < span) { dense[(size_t)t0 * N + i]++; dense[(size_t)t0 * N + j]++; }
+            double tmpANI = 1.0 - d;
+            int ANI = (int)(tmpANI * 100.0);
+            if (ANI >= 101) ANI = 100;
+            ani[ANI]++;
+        }
+    }
+    for (int v = 0; v < N; v++) {
+        int acc = 0;
+        for (int t = 0; t < span; t++) { acc += dense[(size_t)t * N + v]; dense[(size_t)t * N + v] = acc; }
+    }
+    free(radius);
+}
+
+/* getNoiseNode (MST.cpp:189-211) per cluster of size > 1 with alpha = 2 at denseIndex = threshold / 0.01
+ * (sub_command.cpp:3075-3092), then modifyForest (:87-106) and the BFS clusters: labels/order as
+ * oc_clusters_from_mst.  forest = MST edges with dist <= threshold.  Returns #clusters. */
+int oc_remove_noise_clusters(const oc_edge *mst, size_t n_edges, int N, double threshold, const int32_t *dense,
+                             int span, int32_t *labels, int32_t *order)
+{
+    int32_t *lab0 = (int32_t *)malloc(sizeof(int32_t) * (N + 1)), *ord0 = (int32_t *)malloc(sizeof(int32_t) * (N + 1));
+    int nc = oc_clusters_from_mst(mst, n_edges, N, threshold, lab0, ord0);
+    int alpha = 2;
+    int denseIndex = threshold / 0.01;
+    char *noise = (char *)calloc(N + 1, 1);
+    int *vals = (int *)malloc(sizeof(int) * (N + 1));
+    int pos = 0;
+    for (int c = 0; c < nc; c++) {
+        int start = pos, m = 0;
+        while (pos < N && lab0[ord0[pos]] == c) { vals[m++] = dense[(size_t)denseIndex * N + ord0[pos]]; pos++; }
+        if (m == 1) continue;
+        /* Q1 of the sorted density values */
+        int *sorted = (int *)malloc(sizeof(int) * m);
+        memcpy(sorted, vals, sizeof(int) * m);
+        for (int a = 1; a < m; a++) { int x = sorted[a], b = a - 1; while (b >= 0 && sorted[b] > x) { sorted[b + 1] = sorted[b]; b--; } sorted[b + 1] = x; }
+        int denseQ1 = sorted[m / 4];
+        int thr = alpha;
+        if (denseQ1 - 1 < thr) thr = denseQ1 - 1;
+        if (thr < 0) thr = 0;
+        for (int a = 0; a < m; a++) if (vals[a] <= thr) noise[ord0[start + a]] = 1;
+        free(sorted);
+    }
+    oc_edge *kept = (oc_edge *)malloc(sizeof(oc_edge) * (n_edges + 1));
+    size_t nk = 0;
+    for (size_t e = 0; e < n_edges; e++)
+        if (mst[e].dist <= threshold && !noise[mst[e].pre] && !noise[mst[e].suf]) kept[nk++] = mst[e];
+    int res = oc_clusters_from_mst(kept, nk, N, threshold, labels, order);
+    free(lab0); free(ord0); free(noise); free(vals); free(kept);
+    (void)span;
+    return res;
+}

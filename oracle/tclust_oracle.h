@@ -102,6 +102,12 @@ size_t oc_mst_bruteforce(const uint64_t *hashes, const uint64_t *off, int N, int
 int oc_greedy_bruteforce(const uint64_t *hashes, const uint64_t *off, int N, int k,
                          uint64_t sketch_size, int containment, double threshold, int32_t *rep_of);
 
+/* ---- --dense epilogue and noise removal ------------------------------------------------ */
+void oc_dense_ani(const uint64_t *hashes, const uint64_t *off, int N, int k, int containment,
+                  double threshold, int span, int32_t *dense /* span x N */, uint64_t *ani /* 101 */);
+int oc_remove_noise_clusters(const oc_edge *mst, size_t n_edges, int N, double threshold, const int32_t *dense,
+                             int span, int32_t *labels, int32_t *order);
+
 #ifdef __cplusplus
 }
 #endif

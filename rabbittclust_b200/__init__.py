@@ -23,7 +23,7 @@ SYMBOLS = [
     "tc_sketches_upload", "tc_sketches_upload_dev", "tc_pair_common", "tc_allpairs_pass",
     "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_mst",
     "tc_greedy_scan", "tc_greedy_cluster",
-    "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce", "tc_greedy_cluster_kssd",
+    "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce", "tc_greedy_cluster_kssd", "tc_dense_ani",
     "tc_jaccard_b", "tc_distance_b", "tc_contain_distance",
     "tc_mash_dist", "tc_aaf_dist", "tc_dist_from_key", "tc_radio", "tc_greedy_common_min", "tc_greedy_dist",
 ]
@@ -83,6 +83,7 @@ def lib():
     L.tc_mst_bruteforce.argtypes = [vp, C.c_int, C.c_uint32, C.c_int, vp, u64p]
     L.tc_greedy_cluster_bruteforce.argtypes = [vp, C.c_int, C.c_uint32, C.c_int, C.c_double, i32p, u32p]
     L.tc_greedy_cluster_kssd.argtypes = [vp, C.c_int, C.c_double, i32p, u32p]
+    L.tc_dense_ani.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, u64p]
     L.tc_jaccard_b.argtypes = [C.c_int] * 4
     L.tc_jaccard_b.restype = C.c_double
     L.tc_distance_b.argtypes = [C.c_int] * 5
@@ -237,6 +238,13 @@ class Context:
         _chk(lib().tc_greedy_cluster_bruteforce(self._h, k, sketch_size, int(containment), threshold,
                                                 _p(rep, C.c_int32), C.byref(nc)))
         return int(nc.value), rep[:self.n].copy()
+
+    def dense_ani(self, k, containment=False, span=100):
+        """--dense epilogue over the candidate pairs of the last pass: (dense[span, n] cumulative, ani[101])."""
+        dense = np.zeros((span, max(self.n, 1)), np.int32)
+        ani = np.zeros(101, np.uint64)
+        _chk(lib().tc_dense_ani(self._h, k, int(containment), span, _p(dense, C.c_int32), _p(ani, C.c_uint64)))
+        return dense, ani
 
     def greedy_cluster_kssd(self, k, threshold):
         rep = np.zeros(max(self.n, 1), np.int32)

@@ -19,7 +19,8 @@
 // FASTA feeder: files are decompressed/parsed on host threads into page-locked batch buffers
 // (tc_host_alloc); a batch is sketched by a background thread (tc_sketch_* pipelines its H2D copies) while the
 // next batch is being parsed.
-// Out of scope: --append/--db/--save-rep, tree/linkage output, --dense, dbscan/leiden,
+//   --dense                   src/MST.cpp:1517-1530,1702-1712 (tc_dense_ani), src/sub_command.cpp:3070-3100 (noise pass)
+// Out of scope: --append/--db/--save-rep, tree/linkage output, dbscan/leiden,
 // --fast with a single multi-FASTA input (the reference's -i KSSD consumer is the
 // quirky variant).
 #include "../../include/tclust.h"
@@ -65,6 +66,7 @@ struct Options {
     int threads = (int)std::thread::hardware_concurrency();
     bool by_file = false, containment = false, jaccard = false, set_kmer = false, no_save = false, fast = false;
     bool has_output = false, has_input = false, presketched = false, premsted = false, has_threshold = false;
+    bool dense = false;
     double threshold = 0.05;
     int kmer = 19, sketch_size = 1000, compress = 1000, drlevel = 3, device = 0;
     uint64_t min_len = 10000;
@@ -809,6 +811,47 @@ void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_fi
     print_result(cluster, g, by_file, o.output, o.threshold);
     cerr << "-----write the cluster result into: " << o.output << endl;
     cerr << "-----the cluster number of: " << o.output << " is: " << cluster.size() << endl;
+    if (o.dense) {
+        // density maps + ANI histogram over the candidate pairs (GPU epilogue), then the reference's noise-removal
+        // pass (sub_command.cpp:3070-3100; getNoiseNode MST.cpp:189-211, modifyForest :87-106)
+        double t4 = now_s();
+        const int span = 100, n = (int)g.size();                        // DENSE_SPAN, common.hpp:26
+        vector<int32_t> dense((size_t)span * n);
+        uint64_t ani[101];
+        tc_or_die(tc_dense_ani(ctx, o.kmer, o.containment, span, dense.data(), ani), "density / ANI histogram");
+        if (save) {
+            FILE *fa = fopen((folder + "/mst.ani").c_str(), "w+");
+            if (!fa) die("saveANI(), cannot open file: " + folder + "/mst.ani");
+            fwrite(ani, sizeof(uint64_t), 101, fa); fclose(fa);
+            cerr << "-----save the ani file into: " << folder << "/mst.ani" << endl;
+            FILE *fd = fopen((folder + "/mst.dense").c_str(), "w+");
+            if (!fd) die("saveDense(), cannot open the file: " + folder + "/mst.dense");
+            wr(fd, n); wr(fd, span);
+            fwrite(dense.data(), sizeof(int), (size_t)span * n, fd); fclose(fd);
+            cerr << "-----save the dense file into: " << folder << endl;
+        }
+        const int alpha = 2;
+        const int dense_index = o.threshold / 0.01;
+        vector<char> noise(n, 0);
+        size_t total_noise = 0;
+        for (const vector<int> &c : cluster) {
+            if (c.size() == 1) continue;
+            vector<int> vals;
+            for (int v : c) vals.push_back(dense[(size_t)dense_index * n + v]);
+            std::sort(vals.begin(), vals.end());
+            int thr = std::max(std::min(vals[vals.size() / 4] - 1, alpha), 0);
+            for (int v : c) if (dense[(size_t)dense_index * n + v] <= thr) { noise[v] = 1; total_noise++; }
+        }
+        cerr << "-----the total noiseArr size is: " << total_noise << endl;
+        vector<tc_edge> forest;
+        for (const tc_edge &e : mst) if (e.dist <= o.threshold && !noise[e.pre] && !noise[e.suf]) forest.push_back(e);
+        vector<vector<int>> clean = clusters_from_forest(forest, o.threshold, n);
+        const string out2 = o.output + ".removeNoise";
+        print_result(clean, g, by_file, out2, -1.0);
+        cerr << "-----write the cluster without noise into: " << out2 << endl;
+        cerr << "-----the cluster number of: " << out2 << " is: " << clean.size() << endl;
+        cerr << "========time of tuning cluster is: " << now_s() - t4 << "========" << endl;
+    }
 #endif
 }
 
@@ -820,7 +863,7 @@ void usage(const char *prog)
 #ifndef GREEDY_CLUST
             " | --premsted DIR"
 #endif
-            ") [--fast [--drlevel N]] [--device N]\n", prog);
+            ") [--fast [--drlevel N]] [--dense] [--device N]\n", prog);
 }
 
 }  // namespace
@@ -848,6 +891,7 @@ int main(int argc, char **argv)
         else if (f == "--premsted") { o.folder = need("--premsted"); o.premsted = true; }
 #endif
         else if (f == "--fast") o.fast = true;
+        else if (f == "--dense") o.dense = true;
         else if (f == "--drlevel") o.drlevel = atoi(need("--drlevel"));
         else if (f == "--device") o.device = atoi(need("--device"));
         else if (f == "-h" || f == "--help") { usage(argv[0]); return 0; }

@@ -191,3 +191,36 @@ def test_semantic_B_golden(oracle, name):
         assert np.array_equal(np.sort(mst["dist"]), z[name + "_mst_w" + tag])
         _, rep = oracle.greedy_bruteforce(sk, k, s, thr, contain)
         assert np.array_equal(rep, z[name + "_rep" + tag])
+
+
+def _read_dense(path):
+    import struct
+    raw = open(path, "rb").read()
+    n, span = struct.unpack_from("<ii", raw, 0)
+    return np.frombuffer(raw, "<i4", n * span, 8).reshape(span, n)
+
+
+@pytest.mark.parametrize("tag,contain", [("mash", False), ("contain", True)])
+def test_dense_ani_and_noise_removal_golden(oracle, tag, contain):
+    """--dense path: mst.ani / mst.dense of the reference's own run and its noise-removed cluster
+    files vs the oracle restatement."""
+    d = os.path.join(GOLD, "dense", tag)
+    hs = sketch_io.read_hash_sketch(os.path.join(d, "hash.sketch"))
+    _, info = sketch_io.read_info_sketch(os.path.join(d, "info.sketch"))
+    dense, ani = oracle.dense_ani(hs["sketches"], hs["k"], 0.05, contain)
+    assert np.array_equal(ani, np.fromfile(os.path.join(d, "mst.ani"), "<u8"))
+    assert np.array_equal(dense, _read_dense(os.path.join(d, "mst.dense")))
+    mst = sketch_io.read_edge_mst(os.path.join(d, "edge.mst"))
+    _, labels, _ = oracle.remove_noise_clusters(mst, len(info), 0.05, dense)
+    mine = sorted(sorted(info[i]["name"] for i in np.nonzero(labels == c)[0]) for c in range(labels.max() + 1))
+    assert mine == partition(sketch_io.parse_cluster_file(os.path.join(d, "clusters.txt.removeNoise")))
+    # --presketched run (the containment set has 3 noise genomes)
+    p = os.path.join(GOLD, "presketched", tag)
+    hs = sketch_io.read_hash_sketch(os.path.join(p, "hash.sketch"))
+    _, info = sketch_io.read_info_sketch(os.path.join(p, "info.sketch"))
+    n = len(info)
+    dense, _ = oracle.dense_ani(hs["sketches"], hs["k"], 0.05, hs["containment"])
+    mst = oracle.mst(hs["sketches"], hs["k"], 0.05, hs["containment"])
+    _, labels, _ = oracle.remove_noise_clusters(mst, n, 0.05, dense)
+    mine = sorted(sorted(info[i]["name"] for i in np.nonzero(labels == c)[0]) for c in range(labels.max() + 1))
+    assert mine == partition(sketch_io.parse_cluster_file(os.path.join(GOLD, "dense", "presk_%s.removeNoise" % tag)))
