@@ -20,7 +20,8 @@
 // (tc_host_alloc); a batch is sketched by a background thread (tc_sketch_* pipelines its H2D copies) while the
 // next batch is being parsed.
 //   --dense                   src/MST.cpp:1517-1530,1702-1712 (tc_dense_ani), src/sub_command.cpp:3070-3100 (noise pass)
-// Out of scope: --append/--db/--save-rep, tree/linkage output, dbscan/leiden,
+//   tree / linkage output     src/MST.cpp:1088-1147,1235-1284, src/MST_IO.cpp:263-375
+// Out of scope: --append/--db/--save-rep, --auto-threshold/--stability analytics, dbscan/leiden,
 // --fast with a single multi-FASTA input (the reference's -i KSSD consumer is the
 // quirky variant).
 #include "../../include/tclust.h"
@@ -66,7 +67,7 @@ struct Options {
     int threads = (int)std::thread::hardware_concurrency();
     bool by_file = false, containment = false, jaccard = false, set_kmer = false, no_save = false, fast = false;
     bool has_output = false, has_input = false, presketched = false, premsted = false, has_threshold = false;
-    bool dense = false;
+    bool dense = false, newick = false, phylip = false, nexus = false, linkage = false;
     double threshold = 0.05;
     int kmer = 19, sketch_size = 1000, compress = 1000, drlevel = 3, device = 0;
     uint64_t min_len = 10000;
@@ -772,6 +773,130 @@ vector<vector<int>> clusters_from_forest(const vector<tc_edge> &mst, double thre
     return res;
 }
 
+// ---- MST consumers: single-linkage dendrogram as Newick / PHYLIP / NEXUS text and as a linkage matrix
+// (get_newick_tree src/MST.cpp:1088-1147, get_linkage_from_mst :1235-1284, printers src/MST_IO.cpp:263-375).
+// Edges are merged in ascending distance (std::sort on dist alone, as the reference); every merge creates an inner
+// node at height = edge distance whose children hang on branches of length max(0, height - child height); the tree
+// printed is the component of genome 0.
+struct MergeForest {                      // union-find by rank; find() returns the set's root element
+    vector<int> p, r;
+    explicit MergeForest(int n) : p(n), r(n, 0) { for (int i = 0; i < n; i++) p[i] = i; }
+    int find(int x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; }
+    int unite(int a, int b)
+    {
+        a = find(a); b = find(b);
+        if (a == b) return a;
+        if (r[a] < r[b]) std::swap(a, b);
+        p[b] = a;
+        if (r[a] == r[b]) r[a]++;
+        return a;
+    }
+};
+
+vector<tc_edge> edges_by_distance(const vector<tc_edge> &mst)
+{
+    vector<tc_edge> e = mst;
+    std::sort(e.begin(), e.end(), [](const tc_edge &a, const tc_edge &b) { return a.dist < b.dist; });
+    return e;
+}
+
+string newick_of(const vector<Genome> &g, const vector<tc_edge> &mst, bool by_file)
+{
+    const int n = (int)g.size();
+    auto label = [&](int i) { return by_file ? g[i].file_name : g[i].name; };
+    if (n == 0) return ";";
+    if (n == 1) return label(0) + ";";
+    struct Child { int node; double len; };
+    vector<std::pair<Child, Child>> kids(2 * n - 1, {{-1, 0.0}, {-1, 0.0}});
+    vector<double> height(2 * n - 1, 0.0);
+    vector<int> top(n);                                   // dendrogram node on top of each set root
+    for (int i = 0; i < n; i++) top[i] = i;
+    MergeForest uf(n);
+    int next = n;
+    for (const tc_edge &e : edges_by_distance(mst)) {
+        const int ru = uf.find(e.pre), rv = uf.find(e.suf);
+        if (ru == rv) continue;
+        const int a = top[ru], b = top[rv];
+        kids[next] = {{a, std::max(0.0, e.dist - height[a])}, {b, std::max(0.0, e.dist - height[b])}};
+        height[next] = e.dist;
+        top[uf.unite(ru, rv)] = next++;
+    }
+    // iterative pre-order emission (a 100k-leaf caterpillar tree would overflow a recursive walk)
+    string out;
+    struct Frame { int node; int stage; double len; bool has_len; };
+    vector<Frame> st;
+    st.push_back({top[uf.find(0)], 0, 0.0, false});
+    while (!st.empty()) {
+        Frame &f = st.back();
+        const int node = f.node;
+        if (kids[node].first.node < 0) {                   // leaf
+            out += label(node);
+            if (f.has_len) out += ":" + std::to_string(f.len);
+            st.pop_back();
+            continue;
+        }
+        if (f.stage == 0) { out += "("; f.stage = 1; st.push_back({kids[node].first.node, 0, kids[node].first.len, true}); }
+        else if (f.stage == 1) { out += ","; f.stage = 2; st.push_back({kids[node].second.node, 0, kids[node].second.len, true}); }
+        else {
+            out += ")";
+            if (f.has_len) out += ":" + std::to_string(f.len);
+            st.pop_back();
+        }
+    }
+    return out + ";";
+}
+
+void write_tree_outputs(const vector<Genome> &g, const vector<tc_edge> &mst, bool by_file, const Options &o)
+{
+    auto open_or_die = [](const string &path) { FILE *fp = fopen(path.c_str(), "w"); if (!fp) die("cannot write file: " + path); return fp; };
+    string tree;
+    if (o.newick || o.phylip || o.nexus) tree = newick_of(g, mst, by_file);
+    if (o.newick) {
+        const string path = o.output + ".newick.tree";
+        FILE *fp = open_or_die(path); fprintf(fp, "%s\n", tree.c_str()); fclose(fp);
+        cerr << "-----write the newick tree into: " << path << endl;
+    }
+    if (o.phylip) {
+        const string path = o.output + ".phylip.tree";
+        FILE *fp = open_or_die(path); fprintf(fp, "1\n%s\n", tree.c_str()); fclose(fp);
+        cerr << "-----write the PHYLIP tree into: " << path << endl;
+    }
+    if (o.nexus) {
+        const string path = o.output + ".nexus.tree";
+        FILE *fp = open_or_die(path);
+        fprintf(fp, "#NEXUS\nBEGIN TAXA;\n  DIMENSIONS NTAX=%zu;\n  TAXLABELS", g.size());
+        for (const Genome &x : g) {
+            string lab = by_file ? x.file_name : x.name;
+            for (size_t pos = 0; (pos = lab.find('\'', pos)) != string::npos; pos += 2) lab.insert(pos, "'");
+            fprintf(fp, " '%s'", lab.c_str());
+        }
+        fprintf(fp, ";\nEND;\nBEGIN TREES;\n  TREE tree_1 = [&R] %s\nEND;\n", tree.c_str());
+        fclose(fp);
+        cerr << "-----write the NEXUS tree into: " << path << endl;
+    }
+    if (o.linkage) {
+        const string path = o.output + ".linkage.txt";
+        FILE *fp = open_or_die(path);
+        const int n = (int)g.size();
+        if (n > 1) {
+            MergeForest uf(n);
+            vector<int> cid(n), csize(2 * n - 1, 1);
+            for (int i = 0; i < n; i++) cid[i] = i;
+            int next = n;
+            for (const tc_edge &e : edges_by_distance(mst)) {
+                const int ru = uf.find(e.pre), rv = uf.find(e.suf);
+                if (ru == rv) continue;
+                const int a = cid[ru], b = cid[rv];
+                csize[next] = csize[a] + csize[b];
+                fprintf(fp, "%d\t%d\t%.6f\t%d\n", a, b, e.dist, csize[next]);
+                cid[uf.unite(ru, rv)] = next++;
+            }
+        }
+        fclose(fp);
+        cerr << "-----write the linkage matrix into: " << path << endl;
+    }
+}
+
 void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_file, bool save, const string &folder)
 {
     if (g.empty()) die("no sketches to cluster");
@@ -807,6 +932,7 @@ void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_fi
     double t3 = now_s();
     cerr << "========time of generateMST is: " << t3 - t2 << "========" << endl;
     if (save) save_mst(g, mst, folder, by_file, o.fast);
+    write_tree_outputs(g, mst, by_file, o);
     vector<vector<int>> cluster = clusters_from_forest(mst, o.threshold, (int)g.size());
     print_result(cluster, g, by_file, o.output, o.threshold);
     cerr << "-----write the cluster result into: " << o.output << endl;
@@ -863,7 +989,8 @@ void usage(const char *prog)
 #ifndef GREEDY_CLUST
             " | --premsted DIR"
 #endif
-            ") [--fast [--drlevel N]] [--dense] [--device N]\n", prog);
+            ") [--fast [--drlevel N]] [--dense]\n"
+            "          [--newick-tree] [--phylip-tree] [--nexus-tree] [--linkage-matrix] [--device N]\n", prog);
 }
 
 }  // namespace
@@ -892,6 +1019,10 @@ int main(int argc, char **argv)
 #endif
         else if (f == "--fast") o.fast = true;
         else if (f == "--dense") o.dense = true;
+        else if (f == "--newick-tree") o.newick = true;
+        else if (f == "--phylip-tree") o.phylip = true;
+        else if (f == "--nexus-tree") o.nexus = true;
+        else if (f == "--linkage-matrix") o.linkage = true;
         else if (f == "--drlevel") o.drlevel = atoi(need("--drlevel"));
         else if (f == "--device") o.device = atoi(need("--device"));
         else if (f == "-h" || f == "--help") { usage(argv[0]); return 0; }
@@ -907,8 +1038,10 @@ int main(int argc, char **argv)
     if (o.premsted) {                       // clust_from_mst: host only, no GPU needed
         vector<Genome> g; vector<tc_edge> mst;
         bool by_file = load_mst(g, mst, o.folder, o.fast);
+        write_tree_outputs(g, mst, by_file, o);
         vector<vector<int>> cluster = clusters_from_forest(mst, o.threshold, (int)g.size());
-        print_result(cluster, g, by_file, o.output, o.threshold);
+        // clust_from_mst prints without the threshold header (sub_command.cpp:1898), clust_from_mst_fast with it (:1790)
+        print_result(cluster, g, by_file, o.output, o.fast ? o.threshold : -1.0);
         cerr << "-----write the cluster result into: " << o.output << endl;
         cerr << "-----the cluster number of: " << o.output << " is: " << cluster.size() << endl;
         return 0;

@@ -45,3 +45,22 @@ def test_no_silent_cpu_fallback(tc):
         pytest.skip("GPU present")
     with pytest.raises(tc.TclustError):
         tc.Context(0)
+
+
+def test_premsted_tree_outputs_match_reference_golden(tmp_path):
+    """clust-mst --premsted needs no GPU (host-only consumers of the saved tree): cluster file, Newick /
+    PHYLIP / NEXUS trees and the linkage matrix are byte-identical to the reference's own run on the same folder
+    (tests/golden/trees = `oracle/_ref/clust-mst -t 1 --premsted tests/golden/mst_list -d 0.05 -o mst.txt
+    --newick-tree --phylip-tree --nexus-tree --linkage-matrix`)."""
+    import subprocess
+    host = os.path.join(ROOT, "rabbittclust_b200", "host")
+    from rabbittclust_b200 import build
+    build.build()
+    subprocess.check_call(["make", "-s", "-C", host])
+    gold = os.path.join(ROOT, "tests", "golden")
+    r = subprocess.run([os.path.join(host, "bin", "clust-mst"), "--premsted", os.path.join(gold, "mst_list"), "-d", "0.05", "-o",
+                        "mst.txt", "--newick-tree", "--phylip-tree", "--nexus-tree", "--linkage-matrix"], cwd=tmp_path,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-1000:]
+    for suffix in ("", ".newick.tree", ".phylip.tree", ".nexus.tree", ".linkage.txt"):
+        assert open(os.path.join(gold, "trees", "mst.txt" + suffix)).read() == open(tmp_path / ("mst.txt" + suffix)).read(), suffix

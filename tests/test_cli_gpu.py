@@ -108,8 +108,14 @@ def test_clust_mst_matches_reference(genomes, tmp_path, mode, extra):
     # --presketched and --premsted on the folder the reference wrote
     _run(os.path.join(OURS, "clust-mst"), ["--presketched", rf, "-d", "0.05", "-o", "pre.txt"], str(tmp_path / "ours"))
     assert _partition(str(tmp_path / "ours" / "pre.txt")) == _partition(ref_out)
-    _run(os.path.join(OURS, "clust-mst"), ["--premsted", rf, "-d", "0.05", "-o", "mst.txt"], str(tmp_path / "ours"))
-    assert open(str(tmp_path / "ours" / "mst.txt")).read() == open(ref_out).read()   # same tree -> same bytes
+    # --premsted on the reference's tree, with every tree/linkage output: same tree -> same bytes as the reference's
+    # own --premsted run (which prints no threshold header, sub_command.cpp:1898)
+    tree_flags = ["--newick-tree", "--phylip-tree", "--nexus-tree", "--linkage-matrix"]
+    _run(os.path.join(REF, "clust-mst"), ["-t", "1", "--premsted", rf, "-d", "0.05", "-o", "mst.txt"] + tree_flags, str(tmp_path / "ref"))
+    _run(os.path.join(OURS, "clust-mst"), ["--premsted", rf, "-d", "0.05", "-o", "mst.txt"] + tree_flags, str(tmp_path / "ours"))
+    for suffix in ("", ".newick.tree", ".phylip.tree", ".nexus.tree", ".linkage.txt"):
+        assert open(str(tmp_path / "ours" / ("mst.txt" + suffix))).read() == open(str(tmp_path / "ref" / ("mst.txt" + suffix))).read(), suffix
+    assert _partition(str(tmp_path / "ours" / "mst.txt")) == _partition(ref_out)
 
 
 @pytest.mark.parametrize("mode", ["list", "single"])

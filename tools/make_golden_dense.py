@@ -2,7 +2,8 @@
 """Golden vectors of the --dense path from the UNMODIFIED reference (oracle/_ref/clust-mst --dense -t 1):
 tests/golden/dense/{mash,contain}/ = hash.sketch, info.sketch, edge.mst, mst.ani, mst.dense, clusters.txt,
 clusters.txt.removeNoise of a list-mode run on tests/golden/mst_genomes, and presk_{mash,contain}.removeNoise = the
-noise-removed cluster files of --presketched runs on tests/golden/presketched (the containment one removes 3 genomes).
+noise-removed cluster files of --presketched runs on tests/golden/presketched (the containment one removes 3 genomes);
+tests/golden/trees/ = cluster file, Newick/PHYLIP/NEXUS trees and linkage matrix of `--premsted tests/golden/mst_list`.
 """
 import glob
 import os
@@ -35,7 +36,17 @@ def main():
             subprocess.run([REF, "--dense", "-t", "1", "--presketched", "p", "-d", "0.05", "-o", "c.txt"], cwd=tmp, check=True,
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             shutil.copy(os.path.join(tmp, "c.txt.removeNoise"), os.path.join(DST, "presk_%s.removeNoise" % tag))
-    subprocess.call(["du", "-sh", DST])
+    # tree / linkage outputs of --premsted on the committed MST folder (tests/golden/trees)
+    trees = os.path.join(ROOT, "tests", "golden", "trees")
+    shutil.rmtree(trees, ignore_errors=True)
+    os.makedirs(trees)
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.run([REF, "-t", "1", "--premsted", os.path.join(ROOT, "tests", "golden", "mst_list"), "-d", "0.05", "-o", "mst.txt",
+                        "--newick-tree", "--phylip-tree", "--nexus-tree", "--linkage-matrix"], cwd=tmp, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for suffix in ("", ".newick.tree", ".phylip.tree", ".nexus.tree", ".linkage.txt"):
+            shutil.copy(os.path.join(tmp, "mst.txt" + suffix), trees)
+    subprocess.call(["du", "-sh", DST, trees])
 
 
 if __name__ == "__main__":
