@@ -134,6 +134,10 @@ int tc_pair_common_b(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_
  */
 int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts,
                      uint64_t *n_pairs, uint64_t *n_edges);
+/* the append form (start_index of compute_minhash_mst, src/MST.cpp:1375-1383): only rows i >= start_index, i.e. the
+ * pairs (new genome, any earlier genome) */
+int tc_allpairs_pass_from(tc_ctx *ctx, int radio, uint32_t start_index, uint32_t part, uint32_t nparts,
+                          uint64_t *n_pairs, uint64_t *n_edges);
 /* the same pass with semantic-B counts (the all-pairs loop of modifyMST, src/MST.cpp:851-868): edges are the
  * pairs with common_B >= 1, no size-ratio filter; the remaining pairs have distance exactly 1. */
 int tc_allpairs_pass_b(tc_ctx *ctx, uint32_t sketch_size, uint32_t part, uint32_t nparts,
@@ -171,6 +175,14 @@ int tc_boruvka_phase2(tc_ctx *ctx, int containment, const uint64_t *best_key_dev
  */
 int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double threshold,
            tc_edge *out, uint64_t *n_out);
+
+/*
+ * Incremental MST = append_clust_mst (src/sub_command.cpp:1578-1706): the uploaded set is old genomes [0, start_index)
+ * followed by new ones; pre_mst is the saved MST of the old genomes (edge.mst).  Only the pairs (new, earlier) are
+ * evaluated on the device; the result is the MST of old-MST + new candidate edges, sorted by (dist, i, j).
+ */
+int tc_mst_append(tc_ctx *ctx, int kmer_size, int containment, double threshold, uint32_t start_index,
+                  const tc_edge *pre_mst, uint64_t n_pre, tc_edge *out, uint64_t *n_out);
 
 /*
  * --dense epilogue of compute_minhash_mst / compute_kssd_mst (src/MST.cpp:1517-1530, 1702-1712) over the candidate

@@ -23,7 +23,7 @@ SYMBOLS = [
     "tc_sketches_upload", "tc_sketches_upload_dev", "tc_pair_common", "tc_allpairs_pass",
     "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_mst",
     "tc_greedy_scan", "tc_greedy_cluster",
-    "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce", "tc_greedy_cluster_kssd", "tc_dense_ani",
+    "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce", "tc_greedy_cluster_kssd", "tc_dense_ani", "tc_allpairs_pass_from", "tc_mst_append",
     "tc_jaccard_b", "tc_distance_b", "tc_contain_distance",
     "tc_mash_dist", "tc_aaf_dist", "tc_dist_from_key", "tc_radio", "tc_greedy_common_min", "tc_greedy_dist",
 ]
@@ -83,6 +83,8 @@ def lib():
     L.tc_mst_bruteforce.argtypes = [vp, C.c_int, C.c_uint32, C.c_int, vp, u64p]
     L.tc_greedy_cluster_bruteforce.argtypes = [vp, C.c_int, C.c_uint32, C.c_int, C.c_double, i32p, u32p]
     L.tc_greedy_cluster_kssd.argtypes = [vp, C.c_int, C.c_double, i32p, u32p]
+    L.tc_allpairs_pass_from.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u64p]
+    L.tc_mst_append.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_uint32, vp, C.c_uint64, vp, u64p]
     L.tc_dense_ani.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, u64p]
     L.tc_jaccard_b.argtypes = [C.c_int] * 4
     L.tc_jaccard_b.restype = C.c_double
@@ -238,6 +240,20 @@ class Context:
         _chk(lib().tc_greedy_cluster_bruteforce(self._h, k, sketch_size, int(containment), threshold,
                                                 _p(rep, C.c_int32), C.byref(nc)))
         return int(nc.value), rep[:self.n].copy()
+
+    def allpairs_pass_from(self, radio, start_index, part=0, nparts=1):
+        npairs, nedges = C.c_uint64(0), C.c_uint64(0)
+        _chk(lib().tc_allpairs_pass_from(self._h, radio, start_index, part, nparts, C.byref(npairs), C.byref(nedges)))
+        return int(npairs.value), int(nedges.value)
+
+    def mst_append(self, k, threshold, start_index, pre_mst, containment=False):
+        """append_clust_mst: MST of (saved MST of the first start_index genomes) + (new genomes vs everything)."""
+        pre = np.ascontiguousarray(pre_mst, EDGE_DTYPE)
+        out = np.zeros(max(self.n, 1), EDGE_DTYPE)
+        m = C.c_uint64(0)
+        _chk(lib().tc_mst_append(self._h, k, int(containment), threshold, start_index, pre.ctypes.data, len(pre),
+                                 out.ctypes.data, C.byref(m)))
+        return out[:int(m.value)].copy()
 
     def dense_ani(self, k, containment=False, span=100):
         """--dense epilogue over the candidate pairs of the last pass: (dense[span, n] cumulative, ani[101])."""

@@ -54,6 +54,7 @@ struct KHArgs {
     int mode;
     uint32_t *out; uint32_t i0, i1, j0, j1;
     tc_pair *edges; unsigned long long edge_cap; int radio;
+    uint32_t row_min;               // edge mode: only rows i >= row_min (the start_index of the append flows)
 };
 
 // presence filter: word = top (KH_FBITS-5) bits of h = x * golden, the two bit positions = low 10 bits of h
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                             a.out[(size_t)(i - a.i0) * (a.j1 - a.j0) + (j - a.j0)] = cnt;
                     } else {
                         bool keep = false;
-                        if (i < a.n && j < i && cnt >= 1u) {
+                        if (i < a.n && i >= a.row_min && j < i && cnt >= 1u) {
                             const uint32_t s0 = s_len[lane], s1 = clen;
                             const uint32_t mn = min(s0, s1), mx = max(s0, s1);
                             // reference: skip if max_size > radio * min_size (int arithmetic), MST.cpp:1481-1487
@@ -370,22 +371,22 @@ int tc_launch_join_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, ui
     return kh_launch(ctx, a, units);
 }
 
-int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts)
+int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index)
 {
-    // pairs (i, j < i): row block rb needs the columns [0, rb*32+31); units segment-major so that all CTAs
-    // stream the same column segment at the same time (L2 reuse)
+    // pairs (i >= start_index, j < i): row block rb needs the columns [0, rb*32+31); units segment-major so that
+    // all CTAs stream the same column segment at the same time (L2 reuse)
     const uint32_t n = ctx->n, nrb = (n + 31) / 32;
-    if (ctx->kh_edge_units_n != n) {
+    if (ctx->kh_edge_units_n != n || ctx->kh_edge_units_start != start_index) {
         ctx->kh_edge_units.clear();
         for (uint32_t c0 = 0; c0 < n; c0 += KH_CSEG)
-            for (uint32_t rb = c0 / 32; rb < nrb; rb++) {
+            for (uint32_t rb = std::max(c0 / 32, start_index / 32); rb < nrb; rb++) {
                 const uint32_t c1 = std::min<uint32_t>(std::min(n, c0 + KH_CSEG), rb * 32 + 31);
                 if (c1 > c0) ctx->kh_edge_units.push_back(tc_kh_unit{rb, c0, c1});
             }
-        ctx->kh_edge_units_n = n;
+        ctx->kh_edge_units_n = n; ctx->kh_edge_units_start = start_index;
     }
     KHArgs a{};
-    a.mode = KH_MODE_EDGES; a.part = part; a.nparts = nparts ? nparts : 1;
+    a.mode = KH_MODE_EDGES; a.part = part; a.nparts = nparts ? nparts : 1; a.row_min = start_index;
     a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
     return kh_launch(ctx, a, ctx->kh_edge_units);
 }

@@ -73,7 +73,7 @@ struct tc_ctx {
     tc_kh_unit *d_kh_units = nullptr;
     size_t kh_units_cap = 0;
     std::vector<tc_kh_unit> kh_edge_units;
-    uint32_t kh_edge_units_n = 0;
+    uint32_t kh_edge_units_n = 0, kh_edge_units_start = 0;
 
     // KSSD shuffled_dim table (K2), resident once uploaded
     int32_t *d_kssd_dim = nullptr;
@@ -106,7 +106,7 @@ int tc_launch_tiles_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, in
 // hash-join pass (k3h_join.cu)
 int tc_kh_prepare(tc_ctx *ctx);
 int tc_launch_join_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
-int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts);
+int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index = 0);
 // representative table (k5_greedy.cu)
 void tc_rep_table_free(tc_ctx *ctx);
 void tc_rep_table_reset(tc_ctx *ctx);

@@ -287,7 +287,7 @@ static int ensure_edges(tc_ctx *ctx)
 }
 
 static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32_t part, uint32_t nparts,
-                              uint64_t *n_pairs, uint64_t *n_edges)
+                              uint64_t *n_pairs, uint64_t *n_edges, uint32_t start_index = 0)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0, "tc_allpairs_pass: no sketches uploaded");
@@ -299,9 +299,11 @@ static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32
     // TCLUST_PASS_IMPL=merge selects the first-generation tiled merge kernel (k3_tile.cu)
     const char *impl = getenv("TCLUST_PASS_IMPL");
     // semantic B needs the ordered merge (the stop rule depends on the union order): merge kernel only
-    const bool use_merge = semb_size > 0 || (impl && !strcmp(impl, "merge"));
+    const bool use_merge = (semb_size > 0 || (impl && !strcmp(impl, "merge"))) && start_index == 0;
+    TC_CHECK(!(semb_size > 0 && start_index > 0), "tc_allpairs_pass: start_index is not supported for the semantic-B pass");
+    TC_CHECK(start_index <= ctx->n, "tc_allpairs_pass: start_index %u > n %u", start_index, ctx->n);
     ctx->edges_semb_size = semb_size;
-    if (use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts, semb_size) : tc_launch_join_edges(ctx, radio, part, nparts)) return 1;
+    if (use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts, semb_size) : tc_launch_join_edges(ctx, radio, part, nparts, start_index)) return 1;
     unsigned long long cnt[2];
     TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -311,7 +313,7 @@ static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32
     ctx->n_edges = cnt[0];
     if (n_edges) *n_edges = cnt[0];
     if (n_pairs) {
-        if (nparts == 1) *n_pairs = (uint64_t)ctx->n * (ctx->n - 1) / 2;
+        if (nparts == 1) *n_pairs = (uint64_t)ctx->n * (ctx->n - 1) / 2 - (uint64_t)start_index * (start_index ? start_index - 1 : 0) / 2;
         else if (use_merge) {
             // pairs j<i inside the tiles owned by this part
             const uint64_t G = ctx->ngroups;
@@ -329,7 +331,7 @@ static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32
             uint64_t p = 0;
             for (size_t u = part; u < ctx->kh_edge_units.size(); u += nparts) {
                 const tc_kh_unit &un = ctx->kh_edge_units[u];
-                for (uint64_t i = (uint64_t)un.rb * 32; i < std::min<uint64_t>(ctx->n, (uint64_t)un.rb * 32 + 32); i++) {
+                for (uint64_t i = std::max<uint64_t>((uint64_t)un.rb * 32, start_index); i < std::min<uint64_t>(ctx->n, (uint64_t)un.rb * 32 + 32); i++) {
                     const uint64_t hi = std::min<uint64_t>(un.c1, i);
                     if (hi > un.c0) p += hi - un.c0;
                 }
@@ -344,6 +346,12 @@ extern "C" int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t 
                                 uint64_t *n_edges)
 {
     return allpairs_pass_impl(ctx, radio, 0, part, nparts, n_pairs, n_edges);
+}
+
+extern "C" int tc_allpairs_pass_from(tc_ctx *ctx, int radio, uint32_t start_index, uint32_t part, uint32_t nparts,
+                                     uint64_t *n_pairs, uint64_t *n_edges)
+{
+    return allpairs_pass_impl(ctx, radio, 0, part, nparts, n_pairs, n_edges, start_index);
 }
 
 extern "C" int tc_allpairs_pass_b(tc_ctx *ctx, uint32_t sketch_size, uint32_t part, uint32_t nparts,
@@ -542,13 +550,14 @@ struct HostUF {
 // mode = distance mode of the Boruvka keys; complete = add weight-1 edges between the components that share no
 // hash (the brute-force reference builds the MST of the complete graph)
 static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t semb_size, bool complete,
-                    tc_edge *out, uint64_t *n_out)
+                    tc_edge *out, uint64_t *n_out, uint32_t start_index = 0, const tc_edge *pre_mst = nullptr,
+                    uint64_t n_pre = 0)
 {
     const int containment = mode;
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0, "tc_mst: no sketches uploaded");
     const uint32_t n = ctx->n;
-    if (allpairs_pass_impl(ctx, radio, semb_size, 0, 1, nullptr, nullptr)) return 1;
+    if (allpairs_pass_impl(ctx, radio, semb_size, 0, 1, nullptr, nullptr, start_index)) return 1;
     uint64_t *d_key = nullptr, *d_edge = nullptr;
     TC_CUDA(cudaMalloc(&d_key, (size_t)n * 8));
     TC_CUDA(cudaMalloc(&d_edge, (size_t)n * 8));
@@ -594,11 +603,28 @@ static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t se
             mst.push_back(tc_edge{(int32_t)v, first_v, 1.0});
         }
     }
-    std::sort(mst.begin(), mst.end(), [](const tc_edge &x, const tc_edge &y) {
+    auto by_weight = [](const tc_edge &x, const tc_edge &y) {
         if (x.dist != y.dist) return x.dist < y.dist;
         if (x.pre != y.pre) return x.pre < y.pre;
         return x.suf < y.suf;
-    });
+    };
+    std::sort(mst.begin(), mst.end(), by_weight);
+    if (n_pre) {
+        // append: MST(old graph + new edges) = MST(old MST + forest of the new edges)  (sub_command.cpp:1700-1706)
+        std::vector<tc_edge> all(pre_mst, pre_mst + n_pre);
+        for (const tc_edge &e : all)
+            TC_CHECK(e.pre >= 0 && e.suf >= 0 && (uint32_t)e.pre < n && (uint32_t)e.suf < n, "tc_mst_append: pre-MST edge out of range");
+        all.insert(all.end(), mst.begin(), mst.end());
+        std::sort(all.begin(), all.end(), by_weight);
+        HostUF uf2(n);
+        mst.clear();
+        for (const tc_edge &e : all) {
+            const int32_t a = uf2.find(e.pre), b = uf2.find(e.suf);
+            if (a == b) continue;
+            uf2.p[a] = b;
+            mst.push_back(e);
+        }
+    }
     if (out) std::copy(mst.begin(), mst.end(), out);
     if (n_out) *n_out = mst.size();
     return 0;
@@ -608,6 +634,13 @@ extern "C" int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double thresh
 {
     TC_CHECK(containment == 0 || containment == 1, "tc_mst: containment must be 0 or 1");
     return mst_impl(ctx, kmer_size, containment, tc_radio(threshold, kmer_size), 0, false, out, n_out);
+}
+
+extern "C" int tc_mst_append(tc_ctx *ctx, int kmer_size, int containment, double threshold, uint32_t start_index,
+                             const tc_edge *pre_mst, uint64_t n_pre, tc_edge *out, uint64_t *n_out)
+{
+    TC_CHECK(containment == 0 || containment == 1, "tc_mst_append: containment must be 0 or 1");
+    return mst_impl(ctx, kmer_size, containment, tc_radio(threshold, kmer_size), 0, false, out, n_out, start_index, pre_mst, n_pre);
 }
 
 extern "C" int tc_mst_bruteforce(tc_ctx *ctx, int kmer_size, uint32_t sketch_size, int containment, tc_edge *out,

@@ -21,7 +21,9 @@
 // next batch is being parsed.
 //   --dense                   src/MST.cpp:1517-1530,1702-1712 (tc_dense_ani), src/sub_command.cpp:3070-3100 (noise pass)
 //   tree / linkage output     src/MST.cpp:1088-1147,1235-1284, src/MST_IO.cpp:263-375
-// Out of scope: --append/--db/--save-rep, --auto-threshold/--stability analytics, dbscan/leiden,
+//   --append (classic)        src/sub_command.cpp:22-96 (greedy: brute-force greedyCluster), :1578-1757 (mst: new-vs-all
+//                             pass + Kruskal over old MST + new forest)
+// Out of scope: --db/--save-rep state files, --auto-threshold/--stability analytics, dbscan/leiden,
 // --fast with a single multi-FASTA input (the reference's -i KSSD consumer is the
 // quirky variant).
 #include "../../include/tclust.h"
@@ -67,6 +69,7 @@ struct Options {
     int threads = (int)std::thread::hardware_concurrency();
     bool by_file = false, containment = false, jaccard = false, set_kmer = false, no_save = false, fast = false;
     bool has_output = false, has_input = false, presketched = false, premsted = false, has_threshold = false;
+    bool append = false;
     bool dense = false, newick = false, phylip = false, nexus = false, linkage = false;
     double threshold = 0.05;
     int kmer = 19, sketch_size = 1000, compress = 1000, drlevel = 3, device = 0;
@@ -989,7 +992,7 @@ void usage(const char *prog)
 #ifndef GREEDY_CLUST
             " | --premsted DIR"
 #endif
-            ") [--fast [--drlevel N]] [--dense]\n"
+            ") [--append FILE] [--fast [--drlevel N]] [--dense]\n"
             "          [--newick-tree] [--phylip-tree] [--nexus-tree] [--linkage-matrix] [--device N]\n", prog);
 }
 
@@ -1014,6 +1017,7 @@ int main(int argc, char **argv)
         else if (f == "-o" || f == "--output") { o.output = need("-o"); o.has_output = true; }
         else if (f == "-i" || f == "--input") { o.input = need("-i"); o.has_input = true; }
         else if (f == "--presketched") { o.folder = need("--presketched"); o.presketched = true; }
+        else if (f == "--append") { o.input = need("--append"); o.append = true; }
 #ifndef GREEDY_CLUST
         else if (f == "--premsted") { o.folder = need("--premsted"); o.premsted = true; }
 #endif
@@ -1035,7 +1039,7 @@ int main(int argc, char **argv)
     if (o.fast && (o.drlevel < 0 || o.drlevel > 8)) { cerr << "ERROR: invalid drlevel " << o.drlevel << ", should be in [0, 8]" << endl; return 1; }
 
 #ifndef GREEDY_CLUST
-    if (o.premsted) {                       // clust_from_mst: host only, no GPU needed
+    if (o.premsted && !o.append) {          // clust_from_mst: host only, no GPU needed
         vector<Genome> g; vector<tc_edge> mst;
         bool by_file = load_mst(g, mst, o.folder, o.fast);
         write_tree_outputs(g, mst, by_file, o);
@@ -1050,7 +1054,86 @@ int main(int argc, char **argv)
     tc_ctx *ctx = nullptr;
     tc_or_die(tc_ctx_create(o.device, &ctx), "tc_ctx_create");
     vector<Genome> g;
-    if (o.presketched) {                    // clust_from_sketches (sub_command.cpp:2647-2856)
+    if (o.append) {
+        // classic append (no saved cluster state): append_clust_mst (sub_command.cpp:1578-1757) and
+        // append_clust_greedy (:22-96).  The folder's sketch parameters are reused, tune_parameters is not called.
+        if (o.fast) die("--append with --fast is not part of this build (SURVEY.md 8f-4 covers the MinHash flows)");
+        if (o.dense) die("--append with --dense is not part of this build");
+#ifdef GREEDY_CLUST
+        if (!o.presketched) { cerr << "ERROR option --append, option --presketched needed" << endl; return 1; }
+#else
+        if (!o.presketched && !o.premsted) { cerr << "ERROR option --append, option --presketched or --premsted needed" << endl; return 1; }
+#endif
+        vector<Genome> pre;
+        const bool pre_by_file = load_sketches(pre, o.folder, o);
+        cerr << "-----use the same sketch parameters with pre-generated sketches" << endl;
+        cerr << "---the kmer size is: " << o.kmer << endl;
+        if (o.containment) cerr << "---use the AAF distance (variable-sketch-size), the sketch size is in proportion with 1/" << o.compress << endl;
+        else cerr << "---use the Mash distance (fixed-sketch-size), the sketch size is: " << o.sketch_size << endl;
+        cerr << "---the thread number is: " << o.threads << endl;
+        cerr << "---the threshold is: " << o.threshold << endl;
+        vector<Genome> add;
+        if (o.by_file) sketch_files(ctx, o, add); else sketch_sequences(ctx, o, add);
+        const uint32_t n_pre = (uint32_t)pre.size();
+        g = std::move(pre);
+        for (Genome &x : add) g.push_back(std::move(x));
+        const string folder = current_date_time();
+        const bool save = !o.no_save;
+#ifdef GREEDY_CLUST
+        if (pre_by_file != o.by_file) {
+            cerr << "ERROR: append_clust_greedy(), the input format of append genomes and pre-sketched genome is not same (single input genome vs. genome list)" << endl;
+            return 1;
+        }
+        for (size_t i = 0; i < g.size(); i++) g[i].id = i < n_pre ? g[i].id : (int)(i - n_pre);   // ids as loaded / as sketched
+        std::sort(g.begin(), g.end(), [](const Genome &a, const Genome &b) {                    // cmpGenomeSize / cmpSeqSize
+            if (a.total_len != b.total_len) return a.total_len > b.total_len;
+            return a.id < b.id;
+        });
+        if (save) {
+            if (system(("mkdir -p " + folder).c_str()) != 0) die("cannot create " + folder);
+            save_sketches(g, folder, o);
+        }
+        upload(ctx, g);
+        vector<int32_t> centre(g.size());
+        uint32_t nclust = 0;
+        tc_or_die(tc_greedy_cluster_bruteforce(ctx, o.kmer, (uint32_t)o.sketch_size, o.containment, o.threshold, centre.data(), &nclust),
+                  "greedy clustering");
+        vector<vector<int>> cluster;
+        vector<int> cid(g.size(), -1);
+        for (int j = 0; j < (int)g.size(); j++) {
+            if (centre[j] == j) { cid[j] = (int)cluster.size(); cluster.push_back({j}); }
+            else cluster[cid[centre[j]]].push_back(j);
+        }
+        print_result(cluster, g, o.by_file, o.output, -1.0);
+        cerr << "-----write the cluster result into: " << o.output << endl;
+        cerr << "-----the cluster number of " << o.output << " is: " << cluster.size() << endl;
+#else
+        if (pre_by_file != o.by_file) {
+            cerr << "Warning: append_clust_mst(), the input format of append genomes and pre-sketched genome is not same (single input genome vs. genome list)" << endl;
+            cerr << "the output cluster file may not have the genome file name" << endl;
+        }
+        vector<Genome> mst_info; vector<tc_edge> pre_mst;
+        load_mst(mst_info, pre_mst, o.folder, false);
+        if (mst_info.size() != n_pre) die("append_clust_mst(), info.mst and info.sketch of " + o.folder + " differ in size");
+        for (size_t i = 0; i < g.size(); i++) g[i].id = (int)i;
+        if (save) {
+            if (system(("mkdir -p " + folder).c_str()) != 0) die("cannot create " + folder);
+            save_sketches(g, folder, o);
+        }
+        upload(ctx, g);
+        vector<tc_edge> mst(g.size());
+        uint64_t m = 0;
+        tc_or_die(tc_mst_append(ctx, o.kmer, o.containment, o.threshold, n_pre, pre_mst.data(), pre_mst.size(), mst.data(), &m),
+                  "incremental MST generation");
+        mst.resize(m);
+        write_tree_outputs(g, mst, pre_by_file, o);
+        vector<vector<int>> cluster = clusters_from_forest(mst, o.threshold, (int)g.size());
+        print_result(cluster, g, pre_by_file, o.output, o.threshold);
+        cerr << "-----write the cluster result into: " << o.output << endl;
+        cerr << "-----the cluster number of: " << o.output << " is: " << cluster.size() << endl;
+        if (save) save_mst(g, mst, folder, o.by_file, false);
+#endif
+    } else if (o.presketched) {                    // clust_from_sketches (sub_command.cpp:2647-2856)
         double t0 = now_s();
         bool by_file;
         if (o.fast) { by_file = load_kssd_sketches(g, o.folder); o.kmer = 2 * g_kssd.half_k; }   // sub_command.cpp: kmer_size = half_k * 2

@@ -195,3 +195,57 @@ def test_clust_greedy_fast_matches_reference(genomes, tmp_path):
     _run(os.path.join(REF, "clust-greedy"), ["-t", "1", "--fast", "--presketched", rf, "-d", "0.02", "-o", "pre.txt"], str(tmp_path / "ref"))
     _run(os.path.join(OURS, "clust-greedy"), ["--fast", "--presketched", rf, "-d", "0.02", "-o", "pre.txt"], str(tmp_path / "ours"))
     assert open(str(tmp_path / "ref" / "pre.txt")).read() == open(str(tmp_path / "ours" / "pre.txt")).read()
+
+
+def _split_list(lst, tmp_path, n_first):
+    files = open(lst).read().split()
+    a, b = str(tmp_path / "first.txt"), str(tmp_path / "second.txt")
+    open(a, "w").write("\n".join(files[:n_first]) + "\n")
+    open(b, "w").write("\n".join(files[n_first:]) + "\n")
+    return a, b
+
+
+@pytest.mark.parametrize("extra", [["-s", "1000"], ["-c", "100"]])
+def test_clust_mst_append_matches_reference(genomes, tmp_path, extra):
+    """classic --append: the reference clusters the first 20 genomes, then both binaries append the
+    other 10 to that folder: new-vs-all pass + Kruskal over the old MST and the new forest."""
+    lst, _ = genomes
+    first, second = _split_list(lst, tmp_path, 20)
+    base, _ = _run(os.path.join(REF, "clust-mst"), ["-t", "1", "-l", "-i", first, "-k", "21", "-d", "0.05", "-o", "base.txt"] + extra,
+                   str(tmp_path / "base"))
+    args = ["-l", "--append", second, "--presketched", base, "-d", "0.05", "-o", "app.txt", "--linkage-matrix"]
+    rf, _ = _run(os.path.join(REF, "clust-mst"), ["-t", "1"] + args, str(tmp_path / "ref"))
+    of, _ = _run(os.path.join(OURS, "clust-mst"), args, str(tmp_path / "ours"))
+    for fn in ("hash.sketch", "info.sketch", "info.mst"):
+        assert _same_bytes(os.path.join(rf, fn), os.path.join(of, fn)), fn
+    a = sketch_io.read_edge_mst(os.path.join(rf, "edge.mst"))
+    b = sketch_io.read_edge_mst(os.path.join(of, "edge.mst"))
+    assert np.array_equal(np.sort(a["dist"]), np.sort(b["dist"]))
+    ref_out, our_out = str(tmp_path / "ref" / "app.txt"), str(tmp_path / "ours" / "app.txt")
+    assert open(ref_out).read().splitlines()[:3] == open(our_out).read().splitlines()[:3]
+    assert _partition(ref_out) == _partition(our_out)
+    # the appended result equals clustering everything at once
+    full, _ = _run(os.path.join(REF, "clust-mst"), ["-t", "1", "-l", "-i", lst, "-k", "21", "-d", "0.05", "-o", "full.txt"] + extra,
+                   str(tmp_path / "full"))
+    c = sketch_io.read_edge_mst(os.path.join(full, "edge.mst"))
+    assert np.array_equal(np.sort(b["dist"]), np.sort(c["dist"]))
+    # linkage matrices agree in their distance column (tie order inside equal weights is tree dependent)
+    la = [l.split("\t")[2] for l in open(ref_out + ".linkage.txt")]
+    lb = [l.split("\t")[2] for l in open(our_out + ".linkage.txt")]
+    assert la == lb
+
+
+@pytest.mark.parametrize("extra", [["-s", "1000"], ["-c", "100"]])
+def test_clust_greedy_append_matches_reference(genomes, tmp_path, extra):
+    """classic clust-greedy --append: concatenation sorted by genome length, brute-force greedyCluster with
+    MinHash::distance / containDistance (semantic B) -- byte-identical cluster file and sketch folder"""
+    lst, _ = genomes
+    first, second = _split_list(lst, tmp_path, 18)
+    base, _ = _run(os.path.join(REF, "clust-greedy"), ["-t", "1", "-l", "-i", first, "-k", "21", "-d", "0.05", "-o", "base.txt"] + extra,
+                   str(tmp_path / "base"))
+    args = ["-l", "--append", second, "--presketched", base, "-d", "0.05", "-o", "app.txt"]
+    rf, _ = _run(os.path.join(REF, "clust-greedy"), ["-t", "1"] + args, str(tmp_path / "ref"))
+    of, _ = _run(os.path.join(OURS, "clust-greedy"), args, str(tmp_path / "ours"))
+    for fn in ("hash.sketch", "info.sketch"):
+        assert _same_bytes(os.path.join(rf, fn), os.path.join(of, fn)), fn
+    assert open(str(tmp_path / "ref" / "app.txt")).read() == open(str(tmp_path / "ours" / "app.txt")).read()

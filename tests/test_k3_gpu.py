@@ -189,3 +189,35 @@ def test_full_size_pass_properties(ctx):
     ctx.allpairs_pass(4)
     e2 = ctx.edges()
     assert np.array_equal(np.sort(e, order=["i", "j"]), np.sort(e2, order=["i", "j"]))
+
+
+def test_pass_from_and_mst_append(ctx, oracle):
+    """start_index form of the dense pass (compute_minhash_mst with start_index, MST.cpp:1375-1383) and the incremental
+    MST: appending the last third to the MST of the first two thirds gives the weights of the MST of everything."""
+    from rabbittclust_b200 import radio
+    sk = synth.family_sketches(9, 11, s=400, seed=77, keep_lo=0.3)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(sk))
+    sk = [sk[i] for i in perm]
+    n, start = len(sk), 61                                   # not a multiple of 32
+    ctx.upload(sk)
+    npairs, nedges = ctx.allpairs_pass_from(radio(0.05, 21), start)
+    assert npairs == n * (n - 1) // 2 - start * (start - 1) // 2
+    e = ctx.edges()
+    want = oracle.common_matrix(sk)
+    got = np.zeros((n, n), np.uint32)
+    got[e["i"], e["j"]] = e["common"]
+    ref = np.tril(want, -1)
+    ref[:start] = 0
+    assert np.array_equal(got, ref)
+    full = oracle.mst(sk, 21, 0.05)
+    ctx.upload(sk[:start])
+    pre = ctx.mst(21, 0.05)
+    ctx.upload(sk)
+    app = ctx.mst_append(21, 0.05, start, pre)
+    assert np.array_equal(np.sort(app["dist"]), np.sort(full["dist"]))
+    _, la, _ = oracle.clusters_from_mst(app, n, 0.05)
+    _, lb, _ = oracle.clusters_from_mst(full, n, 0.05)
+    assert np.array_equal(la, lb)
+    # start_index = 0 is the ordinary MST, start_index = n keeps the old tree
+    assert np.array_equal(np.sort(ctx.mst_append(21, 0.05, 0, pre[:0])["dist"]), np.sort(full["dist"]))
