@@ -204,6 +204,11 @@ def run_pairs(args):
     per_fam = 100
     h, off = synth.family_sketches_fast(max(n // per_fam, 1), per_fam, 1000, seed=7)
     n = len(off) - 1
+    if args.order == "shuffled":
+        # same sketches in a random order: no two neighbouring sketches are related, so a row block of 32 sketches
+        # holds 32,000 distinct hashes (3 table partitions) instead of ~9,000 (1 partition) -- see DESIGN.md K3H
+        perm = np.random.default_rng(11).permutation(n)
+        h = np.ascontiguousarray(h.reshape(n, 1000)[perm].reshape(-1))
     k, thr = 21, 0.05
     radio = T.radio(thr, k)
     ctx = T.Context(local_rank)
@@ -342,6 +347,8 @@ def run_pairs(args):
             "config": {"workload": "clust-mst dense all-pairs pass on %d pre-sketched s=1000 k=21 sketches, "
                                    "1000-per-family model (BASELINE.json configs[2])" % n,
                        "n_sketches": n, "sketch_size": 1000, "pairs_per_step": pairs_per_step_all,
+                       "order": args.order + (" (generation order: the 100 members of a family are adjacent)"
+                                              if args.order == "family" else " (random permutation of the same sketches)"),
                        "candidate_edges": int(nedges), "parallelism": "tile-sharded x%d, sketches replicated" % world,
                        "l2": "input 0.4 GB of u32 ranks (+0.8 GB u64) per GPU > 126 MB L2"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -402,6 +409,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sketch", action="store_true", help="pairs workload: skip the sketch leg of the line")
     ap.add_argument("--no-semb", action="store_true", help="pairs workload: skip the semantic-B pass")
+    ap.add_argument("--order", default="family", choices=["family", "shuffled"],
+                    help="pairs workload: sketch order (family = as generated, SURVEY 8d config 3; shuffled = random)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -30,13 +30,15 @@ namespace {
 
 constexpr int KH_THREADS = 1024;
 constexpr uint32_t KH_SLOTS = 16384;          // table slots (key, mask), 128 KB
-constexpr uint32_t KH_KCAP = 8256;            // max elements of the row block per partition (32 x 1000 -> 4 partitions)
-constexpr uint32_t KH_FBITS = 18;             // presence filter: 2^18 bits = 32 KB, 2 bits per key in one word
+constexpr uint32_t KH_KCAP = 10752;           // max elements of the row block per partition (32 x 1000 -> 3 partitions, load 0.65)
+constexpr uint32_t KH_FBITS = 19;             // presence filter: 2^19 bits = 64 KB, 2 bits per key in one word
 constexpr uint32_t KH_FWORDS = (1u << KH_FBITS) / 32;
 constexpr uint32_t KH_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t KH_CSEG = 4096;            // columns per unit
 constexpr uint32_t KH_STATE = 33;             // words of state per column: 32 counts + position
 constexpr size_t KH_SMEM = (size_t)KH_SLOTS * 8 + (size_t)KH_FWORDS * 4;
+constexpr uint32_t KH_SORT_CAP = 32768;       // row blocks up to this many elements get distinct-count partitions
+constexpr uint32_t KH_DREC = 7;               // per row block: distinct count + pivot candidates for P = 2, 3, 4
 
 enum { KH_MODE_MATRIX = 0, KH_MODE_EDGES = 1 };
 
@@ -59,7 +61,8 @@ struct KHArgs {
 
 // presence filter: word = top (KH_FBITS-5) bits of h = x * golden, the two bit positions = low 10 bits of h
 __device__ __forceinline__ uint32_t kh_fword(uint32_t h) { return h >> (32 - (KH_FBITS - 5)); }
-__device__ __forceinline__ uint32_t kh_fmask(uint32_t h) { return (1u << (h & 31)) | (1u << ((h >> 5) & 31)); }
+// two bit positions from the low 10 bits of h; the funnel shift takes its amount mod 32 (one SHF.L.W each)
+__device__ __forceinline__ uint32_t kh_fmask(uint32_t h) { return __funnelshift_l(0u, 1u, h) | __funnelshift_l(0u, 1u, h >> 5); }
 __device__ __forceinline__ uint32_t kh_slot(uint32_t x) { return (x * 0x85EBCA6Bu) >> 18; }   // 14 bits
 __device__ __forceinline__ uint32_t kh_lds(uint32_t addr)
 {
@@ -87,10 +90,11 @@ __device__ __forceinline__ uint32_t kh_lower_bound(const uint32_t *a, uint32_t f
 
 // ---- pivots: one warp per row block; interior pivot q = smallest v with #(elements < v) >= q*total/P
 __global__ void k3h_pivot_kernel(const uint32_t *ranks, const unsigned long long *off, const uint32_t *size, uint32_t n,
-                                 const uint32_t *pivoff, uint32_t nrb, uint32_t *pivots)
+                                 const uint32_t *pivoff, uint32_t nrb, const uint32_t *distinct, uint32_t *pivots)
 {
     const uint32_t rb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (rb >= nrb) return;
+    if (distinct[rb * KH_DREC] != 0xFFFFFFFFu) return;      // pivots of this row block came from the sort kernel
     const uint32_t np = pivoff[rb + 1] - pivoff[rb];
     if (np == 0) return;
     const uint32_t id = rb * 32 + lane;
@@ -108,6 +112,79 @@ __global__ void k3h_pivot_kernel(const uint32_t *ranks, const unsigned long long
             if (c >= target) hi = mid; else lo = mid + 1;
         }
         if (lane == 0) pivots[pivoff[rb] + q - 1] = lo;
+    }
+}
+
+// ---- distinct-aware partitions.  The table holds DISTINCT ranks, and the 32 sketches of a row block often share
+// most of theirs (neighbouring genomes of one species): 32 x 1000 elements are then ~9000 distinct keys and fit one
+// partition instead of three.  One CTA sorts the row block's elements in shared memory (bitonic, <= 32768 u32),
+// counts the distinct ones and emits, for P = 2, 3, 4, the keys at distinct rank q*D/P as pivot candidates.
+// out[rb*7] = D (0xFFFFFFFF: block too large, the multiset-quantile kernel above takes over), out[rb*7+1..6] =
+// candidates for (P,q) = (2,1) (3,1) (3,2) (4,1) (4,2) (4,3).
+__global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint32_t *ranks, const unsigned long long *off,
+                                                                      const uint32_t *size, uint32_t n, uint32_t *out)
+{
+    extern __shared__ __align__(16) uint8_t kh_smem[];
+    uint32_t *buf = reinterpret_cast<uint32_t *>(kh_smem);
+    __shared__ uint32_t s_pos[33], s_warp[32], s_d;
+    const uint32_t rb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (uint32_t l = 0; l < 32; l++) { s_pos[l] = acc; const uint32_t id = rb * 32 + l; acc += id < n ? size[id] : 0u; if (acc > KH_SORT_CAP) { acc = KH_SORT_CAP + 1; for (uint32_t m = l + 1; m <= 32; m++) s_pos[m] = acc; break; } }
+        s_pos[32] = acc;
+    }
+    __syncthreads();
+    const uint32_t total = s_pos[32];
+    if (total > KH_SORT_CAP) { if (tid == 0) out[rb * KH_DREC] = 0xFFFFFFFFu; return; }
+    uint32_t npad = 1024;
+    while (npad < total) npad <<= 1;
+    {   // warp w copies row w
+        const uint32_t id = rb * 32 + warp;
+        const uint32_t len = id < n ? size[id] : 0u;
+        const uint32_t *row = ranks + (id < n ? off[id] : 0ULL);
+        for (uint32_t e = lane; e < len; e += 32) buf[s_pos[warp] + e] = __ldg(row + e);
+        for (uint32_t e = total + tid; e < npad; e += KH_THREADS) buf[e] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    for (uint32_t sz = 2; sz <= npad; sz <<= 1)
+        for (uint32_t stride = sz >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = tid; t < (npad >> 1); t += KH_THREADS) {
+                const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const uint32_t x = buf[lo], y = buf[hi];
+                if ((x > y) == ((lo & sz) == 0)) { buf[lo] = y; buf[hi] = x; }
+            }
+            __syncthreads();
+        }
+    // distinct count: thread t owns the chunk [t*c, (t+1)*c)
+    const uint32_t c = npad / KH_THREADS, b0 = tid * c;
+    uint32_t mine = 0;
+    for (uint32_t i = b0; i < b0 + c; i++) mine += (i < total && (i == 0 || buf[i] != buf[i - 1])) ? 1u : 0u;
+    uint32_t incl = mine;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = s_warp[lane];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, v, o); if ((int)lane >= o) v += u; }
+        s_warp[lane] = v;
+        if (lane == 31) s_d = v;
+    }
+    __syncthreads();
+    const uint32_t D = s_d;
+    uint32_t before = incl - mine + (warp ? s_warp[warp - 1] : 0u);       // distinct keys before this chunk
+    if (tid == 0) out[rb * KH_DREC] = D;
+    // wanted distinct ranks
+    uint32_t want[6];
+    want[0] = (uint32_t)((unsigned long long)D * 1 / 2);
+    want[1] = (uint32_t)((unsigned long long)D * 1 / 3); want[2] = (uint32_t)((unsigned long long)D * 2 / 3);
+    want[3] = (uint32_t)((unsigned long long)D * 1 / 4); want[4] = (uint32_t)((unsigned long long)D * 2 / 4);
+    want[5] = (uint32_t)((unsigned long long)D * 3 / 4);
+    for (uint32_t i = b0; i < b0 + c; i++) {
+        if (i < total && (i == 0 || buf[i] != buf[i - 1])) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) if (before == want[q]) out[rb * KH_DREC + 1 + q] = buf[i];
+            before++;
+        }
     }
 }
 
@@ -153,7 +230,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                 uint4 *t4 = reinterpret_cast<uint4 *>(kh_smem);
                 const uint4 e = make_uint4(KH_EMPTY, 0u, KH_EMPTY, 0u);
                 for (uint32_t i = tid; i < KH_SLOTS / 2; i += KH_THREADS) t4[i] = e;
-                for (uint32_t i = tid; i < KH_FWORDS; i += KH_THREADS) filter[i] = 0u;
+                for (uint32_t i = tid; i < KH_FWORDS; i += KH_THREADS) filter[i] = 0xFFFFFFFFu;   // stored inverted: 0 = present
                 if (tid < 32) {
                     const uint32_t *row = a.ranks + s_base[tid];
                     s_hi[tid] = (p + 1 == P) ? s_len[tid] : kh_lower_bound(row, s_lo[tid], s_len[tid], piv_hi);
@@ -168,7 +245,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                 for (uint32_t e = s_lo[warp] + lane; e < s_hi[warp]; e += 32) {
                     const uint32_t x = __ldg(row + e);
                     const uint32_t h = x * 0x9E3779B1u;
-                    atomicOr(&filter[kh_fword(h)], kh_fmask(h));
+                    atomicAnd(&filter[kh_fword(h)], ~kh_fmask(h));
                     uint32_t slot = kh_slot(x);
                     for (;;) {
                         const uint32_t old = atomicCAS(&table[slot].x, KH_EMPTY, x);
@@ -191,12 +268,20 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                 if (p > 0) { pos = st[32]; cnt = st[lane]; }
                 const uint32_t *pc = a.ranks + a.off[c] + pos + lane;   // this lane's element of the current step
                 uint32_t rem = clen - pos;                               // elements left from the step's start
-                uint32_t x[4], xn[4];
+                uint32_t xa[4], xb[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) x[k] = (lane + 32 * k < rem) ? __ldg(pc + 32 * k) : 0xFFFFFFFFu;
-                for (;;) {
+                for (int k = 0; k < 4; k++) xa[k] = (lane + 32 * k < rem) ? __ldg(pc + 32 * k) : 0xFFFFFFFFu;
+                // one step = the 128 elements in x; xn receives the next step's elements (loads issued before the
+                // probes).  Returns false when the partition ends inside this step.  Instantiated twice with the
+                // two register sets swapped, so the hand-over of xn to x costs no moves.
+                auto step = [&](uint32_t (&x)[4], uint32_t (&xn)[4]) -> bool {
+                    if (rem >= 256u) {                       // warp-uniform: the whole next step is in bounds
 #pragma unroll
-                    for (int k = 0; k < 4; k++) xn[k] = (lane + 128 + 32 * k < rem) ? __ldg(pc + 128 + 32 * k) : 0xFFFFFFFFu;
+                        for (int k = 0; k < 4; k++) xn[k] = __ldg(pc + 128 + 32 * k);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) xn[k] = (lane + 128 + 32 * k < rem) ? __ldg(pc + 128 + 32 * k) : 0xFFFFFFFFu;
+                    }
                     // presence filter (blocked Bloom, 2 bits in one word): 4 independent LDS per lane
                     uint32_t fw[4], fm[4];
 #pragma unroll
@@ -208,7 +293,9 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                     bool maybe = false;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        fw[k] = ((~fw[k] & fm[k]) == 0u) && x[k] < piv_hi;
+                        // no range test: an element >= piv_hi (or a tail sentinel) that slips through the filter
+                        // simply misses in the table, which only holds keys of this partition
+                        fw[k] = (fm[k] & fw[k]) == 0u;          // the filter words are stored inverted
                         maybe |= fw[k] != 0u;
                     }
                     uint32_t mask[4] = {0u, 0u, 0u, 0u};
@@ -241,8 +328,8 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                             } else {
 #pragma unroll
                                 for (int r = 0; r < 32; r++) {
-                                    const unsigned b = __ballot_sync(0xffffffffu, (mk >> r) & 1u);
-                                    if (lane == r) cnt += __popc(b);
+                                    const unsigned bb = __ballot_sync(0xffffffffu, (mk >> r) & 1u);
+                                    if (lane == r) cnt += __popc(bb);
                                 }
                             }
                         }
@@ -250,14 +337,24 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                     // sorted stream: the step is consumed completely iff its last element is in the partition
                     if (__shfl_sync(0xffffffffu, x[3], 31) < piv_hi) {
                         pos += 128; pc += 128; rem -= 128;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) x[k] = xn[k];
-                        continue;
+                        return true;
                     }
 #pragma unroll
                     for (int k = 0; k < 4; k++) pos += __popc(__ballot_sync(0xffffffffu, x[k] < piv_hi));
-                    break;
+                    return false;
+                };
+#ifdef KH_PINGPONG
+                for (;;) {
+                    if (!step(xa, xb)) break;
+                    if (!step(xb, xa)) break;
                 }
+#else
+                for (;;) {
+                    if (!step(xa, xb)) break;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) xa[k] = xb[k];
+                }
+#endif
                 if (p + 1 < P) {
                     st[lane] = cnt;
                     if (lane == 0) st[32] = pos;
@@ -308,25 +405,67 @@ int tc_kh_prepare(tc_ctx *ctx)
     cudaFree(ctx->d_kh_pivots); cudaFree(ctx->d_kh_pivoff);
     ctx->d_kh_pivots = nullptr; ctx->d_kh_pivoff = nullptr;
     const uint32_t nrb = (ctx->n + 31) / 32;
+    cudaStream_t st = ctx->stream;
+    // ---- distinct counts and pivot candidates of every row block
+    uint32_t *d_dist = nullptr;
+    TC_CUDA(cudaMalloc(&d_dist, (size_t)nrb * KH_DREC * 4));
+    TC_CUDA(cudaMemsetAsync(d_dist, 0, (size_t)nrb * KH_DREC * 4, st));
+    static bool attr_set = false;
+    if (!attr_set) {
+        TC_CUDA(cudaFuncSetAttribute(k3h_distinct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KH_SORT_CAP * 4)));
+        attr_set = true;
+    }
+    k3h_distinct_kernel<<<nrb, KH_THREADS, KH_SORT_CAP * 4, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
+                                                                 ctx->d_size, ctx->n, d_dist);
+    ctx->launches++;
+    std::vector<uint32_t> dist((size_t)nrb * KH_DREC);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dist.data(), d_dist, dist.size() * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(d_dist); tc_set_error("tc_kh_prepare: %s", cudaGetErrorString(e)); return 1; }
+    // ---- partitions: by distinct keys where known, else by the multiset total
     std::vector<uint32_t> pivoff(nrb + 1, 0);
+    bool any_fallback = false;
     for (uint32_t rb = 0; rb < nrb; rb++) {
-        uint64_t total = 0;
-        for (uint32_t l = 0; l < 32 && rb * 32 + l < ctx->n; l++) total += ctx->h_size[rb * 32 + l];
-        const uint32_t P = (uint32_t)std::max<uint64_t>(1, (total + (KH_KCAP - 64) - 1) / (KH_KCAP - 64));
+        uint64_t keys = dist[(size_t)rb * KH_DREC];
+        if (keys == 0xFFFFFFFFu) {
+            any_fallback = true;
+            keys = 0;
+            for (uint32_t l = 0; l < 32 && rb * 32 + l < ctx->n; l++) keys += ctx->h_size[rb * 32 + l];
+        }
+        const uint32_t P = (uint32_t)std::max<uint64_t>(1, (keys + (KH_KCAP - 64) - 1) / (KH_KCAP - 64));
         pivoff[rb + 1] = pivoff[rb] + (P - 1);
     }
-    TC_CUDA(cudaMalloc(&ctx->d_kh_pivoff, (size_t)(nrb + 1) * 4));
-    TC_CUDA(cudaMalloc(&ctx->d_kh_pivots, std::max<size_t>(pivoff[nrb], 1) * 4));
-    TC_CUDA(cudaMemcpyAsync(ctx->d_kh_pivoff, pivoff.data(), (size_t)(nrb + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (pivoff[nrb] > 0) {
-        const unsigned blocks = (unsigned)(((uint64_t)nrb * 32 + 255) / 256);
-        k3h_pivot_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
-                                                          ctx->d_size, ctx->n, ctx->d_kh_pivoff, nrb, ctx->d_kh_pivots);
-        ctx->launches++;
-        TC_CUDA(cudaGetLastError());
+    std::vector<uint32_t> piv(std::max<size_t>(pivoff[nrb], 1), 0u);
+    for (uint32_t rb = 0; rb < nrb; rb++) {
+        const uint32_t *d = &dist[(size_t)rb * KH_DREC];
+        const uint32_t P = pivoff[rb + 1] - pivoff[rb] + 1;
+        if (d[0] == 0xFFFFFFFFu || P == 1) continue;
+        // candidates: (2,1) (3,1) (3,2) (4,1) (4,2) (4,3)
+        const uint32_t first = P == 2 ? 1 : P == 3 ? 2 : 4;
+        for (uint32_t q = 0; q + 1 < P; q++) piv[pivoff[rb] + q] = d[first + q];
     }
-    TC_CUDA(cudaStreamSynchronize(ctx->stream));   // pivoff (host vector) must outlive the copy
-    return 0;
+    int rc = 1;
+    do {
+        if (cudaMalloc(&ctx->d_kh_pivoff, (size_t)(nrb + 1) * 4) != cudaSuccess ||
+            cudaMalloc(&ctx->d_kh_pivots, piv.size() * 4) != cudaSuccess) { tc_set_error("tc_kh_prepare: out of device memory"); break; }
+        if (cudaMemcpyAsync(ctx->d_kh_pivoff, pivoff.data(), (size_t)(nrb + 1) * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(ctx->d_kh_pivots, piv.data(), piv.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            tc_set_error("tc_kh_prepare: %s", cudaGetErrorString(cudaGetLastError())); break;
+        }
+        if (any_fallback && pivoff[nrb] > 0) {
+            const unsigned blocks = (unsigned)(((uint64_t)nrb * 32 + 255) / 256);
+            k3h_pivot_kernel<<<blocks, 256, 0, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off), ctx->d_size,
+                                                     ctx->n, ctx->d_kh_pivoff, nrb, d_dist, ctx->d_kh_pivots);
+            ctx->launches++;
+        }
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {   // host vectors outlive the copies
+            tc_set_error("tc_kh_prepare: %s", cudaGetErrorString(cudaGetLastError())); break;
+        }
+        rc = 0;
+    } while (0);
+    cudaFree(d_dist);
+    return rc;
 }
 
 static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &units)
