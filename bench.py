@@ -26,6 +26,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
 
 PAIR_BYTES = 16000.0   # algorithmic operand bytes per pair: 8*(|A|+|B|) at s=1000
 
@@ -287,8 +288,14 @@ def run_pairs(args):
     sync_all()
     t0 = time.time()
     d2h = 0
+    h2d = int(h.nbytes + off.nbytes)
     for _ in range(e2e_steps):
-        ctx.upload(hashes=hp, off=off)
+        if dist is None:
+            ctx.upload(hashes=hp, off=off)
+        else:
+            # every rank copies only its 1/world share from the host; the shares are all-gathered over NVLink
+            from rabbittclust_b200 import mst_dist
+            h2d = mst_dist.upload_sharded(ctx, h_pin, off, dist, torch.device("cuda", local_rank)) + int(off.nbytes)
         ctx.allpairs_pass(radio, rank, world)
         e = ctx.edges()
         d2h = e.nbytes
@@ -361,7 +368,7 @@ def run_pairs(args):
                                  "expected, `traffic` is the measured DRAM bytes, and the binding units are the issue "
                                  "slots / ALU pipe (DESIGN.md K3H)"},
             "e2e": {"value": (pairs_per_step_all) / (e2e_ms / 1e3), "unit": "pairs/s",
-                    "h2d_bytes_per_step": int(h.nbytes + off.nbytes) * world, "d2h_bytes_per_step": int(d2h) * world,
+                    "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
         }

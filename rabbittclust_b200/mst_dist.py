@@ -136,6 +136,44 @@ def boruvka(n, ops, dist_from_key, dist=None, device=None, max_rounds=64):
     return mst[np.lexsort((mst["suf"], mst["pre"], mst["dist"]))]
 
 
+def shard_bounds(total, rank, world, align=2):
+    """[lo, hi) of the hash array owned by `rank`: equal shares rounded to `align` elements, the last rank takes
+    the remainder.  Pure function (tests/test_dist_cpu.py)."""
+    per = (total // world) // align * align
+    lo = rank * per
+    hi = total if rank == world - 1 else lo + per
+    return lo, hi
+
+
+def upload_sharded(ctx, hashes_pinned, off, dist, device):
+    """Make the N sketches resident on EVERY rank while each rank moves only 1/world of the raw hashes over its own
+    PCIe link: H2D of the rank's share, all-gather of the shares over NVLink ("one ncclAllGather of
+    sketches so every GPU holds all N sketches for HP-2"), then tc_sketches_upload_dev (rank transform on the device).
+    hashes_pinned: torch uint8/int64 pinned host tensor viewing all hashes (only the own share is read).
+    Returns the bytes this rank copied from the host."""
+    import torch
+    import rabbittclust_b200 as T
+    world, rank = dist.get_world_size(), dist.get_rank()
+    h = hashes_pinned.view(torch.int64)
+    total = int(off[-1])
+    per = (total // world) // 2 * 2
+    tail = total - per * world                                   # remainder, replicated by every rank (tiny)
+    full = torch.empty(total + 1, dtype=torch.int64, device=device)
+    lo = rank * per
+    share = torch.empty(per, dtype=torch.int64, device=device)
+    share.copy_(h[lo:lo + per], non_blocking=True)
+    if per:
+        dist.all_gather_into_tensor(full[:per * world], share)
+    if tail:
+        full[per * world:total].copy_(h[per * world:total], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    off = np.ascontiguousarray(off, np.uint64)
+    ctx.n = len(off) - 1
+    ctx.sizes = np.diff(off).astype(np.int64)
+    T._chk(T.lib().tc_sketches_upload_dev(ctx._h, full.data_ptr(), T._p(off, C.c_uint64), ctx.n))
+    return (per + tail) * 8
+
+
 def distributed_mst(ctx, k, threshold, containment=False, dist=None):
     """Full multi-GPU MST of the sketches uploaded (replicated) on every rank's ctx."""
     import rabbittclust_b200 as T

@@ -20,7 +20,15 @@ def main(out_dir, containment):
     sk = (synth.family_sketches(8, 40, seed=41, ragged=(100, 2500)) if containment
           else synth.family_sketches(10, 40, s=1000, seed=40))
     ctx = T.Context(local)
-    ctx.upload(sk)
+    if containment:
+        ctx.upload(sk)
+    else:
+        # sharded upload: every rank reads only its share of the pinned host hashes, NCCL all-gathers the rest
+        h, off = T.pack_sketches(sk)
+        h_pin = torch.from_numpy(h).pin_memory()
+        mst_dist.upload_sharded(ctx, h_pin, off, dist, torch.device("cuda", local))
+        want = np.array([[len(np.intersect1d(sk[i], sk[j])) for j in range(3)] for i in range(37, 41)], np.uint32)
+        assert np.array_equal(ctx.pair_common(37, 41, 0, 3, impl=2), want), "sharded upload differs"
     mst = mst_dist.distributed_mst(ctx, 21, 0.05, bool(containment), dist)
     np.save(os.path.join(out_dir, "mst_%d.npy" % rank), mst)
     if rank == 0:

@@ -52,3 +52,13 @@ def test_owned_pairs_partition():
     for n in (1, 31, 32, 33, 100, 257):
         for world in (1, 2, 3, 8):
             assert sum(mst_dist.owned_pairs(n, r, world) for r in range(world)) == n * (n - 1) // 2
+
+
+def test_shard_bounds_cover_everything():
+    from rabbittclust_b200 import mst_dist
+    for total in (0, 1, 7, 1000, 100000001):
+        for world in (1, 2, 3, 8):
+            spans = [mst_dist.shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all((hi - lo) % 2 == 0 for lo, hi in spans[:-1])
