@@ -26,7 +26,19 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
+
+# stdout carries exactly ONE JSON line: libraries that print to fd 1 (e.g. NCCL's "NCCL version ..." banner under
+# NCCL_DEBUG=VERSION) are redirected to stderr for the whole run; emit() writes the line to the real stdout
+if "TCLUST_BENCH_STDOUT_FD" not in os.environ or os.environ.get("TCLUST_BENCH_STDOUT_PID") != str(os.getpid()):
+    os.environ["TCLUST_BENCH_STDOUT_FD"] = str(os.dup(1))      # (bench_sketch imports this module a second time)
+    os.environ["TCLUST_BENCH_STDOUT_PID"] = str(os.getpid())
+    os.dup2(2, 1)
+_REAL_STDOUT = int(os.environ["TCLUST_BENCH_STDOUT_FD"])
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 PAIR_BYTES = 16000.0   # algorithmic operand bytes per pair: 8*(|A|+|B|) at s=1000
 
@@ -187,7 +199,7 @@ def run_reference(args):
                 "cpu_baseline": {"value": value, "unit": "genomes/s", "cores": vals[0].get("threads", 1), "kind": kind,
                                  "sample": "%d genomes of %d bp per step" % (vals[0]["genomes"], L)},
                 "e2e": {"value": value, "unit": "genomes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -396,7 +408,7 @@ def run_pairs(args):
         if rank == 0:
             line["sketch"] = bench_sketch.sketch_block(sargs, m, world, None, with_cpu=(world == 1 and not args.no_cpu))
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -237,7 +237,8 @@ def run_sketch(args):
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
     if args.workload == "kssd":
-        print(json.dumps(measure_kssd(args, local_rank, rank)), flush=True)
+        from bench import emit
+        emit(measure_kssd(args, local_rank, rank))
         return
     dist = None
     if world > 1:
@@ -250,7 +251,8 @@ def run_sketch(args):
     clocks = sampler.stop() if rank == 0 else None
     m = reduce_ranks(torch, dist, m)
     if rank == 0:
-        print(json.dumps(sketch_block(args, m, world, clocks, with_cpu=(world == 1 and not args.no_cpu))), flush=True)
+        from bench import emit
+        emit(sketch_block(args, m, world, clocks, with_cpu=(world == 1 and not args.no_cpu)))
     if dist is not None:
         dist.destroy_process_group()
 
