@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <numeric>
 
@@ -132,10 +133,26 @@ __global__ void interleave_kernel(const uint32_t *ranks, const unsigned long lon
 
 static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
 
+// TCLUST_TIMING=1: phase times of the upload on stderr (development aid; synchronises the stream at every mark)
+struct PhaseTimer {
+    bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0;
+    explicit PhaseTimer(cudaStream_t s) : on(getenv("TCLUST_TIMING") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[tclust timing] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_device, const uint64_t *off, uint32_t n)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
+    PhaseTimer pt(ctx->stream);
     free_sketches(ctx);
+    pt.mark("free previous set");
     TC_CHECK(n > 0, "tc_sketches_upload: n == 0");
     const uint64_t total = off[n];
     TC_CHECK(total < 0xFFFFFFF0ull, "tc_sketches_upload: %llu hashes exceed the u32 rank space",
@@ -155,37 +172,48 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     TC_CUDA(cudaMalloc(&ctx->d_off, (size_t)(n + 1) * 8));
     TC_CUDA(cudaMalloc(&ctx->d_size, (size_t)n * 4));
     TC_CUDA(cudaMalloc(&ctx->d_ranks, tot1 * 4));
+    pt.mark("host prep + cudaMalloc");
     TC_CUDA(cudaMemcpyAsync(ctx->d_hashes, hashes, total * 8,
                             hashes_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     TC_CUDA(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     sizes_kernel<<<nblk(n, 256), 256, 0, st>>>(reinterpret_cast<unsigned long long *>(ctx->d_off), ctx->d_size, n);
     ctx->launches++;
+    pt.mark("copy of the hashes");
 
     // ---- order-preserving dense rank transform: u64 hash -> u32 rank (equal hash <=> equal rank)
     if (total > 0) {
-        uint64_t *k_in = nullptr, *k_out = nullptr;
-        uint32_t *v_in = nullptr, *v_out = nullptr;
-        TC_CUDA(cudaMalloc(&k_in, total * 8)); TC_CUDA(cudaMalloc(&k_out, total * 8));
-        TC_CUDA(cudaMalloc(&v_in, total * 4)); TC_CUDA(cudaMalloc(&v_out, total * 4));
+        // sort workspace: kept in the context's scratch between uploads (24 B per hash + cub's temporary storage)
+        size_t tmp_bytes = 0, tmp2 = 0;
+        {
+            cub::DoubleBuffer<uint64_t> kb0(nullptr, nullptr);
+            cub::DoubleBuffer<uint32_t> vb0(nullptr, nullptr);
+            TC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb0, vb0, (int)total, 0, 64, st));
+            TC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp2, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)total, st));
+            tmp_bytes = std::max(tmp_bytes, tmp2);
+        }
+        const size_t a256 = 255;
+        const size_t o_kout = (total * 8 + a256) & ~a256, o_vin = o_kout + ((total * 8 + a256) & ~a256);
+        const size_t o_vout = o_vin + ((total * 4 + a256) & ~a256), o_tmp = o_vout + ((total * 4 + a256) & ~a256);
+        void *ws = nullptr;
+        if (tc_scratch(ctx, o_tmp + tmp_bytes, &ws)) return 1;
+        uint8_t *wsb = static_cast<uint8_t *>(ws);
+        uint64_t *k_in = reinterpret_cast<uint64_t *>(wsb), *k_out = reinterpret_cast<uint64_t *>(wsb + o_kout);
+        uint32_t *v_in = reinterpret_cast<uint32_t *>(wsb + o_vin), *v_out = reinterpret_cast<uint32_t *>(wsb + o_vout);
+        void *tmp = wsb + o_tmp;
+        pt.mark("sort workspace");
         TC_CUDA(cudaMemcpyAsync(k_in, ctx->d_hashes, total * 8, cudaMemcpyDeviceToDevice, st));
         iota_kernel<<<nblk(total, 256), 256, 0, st>>>(v_in, total);
         cub::DoubleBuffer<uint64_t> kb(k_in, k_out);
         cub::DoubleBuffer<uint32_t> vb(v_in, v_out);
-        size_t tmp_bytes = 0;
-        TC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)total, 0, 64, st));
-        void *tmp = nullptr;
-        TC_CUDA(cudaMalloc(&tmp, tmp_bytes));
         TC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kb, vb, (int)total, 0, 64, st));
+        pt.mark("radix sort");
         uint32_t *flag = vb.Alternate();  // reuse the spare value buffer
         head_flag_kernel<<<nblk(total, 256), 256, 0, st>>>(kb.Current(), flag, total);
-        size_t tmp2 = 0;
-        TC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp2, flag, flag, (int)total, st));
-        if (tmp2 > tmp_bytes) { cudaFree(tmp); TC_CUDA(cudaMalloc(&tmp, tmp2)); tmp_bytes = tmp2; }
         TC_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp2, flag, flag, (int)total, st));
         scatter_rank_kernel<<<nblk(total, 256), 256, 0, st>>>(flag, vb.Current(), ctx->d_ranks, total);
         ctx->launches += 12;  // iota, sort passes (cub), flags, scan, scatter (approximate; cub internals)
         TC_CUDA(cudaStreamSynchronize(st));
-        cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out); cudaFree(tmp);
+        pt.mark("flags + scan + scatter");
     }
 
     // ---- group-interleaved layout
@@ -210,7 +238,10 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     }
     TC_CUDA(cudaGetLastError());
     TC_CUDA(cudaStreamSynchronize(st));
-    return tc_kh_prepare(ctx);
+    pt.mark("interleaved layout");
+    const int rc = tc_kh_prepare(ctx);
+    pt.mark("distinct counts + pivots");
+    return rc;
 }
 
 extern "C" int tc_sketches_upload(tc_ctx *ctx, const uint64_t *hashes, const uint64_t *off, uint32_t n)
