@@ -46,6 +46,7 @@ struct tc_ctx {
     uint32_t ngroups = 0;
     uint32_t *d_gt = nullptr;     // group-interleaved ranks: [group][row][lane]
     uint64_t *d_goff = nullptr;   // ngroups+1 element offsets into d_gt
+    uint64_t cap_hashes = 0, cap_ranks = 0, cap_gt = 0, cap_n = 0, cap_groups = 0, cap_comp = 0;   // element capacities
     std::vector<uint64_t> h_off;
     std::vector<uint32_t> h_size;
 

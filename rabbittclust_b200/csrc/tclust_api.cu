@@ -60,16 +60,36 @@ extern "C" int tc_ctx_create(int device, tc_ctx **out)
     return 0;
 }
 
-static void free_sketches(tc_ctx *ctx)
+// the big device buffers are kept between uploads (cudaFree/cudaMalloc of GB-sized buffers costs milliseconds, and
+// tens of milliseconds once the context also holds the sort workspace): an upload only grows them
+static void release_sketches(tc_ctx *ctx)
 {
     cudaFree(ctx->d_hashes); cudaFree(ctx->d_off); cudaFree(ctx->d_size); cudaFree(ctx->d_ranks);
     cudaFree(ctx->d_gt); cudaFree(ctx->d_goff); cudaFree(ctx->d_edges); cudaFree(ctx->d_comp);
     cudaFree(ctx->d_kh_pivots); cudaFree(ctx->d_kh_pivoff);
-    ctx->d_kh_pivots = nullptr; ctx->d_kh_pivoff = nullptr; ctx->kh_edge_units.clear(); ctx->kh_edge_units_n = 0;
+    ctx->d_kh_pivots = nullptr; ctx->d_kh_pivoff = nullptr;
     ctx->d_hashes = nullptr; ctx->d_off = nullptr; ctx->d_size = nullptr; ctx->d_ranks = nullptr;
     ctx->d_gt = nullptr; ctx->d_goff = nullptr; ctx->d_edges = nullptr; ctx->d_comp = nullptr;
-    ctx->edge_cap = 0; ctx->n_edges = 0; ctx->n = 0; ctx->total = 0; ctx->ngroups = 0;
+    ctx->cap_hashes = ctx->cap_ranks = ctx->cap_gt = ctx->cap_n = ctx->cap_groups = ctx->cap_comp = 0;
+    ctx->edge_cap = 0;
+}
+
+static void reset_sketches(tc_ctx *ctx)
+{
+    ctx->kh_edge_units.clear(); ctx->kh_edge_units_n = 0;
+    ctx->n_edges = 0; ctx->n = 0; ctx->total = 0; ctx->ngroups = 0; ctx->edges_semb_size = 0;
     tc_rep_table_reset(ctx);
+}
+
+template <typename T>
+static int ensure_cap(T **p, uint64_t *cap, uint64_t need)
+{
+    if (*p && need <= *cap) return 0;
+    cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    TC_CUDA(cudaMalloc(p, std::max<uint64_t>(need, 1) * sizeof(T)));
+    *cap = need;
+    return 0;
 }
 
 extern "C" void tc_ctx_destroy(tc_ctx *ctx)
@@ -77,7 +97,8 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    free_sketches(ctx);
+    reset_sketches(ctx);
+    release_sketches(ctx);
     tc_rep_table_free(ctx);
     tc_k1_free(ctx);
     tc_k2_free(ctx);
@@ -151,8 +172,8 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     PhaseTimer pt(ctx->stream);
-    free_sketches(ctx);
-    pt.mark("free previous set");
+    reset_sketches(ctx);
+    pt.mark("reset previous set");
     TC_CHECK(n > 0, "tc_sketches_upload: n == 0");
     const uint64_t total = off[n];
     TC_CHECK(total < 0xFFFFFFF0ull, "tc_sketches_upload: %llu hashes exceed the u32 rank space",
@@ -168,10 +189,14 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     }
     cudaStream_t st = ctx->stream;
     const uint64_t tot1 = std::max<uint64_t>(total, 1);
-    TC_CUDA(cudaMalloc(&ctx->d_hashes, tot1 * 8));
-    TC_CUDA(cudaMalloc(&ctx->d_off, (size_t)(n + 1) * 8));
-    TC_CUDA(cudaMalloc(&ctx->d_size, (size_t)n * 4));
-    TC_CUDA(cudaMalloc(&ctx->d_ranks, tot1 * 4));
+    if (ensure_cap(&ctx->d_hashes, &ctx->cap_hashes, tot1) || ensure_cap(&ctx->d_ranks, &ctx->cap_ranks, tot1)) return 1;
+    if (n + 1 > ctx->cap_n) {
+        cudaFree(ctx->d_off); cudaFree(ctx->d_size);
+        ctx->d_off = nullptr; ctx->d_size = nullptr; ctx->cap_n = 0;
+        TC_CUDA(cudaMalloc(&ctx->d_off, (size_t)(n + 1) * 8));
+        TC_CUDA(cudaMalloc(&ctx->d_size, (size_t)(n + 1) * 4));
+        ctx->cap_n = n + 1;
+    }
     pt.mark("host prep + cudaMalloc");
     TC_CUDA(cudaMemcpyAsync(ctx->d_hashes, hashes, total * 8,
                             hashes_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
@@ -226,9 +251,9 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
         goff[g + 1] = goff[g] + (uint64_t)rows * TC_GROUP;
         max_rows = std::max<uint64_t>(max_rows, rows);
     }
-    TC_CUDA(cudaMalloc(&ctx->d_goff, (size_t)(ctx->ngroups + 1) * 8));
+    if (ensure_cap(&ctx->d_goff, &ctx->cap_groups, (uint64_t)ctx->ngroups + 1)) return 1;
     TC_CUDA(cudaMemcpyAsync(ctx->d_goff, goff.data(), (size_t)(ctx->ngroups + 1) * 8, cudaMemcpyHostToDevice, st));
-    TC_CUDA(cudaMalloc(&ctx->d_gt, std::max<uint64_t>(goff[ctx->ngroups], 1) * 4));
+    if (ensure_cap(&ctx->d_gt, &ctx->cap_gt, std::max<uint64_t>(goff[ctx->ngroups], 1))) return 1;
     if (max_rows > 0) {
         dim3 grid(nblk(max_rows * TC_GROUP, 256), ctx->ngroups);
         interleave_kernel<<<grid, 256, 0, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
@@ -299,7 +324,6 @@ extern "C" int tc_pair_common_b(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t 
 // ------------------------------------------------------------------------------ dense pass
 static int ensure_edges(tc_ctx *ctx)
 {
-    if (ctx->d_edges) return 0;
     uint64_t cap = (uint64_t)ctx->n * (ctx->n - 1) / 2;
     // default: up to 2^28 edges (3.2 GB), or -- for sets whose candidate graph is denser, e.g. KSSD sketches in a
     // 2^24 hash space at N = 500k (BASELINE configs[4]: ~1.4 % of all pairs share a hash) -- up to half of the
@@ -310,6 +334,9 @@ static int ensure_edges(tc_ctx *ctx)
         lim = std::max<uint64_t>(lim, std::min<uint64_t>(cap / 16, free_b / 2 / sizeof(tc_pair)));
     if (const char *s = getenv("TCLUST_EDGE_CAP")) lim = strtoull(s, nullptr, 10);
     cap = std::max<uint64_t>(std::min(cap, lim), 1);
+    if (ctx->d_edges && ctx->edge_cap >= cap) return 0;          // kept from an earlier pass / upload
+    cudaFree(ctx->d_edges);
+    ctx->d_edges = nullptr; ctx->edge_cap = 0;
     TC_CUDA(cudaMalloc(&ctx->d_edges, cap * sizeof(tc_pair)));
     ctx->edge_cap = cap;
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), ctx->stream));
@@ -452,7 +479,7 @@ extern "C" int tc_boruvka_upload_comp(tc_ctx *ctx, const int32_t *comp, uint32_t
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(n == ctx->n, "tc_boruvka_upload_comp: n mismatch");
-    if (!ctx->d_comp) TC_CUDA(cudaMalloc(&ctx->d_comp, (size_t)n * 4));
+    if (ensure_cap(&ctx->d_comp, &ctx->cap_comp, n)) return 1;
     TC_CUDA(cudaMemcpyAsync(ctx->d_comp, comp, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     return 0;
 }

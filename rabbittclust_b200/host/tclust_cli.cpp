@@ -166,6 +166,8 @@ vector<string> read_list(const string &path)
     return v;
 }
 
+uint64_t g_input_bytes = 0;              // total size of the input genomes (cal_size), sizes the feeder's buffers
+
 // ------------------------------------------------------------------------ parameter tuning
 void cal_size(const Options &o, uint64_t &max_size, uint64_t &min_size, uint64_t &avg_size)
 {
@@ -193,6 +195,7 @@ void cal_size(const Options &o, uint64_t &max_size, uint64_t &min_size, uint64_t
     }
     if (number == 0) die("calSize(), no genome passes the minimum length filter");
     avg_size = total / number;
+    g_input_bytes = total;
     int total_number = number + bad;
     cerr << "\t===the genome number for clustering is: " << number << endl;
     cerr << "\t===the genome number below the minimum genome length threshold is: " << bad << endl;
@@ -307,7 +310,8 @@ struct PinnedBuf {
     void reserve(size_t need)
     {
         if (need <= cap) return;
-        const size_t nc = std::max<size_t>(need + need / 4, (size_t)64 << 20);
+        // page-locking is slow (~0.3 ms per MB): grow geometrically and let the feeder pre-size the buffer
+        const size_t nc = std::max<size_t>(std::max<size_t>(need, cap * 2), (size_t)16 << 20);
         uint8_t *q = (uint8_t *)tc_host_alloc(nc);
         if (!q) { cerr << "ERROR: cannot allocate " << nc << " bytes of page-locked memory, " << tc_last_error() << endl; exit(1); }
         if (len) memcpy(q, p, len);
@@ -364,7 +368,14 @@ void flush_batch(tc_ctx *ctx, const Options &o, Batch &b, vector<Genome> &out)
 struct Feeder {
     tc_ctx *ctx; const Options &o; vector<Genome> &out;
     Batch batch[2]; int cur = 0; std::thread worker; bool running = false;
-    Feeder(tc_ctx *c, const Options &opt, vector<Genome> &dst) : ctx(c), o(opt), out(dst) {}
+    Feeder(tc_ctx *c, const Options &opt, vector<Genome> &dst, uint64_t expect_bytes, uint64_t batch_bytes)
+        : ctx(c), o(opt), out(dst)
+    {
+        // one allocation per buffer: the whole input if it fits a batch, else a full batch (+ the largest overshoot)
+        const uint64_t first = std::min<uint64_t>(expect_bytes + (1u << 20), batch_bytes + (batch_bytes >> 3));
+        batch[0].seq.reserve(first);
+        if (expect_bytes > batch_bytes) batch[1].seq.reserve(first);
+    }
     Batch &fill() { return batch[cur]; }
     void wait() { if (running) { worker.join(); running = false; } }
     void submit()                      // hand the filled batch to the GPU, continue in the other one
@@ -396,7 +407,7 @@ void sketch_files(tc_ctx *ctx, const Options &o, vector<Genome> &out)
     const uint64_t batch_bytes = 1ull << 29;
     struct Parsed { vector<uint8_t> seq; vector<Record> recs; int file_len = 0; bool ok = false; };
     size_t next = 0;
-    Feeder feeder(ctx, o, out);
+    Feeder feeder(ctx, o, out, g_input_bytes, batch_bytes);
     while (next < nfiles) {
         // read + parse a window of files on the host threads, then append them in list order
         const size_t win = std::min(nfiles - next, (size_t)std::max(o.threads * 4, 16));
@@ -452,7 +463,7 @@ void sketch_sequences(tc_ctx *ctx, const Options &o, vector<Genome> &out)
     vector<uint8_t> seq; vector<Record> recs;
     parse_fasta(text, false, seq, recs);
     text.clear(); text.shrink_to_fit();
-    Feeder feeder(ctx, o, out);
+    Feeder feeder(ctx, o, out, seq.size(), 1ull << 29);
     for (const Record &r : recs) {
         const uint64_t len = r.end - r.begin;
         if (len < o.min_len) continue;                                   // SketchInfo.cpp:217
