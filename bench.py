@@ -264,7 +264,7 @@ def run_pairs(args):
         sampler.start()
     launches0 = ctx.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k3_ms, pairs_mine, nedges = 0.0, 0, 0
+    k3_ms, pairs_mine, nedges, k3_steps, kern_steps = 0.0, 0, 0, [], []
     with torch.cuda.stream(stream):
         ev0.record()
     t_wall0 = time.time()
@@ -276,7 +276,9 @@ def run_pairs(args):
         with torch.cuda.stream(stream):
             b.record()
         b.synchronize()
-        k3_ms += a.elapsed_time(b)
+        k3_steps.append(a.elapsed_time(b))            # whole tc_allpairs_pass call (unit upload, kernel, count read-back)
+        kern_steps.append(ctx.last_pass_kernel_ms)    # events recorded by the library right around the kernel
+        k3_ms += kern_steps[-1]
         pairs_mine += npairs
         T._chk(L.tc_boruvka_upload_comp(ctx._h, comp.ctypes.data_as(C.POINTER(C.c_int32)), n))
         T._chk(L.tc_boruvka_phase1(ctx._h, 0, best_key.data_ptr()))
@@ -373,6 +375,8 @@ def run_pairs(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": how,
                          "kernel": kernel, "kernel_ms": 1e3 * k3_avg_s, "kernel_ms_per_rank": per_rank_ms,
+                         "kernel_ms_steps": [round(x, 3) for x in kern_steps],
+                         "pass_call_ms_steps": [round(x, 3) for x in k3_steps],
                          "binding_units": binding,
                          "note": "algorithmic bytes = SURVEY 8(d)'s operand bytes 8*(|A|+|B|) = 16000 B/pair x pairs per "
                                  "launch.  Every column element is probed once per 32 row sketches (shared-memory hash "

@@ -49,6 +49,9 @@ int  tc_ctx_create(int device, tc_ctx **out);
 void tc_ctx_destroy(tc_ctx *ctx);
 /* number of kernels of this library launched on the context so far (bench accounting) */
 uint64_t tc_kernel_launches(const tc_ctx *ctx);
+/* duration of the last dense-pass kernel (tc_allpairs_pass*, tc_mst*), CUDA events recorded on the context's stream
+ * immediately around the launch; -1 if no pass has completed */
+double tc_last_pass_kernel_ms(const tc_ctx *ctx);
 /* CUDA stream (cudaStream_t) the context launches on, for event timing by the caller */
 void *tc_stream(const tc_ctx *ctx);
 

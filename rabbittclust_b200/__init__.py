@@ -18,7 +18,7 @@ PAIR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("common", "<u4")])
 
 # every symbol include/tclust.h declares (tests check the built library exports all of them)
 SYMBOLS = [
-    "tc_version", "tc_last_error", "tc_ctx_create", "tc_ctx_destroy", "tc_kernel_launches", "tc_stream",
+    "tc_version", "tc_last_error", "tc_ctx_create", "tc_ctx_destroy", "tc_kernel_launches", "tc_last_pass_kernel_ms", "tc_stream",
     "tc_host_alloc", "tc_host_free", "tc_sketch_minhash", "tc_sketch_minhash_dev", "tc_kssd_shuffled_dim", "tc_sketch_kssd", "tc_sketch_kssd_dev",
     "tc_sketches_upload", "tc_sketches_upload_dev", "tc_pair_common", "tc_allpairs_pass",
     "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_mst",
@@ -54,6 +54,8 @@ def lib():
     L.tc_ctx_destroy.restype = None
     L.tc_kernel_launches.argtypes = [vp]
     L.tc_kernel_launches.restype = C.c_uint64
+    L.tc_last_pass_kernel_ms.argtypes = [vp]
+    L.tc_last_pass_kernel_ms.restype = C.c_double
     L.tc_stream.argtypes = [vp]
     L.tc_stream.restype = vp
     L.tc_host_alloc.argtypes = [C.c_size_t]
@@ -167,6 +169,10 @@ class Context:
     @property
     def launches(self):
         return int(lib().tc_kernel_launches(self._h))
+
+    @property
+    def last_pass_kernel_ms(self):
+        return float(lib().tc_last_pass_kernel_ms(self._h))
 
     @property
     def stream(self):

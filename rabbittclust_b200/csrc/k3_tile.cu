@@ -358,6 +358,7 @@ int k3_launch(tc_ctx *ctx, K3Args &a, int mode, bool fh)
     int grid = (int)(my_tiles < ctx->num_sms ? my_tiles : ctx->num_sms);
     int rc;
     const bool semb = a.semb_size > 0;
+    if (ctx->ev_pass0) cudaEventRecord(ctx->ev_pass0, ctx->stream);      // kernel-only duration, tc_last_pass_kernel_ms
     if (mode == K3_MODE_MATRIX)
         rc = semb ? k3_launch_t<K3_MODE_MATRIX, false, true>(ctx, a, grid)
            : fh   ? k3_launch_t<K3_MODE_MATRIX, true, false>(ctx, a, grid)
@@ -367,6 +368,7 @@ int k3_launch(tc_ctx *ctx, K3Args &a, int mode, bool fh)
     else
         rc = semb ? k3_launch_t<K3_MODE_CAND, false, true>(ctx, a, grid) : k3_launch_t<K3_MODE_CAND, true, false>(ctx, a, grid);
     if (rc) return rc;
+    if (ctx->ev_pass1) cudaEventRecord(ctx->ev_pass1, ctx->stream);
     ctx->launches++;
     TC_CUDA(cudaGetLastError());
     return 0;

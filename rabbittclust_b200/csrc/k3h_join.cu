@@ -468,7 +468,9 @@ int tc_kh_prepare(tc_ctx *ctx)
     return rc;
 }
 
-static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &units)
+// edge_list: `units` is ctx->kh_edge_units, which stays resident on the device between passes (no per-pass copy
+// from pageable host memory in front of the kernel)
+static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &units, bool edge_list = false)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -477,12 +479,16 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
     }
     if (units.empty()) return 0;
     if (units.size() > ctx->kh_units_cap) {
-        cudaFree(ctx->d_kh_units); ctx->d_kh_units = nullptr; ctx->kh_units_cap = 0;
+        cudaFree(ctx->d_kh_units); ctx->d_kh_units = nullptr; ctx->kh_units_cap = 0; ctx->kh_units_on_device = false;
         TC_CUDA(cudaMalloc(&ctx->d_kh_units, units.size() * sizeof(tc_kh_unit)));
         ctx->kh_units_cap = units.size();
     }
-    TC_CUDA(cudaMemcpyAsync(ctx->d_kh_units, units.data(), units.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice,
-                            ctx->stream));
+    if (!(edge_list && ctx->kh_units_on_device)) {
+        TC_CUDA(cudaMemcpyAsync(ctx->d_kh_units, units.data(), units.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice,
+                                ctx->stream));
+        TC_CUDA(cudaStreamSynchronize(ctx->stream));   // `units` (host) must outlive the copy
+        ctx->kh_units_on_device = edge_list;
+    }
     const long long mine = ((long long)units.size() - a.part + a.nparts - 1) / a.nparts;
     if (mine <= 0) { TC_CUDA(cudaStreamSynchronize(ctx->stream)); return 0; }
     const int grid = (int)std::min<long long>(mine, ctx->num_sms);
@@ -492,7 +498,9 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
     a.units = ctx->d_kh_units; a.nunits = (uint32_t)units.size();
     a.counters = ctx->d_edge_count; a.state = ctx->d_kh_state;
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count + 2, 0, sizeof(unsigned long long), ctx->stream));
+    if (ctx->ev_pass0) cudaEventRecord(ctx->ev_pass0, ctx->stream);      // kernel-only duration, tc_last_pass_kernel_ms
     k3h_join_kernel<<<grid, KH_THREADS, KH_SMEM, ctx->stream>>>(a);
+    if (ctx->ev_pass1) cudaEventRecord(ctx->ev_pass1, ctx->stream);
     ctx->launches++;
     TC_CUDA(cudaGetLastError());
     TC_CUDA(cudaStreamSynchronize(ctx->stream));   // `units` (host) must outlive the copy
@@ -523,9 +531,10 @@ int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts,
                 if (c1 > c0) ctx->kh_edge_units.push_back(tc_kh_unit{rb, c0, c1});
             }
         ctx->kh_edge_units_n = n; ctx->kh_edge_units_start = start_index;
+        ctx->kh_units_on_device = false;
     }
     KHArgs a{};
     a.mode = KH_MODE_EDGES; a.part = part; a.nparts = nparts ? nparts : 1; a.row_min = start_index;
     a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
-    return kh_launch(ctx, a, ctx->kh_edge_units);
+    return kh_launch(ctx, a, ctx->kh_edge_units, true);
 }

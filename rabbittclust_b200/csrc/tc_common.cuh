@@ -35,6 +35,7 @@ struct tc_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
+    cudaEvent_t ev_pass0 = nullptr, ev_pass1 = nullptr;   // around the last dense-pass kernel
 
     // resident sketches (HP-2)
     uint32_t n = 0;               // number of sketches
@@ -53,6 +54,7 @@ struct tc_ctx {
     // candidate edges (semantic-A graph) produced by the dense pass
     tc_pair *d_edges = nullptr;
     uint64_t edge_cap = 0;
+    uint32_t edge_cap_for_n = 0;  // n the edge buffer was last sized for (0: re-evaluate)
     unsigned long long *d_edge_count = nullptr;  // [0] = count, [1] = overflow flag, [2] = tile counter
     uint64_t n_edges = 0;
     uint32_t edges_semb_size = 0;     // > 0: the edges carry semantic-B counts taken with this sketchSize
@@ -75,6 +77,7 @@ struct tc_ctx {
     size_t kh_units_cap = 0;
     std::vector<tc_kh_unit> kh_edge_units;
     uint32_t kh_edge_units_n = 0, kh_edge_units_start = 0;
+    bool kh_units_on_device = false;     // d_kh_units currently holds kh_edge_units
 
     // KSSD shuffled_dim table (K2), resident once uploaded
     int32_t *d_kssd_dim = nullptr;

@@ -45,6 +45,11 @@ extern "C" int tc_ctx_create(int device, tc_ctx **out)
         return 1;
     }
     TC_CHECK(device >= 0 && device < ndev, "tc_ctx_create: device %d out of range (%d devices)", device, ndev);
+    if (const char *m = getenv("TCLUST_SYNC")) {          // how the host waits in cudaStreamSynchronize (before the context exists)
+        const unsigned f = !strcmp(m, "spin") ? cudaDeviceScheduleSpin : !strcmp(m, "yield") ? cudaDeviceScheduleYield
+                         : !strcmp(m, "block") ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto;
+        if (cudaSetDeviceFlags(f) != cudaSuccess) cudaGetLastError();
+    }
     TC_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     TC_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -54,6 +59,8 @@ extern "C" int tc_ctx_create(int device, tc_ctx **out)
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     TC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    TC_CUDA(cudaEventCreate(&ctx->ev_pass0));
+    TC_CUDA(cudaEventCreate(&ctx->ev_pass1));
     TC_CUDA(cudaMalloc(&ctx->d_edge_count, 4 * sizeof(unsigned long long)));
     TC_CUDA(cudaMemset(ctx->d_edge_count, 0, 4 * sizeof(unsigned long long)));
     *out = ctx;
@@ -71,13 +78,14 @@ static void release_sketches(tc_ctx *ctx)
     ctx->d_hashes = nullptr; ctx->d_off = nullptr; ctx->d_size = nullptr; ctx->d_ranks = nullptr;
     ctx->d_gt = nullptr; ctx->d_goff = nullptr; ctx->d_edges = nullptr; ctx->d_comp = nullptr;
     ctx->cap_hashes = ctx->cap_ranks = ctx->cap_gt = ctx->cap_n = ctx->cap_groups = ctx->cap_comp = 0;
-    ctx->edge_cap = 0;
+    ctx->edge_cap = 0; ctx->edge_cap_for_n = 0;
 }
 
 static void reset_sketches(tc_ctx *ctx)
 {
-    ctx->kh_edge_units.clear(); ctx->kh_edge_units_n = 0;
+    ctx->kh_edge_units.clear(); ctx->kh_edge_units_n = 0; ctx->kh_units_on_device = false;
     ctx->n_edges = 0; ctx->n = 0; ctx->total = 0; ctx->ngroups = 0; ctx->edges_semb_size = 0;
+    ctx->edge_cap_for_n = 0;
     tc_rep_table_reset(ctx);
 }
 
@@ -106,11 +114,19 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_kssd_dim); cudaFree(ctx->d_kssd_filter);
     cudaFree(ctx->d_kh_state); cudaFree(ctx->d_kh_units);
+    if (ctx->ev_pass0) cudaEventDestroy(ctx->ev_pass0);
+    if (ctx->ev_pass1) cudaEventDestroy(ctx->ev_pass1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 extern "C" uint64_t tc_kernel_launches(const tc_ctx *ctx) { return ctx->launches; }
+extern "C" double tc_last_pass_kernel_ms(const tc_ctx *ctx)
+{
+    float ms = 0.f;
+    if (!ctx->ev_pass0 || cudaEventElapsedTime(&ms, ctx->ev_pass0, ctx->ev_pass1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    return (double)ms;
+}
 extern "C" void *tc_stream(const tc_ctx *ctx) { return (void *)ctx->stream; }
 
 // ------------------------------------------------------------------ rank transform kernels
@@ -322,19 +338,32 @@ extern "C" int tc_pair_common_b(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t 
 }
 
 // ------------------------------------------------------------------------------ dense pass
-static int ensure_edges(tc_ctx *ctx)
+// Candidate-edge buffer: min(all pairs, 2^28 entries = 3.2 GB) to start with (TCLUST_EDGE_CAP overrides).  Sets whose
+// candidate graph is denser -- e.g. KSSD sketches in a 2^24 hash space at N = 500k (BASELINE configs[4]): ~1.4 % of all
+// pairs share a hash, 1.8e9 edges -- make the pass overflow; the kernels keep counting, so the exact need is known
+// and the pass is repeated once with a buffer of that size (`need` > 0), memory permitting.  No cudaMemGetInfo on the
+// normal path: that call alone costs up to tens of milliseconds.
+static int ensure_edges(tc_ctx *ctx, uint64_t need = 0)
 {
+    if (!need && ctx->d_edges && ctx->edge_cap_for_n == ctx->n) return 0;    // sized once per sketch set
     uint64_t cap = (uint64_t)ctx->n * (ctx->n - 1) / 2;
-    // default: up to 2^28 edges (3.2 GB), or -- for sets whose candidate graph is denser, e.g. KSSD sketches in a
-    // 2^24 hash space at N = 500k (BASELINE configs[4]: ~1.4 % of all pairs share a hash) -- up to half of the
-    // free HBM; TCLUST_EDGE_CAP overrides
     uint64_t lim = 1ull << 28;
-    size_t free_b = 0, total_b = 0;
-    if (cap > lim && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
-        lim = std::max<uint64_t>(lim, std::min<uint64_t>(cap / 16, free_b / 2 / sizeof(tc_pair)));
-    if (const char *s = getenv("TCLUST_EDGE_CAP")) lim = strtoull(s, nullptr, 10);
+    const char *env = getenv("TCLUST_EDGE_CAP");                 // hard limit: no growth beyond it
+    if (env) lim = strtoull(env, nullptr, 10);
+    else if (const char *init = getenv("TCLUST_EDGE_CAP_INIT")) lim = strtoull(init, nullptr, 10);   // first size only
+    if (need) {
+        TC_CHECK(!env, "tc_allpairs_pass: %llu candidate edges exceed TCLUST_EDGE_CAP=%s", (unsigned long long)need, env);
+        size_t free_b = 0, total_b = 0;
+        TC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t want = need + need / 64 + 1024;
+        const uint64_t room = (free_b + ctx->edge_cap * sizeof(tc_pair)) / sizeof(tc_pair);   // the old buffer is released first
+        TC_CHECK(want <= room - room / 8, "tc_allpairs_pass: %llu candidate edges need %.1f GB, more than the free device memory",
+                 (unsigned long long)need, want * sizeof(tc_pair) / 1e9);
+        lim = want;
+    }
     cap = std::max<uint64_t>(std::min(cap, lim), 1);
-    if (ctx->d_edges && ctx->edge_cap >= cap) return 0;          // kept from an earlier pass / upload
+    ctx->edge_cap_for_n = ctx->n;
+    if (ctx->d_edges && ctx->edge_cap >= cap) return 0;          // kept from an earlier upload
     cudaFree(ctx->d_edges);
     ctx->d_edges = nullptr; ctx->edge_cap = 0;
     TC_CUDA(cudaMalloc(&ctx->d_edges, cap * sizeof(tc_pair)));
@@ -361,13 +390,18 @@ static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32
     TC_CHECK(!(semb_size > 0 && start_index > 0), "tc_allpairs_pass: start_index is not supported for the semantic-B pass");
     TC_CHECK(start_index <= ctx->n, "tc_allpairs_pass: start_index %u > n %u", start_index, ctx->n);
     ctx->edges_semb_size = semb_size;
-    if (use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts, semb_size) : tc_launch_join_edges(ctx, radio, part, nparts, start_index)) return 1;
-    unsigned long long cnt[2];
-    TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    TC_CUDA(cudaStreamSynchronize(ctx->stream));
-    TC_CHECK(cnt[1] == 0 && cnt[0] <= ctx->edge_cap,
-             "tc_allpairs_pass: %llu candidate edges exceed the device edge buffer (%llu); raise TCLUST_EDGE_CAP",
-             cnt[0], (unsigned long long)ctx->edge_cap);
+    unsigned long long cnt[2] = {0, 0};
+    for (int attempt = 0;; attempt++) {
+        if (use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts, semb_size) : tc_launch_join_edges(ctx, radio, part, nparts, start_index)) return 1;
+        TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        TC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (cnt[1] == 0 && cnt[0] <= ctx->edge_cap) break;
+        // overflow: cnt[0] is the exact number of candidate edges; grow the buffer to it and repeat the pass once
+        TC_CHECK(attempt == 0, "tc_allpairs_pass: %llu candidate edges exceed the device edge buffer (%llu)",
+                 cnt[0], (unsigned long long)ctx->edge_cap);
+        if (ensure_edges(ctx, cnt[0])) return 1;
+        TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    }
     ctx->n_edges = cnt[0];
     if (n_edges) *n_edges = cnt[0];
     if (n_pairs) {

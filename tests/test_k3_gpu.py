@@ -221,3 +221,29 @@ def test_pass_from_and_mst_append(ctx, oracle):
     assert np.array_equal(la, lb)
     # start_index = 0 is the ordinary MST, start_index = n keeps the old tree
     assert np.array_equal(np.sort(ctx.mst_append(21, 0.05, 0, pre[:0])["dist"]), np.sort(full["dist"]))
+
+
+def test_edge_buffer_grows_on_overflow(tc, oracle, monkeypatch):
+    """a candidate graph denser than the first edge buffer: the pass overflows, the kernels keep counting, the buffer
+    is re-sized to the exact need and the pass repeated; a hard TCLUST_EDGE_CAP makes the same situation an error"""
+    sk = synth.family_sketches(4, 30, s=200, seed=5)
+    n = len(sk)
+    want = np.tril(oracle.common_matrix(sk), -1)
+    monkeypatch.setenv("TCLUST_EDGE_CAP_INIT", "100")
+    with tc.Context(0) as c:
+        c.upload(sk)
+        for impl in ("join", "merge"):
+            monkeypatch.setenv("TCLUST_PASS_IMPL", impl)
+            _, nedges = c.allpairs_pass(1 << 30)
+            assert nedges == int((want > 0).sum()) > 100
+            e = c.edges()
+            got = np.zeros((n, n), np.uint32)
+            got[e["i"], e["j"]] = e["common"]
+            assert np.array_equal(got, want)
+    monkeypatch.delenv("TCLUST_EDGE_CAP_INIT")
+    monkeypatch.delenv("TCLUST_PASS_IMPL")
+    monkeypatch.setenv("TCLUST_EDGE_CAP", "100")
+    with tc.Context(0) as c:
+        c.upload(sk)
+        with pytest.raises(tc.TclustError, match="TCLUST_EDGE_CAP"):
+            c.allpairs_pass(1 << 30)
