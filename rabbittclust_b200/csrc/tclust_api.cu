@@ -145,6 +145,15 @@ __global__ void scatter_rank_kernel(const uint32_t *scan, const uint32_t *perm, 
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) ranks[perm[i]] = scan[i] - 1u;  // inclusive scan of head flags, 0-based dense rank
 }
+// every sketch must be strictly ascending (sorted, duplicate-free): the merge and the hash join rely on it
+__global__ void check_sorted_kernel(const uint64_t *h, const unsigned long long *off, uint32_t n, unsigned int *bad)
+{
+    const uint32_t g = blockIdx.x;
+    if (g >= n) return;
+    const unsigned long long o = off[g], len = off[g + 1] - o;
+    for (unsigned long long i = threadIdx.x + 1; i < len; i += blockDim.x)
+        if (h[o + i] <= h[o + i - 1]) { atomicMin(bad, g); return; }
+}
 __global__ void sizes_kernel(const unsigned long long *off, uint32_t *size, uint32_t n)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,7 +228,22 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     TC_CUDA(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     sizes_kernel<<<nblk(n, 256), 256, 0, st>>>(reinterpret_cast<unsigned long long *>(ctx->d_off), ctx->d_size, n);
     ctx->launches++;
-    pt.mark("copy of the hashes");
+    {   // input contract check (0.8 GB read at N = 100k: ~0.2 ms)
+        unsigned int *d_bad = reinterpret_cast<unsigned int *>(ctx->d_edge_count + 3), h_bad = 0xFFFFFFFFu;
+        TC_CUDA(cudaMemsetAsync(d_bad, 0xFF, 4, st));
+        check_sorted_kernel<<<n, 128, 0, st>>>(ctx->d_hashes, reinterpret_cast<unsigned long long *>(ctx->d_off), n, d_bad);
+        ctx->launches++;
+        TC_CUDA(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+        TC_CUDA(cudaStreamSynchronize(st));
+        if (h_bad != 0xFFFFFFFFu) {
+            const uint32_t g = h_bad;
+            reset_sketches(ctx);
+            tc_set_error("tc_sketches_upload: sketch %u is not strictly ascending (sketches must be sorted and duplicate-free, "
+                         "as Sketch::MinHash::storeMinHashes returns them)", g);
+            return 1;
+        }
+    }
+    pt.mark("copy of the hashes + check");
 
     // ---- order-preserving dense rank transform: u64 hash -> u32 rank (equal hash <=> equal rank)
     if (total > 0) {

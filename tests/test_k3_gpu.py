@@ -247,3 +247,41 @@ def test_edge_buffer_grows_on_overflow(tc, oracle, monkeypatch):
         c.upload(sk)
         with pytest.raises(tc.TclustError, match="TCLUST_EDGE_CAP"):
             c.allpairs_pass(1 << 30)
+
+
+def test_upload_rejects_unsorted_or_duplicate_sketches(tc):
+    a = np.array([5, 9, 9, 12], np.uint64)           # duplicate
+    b = np.array([3, 2, 7], np.uint64)               # not ascending
+    ok = np.array([1, 2, 3], np.uint64)
+    with tc.Context(0) as c:
+        for bad, idx in (([ok, a], 1), ([b, ok], 0), ([ok, ok, b], 2)):
+            with pytest.raises(tc.TclustError, match="sketch %d is not strictly ascending" % idx):
+                c.upload(bad)
+        c.upload([ok, ok])
+        assert c.pair_common(0, 2, 0, 2, impl=2).tolist() == [[3, 3], [3, 3]]
+        with pytest.raises(tc.TclustError):
+            c.pair_common(0, 3, 0, 2)                 # range out of bounds
+
+
+def test_randomised_shapes_vs_oracle(ctx, oracle):
+    """random mixtures of sizes, value ranges, duplicates of whole sketches and empty sketches: all three kernels
+    against the oracle, plus the semantic-B kernel at a random stop size"""
+    rng = np.random.default_rng(2024)
+    for trial in range(6):
+        n = int(rng.integers(2, 90))
+        hi = int(rng.choice([300, 5000, 2**20, 2**63]))
+        sk = []
+        for _ in range(n):
+            size = int(rng.choice([0, 1, 2, 31, 32, 33, 200, 887, 888, 889, 1500]))
+            size = min(size, hi)
+            sk.append(np.sort(rng.choice(hi, size, replace=False).astype(np.uint64)) if hi < 2**21
+                      else np.unique(rng.integers(0, hi, size, dtype=np.uint64)))
+        for _ in range(3):
+            i, j = rng.integers(0, n, 2)
+            sk[i] = sk[j].copy()
+        ctx.upload(sk)
+        want = oracle.common_matrix(sk)
+        for impl in (0, 1, 2):
+            assert np.array_equal(ctx.pair_common(0, n, 0, n, impl=impl), want), (trial, impl)
+        s = int(rng.choice([1, 50, 888, 1000, 4000]))
+        assert np.array_equal(ctx.pair_common_b(0, n, 0, n, s), oracle.common_B_matrix(sk, s)), (trial, s)
