@@ -36,11 +36,12 @@ constexpr uint32_t KH_FWORDS = (1u << KH_FBITS) / 32;
 constexpr uint32_t KH_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t KH_CSEG = 4096;            // columns per unit
 constexpr uint32_t KH_STATE = 33;             // words of state per column: 32 counts + position
+constexpr uint32_t KH_STATE_CAND = 65;        // candidate mode: + 32 smallest shared ranks
 constexpr size_t KH_SMEM = (size_t)KH_SLOTS * 8 + (size_t)KH_FWORDS * 4;
 constexpr uint32_t KH_SORT_CAP = 32768;       // row blocks up to this many elements get distinct-count partitions
 constexpr uint32_t KH_DREC = 7;               // per row block: distinct count + pivot candidates for P = 2, 3, 4
 
-enum { KH_MODE_MATRIX = 0, KH_MODE_EDGES = 1 };
+enum { KH_MODE_MATRIX = 0, KH_MODE_EDGES = 1, KH_MODE_CAND = 2 };
 
 struct KHArgs {
     const uint32_t *ranks;
@@ -57,6 +58,11 @@ struct KHArgs {
     uint32_t *out; uint32_t i0, i1, j0, j1;
     tc_pair *edges; unsigned long long edge_cap; int radio;
     uint32_t row_min;               // edge mode: only rows i >= row_min (the start_index of the append flows)
+    // candidate mode (greedy representative scan, K5): columns are the sketches col_ids[c] (nullptr: c itself) for c in
+    // the unit's range, rows the queries [q0, q1); emits (query, rep, common, smallest shared rank) when common >= 1 and
+    // common + 1 >= common_min(pair)  -- the rule of k3_tile.cu's candidate mode
+    const uint32_t *col_ids; uint32_t q0, q1;
+    tc_cand *cands; int lower_only, cmin_fixed, containment; double jmin, one_plus_jmin;
 };
 
 // presence filter: word = top (KH_FBITS-5) bits of h = x * golden, the two bit positions = low 10 bits of h
@@ -188,8 +194,11 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint3
     }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
 {
+    constexpr bool CAND = MODE == KH_MODE_CAND;
+    constexpr uint32_t STRIDE = CAND ? KH_STATE_CAND : KH_STATE;
     extern __shared__ __align__(16) uint8_t kh_smem[];
     uint2 *table = reinterpret_cast<uint2 *>(kh_smem);
     uint32_t *filter = reinterpret_cast<uint32_t *>(kh_smem + (size_t)KH_SLOTS * 8);
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
     asm volatile("" : "+r"(tab_addr));
     uint32_t filt_addr = (uint32_t)__cvta_generic_to_shared(filter);
     asm volatile("" : "+r"(filt_addr));      // keep the shared-window addresses in registers (no rematerialisation)
-    uint32_t *state = a.state + (size_t)blockIdx.x * KH_CSEG * KH_STATE;
+    uint32_t *state = a.state + (size_t)blockIdx.x * KH_CSEG * STRIDE;
 
     for (;;) {
         if (tid == 0) s_unit = (uint32_t)(atomicAdd(&a.counters[2], 1ULL) * a.nparts + a.part);
@@ -262,11 +271,13 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                 if (lane == 0) c = atomicAdd(&s_next, 1u);
                 c = __shfl_sync(0xffffffffu, c, 0);
                 if (c >= c1) break;
-                const uint32_t clen = a.size[c];
-                uint32_t *st = state + (size_t)(c - c0) * KH_STATE;
+                const uint32_t cid = (CAND && a.col_ids) ? __ldg(a.col_ids + c) : c;      // sketch streamed as column c
+                const uint32_t clen = a.size[cid];
+                uint32_t *st = state + (size_t)(c - c0) * STRIDE;
                 uint32_t pos = 0, cnt = 0;
-                if (p > 0) { pos = st[32]; cnt = st[lane]; }
-                const uint32_t *pc = a.ranks + a.off[c] + pos + lane;   // this lane's element of the current step
+                uint32_t first_x = 0xFFFFFFFFu;        // CAND: smallest shared rank with row `lane` (= first one met)
+                if (p > 0) { pos = st[32]; cnt = st[lane]; if (CAND) first_x = st[33 + lane]; }
+                const uint32_t *pc = a.ranks + a.off[cid] + pos + lane;   // this lane's element of the current step
                 uint32_t rem = clen - pos;                               // elements left from the step's start
                 uint32_t xa[4], xb[4];
 #pragma unroll
@@ -317,12 +328,17 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
 #pragma unroll 1
                         for (int k = 0; k < 4; k++) {
                             const uint32_t mk = k == 0 ? mask[0] : k == 1 ? mask[1] : k == 2 ? mask[2] : mask[3];
+                            const uint32_t xk = k == 0 ? x[0] : k == 1 ? x[1] : k == 2 ? x[2] : x[3];
                             unsigned hit = __ballot_sync(0xffffffffu, mk != 0u);
                             if (__popc(hit) <= 16) {
                                 while (hit) {
                                     const int src = __ffs(hit) - 1;
                                     const uint32_t m = __shfl_sync(0xffffffffu, mk, src);
                                     cnt += (m >> lane) & 1u;
+                                    if (CAND) {        // elements arrive in ascending order: the first hit is the smallest
+                                        const uint32_t xv = __shfl_sync(0xffffffffu, xk, src);
+                                        if (((m >> lane) & 1u) && first_x == 0xFFFFFFFFu) first_x = xv;
+                                    }
                                     hit &= hit - 1;
                                 }
                             } else {
@@ -330,6 +346,10 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                                 for (int r = 0; r < 32; r++) {
                                     const unsigned bb = __ballot_sync(0xffffffffu, (mk >> r) & 1u);
                                     if (lane == r) cnt += __popc(bb);
+                                    if (CAND) {
+                                        const uint32_t xv = __shfl_sync(0xffffffffu, xk, bb ? __ffs(bb) - 1 : 0);
+                                        if (lane == r && bb && first_x == 0xFFFFFFFFu) first_x = xv;
+                                    }
                                 }
                             }
                         }
@@ -357,11 +377,40 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
 #endif
                 if (p + 1 < P) {
                     st[lane] = cnt;
+                    if (CAND) st[33 + lane] = first_x;
                     if (lane == 0) st[32] = pos;
                 } else {
                     // ---- epilogue: lane r holds |row r n column c|
-                    const uint32_t i = rb * 32 + lane, j = c;
-                    if (a.mode == KH_MODE_MATRIX) {
+                    const uint32_t i = rb * 32 + lane, j = cid;
+                    if (CAND) {
+                        bool keep = false;
+                        if (i >= a.q0 && i < a.q1 && cnt >= 1u && (!a.lower_only || j < i)) {
+                            const uint32_t s0 = s_len[lane], s1 = clen;
+                            int cmin = a.cmin_fixed;
+                            if (cmin < 0) {   // greedy.cpp:1211-1219, IEEE-exact operations in the host's order
+                                const double t = a.containment
+                                    ? __dmul_rn(a.jmin, (double)min(s0, s1))
+                                    : __ddiv_rn(__dmul_rn(a.jmin, (double)(s0 + s1)), a.one_plus_jmin);
+                                cmin = (int)ceil(t);
+                            }
+                            keep = (long long)cnt + 1 >= (long long)cmin;
+                        }
+                        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+                        if (ballot) {
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)__popc(ballot));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (keep) {
+                                const unsigned long long idx = base + __popc(ballot & ((1u << lane) - 1));
+                                if (idx < a.edge_cap) {
+                                    tc_cand cd; cd.query = i; cd.rep = j; cd.common = cnt; cd.first_hit = first_x;
+                                    a.cands[idx] = cd;
+                                } else {
+                                    a.counters[1] = 1ULL;
+                                }
+                            }
+                        }
+                    } else if (a.mode == KH_MODE_MATRIX) {
                         if (i >= a.i0 && i < a.i1 && j >= a.j0 && j < a.j1)
                             a.out[(size_t)(i - a.i0) * (a.j1 - a.j0) + (j - a.j0)] = cnt;
                     } else {
@@ -474,7 +523,8 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
 {
     static bool attr_set = false;
     if (!attr_set) {
-        TC_CUDA(cudaFuncSetAttribute(k3h_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KH_SMEM));
+        TC_CUDA(cudaFuncSetAttribute(k3h_join_kernel<KH_MODE_EDGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KH_SMEM));
+        TC_CUDA(cudaFuncSetAttribute(k3h_join_kernel<KH_MODE_CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KH_SMEM));
         attr_set = true;
     }
     if (units.empty()) return 0;
@@ -492,14 +542,15 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
     const long long mine = ((long long)units.size() - a.part + a.nparts - 1) / a.nparts;
     if (mine <= 0) { TC_CUDA(cudaStreamSynchronize(ctx->stream)); return 0; }
     const int grid = (int)std::min<long long>(mine, ctx->num_sms);
-    if (!ctx->d_kh_state) TC_CUDA(cudaMalloc(&ctx->d_kh_state, (size_t)ctx->num_sms * KH_CSEG * KH_STATE * 4));
+    if (!ctx->d_kh_state) TC_CUDA(cudaMalloc(&ctx->d_kh_state, (size_t)ctx->num_sms * KH_CSEG * KH_STATE_CAND * 4));
     a.ranks = ctx->d_ranks; a.off = reinterpret_cast<const unsigned long long *>(ctx->d_off); a.size = ctx->d_size;
     a.n = ctx->n; a.pivots = ctx->d_kh_pivots; a.pivoff = ctx->d_kh_pivoff;
     a.units = ctx->d_kh_units; a.nunits = (uint32_t)units.size();
     a.counters = ctx->d_edge_count; a.state = ctx->d_kh_state;
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count + 2, 0, sizeof(unsigned long long), ctx->stream));
     if (ctx->ev_pass0) cudaEventRecord(ctx->ev_pass0, ctx->stream);      // kernel-only duration, tc_last_pass_kernel_ms
-    k3h_join_kernel<<<grid, KH_THREADS, KH_SMEM, ctx->stream>>>(a);
+    if (a.mode == KH_MODE_CAND) k3h_join_kernel<KH_MODE_CAND><<<grid, KH_THREADS, KH_SMEM, ctx->stream>>>(a);
+    else k3h_join_kernel<KH_MODE_EDGES><<<grid, KH_THREADS, KH_SMEM, ctx->stream>>>(a);     // matrix and edge epilogues
     if (ctx->ev_pass1) cudaEventRecord(ctx->ev_pass1, ctx->stream);
     ctx->launches++;
     TC_CUDA(cudaGetLastError());
@@ -537,4 +588,27 @@ int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts,
     a.mode = KH_MODE_EDGES; a.part = part; a.nparts = nparts ? nparts : 1; a.row_min = start_index;
     a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
     return kh_launch(ctx, a, ctx->kh_edge_units, true);
+}
+
+// greedy candidates of the query batch [q0, q1) (q0 multiple of 32) on the hash-join kernel: against the representative
+// table (vs_reps; columns = ctx->d_rep_ids) or against the batch itself (earlier members only).  Appends to
+// ctx->d_cands; tc_cand.first_hit carries the smallest shared RANK (the reference orders `touched` by the first
+// shared query hash, greedy.cpp:1148-1164; ranks are order-preserving, so comparing them is the same order).
+int tc_launch_join_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment, double jmin)
+{
+    const uint32_t ccount = vs_reps ? ctx->nrep : q1, cfirst = vs_reps ? 0u : q0;
+    std::vector<tc_kh_unit> units;
+    for (uint32_t c0 = cfirst; c0 < ccount; c0 += KH_CSEG)
+        for (uint32_t rb = q0 / 32; rb * 32 < q1; rb++) {
+            uint32_t c1 = std::min(ccount, c0 + KH_CSEG);
+            if (!vs_reps) c1 = std::min<uint32_t>(c1, rb * 32 + 31);      // only columns with an id below some row of the block
+            if (c1 > c0) units.push_back(tc_kh_unit{rb, c0, c1});
+        }
+    if (units.empty()) return 0;
+    KHArgs a{};
+    a.mode = KH_MODE_CAND; a.part = 0; a.nparts = 1;
+    a.col_ids = vs_reps ? ctx->d_rep_ids : nullptr; a.q0 = q0; a.q1 = q1;
+    a.cands = ctx->d_cands; a.edge_cap = ctx->cand_cap; a.lower_only = vs_reps ? 0 : 1;
+    a.cmin_fixed = cmin_fixed; a.containment = containment; a.jmin = jmin; a.one_plus_jmin = 1.0 + jmin;
+    return kh_launch(ctx, a, units);
 }

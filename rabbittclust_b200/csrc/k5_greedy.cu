@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 
 namespace {
@@ -212,6 +213,8 @@ static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double thres
     if (const char *s = getenv("TCLUST_GREEDY_BATCH")) batch = (uint32_t)std::max<long>(atol(s), 32);
     batch = (batch + TC_GROUP - 1) / TC_GROUP * TC_GROUP;
 
+    const char *gimpl = getenv("TCLUST_GREEDY_IMPL");
+    const bool use_join = semb_size == 0 && !(gimpl && !strcmp(gimpl, "merge"));
     tc_rep_table_reset(ctx);
     std::vector<int32_t> order_of(n, -1);      // representative creation order, -1 = not a representative
     std::vector<tc_cand> cands;
@@ -223,8 +226,15 @@ static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double thres
     for (uint32_t b0 = 0; b0 < n;) {
         const uint32_t b1 = std::min<uint64_t>(n, (uint64_t)b0 + batch);
         TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), st));
-        if (ctx->nrep > 0 && tc_launch_tiles_cands(ctx, b0, b1, 1, cmin_fixed, containment, jmin, 0, 1, semb_size)) return 1;
-        if (tc_launch_tiles_cands(ctx, b0, b1, 0, cmin_fixed, containment, jmin, 0, 1, semb_size)) return 1;
+        // candidates: the hash-join kernel (first_hit = smallest shared rank, same `touched` order), except for the
+        // semantic-B counts of the brute-force rule, which need the ordered merge (TCLUST_GREEDY_IMPL=merge forces it)
+        if (use_join) {
+            if (ctx->nrep > 0 && tc_launch_join_cands(ctx, b0, b1, 1, cmin_fixed, containment, jmin)) return 1;
+            if (tc_launch_join_cands(ctx, b0, b1, 0, cmin_fixed, containment, jmin)) return 1;
+        } else {
+            if (ctx->nrep > 0 && tc_launch_tiles_cands(ctx, b0, b1, 1, cmin_fixed, containment, jmin, 0, 1, semb_size)) return 1;
+            if (tc_launch_tiles_cands(ctx, b0, b1, 0, cmin_fixed, containment, jmin, 0, 1, semb_size)) return 1;
+        }
         unsigned long long cnt[2];
         TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, st));
         TC_CUDA(cudaStreamSynchronize(st));

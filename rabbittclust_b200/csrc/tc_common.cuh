@@ -110,6 +110,7 @@ int tc_launch_tiles_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, in
 // hash-join pass (k3h_join.cu)
 int tc_kh_prepare(tc_ctx *ctx);
 int tc_launch_join_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
+int tc_launch_join_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment, double jmin);
 int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index = 0);
 // representative table (k5_greedy.cu)
 void tc_rep_table_free(tc_ctx *ctx);
