@@ -11,15 +11,17 @@
 //   * hash = MurmurHash3_x64_128(k ASCII bytes of that strand, seed)[0];
 //   * sketch = the s smallest DISTINCT hashes, ascending.
 //
-// Design (DESIGN.md "K1"): the path is integer-ALU bound (~125 INT32 ops per k-mer), not
-// HBM bound.  A genome is cut into segments of whole windows; one CTA sketches one segment:
-// every thread walks its own contiguous run of windows with the two strands kept as
-// big-endian ASCII words in registers (shift one byte per base), so the memcmp is a
-// multi-word integer compare and there is no special path for non-ACGT bytes.  Hashes not
-// above the running threshold tau (the s-th smallest distinct hash seen so far) are appended
-// to a shared-memory candidate buffer which is sorted/deduplicated/truncated (bitonic) when
-// it fills; tau is shared between the segments of a genome through a global atomicMin.  A
-// second kernel merges the per-segment partial sketches of each genome.
+// Design (DESIGN.md "K1"): the path is integer-issue bound (Murmur3 = ten 64-bit multiplies per k-mer), not
+// HBM bound.  A genome is cut into segments of whole windows; one CTA sketches one segment: every thread
+// walks its own contiguous run of windows with the next 8*(NW+1) bases held in registers twice -- as read
+// (forward strand, already the little-endian word layout Murmur3 consumes) and complemented + shifted so
+// that the reverse-complement k-mer, read backwards, is a byte range whose words compare like memcmp (see
+// the comment on k1_sketch_segment_kernel).  There is no special path for non-ACGT bytes.  Hashes not
+// above the running threshold tau (the s-th smallest distinct hash seen so far) are appended to a
+// shared-memory candidate buffer which is sorted/deduplicated/truncated (bitonic) when it fills; tau is
+// shared between the segments of a genome through a global atomicMin.  A second kernel merges the
+// per-segment partial sketches of each genome (prefixes cut at tau, compaction on overflow).  The host
+// entry point pipelines batches of genomes over two staging slots (H2D of batch c+1 under the kernels of c).
 #include "tc_common.cuh"
 #include "k_sort.cuh"
 #include <algorithm>

@@ -10,17 +10,21 @@
 // Design (DESIGN.md "K3H"):
 //  * a work unit is a row block of 32 sketches x a segment of up to 4096 column sketches.  One persistent
 //    CTA (1024 threads) per SM takes units from an atomic counter; unit u belongs to rank u % nparts.
-//  * the 32 row sketches are cut into P value ranges ("partitions") of at most ~8000 elements each
-//    (pivots = equal-count quantiles of the row block, computed once per upload by k3h_pivot_kernel).
-//    Per partition the CTA builds, in shared memory, an open-addressing table  rank -> 32-bit mask of the
-//    row sketches that contain it  (16384 slots, load <= 0.5) plus a 128-Kbit presence filter.
-//  * the column sketches stream through the table: one warp per column, 32 consecutive elements per step
-//    (one coalesced 128-byte load from the row-major u32 ranks); a lane whose element misses the presence
-//    filter is done after one LDS; hits fetch the mask from the table.  Lane r accumulates count(row r,
-//    column): masks are redistributed with shuffles (few hits) or 32 ballots (many hits).
-//  * between partitions the per-column state (32 counts + stream position) lives in a per-CTA scratch in
-//    global memory (4096 x 33 words = 540 KB per CTA, L2 resident); after the last partition the epilogue
-//    emits the candidate edge / matrix cell.
+//  * per unit the CTA builds, in shared memory, an open-addressing table  rank -> 32-bit mask of the row
+//    sketches that contain it  (16384 slots, at most 10688 DISTINCT ranks per build) plus a 64 KB blocked-Bloom
+//    presence filter (2 bits per key in one word, stored inverted).  A row block with more distinct ranks is cut
+//    into P value ranges ("partitions"); k3h_distinct_kernel sizes P and the pivots from the distinct count once
+//    per upload (32 related sketches share most ranks: P = 1), k3h_pivot_kernel is the fall-back for row blocks
+//    too large to sort in shared memory.
+//  * the column sketches stream through the table: one warp per column, 128 elements per step (4 coalesced
+//    128-byte loads from the row-major u32 ranks, next step prefetched); a lane whose element misses the
+//    presence filter is done after one LDS; hits fetch the mask from the table.  Lane r accumulates
+//    count(row r, column): masks are redistributed with shuffles (few hits) or 32 ballots (many hits).
+//  * between partitions the per-column state (32 counts + stream position; candidate mode: + 32 first shared
+//    ranks) lives in a per-CTA scratch in global memory (L2 resident); after the last partition the epilogue
+//    emits the candidate edge / matrix cell / greedy candidate.
+//  * candidate mode (greedy scan, K5): columns are streamed through an id indirection (the representative
+//    table), rows are restricted to the query batch.
 //  Units are ordered segment-major, so at any moment all CTAs stream the same 16 MB of column data: the
 //  column stream is served by L2, not HBM.
 #include "tc_common.cuh"
@@ -283,8 +287,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
 #pragma unroll
                 for (int k = 0; k < 4; k++) xa[k] = (lane + 32 * k < rem) ? __ldg(pc + 32 * k) : 0xFFFFFFFFu;
                 // one step = the 128 elements in x; xn receives the next step's elements (loads issued before the
-                // probes).  Returns false when the partition ends inside this step.  Instantiated twice with the
-                // two register sets swapped, so the hand-over of xn to x costs no moves.
+                // probes).  Returns false when the partition ends inside this step.
                 auto step = [&](uint32_t (&x)[4], uint32_t (&xn)[4]) -> bool {
                     if (rem >= 256u) {                       // warp-uniform: the whole next step is in bounds
 #pragma unroll
@@ -363,18 +366,13 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                     for (int k = 0; k < 4; k++) pos += __popc(__ballot_sync(0xffffffffu, x[k] < piv_hi));
                     return false;
                 };
-#ifdef KH_PINGPONG
-                for (;;) {
-                    if (!step(xa, xb)) break;
-                    if (!step(xb, xa)) break;
-                }
-#else
+                // (instantiating the step twice with the register sets swapped saves the four moves but doubles the
+                // loop body; measured 3 % slower)
                 for (;;) {
                     if (!step(xa, xb)) break;
 #pragma unroll
                     for (int k = 0; k < 4; k++) xa[k] = xb[k];
                 }
-#endif
                 if (p + 1 < P) {
                     st[lane] = cnt;
                     if (CAND) st[33 + lane] = first_x;
