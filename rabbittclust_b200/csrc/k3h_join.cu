@@ -67,6 +67,8 @@ struct KHArgs {
     // common + 1 >= common_min(pair)  -- the rule of k3_tile.cu's candidate mode
     const uint32_t *col_ids; uint32_t q0, q1;
     tc_cand *cands; int lower_only, cmin_fixed, containment; double jmin, one_plus_jmin;
+    // block join (K3J): union lists of the 32-sketch column blocks
+    const uint32_t *bu_keys, *bu_mask, *bu_count;
 };
 
 // presence filter: word = top (KH_FBITS-5) bits of h = x * golden, the two bit positions = low 10 bits of h
@@ -132,10 +134,12 @@ __global__ void k3h_pivot_kernel(const uint32_t *ranks, const unsigned long long
 // out[rb*7] = D (0xFFFFFFFF: block too large, the multiset-quantile kernel above takes over), out[rb*7+1..6] =
 // candidates for (P,q) = (2,1) (3,1) (3,2) (4,1) (4,2) (4,3).
 __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint32_t *ranks, const unsigned long long *off,
-                                                                      const uint32_t *size, uint32_t n, uint32_t *out)
+                                                                      const uint32_t *size, uint32_t n, uint32_t *out,
+                                                                      uint32_t *ukeys, uint32_t *umask)
 {
     extern __shared__ __align__(16) uint8_t kh_smem[];
     uint32_t *buf = reinterpret_cast<uint32_t *>(kh_smem);
+    uint8_t *rowof = kh_smem + (size_t)KH_SORT_CAP * 4;          // which of the 32 sketches an element came from
     __shared__ uint32_t s_pos[33], s_warp[32], s_d;
     const uint32_t rb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -152,8 +156,8 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint3
         const uint32_t id = rb * 32 + warp;
         const uint32_t len = id < n ? size[id] : 0u;
         const uint32_t *row = ranks + (id < n ? off[id] : 0ULL);
-        for (uint32_t e = lane; e < len; e += 32) buf[s_pos[warp] + e] = __ldg(row + e);
-        for (uint32_t e = total + tid; e < npad; e += KH_THREADS) buf[e] = 0xFFFFFFFFu;
+        for (uint32_t e = lane; e < len; e += 32) { buf[s_pos[warp] + e] = __ldg(row + e); rowof[s_pos[warp] + e] = (uint8_t)warp; }
+        for (uint32_t e = total + tid; e < npad; e += KH_THREADS) { buf[e] = 0xFFFFFFFFu; rowof[e] = 0; }
     }
     __syncthreads();
     for (uint32_t sz = 2; sz <= npad; sz <<= 1)
@@ -161,7 +165,10 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint3
             for (uint32_t t = tid; t < (npad >> 1); t += KH_THREADS) {
                 const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
                 const uint32_t x = buf[lo], y = buf[hi];
-                if ((x > y) == ((lo & sz) == 0)) { buf[lo] = y; buf[hi] = x; }
+                if ((x > y) == ((lo & sz) == 0)) {
+                    buf[lo] = y; buf[hi] = x;
+                    const uint8_t rx = rowof[lo]; rowof[lo] = rowof[hi]; rowof[hi] = rx;
+                }
             }
             __syncthreads();
         }
@@ -189,10 +196,20 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint3
     want[1] = (uint32_t)((unsigned long long)D * 1 / 3); want[2] = (uint32_t)((unsigned long long)D * 2 / 3);
     want[3] = (uint32_t)((unsigned long long)D * 1 / 4); want[4] = (uint32_t)((unsigned long long)D * 2 / 4);
     want[5] = (uint32_t)((unsigned long long)D * 3 / 4);
+    // union list of the block (K3J): distinct key d -> (key, mask of the sketches that hold it), ascending, stored at
+    // the element offset of the block's first sketch (a block never has more distinct keys than elements)
+    const unsigned long long base = rb * 32 < n ? off[rb * 32] : 0ULL;
     for (uint32_t i = b0; i < b0 + c; i++) {
         if (i < total && (i == 0 || buf[i] != buf[i - 1])) {
 #pragma unroll
             for (int q = 0; q < 6; q++) if (before == want[q]) out[rb * KH_DREC + 1 + q] = buf[i];
+            if (ukeys) {
+                const uint32_t key = buf[i];
+                uint32_t m = 0;
+                for (uint32_t j = i; j < total && buf[j] == key; j++) m |= 1u << rowof[j];
+                ukeys[base + before] = key;
+                umask[base + before] = m;
+            }
             before++;
         }
     }
@@ -446,6 +463,242 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
 
 }  // namespace
 
+// =====================================================================================================
+// K3J  k3j_block_kernel -- the dense pass as a join of 32-sketch BLOCKS on both sides.
+//
+// K3H streams every column sketch through the row block's table on its own: each (column, partition) visit has a
+// fixed cost, a partition slice of one sketch is only ~2.5 steps long, and 32 related columns probe the same keys 32
+// times.  Here the column side is a block as well: k3h_distinct_kernel leaves, per block of 32 sketches, the sorted
+// list of its DISTINCT ranks with a 32-bit mask of the member sketches that hold each.  A warp takes a (row block x
+// column block) tile, streams that one list (9,000 keys for 32 related sketches, 32,000 for unrelated ones, instead of
+// 32 x 1,000) through the table, and on a hit adds 1 to count[r][c] for every r in the row mask and c in the column
+// mask.  The 32 x 32 counters of the tile are u16 in shared memory (2 KB per warp); hits are rare outside related
+// tiles, and a tile without any hit skips its epilogue.  Partition slices of a sorted list are index ranges, so there
+// is no per-column stream state; with P > 1 partitions the tile's counters are parked in the per-CTA scratch.
+// Column blocks too large for a union list (bu_count = 0xFFFFFFFF) are routed to K3H by the host.
+constexpr uint32_t KJ_FBITS = 18;                                   // 32 KB presence filter (64 KB go to the counters)
+constexpr uint32_t KJ_FWORDS = (1u << KJ_FBITS) / 32;
+constexpr uint32_t KJ_TILE_WORDS = 512;                             // 32 x 32 u16 counters
+constexpr uint32_t KJ_TILE_STATE = KJ_TILE_WORDS + 1;               // + "tile had a hit" flag
+constexpr size_t KJ_SMEM = (size_t)KH_SLOTS * 8 + (size_t)KJ_FWORDS * 4 + (size_t)32 * KJ_TILE_WORDS * 4;
+static_assert(KJ_SMEM <= 227 * 1024 - 1024, "K3J shared memory");
+static_assert((KH_CSEG / 32) * KJ_TILE_STATE <= KH_CSEG * KH_STATE_CAND, "K3J tile state fits the per-CTA scratch");
+
+__device__ __forceinline__ uint32_t kj_fword(uint32_t h) { return h >> (32 - (KJ_FBITS - 5)); }
+
+__global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a)
+{
+    extern __shared__ __align__(16) uint8_t kh_smem[];
+    uint2 *table = reinterpret_cast<uint2 *>(kh_smem);
+    uint32_t *filter = reinterpret_cast<uint32_t *>(kh_smem + (size_t)KH_SLOTS * 8);
+    uint32_t *cnt_all = filter + KJ_FWORDS;
+    __shared__ uint32_t s_unit, s_next;
+    __shared__ uint32_t s_lo[32], s_hi[32], s_len[32];
+    __shared__ unsigned long long s_base[32];
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint32_t lane = tid & 31;
+    asm volatile("" : "+r"(lane));
+    uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(table);
+    asm volatile("" : "+r"(tab_addr));
+    uint32_t filt_addr = (uint32_t)__cvta_generic_to_shared(filter);
+    asm volatile("" : "+r"(filt_addr));
+    uint32_t *cntw = cnt_all + warp * KJ_TILE_WORDS;                  // this warp's tile counters, as 512 words
+    uint16_t *cnt = reinterpret_cast<uint16_t *>(cntw);              // cnt[r * 32 + c]
+    uint32_t *state = a.state + (size_t)blockIdx.x * KH_CSEG * KH_STATE_CAND;
+
+    for (;;) {
+        if (tid == 0) s_unit = (uint32_t)(atomicAdd(&a.counters[2], 1ULL) * a.nparts + a.part);
+        __syncthreads();
+        const uint32_t u = s_unit;
+        if (u >= a.nunits) break;
+        const tc_kh_unit unit = a.units[u];
+        const uint32_t rb = unit.rb, c0 = unit.c0, c1 = unit.c1;      // c0 is a multiple of 32
+        const uint32_t piv0 = a.pivoff[rb];
+        const uint32_t P = a.pivoff[rb + 1] - piv0 + 1;
+        if (tid < 32) {
+            const uint32_t id = rb * 32 + tid;
+            s_len[tid] = id < a.n ? a.size[id] : 0u;
+            s_base[tid] = id < a.n ? a.off[id] : 0ULL;
+            s_lo[tid] = 0;
+        }
+        __syncthreads();
+
+        for (uint32_t p = 0; p < P; p++) {
+            const uint32_t piv_lo = p == 0 ? 0u : a.pivots[piv0 + p - 1];
+            const uint32_t piv_hi = (p + 1 == P) ? 0xFFFFFFFFu : a.pivots[piv0 + p];
+            {   // clear table + filter, find this partition's end in every row
+                uint4 *t4 = reinterpret_cast<uint4 *>(kh_smem);
+                const uint4 e = make_uint4(KH_EMPTY, 0u, KH_EMPTY, 0u);
+                for (uint32_t i = tid; i < KH_SLOTS / 2; i += KH_THREADS) t4[i] = e;
+                for (uint32_t i = tid; i < KJ_FWORDS; i += KH_THREADS) filter[i] = 0xFFFFFFFFu;   // inverted: 0 = present
+                if (tid < 32) {
+                    const uint32_t *row = a.ranks + s_base[tid];
+                    s_hi[tid] = (p + 1 == P) ? s_len[tid] : kh_lower_bound(row, s_lo[tid], s_len[tid], piv_hi);
+                }
+                if (tid == 0) s_next = c0 / 32;
+            }
+            __syncthreads();
+            {   // build: warp w inserts the partition's elements of row w
+                const uint32_t *row = a.ranks + s_base[warp];
+                const uint32_t bit = 1u << warp;
+                for (uint32_t e = s_lo[warp] + lane; e < s_hi[warp]; e += 32) {
+                    const uint32_t x = __ldg(row + e);
+                    const uint32_t h = x * 0x9E3779B1u;
+                    atomicAnd(&filter[kj_fword(h)], ~kh_fmask(h));
+                    uint32_t slot = kh_slot(x);
+                    for (;;) {
+                        const uint32_t old = atomicCAS(&table[slot].x, KH_EMPTY, x);
+                        if (old == KH_EMPTY || old == x) { atomicOr(&table[slot].y, bit); break; }
+                        slot = (slot + 1) & (KH_SLOTS - 1);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- tiles: one warp per column block
+            for (;;) {
+                uint32_t cb = 0;
+                if (lane == 0) cb = atomicAdd(&s_next, 1u);
+                cb = __shfl_sync(0xffffffffu, cb, 0);
+                if (cb * 32 >= c1) break;
+                const uint32_t D = a.bu_count[cb * KH_DREC];
+                const unsigned long long lbase = a.off[cb * 32];
+                const uint32_t *keys = a.bu_keys + lbase, *cmasks = a.bu_mask + lbase;
+                uint32_t lo = 0, hi = D;
+                if (P > 1) {
+                    lo = p == 0 ? 0u : kh_lower_bound(keys, 0, D, piv_lo);
+                    hi = (p + 1 == P) ? D : kh_lower_bound(keys, lo, D, piv_hi);
+                }
+                uint32_t *tst = state + (size_t)(cb - c0 / 32) * KJ_TILE_STATE;
+                uint32_t anyhit = p == 0 ? 0u : tst[KJ_TILE_WORDS];
+                if (anyhit) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) cntw[lane + 32 * q] = tst[lane + 32 * q];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) cntw[lane + 32 * q] = 0u;
+                }
+                __syncwarp();
+                if (hi > lo) {
+                    uint32_t pos = lo, rem = hi - lo;
+                    const uint32_t *pc = keys + lo + lane;
+                    uint32_t x[4], xn[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) x[k] = (lane + 32 * k < rem) ? __ldg(pc + 32 * k) : 0xFFFFFFFFu;
+                    for (;;) {
+                        if (rem >= 256u) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) xn[k] = __ldg(pc + 128 + 32 * k);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) xn[k] = (lane + 128 + 32 * k < rem) ? __ldg(pc + 128 + 32 * k) : 0xFFFFFFFFu;
+                        }
+                        uint32_t fw[4], fm[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t h = x[k] * 0x9E3779B1u;
+                            fw[k] = kh_lds(filt_addr + ((h >> (30 - KJ_FBITS + 5)) & ((KJ_FWORDS - 1) << 2)));
+                            fm[k] = kh_fmask(h);
+                        }
+                        bool maybe = false;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            fw[k] = (fm[k] & fw[k]) == 0u;          // filter words are stored inverted
+                            maybe |= fw[k] != 0u;
+                        }
+                        uint32_t mask[4] = {0u, 0u, 0u, 0u};
+                        if (maybe) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                if (fw[k]) {
+                                    uint32_t slot = kh_slot(x[k]);
+                                    for (;;) {
+                                        const uint2 e = kh_lds2(tab_addr + slot * 8);
+                                        if (e.x == x[k]) { mask[k] = e.y; break; }
+                                        if (e.x == KH_EMPTY) break;
+                                        slot = (slot + 1) & (KH_SLOTS - 1);
+                                    }
+                                }
+                            }
+                        }
+                        if (__ballot_sync(0xffffffffu, (mask[0] | mask[1] | mask[2] | mask[3]) != 0u)) {
+                            anyhit = 1u;
+#pragma unroll 1
+                            for (int k = 0; k < 4; k++) {
+                                const uint32_t mk = k == 0 ? mask[0] : k == 1 ? mask[1] : k == 2 ? mask[2] : mask[3];
+                                unsigned hit = __ballot_sync(0xffffffffu, mk != 0u);
+                                while (hit) {
+                                    const int src = __ffs(hit) - 1;
+                                    uint32_t rm = __shfl_sync(0xffffffffu, mk, src);              // rows that hold the key
+                                    const uint32_t cm = __ldg(cmasks + pos + src + 32 * k);      // columns that hold it
+                                    const bool mine = (cm >> lane) & 1u;                          // lane = column
+                                    while (rm) {
+                                        const int r = __ffs(rm) - 1;
+                                        if (mine) cnt[r * 32 + lane]++;
+                                        rm &= rm - 1;
+                                    }
+                                    hit &= hit - 1;
+                                }
+                            }
+                        }
+                        if (rem <= 128u) break;
+                        pos += 128; pc += 128; rem -= 128;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) x[k] = xn[k];
+                    }
+                }
+                __syncwarp();
+                if (p + 1 < P) {
+                    if (lane == 0) tst[KJ_TILE_WORDS] = anyhit;
+                    if (anyhit) {
+#pragma unroll
+                        for (int q = 0; q < 16; q++) tst[lane + 32 * q] = cntw[lane + 32 * q];
+                    }
+                } else if (a.mode == KH_MODE_MATRIX) {
+                    const uint32_t j = cb * 32 + lane;
+                    for (uint32_t r = 0; r < 32; r++) {
+                        const uint32_t i = rb * 32 + r;
+                        if (i >= a.i0 && i < a.i1 && j >= a.j0 && j < a.j1)
+                            a.out[(size_t)(i - a.i0) * (a.j1 - a.j0) + (j - a.j0)] = anyhit ? (uint32_t)cnt[r * 32 + lane] : 0u;
+                    }
+                } else if (anyhit) {
+                    const uint32_t j = cb * 32 + lane;
+                    const uint32_t s1 = j < a.n ? a.size[j] : 0u;
+                    for (uint32_t r = 0; r < 32; r++) {
+                        const uint32_t i = rb * 32 + r;
+                        const uint32_t c = cnt[r * 32 + lane];
+                        bool keep = false;
+                        if (c >= 1u && i < a.n && i >= a.row_min && j < i) {
+                            const uint32_t s0 = s_len[r];
+                            const uint32_t mn = min(s0, s1), mx = max(s0, s1);
+                            keep = mn > 0 && !((long long)mx > (long long)a.radio * (long long)mn);   // MST.cpp:1481-1487
+                        }
+                        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+                        if (ballot) {
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)__popc(ballot));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (keep) {
+                                const unsigned long long idx = base + __popc(ballot & ((1u << lane) - 1));
+                                if (idx < a.edge_cap) {
+                                    tc_pair e; e.i = i; e.j = j; e.common = c;
+                                    a.edges[idx] = e;
+                                } else {
+                                    a.counters[1] = 1ULL;
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            if (tid < 32) s_lo[tid] = s_hi[tid];
+        }
+        __syncthreads();
+    }
+}
+
 // ---- per-upload setup: partition pivots of every row block
 int tc_kh_prepare(tc_ctx *ctx)
 {
@@ -459,11 +712,20 @@ int tc_kh_prepare(tc_ctx *ctx)
     TC_CUDA(cudaMemsetAsync(d_dist, 0, (size_t)nrb * KH_DREC * 4, st));
     static bool attr_set = false;
     if (!attr_set) {
-        TC_CUDA(cudaFuncSetAttribute(k3h_distinct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KH_SORT_CAP * 4)));
+        TC_CUDA(cudaFuncSetAttribute(k3h_distinct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KH_SORT_CAP * 5)));
         attr_set = true;
     }
-    k3h_distinct_kernel<<<nrb, KH_THREADS, KH_SORT_CAP * 4, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
-                                                                 ctx->d_size, ctx->n, d_dist);
+    // union lists of the 32-sketch blocks (K3J): as many slots as elements
+    if (ctx->total + 1 > ctx->cap_bu) {
+        cudaFree(ctx->d_bu_keys); cudaFree(ctx->d_bu_mask);
+        ctx->d_bu_keys = nullptr; ctx->d_bu_mask = nullptr; ctx->cap_bu = 0;
+        if (cudaMalloc(&ctx->d_bu_keys, (ctx->total + 1) * 4) != cudaSuccess || cudaMalloc(&ctx->d_bu_mask, (ctx->total + 1) * 4) != cudaSuccess) {
+            cudaFree(d_dist); tc_set_error("tc_kh_prepare: out of device memory for the block union lists"); return 1;
+        }
+        ctx->cap_bu = ctx->total + 1;
+    }
+    k3h_distinct_kernel<<<nrb, KH_THREADS, KH_SORT_CAP * 5, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
+                                                                 ctx->d_size, ctx->n, d_dist, ctx->d_bu_keys, ctx->d_bu_mask);
     ctx->launches++;
     std::vector<uint32_t> dist((size_t)nrb * KH_DREC);
     cudaError_t e = cudaGetLastError();
@@ -492,6 +754,8 @@ int tc_kh_prepare(tc_ctx *ctx)
         const uint32_t first = P == 2 ? 1 : P == 3 ? 2 : 4;
         for (uint32_t q = 0; q + 1 < P; q++) piv[pivoff[rb] + q] = d[first + q];
     }
+    ctx->bu_count.assign(nrb, 0xFFFFFFFFu);
+    for (uint32_t rb = 0; rb < nrb; rb++) ctx->bu_count[rb] = dist[(size_t)rb * KH_DREC];
     int rc = 1;
     do {
         if (cudaMalloc(&ctx->d_kh_pivoff, (size_t)(nrb + 1) * 4) != cudaSuccess ||
@@ -511,18 +775,21 @@ int tc_kh_prepare(tc_ctx *ctx)
         }
         rc = 0;
     } while (0);
-    cudaFree(d_dist);
+    cudaFree(ctx->d_bu_count);
+    ctx->d_bu_count = d_dist;              // [rb * KH_DREC] = distinct count of block rb (0xFFFFFFFF: no union list)
     return rc;
 }
 
 // edge_list: `units` is ctx->kh_edge_units, which stays resident on the device between passes (no per-pass copy
 // from pageable host memory in front of the kernel)
-static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &units, bool edge_list = false)
+static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &units, bool edge_list = false,
+                     bool block_kernel = false)
 {
     static bool attr_set = false;
     if (!attr_set) {
         TC_CUDA(cudaFuncSetAttribute(k3h_join_kernel<KH_MODE_EDGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KH_SMEM));
         TC_CUDA(cudaFuncSetAttribute(k3h_join_kernel<KH_MODE_CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KH_SMEM));
+        TC_CUDA(cudaFuncSetAttribute(k3j_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KJ_SMEM));
         attr_set = true;
     }
     if (units.empty()) return 0;
@@ -545,9 +812,11 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
     a.n = ctx->n; a.pivots = ctx->d_kh_pivots; a.pivoff = ctx->d_kh_pivoff;
     a.units = ctx->d_kh_units; a.nunits = (uint32_t)units.size();
     a.counters = ctx->d_edge_count; a.state = ctx->d_kh_state;
+    a.bu_keys = ctx->d_bu_keys; a.bu_mask = ctx->d_bu_mask; a.bu_count = ctx->d_bu_count;
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count + 2, 0, sizeof(unsigned long long), ctx->stream));
     if (ctx->ev_pass0) cudaEventRecord(ctx->ev_pass0, ctx->stream);      // kernel-only duration, tc_last_pass_kernel_ms
-    if (a.mode == KH_MODE_CAND) k3h_join_kernel<KH_MODE_CAND><<<grid, KH_THREADS, KH_SMEM, ctx->stream>>>(a);
+    if (block_kernel) k3j_block_kernel<<<grid, KH_THREADS, KJ_SMEM, ctx->stream>>>(a);
+    else if (a.mode == KH_MODE_CAND) k3h_join_kernel<KH_MODE_CAND><<<grid, KH_THREADS, KH_SMEM, ctx->stream>>>(a);
     else k3h_join_kernel<KH_MODE_EDGES><<<grid, KH_THREADS, KH_SMEM, ctx->stream>>>(a);     // matrix and edge epilogues
     if (ctx->ev_pass1) cudaEventRecord(ctx->ev_pass1, ctx->stream);
     ctx->launches++;
@@ -609,4 +878,53 @@ int tc_launch_join_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int
     a.cands = ctx->d_cands; a.edge_cap = ctx->cand_cap; a.lower_only = vs_reps ? 0 : 1;
     a.cmin_fixed = cmin_fixed; a.containment = containment; a.jmin = jmin; a.one_plus_jmin = 1.0 + jmin;
     return kh_launch(ctx, a, units);
+}
+
+// ---- K3J launchers.  A unit goes to the block kernel when every column block it touches has a union list; the rest
+// (blocks whose 32 sketches hold more than KH_SORT_CAP elements) stays on K3H.
+static bool kj_unit_listed(const tc_ctx *ctx, const tc_kh_unit &u)
+{
+    for (uint32_t cb = u.c0 / 32; cb * 32 < u.c1; cb++)
+        if (cb >= ctx->bu_count.size() || ctx->bu_count[cb] == 0xFFFFFFFFu) return false;
+    return true;
+}
+
+int tc_launch_blockjoin_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out)
+{
+    std::vector<tc_kh_unit> blk, old;
+    for (uint32_t c0 = j0 / 32 * 32; c0 < j1; c0 += KH_CSEG)
+        for (uint32_t rb = i0 / 32; rb * 32 < i1; rb++) {
+            const tc_kh_unit u{rb, c0, std::min(j1, c0 + KH_CSEG)};
+            (kj_unit_listed(ctx, u) ? blk : old).push_back(u);
+        }
+    KHArgs a{};
+    a.mode = KH_MODE_MATRIX; a.part = 0; a.nparts = 1;
+    a.out = d_out; a.i0 = i0; a.i1 = i1; a.j0 = j0; a.j1 = j1;
+    if (kh_launch(ctx, a, blk, false, true)) return 1;
+    for (tc_kh_unit &u : old) u.c0 = std::max(u.c0, j0);
+    return kh_launch(ctx, a, old);
+}
+
+int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index)
+{
+    const uint32_t n = ctx->n, nrb = (n + 31) / 32;
+    // the unit list of K3H (also what tc_allpairs_pass counts pairs from), split by kernel
+    if (ctx->kh_edge_units_n != n || ctx->kh_edge_units_start != start_index) {
+        ctx->kh_edge_units.clear();
+        for (uint32_t c0 = 0; c0 < n; c0 += KH_CSEG)
+            for (uint32_t rb = std::max(c0 / 32, start_index / 32); rb < nrb; rb++) {
+                const uint32_t c1 = std::min<uint32_t>(std::min(n, c0 + KH_CSEG), rb * 32 + 31);
+                if (c1 > c0) ctx->kh_edge_units.push_back(tc_kh_unit{rb, c0, c1});
+            }
+        ctx->kh_edge_units_n = n; ctx->kh_edge_units_start = start_index;
+        ctx->kh_units_on_device = false;
+    }
+    std::vector<tc_kh_unit> blk, old;
+    for (size_t u = part; u < ctx->kh_edge_units.size(); u += (nparts ? nparts : 1))
+        (kj_unit_listed(ctx, ctx->kh_edge_units[u]) ? blk : old).push_back(ctx->kh_edge_units[u]);
+    KHArgs a{};
+    a.mode = KH_MODE_EDGES; a.part = 0; a.nparts = 1; a.row_min = start_index;   // the lists already hold this part only
+    a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
+    if (kh_launch(ctx, a, blk, false, true)) return 1;
+    return kh_launch(ctx, a, old);
 }

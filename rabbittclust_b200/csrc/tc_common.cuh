@@ -78,6 +78,11 @@ struct tc_ctx {
     std::vector<tc_kh_unit> kh_edge_units;
     uint32_t kh_edge_units_n = 0, kh_edge_units_start = 0;
     bool kh_units_on_device = false;     // d_kh_units currently holds kh_edge_units
+    // K3J block join: per 32-sketch block the sorted distinct ranks + 32-bit membership masks, stored at the element
+    // offset of the block's first sketch; bu_count[b] = number of distinct ranks (0xFFFFFFFF: block too large, no list)
+    uint32_t *d_bu_keys = nullptr, *d_bu_mask = nullptr, *d_bu_count = nullptr;
+    uint64_t cap_bu = 0;
+    std::vector<uint32_t> bu_count;
 
     // KSSD shuffled_dim table (K2), resident once uploaded
     int32_t *d_kssd_dim = nullptr;
@@ -110,6 +115,8 @@ int tc_launch_tiles_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, in
 // hash-join pass (k3h_join.cu)
 int tc_kh_prepare(tc_ctx *ctx);
 int tc_launch_join_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
+int tc_launch_blockjoin_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
+int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index);
 int tc_launch_join_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment, double jmin);
 int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index = 0);
 // representative table (k5_greedy.cu)

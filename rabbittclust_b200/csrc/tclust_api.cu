@@ -74,6 +74,8 @@ static void release_sketches(tc_ctx *ctx)
     cudaFree(ctx->d_hashes); cudaFree(ctx->d_off); cudaFree(ctx->d_size); cudaFree(ctx->d_ranks);
     cudaFree(ctx->d_gt); cudaFree(ctx->d_goff); cudaFree(ctx->d_edges); cudaFree(ctx->d_comp);
     cudaFree(ctx->d_kh_pivots); cudaFree(ctx->d_kh_pivoff);
+    cudaFree(ctx->d_bu_keys); cudaFree(ctx->d_bu_mask); cudaFree(ctx->d_bu_count);
+    ctx->d_bu_keys = nullptr; ctx->d_bu_mask = nullptr; ctx->d_bu_count = nullptr; ctx->cap_bu = 0;
     ctx->d_kh_pivots = nullptr; ctx->d_kh_pivoff = nullptr;
     ctx->d_hashes = nullptr; ctx->d_off = nullptr; ctx->d_size = nullptr; ctx->d_ranks = nullptr;
     ctx->d_gt = nullptr; ctx->d_goff = nullptr; ctx->d_edges = nullptr; ctx->d_comp = nullptr;
@@ -330,6 +332,7 @@ extern "C" int tc_pair_common(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0
     TC_CUDA(cudaMalloc(&d_out, cells * 4));
     int rc = impl == 0 ? tc_launch_tiles_matrix(ctx, i0, i1, j0, j1, d_out)
            : impl == 2 ? tc_launch_join_matrix(ctx, i0, i1, j0, j1, d_out)
+           : impl == 3 ? tc_launch_blockjoin_matrix(ctx, i0, i1, j0, j1, d_out)
                        : tc_launch_pair_common_ref(ctx, i0, i1, j0, j1, d_out);
     if (!rc) {
         cudaError_t e = cudaMemcpyAsync(out, d_out, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -416,7 +419,10 @@ static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32
     ctx->edges_semb_size = semb_size;
     unsigned long long cnt[2] = {0, 0};
     for (int attempt = 0;; attempt++) {
-        if (use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts, semb_size) : tc_launch_join_edges(ctx, radio, part, nparts, start_index)) return 1;
+            const bool use_block = !use_merge && impl && !strcmp(impl, "blockjoin");
+        if (use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts, semb_size)
+            : use_block ? tc_launch_blockjoin_edges(ctx, radio, part, nparts, start_index)
+                        : tc_launch_join_edges(ctx, radio, part, nparts, start_index)) return 1;
         TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
         TC_CUDA(cudaStreamSynchronize(ctx->stream));
         if (cnt[1] == 0 && cnt[0] <= ctx->edge_cap) break;

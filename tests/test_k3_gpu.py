@@ -15,9 +15,11 @@ def _check_matrix(ctx, oracle, sketches):
     got_ref = ctx.pair_common(0, n, 0, n, impl=1)
     got = ctx.pair_common(0, n, 0, n, impl=0)
     got_join = ctx.pair_common(0, n, 0, n, impl=2)
+    got_block = ctx.pair_common(0, n, 0, n, impl=3)
     assert np.array_equal(got_ref, want), "u64 global-merge kernel differs from oracle"
     assert np.array_equal(got, want), "tiled merge kernel differs from oracle"
     assert np.array_equal(got_join, want), "hash-join kernel differs from oracle"
+    assert np.array_equal(got_block, want), "block-join kernel differs from oracle"
 
 
 def test_common_fixed_size(ctx, oracle):
@@ -50,7 +52,7 @@ def test_common_subrange(ctx, oracle):
     sk = synth.family_sketches(4, 25, s=500, seed=11)
     ctx.upload(sk)
     want = oracle.common_matrix(sk)
-    for impl in (0, 2):
+    for impl in (0, 2, 3):
         got = ctx.pair_common(37, 91, 3, 66, impl=impl)
         assert np.array_equal(got, want[37:91, 3:66]), impl
 
@@ -281,7 +283,36 @@ def test_randomised_shapes_vs_oracle(ctx, oracle):
             sk[i] = sk[j].copy()
         ctx.upload(sk)
         want = oracle.common_matrix(sk)
-        for impl in (0, 1, 2):
+        for impl in (0, 1, 2, 3):
             assert np.array_equal(ctx.pair_common(0, n, 0, n, impl=impl), want), (trial, impl)
         s = int(rng.choice([1, 50, 888, 1000, 4000]))
         assert np.array_equal(ctx.pair_common_b(0, n, 0, n, s), oracle.common_B_matrix(sk, s)), (trial, s)
+
+
+def test_blockjoin_pass_equals_join_pass(tc, monkeypatch):
+    """K3J (block join) dense pass against K3H on 9000 sketches: three column segments, row blocks with 1..3 table
+    partitions, ragged blocks without a union list (routed to K3H), plus the start_index form"""
+    rng = np.random.default_rng(8)
+    sk = synth.family_sketches(30, 100, s=700, seed=61, keep_lo=0.3)                 # related neighbours: P = 1
+    perm = rng.permutation(3000)
+    sk += [sk[i] for i in perm[:2500]]                                               # unrelated neighbours: P = 2..3
+    sk += synth.family_sketches(5, 100, s=1000, seed=62, ragged=(300, 5000))         # blocks above 32768 elements
+    sk += [np.unique(rng.integers(0, 2**40, int(z), dtype=np.uint64)) for z in rng.integers(0, 1500, 3000)]
+    n = len(sk)
+    with tc.Context(0) as c:
+        c.upload(sk)
+        res = {}
+        for impl in ("join", "blockjoin"):
+            monkeypatch.setenv("TCLUST_PASS_IMPL", impl)
+            npairs, nedges = c.allpairs_pass(4)
+            assert npairs == n * (n - 1) // 2
+            res[impl] = np.sort(c.edges(), order=["i", "j"])
+            c.allpairs_pass_from(4, 7013)
+            res[impl + "_from"] = np.sort(c.edges(), order=["i", "j"])
+            p0 = (c.allpairs_pass(4, 0, 2), np.sort(c.edges(), order=["i", "j"]))[1]
+            p1 = (c.allpairs_pass(4, 1, 2), np.sort(c.edges(), order=["i", "j"]))[1]
+            res[impl + "_parts"] = np.sort(np.concatenate([p0, p1]), order=["i", "j"])
+        assert len(res["join"]) > 100000
+        assert np.array_equal(res["join"], res["blockjoin"])
+        assert np.array_equal(res["join_from"], res["blockjoin_from"])
+        assert np.array_equal(res["join"], res["blockjoin_parts"]) and np.array_equal(res["join"], res["join_parts"])
