@@ -349,9 +349,11 @@ def run_pairs(args):
         k3_avg_s = k3_ms / 1e3 / args.steps
         achieved = (pairs_mine / args.steps) * PAIR_BYTES / k3_avg_s / 1e9
         traffic, binding = None, None
-        kernel = "k3_tile_kernel" if os.environ.get("TCLUST_PASS_IMPL") == "merge" else "k3h_join_kernel"
+        impl_env = os.environ.get("TCLUST_PASS_IMPL")
+        kernel = ("k3_tile_kernel" if impl_env == "merge" else "k3h_join_kernel" if impl_env == "join"
+                  else "k3j_block_kernel (units where the block join does not pay run on k3h_join_kernel)")
         tp = os.path.join(ROOT, "profiles", "k3_traffic.json")
-        if os.path.exists(tp) and kernel == "k3h_join_kernel" and n == 100000 and world == 1:
+        if os.path.exists(tp) and impl_env is None and args.order == "family" and n == 100000 and world == 1:
             try:
                 prof = json.load(open(tp))
                 traffic = prof.get("dram_bytes_per_launch")

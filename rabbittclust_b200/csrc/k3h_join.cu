@@ -623,21 +623,47 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                         }
                         if (__ballot_sync(0xffffffffu, (mask[0] | mask[1] | mask[2] | mask[3]) != 0u)) {
                             anyhit = 1u;
+                            // column masks of the hit keys: every hit lane loads its own (one latency per step)
+                            uint32_t cmv[4];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) cmv[k] = mask[k] ? __ldg(cmasks + pos + lane + 32 * k) : 0u;
 #pragma unroll 1
                             for (int k = 0; k < 4; k++) {
                                 const uint32_t mk = k == 0 ? mask[0] : k == 1 ? mask[1] : k == 2 ? mask[2] : mask[3];
+                                const uint32_t ck = k == 0 ? cmv[0] : k == 1 ? cmv[1] : k == 2 ? cmv[2] : cmv[3];
                                 unsigned hit = __ballot_sync(0xffffffffu, mk != 0u);
-                                while (hit) {
-                                    const int src = __ffs(hit) - 1;
-                                    uint32_t rm = __shfl_sync(0xffffffffu, mk, src);              // rows that hold the key
-                                    const uint32_t cm = __ldg(cmasks + pos + src + 32 * k);      // columns that hold it
-                                    const bool mine = (cm >> lane) & 1u;                          // lane = column
-                                    while (rm) {
-                                        const int r = __ffs(rm) - 1;
-                                        if (mine) cnt[r * 32 + lane]++;
-                                        rm &= rm - 1;
+                                if (__popc(hit) <= 2) {
+                                    while (hit) {                         // few hits: count[r][c]++ for r in rows, c = lane
+                                        const int src = __ffs(hit) - 1;
+                                        uint32_t rm = __shfl_sync(0xffffffffu, mk, src);
+                                        const uint32_t cm = __shfl_sync(0xffffffffu, ck, src);
+                                        const bool mine = (cm >> lane) & 1u;
+                                        while (rm) {
+                                            const int r = __ffs(rm) - 1;
+                                            if (mine) cnt[r * 32 + lane]++;
+                                            rm &= rm - 1;
+                                        }
+                                        hit &= hit - 1;
                                     }
-                                    hit &= hit - 1;
+                                } else {
+                                    // many hits (a tile of related sketches): transpose the 32 keys' masks with ballots --
+                                    // mycols: keys held by column `lane`; per row r the keys held by row r -- and add popcounts
+                                    uint32_t mycols = 0;
+#pragma unroll
+                                    for (int c = 0; c < 32; c++) {
+                                        const unsigned b = __ballot_sync(0xffffffffu, (ck >> c) & 1u);
+                                        if (lane == (uint32_t)c) mycols = b;
+                                    }
+                                    uint32_t rows_any = mk;
+#pragma unroll
+                                    for (int o = 16; o; o >>= 1) rows_any |= __shfl_xor_sync(0xffffffffu, rows_any, o);
+                                    while (rows_any) {
+                                        const int r = __ffs(rows_any) - 1;
+                                        const unsigned rk = __ballot_sync(0xffffffffu, (mk >> r) & 1u);
+                                        const uint32_t add = __popc(rk & mycols);
+                                        if (add) cnt[r * 32 + lane] += (uint16_t)add;
+                                        rows_any &= rows_any - 1;
+                                    }
                                 }
                             }
                         }
@@ -755,7 +781,11 @@ int tc_kh_prepare(tc_ctx *ctx)
         for (uint32_t q = 0; q + 1 < P; q++) piv[pivoff[rb] + q] = d[first + q];
     }
     ctx->bu_count.assign(nrb, 0xFFFFFFFFu);
-    for (uint32_t rb = 0; rb < nrb; rb++) ctx->bu_count[rb] = dist[(size_t)rb * KH_DREC];
+    ctx->kh_parts.assign(nrb, 1);
+    for (uint32_t rb = 0; rb < nrb; rb++) {
+        ctx->bu_count[rb] = dist[(size_t)rb * KH_DREC];
+        ctx->kh_parts[rb] = pivoff[rb + 1] - pivoff[rb] + 1;
+    }
     int rc = 1;
     do {
         if (cudaMalloc(&ctx->d_kh_pivoff, (size_t)(nrb + 1) * 4) != cudaSuccess ||
@@ -783,7 +813,7 @@ int tc_kh_prepare(tc_ctx *ctx)
 // edge_list: `units` is ctx->kh_edge_units, which stays resident on the device between passes (no per-pass copy
 // from pageable host memory in front of the kernel)
 static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &units, bool edge_list = false,
-                     bool block_kernel = false)
+                     bool block_kernel = false, bool record_start = true)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -814,7 +844,7 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
     a.counters = ctx->d_edge_count; a.state = ctx->d_kh_state;
     a.bu_keys = ctx->d_bu_keys; a.bu_mask = ctx->d_bu_mask; a.bu_count = ctx->d_bu_count;
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count + 2, 0, sizeof(unsigned long long), ctx->stream));
-    if (ctx->ev_pass0) cudaEventRecord(ctx->ev_pass0, ctx->stream);      // kernel-only duration, tc_last_pass_kernel_ms
+    if (ctx->ev_pass0 && record_start) cudaEventRecord(ctx->ev_pass0, ctx->stream);   // kernel-only duration, tc_last_pass_kernel_ms
     if (block_kernel) k3j_block_kernel<<<grid, KH_THREADS, KJ_SMEM, ctx->stream>>>(a);
     else if (a.mode == KH_MODE_CAND) k3h_join_kernel<KH_MODE_CAND><<<grid, KH_THREADS, KH_SMEM, ctx->stream>>>(a);
     else k3h_join_kernel<KH_MODE_EDGES><<<grid, KH_THREADS, KH_SMEM, ctx->stream>>>(a);     // matrix and edge epilogues
@@ -905,7 +935,21 @@ int tc_launch_blockjoin_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j
     return kh_launch(ctx, a, old);
 }
 
-int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index)
+// K3J pays when the sketches are related to their neighbours: the row block fits one table partition and the union
+// lists of the unit's column blocks are clearly shorter than the sketches themselves (measured at N = 100k, s = 1000:
+// related neighbours 86 ms vs 153 ms on K3H; unrelated neighbours 657 ms vs 292 ms)
+static bool kj_unit_pays(const tc_ctx *ctx, const tc_kh_unit &u)
+{
+    if (ctx->kh_parts.empty() || ctx->kh_parts[u.rb] != 1) return false;
+    uint64_t keys = 0, elems = 0;
+    for (uint32_t cb = u.c0 / 32; cb * 32 < u.c1; cb++) {
+        keys += ctx->bu_count[cb];
+        elems += ctx->h_off[std::min<uint32_t>(ctx->n, cb * 32 + 32)] - ctx->h_off[cb * 32];
+    }
+    return keys * 10 <= elems * 6;
+}
+
+int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index, bool force_block)
 {
     const uint32_t n = ctx->n, nrb = (n + 31) / 32;
     // the unit list of K3H (also what tc_allpairs_pass counts pairs from), split by kernel
@@ -920,11 +964,13 @@ int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t np
         ctx->kh_units_on_device = false;
     }
     std::vector<tc_kh_unit> blk, old;
-    for (size_t u = part; u < ctx->kh_edge_units.size(); u += (nparts ? nparts : 1))
-        (kj_unit_listed(ctx, ctx->kh_edge_units[u]) ? blk : old).push_back(ctx->kh_edge_units[u]);
+    for (size_t u = part; u < ctx->kh_edge_units.size(); u += (nparts ? nparts : 1)) {
+        const tc_kh_unit &un = ctx->kh_edge_units[u];
+        (kj_unit_listed(ctx, un) && (force_block || kj_unit_pays(ctx, un)) ? blk : old).push_back(un);
+    }
     KHArgs a{};
     a.mode = KH_MODE_EDGES; a.part = 0; a.nparts = 1; a.row_min = start_index;   // the lists already hold this part only
     a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
-    if (kh_launch(ctx, a, blk, false, true)) return 1;
-    return kh_launch(ctx, a, old);
+    if (kh_launch(ctx, a, blk, false, true, true)) return 1;
+    return kh_launch(ctx, a, old, false, false, blk.empty());
 }

@@ -419,10 +419,12 @@ static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32
     ctx->edges_semb_size = semb_size;
     unsigned long long cnt[2] = {0, 0};
     for (int attempt = 0;; attempt++) {
-            const bool use_block = !use_merge && impl && !strcmp(impl, "blockjoin");
+            // default: per work unit the block join (K3J) where it pays, else the per-column join (K3H);
+        // TCLUST_PASS_IMPL = join | blockjoin forces one of them, merge the first-generation kernel
+        const bool force_join = impl && !strcmp(impl, "join"), force_block = impl && !strcmp(impl, "blockjoin");
         if (use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts, semb_size)
-            : use_block ? tc_launch_blockjoin_edges(ctx, radio, part, nparts, start_index)
-                        : tc_launch_join_edges(ctx, radio, part, nparts, start_index)) return 1;
+            : force_join ? tc_launch_join_edges(ctx, radio, part, nparts, start_index)
+                         : tc_launch_blockjoin_edges(ctx, radio, part, nparts, start_index, force_block)) return 1;
         TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
         TC_CUDA(cudaStreamSynchronize(ctx->stream));
         if (cnt[1] == 0 && cnt[0] <= ctx->edge_cap) break;

@@ -302,8 +302,11 @@ def test_blockjoin_pass_equals_join_pass(tc, monkeypatch):
     with tc.Context(0) as c:
         c.upload(sk)
         res = {}
-        for impl in ("join", "blockjoin"):
-            monkeypatch.setenv("TCLUST_PASS_IMPL", impl)
+        for impl in ("join", "blockjoin", "auto"):
+            if impl == "auto":
+                monkeypatch.delenv("TCLUST_PASS_IMPL")            # default: per-unit routing between K3J and K3H
+            else:
+                monkeypatch.setenv("TCLUST_PASS_IMPL", impl)
             npairs, nedges = c.allpairs_pass(4)
             assert npairs == n * (n - 1) // 2
             res[impl] = np.sort(c.edges(), order=["i", "j"])
@@ -316,3 +319,5 @@ def test_blockjoin_pass_equals_join_pass(tc, monkeypatch):
         assert np.array_equal(res["join"], res["blockjoin"])
         assert np.array_equal(res["join_from"], res["blockjoin_from"])
         assert np.array_equal(res["join"], res["blockjoin_parts"]) and np.array_equal(res["join"], res["join_parts"])
+        assert np.array_equal(res["join"], res["auto"]) and np.array_equal(res["join_from"], res["auto_from"])
+        assert np.array_equal(res["join"], res["auto_parts"])
