@@ -813,7 +813,7 @@ int tc_kh_prepare(tc_ctx *ctx)
 // edge_list: `units` is ctx->kh_edge_units, which stays resident on the device between passes (no per-pass copy
 // from pageable host memory in front of the kernel)
 static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &units, bool edge_list = false,
-                     bool block_kernel = false, bool record_start = true)
+                     bool block_kernel = false, bool record_start = true, const tc_kh_unit *d_resident = nullptr)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -823,12 +823,12 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
         attr_set = true;
     }
     if (units.empty()) return 0;
-    if (units.size() > ctx->kh_units_cap) {
+    if (!d_resident && units.size() > ctx->kh_units_cap) {
         cudaFree(ctx->d_kh_units); ctx->d_kh_units = nullptr; ctx->kh_units_cap = 0; ctx->kh_units_on_device = false;
         TC_CUDA(cudaMalloc(&ctx->d_kh_units, units.size() * sizeof(tc_kh_unit)));
         ctx->kh_units_cap = units.size();
     }
-    if (!(edge_list && ctx->kh_units_on_device)) {
+    if (!d_resident && !(edge_list && ctx->kh_units_on_device)) {
         TC_CUDA(cudaMemcpyAsync(ctx->d_kh_units, units.data(), units.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice,
                                 ctx->stream));
         TC_CUDA(cudaStreamSynchronize(ctx->stream));   // `units` (host) must outlive the copy
@@ -840,7 +840,7 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
     if (!ctx->d_kh_state) TC_CUDA(cudaMalloc(&ctx->d_kh_state, (size_t)ctx->num_sms * KH_CSEG * KH_STATE_CAND * 4));
     a.ranks = ctx->d_ranks; a.off = reinterpret_cast<const unsigned long long *>(ctx->d_off); a.size = ctx->d_size;
     a.n = ctx->n; a.pivots = ctx->d_kh_pivots; a.pivoff = ctx->d_kh_pivoff;
-    a.units = ctx->d_kh_units; a.nunits = (uint32_t)units.size();
+    a.units = d_resident ? d_resident : ctx->d_kh_units; a.nunits = (uint32_t)units.size();
     a.counters = ctx->d_edge_count; a.state = ctx->d_kh_state;
     a.bu_keys = ctx->d_bu_keys; a.bu_mask = ctx->d_bu_mask; a.bu_count = ctx->d_bu_count;
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count + 2, 0, sizeof(unsigned long long), ctx->stream));
@@ -940,7 +940,7 @@ int tc_launch_blockjoin_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j
 // related neighbours 86 ms vs 153 ms on K3H; unrelated neighbours 657 ms vs 292 ms)
 static bool kj_unit_pays(const tc_ctx *ctx, const tc_kh_unit &u)
 {
-    if (ctx->kh_parts.empty() || ctx->kh_parts[u.rb] != 1) return false;
+    if (ctx->kh_parts.empty() || ctx->kh_parts[u.rb] > 2) return false;
     uint64_t keys = 0, elems = 0;
     for (uint32_t cb = u.c0 / 32; cb * 32 < u.c1; cb++) {
         keys += ctx->bu_count[cb];
@@ -961,16 +961,27 @@ int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t np
                 if (c1 > c0) ctx->kh_edge_units.push_back(tc_kh_unit{rb, c0, c1});
             }
         ctx->kh_edge_units_n = n; ctx->kh_edge_units_start = start_index;
-        ctx->kh_units_on_device = false;
+        ctx->kh_units_on_device = false; ctx->kj_split_valid = false;
     }
-    std::vector<tc_kh_unit> blk, old;
-    for (size_t u = part; u < ctx->kh_edge_units.size(); u += (nparts ? nparts : 1)) {
-        const tc_kh_unit &un = ctx->kh_edge_units[u];
-        (kj_unit_listed(ctx, un) && (force_block || kj_unit_pays(ctx, un)) ? blk : old).push_back(un);
+    // the routing of this rank's units is decided once per (sketch set, start_index, part) and kept on the device
+    const uint64_t key = ((uint64_t)part << 40) ^ ((uint64_t)(nparts ? nparts : 1) << 33) ^ ((uint64_t)start_index << 1) ^ (force_block ? 1u : 0u);
+    if (!ctx->kj_split_valid || ctx->kj_split_key != key) {
+        std::vector<tc_kh_unit> &blk = ctx->kj_units_blk, &old = ctx->kj_units_old;
+        blk.clear(); old.clear();
+        for (size_t u = part; u < ctx->kh_edge_units.size(); u += (nparts ? nparts : 1)) {
+            const tc_kh_unit &un = ctx->kh_edge_units[u];
+            (kj_unit_listed(ctx, un) && (force_block || kj_unit_pays(ctx, un)) ? blk : old).push_back(un);
+        }
+        cudaFree(ctx->d_kj_units);
+        ctx->d_kj_units = nullptr;
+        TC_CUDA(cudaMalloc(&ctx->d_kj_units, std::max<size_t>(blk.size() + old.size(), 1) * sizeof(tc_kh_unit)));
+        if (!blk.empty()) TC_CUDA(cudaMemcpy(ctx->d_kj_units, blk.data(), blk.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice));
+        if (!old.empty()) TC_CUDA(cudaMemcpy(ctx->d_kj_units + blk.size(), old.data(), old.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice));
+        ctx->kj_split_key = key; ctx->kj_split_valid = true;
     }
     KHArgs a{};
     a.mode = KH_MODE_EDGES; a.part = 0; a.nparts = 1; a.row_min = start_index;   // the lists already hold this part only
     a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
-    if (kh_launch(ctx, a, blk, false, true, true)) return 1;
-    return kh_launch(ctx, a, old, false, false, blk.empty());
+    if (kh_launch(ctx, a, ctx->kj_units_blk, false, true, true, ctx->d_kj_units)) return 1;
+    return kh_launch(ctx, a, ctx->kj_units_old, false, false, ctx->kj_units_blk.empty(), ctx->d_kj_units + ctx->kj_units_blk.size());
 }

@@ -84,6 +84,10 @@ struct tc_ctx {
     uint64_t cap_bu = 0;
     std::vector<uint32_t> bu_count;
     std::vector<uint32_t> kh_parts;      // table partitions per row block
+    std::vector<tc_kh_unit> kj_units_blk, kj_units_old;   // this rank's units routed to K3J / K3H, resident in d_kj_units
+    tc_kh_unit *d_kj_units = nullptr;
+    uint64_t kj_split_key = 0;
+    bool kj_split_valid = false;
 
     // KSSD shuffled_dim table (K2), resident once uploaded
     int32_t *d_kssd_dim = nullptr;

@@ -85,7 +85,7 @@ static void release_sketches(tc_ctx *ctx)
 
 static void reset_sketches(tc_ctx *ctx)
 {
-    ctx->kh_edge_units.clear(); ctx->kh_edge_units_n = 0; ctx->kh_units_on_device = false;
+    ctx->kh_edge_units.clear(); ctx->kh_edge_units_n = 0; ctx->kh_units_on_device = false; ctx->kj_split_valid = false;
     ctx->n_edges = 0; ctx->n = 0; ctx->total = 0; ctx->ngroups = 0; ctx->edges_semb_size = 0;
     ctx->edge_cap_for_n = 0;
     tc_rep_table_reset(ctx);
@@ -115,7 +115,7 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     cudaFree(ctx->d_edge_count);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_kssd_dim); cudaFree(ctx->d_kssd_filter);
-    cudaFree(ctx->d_kh_state); cudaFree(ctx->d_kh_units);
+    cudaFree(ctx->d_kh_state); cudaFree(ctx->d_kh_units); cudaFree(ctx->d_kj_units);
     if (ctx->ev_pass0) cudaEventDestroy(ctx->ev_pass0);
     if (ctx->ev_pass1) cudaEventDestroy(ctx->ev_pass1);
     cudaStreamDestroy(ctx->stream);
