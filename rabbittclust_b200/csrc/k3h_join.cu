@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
     uint2 *table = reinterpret_cast<uint2 *>(kh_smem);
     uint32_t *filter = reinterpret_cast<uint32_t *>(kh_smem + (size_t)KH_SLOTS * 8);
     uint32_t *cnt_all = filter + KJ_FWORDS;
-    __shared__ uint32_t s_unit, s_next;
+    __shared__ uint32_t s_unit, s_next, s_nheavy, s_heavy[KH_CSEG / 32];
     __shared__ uint32_t s_lo[32], s_hi[32], s_len[32];
     __shared__ unsigned long long s_base[32];
 
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                     const uint32_t *row = a.ranks + s_base[tid];
                     s_hi[tid] = (p + 1 == P) ? s_len[tid] : kh_lower_bound(row, s_lo[tid], s_len[tid], piv_hi);
                 }
-                if (tid == 0) s_next = c0 / 32;
+                if (tid == 0) { s_next = c0 / 32; s_nheavy = 0; }
             }
             __syncthreads();
             {   // build: warp w inserts the partition's elements of row w
@@ -555,7 +555,139 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                 }
             }
             __syncthreads();
-            // ---- tiles: one warp per column block
+            // ---- tiles: one warp per column block.  stream_slice runs the keys [lo, hi) of one union list through the
+            //      table and adds the hits to this warp's counters; with may_defer it gives up (returns true) at the
+            //      first group of 32 keys with more than two hits: such a tile -- related sketches on both sides, a
+            //      thousand hits with 32 x 32 increments each -- would keep one warp busy ~50 times longer than the
+            //      others wait at the unit barrier, so it is redone afterwards by all 32 warps together.
+            auto stream_slice = [&](const uint32_t *keys, const uint32_t *cmasks, uint32_t lo, uint32_t hi, bool may_defer,
+                                    uint32_t &anyhit) -> bool {
+                if (hi <= lo) return false;
+                uint32_t pos = lo, rem = hi - lo;
+                const uint32_t *pc = keys + lo + lane;
+                uint32_t x[4], xn[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) x[k] = (lane + 32 * k < rem) ? __ldg(pc + 32 * k) : 0xFFFFFFFFu;
+                for (;;) {
+                    if (rem >= 256u) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) xn[k] = __ldg(pc + 128 + 32 * k);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) xn[k] = (lane + 128 + 32 * k < rem) ? __ldg(pc + 128 + 32 * k) : 0xFFFFFFFFu;
+                    }
+                    uint32_t fw[4], fm[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t h = x[k] * 0x9E3779B1u;
+                        fw[k] = kh_lds(filt_addr + ((h >> (30 - KJ_FBITS + 5)) & ((KJ_FWORDS - 1) << 2)));
+                        fm[k] = kh_fmask(h);
+                    }
+                    bool maybe = false;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        fw[k] = (fm[k] & fw[k]) == 0u;          // filter words are stored inverted
+                        maybe |= fw[k] != 0u;
+                    }
+                    uint32_t mask[4] = {0u, 0u, 0u, 0u};
+                    if (maybe) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            if (fw[k]) {
+                                uint32_t slot = kh_slot(x[k]);
+                                for (;;) {
+                                    const uint2 e = kh_lds2(tab_addr + slot * 8);
+                                    if (e.x == x[k]) { mask[k] = e.y; break; }
+                                    if (e.x == KH_EMPTY) break;
+                                    slot = (slot + 1) & (KH_SLOTS - 1);
+                                }
+                            }
+                        }
+                    }
+                    if (__ballot_sync(0xffffffffu, (mask[0] | mask[1] | mask[2] | mask[3]) != 0u)) {
+                        anyhit = 1u;
+                        // column masks of the hit keys: every hit lane loads its own (one latency per step)
+                        uint32_t cmv[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) cmv[k] = mask[k] ? __ldg(cmasks + pos + lane + 32 * k) : 0u;
+#pragma unroll 1
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t mk = k == 0 ? mask[0] : k == 1 ? mask[1] : k == 2 ? mask[2] : mask[3];
+                            const uint32_t ck = k == 0 ? cmv[0] : k == 1 ? cmv[1] : k == 2 ? cmv[2] : cmv[3];
+                            unsigned hit = __ballot_sync(0xffffffffu, mk != 0u);
+                            if (__popc(hit) <= 2) {
+                                while (hit) {                         // few hits: count[r][c]++ for r in rows, c = lane
+                                    const int src = __ffs(hit) - 1;
+                                    uint32_t rm = __shfl_sync(0xffffffffu, mk, src);
+                                    const uint32_t cm = __shfl_sync(0xffffffffu, ck, src);
+                                    const bool mine = (cm >> lane) & 1u;
+                                    while (rm) {
+                                        const int r = __ffs(rm) - 1;
+                                        if (mine) cnt[r * 32 + lane]++;
+                                        rm &= rm - 1;
+                                    }
+                                    hit &= hit - 1;
+                                }
+                            } else {
+                                if (may_defer) return true;
+                                // many hits: transpose the 32 keys' masks with ballots -- mycols: keys held by column
+                                // `lane`; per row r the keys held by row r -- and add popcounts
+                                uint32_t mycols = 0;
+#pragma unroll
+                                for (int c = 0; c < 32; c++) {
+                                    const unsigned bb = __ballot_sync(0xffffffffu, (ck >> c) & 1u);
+                                    if (lane == (uint32_t)c) mycols = bb;
+                                }
+                                uint32_t rows_any = mk;
+#pragma unroll
+                                for (int o = 16; o; o >>= 1) rows_any |= __shfl_xor_sync(0xffffffffu, rows_any, o);
+                                while (rows_any) {
+                                    const int r = __ffs(rows_any) - 1;
+                                    const unsigned rk = __ballot_sync(0xffffffffu, (mk >> r) & 1u);
+                                    const uint32_t add = __popc(rk & mycols);
+                                    if (add) cnt[r * 32 + lane] += (uint16_t)add;
+                                    rows_any &= rows_any - 1;
+                                }
+                            }
+                        }
+                    }
+                    if (rem <= 128u) break;
+                    pos += 128; pc += 128; rem -= 128;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) x[k] = xn[k];
+                }
+                return false;
+            };
+            // row r = `row` (fixed per call) of one finished tile: matrix cell / candidate edge for column j = cb*32+lane
+            auto emit_row = [&](uint32_t row, uint32_t cb, uint32_t c) {
+                const uint32_t i = rb * 32 + row, j = cb * 32 + lane;
+                if (a.mode == KH_MODE_MATRIX) {
+                    if (i >= a.i0 && i < a.i1 && j >= a.j0 && j < a.j1)
+                        a.out[(size_t)(i - a.i0) * (a.j1 - a.j0) + (j - a.j0)] = c;
+                    return;
+                }
+                bool keep = false;
+                if (c >= 1u && i < a.n && i >= a.row_min && j < i) {
+                    const uint32_t s0 = s_len[row], s1 = a.size[j];
+                    const uint32_t mn = min(s0, s1), mx = max(s0, s1);
+                    keep = mn > 0 && !((long long)mx > (long long)a.radio * (long long)mn);   // MST.cpp:1481-1487
+                }
+                const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+                if (ballot) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)__popc(ballot));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (keep) {
+                        const unsigned long long idx = base + __popc(ballot & ((1u << lane) - 1));
+                        if (idx < a.edge_cap) {
+                            tc_pair e; e.i = i; e.j = j; e.common = c;
+                            a.edges[idx] = e;
+                        } else {
+                            a.counters[1] = 1ULL;
+                        }
+                    }
+                }
+            };
             for (;;) {
                 uint32_t cb = 0;
                 if (lane == 0) cb = atomicAdd(&s_next, 1u);
@@ -579,144 +711,63 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                     for (int q = 0; q < 16; q++) cntw[lane + 32 * q] = 0u;
                 }
                 __syncwarp();
-                if (hi > lo) {
-                    uint32_t pos = lo, rem = hi - lo;
-                    const uint32_t *pc = keys + lo + lane;
-                    uint32_t x[4], xn[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) x[k] = (lane + 32 * k < rem) ? __ldg(pc + 32 * k) : 0xFFFFFFFFu;
-                    for (;;) {
-                        if (rem >= 256u) {
-#pragma unroll
-                            for (int k = 0; k < 4; k++) xn[k] = __ldg(pc + 128 + 32 * k);
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 4; k++) xn[k] = (lane + 128 + 32 * k < rem) ? __ldg(pc + 128 + 32 * k) : 0xFFFFFFFFu;
-                        }
-                        uint32_t fw[4], fm[4];
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const uint32_t h = x[k] * 0x9E3779B1u;
-                            fw[k] = kh_lds(filt_addr + ((h >> (30 - KJ_FBITS + 5)) & ((KJ_FWORDS - 1) << 2)));
-                            fm[k] = kh_fmask(h);
-                        }
-                        bool maybe = false;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            fw[k] = (fm[k] & fw[k]) == 0u;          // filter words are stored inverted
-                            maybe |= fw[k] != 0u;
-                        }
-                        uint32_t mask[4] = {0u, 0u, 0u, 0u};
-                        if (maybe) {
-#pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                if (fw[k]) {
-                                    uint32_t slot = kh_slot(x[k]);
-                                    for (;;) {
-                                        const uint2 e = kh_lds2(tab_addr + slot * 8);
-                                        if (e.x == x[k]) { mask[k] = e.y; break; }
-                                        if (e.x == KH_EMPTY) break;
-                                        slot = (slot + 1) & (KH_SLOTS - 1);
-                                    }
-                                }
-                            }
-                        }
-                        if (__ballot_sync(0xffffffffu, (mask[0] | mask[1] | mask[2] | mask[3]) != 0u)) {
-                            anyhit = 1u;
-                            // column masks of the hit keys: every hit lane loads its own (one latency per step)
-                            uint32_t cmv[4];
-#pragma unroll
-                            for (int k = 0; k < 4; k++) cmv[k] = mask[k] ? __ldg(cmasks + pos + lane + 32 * k) : 0u;
-#pragma unroll 1
-                            for (int k = 0; k < 4; k++) {
-                                const uint32_t mk = k == 0 ? mask[0] : k == 1 ? mask[1] : k == 2 ? mask[2] : mask[3];
-                                const uint32_t ck = k == 0 ? cmv[0] : k == 1 ? cmv[1] : k == 2 ? cmv[2] : cmv[3];
-                                unsigned hit = __ballot_sync(0xffffffffu, mk != 0u);
-                                if (__popc(hit) <= 2) {
-                                    while (hit) {                         // few hits: count[r][c]++ for r in rows, c = lane
-                                        const int src = __ffs(hit) - 1;
-                                        uint32_t rm = __shfl_sync(0xffffffffu, mk, src);
-                                        const uint32_t cm = __shfl_sync(0xffffffffu, ck, src);
-                                        const bool mine = (cm >> lane) & 1u;
-                                        while (rm) {
-                                            const int r = __ffs(rm) - 1;
-                                            if (mine) cnt[r * 32 + lane]++;
-                                            rm &= rm - 1;
-                                        }
-                                        hit &= hit - 1;
-                                    }
-                                } else {
-                                    // many hits (a tile of related sketches): transpose the 32 keys' masks with ballots --
-                                    // mycols: keys held by column `lane`; per row r the keys held by row r -- and add popcounts
-                                    uint32_t mycols = 0;
-#pragma unroll
-                                    for (int c = 0; c < 32; c++) {
-                                        const unsigned b = __ballot_sync(0xffffffffu, (ck >> c) & 1u);
-                                        if (lane == (uint32_t)c) mycols = b;
-                                    }
-                                    uint32_t rows_any = mk;
-#pragma unroll
-                                    for (int o = 16; o; o >>= 1) rows_any |= __shfl_xor_sync(0xffffffffu, rows_any, o);
-                                    while (rows_any) {
-                                        const int r = __ffs(rows_any) - 1;
-                                        const unsigned rk = __ballot_sync(0xffffffffu, (mk >> r) & 1u);
-                                        const uint32_t add = __popc(rk & mycols);
-                                        if (add) cnt[r * 32 + lane] += (uint16_t)add;
-                                        rows_any &= rows_any - 1;
-                                    }
-                                }
-                            }
-                        }
-                        if (rem <= 128u) break;
-                        pos += 128; pc += 128; rem -= 128;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) x[k] = xn[k];
-                    }
-                }
+                const bool deferred = stream_slice(keys, cmasks, lo, hi, true, anyhit);
                 __syncwarp();
+                if (deferred) {                                   // redone by the whole CTA below
+                    if (lane == 0) s_heavy[atomicAdd(&s_nheavy, 1u)] = cb;
+                    continue;
+                }
                 if (p + 1 < P) {
                     if (lane == 0) tst[KJ_TILE_WORDS] = anyhit;
                     if (anyhit) {
 #pragma unroll
                         for (int q = 0; q < 16; q++) tst[lane + 32 * q] = cntw[lane + 32 * q];
                     }
-                } else if (a.mode == KH_MODE_MATRIX) {
-                    const uint32_t j = cb * 32 + lane;
-                    for (uint32_t r = 0; r < 32; r++) {
-                        const uint32_t i = rb * 32 + r;
-                        if (i >= a.i0 && i < a.i1 && j >= a.j0 && j < a.j1)
-                            a.out[(size_t)(i - a.i0) * (a.j1 - a.j0) + (j - a.j0)] = anyhit ? (uint32_t)cnt[r * 32 + lane] : 0u;
-                    }
-                } else if (anyhit) {
-                    const uint32_t j = cb * 32 + lane;
-                    const uint32_t s1 = j < a.n ? a.size[j] : 0u;
-                    for (uint32_t r = 0; r < 32; r++) {
-                        const uint32_t i = rb * 32 + r;
-                        const uint32_t c = cnt[r * 32 + lane];
-                        bool keep = false;
-                        if (c >= 1u && i < a.n && i >= a.row_min && j < i) {
-                            const uint32_t s0 = s_len[r];
-                            const uint32_t mn = min(s0, s1), mx = max(s0, s1);
-                            keep = mn > 0 && !((long long)mx > (long long)a.radio * (long long)mn);   // MST.cpp:1481-1487
-                        }
-                        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-                        if (ballot) {
-                            unsigned long long base = 0;
-                            if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)__popc(ballot));
-                            base = __shfl_sync(0xffffffffu, base, 0);
-                            if (keep) {
-                                const unsigned long long idx = base + __popc(ballot & ((1u << lane) - 1));
-                                if (idx < a.edge_cap) {
-                                    tc_pair e; e.i = i; e.j = j; e.common = c;
-                                    a.edges[idx] = e;
-                                } else {
-                                    a.counters[1] = 1ULL;
-                                }
-                            }
-                        }
-                    }
+                } else if (a.mode == KH_MODE_MATRIX || anyhit) {
+                    for (uint32_t r = 0; r < 32; r++) emit_row(r, cb, anyhit ? (uint32_t)cnt[r * 32 + lane] : 0u);
                 }
                 __syncwarp();
+            }
+            __syncthreads();
+            // ---- deferred tiles: all warps share one tile -- warp w streams the w-th 32nd of the list into its own
+            //      counters, then sums row w over the 32 counter sets and finishes that row
+            const uint32_t nheavy = s_nheavy;
+            for (uint32_t hx = 0; hx < nheavy; hx++) {
+                const uint32_t cb = s_heavy[hx];
+                const uint32_t D = a.bu_count[cb * KH_DREC];
+                const unsigned long long lbase = a.off[cb * 32];
+                const uint32_t *keys = a.bu_keys + lbase, *cmasks = a.bu_mask + lbase;
+                uint32_t lo = 0, hi = D;
+                if (P > 1) {
+                    lo = p == 0 ? 0u : kh_lower_bound(keys, 0, D, piv_lo);
+                    hi = (p + 1 == P) ? D : kh_lower_bound(keys, lo, D, piv_hi);
+                }
+                uint32_t *tst = state + (size_t)(cb - c0 / 32) * KJ_TILE_STATE;
+                const uint32_t prev = p == 0 ? 0u : tst[KJ_TILE_WORDS];
+                if (warp == 0 && prev) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) cntw[lane + 32 * q] = tst[lane + 32 * q];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) cntw[lane + 32 * q] = 0u;
+                }
+                __syncwarp();
+                const uint32_t chunk = ((hi - lo + 31) / 32 + 127) / 128 * 128;
+                const uint32_t slo = min(hi, lo + (uint32_t)warp * chunk), shi = min(hi, slo + chunk);
+                uint32_t anyhit = 0;
+                stream_slice(keys, cmasks, slo, shi, false, anyhit);
+                __syncthreads();
+                uint32_t total = 0;
+#pragma unroll 8
+                for (int v = 0; v < 32; v++) total += reinterpret_cast<const uint16_t *>(cnt_all + v * KJ_TILE_WORDS)[warp * 32 + lane];
+                if (p + 1 < P) {
+                    const uint32_t other = __shfl_down_sync(0xffffffffu, total, 1);
+                    if (!(lane & 1)) tst[warp * 16 + (lane >> 1)] = (total & 0xFFFFu) | (other << 16);
+                    if (tid == 0) tst[KJ_TILE_WORDS] = 1u;
+                } else {
+                    emit_row((uint32_t)warp, cb, total);
+                }
+                __syncthreads();
             }
             __syncthreads();
             if (tid < 32) s_lo[tid] = s_hi[tid];
