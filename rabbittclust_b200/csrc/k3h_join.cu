@@ -779,13 +779,16 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
 // ---- per-upload setup: partition pivots of every row block
 int tc_kh_prepare(tc_ctx *ctx)
 {
-    cudaFree(ctx->d_kh_pivots); cudaFree(ctx->d_kh_pivoff);
-    ctx->d_kh_pivots = nullptr; ctx->d_kh_pivoff = nullptr;
     const uint32_t nrb = (ctx->n + 31) / 32;
     cudaStream_t st = ctx->stream;
-    // ---- distinct counts and pivot candidates of every row block
-    uint32_t *d_dist = nullptr;
-    TC_CUDA(cudaMalloc(&d_dist, (size_t)nrb * KH_DREC * 4));
+    // ---- distinct counts and pivot candidates of every row block ([rb * KH_DREC] = distinct count of block rb,
+    //      0xFFFFFFFF: no union list); the buffers only grow (cudaMalloc/cudaFree stall for milliseconds now and then)
+    if ((uint64_t)nrb * KH_DREC > ctx->cap_bu_count) {
+        cudaFree(ctx->d_bu_count); ctx->d_bu_count = nullptr; ctx->cap_bu_count = 0;
+        TC_CUDA(cudaMalloc(&ctx->d_bu_count, (size_t)nrb * KH_DREC * 4));
+        ctx->cap_bu_count = (uint64_t)nrb * KH_DREC;
+    }
+    uint32_t *d_dist = ctx->d_bu_count;
     TC_CUDA(cudaMemsetAsync(d_dist, 0, (size_t)nrb * KH_DREC * 4, st));
     static bool attr_set = false;
     if (!attr_set) {
@@ -797,7 +800,7 @@ int tc_kh_prepare(tc_ctx *ctx)
         cudaFree(ctx->d_bu_keys); cudaFree(ctx->d_bu_mask);
         ctx->d_bu_keys = nullptr; ctx->d_bu_mask = nullptr; ctx->cap_bu = 0;
         if (cudaMalloc(&ctx->d_bu_keys, (ctx->total + 1) * 4) != cudaSuccess || cudaMalloc(&ctx->d_bu_mask, (ctx->total + 1) * 4) != cudaSuccess) {
-            cudaFree(d_dist); tc_set_error("tc_kh_prepare: out of device memory for the block union lists"); return 1;
+            tc_set_error("tc_kh_prepare: out of device memory for the block union lists"); return 1;
         }
         ctx->cap_bu = ctx->total + 1;
     }
@@ -808,7 +811,7 @@ int tc_kh_prepare(tc_ctx *ctx)
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(dist.data(), d_dist, dist.size() * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { cudaFree(d_dist); tc_set_error("tc_kh_prepare: %s", cudaGetErrorString(e)); return 1; }
+    if (e != cudaSuccess) { tc_set_error("tc_kh_prepare: %s", cudaGetErrorString(e)); return 1; }
     // ---- partitions: by distinct keys where known, else by the multiset total
     std::vector<uint32_t> pivoff(nrb + 1, 0);
     bool any_fallback = false;
@@ -839,8 +842,16 @@ int tc_kh_prepare(tc_ctx *ctx)
     }
     int rc = 1;
     do {
-        if (cudaMalloc(&ctx->d_kh_pivoff, (size_t)(nrb + 1) * 4) != cudaSuccess ||
-            cudaMalloc(&ctx->d_kh_pivots, piv.size() * 4) != cudaSuccess) { tc_set_error("tc_kh_prepare: out of device memory"); break; }
+        if (nrb + 1 > ctx->cap_pivoff) {
+            cudaFree(ctx->d_kh_pivoff); ctx->d_kh_pivoff = nullptr; ctx->cap_pivoff = 0;
+            if (cudaMalloc(&ctx->d_kh_pivoff, (size_t)(nrb + 1) * 4) != cudaSuccess) { tc_set_error("tc_kh_prepare: out of device memory"); break; }
+            ctx->cap_pivoff = nrb + 1;
+        }
+        if (piv.size() > ctx->cap_pivots) {
+            cudaFree(ctx->d_kh_pivots); ctx->d_kh_pivots = nullptr; ctx->cap_pivots = 0;
+            if (cudaMalloc(&ctx->d_kh_pivots, piv.size() * 4) != cudaSuccess) { tc_set_error("tc_kh_prepare: out of device memory"); break; }
+            ctx->cap_pivots = piv.size();
+        }
         if (cudaMemcpyAsync(ctx->d_kh_pivoff, pivoff.data(), (size_t)(nrb + 1) * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
             cudaMemcpyAsync(ctx->d_kh_pivots, piv.data(), piv.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) {
             tc_set_error("tc_kh_prepare: %s", cudaGetErrorString(cudaGetLastError())); break;
@@ -856,8 +867,6 @@ int tc_kh_prepare(tc_ctx *ctx)
         }
         rc = 0;
     } while (0);
-    cudaFree(ctx->d_bu_count);
-    ctx->d_bu_count = d_dist;              // [rb * KH_DREC] = distinct count of block rb (0xFFFFFFFF: no union list)
     return rc;
 }
 
@@ -1023,9 +1032,12 @@ int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t np
             const tc_kh_unit &un = ctx->kh_edge_units[u];
             (kj_unit_listed(ctx, un) && (force_block || kj_unit_pays(ctx, un)) ? blk : old).push_back(un);
         }
-        cudaFree(ctx->d_kj_units);
-        ctx->d_kj_units = nullptr;
-        TC_CUDA(cudaMalloc(&ctx->d_kj_units, std::max<size_t>(blk.size() + old.size(), 1) * sizeof(tc_kh_unit)));
+        if (blk.size() + old.size() > ctx->kj_units_cap || !ctx->d_kj_units) {
+            cudaFree(ctx->d_kj_units);
+            ctx->d_kj_units = nullptr; ctx->kj_units_cap = 0;
+            TC_CUDA(cudaMalloc(&ctx->d_kj_units, std::max<size_t>(blk.size() + old.size(), 1) * sizeof(tc_kh_unit)));
+            ctx->kj_units_cap = blk.size() + old.size();
+        }
         if (!blk.empty()) TC_CUDA(cudaMemcpy(ctx->d_kj_units, blk.data(), blk.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice));
         if (!old.empty()) TC_CUDA(cudaMemcpy(ctx->d_kj_units + blk.size(), old.data(), old.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice));
         ctx->kj_split_key = key; ctx->kj_split_valid = true;

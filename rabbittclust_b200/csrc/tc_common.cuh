@@ -81,13 +81,19 @@ struct tc_ctx {
     // K3J block join: per 32-sketch block the sorted distinct ranks + 32-bit membership masks, stored at the element
     // offset of the block's first sketch; bu_count[b] = number of distinct ranks (0xFFFFFFFF: block too large, no list)
     uint32_t *d_bu_keys = nullptr, *d_bu_mask = nullptr, *d_bu_count = nullptr;
-    uint64_t cap_bu = 0;
+    uint64_t cap_bu = 0, cap_bu_count = 0, cap_pivoff = 0, cap_pivots = 0, kj_units_cap = 0;   // grow-only: no cudaMalloc/cudaFree per upload
     std::vector<uint32_t> bu_count;
     std::vector<uint32_t> kh_parts;      // table partitions per row block
     std::vector<tc_kh_unit> kj_units_blk, kj_units_old;   // this rank's units routed to K3J / K3H, resident in d_kj_units
     tc_kh_unit *d_kj_units = nullptr;
     uint64_t kj_split_key = 0;
     bool kj_split_valid = false;
+
+    // reordered shadow copy of the sketch set for the dense pass (k3r_reorder.cu); d_perm (held by the shadow): new id -> id
+    tc_ctx *shadow = nullptr;
+    bool use_shadow = false;
+    uint32_t *d_perm = nullptr;
+    uint64_t cap_perm = 0;
 
     // KSSD shuffled_dim table (K2), resident once uploaded
     int32_t *d_kssd_dim = nullptr;
@@ -124,6 +130,10 @@ int tc_launch_blockjoin_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j
 int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index, bool force_block);
 int tc_launch_join_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment, double jmin);
 int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index = 0);
+// reordered shadow copy (k3r_reorder.cu)
+int tc_shadow_build(tc_ctx *ctx, const uint32_t *d_scan);
+int tc_shadow_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, bool force_block);
+void tc_shadow_free(tc_ctx *ctx);
 // representative table (k5_greedy.cu)
 void tc_rep_table_free(tc_ctx *ctx);
 void tc_rep_table_reset(tc_ctx *ctx);

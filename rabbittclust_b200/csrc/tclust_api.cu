@@ -75,8 +75,8 @@ static void release_sketches(tc_ctx *ctx)
     cudaFree(ctx->d_gt); cudaFree(ctx->d_goff); cudaFree(ctx->d_edges); cudaFree(ctx->d_comp);
     cudaFree(ctx->d_kh_pivots); cudaFree(ctx->d_kh_pivoff);
     cudaFree(ctx->d_bu_keys); cudaFree(ctx->d_bu_mask); cudaFree(ctx->d_bu_count);
-    ctx->d_bu_keys = nullptr; ctx->d_bu_mask = nullptr; ctx->d_bu_count = nullptr; ctx->cap_bu = 0;
-    ctx->d_kh_pivots = nullptr; ctx->d_kh_pivoff = nullptr;
+    ctx->d_bu_keys = nullptr; ctx->d_bu_mask = nullptr; ctx->d_bu_count = nullptr; ctx->cap_bu = 0; ctx->cap_bu_count = 0;
+    ctx->d_kh_pivots = nullptr; ctx->d_kh_pivoff = nullptr; ctx->cap_pivoff = 0; ctx->cap_pivots = 0;
     ctx->d_hashes = nullptr; ctx->d_off = nullptr; ctx->d_size = nullptr; ctx->d_ranks = nullptr;
     ctx->d_gt = nullptr; ctx->d_goff = nullptr; ctx->d_edges = nullptr; ctx->d_comp = nullptr;
     ctx->cap_hashes = ctx->cap_ranks = ctx->cap_gt = ctx->cap_n = ctx->cap_groups = ctx->cap_comp = 0;
@@ -87,7 +87,7 @@ static void reset_sketches(tc_ctx *ctx)
 {
     ctx->kh_edge_units.clear(); ctx->kh_edge_units_n = 0; ctx->kh_units_on_device = false; ctx->kj_split_valid = false;
     ctx->n_edges = 0; ctx->n = 0; ctx->total = 0; ctx->ngroups = 0; ctx->edges_semb_size = 0;
-    ctx->edge_cap_for_n = 0;
+    ctx->edge_cap_for_n = 0; ctx->use_shadow = false;
     tc_rep_table_reset(ctx);
 }
 
@@ -109,6 +109,7 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     reset_sketches(ctx);
     release_sketches(ctx);
+    tc_shadow_free(ctx);
     tc_rep_table_free(ctx);
     tc_k1_free(ctx);
     tc_k2_free(ctx);
@@ -248,6 +249,7 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     pt.mark("copy of the hashes + check");
 
     // ---- order-preserving dense rank transform: u64 hash -> u32 rank (equal hash <=> equal rank)
+    const uint32_t *d_scan = nullptr;      // rank + 1 of every position of the globally sorted hashes (sort workspace)
     if (total > 0) {
         // sort workspace: kept in the context's scratch between uploads (24 B per hash + cub's temporary storage)
         size_t tmp_bytes = 0, tmp2 = 0;
@@ -278,6 +280,7 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
         head_flag_kernel<<<nblk(total, 256), 256, 0, st>>>(kb.Current(), flag, total);
         TC_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp2, flag, flag, (int)total, st));
         scatter_rank_kernel<<<nblk(total, 256), 256, 0, st>>>(flag, vb.Current(), ctx->d_ranks, total);
+        d_scan = flag;
         ctx->launches += 12;  // iota, sort passes (cub), flags, scan, scatter (approximate; cub internals)
         TC_CUDA(cudaStreamSynchronize(st));
         pt.mark("flags + scan + scatter");
@@ -306,8 +309,10 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     TC_CUDA(cudaGetLastError());
     TC_CUDA(cudaStreamSynchronize(st));
     pt.mark("interleaved layout");
-    const int rc = tc_kh_prepare(ctx);
+    int rc = tc_kh_prepare(ctx);
     pt.mark("distinct counts + pivots");
+    if (!rc) rc = tc_shadow_build(ctx, d_scan);
+    pt.mark("reordered copy");
     return rc;
 }
 
@@ -418,11 +423,14 @@ static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32
     TC_CHECK(start_index <= ctx->n, "tc_allpairs_pass: start_index %u > n %u", start_index, ctx->n);
     ctx->edges_semb_size = semb_size;
     unsigned long long cnt[2] = {0, 0};
+    bool on_shadow = false;               // the pass ran on the reordered copy (k3r_reorder.cu)
     for (int attempt = 0;; attempt++) {
             // default: per work unit the block join (K3J) where it pays, else the per-column join (K3H);
         // TCLUST_PASS_IMPL = join | blockjoin forces one of them, merge the first-generation kernel
         const bool force_join = impl && !strcmp(impl, "join"), force_block = impl && !strcmp(impl, "blockjoin");
-        if (use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts, semb_size)
+        on_shadow = !use_merge && !force_join && start_index == 0 && ctx->use_shadow && ctx->shadow;
+        if (on_shadow ? tc_shadow_pass(ctx, radio, part, nparts, force_block)
+            : use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts, semb_size)
             : force_join ? tc_launch_join_edges(ctx, radio, part, nparts, start_index)
                          : tc_launch_blockjoin_edges(ctx, radio, part, nparts, start_index, force_block)) return 1;
         TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
@@ -453,8 +461,9 @@ static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32
         } else {
             // pairs j<i inside the (row block x column segment) units owned by this part
             uint64_t p = 0;
-            for (size_t u = part; u < ctx->kh_edge_units.size(); u += nparts) {
-                const tc_kh_unit &un = ctx->kh_edge_units[u];
+            const std::vector<tc_kh_unit> &all = on_shadow ? ctx->shadow->kh_edge_units : ctx->kh_edge_units;
+            for (size_t u = part; u < all.size(); u += nparts) {
+                const tc_kh_unit &un = all[u];
                 for (uint64_t i = std::max<uint64_t>((uint64_t)un.rb * 32, start_index); i < std::min<uint64_t>(ctx->n, (uint64_t)un.rb * 32 + 32); i++) {
                     const uint64_t hi = std::min<uint64_t>(un.c1, i);
                     if (hi > un.c0) p += hi - un.c0;

@@ -321,3 +321,39 @@ def test_blockjoin_pass_equals_join_pass(tc, monkeypatch):
         assert np.array_equal(res["join"], res["blockjoin_parts"]) and np.array_equal(res["join"], res["join_parts"])
         assert np.array_equal(res["join"], res["auto"]) and np.array_equal(res["join_from"], res["auto_from"])
         assert np.array_equal(res["join"], res["auto_parts"])
+
+
+def test_reordered_copy_gives_the_same_edges_and_mst(tc, monkeypatch):
+    """Dense pass on the reordered shadow copy (k3r_reorder.cu) against the pass in input order: sketches of 40
+    families in shuffled order, plus empty and unrelated ones; edge sets (also split over two parts), pair counts and
+    the MST must not depend on the internal order"""
+    rng = np.random.default_rng(12)
+    sk = synth.family_sketches(40, 100, s=600, seed=71, keep_lo=0.3)
+    sk += [np.unique(rng.integers(0, 2**40, int(z), dtype=np.uint64)) for z in rng.integers(0, 900, 500)]
+    sk += [np.empty(0, np.uint64)] * 7
+    order = rng.permutation(len(sk))
+    sk = [sk[i] for i in order]
+    n = len(sk)
+    res = {}
+    for mode in ("0", "1", None):
+        if mode is None:
+            monkeypatch.delenv("TCLUST_REORDER", raising=False)       # default: the upload decides (here: shuffled input, reorder)
+        else:
+            monkeypatch.setenv("TCLUST_REORDER", mode)
+        with tc.Context(0) as c:
+            c.upload(sk)
+            npairs, nedges = c.allpairs_pass(4)
+            assert npairs == n * (n - 1) // 2
+            e = np.sort(c.edges(), order=["i", "j"])
+            assert nedges == len(e) and np.all(e["j"] < e["i"])
+            p = [(c.allpairs_pass(4, q, 3), np.sort(c.edges(), order=["i", "j"])) for q in range(3)]
+            assert sum(x[0][0] for x in p) == npairs
+            parts = np.sort(np.concatenate([x[1] for x in p]), order=["i", "j"])
+            c.allpairs_pass_from(4, n - 333)              # start_index form stays in input order
+            frm = np.sort(c.edges(), order=["i", "j"])
+            mst = c.mst(21, 0.05, False)
+            res[mode] = (e, parts, frm, mst)
+    assert len(res["0"][0]) > 100000
+    for mode in ("1", None):
+        for a, b in zip(res["0"], res[mode]):
+            assert np.array_equal(a, b), mode
