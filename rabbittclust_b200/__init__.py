@@ -148,9 +148,13 @@ class Context:
         _chk(lib().tc_ctx_create(device, C.byref(self._h)))
         self.n = 0
         self.sizes = None
+        self._pin, self._pin_bytes = None, 0
 
     def close(self):
         if self._h:
+            if self._pin:
+                lib().tc_host_free(self._pin)
+                self._pin, self._pin_bytes = None, 0
             lib().tc_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -279,12 +283,27 @@ class Context:
         _chk(lib().tc_allpairs_pass(self._h, radio, part, nparts, C.byref(npairs), C.byref(nedges)))
         return int(npairs.value), int(nedges.value)
 
-    def edges(self):
+    def edges(self, pinned=False):
+        """Candidate edges of the last pass.  pinned=True: a view of a page-locked buffer the context keeps and
+        reuses (valid until the next such call) -- the copy runs at PCIe speed instead of through pageable memory."""
         n = C.c_uint64(0)
         _chk(lib().tc_edges_download(self._h, None, 0, C.byref(n)))
-        out = np.zeros(int(n.value), PAIR_DTYPE)
-        if n.value:
-            _chk(lib().tc_edges_download(self._h, out.ctypes.data, n.value, C.byref(n)))
+        m = int(n.value)
+        if pinned:
+            need = max(m, 1) * PAIR_DTYPE.itemsize
+            if need > self._pin_bytes:
+                if self._pin:
+                    lib().tc_host_free(self._pin)
+                self._pin_bytes = need + need // 8
+                self._pin = lib().tc_host_alloc(self._pin_bytes)
+                if not self._pin:
+                    self._pin_bytes = 0
+                    raise TclustError("tc_host_alloc(%d) failed" % need)
+            out = np.frombuffer((C.c_char * (m * PAIR_DTYPE.itemsize)).from_address(self._pin), PAIR_DTYPE, m)
+        else:
+            out = np.zeros(m, PAIR_DTYPE)
+        if m:
+            _chk(lib().tc_edges_download(self._h, out.ctypes.data, m, C.byref(n)))
         return out
 
     def mst(self, k, threshold, containment=False):

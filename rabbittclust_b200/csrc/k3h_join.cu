@@ -150,9 +150,30 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint3
     __syncthreads();
     const uint32_t total = s_pos[32];
     if (total > KH_SORT_CAP) { if (tid == 0) out[rb * KH_DREC] = 0xFFFFFFFFu; return; }
-    uint32_t npad = 1024;
-    while (npad < total) npad <<= 1;
-    {   // warp w copies row w
+    // Every row arrives sorted.  When the longest one fits R <= 1024 slots (R a power of two), row w goes into slots
+    // [w*R, (w+1)*R) padded with 0xFFFFFFFF -- ascending for even w, descending for odd w -- which is the state of a
+    // bitonic sort after its size-R stage: only the merges of size 2R .. 32R remain (65 of 120 stages at R = 1024).
+    uint32_t maxlen = 0;
+    for (uint32_t l = 0; l < 32; l++) maxlen = max(maxlen, s_pos[l + 1] - s_pos[l]);
+    uint32_t R = 32;
+    while (R < maxlen) R <<= 1;
+    const bool presorted = R * 32 <= KH_SORT_CAP;
+    uint32_t npad = 1024, first_sz = 2;
+    if (presorted) {
+        npad = R * 32; first_sz = 2 * R;
+        const uint32_t id = rb * 32 + warp;
+        const uint32_t len = id < n ? size[id] : 0u;
+        const uint32_t *row = ranks + (id < n ? off[id] : 0ULL);
+        uint32_t *dst = buf + warp * R;
+        uint8_t *dro = rowof + warp * R;
+        if (!(warp & 1)) {
+            for (uint32_t e = lane; e < R; e += 32) { dst[e] = e < len ? __ldg(row + e) : 0xFFFFFFFFu; dro[e] = (uint8_t)warp; }
+        } else {
+            const uint32_t pad = R - len;
+            for (uint32_t e = lane; e < R; e += 32) { dst[e] = e < pad ? 0xFFFFFFFFu : __ldg(row + (R - 1 - e)); dro[e] = (uint8_t)warp; }
+        }
+    } else {   // general case: warp w copies row w, everything is sorted from scratch
+        while (npad < total) npad <<= 1;
         const uint32_t id = rb * 32 + warp;
         const uint32_t len = id < n ? size[id] : 0u;
         const uint32_t *row = ranks + (id < n ? off[id] : 0ULL);
@@ -160,7 +181,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint3
         for (uint32_t e = total + tid; e < npad; e += KH_THREADS) { buf[e] = 0xFFFFFFFFu; rowof[e] = 0; }
     }
     __syncthreads();
-    for (uint32_t sz = 2; sz <= npad; sz <<= 1)
+    for (uint32_t sz = first_sz; sz <= npad; sz <<= 1)
         for (uint32_t stride = sz >> 1; stride > 0; stride >>= 1) {
             for (uint32_t t = tid; t < (npad >> 1); t += KH_THREADS) {
                 const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
@@ -997,17 +1018,34 @@ int tc_launch_blockjoin_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j
 
 // K3J pays when the sketches are related to their neighbours: the row block fits one table partition and the union
 // lists of the unit's column blocks are clearly shorter than the sketches themselves (measured at N = 100k, s = 1000:
-// related neighbours 86 ms vs 153 ms on K3H; unrelated neighbours 657 ms vs 292 ms)
-static bool kj_unit_pays(const tc_ctx *ctx, const tc_kh_unit &u)
-{
-    if (ctx->kh_parts.empty() || ctx->kh_parts[u.rb] > 2) return false;
-    uint64_t keys = 0, elems = 0;
-    for (uint32_t cb = u.c0 / 32; cb * 32 < u.c1; cb++) {
-        keys += ctx->bu_count[cb];
-        elems += ctx->h_off[std::min<uint32_t>(ctx->n, cb * 32 + 32)] - ctx->h_off[cb * 32];
+// related neighbours 86 ms vs 153 ms on K3H; unrelated neighbours 657 ms vs 292 ms).  Prefix sums over the column
+// blocks make the test O(1) per unit (40k units x 128 blocks at N = 100k).
+struct KjRouting {
+    std::vector<uint64_t> keys;        // prefix sum of the union-list lengths
+    std::vector<uint32_t> unlisted;    // prefix count of blocks without a list
+    explicit KjRouting(const tc_ctx *ctx)
+    {
+        const uint32_t nb = (ctx->n + 31) / 32;
+        keys.assign(nb + 1, 0); unlisted.assign(nb + 1, 0);
+        for (uint32_t b = 0; b < nb; b++) {
+            const bool listed = b < ctx->bu_count.size() && ctx->bu_count[b] != 0xFFFFFFFFu;
+            keys[b + 1] = keys[b] + (listed ? ctx->bu_count[b] : 0u);
+            unlisted[b + 1] = unlisted[b] + (listed ? 0u : 1u);
+        }
     }
-    return keys * 10 <= elems * 6;
-}
+    bool listed(const tc_kh_unit &u) const
+    {
+        const uint32_t b0 = u.c0 / 32, b1 = (u.c1 + 31) / 32;
+        return b1 < unlisted.size() && unlisted[b1] == unlisted[b0];
+    }
+    bool pays(const tc_ctx *ctx, const tc_kh_unit &u) const
+    {
+        if (ctx->kh_parts.empty() || ctx->kh_parts[u.rb] > 2) return false;
+        const uint32_t b0 = u.c0 / 32, b1 = (u.c1 + 31) / 32;
+        const uint64_t elems = ctx->h_off[std::min<uint32_t>(ctx->n, b1 * 32)] - ctx->h_off[b0 * 32];
+        return (keys[b1] - keys[b0]) * 10 <= elems * 6;
+    }
+};
 
 int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index, bool force_block)
 {
@@ -1028,9 +1066,10 @@ int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t np
     if (!ctx->kj_split_valid || ctx->kj_split_key != key) {
         std::vector<tc_kh_unit> &blk = ctx->kj_units_blk, &old = ctx->kj_units_old;
         blk.clear(); old.clear();
+        const KjRouting route(ctx);
         for (size_t u = part; u < ctx->kh_edge_units.size(); u += (nparts ? nparts : 1)) {
             const tc_kh_unit &un = ctx->kh_edge_units[u];
-            (kj_unit_listed(ctx, un) && (force_block || kj_unit_pays(ctx, un)) ? blk : old).push_back(un);
+            (route.listed(un) && (force_block || route.pays(ctx, un)) ? blk : old).push_back(un);
         }
         if (blk.size() + old.size() > ctx->kj_units_cap || !ctx->d_kj_units) {
             cudaFree(ctx->d_kj_units);
