@@ -382,10 +382,11 @@ def run_pairs(args):
                          "pass_call_ms_steps": [round(x, 3) for x in k3_steps],
                          "binding_units": binding,
                          "note": "algorithmic bytes = SURVEY 8(d)'s operand bytes 8*(|A|+|B|) = 16000 B/pair x pairs per "
-                                 "launch.  Every column element is probed once per 32 row sketches (shared-memory hash "
-                                 "join), so the operand bytes are served from shared memory/L2, not HBM: frac > 1 is "
-                                 "expected, `traffic` is the measured DRAM bytes, and the binding units are the issue "
-                                 "slots / ALU pipe (DESIGN.md K3H)"},
+                                 "launch.  Every distinct rank of a 32-sketch column block is probed once per 32 row "
+                                 "sketches (shared-memory hash join over per-block union lists), so the operand bytes "
+                                 "are served from shared memory/L2, not HBM: frac > 1 is expected, `traffic` is the "
+                                 "measured DRAM bytes, and the binding units are the issue slots / ALU pipe / "
+                                 "shared-memory pipe (DESIGN.md K3J)"},
             "e2e": {"value": (pairs_per_step_all) / (e2e_ms / 1e3), "unit": "pairs/s",
                     "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "ms_per_step": e2e_ms},

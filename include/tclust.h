@@ -133,7 +133,8 @@ int tc_pair_common_b(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_
  * owned by `part` of `nparts` (multi-GPU sharding; 0/1 = everything).  Emits the candidate
  * edges of compute_minhash_mst: common >= 1 and max(size) <= radio*min(size)
  * (src/MST.cpp:1470,1481-1487).  Edges stay on the device for tc_mst_*; n_pairs / n_edges
- * (may be NULL) receive the pairs evaluated and edges kept by this call.
+ * (may be NULL) receive the pairs evaluated and edges kept by this call.  The edge list has no defined order; (i, j)
+ * are always ids of the uploaded set with j < i, also when the pass ran on the library's internally reordered copy.
  */
 int tc_allpairs_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts,
                      uint64_t *n_pairs, uint64_t *n_edges);
