@@ -88,6 +88,8 @@ struct tc_ctx {
     tc_kh_unit *d_kj_units = nullptr;
     uint64_t kj_split_key = 0;
     bool kj_split_valid = false;
+    uint64_t pairs_cache_key = 0, pairs_cache_val = 0;     // n_pairs of the last sharded pass (tc_allpairs_pass, nparts > 1)
+    bool pairs_cache_valid = false;
 
     // reordered shadow copy of the sketch set for the dense pass (k3r_reorder.cu); d_perm (held by the shadow): new id -> id
     tc_ctx *shadow = nullptr;

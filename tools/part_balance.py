@@ -18,5 +18,6 @@ for rep in range(2):
     t0 = time.time(); ctx.allpairs_pass(4); t_all = time.time() - t0
     parts = []
     for p in range(P):
-        t0 = time.time(); np_, ne = ctx.allpairs_pass(4, p, P); parts.append((time.time() - t0, np_, ne))
-    print("all %.1f ms" % (t_all * 1e3), " ".join("part%d %.1f ms (%d pairs, %d edges)" % (p, t * 1e3, a, b) for p, (t, a, b) in enumerate(parts)))
+        ctx.allpairs_pass(4, p, P)          # the unit routing of a part is cached after its first pass
+        t0 = time.time(); np_, ne = ctx.allpairs_pass(4, p, P); parts.append((time.time() - t0, ctx.last_pass_kernel_ms, np_, ne))
+    print("all %.1f ms" % (t_all * 1e3), " ".join("part%d %.2f ms call / %.2f ms kernel (%d pairs, %d edges)" % (p, t * 1e3, k, a, b) for p, (t, k, a, b) in enumerate(parts)))
