@@ -503,7 +503,14 @@ constexpr uint32_t KJ_TILE_WORDS = 512;                             // 32 x 32 u
 constexpr uint32_t KJ_TILE_STATE = KJ_TILE_WORDS + 1;               // + "tile had a hit" flag
 constexpr size_t KJ_SMEM = (size_t)KH_SLOTS * 8 + (size_t)KJ_FWORDS * 4 + (size_t)32 * KJ_TILE_WORDS * 4;
 static_assert(KJ_SMEM <= 227 * 1024 - 1024, "K3J shared memory");
-static_assert((KH_CSEG / 32) * KJ_TILE_STATE <= KH_CSEG * KH_STATE_CAND, "K3J tile state fits the per-CTA scratch");
+// K3J units are wider than K3H's: the per-unit costs (table build, the wait for the last warp at the unit barrier) are
+// a quarter of the pass at 4096 columns per unit (59.4 ms -> 51.1 ms at 8192)
+// (46.8 ms at 16384).  The width is chosen per pass (kj_pick_cseg): as wide as possible while every CTA still gets
+// enough units for the dynamic hand-out to even out the tail.
+constexpr uint32_t KJ_CSEG_MAX = 32768;
+constexpr uint32_t KJ_HEAVY_CAP = 256;                                  // deferred tiles per unit and partition
+constexpr size_t KJ_STATE_WORDS = (size_t)(KJ_CSEG_MAX / 32) * KJ_TILE_STATE;   // per-CTA tile state (P > 1 only)
+constexpr size_t KH_STATE_WORDS_MAX = KJ_STATE_WORDS > (size_t)KH_CSEG * KH_STATE_CAND ? KJ_STATE_WORDS : (size_t)KH_CSEG * KH_STATE_CAND;
 
 __device__ __forceinline__ uint32_t kj_fword(uint32_t h) { return h >> (32 - (KJ_FBITS - 5)); }
 
@@ -513,7 +520,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
     uint2 *table = reinterpret_cast<uint2 *>(kh_smem);
     uint32_t *filter = reinterpret_cast<uint32_t *>(kh_smem + (size_t)KH_SLOTS * 8);
     uint32_t *cnt_all = filter + KJ_FWORDS;
-    __shared__ uint32_t s_unit, s_next, s_nheavy, s_heavy[KH_CSEG / 32];
+    __shared__ uint32_t s_unit, s_next, s_nheavy, s_heavy[KJ_HEAVY_CAP];
     __shared__ uint32_t s_lo[32], s_hi[32], s_len[32];
     __shared__ unsigned long long s_base[32];
 
@@ -526,7 +533,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
     asm volatile("" : "+r"(filt_addr));
     uint32_t *cntw = cnt_all + warp * KJ_TILE_WORDS;                  // this warp's tile counters, as 512 words
     uint16_t *cnt = reinterpret_cast<uint16_t *>(cntw);              // cnt[r * 32 + c]
-    uint32_t *state = a.state + (size_t)blockIdx.x * KH_CSEG * KH_STATE_CAND;
+    uint32_t *state = a.state + (size_t)blockIdx.x * KH_STATE_WORDS_MAX;
 
     for (;;) {
         if (tid == 0) s_unit = (uint32_t)(atomicAdd(&a.counters[2], 1ULL) * a.nparts + a.part);
@@ -735,8 +742,25 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                 const bool deferred = stream_slice(keys, cmasks, lo, hi, true, anyhit);
                 __syncwarp();
                 if (deferred) {                                   // redone by the whole CTA below
-                    if (lane == 0) s_heavy[atomicAdd(&s_nheavy, 1u)] = cb;
-                    continue;
+                    uint32_t slot = 0;
+                    if (lane == 0) slot = atomicAdd(&s_nheavy, 1u);
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    if (slot < KJ_HEAVY_CAP) {
+                        if (lane == 0) s_heavy[slot] = cb;
+                        continue;
+                    }
+                    // list full: this warp redoes the tile on its own
+                    anyhit = p == 0 ? 0u : tst[KJ_TILE_WORDS];
+                    if (anyhit) {
+#pragma unroll
+                        for (int q = 0; q < 16; q++) cntw[lane + 32 * q] = tst[lane + 32 * q];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 16; q++) cntw[lane + 32 * q] = 0u;
+                    }
+                    __syncwarp();
+                    stream_slice(keys, cmasks, lo, hi, false, anyhit);
+                    __syncwarp();
                 }
                 if (p + 1 < P) {
                     if (lane == 0) tst[KJ_TILE_WORDS] = anyhit;
@@ -752,7 +776,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
             __syncthreads();
             // ---- deferred tiles: all warps share one tile -- warp w streams the w-th 32nd of the list into its own
             //      counters, then sums row w over the 32 counter sets and finishes that row
-            const uint32_t nheavy = s_nheavy;
+            const uint32_t nheavy = min(s_nheavy, KJ_HEAVY_CAP);
             for (uint32_t hx = 0; hx < nheavy; hx++) {
                 const uint32_t cb = s_heavy[hx];
                 const uint32_t D = a.bu_count[cb * KH_DREC];
@@ -918,7 +942,7 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
     const long long mine = ((long long)units.size() - a.part + a.nparts - 1) / a.nparts;
     if (mine <= 0) { TC_CUDA(cudaStreamSynchronize(ctx->stream)); return 0; }
     const int grid = (int)std::min<long long>(mine, ctx->num_sms);
-    if (!ctx->d_kh_state) TC_CUDA(cudaMalloc(&ctx->d_kh_state, (size_t)ctx->num_sms * KH_CSEG * KH_STATE_CAND * 4));
+    if (!ctx->d_kh_state) TC_CUDA(cudaMalloc(&ctx->d_kh_state, (size_t)ctx->num_sms * KH_STATE_WORDS_MAX * 4));
     a.ranks = ctx->d_ranks; a.off = reinterpret_cast<const unsigned long long *>(ctx->d_off); a.size = ctx->d_size;
     a.n = ctx->n; a.pivots = ctx->d_kh_pivots; a.pivoff = ctx->d_kh_pivoff;
     a.units = d_resident ? d_resident : ctx->d_kh_units; a.nunits = (uint32_t)units.size();
@@ -947,21 +971,25 @@ int tc_launch_join_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, ui
     return kh_launch(ctx, a, units);
 }
 
+// unit list of an edge pass: pairs (i >= start_index, j < i); row block rb needs the columns [0, rb*32+31); units are
+// segment-major so that all CTAs stream the same column segment at the same time (L2 reuse)
+static void kh_edge_unit_list(tc_ctx *ctx, uint32_t start_index, uint32_t cseg)
+{
+    const uint32_t n = ctx->n, nrb = (n + 31) / 32;
+    if (ctx->kh_edge_units_n == n && ctx->kh_edge_units_start == start_index && ctx->kh_edge_units_cseg == cseg) return;
+    ctx->kh_edge_units.clear();
+    for (uint32_t c0 = 0; c0 < n; c0 += cseg)
+        for (uint32_t rb = std::max(c0 / 32, start_index / 32); rb < nrb; rb++) {
+            const uint32_t c1 = std::min<uint32_t>(std::min(n, c0 + cseg), rb * 32 + 31);
+            if (c1 > c0) ctx->kh_edge_units.push_back(tc_kh_unit{rb, c0, c1});
+        }
+    ctx->kh_edge_units_n = n; ctx->kh_edge_units_start = start_index; ctx->kh_edge_units_cseg = cseg;
+    ctx->kh_units_on_device = false; ctx->kj_split_valid = false;
+}
+
 int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index)
 {
-    // pairs (i >= start_index, j < i): row block rb needs the columns [0, rb*32+31); units segment-major so that
-    // all CTAs stream the same column segment at the same time (L2 reuse)
-    const uint32_t n = ctx->n, nrb = (n + 31) / 32;
-    if (ctx->kh_edge_units_n != n || ctx->kh_edge_units_start != start_index) {
-        ctx->kh_edge_units.clear();
-        for (uint32_t c0 = 0; c0 < n; c0 += KH_CSEG)
-            for (uint32_t rb = std::max(c0 / 32, start_index / 32); rb < nrb; rb++) {
-                const uint32_t c1 = std::min<uint32_t>(std::min(n, c0 + KH_CSEG), rb * 32 + 31);
-                if (c1 > c0) ctx->kh_edge_units.push_back(tc_kh_unit{rb, c0, c1});
-            }
-        ctx->kh_edge_units_n = n; ctx->kh_edge_units_start = start_index;
-        ctx->kh_units_on_device = false;
-    }
+    kh_edge_unit_list(ctx, start_index, KH_CSEG);
     KHArgs a{};
     a.mode = KH_MODE_EDGES; a.part = part; a.nparts = nparts ? nparts : 1; a.row_min = start_index;
     a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
@@ -1047,20 +1075,23 @@ struct KjRouting {
     }
 };
 
+// columns per K3J unit: the widest power of two up to KJ_CSEG_MAX that still leaves every CTA of every rank 8 units
+// (mirrored by rabbittclust_b200/mst_dist.py: join_cseg)
+static uint32_t kj_pick_cseg(uint32_t n, uint32_t start_index, uint32_t nparts, int num_sms)
+{
+    const uint64_t nrb = (n + 31) / 32, rb0 = start_index / 32;
+    for (uint32_t cseg = KJ_CSEG_MAX; cseg > KH_CSEG; cseg >>= 1) {
+        uint64_t units = 0;
+        for (uint64_t c0 = 0; c0 < n; c0 += cseg) units += nrb - std::max<uint64_t>(c0 / 32, rb0);
+        if (units >= (uint64_t)8 * nparts * (uint64_t)num_sms) return cseg;
+    }
+    return KH_CSEG;
+}
+
 int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index, bool force_block)
 {
-    const uint32_t n = ctx->n, nrb = (n + 31) / 32;
-    // the unit list of K3H (also what tc_allpairs_pass counts pairs from), split by kernel
-    if (ctx->kh_edge_units_n != n || ctx->kh_edge_units_start != start_index) {
-        ctx->kh_edge_units.clear();
-        for (uint32_t c0 = 0; c0 < n; c0 += KH_CSEG)
-            for (uint32_t rb = std::max(c0 / 32, start_index / 32); rb < nrb; rb++) {
-                const uint32_t c1 = std::min<uint32_t>(std::min(n, c0 + KH_CSEG), rb * 32 + 31);
-                if (c1 > c0) ctx->kh_edge_units.push_back(tc_kh_unit{rb, c0, c1});
-            }
-        ctx->kh_edge_units_n = n; ctx->kh_edge_units_start = start_index;
-        ctx->kh_units_on_device = false; ctx->kj_split_valid = false;
-    }
+    // the unit list (also what tc_allpairs_pass counts pairs from), split by kernel
+    kh_edge_unit_list(ctx, start_index, kj_pick_cseg(ctx->n, start_index, nparts ? nparts : 1, ctx->num_sms));
     // the routing of this rank's units is decided once per (sketch set, start_index, part) and kept on the device
     const uint64_t key = ((uint64_t)part << 40) ^ ((uint64_t)(nparts ? nparts : 1) << 33) ^ ((uint64_t)start_index << 1) ^ (force_block ? 1u : 0u);
     if (!ctx->kj_split_valid || ctx->kj_split_key != key) {
@@ -1069,7 +1100,9 @@ int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t np
         const KjRouting route(ctx);
         for (size_t u = part; u < ctx->kh_edge_units.size(); u += (nparts ? nparts : 1)) {
             const tc_kh_unit &un = ctx->kh_edge_units[u];
-            (route.listed(un) && (force_block || route.pays(ctx, un)) ? blk : old).push_back(un);
+            if (route.listed(un) && (force_block || route.pays(ctx, un))) { blk.push_back(un); continue; }
+            for (uint32_t c0 = un.c0; c0 < un.c1; c0 += KH_CSEG)          // K3H's per-CTA column state holds KH_CSEG columns
+                old.push_back(tc_kh_unit{un.rb, c0, std::min(un.c1, c0 + KH_CSEG)});
         }
         if (blk.size() + old.size() > ctx->kj_units_cap || !ctx->d_kj_units) {
             cudaFree(ctx->d_kj_units);

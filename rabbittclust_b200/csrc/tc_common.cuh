@@ -76,7 +76,7 @@ struct tc_ctx {
     tc_kh_unit *d_kh_units = nullptr;
     size_t kh_units_cap = 0;
     std::vector<tc_kh_unit> kh_edge_units;
-    uint32_t kh_edge_units_n = 0, kh_edge_units_start = 0;
+    uint32_t kh_edge_units_n = 0, kh_edge_units_start = 0, kh_edge_units_cseg = 0;
     bool kh_units_on_device = false;     // d_kh_units currently holds kh_edge_units
     // K3J block join: per 32-sketch block the sorted distinct ranks + 32-bit membership masks, stored at the element
     // offset of the block's first sketch; bu_count[b] = number of distinct ranks (0xFFFFFFFF: block too large, no list)

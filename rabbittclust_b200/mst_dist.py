@@ -23,9 +23,24 @@ def tile_owner(t, nparts):
     return t % nparts
 
 
-def join_units(n, cseg=4096):
-    """Work units of the hash-join dense pass (k3h_join.cu: tc_launch_join_edges): row block rb x column
+def join_cseg(n, nparts=1, num_sms=148, start_index=0):
+    """Columns per unit of the default dense pass (k3h_join.cu: kj_pick_cseg): the widest power of two up to 32768
+    that leaves every CTA of every rank 8 units; 4096 at least (and always with TCLUST_PASS_IMPL=join)."""
+    nrb, rb0 = (n + 31) // 32, start_index // 32
+    cseg = 32768
+    while cseg > 4096:
+        units = sum(nrb - max(c0 // 32, rb0) for c0 in range(0, n, cseg))
+        if units >= 8 * nparts * num_sms:
+            return cseg
+        cseg >>= 1
+    return 4096
+
+
+def join_units(n, cseg=None, nparts=1):
+    """Work units of the default dense pass (k3h_join.cu: tc_launch_blockjoin_edges): row block rb x column
     segment [c0, c1), segment-major.  Unit u belongs to rank u % nparts."""
+    if cseg is None:
+        cseg = join_cseg(n, nparts)
     nrb = (n + 31) // 32
     units = []
     for c0 in range(0, n, cseg):
@@ -41,7 +56,7 @@ def owned_pairs(n, part, nparts, impl="join", group=32):
     (units) or the first-generation merge pass (32x32 tiles, TCLUST_PASS_IMPL=merge)."""
     total = 0
     if impl == "join":
-        for u, (rb, c0, c1) in enumerate(join_units(n)):
+        for u, (rb, c0, c1) in enumerate(join_units(n, nparts=nparts)):
             if u % nparts != part:
                 continue
             for i in range(rb * 32, min(n, rb * 32 + 32)):
