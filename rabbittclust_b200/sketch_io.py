@@ -44,6 +44,25 @@ def write_minhash_folder(folder, sketches, names, k, sketch_size=1000, containme
                 fi.write(sn + cb)
 
 
+def write_minhash_folder_uniform(folder, hashes, n, s, k, total_len=1_000_000):
+    """The same two files for n sketches of exactly s hashes each (hashes: flat u64 array of n*s), written in bulk --
+    0.8 GB at n = 100000 in a second instead of a Python loop per sketch."""
+    os.makedirs(folder, exist_ok=True)
+    rec = np.empty((n, s + 1), "<u8")            # rows of [count][hashes]
+    rec[:, 0] = s
+    rec[:, 1:] = np.asarray(hashes[:n * s], "<u8").reshape(n, s)
+    with open(os.path.join(folder, "hash.sketch"), "wb") as fh:
+        fh.write(struct.pack("<ii?i", 0, k, False, s))
+        rec.tofile(fh)
+    with open(os.path.join(folder, "info.sketch"), "wb") as fi:
+        fi.write(struct.pack("<?Q", True, n))
+        cb = b"synthetic"
+        for i in range(n):
+            sn = b"g%06d" % i
+            fn = sn + b".fna"
+            fi.write(struct.pack("<iiiiQ", len(fn), len(sn), len(cb), 0, int(total_len)) + fn + sn + cb)
+
+
 def read_hash_sketch(path):
     """-> dict(func_id, k, containment, param, sketches=[np.uint64...])."""
     with open(path, "rb") as f:
