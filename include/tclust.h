@@ -114,6 +114,10 @@ int tc_sketch_kssd_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const uint64_t *rec
  */
 int tc_sketches_upload(tc_ctx *ctx, const uint64_t *hashes, const uint64_t *off, uint32_t n);
 int tc_sketches_upload_dev(tc_ctx *ctx, const uint64_t *hashes_dev, const uint64_t *off, uint32_t n);
+/* the same set given the way the reference holds it -- one array per sketch (vector<SketchInfo>, each with its own
+ * storeMinHashes() / hash64_arr vector): rows[g] points at sizes[g] hashes.  The rows are gathered through page-locked
+ * staging buffers while earlier chunks are already on their way to the device, so the caller needs no flat copy. */
+int tc_sketches_upload_rows(tc_ctx *ctx, const uint64_t *const *rows, const uint64_t *sizes, uint32_t n);
 
 /* validation: common[i-i0][j-j0] = |sketch_i n sketch_j| for i in [i0,i1), j in [j0,j1)
  * (semantic A: the counts of src/MST.cpp:1409-1435).  impl 0 = tiled merge kernel (k3_tile.cu),

@@ -20,7 +20,7 @@ PAIR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("common", "<u4")])
 SYMBOLS = [
     "tc_version", "tc_last_error", "tc_ctx_create", "tc_ctx_destroy", "tc_kernel_launches", "tc_last_pass_kernel_ms", "tc_stream",
     "tc_host_alloc", "tc_host_free", "tc_sketch_minhash", "tc_sketch_minhash_dev", "tc_kssd_shuffled_dim", "tc_sketch_kssd", "tc_sketch_kssd_dev",
-    "tc_sketches_upload", "tc_sketches_upload_dev", "tc_pair_common", "tc_allpairs_pass",
+    "tc_sketches_upload", "tc_sketches_upload_dev", "tc_sketches_upload_rows", "tc_pair_common", "tc_allpairs_pass",
     "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_mst",
     "tc_greedy_scan", "tc_greedy_cluster",
     "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce", "tc_greedy_cluster_kssd", "tc_dense_ani", "tc_allpairs_pass_from", "tc_mst_append",
@@ -71,6 +71,7 @@ def lib():
     L.tc_sketch_kssd_dev.argtypes = L.tc_sketch_kssd.argtypes
     L.tc_sketches_upload.argtypes = [vp, vp, u64p, C.c_uint32]
     L.tc_sketches_upload_dev.argtypes = [vp, vp, u64p, C.c_uint32]
+    L.tc_sketches_upload_rows.argtypes = [vp, vp, u64p, C.c_uint32]
     L.tc_pair_common.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u32p]
     L.tc_allpairs_pass.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, u64p, u64p]
     L.tc_edges_download.argtypes = [vp, vp, C.c_uint64, u64p]
@@ -220,6 +221,15 @@ class Context:
         self.n = len(off) - 1
         self.sizes = np.diff(off).astype(np.int64)
         _chk(lib().tc_sketches_upload(self._h, hashes.ctypes.data, _p(off, C.c_uint64), self.n))
+
+    def upload_rows(self, sketches):
+        """The same from one array per sketch, without a flat copy (tc_sketches_upload_rows)."""
+        rows = [np.ascontiguousarray(x, np.uint64) for x in sketches]
+        self.n = len(rows)
+        ptrs = np.array([r.ctypes.data for r in rows], np.uint64)
+        sizes = np.array([len(r) for r in rows], np.uint64)
+        self.sizes = sizes.astype(np.int64)
+        _chk(lib().tc_sketches_upload_rows(self._h, ptrs.ctypes.data, _p(sizes, C.c_uint64), self.n))
 
     def pair_common(self, i0, i1, j0, j1, impl=0):
         out = np.zeros((i1 - i0, j1 - j0), np.uint32)

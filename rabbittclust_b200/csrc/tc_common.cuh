@@ -108,6 +108,10 @@ struct tc_ctx {
     void *k1_ws = nullptr;
     void *k2_ws = nullptr;       // K2 (KSSD) pipeline workspace (k2_kssd.cu)
 
+    // page-locked staging of tc_sketches_upload_rows (two buffers, allocated on first use)
+    uint64_t *h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+
     // scratch
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <chrono>
+#include <thread>
 #include <cstring>
 #include <numeric>
 
@@ -115,6 +116,10 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     tc_k2_free(ctx);
     cudaFree(ctx->d_edge_count);
     cudaFree(ctx->d_scratch);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
+        if (ctx->ev_stage[b]) cudaEventDestroy(ctx->ev_stage[b]);
+    }
     cudaFree(ctx->d_kssd_dim); cudaFree(ctx->d_kssd_filter);
     cudaFree(ctx->d_kh_state); cudaFree(ctx->d_kh_units); cudaFree(ctx->d_kj_units);
     if (ctx->ev_pass0) cudaEventDestroy(ctx->ev_pass0);
@@ -226,8 +231,9 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
         ctx->cap_n = n + 1;
     }
     pt.mark("host prep + cudaMalloc");
-    TC_CUDA(cudaMemcpyAsync(ctx->d_hashes, hashes, total * 8,
-                            hashes_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (hashes != ctx->d_hashes)          // tc_sketches_upload_rows has staged them in place already
+        TC_CUDA(cudaMemcpyAsync(ctx->d_hashes, hashes, total * 8,
+                                hashes_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     TC_CUDA(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     sizes_kernel<<<nblk(n, 256), 256, 0, st>>>(reinterpret_cast<unsigned long long *>(ctx->d_off), ctx->d_size, n);
     ctx->launches++;
@@ -323,6 +329,51 @@ extern "C" int tc_sketches_upload(tc_ctx *ctx, const uint64_t *hashes, const uin
 extern "C" int tc_sketches_upload_dev(tc_ctx *ctx, const uint64_t *hashes_dev, const uint64_t *off, uint32_t n)
 {
     return upload_common(ctx, hashes_dev, true, off, n);
+}
+
+// rows -> d_hashes through two page-locked staging buffers: host threads gather chunk c+1 while chunk c is copied
+extern "C" int tc_sketches_upload_rows(tc_ctx *ctx, const uint64_t *const *rows, const uint64_t *sizes, uint32_t n)
+{
+    TC_CUDA(cudaSetDevice(ctx->device));
+    TC_CHECK(n > 0, "tc_sketches_upload_rows: n == 0");
+    std::vector<uint64_t> off((size_t)n + 1, 0);
+    for (uint32_t i = 0; i < n; i++) off[i + 1] = off[i] + sizes[i];
+    const uint64_t total = off[n];
+    TC_CHECK(total < 0xFFFFFFF0ull, "tc_sketches_upload_rows: %llu hashes exceed the u32 rank space", (unsigned long long)total);
+    if (ensure_cap(&ctx->d_hashes, &ctx->cap_hashes, std::max<uint64_t>(total, 1))) return 1;
+    constexpr uint64_t CHUNK = 4u << 20;                         // hashes per staging buffer (32 MB)
+    for (int b = 0; b < 2; b++) {
+        if (!ctx->h_stage[b]) TC_CUDA(cudaMallocHost(&ctx->h_stage[b], CHUNK * 8));
+        if (!ctx->ev_stage[b]) TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_stage[b], cudaEventDisableTiming));
+    }
+    const unsigned nthreads = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    uint32_t g = 0;                                              // sketch holding element `pos`
+    int buf = 0;
+    for (uint64_t pos = 0; pos < total; pos += CHUNK, buf ^= 1) {
+        const uint64_t len = std::min(CHUNK, total - pos);
+        TC_CUDA(cudaEventSynchronize(ctx->ev_stage[buf]));       // the copy that last used this buffer is done
+        while (off[g + 1] <= pos) g++;
+        uint32_t g1 = g;
+        while (g1 < n && off[g1] < pos + len) g1++;              // sketches [g, g1) intersect the chunk
+        uint64_t *dst = ctx->h_stage[buf];
+        auto gather = [&](uint32_t a, uint32_t b) {
+            for (uint32_t i = a; i < b; i++) {
+                const uint64_t lo = std::max(off[i], pos), hi = std::min(off[i + 1], pos + len);
+                if (hi > lo) memcpy(dst + (lo - pos), rows[i] + (lo - off[i]), (hi - lo) * 8);
+            }
+        };
+        const uint32_t cnt = g1 - g;
+        if (nthreads == 1 || cnt < 64) gather(g, g1);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nthreads; t++)
+                th.emplace_back(gather, g + (uint32_t)((uint64_t)cnt * t / nthreads), g + (uint32_t)((uint64_t)cnt * (t + 1) / nthreads));
+            for (std::thread &x : th) x.join();
+        }
+        TC_CUDA(cudaMemcpyAsync(ctx->d_hashes + pos, dst, len * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TC_CUDA(cudaEventRecord(ctx->ev_stage[buf], ctx->stream));
+    }
+    return upload_common(ctx, ctx->d_hashes, true, off.data(), n);
 }
 
 extern "C" int tc_pair_common(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, int impl,

@@ -758,11 +758,11 @@ void print_result(const vector<vector<int>> &cluster, const vector<Genome> &g, b
 // ------------------------------------------------------------------------------- clustering
 void upload(tc_ctx *ctx, const vector<Genome> &g)
 {
-    vector<uint64_t> off(g.size() + 1, 0);
-    for (size_t i = 0; i < g.size(); i++) off[i + 1] = off[i] + g[i].hashes.size();
-    vector<uint64_t> hashes(off.back() + 1);
-    for (size_t i = 0; i < g.size(); i++) std::copy(g[i].hashes.begin(), g[i].hashes.end(), hashes.begin() + off[i]);
-    tc_or_die(tc_sketches_upload(ctx, hashes.data(), off.data(), (uint32_t)g.size()), "sketch upload");
+    // one array per genome, as the reference holds them: the library gathers them through page-locked staging buffers
+    vector<const uint64_t *> rows(g.size());
+    vector<uint64_t> sizes(g.size());
+    for (size_t i = 0; i < g.size(); i++) { rows[i] = g[i].hashes.data(); sizes[i] = g[i].hashes.size(); }
+    tc_or_die(tc_sketches_upload_rows(ctx, rows.data(), sizes.data(), (uint32_t)g.size()), "sketch upload");
 }
 
 vector<vector<int>> clusters_from_forest(const vector<tc_edge> &mst, double threshold, int vertices)
@@ -922,6 +922,7 @@ void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_fi
     if (o.fast) std::sort(g.begin(), g.end(), [](const Genome &a, const Genome &b) { return a.hashes.size() > b.hashes.size(); });
 #endif
     upload(ctx, g);
+    if (getenv("TCLUST_TIMING")) cerr << "[tclust timing] upload of the sketches " << (now_s() - t2) * 1e3 << " ms" << endl;
 #ifdef GREEDY_CLUST
     vector<int32_t> rep_of(g.size());
     uint32_t nclust = 0;

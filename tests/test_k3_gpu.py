@@ -357,3 +357,25 @@ def test_reordered_copy_gives_the_same_edges_and_mst(tc, monkeypatch):
     for mode in ("1", None):
         for a, b in zip(res["0"], res[mode]):
             assert np.array_equal(a, b), mode
+
+
+def test_upload_rows_equals_flat_upload(tc):
+    """tc_sketches_upload_rows (one array per sketch, staged in 32 MB chunks) against the flat upload: ragged sizes,
+    empty sketches, a set larger than two staging buffers"""
+    rng = np.random.default_rng(21)
+    sk = synth.family_sketches(12, 20, s=900, seed=81, keep_lo=0.3)
+    sk += [np.unique(rng.integers(0, 2**63, int(z), dtype=np.uint64)) for z in rng.integers(0, 3000, 300)]
+    sk[7] = np.empty(0, np.uint64)
+    sk.append(np.empty(0, np.uint64))
+    big = np.unique(rng.integers(0, 2**64 - 2, 9_500_000, dtype=np.uint64))        # 76 MB: spans three chunks
+    sk.insert(100, big)
+    with tc.Context(0) as a, tc.Context(0) as b:
+        a.upload(sk)
+        b.upload_rows(sk)
+        n = len(sk)
+        assert np.array_equal(a.pair_common(0, n, 0, n, impl=1), b.pair_common(0, n, 0, n, impl=1))
+        a.allpairs_pass(4); b.allpairs_pass(4)
+        assert np.array_equal(np.sort(a.edges(), order=["i", "j"]), np.sort(b.edges(), order=["i", "j"]))
+    with tc.Context(0) as c:
+        with pytest.raises(tc.TclustError):
+            c.upload_rows([np.array([5, 3], np.uint64)])                          # unsorted input is still rejected

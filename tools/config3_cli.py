@@ -49,6 +49,7 @@ def run(exe, args, cwd):
     if r.returncode:
         sys.stderr.write(err[-3000:])
         raise SystemExit("failed: %s" % exe)
+    sys.stderr.write("".join(l + "\n" for l in err.splitlines() if l.startswith("[tclust timing]")))
     phases = {m.group(1).strip(): float(m.group(2)) for m in re.finditer(r"=+time of ([^=]+?) is: ([0-9.eE+-]+)", err)}
     return dt, phases
 
