@@ -43,7 +43,7 @@ constexpr uint32_t KH_STATE = 33;             // words of state per column: 32 c
 constexpr uint32_t KH_STATE_CAND = 65;        // candidate mode: + 32 smallest shared ranks
 constexpr size_t KH_SMEM = (size_t)KH_SLOTS * 8 + (size_t)KH_FWORDS * 4;
 constexpr uint32_t KH_SORT_CAP = 32768;       // row blocks up to this many elements get distinct-count partitions
-constexpr uint32_t KH_DREC = 7;               // per row block: distinct count + pivot candidates for P = 2, 3, 4
+constexpr uint32_t KH_DREC = 8;               // per row block: distinct count, pivot candidates for P = 2, 3, 4, shared elements
 
 enum { KH_MODE_MATRIX = 0, KH_MODE_EDGES = 1, KH_MODE_CAND = 2 };
 
@@ -69,12 +69,14 @@ struct KHArgs {
     tc_cand *cands; int lower_only, cmin_fixed, containment; double jmin, one_plus_jmin;
     // block join (K3J): union lists of the 32-sketch column blocks
     const uint32_t *bu_keys, *bu_mask, *bu_count;
+    const uint32_t *multi;          // bit r = rank r occurs in at least two sketches (only those can be shared)
 };
 
 // presence filter: word = top (KH_FBITS-5) bits of h = x * golden, the two bit positions = low 10 bits of h
 __device__ __forceinline__ uint32_t kh_fword(uint32_t h) { return h >> (32 - (KH_FBITS - 5)); }
 // two bit positions from the low 10 bits of h; the funnel shift takes its amount mod 32 (one SHF.L.W each)
 __device__ __forceinline__ uint32_t kh_fmask(uint32_t h) { return __funnelshift_l(0u, 1u, h) | __funnelshift_l(0u, 1u, h >> 5); }
+__device__ __forceinline__ bool kh_multi(const uint32_t *multi, uint32_t r) { return (__ldg(multi + (r >> 5)) >> (r & 31)) & 1u; }
 __device__ __forceinline__ uint32_t kh_slot(uint32_t x) { return (x * 0x85EBCA6Bu) >> 18; }   // 14 bits
 __device__ __forceinline__ uint32_t kh_lds(uint32_t addr)
 {
@@ -131,54 +133,87 @@ __global__ void k3h_pivot_kernel(const uint32_t *ranks, const unsigned long long
 // most of theirs (neighbouring genomes of one species): 32 x 1000 elements are then ~9000 distinct keys and fit one
 // partition instead of three.  One CTA sorts the row block's elements in shared memory (bitonic, <= 32768 u32),
 // counts the distinct ones and emits, for P = 2, 3, 4, the keys at distinct rank q*D/P as pivot candidates.
-// out[rb*7] = D (0xFFFFFFFF: block too large, the multiset-quantile kernel above takes over), out[rb*7+1..6] =
-// candidates for (P,q) = (2,1) (3,1) (3,2) (4,1) (4,2) (4,3).
+// out[rb*8] = D (0xFFFFFFFF: block too large, the multiset-quantile kernel above takes over), out[rb*8+1..6] =
+// candidates for (P,q) = (2,1) (3,1) (3,2) (4,1) (4,2) (4,3), out[rb*8+7] = elements that entered the sort.
 __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint32_t *ranks, const unsigned long long *off,
-                                                                      const uint32_t *size, uint32_t n, uint32_t *out,
-                                                                      uint32_t *ukeys, uint32_t *umask)
+                                                                      const uint32_t *size, uint32_t n, const uint32_t *multi,
+                                                                      uint32_t *out, uint32_t *ukeys, uint32_t *umask)
 {
     extern __shared__ __align__(16) uint8_t kh_smem[];
     uint32_t *buf = reinterpret_cast<uint32_t *>(kh_smem);
     uint8_t *rowof = kh_smem + (size_t)KH_SORT_CAP * 4;          // which of the 32 sketches an element came from
-    __shared__ uint32_t s_pos[33], s_warp[32], s_d;
+    __shared__ uint32_t s_pos[33], s_warp[32], s_d, s_cnt[32];
+    __shared__ unsigned long long s_raw;
     const uint32_t rb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
+        unsigned long long raw = 0;
+        for (uint32_t l = 0; l < 32; l++) { const uint32_t id = rb * 32 + l; raw += id < n ? size[id] : 0u; }
+        s_raw = raw;
+    }
+    __syncthreads();
+    // blocks of very large sketches are not worth the counting pass: no list, K3H handles them
+    if (s_raw > 8ull * KH_SORT_CAP) { if (tid == 0) out[rb * KH_DREC] = 0xFFFFFFFFu; return; }
+    // Only ranks that occur in at least two sketches of the whole set can ever be shared (bitmap `multi`, from the rank
+    // transform): the others -- strain-private k-mers, a quarter of every sketch in the bench model and far more
+    // between unrelated genomes -- take no part in any intersection and are left out of the lists and of the tables.
+    const uint32_t my_id = rb * 32 + warp;
+    const uint32_t my_len = my_id < n ? size[my_id] : 0u;
+    const uint32_t *my_row = ranks + (my_id < n ? off[my_id] : 0ULL);
+    {   // warp w counts the shared elements of row w
+        uint32_t c = 0;
+        for (uint32_t e0 = 0; e0 < my_len; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            const bool keep = e < my_len && kh_multi(multi, __ldg(my_row + e));
+            c += __popc(__ballot_sync(0xffffffffu, keep));
+        }
+        if (lane == 0) s_cnt[warp] = c;
+    }
+    __syncthreads();
+    if (tid == 0) {
         uint32_t acc = 0;
-        for (uint32_t l = 0; l < 32; l++) { s_pos[l] = acc; const uint32_t id = rb * 32 + l; acc += id < n ? size[id] : 0u; if (acc > KH_SORT_CAP) { acc = KH_SORT_CAP + 1; for (uint32_t m = l + 1; m <= 32; m++) s_pos[m] = acc; break; } }
+        for (uint32_t l = 0; l < 32; l++) { s_pos[l] = acc; acc += s_cnt[l]; }
         s_pos[32] = acc;
     }
     __syncthreads();
     const uint32_t total = s_pos[32];
+    if (tid == 0) out[rb * KH_DREC + 7] = total;                 // shared elements of the block
     if (total > KH_SORT_CAP) { if (tid == 0) out[rb * KH_DREC] = 0xFFFFFFFFu; return; }
     // Every row arrives sorted.  When the longest one fits R <= 1024 slots (R a power of two), row w goes into slots
     // [w*R, (w+1)*R) padded with 0xFFFFFFFF -- ascending for even w, descending for odd w -- which is the state of a
     // bitonic sort after its size-R stage: only the merges of size 2R .. 32R remain (65 of 120 stages at R = 1024).
     uint32_t maxlen = 0;
-    for (uint32_t l = 0; l < 32; l++) maxlen = max(maxlen, s_pos[l + 1] - s_pos[l]);
+    for (uint32_t l = 0; l < 32; l++) maxlen = max(maxlen, s_cnt[l]);
     uint32_t R = 32;
     while (R < maxlen) R <<= 1;
     const bool presorted = R * 32 <= KH_SORT_CAP;
     uint32_t npad = 1024, first_sz = 2;
-    if (presorted) {
-        npad = R * 32; first_sz = 2 * R;
-        const uint32_t id = rb * 32 + warp;
-        const uint32_t len = id < n ? size[id] : 0u;
-        const uint32_t *row = ranks + (id < n ? off[id] : 0ULL);
-        uint32_t *dst = buf + warp * R;
-        uint8_t *dro = rowof + warp * R;
-        if (!(warp & 1)) {
-            for (uint32_t e = lane; e < R; e += 32) { dst[e] = e < len ? __ldg(row + e) : 0xFFFFFFFFu; dro[e] = (uint8_t)warp; }
-        } else {
-            const uint32_t pad = R - len;
-            for (uint32_t e = lane; e < R; e += 32) { dst[e] = e < pad ? 0xFFFFFFFFu : __ldg(row + (R - 1 - e)); dro[e] = (uint8_t)warp; }
+    if (presorted) { npad = R * 32; first_sz = 2 * R; }
+    else while (npad < total) npad <<= 1;
+    {   // warp w compacts the shared elements of row w into its slots
+        const uint32_t cnt = s_cnt[warp];
+        const uint32_t base = presorted ? warp * R : s_pos[warp];
+        const bool reversed = presorted && (warp & 1);
+        uint32_t done = 0;
+        for (uint32_t e0 = 0; e0 < my_len; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            const uint32_t x = e < my_len ? __ldg(my_row + e) : 0u;
+            const bool keep = e < my_len && kh_multi(multi, x);
+            const unsigned b = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const uint32_t idx = done + __popc(b & ((1u << lane) - 1));
+                const uint32_t slot = base + (reversed ? R - 1 - idx : idx);
+                buf[slot] = x; rowof[slot] = (uint8_t)warp;
+            }
+            done += __popc(b);
         }
-    } else {   // general case: warp w copies row w, everything is sorted from scratch
-        while (npad < total) npad <<= 1;
-        const uint32_t id = rb * 32 + warp;
-        const uint32_t len = id < n ? size[id] : 0u;
-        const uint32_t *row = ranks + (id < n ? off[id] : 0ULL);
-        for (uint32_t e = lane; e < len; e += 32) { buf[s_pos[warp] + e] = __ldg(row + e); rowof[s_pos[warp] + e] = (uint8_t)warp; }
-        for (uint32_t e = total + tid; e < npad; e += KH_THREADS) { buf[e] = 0xFFFFFFFFu; rowof[e] = 0; }
+        if (presorted) {
+            for (uint32_t e = cnt + lane; e < R; e += 32) {
+                const uint32_t slot = base + (reversed ? R - 1 - e : e);
+                buf[slot] = 0xFFFFFFFFu; rowof[slot] = 0;
+            }
+        } else {
+            for (uint32_t e = total + tid; e < npad; e += KH_THREADS) { buf[e] = 0xFFFFFFFFu; rowof[e] = 0; }
+        }
     }
     __syncthreads();
     for (uint32_t sz = first_sz; sz <= npad; sz <<= 1)
@@ -295,6 +330,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                 const uint32_t bit = 1u << warp;
                 for (uint32_t e = s_lo[warp] + lane; e < s_hi[warp]; e += 32) {
                     const uint32_t x = __ldg(row + e);
+                    if (!kh_multi(a.multi, x)) continue;          // held by this sketch only: cannot be shared
                     const uint32_t h = x * 0x9E3779B1u;
                     atomicAnd(&filter[kh_fword(h)], ~kh_fmask(h));
                     uint32_t slot = kh_slot(x);
@@ -448,7 +484,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                         }
                     } else if (a.mode == KH_MODE_MATRIX) {
                         if (i >= a.i0 && i < a.i1 && j >= a.j0 && j < a.j1)
-                            a.out[(size_t)(i - a.i0) * (a.j1 - a.j0) + (j - a.j0)] = cnt;
+                            a.out[(size_t)(i - a.i0) * (a.j1 - a.j0) + (j - a.j0)] = i == j ? s_len[lane] : cnt;   // ranks private to one sketch are not in the table
                     } else {
                         bool keep = false;
                         if (i < a.n && i >= a.row_min && j < i && cnt >= 1u) {
@@ -572,6 +608,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                 const uint32_t bit = 1u << warp;
                 for (uint32_t e = s_lo[warp] + lane; e < s_hi[warp]; e += 32) {
                     const uint32_t x = __ldg(row + e);
+                    if (!kh_multi(a.multi, x)) continue;          // held by this sketch only: cannot be shared
                     const uint32_t h = x * 0x9E3779B1u;
                     atomicAnd(&filter[kj_fword(h)], ~kh_fmask(h));
                     uint32_t slot = kh_slot(x);
@@ -691,7 +728,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                 const uint32_t i = rb * 32 + row, j = cb * 32 + lane;
                 if (a.mode == KH_MODE_MATRIX) {
                     if (i >= a.i0 && i < a.i1 && j >= a.j0 && j < a.j1)
-                        a.out[(size_t)(i - a.i0) * (a.j1 - a.j0) + (j - a.j0)] = c;
+                        a.out[(size_t)(i - a.i0) * (a.j1 - a.j0) + (j - a.j0)] = i == j ? s_len[row] : c;   // private ranks are not in the table
                     return;
                 }
                 bool keep = false;
@@ -849,8 +886,9 @@ int tc_kh_prepare(tc_ctx *ctx)
         }
         ctx->cap_bu = ctx->total + 1;
     }
+    TC_CHECK(ctx->d_multi, "tc_kh_prepare: no multiplicity bitmap");
     k3h_distinct_kernel<<<nrb, KH_THREADS, KH_SORT_CAP * 5, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
-                                                                 ctx->d_size, ctx->n, d_dist, ctx->d_bu_keys, ctx->d_bu_mask);
+                                                                 ctx->d_size, ctx->n, ctx->d_multi, d_dist, ctx->d_bu_keys, ctx->d_bu_mask);
     ctx->launches++;
     std::vector<uint32_t> dist((size_t)nrb * KH_DREC);
     cudaError_t e = cudaGetLastError();
@@ -947,7 +985,7 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
     a.n = ctx->n; a.pivots = ctx->d_kh_pivots; a.pivoff = ctx->d_kh_pivoff;
     a.units = d_resident ? d_resident : ctx->d_kh_units; a.nunits = (uint32_t)units.size();
     a.counters = ctx->d_edge_count; a.state = ctx->d_kh_state;
-    a.bu_keys = ctx->d_bu_keys; a.bu_mask = ctx->d_bu_mask; a.bu_count = ctx->d_bu_count;
+    a.bu_keys = ctx->d_bu_keys; a.bu_mask = ctx->d_bu_mask; a.bu_count = ctx->d_bu_count; a.multi = ctx->d_multi;
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count + 2, 0, sizeof(unsigned long long), ctx->stream));
     if (ctx->ev_pass0 && record_start) cudaEventRecord(ctx->ev_pass0, ctx->stream);   // kernel-only duration, tc_last_pass_kernel_ms
     if (block_kernel) k3j_block_kernel<<<grid, KH_THREADS, KJ_SMEM, ctx->stream>>>(a);

@@ -18,11 +18,10 @@
 
 namespace {
 
-// locality key of sketch i: the first of its leading ranks that occurs in another sketch too.  scan[] is the inclusive
-// scan of the head flags over the globally sorted hashes (rank r occupies the positions holding r + 1), left in the
-// sort workspace by the rank transform.
-__global__ void k3r_key_kernel(const uint32_t *ranks, const unsigned long long *off, const uint32_t *scan,
-                               unsigned long long total, uint32_t n, uint32_t *key, uint32_t *idx)
+// locality key of sketch i: the first of its leading ranks that occurs in another sketch too (bitmap `multi` of the
+// rank transform)
+__global__ void k3r_key_kernel(const uint32_t *ranks, const unsigned long long *off, const uint32_t *multi, uint32_t n,
+                               uint32_t *key, uint32_t *idx)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -31,15 +30,10 @@ __global__ void k3r_key_kernel(const uint32_t *ranks, const unsigned long long *
     uint32_t k = 0xFFFFFFFFu;
     if (len) {
         k = ranks[o];
-        const unsigned long long lim = len < 64 ? len : 64;
+        const unsigned long long lim = len < 256 ? len : 256;
         for (unsigned long long e = 0; e < lim; e++) {
             const uint32_t r = ranks[o + e];
-            unsigned long long lo = 0, hi = total;               // first position with scan > r
-            while (lo < hi) {
-                const unsigned long long mid = (lo + hi) >> 1;
-                if (scan[mid] > r) hi = mid; else lo = mid + 1;
-            }
-            if (lo + 1 < total && scan[lo + 1] == r + 1u) { k = r; break; }
+            if ((multi[r >> 5] >> (r & 31)) & 1u) { k = r; break; }
         }
     }
     key[i] = k;
@@ -105,15 +99,15 @@ static double list_ratio(const tc_ctx *c)
     return c->total ? (double)keys / (double)c->total : 1.0;
 }
 
-// Called at the end of an upload (the sort workspace still holds `d_scan`).  TCLUST_REORDER=0 never builds the copy,
+// Called at the end of an upload.  TCLUST_REORDER=0 never builds the copy,
 // =1 always uses it; default: build it when the input order leaves the union lists above 60 % of the elements (the
 // point below which the block join pays, kj_unit_pays) and use it when its lists are at least a fifth shorter.
-int tc_shadow_build(tc_ctx *ctx, const uint32_t *d_scan)
+int tc_shadow_build(tc_ctx *ctx)
 {
     ctx->use_shadow = false;
     const char *env = getenv("TCLUST_REORDER");
     const bool never = env && !strcmp(env, "0"), always = env && !strcmp(env, "1");
-    if (never || ctx->total == 0 || ctx->n < 64 || !d_scan) return 0;
+    if (never || ctx->total == 0 || ctx->n < 64 || !ctx->d_multi) return 0;
     const double own = list_ratio(ctx);
     if (!always && (ctx->n < 2048 || own <= 0.6)) return 0;
     const uint32_t n = ctx->n;
@@ -127,6 +121,7 @@ int tc_shadow_build(tc_ctx *ctx, const uint32_t *d_scan)
     tc_ctx *s = ctx->shadow;
     s->kh_edge_units.clear(); s->kh_edge_units_n = 0; s->kh_units_on_device = false; s->kj_split_valid = false;
     s->n = n; s->total = ctx->total;
+    s->d_multi = ctx->d_multi;                                  // same ranks, same bitmap (owned by ctx)
     // ---- permutation: stable sort of the sketch ids by locality key
     uint32_t *d_key = nullptr;                                  // key in, key out, id in | id out = d_perm
     size_t tmp_bytes = 0;
@@ -140,8 +135,8 @@ int tc_shadow_build(tc_ctx *ctx, const uint32_t *d_scan)
     }
     uint32_t *d_key_out = d_key + n, *d_idx = d_key + 2 * (size_t)n;
     void *d_tmp = reinterpret_cast<uint8_t *>(d_key) + (((size_t)n * 12 + 255) & ~(size_t)255);
-    k3r_key_kernel<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off), d_scan,
-                                                   ctx->total, n, d_key, d_idx);
+    k3r_key_kernel<<<(n + 127) / 128, 128, 0, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off), ctx->d_multi,
+                                                   n, d_key, d_idx);
     cudaError_t e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_key_out, d_idx, s->d_perm, (int)n, 0, 32, st);
     std::vector<uint32_t> perm(n);
     if (e == cudaSuccess) e = cudaMemcpyAsync(perm.data(), s->d_perm, (size_t)n * 4, cudaMemcpyDeviceToHost, st);

@@ -81,6 +81,8 @@ struct tc_ctx {
     // K3J block join: per 32-sketch block the sorted distinct ranks + 32-bit membership masks, stored at the element
     // offset of the block's first sketch; bu_count[b] = number of distinct ranks (0xFFFFFFFF: block too large, no list)
     uint32_t *d_bu_keys = nullptr, *d_bu_mask = nullptr, *d_bu_count = nullptr;
+    uint32_t *d_multi = nullptr;         // bitmap over the ranks: bit r set = rank r occurs in at least two sketches
+    uint64_t cap_multi = 0;              // words
     uint64_t cap_bu = 0, cap_bu_count = 0, cap_pivoff = 0, cap_pivots = 0, kj_units_cap = 0;   // grow-only: no cudaMalloc/cudaFree per upload
     std::vector<uint32_t> bu_count;
     std::vector<uint32_t> kh_parts;      // table partitions per row block
@@ -137,7 +139,7 @@ int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t np
 int tc_launch_join_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment, double jmin);
 int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index = 0);
 // reordered shadow copy (k3r_reorder.cu)
-int tc_shadow_build(tc_ctx *ctx, const uint32_t *d_scan);
+int tc_shadow_build(tc_ctx *ctx);
 int tc_shadow_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, bool force_block);
 void tc_shadow_free(tc_ctx *ctx);
 // representative table (k5_greedy.cu)

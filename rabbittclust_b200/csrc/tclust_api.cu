@@ -75,7 +75,8 @@ static void release_sketches(tc_ctx *ctx)
     cudaFree(ctx->d_hashes); cudaFree(ctx->d_off); cudaFree(ctx->d_size); cudaFree(ctx->d_ranks);
     cudaFree(ctx->d_gt); cudaFree(ctx->d_goff); cudaFree(ctx->d_edges); cudaFree(ctx->d_comp);
     cudaFree(ctx->d_kh_pivots); cudaFree(ctx->d_kh_pivoff);
-    cudaFree(ctx->d_bu_keys); cudaFree(ctx->d_bu_mask); cudaFree(ctx->d_bu_count);
+    cudaFree(ctx->d_bu_keys); cudaFree(ctx->d_bu_mask); cudaFree(ctx->d_bu_count); cudaFree(ctx->d_multi);
+    ctx->d_multi = nullptr; ctx->cap_multi = 0;
     ctx->d_bu_keys = nullptr; ctx->d_bu_mask = nullptr; ctx->d_bu_count = nullptr; ctx->cap_bu = 0; ctx->cap_bu_count = 0;
     ctx->d_kh_pivots = nullptr; ctx->d_kh_pivoff = nullptr; ctx->cap_pivoff = 0; ctx->cap_pivots = 0;
     ctx->d_hashes = nullptr; ctx->d_off = nullptr; ctx->d_size = nullptr; ctx->d_ranks = nullptr;
@@ -152,6 +153,15 @@ __global__ void scatter_rank_kernel(const uint32_t *scan, const uint32_t *perm, 
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) ranks[perm[i]] = scan[i] - 1u;  // inclusive scan of head flags, 0-based dense rank
+}
+// scan = inclusive scan of the head flags over the sorted hashes: rank r sits at the positions holding r + 1; the first
+// position of a run of two or more marks its rank in the bitmap
+__global__ void multi_bitmap_kernel(const uint32_t *scan, uint64_t n, uint32_t *multi)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    const uint32_t v = scan[i];
+    if (scan[i + 1] == v && (i == 0 || scan[i - 1] != v)) atomicOr(&multi[(v - 1u) >> 5], 1u << ((v - 1u) & 31));
 }
 // every sketch must be strictly ascending (sorted, duplicate-free): the merge and the hash join rely on it
 __global__ void check_sorted_kernel(const uint64_t *h, const unsigned long long *off, uint32_t n, unsigned int *bad)
@@ -255,7 +265,10 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     pt.mark("copy of the hashes + check");
 
     // ---- order-preserving dense rank transform: u64 hash -> u32 rank (equal hash <=> equal rank)
-    const uint32_t *d_scan = nullptr;      // rank + 1 of every position of the globally sorted hashes (sort workspace)
+    if (total == 0) {                      // nothing can be shared: an empty bitmap keeps the kernels' argument valid
+        if (ensure_cap(&ctx->d_multi, &ctx->cap_multi, 1)) return 1;
+        TC_CUDA(cudaMemsetAsync(ctx->d_multi, 0, 4, ctx->stream));
+    }
     if (total > 0) {
         // sort workspace: kept in the context's scratch between uploads (24 B per hash + cub's temporary storage)
         size_t tmp_bytes = 0, tmp2 = 0;
@@ -286,7 +299,11 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
         head_flag_kernel<<<nblk(total, 256), 256, 0, st>>>(kb.Current(), flag, total);
         TC_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp2, flag, flag, (int)total, st));
         scatter_rank_kernel<<<nblk(total, 256), 256, 0, st>>>(flag, vb.Current(), ctx->d_ranks, total);
-        d_scan = flag;
+        // which ranks occur in more than one sketch (sketches are duplicate-free, so a run of equal hashes spans sketches)
+        const uint64_t mwords = total / 32 + 1;
+        if (ensure_cap(&ctx->d_multi, &ctx->cap_multi, mwords)) return 1;
+        TC_CUDA(cudaMemsetAsync(ctx->d_multi, 0, mwords * 4, st));
+        multi_bitmap_kernel<<<nblk(total, 256), 256, 0, st>>>(flag, total, ctx->d_multi);
         ctx->launches += 12;  // iota, sort passes (cub), flags, scan, scatter (approximate; cub internals)
         TC_CUDA(cudaStreamSynchronize(st));
         pt.mark("flags + scan + scatter");
@@ -317,7 +334,7 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     pt.mark("interleaved layout");
     int rc = tc_kh_prepare(ctx);
     pt.mark("distinct counts + pivots");
-    if (!rc) rc = tc_shadow_build(ctx, d_scan);
+    if (!rc) rc = tc_shadow_build(ctx);
     pt.mark("reordered copy");
     return rc;
 }
