@@ -37,6 +37,7 @@
 #include <cstring>
 #include <ctime>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <queue>
 #include <string>
@@ -942,9 +943,11 @@ void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_fi
 #else
     vector<tc_edge> mst(g.size());
     uint64_t m = 0;
+    const double t_mst = now_s();
     tc_or_die(tc_mst(ctx, o.kmer, o.containment, o.threshold, mst.data(), &m), "MST generation");
     mst.resize(m);
     double t3 = now_s();
+    if (getenv("TCLUST_TIMING")) cerr << "[tclust timing] tc_mst " << (t3 - t_mst) * 1e3 << " ms" << endl;
     cerr << "========time of generateMST is: " << t3 - t2 << "========" << endl;
     if (save) save_mst(g, mst, folder, by_file, o.fast);
     write_tree_outputs(g, mst, by_file, o);
@@ -952,6 +955,7 @@ void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_fi
     print_result(cluster, g, by_file, o.output, o.threshold);
     cerr << "-----write the cluster result into: " << o.output << endl;
     cerr << "-----the cluster number of: " << o.output << " is: " << cluster.size() << endl;
+    if (getenv("TCLUST_TIMING")) cerr << "[tclust timing] forest, clusters, output " << (now_s() - t3) * 1e3 << " ms" << endl;
     if (o.dense) {
         // density maps + ANI histogram over the candidate pairs (GPU epilogue), then the reference's noise-removal
         // pass (sub_command.cpp:3070-3100; getNoiseNode MST.cpp:189-211, modifyForest :87-106)
@@ -1063,8 +1067,23 @@ int main(int argc, char **argv)
         return 0;
     }
 #endif
+    // The CUDA context takes about a second to come up on a 180 GB device: it is created on a second thread, so that
+    // --presketched can read its sketch files in the meantime; every other flow waits for it right away.
     tc_ctx *ctx = nullptr;
-    tc_or_die(tc_ctx_create(o.device, &ctx), "tc_ctx_create");
+    const bool timing = getenv("TCLUST_TIMING") != nullptr;
+    const double t_ctx = now_s();
+    string ctx_err;
+    std::future<int> ctx_ready = std::async(std::launch::async, [&]() {
+        const int rc = tc_ctx_create(o.device, &ctx);
+        if (rc) ctx_err = tc_last_error();                  // the error text is per thread
+        return rc;
+    });
+    auto need_ctx = [&]() {
+        if (!ctx_ready.valid()) return;
+        if (ctx_ready.get()) die("tc_ctx_create: " + ctx_err);
+        if (timing) cerr << "[tclust timing] CUDA context ready " << (now_s() - t_ctx) * 1e3 << " ms after start" << endl;
+    };
+    if (!(o.presketched && !o.append)) need_ctx();
     vector<Genome> g;
     if (o.append) {
         // classic append (no saved cluster state): append_clust_mst (sub_command.cpp:1578-1757) and
@@ -1159,6 +1178,7 @@ int main(int argc, char **argv)
         });
 #endif
         cerr << "========time of load genome Infos and sketch Infos is: " << now_s() - t0 << endl;
+        need_ctx();
         run_clustering(ctx, g, o, by_file, false, o.folder);
     } else {
         if (!o.has_input) { usage(argv[0]); die("option -i/--input or --presketched is required"); }
@@ -1182,6 +1202,9 @@ int main(int argc, char **argv)
         }
         run_clustering(ctx, g, o, o.by_file, save, folder);
     }
+    const double t_end = now_s();
+    need_ctx();
     tc_ctx_destroy(ctx);
+    if (timing) cerr << "[tclust timing] context teardown " << (now_s() - t_end) * 1e3 << " ms" << endl;
     return 0;
 }
