@@ -54,20 +54,63 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clock/throttle sampling during the timed region."""
+    """SM clock / throttle-reason sampling during the timed region.  The timed region of the pairs leg is tens of
+    milliseconds, so the samples come from NVML directly (a thread polling every ~2 ms; the ctypes/torch calls of the
+    timed loop release the GIL); `nvidia-smi -lms` is the fallback when pynvml cannot be used."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
-        self.period_ms = int(os.environ.get("TCLUST_BENCH_SAMPLER_MS", "200"))
+        self.period_ms = int(os.environ.get("TCLUST_BENCH_SAMPLER_MS", "2"))
+        self.nvml, self.handle, self.thread, self.stop_flag = None, None, None, threading.Event()
+        self.samples, self.reason_bits, self.max_mhz = [], 0, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:
+            import torch
+            u = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(u if u.startswith("GPU-") else "GPU-" + u)
+        except Exception:
+            h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        while True:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            except Exception:
+                pass
+            try:
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                try:
+                    self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                except Exception:
+                    pass
+            if self.stop_flag.wait(self.period_ms / 1e3):
+                return
 
     def start(self):
         if self.period_ms <= 0:
             return
         try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
+                                          "--format=csv,noheader,nounits", "-lms", str(max(self.period_ms, 20))],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -79,6 +122,17 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            nv, b = self.nvml, self.reason_bits
+            names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                     ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                     ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                     ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown)]
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(self.samples), "reasons": sorted(k for k, m in names if b & m), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -91,7 +145,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": reasons}
+                "samples": len(sm), "reasons": reasons, "source": "nvidia-smi"}
 
 
 def dist_env():

@@ -129,6 +129,62 @@ __global__ void k3h_pivot_kernel(const uint32_t *ranks, const unsigned long long
     }
 }
 
+// ---- register-blocked passes of the bitonic merges in k3h_distinct_kernel.  A merge of size sz is the strides sz/2 .. 1;
+// one pass over shared memory per stride (and a CTA barrier) made the sort 65 passes long.  kd_pass_high does B strides
+// 2^(j+B-1) .. 2^j (j >= 5) per pass: a thread holds the 2^B elements that differ in bits [j, j+B) and exchanges them in
+// registers (lanes walk consecutive addresses: no bank conflicts).  kd_pass_low does the nine strides 256 .. 1: a warp
+// owns a 512-element chunk, lane l holds elements l + 32k (k < 16); strides 256 .. 32 are register exchanges, 16 .. 1
+// warp shuffles.  Both need sz >= 512, so the direction bit (idx & sz) is the same for everything a thread touches.
+__device__ __forceinline__ void kd_cx(uint32_t &x, uint32_t &y, uint32_t &rx, uint32_t &ry, bool asc)
+{
+    if ((x > y) == asc) { uint32_t t = x; x = y; y = t; t = rx; rx = ry; ry = t; }
+}
+template <int B>
+__device__ __forceinline__ void kd_pass_high(uint32_t *buf, uint8_t *rowof, uint32_t npad, uint32_t sz, uint32_t j, uint32_t tid)
+{
+    constexpr int E = 1 << B;
+    for (uint32_t t = tid; t < npad / E; t += KH_THREADS) {
+        const uint32_t base = ((t >> j) << (j + B)) | (t & ((1u << j) - 1u));
+        const bool asc = (base & sz) == 0;
+        uint32_t v[E], r[E];
+#pragma unroll
+        for (int k = 0; k < E; k++) { v[k] = buf[base + ((uint32_t)k << j)]; r[k] = rowof[base + ((uint32_t)k << j)]; }
+#pragma unroll
+        for (int m = B - 1; m >= 0; m--)
+#pragma unroll
+            for (int k = 0; k < E; k++)
+                if (!(k & (1 << m))) kd_cx(v[k], v[k | (1 << m)], r[k], r[k | (1 << m)], asc);
+#pragma unroll
+        for (int k = 0; k < E; k++) { buf[base + ((uint32_t)k << j)] = v[k]; rowof[base + ((uint32_t)k << j)] = (uint8_t)r[k]; }
+    }
+}
+__device__ __forceinline__ void kd_pass_low(uint32_t *buf, uint8_t *rowof, uint32_t npad, uint32_t sz, uint32_t warp, uint32_t lane)
+{
+    for (uint32_t cb = warp * 512u; cb < npad; cb += (KH_THREADS / 32) * 512u) {
+        const bool asc = (cb & sz) == 0;
+        uint32_t v[16], r[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) { v[k] = buf[cb + lane + 32u * k]; r[k] = rowof[cb + lane + 32u * k]; }
+#pragma unroll
+        for (int m = 3; m >= 0; m--)
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if (!(k & (1 << m))) kd_cx(v[k], v[k | (1 << m)], r[k], r[k | (1 << m)], asc);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const bool upper = (lane & s) != 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint32_t ov = __shfl_xor_sync(0xffffffffu, v[k], s), orow = __shfl_xor_sync(0xffffffffu, r[k], s);
+                const uint32_t x = upper ? ov : v[k], y = upper ? v[k] : ov;     // x sits at the lower index
+                if ((x > y) == asc) { v[k] = ov; r[k] = orow; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) { buf[cb + lane + 32u * k] = v[k]; rowof[cb + lane + 32u * k] = (uint8_t)r[k]; }
+    }
+}
+
 // ---- distinct-aware partitions.  The table holds DISTINCT ranks, and the 32 sketches of a row block often share
 // most of theirs (neighbouring genomes of one species): 32 x 1000 elements are then ~9000 distinct keys and fit one
 // partition instead of three.  One CTA sorts the row block's elements in shared memory (bitonic, <= 32768 u32),
@@ -137,7 +193,7 @@ __global__ void k3h_pivot_kernel(const uint32_t *ranks, const unsigned long long
 // candidates for (P,q) = (2,1) (3,1) (3,2) (4,1) (4,2) (4,3), out[rb*8+7] = elements that entered the sort.
 __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint32_t *ranks, const unsigned long long *off,
                                                                       const uint32_t *size, uint32_t n, const uint32_t *multi,
-                                                                      uint32_t *out, uint32_t *ukeys, uint32_t *umask)
+                                                                      uint32_t *out, uint32_t *ukeys, uint32_t *umask, int blocked)
 {
     extern __shared__ __align__(16) uint8_t kh_smem[];
     uint32_t *buf = reinterpret_cast<uint32_t *>(kh_smem);
@@ -216,7 +272,24 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint3
         }
     }
     __syncthreads();
-    for (uint32_t sz = first_sz; sz <= npad; sz <<= 1)
+    for (uint32_t sz = first_sz; sz <= npad; sz <<= 1) {
+        if (blocked && sz >= 512) {
+            // strides sz/2 .. 512 in register-blocked passes of up to four strides, then 256 .. 1 in one pass
+            int top = 31 - __clz(sz) - 1;                        // exponent of the largest stride
+            while (top >= 9) {
+                const int B = min(4, top - 8);
+                const uint32_t j = (uint32_t)(top - B + 1);
+                if (B == 4) kd_pass_high<4>(buf, rowof, npad, sz, j, tid);
+                else if (B == 3) kd_pass_high<3>(buf, rowof, npad, sz, j, tid);
+                else if (B == 2) kd_pass_high<2>(buf, rowof, npad, sz, j, tid);
+                else kd_pass_high<1>(buf, rowof, npad, sz, j, tid);
+                __syncthreads();
+                top -= B;
+            }
+            kd_pass_low(buf, rowof, npad, sz, warp, lane);
+            __syncthreads();
+            continue;
+        }
         for (uint32_t stride = sz >> 1; stride > 0; stride >>= 1) {
             for (uint32_t t = tid; t < (npad >> 1); t += KH_THREADS) {
                 const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
@@ -228,6 +301,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint3
             }
             __syncthreads();
         }
+    }
     // distinct count: thread t owns the chunk [t*c, (t+1)*c)
     const uint32_t c = npad / KH_THREADS, b0 = tid * c;
     uint32_t mine = 0;
@@ -887,8 +961,11 @@ int tc_kh_prepare(tc_ctx *ctx)
         ctx->cap_bu = ctx->total + 1;
     }
     TC_CHECK(ctx->d_multi, "tc_kh_prepare: no multiplicity bitmap");
+    const char *sort_env = getenv("TCLUST_DISTINCT_SORT");       // "plain": one pass per stride (the first version)
+    const int blocked = !(sort_env && !strcmp(sort_env, "plain"));
     k3h_distinct_kernel<<<nrb, KH_THREADS, KH_SORT_CAP * 5, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
-                                                                 ctx->d_size, ctx->n, ctx->d_multi, d_dist, ctx->d_bu_keys, ctx->d_bu_mask);
+                                                                 ctx->d_size, ctx->n, ctx->d_multi, d_dist, ctx->d_bu_keys, ctx->d_bu_mask,
+                                                                 blocked);
     ctx->launches++;
     std::vector<uint32_t> dist((size_t)nrb * KH_DREC);
     cudaError_t e = cudaGetLastError();

@@ -24,6 +24,7 @@ void tc_set_error(const char *fmt, ...);
     } while (0)
 
 constexpr uint32_t TC_GROUP = 32;            // sketches per interleaved group (= warp width)
+constexpr int TC_UP_CHUNKS = 8;             // pieces of a chunked host upload (tclust_api.cu, upload_sorted_runs)
 constexpr uint32_t TC_SENT_A = 0xFFFFFFFFu;  // end-of-window sentinel, row streams
 constexpr uint32_t TC_SENT_B = 0xFFFFFFFEu;  // end-of-window sentinel, column streams
 constexpr uint32_t TC_RANK_MAX = 0xFFFFFFFDu;
@@ -113,6 +114,9 @@ struct tc_ctx {
     // page-locked staging of tc_sketches_upload_rows (two buffers, allocated on first use)
     uint64_t *h_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    // tc_sketches_upload of a large host array: copy stream + one event per piece (+1: "work stream idle")
+    cudaStream_t up_copy_stream = nullptr;
+    cudaEvent_t ev_chunk[TC_UP_CHUNKS + 1] = {};
 
     // scratch
     void *d_scratch = nullptr;

@@ -121,6 +121,8 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
         if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
         if (ctx->ev_stage[b]) cudaEventDestroy(ctx->ev_stage[b]);
     }
+    for (cudaEvent_t &e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
+    if (ctx->up_copy_stream) cudaStreamDestroy(ctx->up_copy_stream);
     cudaFree(ctx->d_kssd_dim); cudaFree(ctx->d_kssd_filter);
     cudaFree(ctx->d_kh_state); cudaFree(ctx->d_kh_units); cudaFree(ctx->d_kj_units);
     if (ctx->ev_pass0) cudaEventDestroy(ctx->ev_pass0);
@@ -211,6 +213,113 @@ struct PhaseTimer {
     }
 };
 
+// ---- sort workspace of the rank transform: two key and two value buffers + cub's temporary storage, carved out of the
+// context's scratch (24 B per hash + temporary storage; kept between uploads)
+constexpr int UP_CHUNKS = TC_UP_CHUNKS;
+struct UploadSort {
+    uint64_t *k_a = nullptr, *k_b = nullptr;
+    uint32_t *v_a = nullptr, *v_b = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const uint64_t *keys = nullptr;      // the globally sorted hashes ...
+    const uint32_t *vals = nullptr;      // ... and the input position of each
+    uint32_t *spare = nullptr;           // the value buffer not holding `vals`
+};
+
+static int upload_sort_workspace(tc_ctx *ctx, uint64_t total, uint64_t clen, UploadSort *us)
+{
+    cudaStream_t st = ctx->stream;
+    size_t tmp_bytes = 0, t = 0;
+    TC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)total, st));
+    if (clen == 0) {
+        cub::DoubleBuffer<uint64_t> kb0(nullptr, nullptr);
+        cub::DoubleBuffer<uint32_t> vb0(nullptr, nullptr);
+        TC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t, kb0, vb0, (int)total, 0, 64, st));
+        tmp_bytes = std::max(tmp_bytes, t);
+    } else {
+        // out-of-place sort of one piece (cub keeps its alternate buffers in the temporary storage) and the merges
+        TC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr,
+                                                (uint32_t *)nullptr, (int)clen, 0, 64, st));
+        tmp_bytes = std::max(tmp_bytes, t);
+        for (uint64_t w = clen; w < total; w *= 2) {
+            const uint64_t a = std::min(w, total), b = std::min(w, total - a);
+            t = 0;
+            TC_CUDA(cub::DeviceMerge::MergePairs(nullptr, t, (const uint64_t *)nullptr, (const uint32_t *)nullptr, (int)a,
+                                                 (const uint64_t *)nullptr, (const uint32_t *)nullptr, (int)b, (uint64_t *)nullptr,
+                                                 (uint32_t *)nullptr, ::cuda::std::less<>{}, st));
+            tmp_bytes = std::max(tmp_bytes, t);
+        }
+    }
+    tmp_bytes = (tmp_bytes + 255) & ~(size_t)255;
+    const size_t a256 = 255;
+    const size_t o_kb = (total * 8 + a256) & ~a256, o_va = o_kb + ((total * 8 + a256) & ~a256);
+    const size_t o_vb = o_va + ((total * 4 + a256) & ~a256), o_tmp = o_vb + ((total * 4 + a256) & ~a256);
+    void *ws = nullptr;
+    if (tc_scratch(ctx, o_tmp + tmp_bytes, &ws)) return 1;
+    uint8_t *wsb = static_cast<uint8_t *>(ws);
+    us->k_a = reinterpret_cast<uint64_t *>(wsb); us->k_b = reinterpret_cast<uint64_t *>(wsb + o_kb);
+    us->v_a = reinterpret_cast<uint32_t *>(wsb + o_va); us->v_b = reinterpret_cast<uint32_t *>(wsb + o_vb);
+    us->tmp = wsb + o_tmp; us->tmp_bytes = tmp_bytes;
+    return 0;
+}
+
+// Host hashes -> d_hashes in UP_CHUNKS pieces on the copy stream; on the work stream piece c is sorted (with its input
+// positions as values) into run c of buffer B as soon as its copy has landed, and whenever two neighbouring runs of one
+// width are complete they are merged into the other buffer (binary-counter order), so the work left when the last
+// byte arrives is one piece's sort and log2(UP_CHUNKS) merges instead of the sort of the whole set.
+static int upload_sorted_runs(tc_ctx *ctx, const uint64_t *hashes, uint64_t total, UploadSort *us)
+{
+    cudaStream_t st = ctx->stream;
+    if (!ctx->up_copy_stream) TC_CUDA(cudaStreamCreateWithFlags(&ctx->up_copy_stream, cudaStreamNonBlocking));
+    for (int c = 0; c <= UP_CHUNKS; c++)
+        if (!ctx->ev_chunk[c]) TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_chunk[c], cudaEventDisableTiming));
+    const uint64_t clen = ((total + UP_CHUNKS - 1) / UP_CHUNKS + 1023) & ~1023ull;
+    if (upload_sort_workspace(ctx, total, clen, us)) return 1;
+    // the copies start once everything queued on the work stream so far (a previous set's kernels) is done
+    TC_CUDA(cudaEventRecord(ctx->ev_chunk[UP_CHUNKS], st));
+    TC_CUDA(cudaStreamWaitEvent(ctx->up_copy_stream, ctx->ev_chunk[UP_CHUNKS], 0));
+    for (int c = 0; c < UP_CHUNKS; c++) {
+        const uint64_t pos = std::min(total, (uint64_t)c * clen), len = std::min(clen, total - pos);
+        if (len) TC_CUDA(cudaMemcpyAsync(ctx->d_hashes + pos, hashes + pos, len * 8, cudaMemcpyHostToDevice, ctx->up_copy_stream));
+        TC_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->up_copy_stream));
+    }
+    iota_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(us->v_a, total);
+    // level 0 (sorted pieces) lives in B, level 1 in A, level 2 in B, ...
+    auto kbuf = [&](int level) { return (level & 1) ? us->k_a : us->k_b; };
+    auto vbuf = [&](int level) { return (level & 1) ? us->v_a : us->v_b; };
+    int top = 0;
+    while ((1 << top) < UP_CHUNKS) top++;
+    for (int c = 0; c < UP_CHUNKS; c++) {
+        const uint64_t pos = std::min(total, (uint64_t)c * clen), len = std::min(clen, total - pos);
+        TC_CUDA(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
+        if (len) {
+            size_t tb = us->tmp_bytes;
+            TC_CUDA(cub::DeviceRadixSort::SortPairs(us->tmp, tb, (const uint64_t *)(ctx->d_hashes + pos), us->k_b + pos,
+                                                    (const uint32_t *)(us->v_a + pos), us->v_b + pos, (int)len, 0, 64, st));
+        }
+        for (int level = 1; level <= top && ((c + 1) & ((1 << level) - 1)) == 0; level++) {
+            const uint64_t w = clen << (level - 1);                        // width of the two runs being merged
+            const uint64_t p0 = std::min(total, (uint64_t)(c + 1 - (1 << level)) * clen);
+            const uint64_t la = std::min(w, total - p0), lb = std::min(w, total - p0 - la);
+            if (la + lb == 0) continue;
+            if (lb == 0) {
+                TC_CUDA(cudaMemcpyAsync(kbuf(level) + p0, kbuf(level - 1) + p0, la * 8, cudaMemcpyDeviceToDevice, st));
+                TC_CUDA(cudaMemcpyAsync(vbuf(level) + p0, vbuf(level - 1) + p0, la * 4, cudaMemcpyDeviceToDevice, st));
+                continue;
+            }
+            size_t tb = us->tmp_bytes;
+            TC_CUDA(cub::DeviceMerge::MergePairs(us->tmp, tb, (const uint64_t *)(kbuf(level - 1) + p0),
+                                                 (const uint32_t *)(vbuf(level - 1) + p0), (int)la,
+                                                 (const uint64_t *)(kbuf(level - 1) + p0 + la),
+                                                 (const uint32_t *)(vbuf(level - 1) + p0 + la), (int)lb, kbuf(level) + p0,
+                                                 vbuf(level) + p0, ::cuda::std::less<>{}, st));
+        }
+    }
+    us->keys = kbuf(top); us->vals = vbuf(top); us->spare = vbuf(top + 1);
+    ctx->launches += 2 * UP_CHUNKS;
+    return 0;
+}
+
 static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_device, const uint64_t *off, uint32_t n)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
@@ -241,7 +350,17 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
         ctx->cap_n = n + 1;
     }
     pt.mark("host prep + cudaMalloc");
-    if (hashes != ctx->d_hashes)          // tc_sketches_upload_rows has staged them in place already
+    // Host hashes of a large set arrive in UP_CHUNKS pieces on a copy stream; every piece is radix-sorted as soon as it
+    // has landed and the sorted runs are merged pairwise (cub::DeviceMerge), so that all but the last piece's sort and
+    // the last merges run under the PCIe copy (upload_sorted_runs below).  TCLUST_UPLOAD_OVERLAP=0: one copy, one sort; =1: pieces whatever the size.
+    const char *ov = getenv("TCLUST_UPLOAD_OVERLAP");
+    const bool ov_off = ov && !strcmp(ov, "0"), ov_force = ov && !strcmp(ov, "1");   // 1: whatever the size (tests)
+    const bool chunked = !hashes_on_device && hashes != ctx->d_hashes && !ov_off &&
+                         (total >= (16ull << 20) || (ov_force && total >= 2));
+    UploadSort us;
+    if (chunked) {
+        if (upload_sorted_runs(ctx, hashes, total, &us)) return 1;
+    } else if (hashes != ctx->d_hashes)   // tc_sketches_upload_rows has staged them in place already
         TC_CUDA(cudaMemcpyAsync(ctx->d_hashes, hashes, total * 8,
                                 hashes_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     TC_CUDA(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -270,35 +389,23 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
         TC_CUDA(cudaMemsetAsync(ctx->d_multi, 0, 4, ctx->stream));
     }
     if (total > 0) {
-        // sort workspace: kept in the context's scratch between uploads (24 B per hash + cub's temporary storage)
-        size_t tmp_bytes = 0, tmp2 = 0;
-        {
-            cub::DoubleBuffer<uint64_t> kb0(nullptr, nullptr);
-            cub::DoubleBuffer<uint32_t> vb0(nullptr, nullptr);
-            TC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb0, vb0, (int)total, 0, 64, st));
-            TC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp2, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)total, st));
-            tmp_bytes = std::max(tmp_bytes, tmp2);
+        if (!chunked) {
+            // sort workspace: kept in the context's scratch between uploads (24 B per hash + cub's temporary storage)
+            if (upload_sort_workspace(ctx, total, 0, &us)) return 1;
+            pt.mark("sort workspace");
+            TC_CUDA(cudaMemcpyAsync(us.k_a, ctx->d_hashes, total * 8, cudaMemcpyDeviceToDevice, st));
+            iota_kernel<<<nblk(total, 256), 256, 0, st>>>(us.v_a, total);
+            cub::DoubleBuffer<uint64_t> kb(us.k_a, us.k_b);
+            cub::DoubleBuffer<uint32_t> vb(us.v_a, us.v_b);
+            TC_CUDA(cub::DeviceRadixSort::SortPairs(us.tmp, us.tmp_bytes, kb, vb, (int)total, 0, 64, st));
+            us.keys = kb.Current(); us.vals = vb.Current(); us.spare = vb.Alternate();
         }
-        const size_t a256 = 255;
-        const size_t o_kout = (total * 8 + a256) & ~a256, o_vin = o_kout + ((total * 8 + a256) & ~a256);
-        const size_t o_vout = o_vin + ((total * 4 + a256) & ~a256), o_tmp = o_vout + ((total * 4 + a256) & ~a256);
-        void *ws = nullptr;
-        if (tc_scratch(ctx, o_tmp + tmp_bytes, &ws)) return 1;
-        uint8_t *wsb = static_cast<uint8_t *>(ws);
-        uint64_t *k_in = reinterpret_cast<uint64_t *>(wsb), *k_out = reinterpret_cast<uint64_t *>(wsb + o_kout);
-        uint32_t *v_in = reinterpret_cast<uint32_t *>(wsb + o_vin), *v_out = reinterpret_cast<uint32_t *>(wsb + o_vout);
-        void *tmp = wsb + o_tmp;
-        pt.mark("sort workspace");
-        TC_CUDA(cudaMemcpyAsync(k_in, ctx->d_hashes, total * 8, cudaMemcpyDeviceToDevice, st));
-        iota_kernel<<<nblk(total, 256), 256, 0, st>>>(v_in, total);
-        cub::DoubleBuffer<uint64_t> kb(k_in, k_out);
-        cub::DoubleBuffer<uint32_t> vb(v_in, v_out);
-        TC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kb, vb, (int)total, 0, 64, st));
         pt.mark("radix sort");
-        uint32_t *flag = vb.Alternate();  // reuse the spare value buffer
-        head_flag_kernel<<<nblk(total, 256), 256, 0, st>>>(kb.Current(), flag, total);
-        TC_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp2, flag, flag, (int)total, st));
-        scatter_rank_kernel<<<nblk(total, 256), 256, 0, st>>>(flag, vb.Current(), ctx->d_ranks, total);
+        uint32_t *flag = us.spare;        // reuse the spare value buffer
+        size_t tmp2 = us.tmp_bytes;
+        head_flag_kernel<<<nblk(total, 256), 256, 0, st>>>(us.keys, flag, total);
+        TC_CUDA(cub::DeviceScan::InclusiveSum(us.tmp, tmp2, flag, flag, (int)total, st));
+        scatter_rank_kernel<<<nblk(total, 256), 256, 0, st>>>(flag, us.vals, ctx->d_ranks, total);
         // which ranks occur in more than one sketch (sketches are duplicate-free, so a run of equal hashes spans sketches)
         const uint64_t mwords = total / 32 + 1;
         if (ensure_cap(&ctx->d_multi, &ctx->cap_multi, mwords)) return 1;

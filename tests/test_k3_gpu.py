@@ -379,3 +379,54 @@ def test_upload_rows_equals_flat_upload(tc):
     with tc.Context(0) as c:
         with pytest.raises(tc.TclustError):
             c.upload_rows([np.array([5, 3], np.uint64)])                          # unsorted input is still rejected
+
+
+def test_chunked_upload_equals_single_copy_upload(tc, oracle, monkeypatch):
+    """tc_sketches_upload of a large host array copies it in pieces and sorts/merges the pieces under the copy
+    (upload_sorted_runs); TCLUST_UPLOAD_OVERLAP=1 forces that path at any size.  The rank transform it feeds must give the
+    same `common` for every pair as the oracle, for totals that leave pieces empty, ragged, or a single element."""
+    rng = np.random.default_rng(33)
+    sets = [
+        synth.family_sketches(5, 9, s=1000, seed=4),                                         # 45 000 hashes: 8 full pieces
+        [np.unique(rng.integers(0, 2**64 - 1, int(z), dtype=np.uint64)) for z in rng.integers(0, 120, 40)],  # ~2 400: 3 pieces
+        [np.array([7], np.uint64), np.array([7, 9], np.uint64)],                              # 3 hashes: one piece
+        [np.unique(rng.integers(0, 3000, int(z), dtype=np.uint64)) for z in rng.integers(500, 2500, 30)],    # many equal hashes
+    ]
+    monkeypatch.setenv("TCLUST_UPLOAD_OVERLAP", "1")
+    with tc.Context(0) as c:
+        for sk in sets:
+            c.upload(sk)
+            n = len(sk)
+            want = oracle.common_matrix(sk)
+            for impl in (0, 2, 3):
+                assert np.array_equal(c.pair_common(0, n, 0, n, impl=impl), want), impl
+        with pytest.raises(tc.TclustError, match="sketch 1 is not strictly ascending"):
+            c.upload([np.array([1, 2, 3], np.uint64), np.array([5, 5], np.uint64)])
+    # and the edges of a dense pass agree with the single-copy upload
+    sk = synth.family_sketches(8, 40, s=700, seed=12, keep_lo=0.4)
+    with tc.Context(0) as a:
+        a.upload(sk); a.allpairs_pass(4); ea = np.sort(a.edges(), order=["i", "j"])
+    monkeypatch.setenv("TCLUST_UPLOAD_OVERLAP", "0")
+    with tc.Context(0) as b:
+        b.upload(sk); b.allpairs_pass(4); eb = np.sort(b.edges(), order=["i", "j"])
+    assert np.array_equal(ea, eb)
+
+
+def test_distinct_sort_blocked_equals_plain(tc, oracle, monkeypatch):
+    """k3h_distinct_kernel sorts a block's shared ranks with register-blocked bitonic passes; TCLUST_DISTINCT_SORT=plain
+    keeps the one-pass-per-stride version.  Both must give the oracle's counts through the block join (which reads the
+    union lists) for short rows (R < 512: mixed plain/blocked stages), long rows and an unsorted-slot block."""
+    rng = np.random.default_rng(44)
+    sets = [
+        synth.family_sketches(3, 40, s=1000, seed=5),                                       # R = 1024
+        synth.family_sketches(4, 33, s=200, seed=6, keep_lo=0.2),                            # R = 256
+        [np.unique(rng.integers(0, 4000, int(z), dtype=np.uint64)) for z in rng.integers(0, 60, 100)],       # R = 32/64
+        [np.unique(rng.integers(0, 20000, int(z), dtype=np.uint64)) for z in ([1500] * 3 + [40] * 61)],      # rows > 1024
+    ]
+    for mode in ("blocked", "plain"):
+        monkeypatch.setenv("TCLUST_DISTINCT_SORT", mode)
+        with tc.Context(0) as c:
+            for sk in sets:
+                c.upload(sk)
+                n = len(sk)
+                assert np.array_equal(c.pair_common(0, n, 0, n, impl=3), oracle.common_matrix(sk)), mode
