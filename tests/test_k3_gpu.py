@@ -421,7 +421,7 @@ def test_distinct_sort_blocked_equals_plain(tc, oracle, monkeypatch):
         synth.family_sketches(3, 40, s=1000, seed=5),                                       # R = 1024
         synth.family_sketches(4, 33, s=200, seed=6, keep_lo=0.2),                            # R = 256
         [np.unique(rng.integers(0, 4000, int(z), dtype=np.uint64)) for z in rng.integers(0, 60, 100)],       # R = 32/64
-        [np.unique(rng.integers(0, 20000, int(z), dtype=np.uint64)) for z in ([1500] * 3 + [40] * 61)],      # rows > 1024
+        [np.unique(rng.integers(0, 4000, int(z), dtype=np.uint64)) for z in ([3000] * 3 + [40] * 61)],       # rows > 1024: slots unsorted
     ]
     for mode in ("blocked", "plain"):
         monkeypatch.setenv("TCLUST_DISTINCT_SORT", mode)
