@@ -351,19 +351,28 @@ def run_pairs(args):
     L = T.lib()
     import ctypes as C
 
+    # The Boruvka phases of a step are queued back to back on the library's stream (tc_boruvka_set_async): phase 1,
+    # all-reduce(min) of the keys, phase 2, all-reduce(min) of the edges -- NCCL orders itself after the current stream,
+    # which is the library's here -- and the host waits once, at the end of the round.
+    T._chk(L.tc_boruvka_set_async(ctx._h, 1))
+
+    def boruvka_round1():
+        with torch.cuda.stream(stream):
+            T._chk(L.tc_boruvka_upload_comp(ctx._h, comp.ctypes.data_as(C.POINTER(C.c_int32)), n))
+            T._chk(L.tc_boruvka_phase1(ctx._h, 0, best_key.data_ptr()))
+            if dist is not None:
+                # keys are u64 bit patterns < 2^63 is NOT guaranteed: reduce as unsigned via the sign flip
+                best_key.bitwise_xor_(-2**63); dist.all_reduce(best_key, op=dist.ReduceOp.MIN); best_key.bitwise_xor_(-2**63)
+            T._chk(L.tc_boruvka_phase2(ctx._h, 0, best_key.data_ptr(), best_edge.data_ptr()))
+            if dist is not None:
+                best_edge.bitwise_xor_(-2**63); dist.all_reduce(best_edge, op=dist.ReduceOp.MIN); best_edge.bitwise_xor_(-2**63)
+        # a Boruvka round ends with the reduced edges on every rank (the host unions the components next):
+        # the phases and collectives are complete before the next pass starts, they are not left to overlap it
+        stream.synchronize()
+
     def device_step():
         npairs, nedges = ctx.allpairs_pass(radio, rank, world)
-        T._chk(L.tc_boruvka_upload_comp(ctx._h, comp.ctypes.data_as(C.POINTER(C.c_int32)), n))
-        T._chk(L.tc_boruvka_phase1(ctx._h, 0, best_key.data_ptr()))
-        if dist is not None:
-            # keys are u64 bit patterns < 2^63 is NOT guaranteed: reduce as unsigned via the sign flip
-            best_key.bitwise_xor_(-2**63); dist.all_reduce(best_key, op=dist.ReduceOp.MIN); best_key.bitwise_xor_(-2**63)
-        T._chk(L.tc_boruvka_phase2(ctx._h, 0, best_key.data_ptr(), best_edge.data_ptr()))
-        if dist is not None:
-            best_edge.bitwise_xor_(-2**63); dist.all_reduce(best_edge, op=dist.ReduceOp.MIN); best_edge.bitwise_xor_(-2**63)
-            # a Boruvka round ends with the reduced edges on every rank (the host unions the components next):
-            # the collectives must be complete before the next pass starts, they are not left to overlap it
-            torch.cuda.current_stream().synchronize()
+        boruvka_round1()
         return npairs, nedges
 
     def sync_all():
@@ -397,14 +406,7 @@ def run_pairs(args):
         kern_steps.append(ctx.last_pass_kernel_ms)    # events recorded by the library right around the kernel
         k3_ms += kern_steps[-1]
         pairs_mine += npairs
-        T._chk(L.tc_boruvka_upload_comp(ctx._h, comp.ctypes.data_as(C.POINTER(C.c_int32)), n))
-        T._chk(L.tc_boruvka_phase1(ctx._h, 0, best_key.data_ptr()))
-        if dist is not None:
-            best_key.bitwise_xor_(-2**63); dist.all_reduce(best_key, op=dist.ReduceOp.MIN); best_key.bitwise_xor_(-2**63)
-        T._chk(L.tc_boruvka_phase2(ctx._h, 0, best_key.data_ptr(), best_edge.data_ptr()))
-        if dist is not None:
-            best_edge.bitwise_xor_(-2**63); dist.all_reduce(best_edge, op=dist.ReduceOp.MIN); best_edge.bitwise_xor_(-2**63)
-            torch.cuda.current_stream().synchronize()      # round complete on this rank (see device_step)
+        boruvka_round1()                                   # round complete on this rank when it returns
     with torch.cuda.stream(stream):
         ev1.record()
     sync_all()

@@ -174,6 +174,11 @@ int tc_boruvka_upload_comp(tc_ctx *ctx, const int32_t *comp, uint32_t n);
 int tc_boruvka_phase1(tc_ctx *ctx, int containment, uint64_t *best_key_dev);
 int tc_boruvka_phase2(tc_ctx *ctx, int containment, const uint64_t *best_key_dev,
                       uint64_t *best_edge_dev);
+/* on = 1: tc_boruvka_upload_comp / _phase1 / _phase2 only enqueue their work on tc_stream(ctx) and return; the
+ * caller orders what follows (the NCCL all-reduce of the *_dev buffers, the next phase) on that stream and
+ * synchronises once per round.  on = 0 (default): every phase returns with its result complete.  `comp` must stay
+ * valid until the stream has consumed it. */
+int tc_boruvka_set_async(tc_ctx *ctx, int on);
 
 /*
  * Whole single-GPU MST build = compute_minhash_mst (src/MST.cpp:1290-1737): dense pass +

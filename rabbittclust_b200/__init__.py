@@ -21,7 +21,7 @@ SYMBOLS = [
     "tc_version", "tc_last_error", "tc_ctx_create", "tc_ctx_destroy", "tc_kernel_launches", "tc_last_pass_kernel_ms", "tc_stream",
     "tc_host_alloc", "tc_host_free", "tc_sketch_minhash", "tc_sketch_minhash_dev", "tc_kssd_shuffled_dim", "tc_sketch_kssd", "tc_sketch_kssd_dev",
     "tc_sketches_upload", "tc_sketches_upload_dev", "tc_sketches_upload_rows", "tc_pair_common", "tc_allpairs_pass",
-    "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_mst",
+    "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_boruvka_set_async", "tc_mst",
     "tc_greedy_scan", "tc_greedy_cluster",
     "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce", "tc_greedy_cluster_kssd", "tc_dense_ani", "tc_allpairs_pass_from", "tc_mst_append",
     "tc_jaccard_b", "tc_distance_b", "tc_contain_distance",
@@ -78,6 +78,7 @@ def lib():
     L.tc_boruvka_upload_comp.argtypes = [vp, i32p, C.c_uint32]
     L.tc_boruvka_phase1.argtypes = [vp, C.c_int, vp]
     L.tc_boruvka_phase2.argtypes = [vp, C.c_int, vp, vp]
+    L.tc_boruvka_set_async.argtypes = [vp, C.c_int]
     L.tc_mst.argtypes = [vp, C.c_int, C.c_int, C.c_double, vp, u64p]
     L.tc_greedy_scan.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, C.c_uint32, u32p, u32p]
     L.tc_greedy_cluster.argtypes = [vp, C.c_int, C.c_int, C.c_double, i32p, u32p]

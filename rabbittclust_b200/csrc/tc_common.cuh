@@ -37,6 +37,7 @@ struct tc_ctx {
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     cudaEvent_t ev_pass0 = nullptr, ev_pass1 = nullptr;   // around the last dense-pass kernel
+    bool boruvka_async = false;           // tc_boruvka_set_async: the Boruvka phases do not synchronise the stream
 
     // resident sketches (HP-2)
     uint32_t n = 0;               // number of sketches

@@ -762,7 +762,7 @@ extern "C" int tc_boruvka_phase1(tc_ctx *ctx, int containment, uint64_t *best_ke
         ctx->launches++;
     }
     TC_CUDA(cudaGetLastError());
-    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->boruvka_async) TC_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -779,7 +779,14 @@ extern "C" int tc_boruvka_phase2(tc_ctx *ctx, int containment, const uint64_t *b
         ctx->launches++;
     }
     TC_CUDA(cudaGetLastError());
-    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->boruvka_async) TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int tc_boruvka_set_async(tc_ctx *ctx, int on)
+{
+    TC_CHECK(ctx, "tc_boruvka_set_async: null context");
+    ctx->boruvka_async = on != 0;
     return 0;
 }
 
@@ -868,6 +875,11 @@ static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t se
                     uint64_t n_pre = 0)
 {
     const int containment = mode;
+    struct SyncPhases {                                  // the rounds below read every phase's result right away
+        tc_ctx *c; bool was;
+        explicit SyncPhases(tc_ctx *x) : c(x), was(x->boruvka_async) { x->boruvka_async = false; }
+        ~SyncPhases() { c->boruvka_async = was; }
+    } sync_phases(ctx);
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0, "tc_mst: no sketches uploaded");
     const uint32_t n = ctx->n;

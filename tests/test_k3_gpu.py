@@ -430,3 +430,34 @@ def test_distinct_sort_blocked_equals_plain(tc, oracle, monkeypatch):
                 c.upload(sk)
                 n = len(sk)
                 assert np.array_equal(c.pair_common(0, n, 0, n, impl=3), oracle.common_matrix(sk)), mode
+
+
+def test_boruvka_async_phases_equal_sync_phases(ctx, tc):
+    """tc_boruvka_set_async(1): the phases only enqueue on the library's stream; after one synchronize their buffers
+    hold what the synchronous phases return, and tc_mst (which reads every phase's result at once) is unaffected."""
+    import ctypes as C
+    import torch
+    sk = synth.family_sketches(9, 14, s=600, seed=31, keep_lo=0.3)
+    n = len(sk)
+    ctx.upload(sk)
+    ctx.allpairs_pass(4)
+    L = tc.lib()
+    comp = (np.arange(n, dtype=np.int32) // 3 * 3).astype(np.int32)       # components of three vertices
+    stream = torch.cuda.ExternalStream(ctx.stream, device=0)
+    res = {}
+    for mode in (0, 1):
+        key = torch.empty(n, dtype=torch.int64, device="cuda:0")
+        edge = torch.empty(n, dtype=torch.int64, device="cuda:0")
+        torch.cuda.synchronize()
+        tc._chk(L.tc_boruvka_set_async(ctx._h, mode))
+        tc._chk(L.tc_boruvka_upload_comp(ctx._h, comp.ctypes.data_as(C.POINTER(C.c_int32)), n))
+        tc._chk(L.tc_boruvka_phase1(ctx._h, 0, key.data_ptr()))
+        tc._chk(L.tc_boruvka_phase2(ctx._h, 0, key.data_ptr(), edge.data_ptr()))
+        stream.synchronize()
+        res[mode] = (key.cpu().numpy(), edge.cpu().numpy())
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert (res[0][1] != -1).any()
+    want = ctx.mst(21, 0.05)                                              # async still on: tc_mst forces its own syncs
+    tc._chk(L.tc_boruvka_set_async(ctx._h, 0))
+    got = ctx.mst(21, 0.05)
+    assert np.array_equal(want, got)
