@@ -617,7 +617,8 @@ static_assert(KJ_SMEM <= 227 * 1024 - 1024, "K3J shared memory");
 // a quarter of the pass at 4096 columns per unit (59.4 ms -> 51.1 ms at 8192)
 // (46.8 ms at 16384).  The width is chosen per pass (kj_pick_cseg): as wide as possible while every CTA still gets
 // enough units for the dynamic hand-out to even out the tail.
-constexpr uint32_t KJ_CSEG_MAX = 32768;
+constexpr uint32_t KJ_CSEG_MAX = 32768;                                  // widest unit of a partitioned row block (P > 1): what the per-CTA tile state holds
+constexpr uint32_t KJ_CSEG_WIDEST = 1u << 20;                            // widest unit kj_pick_cseg chooses (TCLUST_KJ_CSEG_MAX)
 constexpr uint32_t KJ_HEAVY_CAP = 256;                                  // deferred tiles per unit and partition
 constexpr size_t KJ_STATE_WORDS = (size_t)(KJ_CSEG_MAX / 32) * KJ_TILE_STATE;   // per-CTA tile state (P > 1 only)
 constexpr size_t KH_STATE_WORDS_MAX = KJ_STATE_WORDS > (size_t)KH_CSEG * KH_STATE_CAND ? KJ_STATE_WORDS : (size_t)KH_CSEG * KH_STATE_CAND;
@@ -1190,15 +1191,20 @@ struct KjRouting {
     }
 };
 
-// columns per K3J unit: the widest power of two up to KJ_CSEG_MAX that still leaves every CTA of every rank 4 units
-// (8 units cost 10 % at N = 100k on 8 GPUs: 1.26 ms per part at 16384 columns against 1.14 ms at 32768)
+// columns per K3J unit: the widest power of two up to KJ_CSEG_WIDEST that still leaves every CTA of every rank 2 units.
+// Since the union lists hold shared ranks only they fit the L2 as a whole (32 MB at N = 100k), so nothing is gained from
+// all CTAs streaming the same column segment, while every unit pays a table build and a barrier tail: 8.92 ms per pass
+// at 16384 columns, 7.68 at 32768, 7.21 at 65536 (tools/unit_width_sweep.py).  At N = 100k a unit is a whole row of
+// tiles; tc_launch_blockjoin_edges hands the widest units out first.
 // (mirrored by rabbittclust_b200/mst_dist.py: join_cseg)
 static uint32_t kj_pick_cseg(uint32_t n, uint32_t start_index, uint32_t nparts, int num_sms)
 {
     const uint64_t nrb = (n + 31) / 32, rb0 = start_index / 32;
-    uint64_t per_cta = 4;
+    uint64_t per_cta = 2;
     if (const char *e = getenv("TCLUST_KJ_MIN_UNITS")) per_cta = std::max(1, atoi(e));   // tuning aid (tools/unit_width_sweep.py)
-    for (uint32_t cseg = KJ_CSEG_MAX; cseg > KH_CSEG; cseg >>= 1) {
+    uint32_t cseg_max = KJ_CSEG_WIDEST;
+    if (const char *e = getenv("TCLUST_KJ_CSEG_MAX")) cseg_max = (uint32_t)std::min<long>(KJ_CSEG_WIDEST, std::max<long>(KH_CSEG, atol(e)));
+    for (uint32_t cseg = cseg_max; cseg > KH_CSEG; cseg >>= 1) {
         uint64_t units = 0;
         for (uint64_t c0 = 0; c0 < n; c0 += cseg) units += nrb - std::max<uint64_t>(c0 / 32, rb0);
         if (units >= per_cta * nparts * (uint64_t)num_sms) return cseg;
@@ -1218,10 +1224,17 @@ int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t np
         const KjRouting route(ctx);
         for (size_t u = part; u < ctx->kh_edge_units.size(); u += (nparts ? nparts : 1)) {
             const tc_kh_unit &un = ctx->kh_edge_units[u];
-            if (route.listed(un) && (force_block || route.pays(ctx, un))) { blk.push_back(un); continue; }
+            if (route.listed(un) && (force_block || route.pays(ctx, un))) {
+                // a partitioned row block keeps 2 KB of state per tile between its partitions: units of KJ_CSEG_MAX columns
+                const uint32_t w = ctx->kh_parts[un.rb] > 1 ? KJ_CSEG_MAX : un.c1 - un.c0;
+                for (uint32_t c0 = un.c0; c0 < un.c1; c0 += w) blk.push_back(tc_kh_unit{un.rb, c0, std::min(un.c1, c0 + w)});
+                continue;
+            }
             for (uint32_t c0 = un.c0; c0 < un.c1; c0 += KH_CSEG)          // K3H's per-CTA column state holds KH_CSEG columns
                 old.push_back(tc_kh_unit{un.rb, c0, std::min(un.c1, c0 + KH_CSEG)});
         }
+        // widest units first: the dynamic hand-out then ends on the small ones (a unit is up to a whole row of tiles)
+        std::stable_sort(blk.begin(), blk.end(), [](const tc_kh_unit &x, const tc_kh_unit &y) { return x.c1 - x.c0 > y.c1 - y.c0; });
         if (blk.size() + old.size() > ctx->kj_units_cap || !ctx->d_kj_units) {
             cudaFree(ctx->d_kj_units);
             ctx->d_kj_units = nullptr; ctx->kj_units_cap = 0;

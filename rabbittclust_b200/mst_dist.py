@@ -24,13 +24,14 @@ def tile_owner(t, nparts):
 
 
 def join_cseg(n, nparts=1, num_sms=148, start_index=0):
-    """Columns per unit of the default dense pass (k3h_join.cu: kj_pick_cseg): the widest power of two up to 32768
-    that leaves every CTA of every rank 4 units; 4096 at least (and always with TCLUST_PASS_IMPL=join)."""
+    """Columns per unit of the default dense pass (k3h_join.cu: kj_pick_cseg): the widest power of two up to 2^20
+    (a unit is then a whole row of tiles) that leaves every CTA of every rank 2 units; 4096 at least (and always with
+    TCLUST_PASS_IMPL=join)."""
     nrb, rb0 = (n + 31) // 32, start_index // 32
-    cseg = 32768
+    cseg = 1 << 20
     while cseg > 4096:
         units = sum(nrb - max(c0 // 32, rb0) for c0 in range(0, n, cseg))
-        if units >= 4 * nparts * num_sms:
+        if units >= 2 * nparts * num_sms:
             return cseg
         cseg >>= 1
     return 4096

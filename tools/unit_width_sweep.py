@@ -10,16 +10,17 @@ from rabbittclust_b200 import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 h, off = synth.family_sketches_fast(n // 100, 100, 1000, seed=7)
-for mu in (1, 2, 4, 8, 16, 32):
+for cap, mu in ((1 << 20, 2), (65536, 2), (32768, 2), (1 << 20, 4), (1 << 20, 1)):
     os.environ["TCLUST_KJ_MIN_UNITS"] = str(mu)
+    os.environ["TCLUST_KJ_CSEG_MAX"] = str(cap)
     with T.Context(0) as ctx:
         ctx.upload(hashes=h, off=off)
         res = []
-        for part, nparts in ((0, 1), (0, P), (P - 1, P)):
+        for part, nparts in ((0, 1), (0, 2), (0, 4), (0, P), (P - 1, P)):
             ctx.allpairs_pass(4, part, nparts)
             ks = []
             for _ in range(3):
                 ctx.allpairs_pass(4, part, nparts)
                 ks.append(ctx.last_pass_kernel_ms)
             res.append("part %d/%d %.3f ms" % (part, nparts, min(ks)))
-        print("min units per CTA %2d:" % mu, "  ".join(res), flush=True)
+        print("widest unit %5d, min units per CTA %2d:" % (cap, mu), "  ".join(res), flush=True)
