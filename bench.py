@@ -384,10 +384,10 @@ def run_pairs(args):
     ctx.upload(hashes=hp, off=off)
     for _ in range(args.warmup):
         device_step()
-    sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    sync_all()        # after the sampler's start-up (NVML init, a few ms on rank 0): the other ranks must not wait for it inside their timed region
     launches0 = ctx.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k3_ms, pairs_mine, nedges, k3_steps, kern_steps = 0.0, 0, 0, [], []
