@@ -303,9 +303,15 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint3
         }
     }
     // distinct count: thread t owns the chunk [t*c, (t+1)*c)
+    // (c is a power of two <= 32; the chunk is walked from a lane-dependent start so that the 32 lanes of a warp read 32
+    // banks -- in chunk order every lane would hit the same bank: 43 % of the kernel's shared-memory wavefronts)
     const uint32_t c = npad / KH_THREADS, b0 = tid * c;
-    uint32_t mine = 0;
-    for (uint32_t i = b0; i < b0 + c; i++) mine += (i < total && (i == 0 || buf[i] != buf[i - 1])) ? 1u : 0u;
+    uint32_t heads = 0;                                           // bit k: element b0 + k starts a run of equal keys
+    for (uint32_t kk = 0; kk < c; kk++) {
+        const uint32_t k = (kk + lane) & (c - 1), i = b0 + k;
+        if (i < total && (i == 0 || buf[i] != buf[i - 1])) heads |= 1u << k;
+    }
+    const uint32_t mine = __popc(heads);
     uint32_t incl = mine;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
     if (lane == 31) s_warp[warp] = incl;
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint3
     }
     __syncthreads();
     const uint32_t D = s_d;
-    uint32_t before = incl - mine + (warp ? s_warp[warp - 1] : 0u);       // distinct keys before this chunk
+    const uint32_t before = incl - mine + (warp ? s_warp[warp - 1] : 0u); // distinct keys before this chunk
     if (tid == 0) out[rb * KH_DREC] = D;
     // wanted distinct ranks
     uint32_t want[6];
@@ -329,18 +335,18 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint3
     // union list of the block (K3J): distinct key d -> (key, mask of the sketches that hold it), ascending, stored at
     // the element offset of the block's first sketch (a block never has more distinct keys than elements)
     const unsigned long long base = rb * 32 < n ? off[rb * 32] : 0ULL;
-    for (uint32_t i = b0; i < b0 + c; i++) {
-        if (i < total && (i == 0 || buf[i] != buf[i - 1])) {
+    for (uint32_t kk = 0; kk < c; kk++) {
+        const uint32_t k = (kk + lane) & (c - 1);
+        if (!((heads >> k) & 1u)) continue;
+        const uint32_t i = b0 + k, d = before + __popc(heads & ((1u << k) - 1u));   // distinct rank of this key
+        const uint32_t key = buf[i];
 #pragma unroll
-            for (int q = 0; q < 6; q++) if (before == want[q]) out[rb * KH_DREC + 1 + q] = buf[i];
-            if (ukeys) {
-                const uint32_t key = buf[i];
-                uint32_t m = 0;
-                for (uint32_t j = i; j < total && buf[j] == key; j++) m |= 1u << rowof[j];
-                ukeys[base + before] = key;
-                umask[base + before] = m;
-            }
-            before++;
+        for (int q = 0; q < 6; q++) if (d == want[q]) out[rb * KH_DREC + 1 + q] = key;
+        if (ukeys) {
+            uint32_t m = 0;
+            for (uint32_t j = i; j < total && buf[j] == key; j++) m |= 1u << rowof[j];
+            ukeys[base + d] = key;
+            umask[base + d] = m;
         }
     }
 }
