@@ -22,7 +22,8 @@
 //   --dense                   src/MST.cpp:1517-1530,1702-1712 (tc_dense_ani), src/sub_command.cpp:3070-3100 (noise pass)
 //   tree / linkage output     src/MST.cpp:1088-1147,1235-1284, src/MST_IO.cpp:263-375
 //   --append (classic)        src/sub_command.cpp:22-96 (greedy: brute-force greedyCluster), :1578-1757 (mst: new-vs-all
-//                             pass + Kruskal over old MST + new forest)
+//                             pass + Kruskal over old MST + new forest), :1317-1477 (clust-mst --fast: the same over
+//                             KSSD sketches, append_clust_mst_fast without a saved state)
 // Out of scope: --db/--save-rep state files, --auto-threshold/--stability analytics, dbscan/leiden,
 // --fast with a single multi-FASTA input (the reference's -i KSSD consumer is the
 // quirky variant).
@@ -1088,8 +1089,63 @@ int main(int argc, char **argv)
     if (o.append) {
         // classic append (no saved cluster state): append_clust_mst (sub_command.cpp:1578-1757) and
         // append_clust_greedy (:22-96).  The folder's sketch parameters are reused, tune_parameters is not called.
-        if (o.fast) die("--append with --fast is not part of this build (SURVEY.md 8f-4 covers the MinHash flows)");
         if (o.dense) die("--append with --dense is not part of this build");
+#ifdef GREEDY_CLUST
+        if (o.fast) die("clust-greedy --append with --fast is not part of this build: the reference clusters it incrementally "
+                        "from a cluster_state.bin (KssdIncrementalCluster), see DESIGN.md section 7");
+#else
+        if (o.fast) {
+            // append_clust_mst_fast, the path without a saved mst_cluster_state.bin (sub_command.cpp:1317-1477): KSSD
+            // sketches of the new genomes with the folder's half_k / drlevel, new-vs-all edges, Kruskal over the old MST
+            // and the new forest.  kssd.hash.sketch keeps the OLD folder's parameter block, genome count included
+            // (saveKssdSketches(final_sketches, pre_info, ...), :1349).
+            if (!o.presketched && !o.premsted) { cerr << "ERROR: option --append, option --presketched or --premsted needed" << endl; return 1; }
+            if (!o.by_file) die("--fast needs -l/--list in this build (SURVEY.md 8a-9)");
+            vector<Genome> pre;
+            const bool pre_by_file = load_kssd_sketches(pre, o.folder);
+            const KssdParams pre_info = g_kssd;
+            if (pre_by_file != o.by_file) {
+                cerr << "Warning: append_clust_mst(), the input format of append genomes and pre-sketched genome is not same (single input genome vs. genome list)" << endl;
+                cerr << "the output cluster file may not have the genome file name" << endl;
+            }
+            vector<Genome> mst_info; vector<tc_edge> pre_mst;
+            load_mst(mst_info, pre_mst, o.folder, true);
+            o.kmer = 2 * pre_info.half_k;
+            o.drlevel = pre_info.drlevel;
+            cerr << "---the thread number is: " << o.threads << endl;
+            cerr << "---the threshold is: " << o.threshold << endl;
+            vector<Genome> add;
+            sketch_files(ctx, o, add);                                   // sets g_kssd from o.kmer / o.drlevel
+            if (g_kssd.half_k != pre_info.half_k || g_kssd.half_subk != pre_info.half_subk || g_kssd.drlevel != pre_info.drlevel)
+                die("append_clust_mst_fast(), the KSSD parameters of " + o.folder + " cannot be reproduced for the new genomes");
+            g_kssd = pre_info;
+            const uint32_t n_pre = (uint32_t)pre.size();
+            if (mst_info.size() != n_pre) die("append_clust_mst_fast(), kssd.info.mst and kssd.info.sketch of " + o.folder + " differ in size");
+            g = std::move(pre);
+            for (Genome &x : add) g.push_back(std::move(x));
+            for (size_t i = 0; i < g.size(); i++) g[i].id = (int)i;
+            const string folder = current_date_time();
+            const bool save = !o.no_save;
+            if (save) {
+                if (system(("mkdir -p " + folder).c_str()) != 0) die("cannot create " + folder);
+                save_kssd_sketches(g, folder, o.by_file);                // with kssd.sketch.index / .dict over all genomes
+            }
+            upload(ctx, g);
+            vector<tc_edge> mst(g.size());
+            uint64_t m = 0;
+            tc_or_die(tc_mst_append(ctx, o.kmer, o.containment, o.threshold, n_pre, pre_mst.data(), pre_mst.size(), mst.data(), &m),
+                      "incremental MST generation");
+            mst.resize(m);
+            write_tree_outputs(g, mst, pre_by_file, o);
+            vector<vector<int>> cluster = clusters_from_forest(mst, o.threshold, (int)g.size());
+            print_result(cluster, g, pre_by_file, o.output, o.threshold);
+            cerr << "-----write the cluster result into: " << o.output << endl;
+            cerr << "-----the cluster number of: " << o.output << " is: " << cluster.size() << endl;
+            if (save) save_mst(g, mst, folder, o.by_file, true);
+            tc_ctx_destroy(ctx);
+            return 0;
+        }
+#endif
 #ifdef GREEDY_CLUST
         if (!o.presketched) { cerr << "ERROR option --append, option --presketched needed" << endl; return 1; }
 #else

@@ -254,3 +254,34 @@ def test_clust_greedy_append_matches_reference(genomes, tmp_path, extra):
     for fn in ("hash.sketch", "info.sketch"):
         assert _same_bytes(os.path.join(rf, fn), os.path.join(of, fn)), fn
     assert open(str(tmp_path / "ref" / "app.txt")).read() == open(str(tmp_path / "ours" / "app.txt")).read()
+
+
+def test_clust_mst_fast_append_matches_reference(genomes, tmp_path):
+    """clust-mst --fast --append (append_clust_mst_fast without a saved state, sub_command.cpp:1317-1477): the reference
+    clusters the first 20 genomes with KSSD sketches, then both binaries append the other 10 to that folder.  The new
+    folder's kssd.hash.sketch keeps the old folder's parameter block; index/dict differ only in entry order."""
+    lst, _ = genomes
+    first, second = _split_list(lst, tmp_path, 20)
+    base, _ = _run(os.path.join(REF, "clust-mst"), ["-t", "1", "--fast", "-l", "-i", first, "-d", "0.05", "-o", "base.txt"],
+                   str(tmp_path / "base"))
+    args = ["--fast", "-l", "--append", second, "--presketched", base, "-d", "0.05", "-o", "app.txt", "--linkage-matrix"]
+    rf, _ = _run(os.path.join(REF, "clust-mst"), ["-t", "1"] + args, str(tmp_path / "ref"))
+    of, _ = _run(os.path.join(OURS, "clust-mst"), args, str(tmp_path / "ours"))
+    for fn in ("kssd.hash.sketch", "kssd.info.sketch", "kssd.info.mst"):
+        assert _same_bytes(os.path.join(rf, fn), os.path.join(of, fn)), fn
+    a = sketch_io.read_edge_mst(os.path.join(rf, "edge.mst"))
+    b = sketch_io.read_edge_mst(os.path.join(of, "edge.mst"))
+    assert np.array_equal(np.sort(a["dist"]), np.sort(b["dist"]))
+    ref_out, our_out = str(tmp_path / "ref" / "app.txt"), str(tmp_path / "ours" / "app.txt")
+    assert open(ref_out).read().splitlines()[:3] == open(our_out).read().splitlines()[:3]
+    assert _partition(ref_out) == _partition(our_out)
+    # the appended result equals clustering everything at once, and the reference reads the folder we wrote
+    full, _ = _run(os.path.join(REF, "clust-mst"), ["-t", "1", "--fast", "-l", "-i", lst, "-d", "0.05", "-o", "full.txt"],
+                   str(tmp_path / "full"))
+    c = sketch_io.read_edge_mst(os.path.join(full, "edge.mst"))
+    assert np.array_equal(np.sort(b["dist"]), np.sort(c["dist"]))
+    _run(os.path.join(REF, "clust-mst"), ["-t", "1", "--fast", "--presketched", of, "-d", "0.05", "-o", "x.txt"], str(tmp_path / "ref"))
+    assert _partition(str(tmp_path / "ref" / "x.txt")) == _partition(ref_out)
+    la = [l.split("\t")[2] for l in open(ref_out + ".linkage.txt")]
+    lb = [l.split("\t")[2] for l in open(our_out + ".linkage.txt")]
+    assert la == lb
