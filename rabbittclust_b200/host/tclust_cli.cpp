@@ -705,7 +705,7 @@ bool load_kssd_sketches(vector<Genome> &g, const string &folder)
     return by_file;
 }
 
-void save_mst(const vector<Genome> &g, const vector<tc_edge> &mst, const string &folder, bool by_file, bool fast)
+[[maybe_unused]] void save_mst(const vector<Genome> &g, const vector<tc_edge> &mst, const string &folder, bool by_file, bool fast)
 {
     if (fast) save_kssd_genome_info(g, folder, "mst", by_file, kssd_use64(g_kssd));      // saveKssdMST, MST_IO.cpp:181-198
     else save_genome_info(g, folder, "mst", by_file);
@@ -718,7 +718,7 @@ void save_mst(const vector<Genome> &g, const vector<tc_edge> &mst, const string 
     cerr << (fast ? "-----save the kssd mst into: " : "-----save the mst into: ") << folder << endl;
 }
 
-bool load_mst(vector<Genome> &g, vector<tc_edge> &mst, const string &folder, bool fast)
+[[maybe_unused]] bool load_mst(vector<Genome> &g, vector<tc_edge> &mst, const string &folder, bool fast)
 {
     bool by_file = fast ? load_kssd_genome_info(g, folder, "mst") : load_genome_info(g, folder, "mst");
     string path = folder + "/edge.mst";
@@ -767,7 +767,7 @@ void upload(tc_ctx *ctx, const vector<Genome> &g)
     tc_or_die(tc_sketches_upload_rows(ctx, rows.data(), sizes.data(), (uint32_t)g.size()), "sketch upload");
 }
 
-vector<vector<int>> clusters_from_forest(const vector<tc_edge> &mst, double threshold, int vertices)
+[[maybe_unused]] vector<vector<int>> clusters_from_forest(const vector<tc_edge> &mst, double threshold, int vertices)
 {
     vector<vector<int>> adj(vertices);
     for (const tc_edge &e : mst)
@@ -862,7 +862,7 @@ string newick_of(const vector<Genome> &g, const vector<tc_edge> &mst, bool by_fi
     return out + ";";
 }
 
-void write_tree_outputs(const vector<Genome> &g, const vector<tc_edge> &mst, bool by_file, const Options &o)
+[[maybe_unused]] void write_tree_outputs(const vector<Genome> &g, const vector<tc_edge> &mst, bool by_file, const Options &o)
 {
     auto open_or_die = [](const string &path) { FILE *fp = fopen(path.c_str(), "w"); if (!fp) die("cannot write file: " + path); return fp; };
     string tree;
