@@ -110,7 +110,8 @@ int tc_sketch_kssd_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const uint64_t *rec
 /*
  * Make N sorted, duplicate-free sketches resident on the device (what compute_minhash_mst
  * caches at src/MST.cpp:1311-1322 and greedy.cpp:1138).  sketch g = hashes[off[g]..off[g+1]).
- * Replaces any previously uploaded set.
+ * Replaces any previously uploaded set.  At most 2^31 - 1 hashes in total per context (an error otherwise, never a
+ * truncation); a sketch that is not strictly ascending is an error naming the sketch.
  */
 int tc_sketches_upload(tc_ctx *ctx, const uint64_t *hashes, const uint64_t *off, uint32_t n);
 int tc_sketches_upload_dev(tc_ctx *ctx, const uint64_t *hashes_dev, const uint64_t *off, uint32_t n);

@@ -328,7 +328,8 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     pt.mark("reset previous set");
     TC_CHECK(n > 0, "tc_sketches_upload: n == 0");
     const uint64_t total = off[n];
-    TC_CHECK(total < 0xFFFFFFF0ull, "tc_sketches_upload: %llu hashes exceed the u32 rank space",
+    // (cub's merge and scan entry points used by the rank transform count items in an int)
+    TC_CHECK(total <= 0x7FFFFFFFull, "tc_sketches_upload: %llu hashes exceed the 2^31 - 1 one context ranks at once",
              (unsigned long long)total);
     ctx->n = n; ctx->total = total;
     ctx->h_off.assign(off, off + n + 1);
@@ -463,7 +464,7 @@ extern "C" int tc_sketches_upload_rows(tc_ctx *ctx, const uint64_t *const *rows,
     std::vector<uint64_t> off((size_t)n + 1, 0);
     for (uint32_t i = 0; i < n; i++) off[i + 1] = off[i] + sizes[i];
     const uint64_t total = off[n];
-    TC_CHECK(total < 0xFFFFFFF0ull, "tc_sketches_upload_rows: %llu hashes exceed the u32 rank space", (unsigned long long)total);
+    TC_CHECK(total <= 0x7FFFFFFFull, "tc_sketches_upload_rows: %llu hashes exceed the 2^31 - 1 one context ranks at once", (unsigned long long)total);
     if (ensure_cap(&ctx->d_hashes, &ctx->cap_hashes, std::max<uint64_t>(total, 1))) return 1;
     constexpr uint64_t CHUNK = 4u << 20;                         // hashes per staging buffer (32 MB)
     for (int b = 0; b < 2; b++) {
