@@ -564,7 +564,7 @@ def main():
     ap.add_argument("--n", type=int, default=100000, help="number of sketches (pairs workload)")
     ap.add_argument("--genomes", type=int, default=2048, help="genomes per step (sketch workload)")
     ap.add_argument("--genome-len", type=int, default=5000000)
-    ap.add_argument("--e2e-genomes", type=int, default=128, help="genomes per e2e step (sketch workload)")
+    ap.add_argument("--e2e-genomes", type=int, default=512, help="genomes per e2e step (sketch workload)")
     ap.add_argument("--ref-sample", type=int, default=4000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-bruteforce-only", action="store_true",

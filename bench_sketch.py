@@ -146,7 +146,7 @@ def measure_kssd(args, local_rank=0, rank=0):
     assert (n > 300).all() and (n < 700).all(), "KSSD sketch sizes out of the expected range"   # ~ L / 4096 = 488
     for g in range(0, ng, max(1, ng // 64)):
         assert (o[g, 1:n[g]] > o[g, :n[g] - 1]).all(), "KSSD sketch not strictly ascending"
-    ne = max(1, min(ng, args.e2e_genomes * 2))
+    ne = max(1, min(ng, args.e2e_genomes // 2))
     h_seq = torch.empty(ne * glen + 64, dtype=torch.uint8).pin_memory()
     h_seq[:ne * glen].copy_(seq[:ne * glen]); h_seq[ne * glen:] = 0
     h_out = torch.zeros((ne, stride), dtype=torch.int64).pin_memory()

@@ -613,8 +613,13 @@ extern "C" int tc_sketch_minhash(tc_ctx *ctx, const uint8_t *seqs, const uint64_
         TC_CUDA(cudaMalloc(&ws->d_n, (size_t)ngenomes * 4));
         ws->n_cap = ngenomes;
     }
-    // ---- batches of whole genomes, about TCLUST_SKETCH_CHUNK_MB (default 128) of sequence each
-    uint64_t chunk_bytes = 128ull << 20;
+    // ---- batches of whole genomes, about TCLUST_SKETCH_CHUNK_MB of sequence each.  Default: a quarter of the call's
+    // sequence, between 128 MB and 1 GB -- the copy of batch c+1 hides behind the kernels of batch c only if those are
+    // the shorter of the two, and the segment kernel is efficient from ~100 five-Mbp genomes per launch up (every
+    // segment pays its own bottom-s warm-up: 25 genomes per launch run at a third of the full-size rate; measured,
+    // profiles/r1m_sketch_chunk_sweep.txt)
+    const uint64_t seq_bytes = nrec ? rec_off[nrec] : 0;
+    uint64_t chunk_bytes = std::min<uint64_t>(1ull << 30, std::max<uint64_t>(128ull << 20, seq_bytes / 4));
     if (const char *e = getenv("TCLUST_SKETCH_CHUNK_MB")) chunk_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 1) << 20;
     K1Plan pl;
     uint64_t r0 = 0;
