@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 hot paths (contract: task brief, section 4).
 
-Headline (default, --workload pairs): ONE dense all-pairs pass (K3H hash-join kernel + candidate-edge
-epilogue + Boruvka round 1; TCLUST_PASS_IMPL=merge selects the first-generation merge kernel) over N=100,000 pre-sketched s=1000 MinHash sketches (BASELINE.json configs[2],
-the configuration the north-star's pairs/s target is quoted on; it fits one GPU).
+Headline (default, --workload pairs): ONE dense all-pairs pass (K3J block-join kernel over the per-block union
+lists, units where it does not pay on the K3H hash-join kernel; candidate-edge epilogue + Boruvka round 1;
+TCLUST_PASS_IMPL=join|merge selects K3H / the first-generation merge kernel) over N=100,000 pre-sketched s=1000
+MinHash sketches (BASELINE.json configs[2], the configuration the north-star's pairs/s target is quoted on; it fits
+one GPU).
     value  = pairwise sketch distances / s, sketches resident in HBM (CUDA events)
-    e2e    = same through the C ABI with HOST buffers: H2D upload + rank transform + pass + D2H edges
+    e2e    = same through the C ABI with HOST buffers: H2D upload + rank transform + union lists + pass + D2H edges
 --workload sketch: MinHash sketch construction, synthetic 5 Mbp genomes k=21 s=1000 (configs[1]).
---impl reference: the reference's own CPU path (oracle/_ref/ref_harness, AVX2 build of RabbitSketch)
-on a bounded sample of the same workload, all host threads.
+--impl reference: the reference's own CPU path -- the unmodified clust-mst binary (oracle/_ref, AVX2 build) on the
+full workload, its inverted-index generateMST phase; MinHash::distance brute force on a bounded sample beside it --
+all host threads.
 
 Multi-GPU: one process per GPU (torchrun); sketches replicated, the tile space of the fixed
 N=100k problem is dealt round-robin to the ranks ("strong" scaling); per step one
