@@ -54,6 +54,18 @@ def test_owned_pairs_partition():
             assert sum(mst_dist.owned_pairs(n, r, world) for r in range(world)) == n * (n - 1) // 2
 
 
+def test_unit_width_rule_and_dealing_at_bench_size():
+    # kj_pick_cseg mirror: at the bench size a unit is a whole row of tiles on 1..8 GPUs (2 units per CTA and rank);
+    # small sets keep K3H's 4096 columns; the round-robin dealing tiles the pair space whatever the width
+    assert mst_dist.join_cseg(100000, 1) == mst_dist.join_cseg(100000, 8) == 1 << 20
+    assert len(mst_dist.join_units(100000, nparts=8)) == 3125
+    assert mst_dist.join_cseg(500000, 8) == 1 << 20
+    assert mst_dist.join_cseg(20000, 1) == 1 << 20 and mst_dist.join_cseg(20000, 3) == 8192
+    assert mst_dist.join_cseg(20000, 8) == 4096 and mst_dist.join_cseg(300, 2) == 4096
+    for n, world in ((100000, 8), (20000, 4), (20000, 3)):
+        assert sum(mst_dist.owned_pairs(n, r, world) for r in range(world)) == n * (n - 1) // 2
+
+
 def test_shard_bounds_cover_everything():
     from rabbittclust_b200 import mst_dist
     for total in (0, 1, 7, 1000, 100000001):
