@@ -278,19 +278,20 @@ static int upload_sorted_runs(tc_ctx *ctx, const uint64_t *hashes, uint64_t tota
     // the copies start once everything queued on the work stream so far (a previous set's kernels) is done
     TC_CUDA(cudaEventRecord(ctx->ev_chunk[UP_CHUNKS], st));
     TC_CUDA(cudaStreamWaitEvent(ctx->up_copy_stream, ctx->ev_chunk[UP_CHUNKS], 0));
-    for (int c = 0; c < UP_CHUNKS; c++) {
-        const uint64_t pos = std::min(total, (uint64_t)c * clen), len = std::min(clen, total - pos);
-        if (len) TC_CUDA(cudaMemcpyAsync(ctx->d_hashes + pos, hashes + pos, len * 8, cudaMemcpyHostToDevice, ctx->up_copy_stream));
-        TC_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->up_copy_stream));
-    }
     iota_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(us->v_a, total);
     // level 0 (sorted pieces) lives in B, level 1 in A, level 2 in B, ...
     auto kbuf = [&](int level) { return (level & 1) ? us->k_a : us->k_b; };
     auto vbuf = [&](int level) { return (level & 1) ? us->v_a : us->v_b; };
     int top = 0;
     while ((1 << top) < UP_CHUNKS) top++;
+    // Piece c's copy is queued, then its sort and merges, then piece c+1's copy: from page-locked memory all of it is
+    // asynchronous and the copy queue never runs dry (a piece takes ~2 ms, queueing its sort ~0.1 ms); from pageable memory
+    // (a std::vector of the reference) cudaMemcpyAsync returns when the piece is staged, and the work queued before it runs
+    // on the device in the meantime.
     for (int c = 0; c < UP_CHUNKS; c++) {
         const uint64_t pos = std::min(total, (uint64_t)c * clen), len = std::min(clen, total - pos);
+        if (len) TC_CUDA(cudaMemcpyAsync(ctx->d_hashes + pos, hashes + pos, len * 8, cudaMemcpyHostToDevice, ctx->up_copy_stream));
+        TC_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->up_copy_stream));
         TC_CUDA(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
         if (len) {
             size_t tb = us->tmp_bytes;
