@@ -224,3 +224,57 @@ def test_dense_ani_and_noise_removal_golden(oracle, tag, contain):
     _, labels, _ = oracle.remove_noise_clusters(mst, n, 0.05, dense)
     mine = sorted(sorted(info[i]["name"] for i in np.nonzero(labels == c)[0]) for c in range(labels.max() + 1))
     assert mine == partition(sketch_io.parse_cluster_file(os.path.join(GOLD, "dense", "presk_%s.removeNoise" % tag)))
+
+
+def _read_kssd_hash_sketch(path, nsketch=None):
+    import struct
+    data = open(path, "rb").read()
+    hdr = struct.unpack_from("<iiiii", data, 0)            # id, half_k, half_subk, drlevel, genomeNumber
+    pos, sk = 20, []
+    while pos < len(data) and (nsketch is None or len(sk) < nsketch):
+        (m,) = struct.unpack_from("<Q", data, pos); pos += 8
+        sk.append(np.frombuffer(data, "<u4", m, pos).astype(np.uint64)); pos += 4 * m
+    assert pos == len(data)
+    return hdr, sk
+
+
+def test_append_golden_kssd(oracle):
+    """clust-mst --fast --append of the unmodified reference (tools/make_golden_append.py): 9 genomes clustered, 7
+    appended.  The new folder holds all 16 sketches behind the OLD parameter block (genomeNumber stays 9,
+    sub_command.cpp:1349), and MST(old MST + new-vs-all edges) has the weights of the all-at-once run and of the oracle."""
+    d = os.path.join(GOLD, "append", "kssd")
+    hdr_b, sk_b = _read_kssd_hash_sketch(os.path.join(d, "base", "kssd.hash.sketch"))
+    hdr_r, sk_r = _read_kssd_hash_sketch(os.path.join(d, "result", "kssd.hash.sketch"))
+    assert hdr_b[4] == 9 and len(sk_b) == 9
+    assert hdr_r == hdr_b and len(sk_r) == 16                      # old parameter block, genome count included
+    _, sk_all = _read_kssd_hash_sketch(os.path.join(GOLD, "kssd", "kssd.hash.sketch"))
+    assert all(np.array_equal(a, b) for a, b in zip(sk_r, sk_all))
+    assert all(np.array_equal(a, b) for a, b in zip(sk_r, sk_b))
+    half_k = hdr_b[1]
+    res = sketch_io.read_edge_mst(os.path.join(d, "result", "edge.mst"))
+    full = sketch_io.read_edge_mst(os.path.join(GOLD, "kssd", "edge.mst"))
+    assert np.array_equal(np.sort(res["dist"]), np.sort(full["dist"]))
+    mst = oracle.mst(sk_r, 2 * half_k, 0.05)
+    assert np.array_equal(np.sort(mst["dist"]), np.sort(res["dist"]))
+    # the oracle's append rule itself: forest of the new-vs-all edges + old MST, Kruskal
+    old = sketch_io.read_edge_mst(os.path.join(d, "base", "edge.mst"))
+    assert np.array_equal(np.sort(oracle.mst(sk_b, 2 * half_k, 0.05)["dist"]), np.sort(old["dist"]))
+    assert partition(sketch_io.parse_cluster_file(os.path.join(d, "result", "app.txt"))) == \
+        partition(sketch_io.parse_cluster_file(os.path.join(GOLD, "kssd", "clusters.txt")))
+
+
+def test_append_golden_minhash(oracle):
+    """clust-mst --append of the unmodified reference on the same split (Mash mode, k = 15, s = 1000): folder, weights and
+    partition of the appended result equal the all-at-once golden run (tests/golden/mst_list) and the oracle's MST."""
+    d = os.path.join(GOLD, "append", "minhash")
+    res = sketch_io.read_hash_sketch(os.path.join(d, "result", "hash.sketch"))
+    full = sketch_io.read_hash_sketch(os.path.join(GOLD, "mst_list", "hash.sketch"))
+    assert res["k"] == full["k"] == 15 and res["param"] == full["param"] == 1000 and len(res["sketches"]) == 16
+    assert all(np.array_equal(a, b) for a, b in zip(res["sketches"], full["sketches"]))
+    assert open(os.path.join(d, "result", "info.sketch"), "rb").read() == open(os.path.join(GOLD, "mst_list", "info.sketch"), "rb").read()
+    e_res = sketch_io.read_edge_mst(os.path.join(d, "result", "edge.mst"))
+    e_full = sketch_io.read_edge_mst(os.path.join(GOLD, "mst_list", "edge.mst"))
+    assert np.array_equal(np.sort(e_res["dist"]), np.sort(e_full["dist"]))
+    assert np.array_equal(np.sort(oracle.mst(res["sketches"], 15, 0.05)["dist"]), np.sort(e_res["dist"]))
+    assert partition(sketch_io.parse_cluster_file(os.path.join(d, "result", "app.txt"))) == \
+        partition(sketch_io.parse_cluster_file(os.path.join(GOLD, "mst_list", "clusters.txt")))
