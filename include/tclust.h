@@ -191,6 +191,23 @@ int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double threshold,
            tc_edge *out, uint64_t *n_out);
 
 /*
+ * Multi-GPU group ("N x N tile space sharded over the GPUs of one box, min-reduction per Boruvka round").
+ * One context per GPU -- in one process (one host thread per context) or in one process per GPU (torchrun).  Every
+ * context exports a handle to its exchange buffer, the host gathers the handles of all ranks in rank order (any
+ * plumbing: torch.distributed all_gather, a shared array) and every context joins with the full list.  From then on
+ * tc_mst / tc_mst_append on the member contexts are COLLECTIVE calls: every rank must hold the same sketch set (same
+ * n <= n_max) and call them in the same order.  Rank r evaluates the work units u with u mod G == r of the dense pass;
+ * the per-round min-reductions of Boruvka run inside the kernel over NVLink peer memory (k4_boruvka.cu), with no NCCL
+ * call and no host round trip per round; every rank returns the same MST.  Replaces the OpenMP task pool plus final
+ * Kruskal of compute_minhash_mst (src/MST.cpp:1373-1386, 1715-1723) across GPUs.  At most 8 ranks.
+ */
+#define TC_MG_HANDLE_BYTES 128
+int tc_mg_export(tc_ctx *ctx, uint32_t n_max, void *handle_out /* TC_MG_HANDLE_BYTES */);
+int tc_mg_join(tc_ctx *ctx, int rank, int nranks, const void *handles /* nranks x TC_MG_HANDLE_BYTES, rank order */);
+int tc_mg_leave(tc_ctx *ctx);
+int tc_mg_rank(const tc_ctx *ctx, int *rank, int *nranks);
+
+/*
  * Incremental MST = append_clust_mst (src/sub_command.cpp:1578-1706): the uploaded set is old genomes [0, start_index)
  * followed by new ones; pre_mst is the saved MST of the old genomes (edge.mst).  Only the pairs (new, earlier) are
  * evaluated on the device; the result is the MST of old-MST + new candidate edges, sorted by (dist, i, j).

@@ -26,7 +26,9 @@ SYMBOLS = [
     "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce", "tc_greedy_cluster_kssd", "tc_dense_ani", "tc_allpairs_pass_from", "tc_mst_append",
     "tc_jaccard_b", "tc_distance_b", "tc_contain_distance",
     "tc_mash_dist", "tc_aaf_dist", "tc_dist_from_key", "tc_radio", "tc_greedy_common_min", "tc_greedy_dist",
+    "tc_mg_export", "tc_mg_join", "tc_mg_leave", "tc_mg_rank", "tc_mst_stats",
 ]
+MG_HANDLE_BYTES = 128
 
 
 class TclustError(RuntimeError):
@@ -105,6 +107,11 @@ def lib():
     L.tc_greedy_common_min.restype = C.c_int
     L.tc_greedy_dist.argtypes = [C.c_int] * 5
     L.tc_greedy_dist.restype = C.c_double
+    L.tc_mg_export.argtypes = [vp, C.c_uint32, vp]
+    L.tc_mg_join.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.tc_mg_leave.argtypes = [vp]
+    L.tc_mg_rank.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.tc_mst_stats.argtypes = [vp, C.POINTER(C.c_double)]
     L.tc_radio.argtypes = [C.c_double, C.c_int]
     L.tc_radio.restype = C.c_int
     _lib = L
@@ -322,6 +329,29 @@ class Context:
         m = C.c_uint64(0)
         _chk(lib().tc_mst(self._h, k, int(containment), threshold, out.ctypes.data, C.byref(m)))
         return out[:int(m.value)].copy()
+
+    # ---- multi-GPU group (tc_mg_*): after join(), mst()/mst_append() are collective over the ranks
+    def mg_export(self, n_max):
+        """Handle (bytes) of this context's exchange buffer, laid out for sets of up to n_max sketches."""
+        buf = C.create_string_buffer(MG_HANDLE_BYTES)
+        _chk(lib().tc_mg_export(self._h, n_max, buf))
+        return buf.raw
+
+    def mg_join(self, rank, nranks, handles):
+        """handles: the exported handles of all ranks, in rank order (list of bytes or one bytes object)."""
+        blob = handles if isinstance(handles, (bytes, bytearray)) else b"".join(handles)
+        assert len(blob) == nranks * MG_HANDLE_BYTES
+        _chk(lib().tc_mg_join(self._h, rank, nranks, C.c_char_p(bytes(blob))))
+
+    def mg_leave(self):
+        _chk(lib().tc_mg_leave(self._h))
+
+    def mst_stats(self):
+        """Timings of the last mst() on this context (CUDA events on its stream), candidate edges, Boruvka rounds."""
+        v = (C.c_double * 8)()
+        _chk(lib().tc_mst_stats(self._h, v))
+        return {"pass_ms": v[0], "boruvka_ms": v[1], "sort_ms": v[2], "edges": int(v[3]), "rounds": int(v[4]),
+                "tiles_flagged": int(v[5]), "tiles_total": int(v[6]), "on_reordered_copy": bool(v[7])}
 
     def greedy_scan(self, q0, q1, rep_ids):
         reps = np.ascontiguousarray(rep_ids, np.uint32)

@@ -324,11 +324,8 @@ __global__ void pair_common_ref_kernel(const uint64_t *hashes, const unsigned lo
 template <int MODE, bool FH, bool SEMB>
 int k3_launch_t(tc_ctx *ctx, const K3Args &a, int grid)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        TC_CUDA(cudaFuncSetAttribute(k3_tile_kernel<MODE, FH, SEMB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM));
-        attr_set = true;
-    }
+    // set on every launch: the attribute is per device (a process may hold contexts on several) and the call is host-only
+    TC_CUDA(cudaFuncSetAttribute(k3_tile_kernel<MODE, FH, SEMB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM));
     k3_tile_kernel<MODE, FH, SEMB><<<grid, K3_THREADS, K3_SMEM, ctx->stream>>>(a);
     return 0;
 }
@@ -379,6 +376,7 @@ int k3_launch(tc_ctx *ctx, K3Args &a, int mode, bool fh)
 int tc_launch_tiles_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out,
                            uint32_t semb_size)
 {
+    if (tc_ensure_interleaved(ctx)) return 1;
     K3Args a{};
     a.semb_size = semb_size;
     a.row = main_set(ctx); a.col = main_set(ctx);
@@ -394,6 +392,7 @@ int tc_launch_tiles_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, u
 // queries [q0,q1) of the main set against the representative table: common and first_hit matrices
 int tc_launch_tiles_rep_matrix(tc_ctx *ctx, uint32_t q0, uint32_t q1, uint32_t *d_common, uint32_t *d_first_hit)
 {
+    if (tc_ensure_interleaved(ctx)) return 1;
     K3Args a{};
     a.row = main_set(ctx); a.col = rep_set(ctx);
     a.rg0 = q0 / TC_GROUP; a.rg1 = (q1 + TC_GROUP - 1) / TC_GROUP;
@@ -407,6 +406,7 @@ int tc_launch_tiles_rep_matrix(tc_ctx *ctx, uint32_t q0, uint32_t q1, uint32_t *
 
 int tc_launch_tiles_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t semb_size)
 {
+    if (tc_ensure_interleaved(ctx)) return 1;
     K3Args a{};
     a.semb_size = semb_size;
     a.row = main_set(ctx); a.col = main_set(ctx);
@@ -423,6 +423,7 @@ int tc_launch_tiles_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts
 int tc_launch_tiles_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment,
                           double jmin, uint32_t part, uint32_t nparts, uint32_t semb_size)
 {
+    if (tc_ensure_interleaved(ctx)) return 1;
     K3Args a{};
     a.semb_size = semb_size;
     a.row = main_set(ctx);

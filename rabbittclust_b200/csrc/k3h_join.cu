@@ -70,6 +70,8 @@ struct KHArgs {
     // block join (K3J): union lists of the 32-sketch column blocks
     const uint32_t *bu_keys, *bu_mask, *bu_count;
     const uint32_t *multi;          // bit r = rank r occurs in at least two sketches (only those can be shared)
+    // tile candidacy (k3t_tileflags.cu): bit cb of row rb set = blocks rb and cb share a rank; nullptr = visit every tile
+    const uint32_t *tile_flags; uint32_t tile_words;
 };
 
 // presence filter: word = top (KH_FBITS-5) bits of h = x * golden, the two bit positions = low 10 bits of h
@@ -429,6 +431,10 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                 if (lane == 0) c = atomicAdd(&s_next, 1u);
                 c = __shfl_sync(0xffffffffu, c, 0);
                 if (c >= c1) break;
+                if (!CAND && a.tile_flags) {           // no rank of this column's block occurs in the row block: every count is 0
+                    const uint32_t cb = c >> 5;
+                    if (!((__ldg(a.tile_flags + (size_t)rb * a.tile_words + (cb >> 5)) >> (cb & 31)) & 1u)) continue;
+                }
                 const uint32_t cid = (CAND && a.col_ids) ? __ldg(a.col_ids + c) : c;      // sketch streamed as column c
                 const uint32_t clen = a.size[cid];
                 uint32_t *st = state + (size_t)(c - c0) * STRIDE;
@@ -640,6 +646,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
     __shared__ uint32_t s_unit, s_next, s_nheavy, s_heavy[KJ_HEAVY_CAP];
     __shared__ uint32_t s_lo[32], s_hi[32], s_len[32];
     __shared__ unsigned long long s_base[32];
+    __shared__ uint32_t s_rlo, s_rhi, s_nflag;
 
     const int tid = threadIdx.x, warp = tid >> 5;
     uint32_t lane = tid & 31;
@@ -661,13 +668,30 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
         const uint32_t rb = unit.rb, c0 = unit.c0, c1 = unit.c1;      // c0 is a multiple of 32
         const uint32_t piv0 = a.pivoff[rb];
         const uint32_t P = a.pivoff[rb + 1] - piv0 + 1;
+        const uint32_t cb_begin = c0 / 32, cb_end = (c1 + 31) / 32;
+        const uint32_t *flag_row = a.tile_flags ? a.tile_flags + (size_t)rb * a.tile_words : nullptr;
+        // the row block's own union list (ascending distinct shared ranks + the mask of the rows holding each): the
+        // table is built from it -- ~1,300 insertions for 32 related sketches instead of 32 x 1000 elements with a
+        // bitmap look-up each.  0xFFFFFFFF: the block has no list, build from the rows.
+        const uint32_t Drow = a.bu_count[rb * KH_DREC];
+        const unsigned long long rbase = rb * 32 < a.n ? a.off[rb * 32] : 0ULL;
+        const uint32_t *rkeys = a.bu_keys + rbase, *rmasks = a.bu_mask + rbase;
         if (tid < 32) {
             const uint32_t id = rb * 32 + tid;
             s_len[tid] = id < a.n ? a.size[id] : 0u;
             s_base[tid] = id < a.n ? a.off[id] : 0ULL;
             s_lo[tid] = 0;
+            // flagged tiles of this unit: with many of them every warp keeps its tiles to itself, with a few the
+            // dense ones are shared by the whole CTA (deferred tiles below)
+            uint32_t nf = 0;
+            if (flag_row) {
+                for (uint32_t cb = cb_begin + tid; cb < cb_end; cb += 32) nf += (__ldg(flag_row + (cb >> 5)) >> (cb & 31)) & 1u;
+                for (int o = 16; o; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
+            } else nf = cb_end - cb_begin;
+            if (tid == 0) s_nflag = nf;
         }
         __syncthreads();
+        const bool unit_defers = s_nflag < 64u;
 
         for (uint32_t p = 0; p < P; p++) {
             const uint32_t piv_lo = p == 0 ? 0u : a.pivots[piv0 + p - 1];
@@ -677,14 +701,30 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                 const uint4 e = make_uint4(KH_EMPTY, 0u, KH_EMPTY, 0u);
                 for (uint32_t i = tid; i < KH_SLOTS / 2; i += KH_THREADS) t4[i] = e;
                 for (uint32_t i = tid; i < KJ_FWORDS; i += KH_THREADS) filter[i] = 0xFFFFFFFFu;   // inverted: 0 = present
-                if (tid < 32) {
-                    const uint32_t *row = a.ranks + s_base[tid];
-                    s_hi[tid] = (p + 1 == P) ? s_len[tid] : kh_lower_bound(row, s_lo[tid], s_len[tid], piv_hi);
+                if (Drow == 0xFFFFFFFFu) {
+                    if (tid < 32) {
+                        const uint32_t *row = a.ranks + s_base[tid];
+                        s_hi[tid] = (p + 1 == P) ? s_len[tid] : kh_lower_bound(row, s_lo[tid], s_len[tid], piv_hi);
+                    }
+                } else if (tid == 32) {
+                    const uint32_t lo = p == 0 ? 0u : kh_lower_bound(rkeys, 0, Drow, piv_lo);
+                    s_rlo = lo; s_rhi = (p + 1 == P) ? Drow : kh_lower_bound(rkeys, lo, Drow, piv_hi);
                 }
-                if (tid == 0) { s_next = c0 / 32; s_nheavy = 0; }
+                if (tid == 0) { s_next = 0; s_nheavy = 0; }
             }
             __syncthreads();
-            {   // build: warp w inserts the partition's elements of row w
+            if (Drow != 0xFFFFFFFFu) {   // build from the union list: distinct keys, the mask is ready
+                for (uint32_t e = s_rlo + tid; e < s_rhi; e += KH_THREADS) {
+                    const uint32_t x = __ldg(rkeys + e), m = __ldg(rmasks + e);
+                    const uint32_t h = x * 0x9E3779B1u;
+                    atomicAnd(&filter[kj_fword(h)], ~kh_fmask(h));
+                    uint32_t slot = kh_slot(x);
+                    for (;;) {
+                        if (atomicCAS(&table[slot].x, KH_EMPTY, x) == KH_EMPTY) { table[slot].y = m; break; }
+                        slot = (slot + 1) & (KH_SLOTS - 1);
+                    }
+                }
+            } else {   // build: warp w inserts the partition's elements of row w
                 const uint32_t *row = a.ranks + s_base[warp];
                 const uint32_t bit = 1u << warp;
                 for (uint32_t e = s_lo[warp] + lane; e < s_hi[warp]; e += 32) {
@@ -834,11 +874,8 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                     }
                 }
             };
-            for (;;) {
-                uint32_t cb = 0;
-                if (lane == 0) cb = atomicAdd(&s_next, 1u);
-                cb = __shfl_sync(0xffffffffu, cb, 0);
-                if (cb * 32 >= c1) break;
+            // one tile (row block x column block cb) on this warp
+            auto process_tile = [&](const uint32_t cb) {
                 const uint32_t D = a.bu_count[cb * KH_DREC];
                 const unsigned long long lbase = a.off[cb * 32];
                 const uint32_t *keys = a.bu_keys + lbase, *cmasks = a.bu_mask + lbase;
@@ -857,7 +894,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                     for (int q = 0; q < 16; q++) cntw[lane + 32 * q] = 0u;
                 }
                 __syncwarp();
-                const bool deferred = stream_slice(keys, cmasks, lo, hi, true, anyhit);
+                const bool deferred = stream_slice(keys, cmasks, lo, hi, unit_defers, anyhit);
                 __syncwarp();
                 if (deferred) {                                   // redone by the whole CTA below
                     uint32_t slot = 0;
@@ -865,7 +902,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                     slot = __shfl_sync(0xffffffffu, slot, 0);
                     if (slot < KJ_HEAVY_CAP) {
                         if (lane == 0) s_heavy[slot] = cb;
-                        continue;
+                        return;
                     }
                     // list full: this warp redoes the tile on its own
                     anyhit = p == 0 ? 0u : tst[KJ_TILE_WORDS];
@@ -890,6 +927,22 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                     for (uint32_t r = 0; r < 32; r++) emit_row(r, cb, anyhit ? (uint32_t)cnt[r * 32 + lane] : 0u);
                 }
                 __syncwarp();
+            };
+            // hand-out: 8 column blocks per grab, only the flagged ones are visited
+            for (;;) {
+                uint32_t g = 0;
+                if (lane == 0) g = atomicAdd(&s_next, 1u);
+                g = __shfl_sync(0xffffffffu, g, 0);
+                const uint32_t cb0 = cb_begin + g * 8u;
+                if (cb0 >= cb_end) break;
+                uint32_t bits = 0xFFu;
+                if (flag_row) bits = __funnelshift_r(__ldg(flag_row + (cb0 >> 5)), __ldg(flag_row + (cb0 >> 5) + 1), cb0 & 31) & 0xFFu;
+                if (cb_end - cb0 < 8u) bits &= (1u << (cb_end - cb0)) - 1u;
+                while (bits) {
+                    const uint32_t cb = cb0 + (uint32_t)__ffs(bits) - 1u;
+                    bits &= bits - 1u;
+                    process_tile(cb);
+                }
             }
             __syncthreads();
             // ---- deferred tiles: all warps share one tile -- warp w streams the w-th 32nd of the list into its own
@@ -915,7 +968,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                     for (int q = 0; q < 16; q++) cntw[lane + 32 * q] = 0u;
                 }
                 __syncwarp();
-                const uint32_t chunk = ((hi - lo + 31) / 32 + 127) / 128 * 128;
+                const uint32_t chunk = ((hi - lo + 31) / 32 + 31) / 32 * 32;      // whole groups of 32 keys per warp
                 const uint32_t slo = min(hi, lo + (uint32_t)warp * chunk), shi = min(hi, slo + chunk);
                 uint32_t anyhit = 0;
                 stream_slice(keys, cmasks, slo, shi, false, anyhit);
@@ -953,10 +1006,9 @@ int tc_kh_prepare(tc_ctx *ctx)
     }
     uint32_t *d_dist = ctx->d_bu_count;
     TC_CUDA(cudaMemsetAsync(d_dist, 0, (size_t)nrb * KH_DREC * 4, st));
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_set & 1u)) {        // per context: the attribute is a per-device property
         TC_CUDA(cudaFuncSetAttribute(k3h_distinct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KH_SORT_CAP * 5)));
-        attr_set = true;
+        ctx->attr_set |= 1u;
     }
     // union lists of the 32-sketch blocks (K3J): as many slots as elements
     if (ctx->total + 1 > ctx->cap_bu) {
@@ -1034,6 +1086,7 @@ int tc_kh_prepare(tc_ctx *ctx)
         }
         rc = 0;
     } while (0);
+    if (!rc) rc = tc_tile_flags_build(ctx, dist);
     return rc;
 }
 
@@ -1042,12 +1095,11 @@ int tc_kh_prepare(tc_ctx *ctx)
 static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &units, bool edge_list = false,
                      bool block_kernel = false, bool record_start = true, const tc_kh_unit *d_resident = nullptr)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_set & 2u)) {
         TC_CUDA(cudaFuncSetAttribute(k3h_join_kernel<KH_MODE_EDGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KH_SMEM));
         TC_CUDA(cudaFuncSetAttribute(k3h_join_kernel<KH_MODE_CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KH_SMEM));
         TC_CUDA(cudaFuncSetAttribute(k3j_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KJ_SMEM));
-        attr_set = true;
+        ctx->attr_set |= 2u;
     }
     if (units.empty()) return 0;
     if (!d_resident && units.size() > ctx->kh_units_cap) {
@@ -1061,8 +1113,9 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
         TC_CUDA(cudaStreamSynchronize(ctx->stream));   // `units` (host) must outlive the copy
         ctx->kh_units_on_device = edge_list;
     }
+    const bool nosync = d_resident && ctx->pass_nosync;       // nothing on the host has to outlive a copy
     const long long mine = ((long long)units.size() - a.part + a.nparts - 1) / a.nparts;
-    if (mine <= 0) { TC_CUDA(cudaStreamSynchronize(ctx->stream)); return 0; }
+    if (mine <= 0) { if (!nosync) TC_CUDA(cudaStreamSynchronize(ctx->stream)); return 0; }
     const int grid = (int)std::min<long long>(mine, ctx->num_sms);
     if (!ctx->d_kh_state) TC_CUDA(cudaMalloc(&ctx->d_kh_state, (size_t)ctx->num_sms * KH_STATE_WORDS_MAX * 4));
     a.ranks = ctx->d_ranks; a.off = reinterpret_cast<const unsigned long long *>(ctx->d_off); a.size = ctx->d_size;
@@ -1070,6 +1123,8 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
     a.units = d_resident ? d_resident : ctx->d_kh_units; a.nunits = (uint32_t)units.size();
     a.counters = ctx->d_edge_count; a.state = ctx->d_kh_state;
     a.bu_keys = ctx->d_bu_keys; a.bu_mask = ctx->d_bu_mask; a.bu_count = ctx->d_bu_count; a.multi = ctx->d_multi;
+    a.tile_flags = nullptr; a.tile_words = 0;
+    if (a.mode == KH_MODE_EDGES && ctx->tile_words) { a.tile_flags = ctx->d_tile_flags; a.tile_words = ctx->tile_words; }
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count + 2, 0, sizeof(unsigned long long), ctx->stream));
     if (ctx->ev_pass0 && record_start) cudaEventRecord(ctx->ev_pass0, ctx->stream);   // kernel-only duration, tc_last_pass_kernel_ms
     if (block_kernel) k3j_block_kernel<<<grid, KH_THREADS, KJ_SMEM, ctx->stream>>>(a);
@@ -1078,7 +1133,7 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
     if (ctx->ev_pass1) cudaEventRecord(ctx->ev_pass1, ctx->stream);
     ctx->launches++;
     TC_CUDA(cudaGetLastError());
-    TC_CUDA(cudaStreamSynchronize(ctx->stream));   // `units` (host) must outlive the copy
+    if (!nosync) TC_CUDA(cudaStreamSynchronize(ctx->stream));   // `units` (host) must outlive the copy
     return 0;
 }
 
@@ -1190,6 +1245,8 @@ struct KjRouting {
     }
     bool pays(const tc_ctx *ctx, const tc_kh_unit &u) const
     {
+        // a row block that shares ranks with few column blocks visits few tiles on the block kernel (tile flags)
+        if (ctx->tile_words && u.rb < ctx->tile_rowcount.size() && (uint64_t)ctx->tile_rowcount[u.rb] * 8 <= u.rb + 1) return true;
         if (ctx->kh_parts.empty() || ctx->kh_parts[u.rb] > 2) return false;
         const uint32_t b0 = u.c0 / 32, b1 = (u.c1 + 31) / 32;
         const uint64_t elems = ctx->h_off[std::min<uint32_t>(ctx->n, b1 * 32)] - ctx->h_off[b0 * 32];
@@ -1240,7 +1297,13 @@ int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t np
                 old.push_back(tc_kh_unit{un.rb, c0, std::min(un.c1, c0 + KH_CSEG)});
         }
         // widest units first: the dynamic hand-out then ends on the small ones (a unit is up to a whole row of tiles)
-        std::stable_sort(blk.begin(), blk.end(), [](const tc_kh_unit &x, const tc_kh_unit &y) { return x.c1 - x.c0 > y.c1 - y.c0; });
+        // (with tile flags the work of a unit is its flagged tiles: the share of the row's flagged tiles its width covers)
+        auto weight = [&](const tc_kh_unit &x) -> uint64_t {
+            const uint64_t w = x.c1 - x.c0;
+            if (!ctx->tile_words || x.rb >= ctx->tile_rowcount.size()) return w;
+            return (uint64_t)ctx->tile_rowcount[x.rb] * 32 * w / ((uint64_t)x.rb * 32 + 32) + 1;
+        };
+        std::stable_sort(blk.begin(), blk.end(), [&](const tc_kh_unit &x, const tc_kh_unit &y) { return weight(x) > weight(y); });
         if (blk.size() + old.size() > ctx->kj_units_cap || !ctx->d_kj_units) {
             cudaFree(ctx->d_kj_units);
             ctx->d_kj_units = nullptr; ctx->kj_units_cap = 0;

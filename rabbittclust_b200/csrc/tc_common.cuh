@@ -31,12 +31,30 @@ constexpr uint32_t TC_RANK_MAX = 0xFFFFFFFDu;
 
 struct tc_kh_unit { uint32_t rb, c0, c1; };   // K3H work unit: row block x column segment [c0, c1)
 
+// K4 (k4_boruvka.cu): device-resident Boruvka state; xbuf is the buffer peers map in a multi-GPU group
+struct tc_k4_state {
+    unsigned long long *d_xbuf = nullptr; uint64_t cap_xbuf = 0; uint32_t xbuf_n = 0;
+    unsigned long long *d_red = nullptr;  uint64_t cap_red = 0;
+    uint32_t *d_parent = nullptr;         uint64_t cap_parent = 0;
+    unsigned long long *d_out = nullptr;  uint64_t cap_out = 0;      // forest (key, id) + sort alternates: 4 x n
+    uint32_t *d_ctl = nullptr;
+    void *d_sort_tmp = nullptr;           uint64_t cap_sort_tmp = 0;
+    void *h_out = nullptr;                uint64_t h_out_bytes = 0;  // page-locked read-back buffer
+    int grid = 0;
+    int rank = 0, nranks = 0;             // multi-GPU group (0/1: single GPU)
+    unsigned long long *peer_xbuf[8] = {};
+    bool peer_opened[8] = {};             // mapped with cudaIpcOpenMemHandle (another process), to be closed
+    unsigned long long sys_base = 0;
+    uint32_t last_rounds = 0;             // Boruvka rounds of the last tc_mst
+};
+
 struct tc_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     cudaEvent_t ev_pass0 = nullptr, ev_pass1 = nullptr;   // around the last dense-pass kernel
+    uint32_t attr_set = 0;                // dynamic shared-memory opt-ins done on this context's device (bit per file)
     bool boruvka_async = false;           // tc_boruvka_set_async: the Boruvka phases do not synchronise the stream
 
     // resident sketches (HP-2)
@@ -47,6 +65,7 @@ struct tc_ctx {
     uint32_t *d_size = nullptr;   // n sizes
     uint32_t *d_ranks = nullptr;  // order-preserving dense u32 ranks of the hashes, same layout as d_hashes
     uint32_t ngroups = 0;
+    bool gt_valid = false;        // d_gt / d_goff hold the current set (built on first use by the merge kernel's launchers)
     uint32_t *d_gt = nullptr;     // group-interleaved ranks: [group][row][lane]
     uint64_t *d_goff = nullptr;   // ngroups+1 element offsets into d_gt
     uint64_t cap_hashes = 0, cap_ranks = 0, cap_gt = 0, cap_n = 0, cap_groups = 0, cap_comp = 0;   // element capacities
@@ -92,6 +111,12 @@ struct tc_ctx {
     tc_kh_unit *d_kj_units = nullptr;
     uint64_t kj_split_key = 0;
     bool kj_split_valid = false;
+    // tile candidacy (k3t_tileflags.cu): bit (rb, cb) of row rb = some rank occurs both in block rb and in block cb
+    uint32_t *d_tile_flags = nullptr, *d_tile_rowcount = nullptr;
+    uint64_t cap_tile_flags = 0, cap_tile_rowcount = 0;
+    uint32_t tile_words = 0;             // words per row of d_tile_flags (0: no flags, every tile is visited)
+    std::vector<uint32_t> tile_rowcount; // flagged tiles per row block
+    uint64_t tiles_flagged = 0;
     uint64_t pairs_cache_key = 0, pairs_cache_val = 0;     // n_pairs of the last sharded pass (tc_allpairs_pass, nparts > 1)
     bool pairs_cache_valid = false;
 
@@ -119,13 +144,24 @@ struct tc_ctx {
     cudaStream_t up_copy_stream = nullptr;
     cudaEvent_t ev_chunk[TC_UP_CHUNKS + 1] = {};
 
+    tc_k4_state k4;
+    bool pass_nosync = false;            // dense-pass launchers do not wait for the device (tc_mst queues pass + Boruvka back to back)
+
     // scratch
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
 };
 
 int tc_scratch(tc_ctx *ctx, size_t bytes, void **out);
+int tc_ensure_interleaved(tc_ctx *ctx);    // tclust_api.cu
 void tc_k1_free(tc_ctx *ctx);
+// device Boruvka (k4_boruvka.cu)
+size_t tc_k4_xbuf_words(uint32_t n);
+void tc_k4_free(tc_ctx *ctx);
+int tc_k4_reserve(tc_ctx *ctx, uint32_t n);
+int tc_k4_enqueue(tc_ctx *ctx, int mode, const unsigned long long *d_fin_key, const unsigned long long *d_fin_id, uint32_t nfin);
+int tc_k4_collect(tc_ctx *ctx, int mode, int kmer_size, std::vector<tc_edge> &mst, uint64_t *n_edges_dev, bool *overflow,
+                  std::vector<int32_t> *comp_out);
 void tc_k2_free(tc_ctx *ctx);
 
 // tile-kernel entry points (k3_tile.cu)
@@ -138,6 +174,7 @@ int tc_launch_tiles_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, in
                           double jmin, uint32_t part, uint32_t nparts, uint32_t semb_size = 0);
 // hash-join pass (k3h_join.cu)
 int tc_kh_prepare(tc_ctx *ctx);
+int tc_tile_flags_build(tc_ctx *ctx, const std::vector<uint32_t> &dist);   // k3t_tileflags.cu
 int tc_launch_join_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
 int tc_launch_blockjoin_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
 int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index, bool force_block);

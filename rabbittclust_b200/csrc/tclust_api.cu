@@ -36,6 +36,7 @@ int tc_scratch(tc_ctx *ctx, size_t bytes, void **out)
     return 0;
 }
 
+extern "C" void tc_ctx_destroy(tc_ctx *ctx);
 extern "C" int tc_ctx_create(int device, tc_ctx **out)
 {
     int ndev = 0;
@@ -46,12 +47,12 @@ extern "C" int tc_ctx_create(int device, tc_ctx **out)
         return 1;
     }
     TC_CHECK(device >= 0 && device < ndev, "tc_ctx_create: device %d out of range (%d devices)", device, ndev);
-    if (const char *m = getenv("TCLUST_SYNC")) {          // how the host waits in cudaStreamSynchronize (before the context exists)
+    TC_CUDA(cudaSetDevice(device));
+    if (const char *m = getenv("TCLUST_SYNC")) {          // how the host waits in cudaStreamSynchronize, for THIS device (set before its context is used)
         const unsigned f = !strcmp(m, "spin") ? cudaDeviceScheduleSpin : !strcmp(m, "yield") ? cudaDeviceScheduleYield
                          : !strcmp(m, "block") ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto;
         if (cudaSetDeviceFlags(f) != cudaSuccess) cudaGetLastError();
     }
-    TC_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     TC_CUDA(cudaGetDeviceProperties(&prop, device));
     TC_CHECK(prop.major >= 10, "tc_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
@@ -59,11 +60,17 @@ extern "C" int tc_ctx_create(int device, tc_ctx **out)
     tc_ctx *ctx = new tc_ctx();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
-    TC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    TC_CUDA(cudaEventCreate(&ctx->ev_pass0));
-    TC_CUDA(cudaEventCreate(&ctx->ev_pass1));
-    TC_CUDA(cudaMalloc(&ctx->d_edge_count, 4 * sizeof(unsigned long long)));
-    TC_CUDA(cudaMemset(ctx->d_edge_count, 0, 4 * sizeof(unsigned long long)));
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_pass0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_pass1);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_edge_count, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_edge_count, 0, 4 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {                               // a partly built context is torn down, not leaked
+        tc_set_error("tc_ctx_create: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        tc_ctx_destroy(ctx);
+        return 1;
+    }
     *out = ctx;
     return 0;
 }
@@ -76,6 +83,8 @@ static void release_sketches(tc_ctx *ctx)
     cudaFree(ctx->d_gt); cudaFree(ctx->d_goff); cudaFree(ctx->d_edges); cudaFree(ctx->d_comp);
     cudaFree(ctx->d_kh_pivots); cudaFree(ctx->d_kh_pivoff);
     cudaFree(ctx->d_bu_keys); cudaFree(ctx->d_bu_mask); cudaFree(ctx->d_bu_count); cudaFree(ctx->d_multi);
+    cudaFree(ctx->d_tile_flags); cudaFree(ctx->d_tile_rowcount);
+    ctx->d_tile_flags = nullptr; ctx->d_tile_rowcount = nullptr; ctx->cap_tile_flags = ctx->cap_tile_rowcount = 0; ctx->tile_words = 0;
     ctx->d_multi = nullptr; ctx->cap_multi = 0;
     ctx->d_bu_keys = nullptr; ctx->d_bu_mask = nullptr; ctx->d_bu_count = nullptr; ctx->cap_bu = 0; ctx->cap_bu_count = 0;
     ctx->d_kh_pivots = nullptr; ctx->d_kh_pivoff = nullptr; ctx->cap_pivoff = 0; ctx->cap_pivots = 0;
@@ -89,7 +98,7 @@ static void reset_sketches(tc_ctx *ctx)
 {
     ctx->kh_edge_units.clear(); ctx->kh_edge_units_n = 0; ctx->kh_units_on_device = false; ctx->kj_split_valid = false;
     ctx->n_edges = 0; ctx->n = 0; ctx->total = 0; ctx->ngroups = 0; ctx->edges_semb_size = 0;
-    ctx->edge_cap_for_n = 0; ctx->use_shadow = false; ctx->pairs_cache_valid = false;
+    ctx->edge_cap_for_n = 0; ctx->use_shadow = false; ctx->pairs_cache_valid = false; ctx->gt_valid = false;
     tc_rep_table_reset(ctx);
 }
 
@@ -108,13 +117,14 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     reset_sketches(ctx);
     release_sketches(ctx);
     tc_shadow_free(ctx);
     tc_rep_table_free(ctx);
     tc_k1_free(ctx);
     tc_k2_free(ctx);
+    tc_k4_free(ctx);
     cudaFree(ctx->d_edge_count);
     cudaFree(ctx->d_scratch);
     for (int b = 0; b < 2; b++) {
@@ -127,7 +137,7 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     cudaFree(ctx->d_kh_state); cudaFree(ctx->d_kh_units); cudaFree(ctx->d_kj_units);
     if (ctx->ev_pass0) cudaEventDestroy(ctx->ev_pass0);
     if (ctx->ev_pass1) cudaEventDestroy(ctx->ev_pass1);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -321,6 +331,36 @@ static int upload_sorted_runs(tc_ctx *ctx, const uint64_t *hashes, uint64_t tota
     return 0;
 }
 
+// gt[goff[g] + row*32 + lane] layout of the resident ranks for k3_tile.cu, built when a merge-kernel entry point needs it
+int tc_ensure_interleaved(tc_ctx *ctx)
+{
+    if (ctx->gt_valid) return 0;
+    const uint32_t n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    std::vector<uint64_t> goff(ctx->ngroups + 1, 0);
+    uint64_t max_rows = 0;
+    for (uint32_t g = 0; g < ctx->ngroups; g++) {
+        uint32_t rows = 0;
+        for (uint32_t l = 0; l < TC_GROUP && g * TC_GROUP + l < n; l++) rows = std::max(rows, ctx->h_size[g * TC_GROUP + l]);
+        goff[g + 1] = goff[g] + (uint64_t)rows * TC_GROUP;
+        max_rows = std::max<uint64_t>(max_rows, rows);
+    }
+    if (ensure_cap(&ctx->d_goff, &ctx->cap_groups, (uint64_t)ctx->ngroups + 1)) return 1;
+    TC_CUDA(cudaMemcpyAsync(ctx->d_goff, goff.data(), (size_t)(ctx->ngroups + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (ensure_cap(&ctx->d_gt, &ctx->cap_gt, std::max<uint64_t>(goff[ctx->ngroups], 1))) return 1;
+    if (max_rows > 0) {
+        dim3 grid(nblk(max_rows * TC_GROUP, 256), ctx->ngroups);
+        interleave_kernel<<<grid, 256, 0, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
+                                                reinterpret_cast<unsigned long long *>(ctx->d_goff), n, ctx->ngroups,
+                                                ctx->d_gt);
+        ctx->launches++;
+    }
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(st));          // `goff` (host) must outlive its copy
+    ctx->gt_valid = true;
+    return 0;
+}
+
 static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_device, const uint64_t *off, uint32_t n)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
@@ -418,29 +458,10 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
         pt.mark("flags + scan + scatter");
     }
 
-    // ---- group-interleaved layout
+    // ---- group-interleaved layout: only the first-generation merge kernel (semantic B, validation) reads it; built
+    //      on first use (tc_ensure_interleaved)
     ctx->ngroups = (n + TC_GROUP - 1) / TC_GROUP;
-    std::vector<uint64_t> goff(ctx->ngroups + 1, 0);
-    uint64_t max_rows = 0;
-    for (uint32_t g = 0; g < ctx->ngroups; g++) {
-        uint32_t rows = 0;
-        for (uint32_t l = 0; l < TC_GROUP && g * TC_GROUP + l < n; l++) rows = std::max(rows, ctx->h_size[g * TC_GROUP + l]);
-        goff[g + 1] = goff[g] + (uint64_t)rows * TC_GROUP;
-        max_rows = std::max<uint64_t>(max_rows, rows);
-    }
-    if (ensure_cap(&ctx->d_goff, &ctx->cap_groups, (uint64_t)ctx->ngroups + 1)) return 1;
-    TC_CUDA(cudaMemcpyAsync(ctx->d_goff, goff.data(), (size_t)(ctx->ngroups + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (ensure_cap(&ctx->d_gt, &ctx->cap_gt, std::max<uint64_t>(goff[ctx->ngroups], 1))) return 1;
-    if (max_rows > 0) {
-        dim3 grid(nblk(max_rows * TC_GROUP, 256), ctx->ngroups);
-        interleave_kernel<<<grid, 256, 0, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
-                                                reinterpret_cast<unsigned long long *>(ctx->d_goff), n, ctx->ngroups,
-                                                ctx->d_gt);
-        ctx->launches++;
-    }
-    TC_CUDA(cudaGetLastError());
-    TC_CUDA(cudaStreamSynchronize(st));
-    pt.mark("interleaved layout");
+    ctx->gt_valid = false;
     int rc = tc_kh_prepare(ctx);
     pt.mark("distinct counts + pivots");
     if (!rc) rc = tc_shadow_build(ctx);
@@ -462,6 +483,7 @@ extern "C" int tc_sketches_upload_rows(tc_ctx *ctx, const uint64_t *const *rows,
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(n > 0, "tc_sketches_upload_rows: n == 0");
+    reset_sketches(ctx);                 // d_hashes is overwritten below: a failure part-way must not leave the old set's n/ranks
     std::vector<uint64_t> off((size_t)n + 1, 0);
     for (uint32_t i = 0; i < n; i++) off[i + 1] = off[i] + sizes[i];
     const uint64_t total = off[n];
@@ -582,8 +604,10 @@ static int ensure_edges(tc_ctx *ctx, uint64_t need = 0)
     return 0;
 }
 
+// defer = true: the pass is only queued on the context's stream -- no count read-back, no overflow handling (the caller
+// reads the counters later, tc_k4_collect) -- so that what follows (the device Boruvka) can be queued right behind it.
 static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32_t part, uint32_t nparts,
-                              uint64_t *n_pairs, uint64_t *n_edges, uint32_t start_index = 0)
+                              uint64_t *n_pairs, uint64_t *n_edges, uint32_t start_index = 0, bool defer = false)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0, "tc_allpairs_pass: no sketches uploaded");
@@ -610,6 +634,7 @@ static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32
             : use_merge ? tc_launch_tiles_edges(ctx, radio, part, nparts, semb_size)
             : force_join ? tc_launch_join_edges(ctx, radio, part, nparts, start_index)
                          : tc_launch_blockjoin_edges(ctx, radio, part, nparts, start_index, force_block)) return 1;
+        if (defer) return 0;
         TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
         TC_CUDA(cudaStreamSynchronize(ctx->stream));
         if (cnt[1] == 0 && cnt[0] <= ctx->edge_cap) break;
@@ -861,82 +886,71 @@ extern "C" double tc_contain_distance(int common, int size0, int size1, int kmer
     return distance;
 }
 
-// ------------------------------------------------------------------- single-GPU MST driver
+// ------------------------------------------------------------------------------ MST driver
 namespace {
 struct HostUF {
     std::vector<int32_t> p;
     explicit HostUF(uint32_t n) : p(n) { std::iota(p.begin(), p.end(), 0); }
     int32_t find(int32_t x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; }
 };
+struct NoSyncPass {                                      // the launchers of the dense pass only queue while this lives
+    tc_ctx *c; bool was;
+    explicit NoSyncPass(tc_ctx *x) : c(x), was(x->pass_nosync) { x->pass_nosync = true; if (x->shadow) x->shadow->pass_nosync = true; }
+    ~NoSyncPass() { c->pass_nosync = was; if (c->shadow) c->shadow->pass_nosync = was; }
+};
 }  // namespace
 
 // mode = distance mode of the Boruvka keys; complete = add weight-1 edges between the components that share no
-// hash (the brute-force reference builds the MST of the complete graph)
+// hash (the brute-force reference builds the MST of the complete graph).
+// The dense pass (this GPU's part) and the whole Boruvka (k4_boruvka.cu; with a multi-GPU group the per-round
+// reduction over peer memory) are queued back to back; the host waits once, for the sorted forest.
 static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t semb_size, bool complete,
                     tc_edge *out, uint64_t *n_out, uint32_t start_index = 0, const tc_edge *pre_mst = nullptr,
                     uint64_t n_pre = 0)
 {
-    const int containment = mode;
-    struct SyncPhases {                                  // the rounds below read every phase's result right away
-        tc_ctx *c; bool was;
-        explicit SyncPhases(tc_ctx *x) : c(x), was(x->boruvka_async) { x->boruvka_async = false; }
-        ~SyncPhases() { c->boruvka_async = was; }
-    } sync_phases(ctx);
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0, "tc_mst: no sketches uploaded");
     const uint32_t n = ctx->n;
-    if (allpairs_pass_impl(ctx, radio, semb_size, 0, 1, nullptr, nullptr, start_index)) return 1;
-    uint64_t *d_key = nullptr, *d_edge = nullptr;
-    TC_CUDA(cudaMalloc(&d_key, (size_t)n * 8));
-    TC_CUDA(cudaMalloc(&d_edge, (size_t)n * 8));
-    std::vector<uint64_t> key(n), edge(n);
-    std::vector<int32_t> comp(n);
-    HostUF uf(n);
+    const uint32_t part = ctx->k4.nranks > 1 ? (uint32_t)ctx->k4.rank : 0u, nparts = ctx->k4.nranks > 1 ? (uint32_t)ctx->k4.nranks : 1u;
     std::vector<tc_edge> mst;
-    mst.reserve(n);
-    int rc = 0;
-    for (int round = 0; round < 64 && !rc; round++) {
-        for (uint32_t v = 0; v < n; v++) comp[v] = uf.find((int32_t)v);
-        if ((rc = tc_boruvka_upload_comp(ctx, comp.data(), n))) break;
-        if ((rc = tc_boruvka_phase1(ctx, containment, d_key))) break;
-        if ((rc = tc_boruvka_phase2(ctx, containment, d_key, d_edge))) break;
-        if (cudaMemcpy(key.data(), d_key, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-            cudaMemcpy(edge.data(), d_edge, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
-            tc_set_error("tc_mst: device-to-host copy failed");
-            rc = 1;
-            break;
+    std::vector<int32_t> comp;
+    for (int attempt = 0;; attempt++) {
+        uint64_t cnt = 0;
+        bool overflow = false;
+        {
+            NoSyncPass nosync(ctx);
+            if (allpairs_pass_impl(ctx, radio, semb_size, part, nparts, nullptr, nullptr, start_index, true)) return 1;
         }
-        uint64_t merged = 0;
-        for (uint32_t c = 0; c < n; c++) {
-            if (edge[c] == UINT64_MAX) continue;
-            const int32_t i = (int32_t)(edge[c] >> 32), j = (int32_t)(edge[c] & 0xffffffffu);
-            const int32_t a = uf.find(i), b = uf.find(j);
-            if (a == b) continue;
-            uf.p[a] = b;
-            mst.push_back(tc_edge{i, j, tc_dist_from_key(key[c], containment, kmer_size)});
-            merged++;
-        }
-        if (!merged) break;
-    }
-    cudaFree(d_key); cudaFree(d_edge);
-    if (rc) return rc;
-    if (complete) {
-        // pairs without a shared hash have distance exactly 1 (J = 0): chain the remaining components
-        int32_t first_root = -1, first_v = -1;
-        for (uint32_t v = 0; v < n; v++) {
-            const int32_t r = uf.find((int32_t)v);
-            if (first_root < 0) { first_root = r; first_v = (int32_t)v; continue; }
-            if (r == first_root) continue;
-            uf.p[r] = first_root;
-            mst.push_back(tc_edge{(int32_t)v, first_v, 1.0});
-        }
+        if (tc_k4_enqueue(ctx, mode, nullptr, nullptr, 0)) return 1;
+        if (tc_k4_collect(ctx, mode, kmer_size, mst, &cnt, &overflow, complete ? &comp : nullptr)) return 1;
+        ctx->n_edges = std::min<uint64_t>(cnt, ctx->edge_cap);
+        if (!overflow) break;
+        // the candidate edges did not fit: cnt is the exact need; grow the buffer to it and repeat once.  In a multi-GPU
+        // group the kernel has told every rank, so all of them repeat the (collective) call together.
+        TC_CHECK(attempt == 0, "tc_mst: %llu candidate edges exceed the device edge buffer (%llu)",
+                 (unsigned long long)cnt, (unsigned long long)ctx->edge_cap);
+        if (cnt > ctx->edge_cap && ensure_edges(ctx, cnt)) return 1;      // (in a group: only the ranks that overflowed grow)
     }
     auto by_weight = [](const tc_edge &x, const tc_edge &y) {
         if (x.dist != y.dist) return x.dist < y.dist;
         if (x.pre != y.pre) return x.pre < y.pre;
         return x.suf < y.suf;
     };
-    std::sort(mst.begin(), mst.end(), by_weight);
+    if (complete) {
+        // pairs without a shared hash have distance exactly 1 (J = 0): chain the remaining components
+        std::vector<char> seen(n, 0);
+        const int32_t first_root = comp[0];
+        seen[first_root] = 1;
+        bool added = false;
+        for (uint32_t v = 1; v < n; v++) {
+            const int32_t r = comp[v];
+            if (seen[r]) continue;
+            seen[r] = 1;
+            mst.push_back(tc_edge{(int32_t)v, 0, 1.0});
+            added = true;
+        }
+        if (added) std::sort(mst.begin(), mst.end(), by_weight);
+    }
     if (n_pre) {
         // append: MST(old graph + new edges) = MST(old MST + forest of the new edges)  (sub_command.cpp:1700-1706)
         std::vector<tc_edge> all(pre_mst, pre_mst + n_pre);
