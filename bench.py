@@ -46,6 +46,12 @@ def emit(line):
 PAIR_BYTES = 16000.0   # algorithmic operand bytes per pair: 8*(|A|+|B|) at s=1000
 
 
+def workload_name(n):
+    """config.workload, identical in both arms (the driver compares the strings)."""
+    return ("clust-mst --presketched: all-pairs sketch intersection + MST on %d pre-sketched s=1000 k=21 MinHash sketches, "
+            "%d families x 100 (BASELINE.json configs[2])" % (n, n // 100))
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -202,7 +208,23 @@ def ref_index_mst(n, threads, hashes, off, runs, workdir=None, k=21, s=1000, kee
                 return None
             res.append({"generate_mst_s": ph["generateMST"], "load_s": ph.get("load genome Infos and sketch Infos"),
                         "wall_s": wall})
-        return {"pairs": n * (n - 1) // 2, "threads": threads, "first_run": res[0], "runs": res[1:]}
+        result = None
+        if keep:
+            # the reference's results on this folder: the cluster file the binary has just written, and its MST --
+            # clust-mst --presketched never writes edge.mst, so the unmodified compute_minhash_mst is called once more
+            # through ref_harness (same objects, same index cache) to get the weights
+            try:
+                cl = sketch_io.parse_cluster_file(os.path.join(d, "out.txt"))
+                result = {"labels": labels_from_clusters(n, cl), "dist": None}
+                hx = pyoracle.ref_bin("ref_harness")
+                if hx is not None:
+                    ob = os.path.join(d, "ref_mst.bin")
+                    subprocess.run([hx, "msti", folder, str(threads), "0.05", ob], cwd=d, check=True,
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+                    result["dist"] = np.asarray(sketch_io.read_edge_mst(ob)["dist"], np.float64)
+            except Exception as ex:      # the timing stands; parity is then reported as missing
+                sys.stderr.write("bench: could not read the reference's result: %r\n" % (ex,))
+        return {"pairs": n * (n - 1) // 2, "threads": threads, "first_run": res[0], "runs": res[1:], "result": result}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
@@ -278,8 +300,7 @@ def run_reference(args):
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "config": {"workload": "clust-mst all-pairs on 100,000 pre-sketched s=1000 k=21 sketches "
-                                       "(BASELINE.json configs[2])", "note": note},
+                "config": {"workload": workload_name(args.n // 100 * 100), "note": note},
                 "cpu_baseline": cpu,
                 "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         # the sketch half of the metric on the same arm: MinHash::update of the reference on all host threads
@@ -323,60 +344,56 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ our arm
+def partition_labels(n, pre, suf, dist, thr):
+    """Connected components of the forest edges with dist <= thr (generateForest + BFS of the reference,
+    src/MST.cpp:77-142): label = smallest vertex id of the component."""
+    parent = np.arange(n, dtype=np.int64)
+    keep = dist <= thr
+    for a, b in zip(pre[keep].tolist(), suf[keep].tolist()):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]; a = parent[a]
+        while parent[b] != b:
+            parent[b] = parent[parent[b]]; b = parent[b]
+        if a != b:
+            parent[max(a, b)] = min(a, b)
+    while True:
+        q = parent[parent]
+        if np.array_equal(q, parent):
+            return parent
+        parent = q
+
+
+def labels_from_clusters(n, clusters):
+    lab = np.full(n, -1, np.int64)
+    for c in clusters:
+        ids = [m[0] if isinstance(m, tuple) else m for m in c]
+        lab[ids] = min(ids)
+    return lab
+
+
 def run_pairs(args):
     import torch
     import rabbittclust_b200 as T
     from rabbittclust_b200 import synth
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
     n = args.n
     per_fam = 100
     h, off = synth.family_sketches_fast(max(n // per_fam, 1), per_fam, 1000, seed=7)
     n = len(off) - 1
     if args.order == "shuffled":
-        # same sketches in a random order: no two neighbouring sketches are related, so a row block of 32 sketches
-        # holds 32,000 distinct hashes (3 table partitions) instead of ~9,000 (1 partition) -- see DESIGN.md K3H
         perm = np.random.default_rng(11).permutation(n)
         h = np.ascontiguousarray(h.reshape(n, 1000)[perm].reshape(-1))
     k, thr = 21, 0.05
-    radio = T.radio(thr, k)
     ctx = T.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     h_pin = torch.from_numpy(h).pin_memory()
     hp = h_pin.numpy()
-    best_key = torch.empty(n, dtype=torch.int64, device="cuda")
-    best_edge = torch.empty(n, dtype=torch.int64, device="cuda")
-    comp = np.arange(n, dtype=np.int32)
-    L = T.lib()
-    import ctypes as C
-
-    # The Boruvka phases of a step are queued back to back on the library's stream (tc_boruvka_set_async): phase 1,
-    # all-reduce(min) of the keys, phase 2, all-reduce(min) of the edges -- NCCL orders itself after the current stream,
-    # which is the library's here -- and the host waits once, at the end of the round.
-    T._chk(L.tc_boruvka_set_async(ctx._h, 1))
-
-    def boruvka_round1():
-        with torch.cuda.stream(stream):
-            T._chk(L.tc_boruvka_upload_comp(ctx._h, comp.ctypes.data_as(C.POINTER(C.c_int32)), n))
-            T._chk(L.tc_boruvka_phase1(ctx._h, 0, best_key.data_ptr()))
-            if dist is not None:
-                # keys are u64 bit patterns < 2^63 is NOT guaranteed: reduce as unsigned via the sign flip
-                best_key.bitwise_xor_(-2**63); dist.all_reduce(best_key, op=dist.ReduceOp.MIN); best_key.bitwise_xor_(-2**63)
-            T._chk(L.tc_boruvka_phase2(ctx._h, 0, best_key.data_ptr(), best_edge.data_ptr()))
-            if dist is not None:
-                best_edge.bitwise_xor_(-2**63); dist.all_reduce(best_edge, op=dist.ReduceOp.MIN); best_edge.bitwise_xor_(-2**63)
-        # a Boruvka round ends with the reduced edges on every rank (the host unions the components next):
-        # the phases and collectives are complete before the next pass starts, they are not left to overlap it
-        stream.synchronize()
-
-    def device_step():
-        npairs, nedges = ctx.allpairs_pass(radio, rank, world)
-        boruvka_round1()
-        return npairs, nedges
 
     def sync_all():
         torch.cuda.synchronize()
@@ -384,32 +401,45 @@ def run_pairs(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    ctx.upload(hashes=hp, off=off)
+    if dist is not None:
+        # multi-GPU group: every rank exports its exchange buffer, the handles travel over torch.distributed (plumbing),
+        # and from then on ctx.mst() is a collective whose reductions run inside the Boruvka kernel over NVLink
+        mine = torch.frombuffer(bytearray(ctx.mg_export(n)), dtype=torch.uint8).to(dev)
+        allh = torch.empty(world * T.MG_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine)
+        ctx.mg_join(rank, world, bytes(allh.cpu().numpy().tobytes()))
+        sync_all()
+
+    def upload():
+        if dist is None:
+            ctx.upload(hashes=hp, off=off)
+            return int(h.nbytes + off.nbytes)
+        # every rank copies only its 1/world share from the host; the shares are all-gathered over NVLink
+        from rabbittclust_b200 import mst_dist
+        return mst_dist.upload_sharded(ctx, h_pin, off, dist, dev) + int(off.nbytes)
+
+    # ---- value: the whole operation on resident sketches -- dense pass (this rank's units) + every Boruvka round +
+    #      the sorted MST on the host (tc_mst), CUDA events on the library's stream
+    upload()
     for _ in range(args.warmup):
-        device_step()
+        ctx.mst(k, thr)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    sync_all()        # after the sampler's start-up (NVML init, a few ms on rank 0): the other ranks must not wait for it inside their timed region
+    sync_all()        # after the sampler's start-up (NVML init on rank 0): no rank waits for it inside its timed region
     launches0 = ctx.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k3_ms, pairs_mine, nedges, k3_steps, kern_steps = 0.0, 0, 0, [], []
+    pass_steps, bor_steps, sort_steps, call_steps = [], [], [], []
     with torch.cuda.stream(stream):
         ev0.record()
     t_wall0 = time.time()
+    mst = None
     for _ in range(args.steps):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            a.record()
-        npairs, nedges = ctx.allpairs_pass(radio, rank, world)
-        with torch.cuda.stream(stream):
-            b.record()
-        b.synchronize()
-        k3_steps.append(a.elapsed_time(b))            # whole tc_allpairs_pass call (unit upload, kernel, count read-back)
-        kern_steps.append(ctx.last_pass_kernel_ms)    # events recorded by the library right around the kernel
-        k3_ms += kern_steps[-1]
-        pairs_mine += npairs
-        boruvka_round1()                                   # round complete on this rank when it returns
+        t_c = time.time()
+        mst = ctx.mst(k, thr)
+        call_steps.append((time.time() - t_c) * 1e3)
+        st = ctx.mst_stats()
+        pass_steps.append(st["pass_ms"]); bor_steps.append(st["boruvka_ms"]); sort_steps.append(st["sort_ms"])
     with torch.cuda.stream(stream):
         ev1.record()
     sync_all()
@@ -418,28 +448,30 @@ def run_pairs(args):
     wall_ms = (time.time() - t_wall0) * 1e3
     launches = ctx.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
+    stats = ctx.mst_stats()
 
-    # ---- e2e: host buffers -> upload (H2D + rank transform) -> pass -> edges D2H
+    # ---- e2e: host buffers -> upload (H2D + rank transform + union lists + tile flags) -> tc_mst -> MST edges on the host
     e2e_steps = max(1, min(args.steps, 3))
-    ctx.edges(pinned=True)               # the page-locked result buffer exists before the timed steps (it is reused)
     sync_all()
     t0 = time.time()
-    d2h = 0
-    h2d = int(h.nbytes + off.nbytes)
+    h2d = 0
     for _ in range(e2e_steps):
-        if dist is None:
-            ctx.upload(hashes=hp, off=off)
-        else:
-            # every rank copies only its 1/world share from the host; the shares are all-gathered over NVLink
-            from rabbittclust_b200 import mst_dist
-            h2d = mst_dist.upload_sharded(ctx, h_pin, off, dist, torch.device("cuda", local_rank)) + int(off.nbytes)
-        ctx.allpairs_pass(radio, rank, world)
-        e = ctx.edges(pinned=True)
-        d2h = e.nbytes
+        h2d = upload()
+        mst = ctx.mst(k, thr)
     sync_all()
     e2e_ms = (time.time() - t0) * 1e3 / e2e_steps
+    d2h = int(mst.nbytes)
 
-    # ---- semantic B (MinHash::distance, the computation the CPU arm times): one pass of the step-budget merge kernel
+    # ---- N > 1: the collective result must be the single-GPU result, edge for edge
+    same_as_single = None
+    if dist is not None and rank == 0:
+        with T.Context(local_rank) as c1:
+            c1.upload(hashes=hp, off=off)
+            m1 = c1.mst(k, thr)
+        same_as_single = bool(len(m1) == len(mst) and np.array_equal(m1["pre"], mst["pre"]) and
+                              np.array_equal(m1["suf"], mst["suf"]) and np.array_equal(m1["dist"], mst["dist"]))
+
+    # ---- semantic B (MinHash::distance, the computation the brute-force CPU leg times): one pass of the merge kernel
     semb_ms, semb_pairs = None, 0
     if not args.no_semb:
         sync_all()
@@ -453,71 +485,132 @@ def run_pairs(args):
         semb_ms = a.elapsed_time(b)
         sync_all()
 
-    t = torch.tensor([dev_ms, e2e_ms, k3_ms, float(pairs_mine), float(launches)], dtype=torch.float64, device="cuda")
+    # ---- robustness (1 GPU): the same sketches in random order, a set in which every pair is related, and the default
+    #      set with the tile flags switched off (what the pass cost before them)
+    robust = None
+    if world == 1 and not args.no_robust:
+        robust = {}
+
+        def leg(hh, oo, env=None):
+            for kk, vv in (env or {}).items():
+                os.environ[kk] = vv
+            try:
+                with T.Context(local_rank) as c2:
+                    t_u = time.time()
+                    c2.upload(hashes=hh, off=oo)
+                    up_ms = (time.time() - t_u) * 1e3
+                    c2.mst(k, thr)
+                    t_m = time.time()
+                    m2 = c2.mst(k, thr)
+                    mst_ms = (time.time() - t_m) * 1e3
+                    s2 = c2.mst_stats()
+            finally:
+                for kk in (env or {}):
+                    os.environ.pop(kk, None)
+            nn = len(oo) - 1
+            return {"n": nn, "pairs": nn * (nn - 1) // 2, "upload_ms": round(up_ms, 3), "mst_ms": round(mst_ms, 3),
+                    "pass_kernel_ms": round(s2["pass_ms"], 3), "boruvka_kernel_ms": round(s2["boruvka_ms"], 3),
+                    "rounds": s2["rounds"], "candidate_edges": s2["edges"], "tiles_visited": s2["tiles_flagged"],
+                    "tiles_total": s2["tiles_total"], "on_reordered_copy": s2["on_reordered_copy"],
+                    "mst_edges": int(len(m2))}, m2
+        other = "shuffled" if args.order == "family" else "family"
+        if other == "shuffled":
+            perm = np.random.default_rng(11).permutation(n)
+            h2 = np.ascontiguousarray(h.reshape(n, 1000)[perm].reshape(-1))
+            robust["shuffled_order"], m_sh = leg(h2, off)
+            # same sketches, other ids: the weights must be the same multiset
+            robust["shuffled_order"]["weights_equal_family_order"] = bool(np.array_equal(np.sort(m_sh["dist"]), np.sort(mst["dist"])))
+            del h2
+        hd, od = synth.family_sketches_fast(1, args.dense_n, 1000, seed=5)
+        robust["one_species"], _ = leg(hd, od)
+        robust["one_species"]["what"] = ("one family of %d sketches: every pair shares hashes, every tile is visited and is dense "
+                                         "(worst case for the tile flags)" % args.dense_n)
+        robust["every_tile_visited"], m_off = leg(hp, off, {"TCLUST_TILE_FLAGS": "0"})
+        robust["every_tile_visited"]["what"] = "the default set with the tile flags switched off (TCLUST_TILE_FLAGS=0): all 4.9e6 tiles streamed"
+        robust["every_tile_visited"]["same_mst"] = bool(np.array_equal(m_off, mst))
+
+    t = torch.tensor([dev_ms, e2e_ms, float(launches), float(np.mean(pass_steps)), float(np.mean(bor_steps))],
+                     dtype=torch.float64, device="cuda")
     if dist is not None:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dev_ms, e2e_ms = float(tmax[0]), float(tmax[1])
-        total_pairs, launches = float(tsum[3]), int(tsum[4])
-        gl = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
-        dist.all_gather(gl, torch.tensor([k3_ms / args.steps], dtype=torch.float64, device="cuda"))
-        per_rank_ms = [float(x[0]) for x in gl]
+        launches = int(tsum[2])
+        gl = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(gl, t[3:5].clone())
+        per_rank_pass = [float(x[0]) for x in gl]
+        per_rank_bor = [float(x[1]) for x in gl]
     else:
-        total_pairs = float(pairs_mine)
-        per_rank_ms = [k3_ms / args.steps]
+        per_rank_pass, per_rank_bor = [float(np.mean(pass_steps))], [float(np.mean(bor_steps))]
+    line = None
     if rank == 0:
         peak, how = measured_peak()
-        pairs_per_step_all = n * (n - 1) / 2
-        value = total_pairs / (dev_ms / 1e3)
-        k3_avg_s = k3_ms / 1e3 / args.steps
-        achieved = (pairs_mine / args.steps) * PAIR_BYTES / k3_avg_s / 1e9
-        traffic, binding = None, None
-        impl_env = os.environ.get("TCLUST_PASS_IMPL")
-        kernel = ("k3_tile_kernel" if impl_env == "merge" else "k3h_join_kernel" if impl_env == "join"
-                  else "k3j_block_kernel (units where the block join does not pay run on k3h_join_kernel)")
+        pairs_per_step = n * (n - 1) / 2
+        value = pairs_per_step * args.steps / (dev_ms / 1e3)
+        pass_s = max(per_rank_pass) / 1e3
+        achieved = (pairs_per_step / world) * PAIR_BYTES / pass_s / 1e9
+        prof, traffic, binding = None, None, None
         tp = os.path.join(ROOT, "profiles", "k3_traffic.json")
+        impl_env = os.environ.get("TCLUST_PASS_IMPL")
         if os.path.exists(tp) and impl_env is None and args.order == "family" and n == 100000 and world == 1:
             try:
                 prof = json.load(open(tp))
                 traffic = prof.get("dram_bytes_per_launch")
-                binding = {k: prof[k] for k in ("issue_active_pct", "alu_pipe_pct", "lsu_pipe_pct",
-                                                "shared_wavefronts_pct", "l2_hit_pct") if k in prof}
-                binding["source"] = "ncu capture of this command, profiles/k3_traffic.json"
+                binding = {kk: prof[kk] for kk in ("issue_active_pct", "alu_pipe_pct", "lsu_pipe_pct",
+                                                   "shared_wavefronts_pct", "l2_hit_pct", "kernel_ms_under_ncu") if kk in prof}
+                binding["source"] = "committed ncu capture of this command (profiles/k3_traffic.json), not measured in this run"
             except Exception:
-                traffic = None
+                prof = None
+        kernel = ("k3_tile_kernel" if impl_env == "merge" else "k3h_join_kernel" if impl_env == "join"
+                  else "k3j_block_kernel (flagged tiles only; units where the block join does not pay run on k3h_join_kernel)")
         line = {
             "metric": "pairwise sketch distances/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 ranks of u64 hashes",
             "data": "synthetic",
-            "config": {"workload": "clust-mst dense all-pairs pass on %d pre-sketched s=1000 k=21 sketches, "
-                                   "1000-per-family model (BASELINE.json configs[2])" % n,
-                       "n_sketches": n, "sketch_size": 1000, "pairs_per_step": pairs_per_step_all,
+            "config": {"workload": workload_name(n),
+                       "step": "tc_mst on resident sketches: dense all-pairs pass (candidate edges) + all Boruvka rounds on "
+                               "the device + sorted MST edges read back to the host",
+                       "n_sketches": n, "sketch_size": 1000, "pairs_per_step": pairs_per_step,
                        "order": args.order + (" (generation order: the 100 members of a family are adjacent)"
                                               if args.order == "family" else " (random permutation of the same sketches)"),
-                       "candidate_edges": int(nedges), "parallelism": "tile-sharded x%d, sketches replicated" % world,
+                       "candidate_edges_rank0": stats["edges"], "boruvka_rounds": stats["rounds"],
+                       "tiles_visited": stats["tiles_flagged"], "tiles_total": stats["tiles_total"],
+                       "mst_edges": int(len(mst)),
+                       "parallelism": "work units of the pass dealt round-robin x%d, sketches replicated, Boruvka "
+                                      "min-reduction fused into the kernel over NVLink peer memory" % world,
                        "l2": "input 0.4 GB of u32 ranks (+0.8 GB u64) per GPU > 126 MB L2"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": how,
-                         "kernel": kernel, "kernel_ms": 1e3 * k3_avg_s, "kernel_ms_per_rank": per_rank_ms,
-                         "kernel_ms_steps": [round(x, 3) for x in kern_steps],
-                         "pass_call_ms_steps": [round(x, 3) for x in k3_steps],
+                         "kernel": kernel, "kernel_ms": 1e3 * pass_s, "kernel_ms_per_rank": per_rank_pass,
+                         "kernel_ms_steps": [round(x, 3) for x in pass_steps],
+                         "boruvka_kernel_ms_per_rank": per_rank_bor,
+                         "boruvka_kernel_ms_steps": [round(x, 3) for x in bor_steps],
+                         "forest_sort_ms_steps": [round(x, 3) for x in sort_steps],
+                         "tc_mst_call_ms_steps": [round(x, 3) for x in call_steps],
+                         "issue_frac": (prof or {}).get("issue_active_pct", None) and prof["issue_active_pct"] / 100.0,
+                         "dram_frac": (traffic / pass_s / 1e9 / peak) if traffic else None,
                          "binding_units": binding,
-                         "note": "algorithmic bytes = SURVEY 8(d)'s operand bytes 8*(|A|+|B|) = 16000 B/pair x pairs per "
-                                 "launch.  Every distinct rank of a 32-sketch column block is probed once per 32 row "
-                                 "sketches (shared-memory hash join over per-block union lists), so the operand bytes "
-                                 "are served from shared memory/L2, not HBM: frac > 1 is expected, `traffic` is the "
-                                 "measured DRAM bytes, and the binding units are the issue slots / ALU pipe / "
-                                 "shared-memory pipe (DESIGN.md K3J)"},
-            "e2e": {"value": (pairs_per_step_all) / (e2e_ms / 1e3), "unit": "pairs/s",
+                         "note": "`achieved`/`frac` follow SURVEY 8(d): operand bytes 8*(|A|+|B|) = 16000 B/pair x the pairs "
+                                 "this launch covers / kernel time.  It is NOT a utilisation: the kernel only visits the tiles "
+                                 "whose sketch blocks share a rank (config.tiles_visited of config.tiles_total) and serves "
+                                 "those from shared memory/L2, so it moves a tiny fraction of the operand bytes.  What it "
+                                 "really uses of the chip: dram_frac = measured DRAM bytes (ncu) / kernel time / HBM peak, "
+                                 "issue_frac = issue slots busy (ncu), both from the committed capture"},
+            "e2e": {"value": pairs_per_step / (e2e_ms / 1e3), "unit": "pairs/s",
                     "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
-                    "ms_per_step": e2e_ms},
+                    "ms_per_step": e2e_ms,
+                    "what": "host hashes -> tc_sketches_upload -> tc_mst -> sorted MST edges on the host (all Boruvka rounds)"},
             "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
         }
+        if same_as_single is not None:
+            line["mst_equals_single_gpu"] = same_as_single
+        if robust is not None:
+            line["robustness"] = robust
         if semb_ms is not None:
             line["semantic_b"] = {"what": "the same pass with Mash union-limited counts (MinHash::jaccard stop rule, "
                                           "sketchSize 1000) on the step-budget merge kernel k3_tile_kernel<EDGES,SEMB>; "
-                                          "this is the computation the cpu_baseline runs; rank 0's share",
+                                          "this is the computation cpu_baseline.minhash_distance runs; rank 0's share",
                                   "value": semb_pairs / (semb_ms / 1e3), "unit": "pairs/s", "ms": semb_ms,
                                   "pairs": int(semb_pairs)}
         if world == 1 and not args.no_cpu:
@@ -530,19 +623,37 @@ def run_pairs(args):
                      "kind": kind, "sample": "all pairs of the first %d sketches (%d pairs), "
                      "MinHash::distance AVX2 build" % (min(args.ref_sample, n), r["pairs"])}
             idx = None
-            if args.order == "family" and not args.ref_bruteforce_only:
-                idx = ref_index_mst(n, threads, h, off, 1)
+            if not args.ref_bruteforce_only:
+                idx = ref_index_mst(n, threads, h, off, 1, keep=True)
             if idx is not None:
                 line["cpu_baseline"] = {
                     "value": idx["pairs"] / idx["runs"][0]["generate_mst_s"], "unit": "pairs/s", "cores": idx["threads"],
                     "kind": "reference",
                     "sample": "the full workload once: unmodified clust-mst --presketched on the same %d sketches, "
-                              "generateMST phase (inverted-index compute_minhash_mst), index cached by a first run" % n,
+                              "generateMST phase (inverted-index compute_minhash_mst + Kruskal), index cached by a first run" % n,
                     "generate_mst_s": idx["runs"][0]["generate_mst_s"], "wall_s": idx["runs"][0]["wall_s"],
                     "first_run_generate_mst_s": idx["first_run"]["generate_mst_s"],
                     "minhash_distance": brute}
+                # parity at full size: the reference's own edge.mst and cluster file against this run's MST
+                ref = idx.get("result")
+                if ref is not None:
+                    ours_w = np.sort(mst["dist"])
+                    lab = partition_labels(n, mst["pre"], mst["suf"], mst["dist"], thr)
+                    rd = ref["dist"]
+                    line["parity"] = {
+                        "vs": "the unmodified reference on the same %d sketches in this run: cluster file of clust-mst "
+                              "--presketched; MST weights of its compute_minhash_mst (called through oracle/_ref/ref_harness "
+                              "msti, the binary itself does not write edge.mst in this mode)" % n,
+                        "mst_edges": [int(len(mst)), None if rd is None else int(len(rd))],
+                        "sorted_weights_bit_identical": None if rd is None else bool(
+                            len(ours_w) == len(rd) and np.array_equal(ours_w.view(np.uint64), np.sort(rd).view(np.uint64))),
+                        "partition_identical": bool(np.array_equal(lab, ref["labels"])),
+                        "clusters": [int(len(np.unique(lab))), int(len(np.unique(ref["labels"])))]}
+                    line["parity"]["ok"] = bool(line["parity"]["sorted_weights_bit_identical"] and line["parity"]["partition_identical"])
             else:
                 line["cpu_baseline"] = brute
+    if dist is not None:
+        ctx.mg_leave()
     ctx.close()
     # ---- second half of BASELINE.json's metric: genomes sketched/sec (configs[1] shape), same JSON line
     if not args.no_sketch:
@@ -574,6 +685,8 @@ def main():
                     help="CPU legs: only MinHash::distance over the sample, not the reference binary on the full workload")
     ap.add_argument("--no-sketch", action="store_true", help="pairs workload: skip the sketch leg of the line")
     ap.add_argument("--no-semb", action="store_true", help="pairs workload: skip the semantic-B pass")
+    ap.add_argument("--no-robust", action="store_true", help="pairs workload: skip the robustness legs")
+    ap.add_argument("--dense-n", type=int, default=16384, help="robustness: sketches of the one-species set")
     ap.add_argument("--order", default="family", choices=["family", "shuffled"],
                     help="pairs workload: sketch order (family = as generated, SURVEY 8d config 3; shuffled = random)")
     args = ap.parse_args()

@@ -190,6 +190,16 @@ int tc_boruvka_set_async(tc_ctx *ctx, int on);
 int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double threshold,
            tc_edge *out, uint64_t *n_out);
 
+/* the Boruvka half of tc_mst alone: MST of the candidate edges the last tc_allpairs_pass / _from / _b left on the device
+ * (the reference's final Kruskal, src/MST.cpp:1715-1723; `containment` = TC_DIST_* mode matching that pass).  For callers
+ * that use the edges in between (tc_dense_ani).  In a multi-GPU group: collective, every rank brings the edges of its part. */
+int tc_mst_of_edges(tc_ctx *ctx, int kmer_size, int containment, tc_edge *out, uint64_t *n_out);
+
+/* timings and counts of the last tc_mst / tc_mst_append on the context (bench accounting): out[0] dense-pass kernel ms,
+ * [1] Boruvka kernel ms, [2] forest sort ms (CUDA events on tc_stream), [3] candidate edges of this rank, [4] Boruvka
+ * rounds, [5] tiles the pass visits (-1: tile flags off), [6] tiles in the lower triangle, [7] 1 = pass on the reordered copy */
+int tc_mst_stats(const tc_ctx *ctx, double *out /* 8 doubles */);
+
 /*
  * Multi-GPU group ("N x N tile space sharded over the GPUs of one box, min-reduction per Boruvka round").
  * One context per GPU -- in one process (one host thread per context) or in one process per GPU (torchrun).  Every

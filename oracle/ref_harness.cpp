@@ -21,6 +21,13 @@
  *   ref_harness mstb <hash.sketch> <nmax> <threads> [contain]
  *                                                   the reference's brute-force MST modifyMST
  *                                                   (src/MST.cpp:809-1018); binary: u64 n, {i32,i32,f64}[n]
+ *   ref_harness msti <folder> <threads> <threshold> <out.bin>
+ *                                                   the reference's default MST path on a --presketched folder:
+ *                                                   loadSketches + MinHashInvertedIndex (loaded from the folder's cache or
+ *                                                   built) + compute_minhash_mst (src/MST.cpp:1290-1737, incl. its final
+ *                                                   Kruskal); out.bin: u64 n, {i32,i32,f64}[n].  clust-mst --presketched
+ *                                                   itself never writes edge.mst, so this is how the full-size MST weights
+ *                                                   of the unmodified reference are obtained (bench.py parity)
  *   ref_harness greedyb <hash.sketch> <nmax> <threads> <threshold> [contain]
  *                                                   the reference's brute-force greedyCluster
  *                                                   (src/greedy.cpp:285-351); text: one cluster per line
@@ -28,6 +35,8 @@
 #include "Sketch.h"
 #include "MST.h"
 #include "greedy.h"
+#include "Sketch_IO.h"
+#include "SketchInfo.h"
 #include <zlib.h>
 #include "kseq.h"
 #include <omp.h>
@@ -192,6 +201,41 @@ static int cmd_mstb(int argc, char **argv)
     return 0;
 }
 
+static int cmd_msti(int argc, char **argv)
+{
+    const std::string folder = argv[2];
+    const int threads = atoi(argv[3]);
+    const double thr = atof(argv[4]);
+    std::vector<SketchInfo> v;
+    int func_id = 0;
+    const double t0 = now_s();
+    loadSketches(folder, threads, v, func_id);
+    if (func_id != 0 || v.empty() || v[0].minHash == nullptr) { fprintf(stderr, "msti: not a MinHash folder\n"); return 1; }
+    int fid, k = 21, cc, ss, hk, hs, dr;
+    bool contain = false;
+    read_sketch_parameters(folder, fid, k, contain, cc, ss, hk, hs, dr);
+    MinHashInvertedIndex idx;
+    if (!idx.load_from_file(folder)) {
+        for (size_t i = 0; i < v.size(); i++) {
+            v[i].id = (int)i;
+            std::vector<uint64_t> h = v[i].minHash->storeMinHashes();
+            for (uint64_t x : h) idx.hash_map[x].push_back((uint32_t)i);
+        }
+    }
+    const double t1 = now_s();
+    int **dense = nullptr; uint64_t *ani = nullptr;
+    std::vector<EdgeInfo> mst = compute_minhash_mst(v, 0, true, contain, threads, dense, 0, ani, thr, k, &idx);
+    const double t2 = now_s();
+    FILE *fo = fopen(argv[5], "wb");
+    if (!fo) { fprintf(stderr, "msti: cannot write %s\n", argv[5]); return 1; }
+    uint64_t n = mst.size();
+    fwrite(&n, 8, 1, fo);
+    for (const EdgeInfo &e : mst) { fwrite(&e.preNode, 4, 1, fo); fwrite(&e.sufNode, 4, 1, fo); fwrite(&e.dist, 8, 1, fo); }
+    fclose(fo);
+    printf("{\"edges\": %llu, \"load_s\": %.3f, \"mst_s\": %.3f, \"threads\": %d}\n", (unsigned long long)n, t1 - t0, t2 - t1, threads);
+    return 0;
+}
+
 static int cmd_greedyb(int argc, char **argv)
 {
     Folder f;
@@ -213,6 +257,7 @@ int main(int argc, char **argv)
 {
     if (argc >= 4 && !strcmp(argv[1], "pairsdump")) return cmd_pairsdump(argc, argv);
     if (argc >= 5 && !strcmp(argv[1], "mstb")) return cmd_mstb(argc, argv);
+    if (argc >= 6 && !strcmp(argv[1], "msti")) return cmd_msti(argc, argv);
     if (argc >= 6 && !strcmp(argv[1], "greedyb")) return cmd_greedyb(argc, argv);
     if (argc >= 5 && !strcmp(argv[1], "sketch")) return cmd_sketch(argc, argv);
     if (argc >= 5 && !strcmp(argv[1], "pairs")) return cmd_pairs(argc, argv);

@@ -26,7 +26,7 @@ SYMBOLS = [
     "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce", "tc_greedy_cluster_kssd", "tc_dense_ani", "tc_allpairs_pass_from", "tc_mst_append",
     "tc_jaccard_b", "tc_distance_b", "tc_contain_distance",
     "tc_mash_dist", "tc_aaf_dist", "tc_dist_from_key", "tc_radio", "tc_greedy_common_min", "tc_greedy_dist",
-    "tc_mg_export", "tc_mg_join", "tc_mg_leave", "tc_mg_rank", "tc_mst_stats",
+    "tc_mg_export", "tc_mg_join", "tc_mg_leave", "tc_mg_rank", "tc_mst_stats", "tc_mst_of_edges",
 ]
 MG_HANDLE_BYTES = 128
 
@@ -112,6 +112,7 @@ def lib():
     L.tc_mg_leave.argtypes = [vp]
     L.tc_mg_rank.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.tc_mst_stats.argtypes = [vp, C.POINTER(C.c_double)]
+    L.tc_mst_of_edges.argtypes = [vp, C.c_int, C.c_int, vp, u64p]
     L.tc_radio.argtypes = [C.c_double, C.c_int]
     L.tc_radio.restype = C.c_int
     _lib = L
@@ -325,10 +326,10 @@ class Context:
         return out
 
     def mst(self, k, threshold, containment=False):
-        out = np.zeros(max(self.n, 1), EDGE_DTYPE)
+        out = np.empty(max(self.n, 1), EDGE_DTYPE)
         m = C.c_uint64(0)
         _chk(lib().tc_mst(self._h, k, int(containment), threshold, out.ctypes.data, C.byref(m)))
-        return out[:int(m.value)].copy()
+        return out[:int(m.value)]
 
     # ---- multi-GPU group (tc_mg_*): after join(), mst()/mst_append() are collective over the ranks
     def mg_export(self, n_max):
@@ -345,6 +346,13 @@ class Context:
 
     def mg_leave(self):
         _chk(lib().tc_mg_leave(self._h))
+
+    def mst_of_edges(self, k, mode=0):
+        """Boruvka over the candidate edges of the last allpairs_pass (collective in a group)."""
+        out = np.zeros(max(self.n, 1), EDGE_DTYPE)
+        m = C.c_uint64(0)
+        _chk(lib().tc_mst_of_edges(self._h, k, int(mode), out.ctypes.data, C.byref(m)))
+        return out[:int(m.value)].copy()
 
     def mst_stats(self):
         """Timings of the last mst() on this context (CUDA events on its stream), candidate edges, Boruvka rounds."""

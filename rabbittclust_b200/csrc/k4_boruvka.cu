@@ -25,6 +25,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <unistd.h>
 
@@ -261,6 +262,7 @@ void tc_k4_free(tc_ctx *ctx)
         if (k.peer_opened[g]) { cudaIpcCloseMemHandle(k.peer_xbuf[g]); k.peer_opened[g] = false; }
     cudaFree(k.d_xbuf); cudaFree(k.d_red); cudaFree(k.d_parent); cudaFree(k.d_out); cudaFree(k.d_ctl); cudaFree(k.d_sort_tmp);
     if (k.h_out) cudaFreeHost(k.h_out);
+    for (int e = 0; e < 3; e++) if (k.ev[e]) cudaEventDestroy(k.ev[e]);
     k = tc_k4_state();
 }
 
@@ -304,7 +306,9 @@ int tc_k4_enqueue(tc_ctx *ctx, int mode, const unsigned long long *d_fin_key, co
         int occ = 0;
         TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k4_boruvka_kernel, K4_THREADS, 0));
         TC_CHECK(occ >= 1, "tc_k4_enqueue: the Boruvka kernel does not fit an SM");
-        k.grid = ctx->num_sms * std::min(occ, 2);
+        int per_sm = std::min(occ, 2);
+        if (const char *e = getenv("TCLUST_K4_CTAS_PER_SM")) per_sm = std::max(1, std::min(occ, atoi(e)));   // 1: two group members can share one GPU (tests)
+        k.grid = ctx->num_sms * per_sm;
     }
     size_t tmp_bytes = 0;
     TC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
@@ -332,14 +336,22 @@ int tc_k4_enqueue(tc_ctx *ctx, int mode, const unsigned long long *d_fin_key, co
         a.sys_base = k.sys_base;
         k.sys_base += 1ull << 20;
     }
+    for (int e = 0; e < 3; e++) if (!k.ev[e]) TC_CUDA(cudaEventCreate(&k.ev[e]));
+    TC_CUDA(cudaEventRecord(k.ev[0], st));
     void *params[] = {(void *)&a};
     TC_CUDA(cudaLaunchCooperativeKernel((const void *)k4_boruvka_kernel, dim3(k.grid), dim3(K4_THREADS), params, 0, st));
+    TC_CUDA(cudaEventRecord(k.ev[1], st));
     ctx->launches++;
     // forest sorted by (key, i, j): stable sort by id, then by key; the unused tail (all ones) stays at the end
+    // (ids are (i << 32 | j) with i, j < n; the all-ones padding also sorts last on the low id_bits bits alone only if those
+    //  bits are all ones there too, which they are)
+    int id_bits = 33;
+    while (id_bits < 64 && ((unsigned long long)n >> (id_bits - 32))) id_bits++;
     size_t tb = tmp_bytes;
-    TC_CUDA(cub::DeviceRadixSort::SortPairs(k.d_sort_tmp, tb, (const unsigned long long *)o_id, t_id, (const unsigned long long *)o_key, t_key, (int)n, 0, 64, st));
+    TC_CUDA(cub::DeviceRadixSort::SortPairs(k.d_sort_tmp, tb, (const unsigned long long *)o_id, t_id, (const unsigned long long *)o_key, t_key, (int)n, 0, id_bits, st));
     tb = tmp_bytes;
     TC_CUDA(cub::DeviceRadixSort::SortPairs(k.d_sort_tmp, tb, (const unsigned long long *)t_key, o_key, (const unsigned long long *)t_id, o_id, (int)n, 0, 64, st));
+    TC_CUDA(cudaEventRecord(k.ev[2], st));
     ctx->launches += 2;
     return 0;
 }
@@ -347,6 +359,7 @@ int tc_k4_enqueue(tc_ctx *ctx, int mode, const unsigned long long *d_fin_key, co
 // Wait for the queued work and turn the forest into the reference's edges: {i, j<i, dist} sorted by (dist, i, j), dist by
 // tc_dist_from_key (glibc log, the reference's expression order).  *n_edges_dev / *overflow: the candidate-edge counters
 // of the pass that fed it.  comp_out (may be NULL): final component label of every vertex.
+// One wait: control words, counters and the (at most n-1, padded to n) sorted forest entries come back together.
 int tc_k4_collect(tc_ctx *ctx, int mode, int kmer_size, std::vector<tc_edge> &mst, uint64_t *n_edges_dev, bool *overflow,
                   std::vector<int32_t> *comp_out)
 {
@@ -356,45 +369,68 @@ int tc_k4_collect(tc_ctx *ctx, int mode, int kmer_size, std::vector<tc_edge> &ms
     uint8_t *h = static_cast<uint8_t *>(k.h_out);
     uint32_t *h_ctl = reinterpret_cast<uint32_t *>(h);
     unsigned long long *h_cnt = reinterpret_cast<unsigned long long *>(h + 64 - 16);
+    unsigned long long *h_key = reinterpret_cast<unsigned long long *>(h + 64), *h_id = h_key + n;
     TC_CUDA(cudaMemcpyAsync(h_ctl, k.d_ctl, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     TC_CUDA(cudaMemcpyAsync(h_cnt, ctx->d_edge_count, 16, cudaMemcpyDeviceToHost, st));
-    TC_CUDA(cudaStreamSynchronize(st));
-    TC_CHECK(h_ctl[4] == 0, "tc_mst: the Boruvka kernel gave up at a %s barrier (a peer GPU did not arrive)", h_ctl[4] == 2 ? "multi-GPU" : "grid");
-    const uint32_t nf = std::min(h_ctl[0], n);
-    if (n_edges_dev) *n_edges_dev = h_cnt[0];
-    if (overflow) *overflow = h_cnt[1] != 0 || h_cnt[0] > ctx->edge_cap || h_ctl[6] != 0;   // this rank's or (group) any rank's
-    ctx->k4.last_rounds = h_ctl[5];
-    unsigned long long *h_key = reinterpret_cast<unsigned long long *>(h + 64), *h_id = h_key + n;
-    if (nf) {
-        TC_CUDA(cudaMemcpyAsync(h_key, k.d_out, (size_t)nf * 8, cudaMemcpyDeviceToHost, st));
-        TC_CUDA(cudaMemcpyAsync(h_id, k.d_out + n, (size_t)nf * 8, cudaMemcpyDeviceToHost, st));
-    }
+    TC_CUDA(cudaMemcpyAsync(h_key, k.d_out, (size_t)2 * n * 8, cudaMemcpyDeviceToHost, st));     // keys and ids are adjacent
     if (comp_out) {
         comp_out->resize(n);
         TC_CUDA(cudaMemcpyAsync(comp_out->data(), ctx->d_comp, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     }
     TC_CUDA(cudaStreamSynchronize(st));
+    TC_CHECK(h_ctl[4] == 0, "tc_mst: the Boruvka kernel gave up at a barrier (%s)", h_ctl[4] == 2 ? "a peer GPU of the group did not arrive" : "grid barrier");
+    const uint32_t nf = std::min(h_ctl[0], n);
+    if (n_edges_dev) *n_edges_dev = h_cnt[0];
+    if (overflow) *overflow = h_cnt[1] != 0 || h_cnt[0] > ctx->edge_cap || h_ctl[6] != 0;   // this rank's or (group) any rank's
+    ctx->k4.last_rounds = h_ctl[5];
     mst.resize(nf);
-    double d = 0.0;
-    for (uint32_t e = 0; e < nf; e++) {
-        if (e == 0 || h_key[e] != h_key[e - 1]) d = tc_dist_from_key(h_key[e], mode, kmer_size);
-        mst[e] = tc_edge{(int32_t)(h_id[e] >> 32), (int32_t)(h_id[e] & 0xFFFFFFFFull), d};
-    }
-    // key order is distance order, except where two different quotients round to the same distance: such a run is
-    // put into (i, j) order (never seen on real keys; cheap to keep exact)
     auto by_weight = [](const tc_edge &x, const tc_edge &y) {
         if (x.dist != y.dist) return x.dist < y.dist;
         if (x.pre != y.pre) return x.pre < y.pre;
         return x.suf < y.suf;
     };
-    for (uint32_t e = 0; e < nf;) {
-        uint32_t f = e + 1;
-        bool mixed = false;
-        while (f < nf && mst[f].dist == mst[e].dist) { mixed |= h_key[f] != h_key[e]; f++; }
-        if (mixed) std::sort(mst.begin() + e, mst.begin() + f, by_weight);
-        e = f;
+    // key order is distance order, except where two different quotients round to the same distance: such a run is put
+    // into (i, j) order (never seen on real keys; cheap to keep exact).  One distance per distinct key.
+    double d = 0.0, prev_d = -1.0;
+    uint32_t run0 = 0;                 // first edge of the current run of equal distances
+    bool mixed = false, monotone = true;
+    for (uint32_t e = 0; e < nf; e++) {
+        if (e == 0 || h_key[e] != h_key[e - 1]) {
+            d = tc_dist_from_key(h_key[e], mode, kmer_size);
+            if (e > 0 && d == prev_d) mixed = true;
+            else {
+                if (mixed) std::sort(mst.begin() + run0, mst.begin() + e, by_weight);
+                if (e > 0 && d < prev_d) monotone = false;
+                run0 = e; mixed = false;
+            }
+            prev_d = d;
+        }
+        mst[e] = tc_edge{(int32_t)(h_id[e] >> 32), (int32_t)(h_id[e] & 0xFFFFFFFFull), d};
     }
-    if (!std::is_sorted(mst.begin(), mst.end(), by_weight)) std::sort(mst.begin(), mst.end(), by_weight);   // distances not monotone in the key (never for valid modes)
+    if (mixed) std::sort(mst.begin() + run0, mst.end(), by_weight);
+    if (!monotone) std::sort(mst.begin(), mst.end(), by_weight);   // distances not monotone in the key (never for the valid modes)
+    return 0;
+}
+
+// out[0] dense-pass kernel ms, [1] Boruvka kernel ms, [2] forest sort ms (CUDA events on the context's stream, last tc_mst),
+// [3] candidate edges of this rank, [4] Boruvka rounds, [5] flagged tiles, [6] tiles in the lower triangle,
+// [7] 1 when the pass ran on the reordered copy
+extern "C" int tc_mst_stats(const tc_ctx *ctx, double *out)
+{
+    TC_CHECK(ctx && out, "tc_mst_stats: bad arguments");
+    const tc_k4_state &k = ctx->k4;
+    float ms = 0.f;
+    out[0] = tc_last_pass_kernel_ms(ctx);
+    out[1] = (k.ev[0] && cudaEventElapsedTime(&ms, k.ev[0], k.ev[1]) == cudaSuccess) ? ms : -1.0;
+    out[2] = (k.ev[1] && cudaEventElapsedTime(&ms, k.ev[1], k.ev[2]) == cudaSuccess) ? ms : -1.0;
+    cudaGetLastError();
+    out[3] = (double)ctx->n_edges;
+    out[4] = (double)k.last_rounds;
+    const tc_ctx *src = (ctx->use_shadow && ctx->shadow) ? ctx->shadow : ctx;
+    out[5] = src->tile_words ? (double)src->tiles_flagged : -1.0;
+    const double nrb = (ctx->n + 31) / 32;
+    out[6] = nrb * (nrb + 1) / 2;
+    out[7] = (ctx->use_shadow && ctx->shadow) ? 1.0 : 0.0;
     return 0;
 }
 
@@ -430,6 +466,7 @@ extern "C" int tc_mg_export(tc_ctx *ctx, uint32_t n_max, void *handle_out)
     h.ptr = (unsigned long long)(uintptr_t)k.d_xbuf; h.pid = (long long)getpid(); h.device = ctx->device; h.n_max = n_max;
     memset(handle_out, 0, TC_MG_HANDLE_BYTES);
     memcpy(handle_out, &h, sizeof h);
+    k.export_fresh = true;
     return 0;
 }
 
@@ -442,18 +479,22 @@ extern "C" int tc_mg_join(tc_ctx *ctx, int rank, int nranks, const void *handles
     MgHandle me;
     memcpy(&me, hb + (size_t)rank * TC_MG_HANDLE_BYTES, sizeof me);
     TC_CHECK(me.ptr == (unsigned long long)(uintptr_t)k.d_xbuf && me.pid == (long long)getpid(), "tc_mg_join: handle %d is not this context's (tc_mg_export)", rank);
+    TC_CHECK(k.export_fresh, "tc_mg_join: the exchange buffer has been used by an earlier group; call tc_mg_export again (its barrier flags must start at zero)");
+    k.export_fresh = false;
     for (int g = 0; g < nranks; g++) {
         MgHandle h;
         memcpy(&h, hb + (size_t)g * TC_MG_HANDLE_BYTES, sizeof h);
         TC_CHECK(h.n_max == me.n_max, "tc_mg_join: rank %d exported for %u sketches, this rank for %u", g, h.n_max, me.n_max);
         if (g == rank) { k.peer_xbuf[g] = k.d_xbuf; continue; }
         if (h.pid == (long long)getpid()) {                     // same process: peer access + the raw pointer
-            int can = 0;
-            TC_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, h.device));
-            TC_CHECK(can, "tc_mg_join: device %d cannot access device %d", ctx->device, h.device);
-            cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { tc_set_error("tc_mg_join: %s", cudaGetErrorString(e)); return 1; }
-            cudaGetLastError();
+            if (h.device != ctx->device) {                      // (two contexts on one device: tests of the group logic on a 1-GPU box)
+                int can = 0;
+                TC_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, h.device));
+                TC_CHECK(can, "tc_mg_join: device %d cannot access device %d", ctx->device, h.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { tc_set_error("tc_mg_join: %s", cudaGetErrorString(e)); return 1; }
+                cudaGetLastError();
+            }
             k.peer_xbuf[g] = reinterpret_cast<unsigned long long *>((uintptr_t)h.ptr);
         } else {
             void *p = nullptr;

@@ -45,7 +45,9 @@ struct tc_k4_state {
     unsigned long long *peer_xbuf[8] = {};
     bool peer_opened[8] = {};             // mapped with cudaIpcOpenMemHandle (another process), to be closed
     unsigned long long sys_base = 0;
+    bool export_fresh = false;            // tc_mg_export done and not yet consumed by a tc_mg_join
     uint32_t last_rounds = 0;             // Boruvka rounds of the last tc_mst
+    cudaEvent_t ev[3] = {};               // before / after the Boruvka kernel, after the forest sort
 };
 
 struct tc_ctx {

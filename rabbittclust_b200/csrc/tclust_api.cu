@@ -906,7 +906,7 @@ struct NoSyncPass {                                      // the launchers of the
 // reduction over peer memory) are queued back to back; the host waits once, for the sorted forest.
 static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t semb_size, bool complete,
                     tc_edge *out, uint64_t *n_out, uint32_t start_index = 0, const tc_edge *pre_mst = nullptr,
-                    uint64_t n_pre = 0)
+                    uint64_t n_pre = 0, bool edges_only = false)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0, "tc_mst: no sketches uploaded");
@@ -917,7 +917,7 @@ static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t se
     for (int attempt = 0;; attempt++) {
         uint64_t cnt = 0;
         bool overflow = false;
-        {
+        if (!edges_only) {
             NoSyncPass nosync(ctx);
             if (allpairs_pass_impl(ctx, radio, semb_size, part, nparts, nullptr, nullptr, start_index, true)) return 1;
         }
@@ -925,6 +925,7 @@ static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t se
         if (tc_k4_collect(ctx, mode, kmer_size, mst, &cnt, &overflow, complete ? &comp : nullptr)) return 1;
         ctx->n_edges = std::min<uint64_t>(cnt, ctx->edge_cap);
         if (!overflow) break;
+        TC_CHECK(!edges_only, "tc_mst_of_edges: the candidate edges of the last pass overflowed the edge buffer");
         // the candidate edges did not fit: cnt is the exact need; grow the buffer to it and repeat once.  In a multi-GPU
         // group the kernel has told every rank, so all of them repeat the (collective) call together.
         TC_CHECK(attempt == 0, "tc_mst: %llu candidate edges exceed the device edge buffer (%llu)",
@@ -976,6 +977,16 @@ extern "C" int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double thresh
 {
     TC_CHECK(containment == 0 || containment == 1, "tc_mst: containment must be 0 or 1");
     return mst_impl(ctx, kmer_size, containment, tc_radio(threshold, kmer_size), 0, false, out, n_out);
+}
+
+// Boruvka alone over the candidate edges the last tc_allpairs_pass* left on the device (in a group: every rank's own
+// part, reduced inside the kernel)
+extern "C" int tc_mst_of_edges(tc_ctx *ctx, int kmer_size, int containment, tc_edge *out, uint64_t *n_out)
+{
+    TC_CHECK(containment >= 0 && containment <= 3, "tc_mst_of_edges: distance mode %d unknown", containment);
+    TC_CHECK((containment == TC_DIST_MASH_B) == (ctx->edges_semb_size > 0),
+             "tc_mst_of_edges: distance mode %d does not match the pass that produced the edges", containment);
+    return mst_impl(ctx, kmer_size, containment, 0, ctx->edges_semb_size, false, out, n_out, 0, nullptr, 0, true);
 }
 
 extern "C" int tc_mst_append(tc_ctx *ctx, int kmer_size, int containment, double threshold, uint32_t start_index,

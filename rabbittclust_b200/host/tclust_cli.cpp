@@ -42,6 +42,7 @@
 #include <iostream>
 #include <queue>
 #include <string>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include <atomic>
@@ -75,6 +76,7 @@ struct Options {
     bool dense = false, newick = false, phylip = false, nexus = false, linkage = false;
     double threshold = 0.05;
     int kmer = 19, sketch_size = 1000, compress = 1000, drlevel = 3, device = 0;
+    int gpus = 1;                 // --gpus G: devices device .. device+G-1 build the MST together (multi-GPU group of the library)
     uint64_t min_len = 10000;
 };
 
@@ -945,6 +947,46 @@ void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_fi
     vector<tc_edge> mst(g.size());
     uint64_t m = 0;
     const double t_mst = now_s();
+    if (o.gpus > 1) {
+        // Multi-GPU MST: one context and one host thread per device.  Every device holds all sketches
+        // (uploaded over its own PCIe link), evaluates its share of the work units of the dense pass, and the Boruvka
+        // min-reductions run inside the kernel over NVLink peer memory (tc_mg_*).  Every rank gets the same MST.
+        const int G = o.gpus;
+        vector<tc_ctx *> cs(G, nullptr);
+        cs[0] = ctx;
+        for (int r = 1; r < G; r++) tc_or_die(tc_ctx_create(o.device + r, &cs[r]), "tc_ctx_create (--gpus)");
+        vector<unsigned char> handles((size_t)G * TC_MG_HANDLE_BYTES);
+        for (int r = 0; r < G; r++) tc_or_die(tc_mg_export(cs[r], (uint32_t)g.size(), handles.data() + (size_t)r * TC_MG_HANDLE_BYTES), "tc_mg_export");
+        vector<string> errs(G);
+        vector<std::thread> th;
+        vector<tc_edge> other(g.size());
+        std::mutex other_mu;
+        for (int r = 0; r < G; r++)
+            th.emplace_back([&, r]() {
+                auto fail = [&](const char *what) { errs[r] = string(what) + ", " + tc_last_error(); };
+                if (tc_mg_join(cs[r], r, G, handles.data())) { fail("tc_mg_join"); return; }
+                if (r > 0) {                     // rank 0's sketches are resident already
+                    vector<const uint64_t *> rows(g.size());
+                    vector<uint64_t> sizes(g.size());
+                    for (size_t i = 0; i < g.size(); i++) { rows[i] = g[i].hashes.data(); sizes[i] = g[i].hashes.size(); }
+                    if (tc_sketches_upload_rows(cs[r], rows.data(), sizes.data(), (uint32_t)g.size())) { fail("sketch upload"); return; }
+                }
+                uint64_t mm = 0;
+                if (r == 0) { if (tc_mst(cs[r], o.kmer, o.containment, o.threshold, mst.data(), &mm)) { fail("MST generation"); return; } m = mm; }
+                else {
+                    vector<tc_edge> mine(g.size());
+                    if (tc_mst(cs[r], o.kmer, o.containment, o.threshold, mine.data(), &mm)) { fail("MST generation"); return; }
+                }
+            });
+        for (std::thread &t : th) t.join();
+        for (int r = 0; r < G; r++) if (!errs[r].empty()) die("GPU " + std::to_string(o.device + r) + ": " + errs[r]);
+        for (int r = 0; r < G; r++) tc_mg_leave(cs[r]);
+        for (int r = 1; r < G; r++) tc_ctx_destroy(cs[r]);
+        if (o.dense) {                           // the density epilogue reads ALL candidate pairs: one full pass on device 0
+            uint64_t np = 0, ne = 0;
+            tc_or_die(tc_allpairs_pass(ctx, tc_radio(o.threshold, o.kmer), 0, 1, &np, &ne), "dense pass for --dense");
+        }
+    } else
     tc_or_die(tc_mst(ctx, o.kmer, o.containment, o.threshold, mst.data(), &m), "MST generation");
     mst.resize(m);
     double t3 = now_s();
@@ -1010,7 +1052,7 @@ void usage(const char *prog)
             " | --premsted DIR"
 #endif
             ") [--append FILE] [--fast [--drlevel N]] [--dense]\n"
-            "          [--newick-tree] [--phylip-tree] [--nexus-tree] [--linkage-matrix] [--device N]\n", prog);
+            "          [--newick-tree] [--phylip-tree] [--nexus-tree] [--linkage-matrix] [--device N] [--gpus G]\n", prog);
 }
 
 }  // namespace
@@ -1046,11 +1088,13 @@ int main(int argc, char **argv)
         else if (f == "--linkage-matrix") o.linkage = true;
         else if (f == "--drlevel") o.drlevel = atoi(need("--drlevel"));
         else if (f == "--device") o.device = atoi(need("--device"));
+        else if (f == "--gpus") o.gpus = atoi(need("--gpus"));
         else if (f == "-h" || f == "--help") { usage(argv[0]); return 0; }
         else { usage(argv[0]); die("unsupported option " + f + " (see DESIGN.md: out of scope for the B200 hot-path build)"); }
     }
     if (!o.has_output) { cerr << "ERROR: option -o/--output is required (unless --buildDB or --stats is used)" << endl; return 1; }
     if (o.threads < 1) { fprintf(stderr, "-----Invalid thread number %d\n", o.threads); return 1; }
+    if (o.gpus < 1 || o.gpus > 8) { fprintf(stderr, "-----Invalid --gpus %d (1..8)\n", o.gpus); return 1; }
     fprintf(stderr, "-----set the thread number %d\n", o.threads);
     if (!o.has_threshold) cerr << "-----use default threshold: " << o.threshold << endl;
     if (o.fast && (o.drlevel < 0 || o.drlevel > 8)) { cerr << "ERROR: invalid drlevel " << o.drlevel << ", should be in [0, 8]" << endl; return 1; }

@@ -285,3 +285,19 @@ def test_clust_mst_fast_append_matches_reference(genomes, tmp_path):
     la = [l.split("\t")[2] for l in open(ref_out + ".linkage.txt")]
     lb = [l.split("\t")[2] for l in open(our_out + ".linkage.txt")]
     assert la == lb
+
+
+def test_clust_mst_gpus_flag(genomes, tmp_path):
+    """clust-mst --gpus G (multi-GPU group inside the binary: one context + host thread per device, Boruvka reductions
+    over peer memory): same edge.mst and cluster file as the single-GPU run, also with --dense."""
+    import torch
+    g = min(torch.cuda.device_count(), 4)
+    if g < 2:
+        pytest.skip("needs at least 2 GPUs")
+    lst, _ = genomes
+    args = ["-l", "-i", lst, "-k", "21", "-d", "0.05", "-s", "1000", "--dense", "-o", "out.txt"]
+    f1, _ = _run(os.path.join(OURS, "clust-mst"), args, str(tmp_path / "one"))
+    fg, _ = _run(os.path.join(OURS, "clust-mst"), args + ["--gpus", str(g)], str(tmp_path / "many"))
+    for name in ("edge.mst", "hash.sketch", "mst.ani", "mst.dense"):
+        assert _same_bytes(os.path.join(f1, name), os.path.join(fg, name)), name
+    assert open(str(tmp_path / "one" / "out.txt")).read() == open(str(tmp_path / "many" / "out.txt")).read()

@@ -72,10 +72,11 @@ def test_join_many_segments_and_partitions(ctx):
         assert np.array_equal(a, b), (i0, i1, j0, j1)
 
 
-@pytest.mark.parametrize("pass_impl", ["join", "merge"])
+@pytest.mark.parametrize("pass_impl", ["default", "blockjoin", "join", "merge"])
 @pytest.mark.parametrize("containment", [False, True])
 def test_dense_pass_edges_and_mst(ctx, oracle, tc, containment, pass_impl, monkeypatch):
-    monkeypatch.setenv("TCLUST_PASS_IMPL", pass_impl)
+    if pass_impl != "default":      # "default" = the production routing (K3J per unit where it pays, else K3H; tile flags)
+        monkeypatch.setenv("TCLUST_PASS_IMPL", pass_impl)
     k, thr = 21, 0.05
     if containment:
         sk = synth.family_sketches(8, 12, seed=21, ragged=(100, 2000))
