@@ -190,6 +190,19 @@ int tc_boruvka_set_async(tc_ctx *ctx, int on);
 int tc_mst(tc_ctx *ctx, int kmer_size, int containment, double threshold,
            tc_edge *out, uint64_t *n_out);
 
+/*
+ * Threshold-only clustering: the clusters of clust-mst at `threshold` without the MST -- connected
+ * components of the candidate pairs whose distance is <= threshold, i.e. the partition generateForest +
+ * generateClusterWithBfs (src/MST.cpp:77-142) cut out of the MST.  The dense pass unions the pairs in a device-resident
+ * union-find instead of writing edges: O(n) memory whatever the candidate graph, no Boruvka.  labels[v] = smallest id
+ * of v's cluster, over the pairs of `part` of `nparts` (multi-GPU: one part per GPU, then tc_labels_merge on the host).
+ * The within-threshold test is exact: J = common/denom against the smallest J whose reference distance is <= threshold.
+ */
+int tc_cluster_threshold(tc_ctx *ctx, int kmer_size, int containment, double threshold, uint32_t part, uint32_t nparts,
+                         int32_t *labels, uint32_t *n_clusters);
+/* host: into[] := labels of the union of the two partial partitions; *n_clusters (may be NULL) = clusters after it */
+int tc_labels_merge(int32_t *into, const int32_t *other, uint32_t n, uint32_t *n_clusters);
+
 /* the Boruvka half of tc_mst alone: MST of the candidate edges the last tc_allpairs_pass / _from / _b left on the device
  * (the reference's final Kruskal, src/MST.cpp:1715-1723; `containment` = TC_DIST_* mode matching that pass).  For callers
  * that use the edges in between (tc_dense_ani).  In a multi-GPU group: collective, every rank brings the edges of its part. */
@@ -197,8 +210,11 @@ int tc_mst_of_edges(tc_ctx *ctx, int kmer_size, int containment, tc_edge *out, u
 
 /* timings and counts of the last tc_mst / tc_mst_append on the context (bench accounting): out[0] dense-pass kernel ms,
  * [1] Boruvka kernel ms, [2] forest sort ms (CUDA events on tc_stream), [3] candidate edges of this rank, [4] Boruvka
- * rounds, [5] tiles the pass visits (-1: tile flags off), [6] tiles in the lower triangle, [7] 1 = pass on the reordered copy */
-int tc_mst_stats(const tc_ctx *ctx, double *out /* 8 doubles */);
+ * rounds, [5] tiles the pass visits (-1: tile flags off), [6] tiles in the lower triangle, [7] 1 = pass on the reordered copy,
+ * [8] batches and [9] forest reductions of a bounded-memory build (0: the candidate graph fitted the edge buffer; otherwise
+ * the pass ran in batches sized to the buffer -- TCLUST_EDGE_CAP entries or what the device has free -- and Boruvka folded
+ * every full buffer into a forest of <= n-1 edges, as the reference does per task, src/MST.cpp:1373-1386) */
+int tc_mst_stats(const tc_ctx *ctx, double *out /* 12 doubles */);
 
 /*
  * Multi-GPU group ("N x N tile space sharded over the GPUs of one box, min-reduction per Boruvka round").

@@ -26,7 +26,7 @@ SYMBOLS = [
     "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce", "tc_greedy_cluster_kssd", "tc_dense_ani", "tc_allpairs_pass_from", "tc_mst_append",
     "tc_jaccard_b", "tc_distance_b", "tc_contain_distance",
     "tc_mash_dist", "tc_aaf_dist", "tc_dist_from_key", "tc_radio", "tc_greedy_common_min", "tc_greedy_dist",
-    "tc_mg_export", "tc_mg_join", "tc_mg_leave", "tc_mg_rank", "tc_mst_stats", "tc_mst_of_edges",
+    "tc_mg_export", "tc_mg_join", "tc_mg_leave", "tc_mg_rank", "tc_mst_stats", "tc_mst_of_edges", "tc_cluster_threshold", "tc_labels_merge",
 ]
 MG_HANDLE_BYTES = 128
 
@@ -113,6 +113,8 @@ def lib():
     L.tc_mg_rank.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.tc_mst_stats.argtypes = [vp, C.POINTER(C.c_double)]
     L.tc_mst_of_edges.argtypes = [vp, C.c_int, C.c_int, vp, u64p]
+    L.tc_cluster_threshold.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_uint32, C.c_uint32, i32p, u32p]
+    L.tc_labels_merge.argtypes = [i32p, i32p, C.c_uint32, u32p]
     L.tc_radio.argtypes = [C.c_double, C.c_int]
     L.tc_radio.restype = C.c_int
     _lib = L
@@ -356,10 +358,18 @@ class Context:
 
     def mst_stats(self):
         """Timings of the last mst() on this context (CUDA events on its stream), candidate edges, Boruvka rounds."""
-        v = (C.c_double * 8)()
+        v = (C.c_double * 12)()
         _chk(lib().tc_mst_stats(self._h, v))
         return {"pass_ms": v[0], "boruvka_ms": v[1], "sort_ms": v[2], "edges": int(v[3]), "rounds": int(v[4]),
-                "tiles_flagged": int(v[5]), "tiles_total": int(v[6]), "on_reordered_copy": bool(v[7])}
+                "tiles_flagged": int(v[5]), "tiles_total": int(v[6]), "on_reordered_copy": bool(v[7]),
+                "bounded_batches": int(v[8]), "bounded_folds": int(v[9])}
+
+    def cluster_threshold(self, k, threshold, containment=False, part=0, nparts=1):
+        """Threshold-only clustering (no MST, no edge list): (n_clusters, labels) with labels[v] = smallest id of v's cluster."""
+        lab = np.zeros(max(self.n, 1), np.int32)
+        nc = C.c_uint32(0)
+        _chk(lib().tc_cluster_threshold(self._h, k, int(containment), threshold, part, nparts, _p(lab, C.c_int32), C.byref(nc)))
+        return int(nc.value), lab[:self.n]
 
     def greedy_scan(self, q0, q1, rep_ids):
         reps = np.ascontiguousarray(rep_ids, np.uint32)
@@ -374,6 +384,15 @@ class Context:
         nc = C.c_uint32(0)
         _chk(lib().tc_greedy_cluster(self._h, k, int(containment), threshold, _p(rep, C.c_int32), C.byref(nc)))
         return int(nc.value), rep[:self.n].copy()
+
+
+def labels_merge(into, other):
+    """Union of two partial partitions given as smallest-id labels (tc_labels_merge); returns (n_clusters, labels)."""
+    a = np.ascontiguousarray(into, np.int32).copy()
+    b = np.ascontiguousarray(other, np.int32)
+    nc = C.c_uint32(0)
+    _chk(lib().tc_labels_merge(_p(a, C.c_int32), _p(b, C.c_int32), len(a), C.byref(nc)))
+    return int(nc.value), a
 
 
 def mash_dist(common, size0, size1, k):

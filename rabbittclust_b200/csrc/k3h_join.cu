@@ -72,7 +72,39 @@ struct KHArgs {
     const uint32_t *multi;          // bit r = rank r occurs in at least two sketches (only those can be shared)
     // tile candidacy (k3t_tileflags.cu): bit cb of row rb set = blocks rb and cb share a rank; nullptr = visit every tile
     const uint32_t *tile_flags; uint32_t tile_words;
+    // threshold-only clustering (tc_cluster_threshold): instead of appending a candidate edge, union (i, j) in a
+    // device-resident union-find when J = common/denom >= uf_jmin (<=> reference distance <= threshold);
+    // uf_perm: ids of the reordered copy -> input ids (nullptr: identity); distance mode in `containment`
+    uint32_t *uf; const uint32_t *uf_perm; double uf_jmin;
 };
+
+// lock-free union-find (hook the larger root under the smaller: the root of a component is its smallest vertex)
+__device__ __forceinline__ uint32_t kh_uf_find(uint32_t *p, uint32_t x)
+{
+    for (;;) {
+        const uint32_t q = *(volatile uint32_t *)&p[x];
+        if (q == x) return x;
+        x = q;
+    }
+}
+__device__ __forceinline__ void kh_uf_union(uint32_t *p, uint32_t a, uint32_t b)
+{
+    for (;;) {
+        a = kh_uf_find(p, a); b = kh_uf_find(p, b);
+        if (a == b) return;
+        if (a < b) { const uint32_t t = a; a = b; b = t; }
+        if (atomicCAS(&p[a], a, b) == a) return;
+    }
+}
+// the pair (i, j) with `common` shared hashes joins one cluster iff its distance is within the threshold
+__device__ __forceinline__ void kh_uf_edge(const KHArgs &a, uint32_t i, uint32_t j, uint32_t common, uint32_t s0, uint32_t s1)
+{
+    const uint32_t denom = a.containment ? min(s0, s1) : s0 + s1 - common;
+    const double J = denom == 0 ? 0.0 : __ddiv_rn((double)common, (double)denom);
+    if (!(J >= a.uf_jmin)) return;
+    if (a.uf_perm) { i = __ldg(a.uf_perm + i); j = __ldg(a.uf_perm + j); }
+    kh_uf_union(a.uf, i, j);
+}
 
 // presence filter: word = top (KH_FBITS-5) bits of h = x * golden, the two bit positions = low 10 bits of h
 __device__ __forceinline__ uint32_t kh_fword(uint32_t h) { return h >> (32 - (KH_FBITS - 5)); }
@@ -579,6 +611,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_join_kernel(const KHArgs a)
                             // reference: skip if max_size > radio * min_size (int arithmetic), MST.cpp:1481-1487
                             keep = mn > 0 && !((long long)mx > (long long)a.radio * (long long)mn);
                         }
+                        if (a.uf && keep) { kh_uf_edge(a, i, j, cnt, s_len[lane], clen); keep = false; }
                         const unsigned ballot = __ballot_sync(0xffffffffu, keep);
                         if (ballot) {
                             unsigned long long base = 0;
@@ -857,6 +890,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
                     const uint32_t s0 = s_len[row], s1 = a.size[j];
                     const uint32_t mn = min(s0, s1), mx = max(s0, s1);
                     keep = mn > 0 && !((long long)mx > (long long)a.radio * (long long)mn);   // MST.cpp:1481-1487
+                    if (a.uf && keep) { kh_uf_edge(a, i, j, c, s0, s1); keep = false; }
                 }
                 const unsigned ballot = __ballot_sync(0xffffffffu, keep);
                 if (ballot) {
@@ -1092,9 +1126,14 @@ int tc_kh_prepare(tc_ctx *ctx)
 
 // edge_list: `units` is ctx->kh_edge_units, which stays resident on the device between passes (no per-pass copy
 // from pageable host memory in front of the kernel)
-static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &units, bool edge_list = false,
-                     bool block_kernel = false, bool record_start = true, const tc_kh_unit *d_resident = nullptr)
+static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &units_all, bool edge_list = false,
+                     bool block_kernel = false, bool record_start = true, const tc_kh_unit *d_resident = nullptr,
+                     size_t range_begin = 0, size_t range_end = ~(size_t)0)
 {
+    // units [range_begin, range_end) of a device-resident list (bounded-memory passes launch a list piece by piece)
+    struct Range { size_t b, e; size_t size() const { return e - b; } bool empty() const { return e <= b; } };
+    const Range units{d_resident ? std::min(range_begin, units_all.size()) : 0, d_resident ? std::min(range_end, units_all.size()) : units_all.size()};
+    if (d_resident) d_resident += units.b;
     if (!(ctx->attr_set & 2u)) {
         TC_CUDA(cudaFuncSetAttribute(k3h_join_kernel<KH_MODE_EDGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KH_SMEM));
         TC_CUDA(cudaFuncSetAttribute(k3h_join_kernel<KH_MODE_CAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KH_SMEM));
@@ -1108,7 +1147,7 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
         ctx->kh_units_cap = units.size();
     }
     if (!d_resident && !(edge_list && ctx->kh_units_on_device)) {
-        TC_CUDA(cudaMemcpyAsync(ctx->d_kh_units, units.data(), units.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice,
+        TC_CUDA(cudaMemcpyAsync(ctx->d_kh_units, units_all.data(), units.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice,
                                 ctx->stream));
         TC_CUDA(cudaStreamSynchronize(ctx->stream));   // `units` (host) must outlive the copy
         ctx->kh_units_on_device = edge_list;
@@ -1125,6 +1164,8 @@ static int kh_launch(tc_ctx *ctx, KHArgs &a, const std::vector<tc_kh_unit> &unit
     a.bu_keys = ctx->d_bu_keys; a.bu_mask = ctx->d_bu_mask; a.bu_count = ctx->d_bu_count; a.multi = ctx->d_multi;
     a.tile_flags = nullptr; a.tile_words = 0;
     if (a.mode == KH_MODE_EDGES && ctx->tile_words) { a.tile_flags = ctx->d_tile_flags; a.tile_words = ctx->tile_words; }
+    a.uf = nullptr; a.uf_perm = nullptr; a.uf_jmin = 2.0;
+    if (a.mode == KH_MODE_EDGES && ctx->uf_parent) { a.uf = ctx->uf_parent; a.uf_perm = ctx->uf_perm; a.uf_jmin = ctx->uf_jmin; a.containment = ctx->uf_containment; }
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count + 2, 0, sizeof(unsigned long long), ctx->stream));
     if (ctx->ev_pass0 && record_start) cudaEventRecord(ctx->ev_pass0, ctx->stream);   // kernel-only duration, tc_last_pass_kernel_ms
     if (block_kernel) k3j_block_kernel<<<grid, KH_THREADS, KJ_SMEM, ctx->stream>>>(a);
@@ -1275,7 +1316,7 @@ static uint32_t kj_pick_cseg(uint32_t n, uint32_t start_index, uint32_t nparts, 
     return KH_CSEG;
 }
 
-int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index, bool force_block)
+int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index, bool force_block, bool plan_only)
 {
     // the unit list (also what tc_allpairs_pass counts pairs from), split by kernel
     kh_edge_unit_list(ctx, start_index, kj_pick_cseg(ctx->n, start_index, nparts ? nparts : 1, ctx->num_sms));
@@ -1314,9 +1355,31 @@ int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t np
         if (!old.empty()) TC_CUDA(cudaMemcpy(ctx->d_kj_units + blk.size(), old.data(), old.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice));
         ctx->kj_split_key = key; ctx->kj_split_valid = true;
     }
+    if (plan_only) return 0;
     KHArgs a{};
     a.mode = KH_MODE_EDGES; a.part = 0; a.nparts = 1; a.row_min = start_index;   // the lists already hold this part only
     a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
     if (kh_launch(ctx, a, ctx->kj_units_blk, false, true, true, ctx->d_kj_units)) return 1;
     return kh_launch(ctx, a, ctx->kj_units_old, false, false, ctx->kj_units_blk.empty(), ctx->d_kj_units + ctx->kj_units_blk.size());
+}
+
+// ---- the same pass piece by piece (bounded edge memory, tclust_api.cu mst_bounded): units [u0, u1) of this context's
+// block-join list (block_list) or hash-join list, after tc_launch_blockjoin_edges(..., plan_only = true)
+int tc_blockjoin_run_range(tc_ctx *ctx, int radio, uint32_t start_index, bool block_list, size_t u0, size_t u1)
+{
+    KHArgs a{};
+    a.mode = KH_MODE_EDGES; a.part = 0; a.nparts = 1; a.row_min = start_index;
+    a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
+    if (block_list) return kh_launch(ctx, a, ctx->kj_units_blk, false, true, true, ctx->d_kj_units, u0, u1);
+    return kh_launch(ctx, a, ctx->kj_units_old, false, false, true, ctx->d_kj_units + ctx->kj_units_blk.size(), u0, u1);
+}
+
+// most candidate edges unit u of that list can emit: 32 rows x its columns, or 1024 per flagged tile of a whole-row unit
+uint64_t tc_blockjoin_unit_bound(const tc_ctx *ctx, bool block_list, size_t u)
+{
+    const tc_kh_unit &x = block_list ? ctx->kj_units_blk[u] : ctx->kj_units_old[u];
+    uint64_t b = (uint64_t)32 * (x.c1 - x.c0);
+    if (ctx->tile_words && x.c0 == 0 && x.c1 + 32 > x.rb * 32 && x.rb < ctx->tile_rowcount.size())
+        b = std::min<uint64_t>(b, (uint64_t)ctx->tile_rowcount[x.rb] * 1024);
+    return b;
 }

@@ -50,11 +50,12 @@ __global__ void k3r_gather_kernel(const uint32_t *ranks, const unsigned long lon
     if (threadIdx.x == 0) new_size[i] = (uint32_t)len;
 }
 
-__global__ void k3r_remap_kernel(tc_pair *edges, const unsigned long long *counters, unsigned long long cap, const uint32_t *perm)
+__global__ void k3r_remap_kernel(tc_pair *edges, const unsigned long long *counters, unsigned long long cap, const uint32_t *perm,
+                                 unsigned long long first)
 {
     unsigned long long m = counters[0];
     if (m > cap) m = cap;
-    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < m;
+    for (unsigned long long e = first + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < m;
          e += (unsigned long long)gridDim.x * blockDim.x) {
         tc_pair p = edges[e];
         const uint32_t a = perm[p.i], b = perm[p.j];
@@ -185,7 +186,13 @@ int tc_shadow_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, bool 
     ctx->d_kh_state = s->d_kh_state;
     ctx->launches += s->launches; s->launches = 0;
     if (rc) return rc;
-    k3r_remap_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->d_edges, ctx->d_edge_count, ctx->edge_cap, s->d_perm);
+    return tc_shadow_remap_from(ctx, 0);
+}
+
+int tc_shadow_remap_from(tc_ctx *ctx, uint64_t first_edge)
+{
+    tc_ctx *s = ctx->shadow;
+    k3r_remap_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->d_edges, ctx->d_edge_count, ctx->edge_cap, s->d_perm, first_edge);
     if (ctx->ev_pass1) cudaEventRecord(ctx->ev_pass1, ctx->stream);      // tc_last_pass_kernel_ms covers the remap too
     ctx->launches++;
     TC_CUDA(cudaGetLastError());

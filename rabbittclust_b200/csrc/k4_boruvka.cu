@@ -260,7 +260,7 @@ void tc_k4_free(tc_ctx *ctx)
     tc_k4_state &k = ctx->k4;
     for (int g = 0; g < 8; g++)
         if (k.peer_opened[g]) { cudaIpcCloseMemHandle(k.peer_xbuf[g]); k.peer_opened[g] = false; }
-    cudaFree(k.d_xbuf); cudaFree(k.d_red); cudaFree(k.d_parent); cudaFree(k.d_out); cudaFree(k.d_ctl); cudaFree(k.d_sort_tmp);
+    cudaFree(k.d_xbuf); cudaFree(k.d_red); cudaFree(k.d_parent); cudaFree(k.d_out); cudaFree(k.d_fin); cudaFree(k.d_ctl); cudaFree(k.d_sort_tmp);
     if (k.h_out) cudaFreeHost(k.h_out);
     for (int e = 0; e < 3; e++) if (k.ev[e]) cudaEventDestroy(k.ev[e]);
     k = tc_k4_state();
@@ -412,6 +412,30 @@ int tc_k4_collect(tc_ctx *ctx, int mode, int kmer_size, std::vector<tc_edge> &ms
     return 0;
 }
 
+// Bounded-memory MST: wait for the queued Boruvka and keep its (sorted) forest on the device as the explicit (key, id)
+// edges of the next launch -- MSF(E1 u E2) = MSF(MSF(E1) u E2), what the reference does per task of 8 rows
+// (src/MST.cpp:1373-1386, 571-572).  The candidate-edge counter restarts at 0.
+int tc_k4_fold(tc_ctx *ctx, uint32_t *nfin)
+{
+    tc_k4_state &k = ctx->k4;
+    const uint32_t n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    uint32_t h_ctl[8];
+    TC_CUDA(cudaMemcpyAsync(h_ctl, k.d_ctl, sizeof h_ctl, cudaMemcpyDeviceToHost, st));
+    TC_CUDA(cudaStreamSynchronize(st));
+    TC_CHECK(h_ctl[4] == 0, "tc_mst: the Boruvka kernel gave up at a barrier");
+    TC_CHECK(h_ctl[6] == 0, "tc_mst: a batch of candidate edges overflowed the edge buffer (bounded-memory MST)");
+    const uint32_t nf = std::min(h_ctl[0], n);
+    if (k4_grow(&k.d_fin, &k.cap_fin, (uint64_t)2 * n)) return 1;
+    if (nf) {
+        TC_CUDA(cudaMemcpyAsync(k.d_fin, k.d_out, (size_t)nf * 8, cudaMemcpyDeviceToDevice, st));
+        TC_CUDA(cudaMemcpyAsync(k.d_fin + n, k.d_out + n, (size_t)nf * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), st));
+    *nfin = nf;
+    return 0;
+}
+
 // out[0] dense-pass kernel ms, [1] Boruvka kernel ms, [2] forest sort ms (CUDA events on the context's stream, last tc_mst),
 // [3] candidate edges of this rank, [4] Boruvka rounds, [5] flagged tiles, [6] tiles in the lower triangle,
 // [7] 1 when the pass ran on the reordered copy
@@ -431,6 +455,7 @@ extern "C" int tc_mst_stats(const tc_ctx *ctx, double *out)
     const double nrb = (ctx->n + 31) / 32;
     out[6] = nrb * (nrb + 1) / 2;
     out[7] = (ctx->use_shadow && ctx->shadow) ? 1.0 : 0.0;
+    out[8] = (double)ctx->bounded_batches; out[9] = (double)ctx->bounded_folds; out[10] = out[11] = 0.0;
     return 0;
 }
 

@@ -121,6 +121,8 @@ extern "C" int tc_dense_ani(tc_ctx *ctx, int kmer_size, int containment, int den
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0 && ctx->d_edges, "tc_dense_ani: run tc_allpairs_pass / tc_mst first");
     TC_CHECK(ctx->edges_semb_size == 0, "tc_dense_ani: the candidate edges must come from tc_allpairs_pass (semantic A)");
+    TC_CHECK(!ctx->edges_partial, "tc_dense_ani: the last MST was built in bounded edge memory (or by one rank of a multi-GPU group): "
+             "the device holds only part of the candidate pairs; run tc_allpairs_pass first");
     TC_CHECK(dense_span >= 1 && dense_span <= K6_MAX_SPAN, "tc_dense_ani: dense_span=%d out of range (1..%d)", dense_span, K6_MAX_SPAN);
     TC_CHECK(containment == 0 || containment == 1, "tc_dense_ani: containment must be 0 or 1");
     const uint32_t n = ctx->n;

@@ -37,6 +37,7 @@ struct tc_k4_state {
     unsigned long long *d_red = nullptr;  uint64_t cap_red = 0;
     uint32_t *d_parent = nullptr;         uint64_t cap_parent = 0;
     unsigned long long *d_out = nullptr;  uint64_t cap_out = 0;      // forest (key, id) + sort alternates: 4 x n
+    unsigned long long *d_fin = nullptr;  uint64_t cap_fin = 0;      // forest of the edge batches seen so far (bounded-memory MST): 2 x n
     uint32_t *d_ctl = nullptr;
     void *d_sort_tmp = nullptr;           uint64_t cap_sort_tmp = 0;
     void *h_out = nullptr;                uint64_t h_out_bytes = 0;  // page-locked read-back buffer
@@ -80,6 +81,8 @@ struct tc_ctx {
     uint32_t edge_cap_for_n = 0;  // n the edge buffer was last sized for (0: re-evaluate)
     unsigned long long *d_edge_count = nullptr;  // [0] = count, [1] = overflow flag, [2] = tile counter
     uint64_t n_edges = 0;
+    uint64_t bounded_batches = 0, bounded_folds = 0;   // last bounded-memory MST (0: the candidate graph fitted)
+    bool edges_partial = false;       // d_edges holds only part of the candidate graph (bounded-memory MST, one rank of a group)
     uint32_t edges_semb_size = 0;     // > 0: the edges carry semantic-B counts taken with this sketchSize
     int32_t *d_comp = nullptr;
 
@@ -147,6 +150,9 @@ struct tc_ctx {
     cudaEvent_t ev_chunk[TC_UP_CHUNKS + 1] = {};
 
     tc_k4_state k4;
+    // threshold-only clustering: while set, the edge passes union (i, j) on the device instead of appending edges
+    uint32_t *uf_parent = nullptr; const uint32_t *uf_perm = nullptr; double uf_jmin = 2.0; int uf_containment = 0;
+    uint32_t *d_uf = nullptr; uint64_t cap_uf = 0;
     bool pass_nosync = false;            // dense-pass launchers do not wait for the device (tc_mst queues pass + Boruvka back to back)
 
     // scratch
@@ -164,6 +170,7 @@ int tc_k4_reserve(tc_ctx *ctx, uint32_t n);
 int tc_k4_enqueue(tc_ctx *ctx, int mode, const unsigned long long *d_fin_key, const unsigned long long *d_fin_id, uint32_t nfin);
 int tc_k4_collect(tc_ctx *ctx, int mode, int kmer_size, std::vector<tc_edge> &mst, uint64_t *n_edges_dev, bool *overflow,
                   std::vector<int32_t> *comp_out);
+int tc_k4_fold(tc_ctx *ctx, uint32_t *nfin);     // wait for the queued Boruvka and keep its forest on the device as the next launch's extra edges
 void tc_k2_free(tc_ctx *ctx);
 
 // tile-kernel entry points (k3_tile.cu)
@@ -179,12 +186,16 @@ int tc_kh_prepare(tc_ctx *ctx);
 int tc_tile_flags_build(tc_ctx *ctx, const std::vector<uint32_t> &dist);   // k3t_tileflags.cu
 int tc_launch_join_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
 int tc_launch_blockjoin_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
-int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index, bool force_block);
+int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index, bool force_block,
+                              bool plan_only = false);
+int tc_blockjoin_run_range(tc_ctx *ctx, int radio, uint32_t start_index, bool block_list, size_t u0, size_t u1);
+uint64_t tc_blockjoin_unit_bound(const tc_ctx *ctx, bool block_list, size_t u);
 int tc_launch_join_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment, double jmin);
 int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index = 0);
 // reordered shadow copy (k3r_reorder.cu)
 int tc_shadow_build(tc_ctx *ctx);
 int tc_shadow_pass(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, bool force_block);
+int tc_shadow_remap_from(tc_ctx *ctx, uint64_t first_edge);      // candidate edges [first_edge, count): ids of the copy -> input ids
 void tc_shadow_free(tc_ctx *ctx);
 // representative table (k5_greedy.cu)
 void tc_rep_table_free(tc_ctx *ctx);

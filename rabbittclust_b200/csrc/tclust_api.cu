@@ -98,7 +98,7 @@ static void reset_sketches(tc_ctx *ctx)
 {
     ctx->kh_edge_units.clear(); ctx->kh_edge_units_n = 0; ctx->kh_units_on_device = false; ctx->kj_split_valid = false;
     ctx->n_edges = 0; ctx->n = 0; ctx->total = 0; ctx->ngroups = 0; ctx->edges_semb_size = 0;
-    ctx->edge_cap_for_n = 0; ctx->use_shadow = false; ctx->pairs_cache_valid = false; ctx->gt_valid = false;
+    ctx->edge_cap_for_n = 0; ctx->use_shadow = false; ctx->pairs_cache_valid = false; ctx->gt_valid = false; ctx->edges_partial = false;
     tc_rep_table_reset(ctx);
 }
 
@@ -126,6 +126,7 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     tc_k2_free(ctx);
     tc_k4_free(ctx);
     cudaFree(ctx->d_edge_count);
+    cudaFree(ctx->d_uf);
     cudaFree(ctx->d_scratch);
     for (int b = 0; b < 2; b++) {
         if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
@@ -623,6 +624,7 @@ static int allpairs_pass_impl(tc_ctx *ctx, int radio, uint32_t semb_size, uint32
     TC_CHECK(!(semb_size > 0 && start_index > 0), "tc_allpairs_pass: start_index is not supported for the semantic-B pass");
     TC_CHECK(start_index <= ctx->n, "tc_allpairs_pass: start_index %u > n %u", start_index, ctx->n);
     ctx->edges_semb_size = semb_size;
+    ctx->edges_partial = nparts > 1;
     unsigned long long cnt[2] = {0, 0};
     bool on_shadow = false;               // the pass ran on the reordered copy (k3r_reorder.cu)
     for (int attempt = 0;; attempt++) {
@@ -886,6 +888,105 @@ extern "C" double tc_contain_distance(int common, int size0, int size1, int kmer
     return distance;
 }
 
+// ------------------------------------------------------------------ threshold-only clustering
+__global__ void uf_init_kernel(uint32_t *p, uint32_t n)
+{
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n) p[v] = v;
+}
+__global__ void uf_labels_kernel(const uint32_t *p, int32_t *labels, uint32_t n)
+{
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    uint32_t x = v;
+    while (p[x] != x) x = p[x];
+    labels[v] = (int32_t)x;
+}
+
+// smallest J in (0, 1] whose reference distance is <= threshold (distance is non-increasing in J): bisection over the
+// bit patterns of the positive doubles with the very function that produces the MST weights; 2.0 if none
+static double jmin_for_threshold(double threshold, int mode, int kmer_size)
+{
+    auto ok = [&](double J) { uint64_t b; memcpy(&b, &J, 8); return tc_dist_from_key(~b, mode, kmer_size) <= threshold; };
+    if (!ok(1.0)) return 2.0;
+    const double one = 1.0;
+    uint64_t lo = 1, hi;
+    memcpy(&hi, &one, 8);
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        double v;
+        memcpy(&v, &mid, 8);
+        if (ok(v)) hi = mid; else lo = mid + 1;
+    }
+    double v;
+    memcpy(&v, &lo, 8);
+    return v;
+}
+
+// Clusters at `threshold` without building (or storing) the MST: the connected components of the candidate pairs with
+// distance <= threshold -- exactly the partition generateForest + generateClusterWithBfs give on the MST
+// (src/MST.cpp:77-142: an MST keeps, for every threshold, the connectivity of the graph restricted to edges <= it).
+// The dense pass runs with a union-find epilogue: no candidate edge is written, memory is O(n).
+// labels[v] = smallest vertex id of v's cluster over the pairs of `part`; merge the parts with tc_labels_merge.
+extern "C" int tc_cluster_threshold(tc_ctx *ctx, int kmer_size, int containment, double threshold, uint32_t part, uint32_t nparts,
+                                    int32_t *labels, uint32_t *n_clusters)
+{
+    TC_CHECK(ctx && labels, "tc_cluster_threshold: bad arguments");
+    TC_CHECK(containment == 0 || containment == 1, "tc_cluster_threshold: containment must be 0 or 1");
+    TC_CUDA(cudaSetDevice(ctx->device));
+    TC_CHECK(ctx->n > 0, "tc_cluster_threshold: no sketches uploaded");
+    const char *impl = getenv("TCLUST_PASS_IMPL");
+    TC_CHECK(!(impl && !strcmp(impl, "merge")), "tc_cluster_threshold: not available on the first-generation merge kernel");
+    const uint32_t n = ctx->n;
+    if (ensure_cap(&ctx->d_uf, &ctx->cap_uf, (uint64_t)2 * n)) return 1;
+    cudaStream_t st = ctx->stream;
+    uf_init_kernel<<<nblk(n, 256), 256, 0, st>>>(ctx->d_uf, n);
+    ctx->launches++;
+    ctx->uf_parent = ctx->d_uf;
+    ctx->uf_jmin = jmin_for_threshold(threshold, containment, kmer_size);
+    ctx->uf_containment = containment;
+    ctx->uf_perm = nullptr;
+    if (ctx->shadow) {
+        ctx->shadow->uf_parent = ctx->d_uf; ctx->shadow->uf_jmin = ctx->uf_jmin; ctx->shadow->uf_containment = containment;
+        ctx->shadow->uf_perm = ctx->shadow->d_perm;
+    }
+    uint64_t np = 0, ne = 0;
+    const int rc = allpairs_pass_impl(ctx, tc_radio(threshold, kmer_size), 0, part, nparts, &np, &ne);
+    ctx->uf_parent = nullptr;
+    if (ctx->shadow) ctx->shadow->uf_parent = nullptr;
+    ctx->edges_partial = true; ctx->n_edges = 0;
+    if (rc) return rc;
+    int32_t *d_lab = reinterpret_cast<int32_t *>(ctx->d_uf + n);
+    uf_labels_kernel<<<nblk(n, 256), 256, 0, st>>>(ctx->d_uf, d_lab, n);
+    ctx->launches++;
+    TC_CUDA(cudaMemcpyAsync(labels, d_lab, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    TC_CUDA(cudaStreamSynchronize(st));
+    if (n_clusters) {
+        uint32_t c = 0;
+        for (uint32_t v = 0; v < n; v++) c += labels[v] == (int32_t)v;
+        *n_clusters = c;
+    }
+    return 0;
+}
+
+// host: into[] := labels of the union of the two partitions (both label arrays: smallest vertex id of the cluster)
+extern "C" int tc_labels_merge(int32_t *into, const int32_t *other, uint32_t n, uint32_t *n_clusters)
+{
+    TC_CHECK(into && other, "tc_labels_merge: bad arguments");
+    std::vector<int32_t> p(n);
+    std::iota(p.begin(), p.end(), 0);
+    auto find = [&](int32_t x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; };
+    auto unite = [&](int32_t a, int32_t b) { a = find(a); b = find(b); if (a != b) { if (a < b) p[b] = a; else p[a] = b; } };
+    for (uint32_t v = 0; v < n; v++) {
+        TC_CHECK(into[v] >= 0 && (uint32_t)into[v] < n && other[v] >= 0 && (uint32_t)other[v] < n, "tc_labels_merge: label out of range at %u", v);
+        unite((int32_t)v, into[v]); unite((int32_t)v, other[v]);
+    }
+    uint32_t c = 0;
+    for (uint32_t v = 0; v < n; v++) { into[v] = find((int32_t)v); c += into[v] == (int32_t)v; }
+    if (n_clusters) *n_clusters = c;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------ MST driver
 namespace {
 struct HostUF {
@@ -899,6 +1000,83 @@ struct NoSyncPass {                                      // the launchers of the
     ~NoSyncPass() { c->pass_nosync = was; if (c->shadow) c->shadow->pass_nosync = was; }
 };
 }  // namespace
+
+static bool edges_can_grow(tc_ctx *ctx, uint64_t need)
+{
+    if (getenv("TCLUST_EDGE_CAP")) return false;                 // hard limit on the edge buffer
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
+    const uint64_t want = need + need / 64 + 1024;
+    const uint64_t room = (free_b + ctx->edge_cap * sizeof(tc_pair)) / sizeof(tc_pair);
+    return want <= room - room / 8;
+}
+
+// Bounded edge memory: the candidate graph does not fit the edge buffer (a set in which
+// most sketches are related has ~N^2/2 candidate pairs: 60 GB at N = 100k).  The reference never materialises it either:
+// every task of 8 rows reduces its edges to a forest and the forests are merged at the end (src/MST.cpp:1373-1386,
+// 571-572, 1715-1723).  Same identity here, batch-wise: MSF(E1 u E2) = MSF(MSF(E1) u E2).  The work units of the dense
+// pass are launched in batches whose worst-case edge count fits the buffer; whenever the next batch might not fit, the
+// device Boruvka reduces (forest so far + buffered edges) to a forest of <= n-1 edges that stays on the device and the
+// buffer restarts empty.  Exact: the strict order (key, i, j) makes the minimum spanning forest unique.
+static int mst_bounded(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t start_index, std::vector<tc_edge> &mst,
+                       std::vector<int32_t> *comp)
+{
+    const char *impl = getenv("TCLUST_PASS_IMPL");
+    TC_CHECK(!(impl && (!strcmp(impl, "merge") || !strcmp(impl, "join"))),
+             "tc_mst: the candidate edges exceed the edge buffer and TCLUST_PASS_IMPL=%s has no bounded-memory form", impl);
+    const bool force_block = impl && !strcmp(impl, "blockjoin");
+    const bool on_shadow = start_index == 0 && ctx->use_shadow && ctx->shadow;
+    tc_ctx *src = on_shadow ? ctx->shadow : ctx;
+    if (on_shadow) { src->d_edges = ctx->d_edges; src->edge_cap = ctx->edge_cap; src->d_kh_state = ctx->d_kh_state; }
+    if (tc_launch_blockjoin_edges(src, radio, 0, 1, start_index, force_block, true)) return 1;
+    cudaStream_t st = ctx->stream;
+    TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), st));
+    if (tc_k4_reserve(ctx, ctx->n)) return 1;
+    uint64_t count = 0, batches = 0, folds = 0;
+    uint32_t nfin = 0;
+    auto fin_key = [&]() -> const unsigned long long * { return nfin ? ctx->k4.d_fin : nullptr; };
+    auto fin_id = [&]() -> const unsigned long long * { return nfin ? ctx->k4.d_fin + ctx->n : nullptr; };
+    for (int list = 0; list < 2; list++) {
+        const bool blk = list == 0;
+        const size_t nu = blk ? src->kj_units_blk.size() : src->kj_units_old.size();
+        for (size_t u = 0; u < nu;) {
+            size_t u1 = u;
+            uint64_t bound = 0;
+            while (u1 < nu && count + bound + tc_blockjoin_unit_bound(src, blk, u1) <= ctx->edge_cap) bound += tc_blockjoin_unit_bound(src, blk, u1++);
+            if (u1 == u) {
+                TC_CHECK(count > 0, "tc_mst: one work unit of the dense pass can emit %llu candidate edges, more than the edge buffer holds (%llu): raise TCLUST_EDGE_CAP",
+                         (unsigned long long)tc_blockjoin_unit_bound(src, blk, u), (unsigned long long)ctx->edge_cap);
+                if (tc_k4_enqueue(ctx, mode, fin_key(), fin_id(), nfin) || tc_k4_fold(ctx, &nfin)) return 1;
+                count = 0; folds++;
+                continue;
+            }
+            if (tc_blockjoin_run_range(src, radio, start_index, blk, u, u1)) return 1;
+            if (on_shadow) {
+                ctx->d_kh_state = src->d_kh_state;
+                if (tc_shadow_remap_from(ctx, count)) return 1;
+            }
+            unsigned long long cnt[2] = {0, 0};
+            TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, st));
+            TC_CUDA(cudaStreamSynchronize(st));
+            TC_CHECK(cnt[1] == 0 && cnt[0] <= ctx->edge_cap, "tc_mst: a batch of the bounded-memory pass overflowed the edge buffer (%llu > %llu)",
+                     cnt[0], (unsigned long long)ctx->edge_cap);
+            count = cnt[0];
+            u = u1; batches++;
+        }
+    }
+    ctx->launches += src != ctx ? src->launches : 0;
+    if (src != ctx) src->launches = 0;
+    if (tc_k4_enqueue(ctx, mode, fin_key(), fin_id(), nfin)) return 1;
+    uint64_t cnt = 0;
+    bool overflow = false;
+    if (tc_k4_collect(ctx, mode, kmer_size, mst, &cnt, &overflow, comp)) return 1;
+    TC_CHECK(!overflow, "tc_mst: the last batch of the bounded-memory pass overflowed the edge buffer");
+    ctx->n_edges = count; ctx->edges_partial = true;
+    ctx->bounded_batches = batches; ctx->bounded_folds = folds;
+    if (getenv("TCLUST_TIMING")) fprintf(stderr, "[tclust timing] bounded-memory MST: %llu batches, %llu forest reductions, edge buffer %llu entries\n",
+                                         (unsigned long long)batches, (unsigned long long)folds + 1, (unsigned long long)ctx->edge_cap);
+    return 0;
+}
 
 // mode = distance mode of the Boruvka keys; complete = add weight-1 edges between the components that share no
 // hash (the brute-force reference builds the MST of the complete graph).
@@ -914,6 +1092,7 @@ static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t se
     const uint32_t part = ctx->k4.nranks > 1 ? (uint32_t)ctx->k4.rank : 0u, nparts = ctx->k4.nranks > 1 ? (uint32_t)ctx->k4.nranks : 1u;
     std::vector<tc_edge> mst;
     std::vector<int32_t> comp;
+    ctx->bounded_batches = ctx->bounded_folds = 0;
     for (int attempt = 0;; attempt++) {
         uint64_t cnt = 0;
         bool overflow = false;
@@ -930,6 +1109,15 @@ static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t se
         // group the kernel has told every rank, so all of them repeat the (collective) call together.
         TC_CHECK(attempt == 0, "tc_mst: %llu candidate edges exceed the device edge buffer (%llu)",
                  (unsigned long long)cnt, (unsigned long long)ctx->edge_cap);
+        if (cnt > ctx->edge_cap && !edges_can_grow(ctx, cnt)) {
+            // no room for the whole candidate graph: build the MST in bounded edge memory instead
+            TC_CHECK(nparts == 1, "tc_mst: rank %u of the multi-GPU group cannot hold its %llu candidate edges (buffer %llu)", part,
+                     (unsigned long long)cnt, (unsigned long long)ctx->edge_cap);
+            TC_CHECK(semb_size == 0 && !edges_only, "tc_mst: %llu candidate edges exceed the device edge buffer (%llu)",
+                     (unsigned long long)cnt, (unsigned long long)ctx->edge_cap);
+            if (mst_bounded(ctx, kmer_size, mode, radio, start_index, mst, complete ? &comp : nullptr)) return 1;
+            break;
+        }
         if (cnt > ctx->edge_cap && ensure_edges(ctx, cnt)) return 1;      // (in a group: only the ranks that overflowed grow)
     }
     auto by_weight = [](const tc_edge &x, const tc_edge &y) {

@@ -76,6 +76,7 @@ struct Options {
     bool dense = false, newick = false, phylip = false, nexus = false, linkage = false;
     double threshold = 0.05;
     int kmer = 19, sketch_size = 1000, compress = 1000, drlevel = 3, device = 0;
+    bool threshold_only = false;   // --threshold-only: clusters at -d without building / saving the MST (tc_cluster_threshold)
     int gpus = 1;                 // --gpus G: devices device .. device+G-1 build the MST together (multi-GPU group of the library)
     uint64_t min_len = 10000;
 };
@@ -944,6 +945,54 @@ void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_fi
     cerr << "========time of greedyCluster is: " << now_s() - t2 << "========" << endl;
     (void)save; (void)folder;
 #else
+    if (o.threshold_only) {
+        // connected components of the candidate pairs within the threshold, straight from the dense pass
+        // (device union-find epilogue; no edge list, no MST, O(n) memory).  Same partition and cluster order (by smallest
+        // member id) as the MST route; members are listed in ascending id order instead of BFS order.
+        const uint32_t n = (uint32_t)g.size();
+        vector<int32_t> labels(n);
+        uint32_t nc = 0;
+        if (o.gpus > 1) {
+            const int G = o.gpus;
+            vector<tc_ctx *> cs(G, nullptr);
+            cs[0] = ctx;
+            for (int r = 1; r < G; r++) tc_or_die(tc_ctx_create(o.device + r, &cs[r]), "tc_ctx_create (--gpus)");
+            vector<vector<int32_t>> part(G, vector<int32_t>(n));
+            vector<string> errs(G);
+            vector<std::thread> th;
+            for (int r = 0; r < G; r++)
+                th.emplace_back([&, r]() {
+                    if (r > 0) {
+                        vector<const uint64_t *> rows(n);
+                        vector<uint64_t> sizes(n);
+                        for (size_t i = 0; i < n; i++) { rows[i] = g[i].hashes.data(); sizes[i] = g[i].hashes.size(); }
+                        if (tc_sketches_upload_rows(cs[r], rows.data(), sizes.data(), n)) { errs[r] = string("sketch upload, ") + tc_last_error(); return; }
+                    }
+                    if (tc_cluster_threshold(cs[r], o.kmer, o.containment, o.threshold, (uint32_t)r, (uint32_t)G, part[r].data(), nullptr))
+                        errs[r] = string("threshold clustering, ") + tc_last_error();
+                });
+            for (std::thread &t : th) t.join();
+            for (int r = 0; r < G; r++) if (!errs[r].empty()) die("GPU " + std::to_string(o.device + r) + ": " + errs[r]);
+            for (int r = 1; r < G; r++) tc_ctx_destroy(cs[r]);
+            labels = part[0];
+            for (int r = 1; r < G; r++) tc_or_die(tc_labels_merge(labels.data(), part[r].data(), n, &nc), "label merge");
+            if (G == 1) for (uint32_t v = 0; v < n; v++) nc += labels[v] == (int32_t)v;
+        } else
+            tc_or_die(tc_cluster_threshold(ctx, o.kmer, o.containment, o.threshold, 0, 1, labels.data(), &nc), "threshold clustering");
+        cerr << "========time of generateMST is: " << now_s() - t2 << "========" << endl;
+        vector<int> cid(n, -1);
+        vector<vector<int>> cluster;
+        for (uint32_t v = 0; v < n; v++) {
+            const int32_t l = labels[v];                // smallest id of the cluster: it is met first
+            if (cid[l] < 0) { cid[l] = (int)cluster.size(); cluster.emplace_back(); }
+            cluster[cid[l]].push_back((int)v);
+        }
+        print_result(cluster, g, by_file, o.output, o.threshold);
+        cerr << "-----write the cluster result into: " << o.output << endl;
+        cerr << "-----the cluster number of: " << o.output << " is: " << cluster.size() << endl;
+        (void)save; (void)folder;
+        return;
+    }
     vector<tc_edge> mst(g.size());
     uint64_t m = 0;
     const double t_mst = now_s();
@@ -1052,7 +1101,7 @@ void usage(const char *prog)
             " | --premsted DIR"
 #endif
             ") [--append FILE] [--fast [--drlevel N]] [--dense]\n"
-            "          [--newick-tree] [--phylip-tree] [--nexus-tree] [--linkage-matrix] [--device N] [--gpus G]\n", prog);
+            "          [--newick-tree] [--phylip-tree] [--nexus-tree] [--linkage-matrix] [--device N] [--gpus G] [--threshold-only]\n", prog);
 }
 
 }  // namespace
@@ -1089,6 +1138,7 @@ int main(int argc, char **argv)
         else if (f == "--drlevel") o.drlevel = atoi(need("--drlevel"));
         else if (f == "--device") o.device = atoi(need("--device"));
         else if (f == "--gpus") o.gpus = atoi(need("--gpus"));
+        else if (f == "--threshold-only") o.threshold_only = true;
         else if (f == "-h" || f == "--help") { usage(argv[0]); return 0; }
         else { usage(argv[0]); die("unsupported option " + f + " (see DESIGN.md: out of scope for the B200 hot-path build)"); }
     }

@@ -301,3 +301,17 @@ def test_clust_mst_gpus_flag(genomes, tmp_path):
     for name in ("edge.mst", "hash.sketch", "mst.ani", "mst.dense"):
         assert _same_bytes(os.path.join(f1, name), os.path.join(fg, name)), name
     assert open(str(tmp_path / "one" / "out.txt")).read() == open(str(tmp_path / "many" / "out.txt")).read()
+
+
+def test_clust_mst_threshold_only(genomes, tmp_path):
+    """clust-mst --threshold-only: same clusters (and cluster order, by smallest member) as the MST route, no edge.mst."""
+    lst, _ = genomes
+    args = ["-l", "-i", lst, "-k", "21", "-d", "0.05", "-s", "1000"]
+    f1, _ = _run(os.path.join(OURS, "clust-mst"), args + ["-o", "mst.txt"], str(tmp_path / "a"))
+    f2, _ = _run(os.path.join(OURS, "clust-mst"), args + ["-o", "thr.txt", "--threshold-only"], str(tmp_path / "b"))
+    a, b = str(tmp_path / "a" / "mst.txt"), str(tmp_path / "b" / "thr.txt")
+    assert _partition(a) == _partition(b)
+    first = lambda p: [min(i for i, _ in c) for c in sketch_io.parse_cluster_file(p)]
+    assert first(a) == first(b)
+    assert open(a).read().splitlines()[:3] == open(b).read().splitlines()[:3]
+    assert os.path.exists(os.path.join(f1, "edge.mst")) and not os.path.exists(os.path.join(f2, "edge.mst"))

@@ -181,3 +181,64 @@ def test_group_on_all_gpus(tc, oracle):
         single = c.mst(21, 0.05)
     for r in range(g):
         assert np.array_equal(single, res[r]), r
+
+
+def _labels_partition(lab):
+    out = {}
+    for v, l in enumerate(np.asarray(lab).tolist()):
+        out.setdefault(l, []).append(v)
+    return sorted(out.values())
+
+
+@pytest.mark.parametrize("containment", [False, True])
+def test_cluster_threshold_equals_mst_cut(tc, oracle, containment):
+    """tc_cluster_threshold (union-find epilogue of the dense pass, no edges, no MST) = the partition the reference cuts
+    out of its MST at the threshold; labels are smallest ids; parts of a sharded run merge to the same partition."""
+    sk = synth.family_sketches(7, 15, s=500, seed=31) + _graphy_sketches(5, n=150)
+    n = len(sk)
+    for thr in (0.02, 0.05, 0.3):
+        ref = oracle.mst(sk, 21, thr, containment)
+        _, lab_ref, _ = oracle.clusters_from_mst(ref, n, thr)
+        with tc.Context(0) as c:
+            c.upload(sk)
+            nc, lab = c.cluster_threshold(21, thr, containment)
+            parts = [c.cluster_threshold(21, thr, containment, p, 3)[1] for p in range(3)]
+            with pytest.raises(tc.TclustError, match="part of the candidate pairs"):
+                c.dense_ani(21, containment)
+        assert _labels_partition(lab) == _labels_partition(lab_ref), thr
+        assert nc == len(set(lab.tolist()))
+        assert all(min(m) == l for l, m in zip(sorted(set(lab.tolist())), sorted(_labels_partition(lab)))), "labels are smallest ids"
+        merged = parts[0]
+        for p in parts[1:]:
+            ncm, merged = tc.labels_merge(merged, p)
+        assert np.array_equal(merged, lab) and ncm == nc
+
+
+@pytest.mark.parametrize("order", ["family", "shuffled"])
+def test_bounded_memory_mst(tc, order, monkeypatch):
+    """A candidate graph that does not fit the edge buffer (TCLUST_EDGE_CAP): the pass runs in batches, Boruvka folds every
+    full buffer into a forest that stays on the device; the MST is the one of the unbounded build, edge for edge."""
+    h, off = synth.family_sketches_fast(3, 800, s=200, seed=23)          # three big families: ~9.6e5 candidate pairs
+    n = len(off) - 1
+    if order == "shuffled":
+        perm = np.random.default_rng(9).permutation(n)
+        h = np.ascontiguousarray(h.reshape(n, 200)[perm].reshape(-1))
+        monkeypatch.setenv("TCLUST_REORDER", "1")                        # run on the reordered copy (edge ids are mapped back per batch)
+    with tc.Context(0) as c:
+        c.upload(hashes=h, off=off)
+        want = c.mst(21, 0.05).copy()
+        assert c.mst_stats()["bounded_batches"] == 0 and c.mst_stats()["edges"] > 300000
+    monkeypatch.setenv("TCLUST_EDGE_CAP", str(32 * n * 2))               # two whole-row units per batch at most
+    with tc.Context(0) as c:
+        c.upload(hashes=h, off=off)
+        got = c.mst(21, 0.05).copy()
+        st = c.mst_stats()
+        with pytest.raises(tc.TclustError, match="TCLUST_EDGE_CAP"):
+            c.allpairs_pass(tc.radio(0.05, 21))                           # the full candidate list itself cannot be held
+    assert st["bounded_batches"] >= 3 and st["bounded_folds"] >= 2, st
+    assert np.array_equal(got, want)
+    monkeypatch.setenv("TCLUST_EDGE_CAP", "1000")
+    with tc.Context(0) as c:
+        c.upload(hashes=h, off=off)
+        with pytest.raises(tc.TclustError, match="one work unit"):
+            c.mst(21, 0.05)
