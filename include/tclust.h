@@ -277,6 +277,15 @@ int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, double thresh
  * per-pair common_min, the representative with the largest Jaccard wins, ties -> first in `touched` order. */
 int tc_greedy_cluster_kssd(tc_ctx *ctx, int kmer_size, double threshold, int32_t *rep_of, uint32_t *n_clusters);
 
+/* The same two rules with the representative scan sharded over several GPUs (the outer loop over the
+ * genomes is serial, the scan of one batch against the representatives is not): ctxs[0..nctx) are contexts, one per
+ * device, that all hold the SAME uploaded sketch set; representative number c is kept by context c mod nctx, every
+ * context scans the batch against its share on its own host thread (the j-parallel loop of greedy.cpp:1136-1336 across
+ * devices), the candidates are merged on the host and the serial replay is the single-GPU one -- the result does not
+ * depend on nctx.  kssd != 0: the rule of tc_greedy_cluster_kssd (containment ignored).  One caller thread. */
+int tc_greedy_cluster_multi(tc_ctx *const *ctxs, int nctx, int kmer_size, int containment, double threshold, int kssd,
+                            int32_t *rep_of, uint32_t *n_clusters);
+
 /* brute-force greedyCluster (src/greedy.cpp:285-351) with one thread: genome j joins the nearest representative
  * with MinHash::distance (containment: containDistance) <= threshold, ties -> the earliest-created one; else it
  * becomes a representative.  threshold < 1. */

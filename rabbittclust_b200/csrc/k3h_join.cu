@@ -1026,6 +1026,238 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
     }
 }
 
+// =====================================================================================================
+// K3S  k3s_tile_kernel -- the flagged tiles of sparsely related row blocks, one tile per CTA, union lists staged with TMA.
+//
+// With the tile flags (k3t_tileflags.cu) a row block of a family-structured set shares ranks with a handful of column
+// blocks.  K3J still pays a table build, a scan of the flag row and CTA-wide barriers per row block and runs the few
+// dense tiles of a unit one after the other (ncu: `barrier` the top stall, 16 us per tile).  Here the work item is the
+// flagged TILE: a CTA of 8 warps stages the two union lists of the tile -- ascending distinct ranks + 32-bit member
+// masks of the row block and of the column block, ~1,300 entries each for related sketches -- into shared memory with
+// four TMA bulk copies (cp.async.bulk.shared::cluster.global, completion on an mbarrier), intersects them (the column
+// keys are looked up in the row list by a branch-free binary search in shared memory; both lists are sorted and
+// duplicate-free), and accumulates count[r][c] += popc(rows holding key & columns holding key) exactly as K3J does.
+// No hash table, no partitions (a list that does not fit is the host's cue to route the row to K3J), three CTAs per SM
+// overlap each other's copies.  Same epilogue (candidate edge / union-find) and the same `common` for every pair.
+constexpr uint32_t KS_THREADS = 256, KS_WARPS = KS_THREADS / 32;
+constexpr uint32_t KS_RCAP = 4096;                                   // longest row-block list a tile can stage
+constexpr uint32_t KS_CCHUNK = 2048;                                 // column list entries per stage
+constexpr uint32_t KS_ROW_MAX_TILES = 64;                            // rows with more flagged tiles stay on K3J (table amortised)
+constexpr size_t KS_SMEM = (size_t)(KS_RCAP + 4) * 8 + (size_t)(KS_CCHUNK + 4) * 8 + (size_t)KS_WARPS * KJ_TILE_WORDS * 4 + 64;
+
+__device__ __forceinline__ void ks_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ks_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ks_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// TMA bulk copy global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on the mbarrier
+__device__ __forceinline__ void ks_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// row `row` of a finished tile (rb, cb): candidate edge / union for column j = cb*32 + lane (the K3J epilogue with the
+// row sizes read from global memory)
+__device__ __forceinline__ void ks_emit_row(const KHArgs &a, uint32_t rb, uint32_t row, uint32_t cb, uint32_t lane, uint32_t c)
+{
+    const uint32_t i = rb * 32 + row, j = cb * 32 + lane;
+    bool keep = false;
+    if (c >= 1u && i < a.n && i >= a.row_min && j < i) {
+        const uint32_t s0 = a.size[i], s1 = a.size[j];
+        const uint32_t mn = min(s0, s1), mx = max(s0, s1);
+        keep = mn > 0 && !((long long)mx > (long long)a.radio * (long long)mn);   // MST.cpp:1481-1487
+        if (a.uf && keep) { kh_uf_edge(a, i, j, c, s0, s1); keep = false; }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    if (ballot) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) {
+            const unsigned long long idx = base + __popc(ballot & ((1u << lane) - 1));
+            if (idx < a.edge_cap) {
+                tc_pair e; e.i = i; e.j = j; e.common = c;
+                a.edges[idx] = e;
+            } else {
+                a.counters[1] = 1ULL;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(KS_THREADS, 3) k3s_tile_kernel(const KHArgs a, const uint2 *tiles, const uint32_t *ntiles_dev,
+                                                               uint32_t t_begin, uint32_t t_end)
+{
+    extern __shared__ __align__(128) uint8_t ks_smem[];
+    uint32_t *rkeys = reinterpret_cast<uint32_t *>(ks_smem);
+    uint32_t *rmask = rkeys + (KS_RCAP + 4);
+    uint32_t *ckeys = rmask + (KS_RCAP + 4);
+    uint32_t *cmask = ckeys + (KS_CCHUNK + 4);
+    uint32_t *cnt_all = cmask + (KS_CCHUNK + 4);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(cnt_all + KS_WARPS * KJ_TILE_WORDS);
+    __shared__ uint32_t s_tile;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_r = (uint32_t)__cvta_generic_to_shared(&bars[0]), bar_c = (uint32_t)__cvta_generic_to_shared(&bars[1]);
+    const uint32_t rkeys_s = (uint32_t)__cvta_generic_to_shared(rkeys), rmask_s = (uint32_t)__cvta_generic_to_shared(rmask);
+    const uint32_t ckeys_s = (uint32_t)__cvta_generic_to_shared(ckeys), cmask_s = (uint32_t)__cvta_generic_to_shared(cmask);
+    uint32_t *cntw = cnt_all + warp * KJ_TILE_WORDS;
+    uint16_t *cnt = reinterpret_cast<uint16_t *>(cntw);
+    if (tid == 0) {
+        ks_mbar_init(bar_r, 1); ks_mbar_init(bar_c, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t par_r = 0, par_c = 0;
+    const uint32_t t_lim = min(t_end, *ntiles_dev);
+
+    for (;;) {
+        if (tid == 0) s_tile = t_begin + (uint32_t)atomicAdd(&a.counters[2], 1ULL);
+        __syncthreads();
+        const uint32_t t = s_tile;
+        if (t >= t_lim) break;
+        const uint2 tl = tiles[t];
+        const uint32_t rb = tl.x, cb = tl.y;
+        const uint32_t Dr = a.bu_count[rb * KH_DREC], Dc = a.bu_count[cb * KH_DREC];
+        const bool live = Dr > 0 && Dc > 0 && rb * 32 + 31 >= a.row_min;
+        const unsigned long long rel = a.off[rb * 32], cel = a.off[cb * 32];
+        const uint32_t lead_r = (uint32_t)(rel & 3ull), lead_c = (uint32_t)(cel & 3ull);   // bulk copies start 16-byte aligned
+        if (live && tid == 0) {
+            const uint32_t bytes = ((lead_r + Dr + 3u) & ~3u) * 4u;
+            ks_mbar_expect_tx(bar_r, 2u * bytes);
+            ks_bulk_g2s(rkeys_s, a.bu_keys + (rel - lead_r), bytes, bar_r);
+            ks_bulk_g2s(rmask_s, a.bu_mask + (rel - lead_r), bytes, bar_r);
+        }
+        if (live) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) cntw[lane + 32 * q] = 0u;
+        }
+        uint32_t anyhit = 0;
+        const uint32_t *rk = rkeys + lead_r, *rm = rmask + lead_r;
+        uint32_t top = 1;                                        // largest power of two <= Dr
+        while (live && top * 2 <= Dr) top *= 2;
+        for (uint32_t c0 = 0; live && c0 < Dc; c0 += KS_CCHUNK) {
+            const uint32_t len = min(KS_CCHUNK, Dc - c0);
+            if (tid == 0) {
+                const uint32_t bytes = ((lead_c + len + 3u) & ~3u) * 4u;
+                ks_mbar_expect_tx(bar_c, 2u * bytes);
+                ks_bulk_g2s(ckeys_s, a.bu_keys + (cel - lead_c + c0), bytes, bar_c);
+                ks_bulk_g2s(cmask_s, a.bu_mask + (cel - lead_c + c0), bytes, bar_c);
+            }
+            if (c0 == 0) { ks_mbar_wait(bar_r, par_r); par_r ^= 1u; }
+            ks_mbar_wait(bar_c, par_c); par_c ^= 1u;
+            const uint32_t *ck = ckeys + lead_c, *cm = cmask + lead_c;
+            const uint32_t rlo = rk[0], rhi = rk[Dr - 1];
+            for (uint32_t g = warp * 32; g < len; g += KS_WARPS * 32) {
+                const uint32_t k = g + lane;
+                const uint32_t x = k < len ? ck[k] : 0xFFFFFFFFu;
+                uint32_t mk = 0u;
+                if (__any_sync(0xffffffffu, x >= rlo && x <= rhi)) {
+                    // number of row keys < x: branch-free lower bound, the same trip count for every lane
+                    uint32_t lo = 0;
+                    for (uint32_t step = top; step; step >>= 1) {
+                        const uint32_t nx = lo + step;
+                        if (nx <= Dr && rk[nx - 1] < x) lo = nx;
+                    }
+                    if (lo < Dr && rk[lo] == x) mk = rm[lo];
+                }
+                unsigned hit = __ballot_sync(0xffffffffu, mk != 0u);
+                if (!hit) continue;
+                anyhit = 1u;
+                const uint32_t cmk = mk ? cm[k] : 0u;
+                if (__popc(hit) <= 2) {
+                    while (hit) {                         // few hits: count[r][c]++ for r in rows, c = lane
+                        const int src = __ffs(hit) - 1;
+                        uint32_t rmv = __shfl_sync(0xffffffffu, mk, src);
+                        const uint32_t cmv = __shfl_sync(0xffffffffu, cmk, src);
+                        const bool mine = (cmv >> lane) & 1u;
+                        while (rmv) {
+                            const int r = __ffs(rmv) - 1;
+                            if (mine) cnt[r * 32 + lane]++;
+                            rmv &= rmv - 1;
+                        }
+                        hit &= hit - 1;
+                    }
+                } else {
+                    // many hits: transpose the 32 keys' masks with ballots (mycols: keys held by column `lane`; per row r
+                    // the keys held by row r) and add popcounts
+                    uint32_t mycols = 0;
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const unsigned bb = __ballot_sync(0xffffffffu, (cmk >> c) & 1u);
+                        if (lane == (uint32_t)c) mycols = bb;
+                    }
+                    uint32_t rows_any = mk;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) rows_any |= __shfl_xor_sync(0xffffffffu, rows_any, o);
+                    while (rows_any) {
+                        const int r = __ffs(rows_any) - 1;
+                        const unsigned rkb = __ballot_sync(0xffffffffu, (mk >> r) & 1u);
+                        const uint32_t add = __popc(rkb & mycols);
+                        if (add) cnt[r * 32 + lane] += (uint16_t)add;
+                        rows_any &= rows_any - 1;
+                    }
+                }
+            }
+            __syncthreads();                  // every warp is done with this stage's column entries
+        }
+        if (__syncthreads_or((int)anyhit)) {
+            // warp w finishes rows 4w .. 4w+3: sum over the 8 warps' counter sets, then the epilogue
+#pragma unroll 1
+            for (uint32_t r = warp * 4; r < warp * 4 + 4; r++) {
+                uint32_t total = 0;
+#pragma unroll
+                for (uint32_t v = 0; v < KS_WARPS; v++) total += reinterpret_cast<const uint16_t *>(cnt_all + v * KJ_TILE_WORDS)[r * 32 + lane];
+                ks_emit_row(a, rb, r, cb, lane, total);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// flagged tiles of the units routed to K3S, compacted into a device list (one warp per unit; slots reserved with one
+// atomic per 1024 column blocks)
+__global__ void k3s_list_kernel(const tc_kh_unit *units, uint32_t nunits, const uint32_t *flags, uint32_t words, uint2 *tiles,
+                                uint32_t *ntiles, uint32_t cap)
+{
+    const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (u >= nunits) return;
+    const tc_kh_unit un = units[u];
+    const uint32_t cb0 = un.c0 / 32, cb1 = (un.c1 + 31) / 32;       // column blocks [cb0, cb1)
+    const uint32_t *row = flags + (size_t)un.rb * words;
+    for (uint32_t w0 = cb0 >> 5; w0 * 32 < cb1; w0 += 32) {
+        const uint32_t wi = w0 + lane;
+        uint32_t v = wi * 32 < cb1 ? row[wi] : 0u;
+        if (wi == (cb0 >> 5) && (cb0 & 31)) v &= ~((1u << (cb0 & 31)) - 1u);
+        if (wi * 32 + 32 > cb1 && wi * 32 < cb1) v &= (cb1 & 31) ? ((1u << (cb1 & 31)) - 1u) : 0xFFFFFFFFu;
+        const uint32_t pc = __popc(v);
+        uint32_t incl = pc;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += y; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (!total) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ntiles, total);
+        base = __shfl_sync(0xffffffffu, base, 0) + incl - pc;
+        while (v) {
+            const uint32_t b = (uint32_t)__ffs(v) - 1u;
+            if (base < cap) tiles[base] = make_uint2(un.rb, wi * 32 + b);
+            base++;
+            v &= v - 1u;
+        }
+    }
+}
+
 // ---- per-upload setup: partition pivots of every row block
 int tc_kh_prepare(tc_ctx *ctx)
 {
@@ -1045,13 +1277,13 @@ int tc_kh_prepare(tc_ctx *ctx)
         ctx->attr_set |= 1u;
     }
     // union lists of the 32-sketch blocks (K3J): as many slots as elements
-    if (ctx->total + 1 > ctx->cap_bu) {
+    if (ctx->total + 8 > ctx->cap_bu) {      // + 8: K3S copies whole 16-byte quads, up to 3 entries past a list's end
         cudaFree(ctx->d_bu_keys); cudaFree(ctx->d_bu_mask);
         ctx->d_bu_keys = nullptr; ctx->d_bu_mask = nullptr; ctx->cap_bu = 0;
-        if (cudaMalloc(&ctx->d_bu_keys, (ctx->total + 1) * 4) != cudaSuccess || cudaMalloc(&ctx->d_bu_mask, (ctx->total + 1) * 4) != cudaSuccess) {
+        if (cudaMalloc(&ctx->d_bu_keys, (ctx->total + 8) * 4) != cudaSuccess || cudaMalloc(&ctx->d_bu_mask, (ctx->total + 8) * 4) != cudaSuccess) {
             tc_set_error("tc_kh_prepare: out of device memory for the block union lists"); return 1;
         }
-        ctx->cap_bu = ctx->total + 1;
+        ctx->cap_bu = ctx->total + 8;
     }
     TC_CHECK(ctx->d_multi, "tc_kh_prepare: no multiplicity bitmap");
     const char *sort_env = getenv("TCLUST_DISTINCT_SORT");       // "plain": one pass per stride (the first version)
@@ -1316,6 +1548,34 @@ static uint32_t kj_pick_cseg(uint32_t n, uint32_t start_index, uint32_t nparts, 
     return KH_CSEG;
 }
 
+// tiles [t0, t1) of this context's sparse tile list on K3S
+static int ks_launch(tc_ctx *ctx, int radio, uint32_t start_index, uint32_t t0, uint32_t t1, bool record_start)
+{
+    if (ctx->ks_ntiles_host == 0 || t0 >= ctx->ks_ntiles_host) return 0;
+    if (!(ctx->attr_set & 4u)) {
+        TC_CUDA(cudaFuncSetAttribute(k3s_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMEM));
+        ctx->attr_set |= 4u;
+    }
+    KHArgs a{};
+    a.mode = KH_MODE_EDGES; a.part = 0; a.nparts = 1; a.row_min = start_index;
+    a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
+    a.ranks = ctx->d_ranks; a.off = reinterpret_cast<const unsigned long long *>(ctx->d_off); a.size = ctx->d_size; a.n = ctx->n;
+    a.counters = ctx->d_edge_count;
+    a.bu_keys = ctx->d_bu_keys; a.bu_mask = ctx->d_bu_mask; a.bu_count = ctx->d_bu_count; a.multi = ctx->d_multi;
+    a.uf = nullptr; a.uf_perm = nullptr; a.uf_jmin = 2.0;
+    if (ctx->uf_parent) { a.uf = ctx->uf_parent; a.uf_perm = ctx->uf_perm; a.uf_jmin = ctx->uf_jmin; a.containment = ctx->uf_containment; }
+    const uint32_t cnt = std::min(t1, ctx->ks_ntiles_host) - t0;
+    const int grid = (int)std::min<uint64_t>(cnt, (uint64_t)ctx->num_sms * 3);
+    TC_CUDA(cudaMemsetAsync(ctx->d_edge_count + 2, 0, sizeof(unsigned long long), ctx->stream));
+    if (ctx->ev_pass0 && record_start) cudaEventRecord(ctx->ev_pass0, ctx->stream);
+    k3s_tile_kernel<<<grid, KS_THREADS, KS_SMEM, ctx->stream>>>(a, static_cast<const uint2 *>(ctx->d_ks_tiles), ctx->d_ks_count, t0, t1);
+    if (ctx->ev_pass1) cudaEventRecord(ctx->ev_pass1, ctx->stream);
+    ctx->launches++;
+    TC_CUDA(cudaGetLastError());
+    if (!ctx->pass_nosync) TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index, bool force_block, bool plan_only)
 {
     // the unit list (also what tc_allpairs_pass counts pairs from), split by kernel
@@ -1323,11 +1583,21 @@ int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t np
     // the routing of this rank's units is decided once per (sketch set, start_index, part) and kept on the device
     const uint64_t key = ((uint64_t)part << 40) ^ ((uint64_t)(nparts ? nparts : 1) << 33) ^ ((uint64_t)start_index << 1) ^ (force_block ? 1u : 0u);
     if (!ctx->kj_split_valid || ctx->kj_split_key != key) {
-        std::vector<tc_kh_unit> &blk = ctx->kj_units_blk, &old = ctx->kj_units_old;
-        blk.clear(); old.clear();
+        std::vector<tc_kh_unit> &blk = ctx->kj_units_blk, &old = ctx->kj_units_old, &sps = ctx->ks_units;
+        blk.clear(); old.clear(); sps.clear();
         const KjRouting route(ctx);
+        // K3S takes the units of row blocks that share ranks with few column blocks (tile flags) and whose own list can be
+        // staged; sets with a block too large for a union list keep everything on K3J / K3H (TCLUST_K3S=0: never)
+        const char *ks_env = getenv("TCLUST_K3S");
+        const bool ks_on = ctx->tile_words && !force_block && route.unlisted.back() == 0 && !(ks_env && !strcmp(ks_env, "0"));
+        uint64_t ks_cap = 0;
         for (size_t u = part; u < ctx->kh_edge_units.size(); u += (nparts ? nparts : 1)) {
             const tc_kh_unit &un = ctx->kh_edge_units[u];
+            if (ks_on && un.rb < ctx->tile_rowcount.size() && ctx->tile_rowcount[un.rb] < KS_ROW_MAX_TILES && ctx->bu_count[un.rb] <= KS_RCAP) {
+                sps.push_back(un);
+                ks_cap += std::min<uint64_t>(ctx->tile_rowcount[un.rb], (un.c1 - un.c0 + 31) / 32 + 1);
+                continue;
+            }
             if (route.listed(un) && (force_block || route.pays(ctx, un))) {
                 // a partitioned row block keeps 2 KB of state per tile between its partitions: units of KJ_CSEG_MAX columns
                 const uint32_t w = ctx->kh_parts[un.rb] > 1 ? KJ_CSEG_MAX : un.c1 - un.c0;
@@ -1345,39 +1615,74 @@ int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t np
             return (uint64_t)ctx->tile_rowcount[x.rb] * 32 * w / ((uint64_t)x.rb * 32 + 32) + 1;
         };
         std::stable_sort(blk.begin(), blk.end(), [&](const tc_kh_unit &x, const tc_kh_unit &y) { return weight(x) > weight(y); });
-        if (blk.size() + old.size() > ctx->kj_units_cap || !ctx->d_kj_units) {
+        const size_t all_units = blk.size() + old.size() + sps.size();
+        if (all_units > ctx->kj_units_cap || !ctx->d_kj_units) {
             cudaFree(ctx->d_kj_units);
             ctx->d_kj_units = nullptr; ctx->kj_units_cap = 0;
-            TC_CUDA(cudaMalloc(&ctx->d_kj_units, std::max<size_t>(blk.size() + old.size(), 1) * sizeof(tc_kh_unit)));
-            ctx->kj_units_cap = blk.size() + old.size();
+            TC_CUDA(cudaMalloc(&ctx->d_kj_units, std::max<size_t>(all_units, 1) * sizeof(tc_kh_unit)));
+            ctx->kj_units_cap = all_units;
         }
         if (!blk.empty()) TC_CUDA(cudaMemcpy(ctx->d_kj_units, blk.data(), blk.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice));
         if (!old.empty()) TC_CUDA(cudaMemcpy(ctx->d_kj_units + blk.size(), old.data(), old.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice));
+        ctx->ks_ntiles_host = 0;
+        if (!sps.empty()) {
+            // the tile list of the sparse rows: filled on the device from the flag rows, its length stays on the device
+            tc_kh_unit *d_sps = ctx->d_kj_units + blk.size() + old.size();
+            TC_CUDA(cudaMemcpy(d_sps, sps.data(), sps.size() * sizeof(tc_kh_unit), cudaMemcpyHostToDevice));
+            if (ks_cap + 1 > ctx->cap_ks_tiles || !ctx->d_ks_tiles) {
+                cudaFree(ctx->d_ks_tiles); ctx->d_ks_tiles = nullptr; ctx->cap_ks_tiles = 0;
+                TC_CUDA(cudaMalloc(&ctx->d_ks_tiles, (ks_cap + 1) * sizeof(uint2)));
+                ctx->cap_ks_tiles = ks_cap + 1;
+            }
+            if (!ctx->d_ks_count) TC_CUDA(cudaMalloc(&ctx->d_ks_count, 2 * sizeof(uint32_t)));
+            TC_CUDA(cudaMemsetAsync(ctx->d_ks_count, 0, 2 * sizeof(uint32_t), ctx->stream));
+            k3s_list_kernel<<<(unsigned)((sps.size() * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+                d_sps, (uint32_t)sps.size(), ctx->d_tile_flags, ctx->tile_words, static_cast<uint2 *>(ctx->d_ks_tiles), ctx->d_ks_count,
+                (uint32_t)std::min<uint64_t>(ks_cap + 1, 0xFFFFFFFFull));
+            ctx->launches++;
+            TC_CUDA(cudaGetLastError());
+            uint32_t h_cnt = 0;
+            TC_CUDA(cudaMemcpyAsync(&h_cnt, ctx->d_ks_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            TC_CUDA(cudaStreamSynchronize(ctx->stream));
+            TC_CHECK(h_cnt <= ks_cap + 1, "tc_allpairs_pass: sparse tile list overflow (%u > %llu)", h_cnt, (unsigned long long)ks_cap + 1);
+            ctx->ks_ntiles_host = h_cnt;
+        }
         ctx->kj_split_key = key; ctx->kj_split_valid = true;
     }
     if (plan_only) return 0;
+    if (ks_launch(ctx, radio, start_index, 0, 0xFFFFFFFFu, true)) return 1;
     KHArgs a{};
     a.mode = KH_MODE_EDGES; a.part = 0; a.nparts = 1; a.row_min = start_index;   // the lists already hold this part only
     a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
-    if (kh_launch(ctx, a, ctx->kj_units_blk, false, true, true, ctx->d_kj_units)) return 1;
-    return kh_launch(ctx, a, ctx->kj_units_old, false, false, ctx->kj_units_blk.empty(), ctx->d_kj_units + ctx->kj_units_blk.size());
+    const bool first = ctx->ks_ntiles_host == 0;
+    if (kh_launch(ctx, a, ctx->kj_units_blk, false, true, first, ctx->d_kj_units)) return 1;
+    return kh_launch(ctx, a, ctx->kj_units_old, false, false, first && ctx->kj_units_blk.empty(), ctx->d_kj_units + ctx->kj_units_blk.size());
 }
 
-// ---- the same pass piece by piece (bounded edge memory, tclust_api.cu mst_bounded): units [u0, u1) of this context's
-// block-join list (block_list) or hash-join list, after tc_launch_blockjoin_edges(..., plan_only = true)
-int tc_blockjoin_run_range(tc_ctx *ctx, int radio, uint32_t start_index, bool block_list, size_t u0, size_t u1)
+// ---- the same pass piece by piece (bounded edge memory, tclust_api.cu mst_bounded), after
+// tc_launch_blockjoin_edges(..., plan_only = true): items [u0, u1) of list 0 = sparse tiles (K3S), 1 = block-join units
+// (K3J), 2 = hash-join units (K3H)
+size_t tc_blockjoin_list_size(const tc_ctx *ctx, int list)
 {
+    return list == 0 ? ctx->ks_ntiles_host : list == 1 ? ctx->kj_units_blk.size() : ctx->kj_units_old.size();
+}
+
+int tc_blockjoin_run_range(tc_ctx *ctx, int radio, uint32_t start_index, int list, size_t u0, size_t u1)
+{
+    if (list == 0) return ks_launch(ctx, radio, start_index, (uint32_t)u0, (uint32_t)u1, true);
     KHArgs a{};
     a.mode = KH_MODE_EDGES; a.part = 0; a.nparts = 1; a.row_min = start_index;
     a.edges = ctx->d_edges; a.edge_cap = ctx->edge_cap; a.radio = radio;
-    if (block_list) return kh_launch(ctx, a, ctx->kj_units_blk, false, true, true, ctx->d_kj_units, u0, u1);
+    if (list == 1) return kh_launch(ctx, a, ctx->kj_units_blk, false, true, true, ctx->d_kj_units, u0, u1);
     return kh_launch(ctx, a, ctx->kj_units_old, false, false, true, ctx->d_kj_units + ctx->kj_units_blk.size(), u0, u1);
 }
 
-// most candidate edges unit u of that list can emit: 32 rows x its columns, or 1024 per flagged tile of a whole-row unit
-uint64_t tc_blockjoin_unit_bound(const tc_ctx *ctx, bool block_list, size_t u)
+// most candidate edges item u of that list can emit: a tile 1024; a unit 32 rows x its columns, or 1024 per flagged tile
+// of a whole-row unit
+uint64_t tc_blockjoin_unit_bound(const tc_ctx *ctx, int list, size_t u)
 {
-    const tc_kh_unit &x = block_list ? ctx->kj_units_blk[u] : ctx->kj_units_old[u];
+    if (list == 0) return 1024;
+    const tc_kh_unit &x = list == 1 ? ctx->kj_units_blk[u] : ctx->kj_units_old[u];
     uint64_t b = (uint64_t)32 * (x.c1 - x.c0);
     if (ctx->tile_words && x.c0 == 0 && x.c1 + 32 > x.rb * 32 && x.rb < ctx->tile_rowcount.size())
         b = std::min<uint64_t>(b, (uint64_t)ctx->tile_rowcount[x.rb] * 1024);

@@ -84,7 +84,7 @@ void tc_shadow_free(tc_ctx *ctx)
     cudaFree(s->d_ranks); cudaFree(s->d_off); cudaFree(s->d_size); cudaFree(s->d_perm);
     cudaFree(s->d_bu_keys); cudaFree(s->d_bu_mask); cudaFree(s->d_bu_count);
     cudaFree(s->d_kh_pivots); cudaFree(s->d_kh_pivoff); cudaFree(s->d_kh_units); cudaFree(s->d_kj_units); cudaFree(s->d_scratch);
-    cudaFree(s->d_tile_flags); cudaFree(s->d_tile_rowcount);
+    cudaFree(s->d_tile_flags); cudaFree(s->d_tile_rowcount); cudaFree(s->d_ks_tiles); cudaFree(s->d_ks_count);
     delete s;                      // stream, events, edge buffer, counters and column state belong to the owner
     ctx->shadow = nullptr; ctx->use_shadow = false;
 }

@@ -19,6 +19,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <string>
+#include <thread>
 
 namespace {
 
@@ -185,13 +187,22 @@ extern "C" int tc_greedy_scan(tc_ctx *ctx, uint32_t q0, uint32_t q1, const uint3
 //                representative (std::map<double,int>::insert keeps the first key, one thread).
 // kssd = true  : KssdGreedyClusterWithInvertedIndex (greedy.cpp:566-899) with one thread: per-pair common_min,
 //                best = largest Jaccard (strict >) in `touched` order, no distance test beyond common_min.
-static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double threshold, bool brute, uint32_t semb_size,
+//
+// Several GPUs ("sequential over genomes, parallel over representatives"): cs[0..G) are contexts that all
+// hold the same sketch set; the representative table is dealt round-robin over them (representative number c lives on
+// context c mod G), every context scans the batch against its share on its own host thread, the candidate lists are
+// concatenated and the serial replay below runs unchanged -- it depends only on the union of the candidates, so the
+// result is the single-GPU (= one-thread reference) result whatever G.
+static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment, double threshold, bool brute, uint32_t semb_size,
                        int32_t *rep_of, uint32_t *n_clusters, bool kssd = false)
 {
+    tc_ctx *ctx = cs[0];
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0, "tc_greedy_cluster: no sketches uploaded");
     const uint32_t n = ctx->n;
-    cudaStream_t st = ctx->stream;
+    for (int r = 1; r < G; r++)
+        TC_CHECK(cs[r] && cs[r]->n == n && cs[r]->total == ctx->total && cs[r]->h_size == ctx->h_size,
+                 "tc_greedy_cluster_multi: context %d does not hold the same sketch set as context 0", r);
     // fixed-size fast path detection over the first 100 sketches (greedy.cpp:1092-1103)
     const int fixed_size = (int)ctx->h_size[0];
     bool all_fixed = !containment && !brute && !kssd;
@@ -204,10 +215,14 @@ static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double thres
 
     uint64_t cap = 1ull << 24;
     if (const char *s = getenv("TCLUST_CAND_CAP")) cap = std::max<uint64_t>(strtoull(s, nullptr, 10), 1024);
-    if (ctx->cand_cap < cap) {
-        cudaFree(ctx->d_cands); ctx->d_cands = nullptr; ctx->cand_cap = 0;
-        TC_CUDA(cudaMalloc(&ctx->d_cands, cap * sizeof(tc_cand)));
-        ctx->cand_cap = cap;
+    for (int r = 0; r < G; r++) {
+        TC_CUDA(cudaSetDevice(cs[r]->device));
+        if (cs[r]->cand_cap < cap) {
+            cudaFree(cs[r]->d_cands); cs[r]->d_cands = nullptr; cs[r]->cand_cap = 0;
+            TC_CUDA(cudaMalloc(&cs[r]->d_cands, cap * sizeof(tc_cand)));
+            cs[r]->cand_cap = cap;
+        }
+        tc_rep_table_reset(cs[r]);
     }
     uint32_t batch = 4096;
     if (const char *s = getenv("TCLUST_GREEDY_BATCH")) batch = (uint32_t)std::max<long>(atol(s), 32);
@@ -215,9 +230,41 @@ static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double thres
 
     const char *gimpl = getenv("TCLUST_GREEDY_IMPL");
     const bool use_join = semb_size == 0 && !(gimpl && !strcmp(gimpl, "merge"));
-    tc_rep_table_reset(ctx);
     std::vector<int32_t> order_of(n, -1);      // representative creation order, -1 = not a representative
     std::vector<tc_cand> cands;
+    std::vector<std::vector<tc_cand>> part_cands(G);
+    std::vector<std::string> part_err(G);
+    std::vector<char> part_over(G, 0);
+    std::vector<unsigned long long> part_cnt(G, 0);
+    // context r's share of one batch: batch x its representatives (+ on context 0: batch x batch, earlier member only)
+    auto scan_part = [&](int r, uint32_t b0, uint32_t b1) {
+        tc_ctx *c = cs[r];
+        cudaStream_t st = c->stream;
+        auto fail = [&](const char *what) { part_err[r] = std::string(what) + ": " + tc_last_error(); };
+        if (cudaSetDevice(c->device) != cudaSuccess || cudaMemsetAsync(c->d_edge_count, 0, 2 * sizeof(unsigned long long), st) != cudaSuccess) {
+            part_err[r] = "cudaSetDevice / memset failed"; return;
+        }
+        // candidates: the hash-join kernel (first_hit = smallest shared rank, same `touched` order), except for the
+        // semantic-B counts of the brute-force rule, which need the ordered merge (TCLUST_GREEDY_IMPL=merge forces it)
+        if (use_join) {
+            if (c->nrep > 0 && tc_launch_join_cands(c, b0, b1, 1, cmin_fixed, containment, jmin)) { fail("representative scan"); return; }
+            if (r == 0 && tc_launch_join_cands(c, b0, b1, 0, cmin_fixed, containment, jmin)) { fail("batch scan"); return; }
+        } else {
+            if (c->nrep > 0 && tc_launch_tiles_cands(c, b0, b1, 1, cmin_fixed, containment, jmin, 0, 1, semb_size)) { fail("representative scan"); return; }
+            if (r == 0 && tc_launch_tiles_cands(c, b0, b1, 0, cmin_fixed, containment, jmin, 0, 1, semb_size)) { fail("batch scan"); return; }
+        }
+        unsigned long long cnt[2];
+        if (cudaMemcpyAsync(cnt, c->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+            part_err[r] = std::string("candidate count: ") + cudaGetErrorString(cudaGetLastError()); return;
+        }
+        part_cnt[r] = cnt[0];
+        part_over[r] = cnt[1] != 0 || cnt[0] > c->cand_cap;
+        if (part_over[r]) return;
+        part_cands[r].resize(cnt[0]);
+        if (cnt[0] && (cudaMemcpyAsync(part_cands[r].data(), c->d_cands, cnt[0] * sizeof(tc_cand), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                       cudaStreamSynchronize(st) != cudaSuccess))
+            part_err[r] = std::string("candidate download: ") + cudaGetErrorString(cudaGetLastError());
+    };
     std::vector<uint32_t> start;
     std::vector<tc_cand> sorted;
     std::vector<uint32_t> new_reps;
@@ -225,29 +272,29 @@ static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double thres
 
     for (uint32_t b0 = 0; b0 < n;) {
         const uint32_t b1 = std::min<uint64_t>(n, (uint64_t)b0 + batch);
-        TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), st));
-        // candidates: the hash-join kernel (first_hit = smallest shared rank, same `touched` order), except for the
-        // semantic-B counts of the brute-force rule, which need the ordered merge (TCLUST_GREEDY_IMPL=merge forces it)
-        if (use_join) {
-            if (ctx->nrep > 0 && tc_launch_join_cands(ctx, b0, b1, 1, cmin_fixed, containment, jmin)) return 1;
-            if (tc_launch_join_cands(ctx, b0, b1, 0, cmin_fixed, containment, jmin)) return 1;
-        } else {
-            if (ctx->nrep > 0 && tc_launch_tiles_cands(ctx, b0, b1, 1, cmin_fixed, containment, jmin, 0, 1, semb_size)) return 1;
-            if (tc_launch_tiles_cands(ctx, b0, b1, 0, cmin_fixed, containment, jmin, 0, 1, semb_size)) return 1;
+        if (G == 1) scan_part(0, b0, b1);
+        else {
+            std::vector<std::thread> th;
+            for (int r = 0; r < G; r++) th.emplace_back(scan_part, r, b0, b1);
+            for (std::thread &t : th) t.join();
         }
-        unsigned long long cnt[2];
-        TC_CUDA(cudaMemcpyAsync(cnt, ctx->d_edge_count, sizeof cnt, cudaMemcpyDeviceToHost, st));
-        TC_CUDA(cudaStreamSynchronize(st));
-        if (cnt[1] != 0 || cnt[0] > ctx->cand_cap) {
+        bool over = false;
+        unsigned long long worst = 0;
+        for (int r = 0; r < G; r++) {
+            TC_CHECK(part_err[r].empty(), "tc_greedy_cluster: GPU %d: %s", cs[r]->device, part_err[r].c_str());
+            over |= part_over[r] != 0;
+            worst = std::max(worst, part_cnt[r]);
+        }
+        if (over) {
             TC_CHECK(batch > TC_GROUP, "tc_greedy_cluster: %llu candidates of one 32-genome batch exceed the buffer "
-                     "(%llu); raise TCLUST_CAND_CAP", cnt[0], (unsigned long long)ctx->cand_cap);
+                     "(%llu); raise TCLUST_CAND_CAP", worst, (unsigned long long)ctx->cand_cap);
             batch = std::max<uint32_t>(TC_GROUP, batch / 2 / TC_GROUP * TC_GROUP);
             continue;                                           // redo this batch with a smaller one
         }
-        cands.resize(cnt[0]);
-        if (cnt[0]) {
-            TC_CUDA(cudaMemcpyAsync(cands.data(), ctx->d_cands, cnt[0] * sizeof(tc_cand), cudaMemcpyDeviceToHost, st));
-            TC_CUDA(cudaStreamSynchronize(st));
+        if (G == 1) cands.swap(part_cands[0]);
+        else {
+            cands.clear();
+            for (int r = 0; r < G; r++) cands.insert(cands.end(), part_cands[r].begin(), part_cands[r].end());
         }
         // bucket by query (counting sort)
         const uint32_t nb = b1 - b0;
@@ -304,9 +351,24 @@ static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double thres
                 new_reps.push_back(q);
             }
         }
-        if (tc_rep_table_append(ctx, new_reps.data(), (uint32_t)new_reps.size())) return 1;
+        // the new representatives join the tables: creation number c goes to context c mod G
+        if (G == 1) { if (tc_rep_table_append(ctx, new_reps.data(), (uint32_t)new_reps.size())) return 1; }
+        else {
+            std::vector<std::vector<uint32_t>> share(G);
+            for (uint32_t q : new_reps) share[(uint32_t)order_of[q] % (uint32_t)G].push_back(q);
+            std::vector<std::thread> th;
+            for (int r = 0; r < G; r++)
+                th.emplace_back([&, r]() {
+                    if (share[r].empty()) return;
+                    if (cudaSetDevice(cs[r]->device) != cudaSuccess || tc_rep_table_append(cs[r], share[r].data(), (uint32_t)share[r].size()))
+                        part_err[r] = std::string("representative table: ") + tc_last_error();
+                });
+            for (std::thread &t : th) t.join();
+            for (int r = 0; r < G; r++) TC_CHECK(part_err[r].empty(), "tc_greedy_cluster: GPU %d: %s", cs[r]->device, part_err[r].c_str());
+        }
         b0 = b1;
     }
+    cudaSetDevice(ctx->device);
     if (n_clusters) *n_clusters = nrep_total;
     return 0;
 }
@@ -314,12 +376,20 @@ static int greedy_impl(tc_ctx *ctx, int kmer_size, int containment, double thres
 extern "C" int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, double threshold, int32_t *rep_of,
                                  uint32_t *n_clusters)
 {
-    return greedy_impl(ctx, kmer_size, containment, threshold, false, 0, rep_of, n_clusters);
+    return greedy_impl(&ctx, 1, kmer_size, containment, threshold, false, 0, rep_of, n_clusters);
 }
 
 extern "C" int tc_greedy_cluster_kssd(tc_ctx *ctx, int kmer_size, double threshold, int32_t *rep_of, uint32_t *n_clusters)
 {
-    return greedy_impl(ctx, kmer_size, 0, threshold, false, 0, rep_of, n_clusters, true);
+    return greedy_impl(&ctx, 1, kmer_size, 0, threshold, false, 0, rep_of, n_clusters, true);
+}
+
+extern "C" int tc_greedy_cluster_multi(tc_ctx *const *ctxs, int nctx, int kmer_size, int containment, double threshold, int kssd,
+                                       int32_t *rep_of, uint32_t *n_clusters)
+{
+    TC_CHECK(ctxs && nctx >= 1 && nctx <= 64, "tc_greedy_cluster_multi: bad context list");
+    for (int r = 0; r < nctx; r++) TC_CHECK(ctxs[r], "tc_greedy_cluster_multi: context %d is null", r);
+    return greedy_impl(ctxs, nctx, kmer_size, kssd ? 0 : containment, threshold, false, 0, rep_of, n_clusters, kssd != 0);
 }
 
 extern "C" int tc_greedy_cluster_bruteforce(tc_ctx *ctx, int kmer_size, uint32_t sketch_size, int containment,
@@ -328,5 +398,5 @@ extern "C" int tc_greedy_cluster_bruteforce(tc_ctx *ctx, int kmer_size, uint32_t
     TC_CHECK(containment || sketch_size > 0, "tc_greedy_cluster_bruteforce: sketch_size == 0");
     TC_CHECK(threshold < 1.0, "tc_greedy_cluster_bruteforce: threshold must be < 1 (pairs without a shared hash "
              "have distance 1 and are never candidates)");
-    return greedy_impl(ctx, kmer_size, containment, threshold, true, sketch_size, rep_of, n_clusters);
+    return greedy_impl(&ctx, 1, kmer_size, containment, threshold, true, sketch_size, rep_of, n_clusters);
 }

@@ -114,6 +114,10 @@ struct tc_ctx {
     std::vector<uint32_t> kh_parts;      // table partitions per row block
     std::vector<tc_kh_unit> kj_units_blk, kj_units_old;   // this rank's units routed to K3J / K3H, resident in d_kj_units
     tc_kh_unit *d_kj_units = nullptr;
+    // K3S (sparse rows): their units, the flagged tiles as a device list, the list length (device / host copy)
+    std::vector<tc_kh_unit> ks_units;
+    void *d_ks_tiles = nullptr; uint64_t cap_ks_tiles = 0;
+    uint32_t *d_ks_count = nullptr; uint32_t ks_ntiles_host = 0;
     uint64_t kj_split_key = 0;
     bool kj_split_valid = false;
     // tile candidacy (k3t_tileflags.cu): bit (rb, cb) of row rb = some rank occurs both in block rb and in block cb
@@ -188,8 +192,9 @@ int tc_launch_join_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, ui
 int tc_launch_blockjoin_matrix(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0, uint32_t j1, uint32_t *d_out);
 int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index, bool force_block,
                               bool plan_only = false);
-int tc_blockjoin_run_range(tc_ctx *ctx, int radio, uint32_t start_index, bool block_list, size_t u0, size_t u1);
-uint64_t tc_blockjoin_unit_bound(const tc_ctx *ctx, bool block_list, size_t u);
+size_t tc_blockjoin_list_size(const tc_ctx *ctx, int list);            // list 0 = sparse tiles (K3S), 1 = K3J units, 2 = K3H units
+int tc_blockjoin_run_range(tc_ctx *ctx, int radio, uint32_t start_index, int list, size_t u0, size_t u1);
+uint64_t tc_blockjoin_unit_bound(const tc_ctx *ctx, int list, size_t u);
 int tc_launch_join_cands(tc_ctx *ctx, uint32_t q0, uint32_t q1, int vs_reps, int cmin_fixed, int containment, double jmin);
 int tc_launch_join_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t nparts, uint32_t start_index = 0);
 // reordered shadow copy (k3r_reorder.cu)

@@ -135,7 +135,7 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx)
     for (cudaEvent_t &e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     if (ctx->up_copy_stream) cudaStreamDestroy(ctx->up_copy_stream);
     cudaFree(ctx->d_kssd_dim); cudaFree(ctx->d_kssd_filter);
-    cudaFree(ctx->d_kh_state); cudaFree(ctx->d_kh_units); cudaFree(ctx->d_kj_units);
+    cudaFree(ctx->d_kh_state); cudaFree(ctx->d_kh_units); cudaFree(ctx->d_kj_units); cudaFree(ctx->d_ks_tiles); cudaFree(ctx->d_ks_count);
     if (ctx->ev_pass0) cudaEventDestroy(ctx->ev_pass0);
     if (ctx->ev_pass1) cudaEventDestroy(ctx->ev_pass1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1036,9 +1036,8 @@ static int mst_bounded(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t
     uint32_t nfin = 0;
     auto fin_key = [&]() -> const unsigned long long * { return nfin ? ctx->k4.d_fin : nullptr; };
     auto fin_id = [&]() -> const unsigned long long * { return nfin ? ctx->k4.d_fin + ctx->n : nullptr; };
-    for (int list = 0; list < 2; list++) {
-        const bool blk = list == 0;
-        const size_t nu = blk ? src->kj_units_blk.size() : src->kj_units_old.size();
+    for (int blk = 0; blk < 3; blk++) {              // sparse tiles, block-join units, hash-join units
+        const size_t nu = tc_blockjoin_list_size(src, blk);
         for (size_t u = 0; u < nu;) {
             size_t u1 = u;
             uint64_t bound = 0;

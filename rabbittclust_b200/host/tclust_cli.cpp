@@ -931,6 +931,27 @@ void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_fi
 #ifdef GREEDY_CLUST
     vector<int32_t> rep_of(g.size());
     uint32_t nclust = 0;
+    if (o.gpus > 1) {
+        // representative scan sharded over the devices: every device holds all sketches, the representative
+        // table is dealt round-robin; same clusters as with one GPU
+        const int G = o.gpus;
+        vector<tc_ctx *> cs(G, nullptr);
+        cs[0] = ctx;
+        for (int r = 1; r < G; r++) tc_or_die(tc_ctx_create(o.device + r, &cs[r]), "tc_ctx_create (--gpus)");
+        vector<string> errs(G);
+        vector<std::thread> th;
+        for (int r = 1; r < G; r++)
+            th.emplace_back([&, r]() {
+                vector<const uint64_t *> rows(g.size());
+                vector<uint64_t> sizes(g.size());
+                for (size_t i = 0; i < g.size(); i++) { rows[i] = g[i].hashes.data(); sizes[i] = g[i].hashes.size(); }
+                if (tc_sketches_upload_rows(cs[r], rows.data(), sizes.data(), (uint32_t)g.size())) errs[r] = string("sketch upload, ") + tc_last_error();
+            });
+        for (std::thread &t : th) t.join();
+        for (int r = 0; r < G; r++) if (!errs[r].empty()) die("GPU " + std::to_string(o.device + r) + ": " + errs[r]);
+        tc_or_die(tc_greedy_cluster_multi(cs.data(), G, o.kmer, o.containment, o.threshold, o.fast ? 1 : 0, rep_of.data(), &nclust), "greedy clustering");
+        for (int r = 1; r < G; r++) tc_ctx_destroy(cs[r]);
+    } else
     if (o.fast) tc_or_die(tc_greedy_cluster_kssd(ctx, o.kmer, o.threshold, rep_of.data(), &nclust), "greedy clustering");
     else tc_or_die(tc_greedy_cluster(ctx, o.kmer, o.containment, o.threshold, rep_of.data(), &nclust), "greedy clustering");
     vector<vector<int>> cluster;

@@ -162,3 +162,36 @@ def test_greedy_kssd_rule_live_against_reference(ctx, oracle, tmp_path):
             want[gid] = c[0][0]
     assert nc == len(ref)
     assert np.array_equal(rep, want)
+
+
+@pytest.mark.parametrize("mode", ["fixed", "ragged-contain", "kssd"])
+def test_greedy_sharded_representatives(tc, mode, monkeypatch):
+    """tc_greedy_cluster_multi: the representative table dealt over several contexts (here on one device, on a
+    multi-GPU box one per device) gives the clusters of the single-context run, whatever the number of contexts."""
+    import torch
+    monkeypatch.setenv("TCLUST_GREEDY_BATCH", "64")        # many batches: the tables grow on every context
+    if mode == "fixed":
+        sk = synth.family_sketches(12, 25, s=400, seed=41)
+        kw = dict(containment=False, kssd=False)
+    elif mode == "ragged-contain":
+        sk = synth.family_sketches(10, 20, seed=42, ragged=(100, 1500))
+        sk.sort(key=lambda a: -len(a))
+        kw = dict(containment=True, kssd=False)
+    else:
+        sk = synth.family_sketches(10, 20, seed=43, ragged=(200, 600))
+        sk.sort(key=lambda a: -len(a))
+        kw = dict(containment=False, kssd=True)
+    with tc.Context(0) as c:
+        c.upload(sk)
+        want = c.greedy_cluster_kssd(21, 0.05) if mode == "kssd" else c.greedy_cluster(21, 0.05, kw["containment"])
+    ndev = torch.cuda.device_count()
+    for g in (2, 3):
+        ctxs = [tc.Context(r % ndev) for r in range(g)]
+        try:
+            for c in ctxs:
+                c.upload(sk)
+            got = tc.greedy_cluster_multi(ctxs, 21, 0.05, **kw)
+        finally:
+            for c in ctxs:
+                c.close()
+        assert got[0] == want[0] and np.array_equal(got[1], want[1]), (mode, g)
