@@ -1040,9 +1040,9 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3j_block_kernel(const KHArgs a
 // No hash table, no partitions (a list that does not fit is the host's cue to route the row to K3J), three CTAs per SM
 // overlap each other's copies.  Same epilogue (candidate edge / union-find) and the same `common` for every pair.
 constexpr uint32_t KS_THREADS = 256, KS_WARPS = KS_THREADS / 32;
-constexpr uint32_t KS_RCAP = 4096;                                   // longest row-block list a tile can stage
+constexpr uint32_t KS_RCAP = 4096;                                   // row-block list entries per stage
 constexpr uint32_t KS_CCHUNK = 2048;                                 // column list entries per stage
-constexpr uint32_t KS_ROW_MAX_TILES = 64;                            // rows with more flagged tiles stay on K3J (table amortised)
+constexpr uint32_t KS_ROW_MAX_TILES = 0xFFFFFFFFu;                            // rows with more flagged tiles stay on K3J (table amortised); TCLUST_KS_ROW_MAX
 constexpr size_t KS_SMEM = (size_t)(KS_RCAP + 4) * 8 + (size_t)(KS_CCHUNK + 4) * 8 + (size_t)KS_WARPS * KJ_TILE_WORDS * 4 + 64;
 
 __device__ __forceinline__ void ks_mbar_init(uint32_t bar, uint32_t count)
@@ -1066,6 +1066,20 @@ __device__ __forceinline__ void ks_bulk_g2s(uint32_t dst, const void *src, uint3
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// 32 x 32 bit transpose across a warp: in, lane k holds word k; out, lane j holds bit j of every word (bit k = word k's
+// bit j).  Five butterfly stages of one shuffle each (instead of 32 ballots).
+__device__ __forceinline__ uint32_t ks_transpose32(uint32_t x, uint32_t lane)
+{
+#pragma unroll
+    for (int st = 0; st < 5; st++) {
+        const uint32_t s = 16u >> st;
+        const uint32_t mask = st == 0 ? 0x0000FFFFu : st == 1 ? 0x00FF00FFu : st == 2 ? 0x0F0F0F0Fu : st == 3 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+        x = (lane & s) ? ((x & ~mask) | ((y >> s) & mask)) : ((x & mask) | ((y << s) & ~mask));
+    }
+    return x;
 }
 
 // row `row` of a finished tile (rb, cb): candidate edge / union for column j = cb*32 + lane (the K3J epilogue with the
@@ -1133,86 +1147,74 @@ __global__ void __launch_bounds__(KS_THREADS, 3) k3s_tile_kernel(const KHArgs a,
         const bool live = Dr > 0 && Dc > 0 && rb * 32 + 31 >= a.row_min;
         const unsigned long long rel = a.off[rb * 32], cel = a.off[cb * 32];
         const uint32_t lead_r = (uint32_t)(rel & 3ull), lead_c = (uint32_t)(cel & 3ull);   // bulk copies start 16-byte aligned
-        if (live && tid == 0) {
-            const uint32_t bytes = ((lead_r + Dr + 3u) & ~3u) * 4u;
-            ks_mbar_expect_tx(bar_r, 2u * bytes);
-            ks_bulk_g2s(rkeys_s, a.bu_keys + (rel - lead_r), bytes, bar_r);
-            ks_bulk_g2s(rmask_s, a.bu_mask + (rel - lead_r), bytes, bar_r);
-        }
-        if (live) {
+        // count[r][lane] of this warp's share of the keys lives in registers (no shared-memory read-modify-write chain)
+        uint32_t acc[32];
 #pragma unroll
-            for (int q = 0; q < 16; q++) cntw[lane + 32 * q] = 0u;
-        }
+        for (int r = 0; r < 32; r++) acc[r] = 0u;
         uint32_t anyhit = 0;
-        const uint32_t *rk = rkeys + lead_r, *rm = rmask + lead_r;
-        uint32_t top = 1;                                        // largest power of two <= Dr
-        while (live && top * 2 <= Dr) top *= 2;
-        for (uint32_t c0 = 0; live && c0 < Dc; c0 += KS_CCHUNK) {
-            const uint32_t len = min(KS_CCHUNK, Dc - c0);
+        const uint32_t *rk = rkeys + lead_r, *rm = rmask + lead_r, *ck = ckeys + lead_c, *cm = cmask + lead_c;
+        // Both lists are ascending: they are streamed through shared memory in stages (KS_RCAP row entries, KS_CCHUNK
+        // column entries) like the two inputs of a merge -- the stage whose last key is smaller is replaced by its
+        // successor -- so every entry is copied once whatever the list lengths.
+        uint32_t r0 = 0, c0 = 0;
+        bool need_r = live, need_c = live;
+        while (live && r0 < Dr && c0 < Dc) {
+            const uint32_t rlen = min(KS_RCAP, Dr - r0), len = min(KS_CCHUNK, Dc - c0);
             if (tid == 0) {
-                const uint32_t bytes = ((lead_c + len + 3u) & ~3u) * 4u;
-                ks_mbar_expect_tx(bar_c, 2u * bytes);
-                ks_bulk_g2s(ckeys_s, a.bu_keys + (cel - lead_c + c0), bytes, bar_c);
-                ks_bulk_g2s(cmask_s, a.bu_mask + (cel - lead_c + c0), bytes, bar_c);
-            }
-            if (c0 == 0) { ks_mbar_wait(bar_r, par_r); par_r ^= 1u; }
-            ks_mbar_wait(bar_c, par_c); par_c ^= 1u;
-            const uint32_t *ck = ckeys + lead_c, *cm = cmask + lead_c;
-            const uint32_t rlo = rk[0], rhi = rk[Dr - 1];
-            for (uint32_t g = warp * 32; g < len; g += KS_WARPS * 32) {
-                const uint32_t k = g + lane;
-                const uint32_t x = k < len ? ck[k] : 0xFFFFFFFFu;
-                uint32_t mk = 0u;
-                if (__any_sync(0xffffffffu, x >= rlo && x <= rhi)) {
-                    // number of row keys < x: branch-free lower bound, the same trip count for every lane
-                    uint32_t lo = 0;
-                    for (uint32_t step = top; step; step >>= 1) {
-                        const uint32_t nx = lo + step;
-                        if (nx <= Dr && rk[nx - 1] < x) lo = nx;
-                    }
-                    if (lo < Dr && rk[lo] == x) mk = rm[lo];
+                if (need_r) {
+                    const uint32_t bytes = ((lead_r + rlen + 3u) & ~3u) * 4u;
+                    ks_mbar_expect_tx(bar_r, 2u * bytes);
+                    ks_bulk_g2s(rkeys_s, a.bu_keys + (rel - lead_r + r0), bytes, bar_r);
+                    ks_bulk_g2s(rmask_s, a.bu_mask + (rel - lead_r + r0), bytes, bar_r);
                 }
-                unsigned hit = __ballot_sync(0xffffffffu, mk != 0u);
-                if (!hit) continue;
-                anyhit = 1u;
-                const uint32_t cmk = mk ? cm[k] : 0u;
-                if (__popc(hit) <= 2) {
-                    while (hit) {                         // few hits: count[r][c]++ for r in rows, c = lane
-                        const int src = __ffs(hit) - 1;
-                        uint32_t rmv = __shfl_sync(0xffffffffu, mk, src);
-                        const uint32_t cmv = __shfl_sync(0xffffffffu, cmk, src);
-                        const bool mine = (cmv >> lane) & 1u;
-                        while (rmv) {
-                            const int r = __ffs(rmv) - 1;
-                            if (mine) cnt[r * 32 + lane]++;
-                            rmv &= rmv - 1;
+                if (need_c) {
+                    const uint32_t bytes = ((lead_c + len + 3u) & ~3u) * 4u;
+                    ks_mbar_expect_tx(bar_c, 2u * bytes);
+                    ks_bulk_g2s(ckeys_s, a.bu_keys + (cel - lead_c + c0), bytes, bar_c);
+                    ks_bulk_g2s(cmask_s, a.bu_mask + (cel - lead_c + c0), bytes, bar_c);
+                }
+            }
+            if (need_r) { ks_mbar_wait(bar_r, par_r); par_r ^= 1u; }
+            if (need_c) { ks_mbar_wait(bar_c, par_c); par_c ^= 1u; }
+            const uint32_t rlo = rk[0], rhi = rk[rlen - 1], clo = ck[0], chi = ck[len - 1];
+            if (!(chi < rlo || clo > rhi)) {
+                uint32_t top = 1;                                    // largest power of two <= rlen
+                while (top * 2 <= rlen) top *= 2;
+                for (uint32_t g = warp * 32; g < len; g += KS_WARPS * 32) {
+                    const uint32_t k = g + lane;
+                    const uint32_t x = k < len ? ck[k] : 0xFFFFFFFFu;
+                    uint32_t mk = 0u;
+                    if (__any_sync(0xffffffffu, x >= rlo && x <= rhi)) {
+                        // number of row keys < x: branch-free lower bound, the same trip count for every lane
+                        uint32_t lo = 0;
+                        for (uint32_t step = top; step; step >>= 1) {
+                            const uint32_t nx = lo + step;
+                            if (nx <= rlen && rk[nx - 1] < x) lo = nx;
                         }
-                        hit &= hit - 1;
+                        if (lo < rlen && rk[lo] == x) mk = rm[lo];
                     }
-                } else {
-                    // many hits: transpose the 32 keys' masks with ballots (mycols: keys held by column `lane`; per row r
-                    // the keys held by row r) and add popcounts
-                    uint32_t mycols = 0;
+                    if (!__any_sync(0xffffffffu, mk != 0u)) continue;
+                    anyhit = 1u;
+                    const uint32_t cmk = mk ? cm[k] : 0u;
+                    // lane k holds (rows holding key k, columns holding key k); transposed: lane r holds the keys row r
+                    // holds, lane c the keys column c holds; count[r][c] += popc(keys of row r & keys of column c)
+                    const uint32_t rowkeys = ks_transpose32(mk, lane), colkeys = ks_transpose32(cmk, lane);
 #pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const unsigned bb = __ballot_sync(0xffffffffu, (cmk >> c) & 1u);
-                        if (lane == (uint32_t)c) mycols = bb;
-                    }
-                    uint32_t rows_any = mk;
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) rows_any |= __shfl_xor_sync(0xffffffffu, rows_any, o);
-                    while (rows_any) {
-                        const int r = __ffs(rows_any) - 1;
-                        const unsigned rkb = __ballot_sync(0xffffffffu, (mk >> r) & 1u);
-                        const uint32_t add = __popc(rkb & mycols);
-                        if (add) cnt[r * 32 + lane] += (uint16_t)add;
-                        rows_any &= rows_any - 1;
-                    }
+                    for (int r = 0; r < 32; r++) acc[r] += __popc(__shfl_sync(0xffffffffu, rowkeys, r) & colkeys);
                 }
             }
-            __syncthreads();                  // every warp is done with this stage's column entries
+            __syncthreads();                  // every warp is done with both stages
+            need_r = rhi <= chi; need_c = chi <= rhi;
+            if (need_r) r0 += rlen;
+            if (need_c) c0 += len;
         }
-        if (__syncthreads_or((int)anyhit)) {
+        const bool tile_hit = __syncthreads_or((int)anyhit) != 0;
+        if (tile_hit) {
+#pragma unroll
+            for (int r = 0; r < 32; r++) cnt[r * 32 + lane] = (uint16_t)acc[r];
+        }
+        __syncthreads();
+        if (tile_hit) {
             // warp w finishes rows 4w .. 4w+3: sum over the 8 warps' counter sets, then the epilogue
 #pragma unroll 1
             for (uint32_t r = warp * 4; r < warp * 4 + 4; r++) {
@@ -1591,9 +1593,11 @@ int tc_launch_blockjoin_edges(tc_ctx *ctx, int radio, uint32_t part, uint32_t np
         const char *ks_env = getenv("TCLUST_K3S");
         const bool ks_on = ctx->tile_words && !force_block && route.unlisted.back() == 0 && !(ks_env && !strcmp(ks_env, "0"));
         uint64_t ks_cap = 0;
+        uint32_t ks_row_max = KS_ROW_MAX_TILES;          // (measured: K3S wins in the all-dense regime too, 3.1 vs 8.8 ms on a one-species set)
+        if (const char *e = getenv("TCLUST_KS_ROW_MAX")) ks_row_max = (uint32_t)std::max(0l, atol(e));
         for (size_t u = part; u < ctx->kh_edge_units.size(); u += (nparts ? nparts : 1)) {
             const tc_kh_unit &un = ctx->kh_edge_units[u];
-            if (ks_on && un.rb < ctx->tile_rowcount.size() && ctx->tile_rowcount[un.rb] < KS_ROW_MAX_TILES && ctx->bu_count[un.rb] <= KS_RCAP) {
+            if (ks_on && un.rb < ctx->tile_rowcount.size() && ctx->tile_rowcount[un.rb] < ks_row_max && ctx->bu_count[un.rb] != 0xFFFFFFFFu) {
                 sps.push_back(un);
                 ks_cap += std::min<uint64_t>(ctx->tile_rowcount[un.rb], (un.c1 - un.c0 + 31) / 32 + 1);
                 continue;
