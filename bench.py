@@ -462,6 +462,42 @@ def run_pairs(args):
     e2e_ms = (time.time() - t0) * 1e3 / e2e_steps
     d2h = int(mst.nbytes)
 
+    # ---- a set large enough to scale: one species of --dense-n sketches (every pair is a candidate, every tile dense).
+    #      configs[2] itself is ~1 ms of work for one GPU, of which only the dense pass shards; this leg shows the same
+    #      collective tc_mst where the sharded part dominates.  Same code path, every rank, device-timed like `value`.
+    large = None
+    if not args.no_large:
+        hd, od = synth.family_sketches_fast(1, args.dense_n, 1000, seed=5)
+        nd = len(od) - 1
+        if dist is not None:
+            ctx.mg_leave()
+            mine = torch.frombuffer(bytearray(ctx.mg_export(max(n, nd))), dtype=torch.uint8).to(dev)
+            allh = torch.empty(world * T.MG_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine)
+            ctx.mg_join(rank, world, bytes(allh.cpu().numpy().tobytes()))
+        ctx.upload(hashes=hd, off=od)
+        ctx.mst(k, thr)
+        sync_all()
+        la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            la.record()
+        for _ in range(3):
+            md = ctx.mst(k, thr)
+        with torch.cuda.stream(stream):
+            lb.record()
+        sync_all()
+        lb.synchronize()
+        sl = ctx.mst_stats()
+        lt = torch.tensor([la.elapsed_time(lb) / 3, sl["pass_ms"], sl["boruvka_ms"]], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+        large = {"what": "collective tc_mst on one species of %d sketches (s=1000): %d pairs, all of them candidates" % (nd, nd * (nd - 1) // 2),
+                 "n": nd, "pairs": nd * (nd - 1) // 2, "ms_per_step": float(lt[0]), "value": nd * (nd - 1) / 2 / (float(lt[0]) / 1e3),
+                 "unit": "pairs/s", "pass_kernel_ms_max_rank": float(lt[1]), "boruvka_kernel_ms_max_rank": float(lt[2]),
+                 "mst_edges": int(len(md)), "n_gpus": world}
+        del hd
+        h2d_restore = upload()          # the headline set is resident again for what follows
+
     # ---- N > 1: the collective result must be the single-GPU result, edge for edge
     same_as_single = None
     if dist is not None and rank == 0:
@@ -562,7 +598,9 @@ def run_pairs(args):
             except Exception:
                 prof = None
         kernel = ("k3_tile_kernel" if impl_env == "merge" else "k3h_join_kernel" if impl_env == "join"
-                  else "k3j_block_kernel (flagged tiles only; units where the block join does not pay run on k3h_join_kernel)")
+                  else "k3j_block_kernel" if impl_env == "blockjoin"
+                  else "k3s_tile_kernel (flagged tiles only, union lists staged with TMA bulk copies; row blocks without a union "
+                       "list run on k3h_join_kernel)")
         line = {
             "metric": "pairwise sketch distances/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -607,6 +645,8 @@ def run_pairs(args):
             line["mst_equals_single_gpu"] = same_as_single
         if robust is not None:
             line["robustness"] = robust
+        if large is not None:
+            line["large_set"] = large
         if semb_ms is not None:
             line["semantic_b"] = {"what": "the same pass with Mash union-limited counts (MinHash::jaccard stop rule, "
                                           "sketchSize 1000) on the step-budget merge kernel k3_tile_kernel<EDGES,SEMB>; "
@@ -686,6 +726,7 @@ def main():
     ap.add_argument("--no-sketch", action="store_true", help="pairs workload: skip the sketch leg of the line")
     ap.add_argument("--no-semb", action="store_true", help="pairs workload: skip the semantic-B pass")
     ap.add_argument("--no-robust", action="store_true", help="pairs workload: skip the robustness legs")
+    ap.add_argument("--no-large", action="store_true", help="pairs workload: skip the large-set (scaling) leg")
     ap.add_argument("--dense-n", type=int, default=16384, help="robustness: sketches of the one-species set")
     ap.add_argument("--order", default="family", choices=["family", "shuffled"],
                     help="pairs workload: sketch order (family = as generated, SURVEY 8d config 3; shuffled = random)")

@@ -10,7 +10,10 @@ checked through size-independent properties (the oracle cannot run these sizes i
          tc_greedy_cluster.  Properties: every member is within d of its representative (exact host distance on the
          numpy intersection) and every representative is farther than d from every earlier representative of its
          own family sample; cluster count reported.
-usage: python tools/scale_check.py kssd|greedy [N]
+usage: python tools/scale_check.py kssd|greedy [N] [--gpus G]
+--gpus G: additionally the same job on G GPUs of the box -- kssd: one context + host thread per device in a multi-GPU
+group (tc_mg_*: work units of the pass dealt round-robin, Boruvka reductions over NVLink peer memory inside the kernel);
+greedy: tc_greedy_cluster_multi (representative table dealt round-robin) -- and the result must equal the 1-GPU one.
 """
 import json
 import os
@@ -55,7 +58,44 @@ def ragged_families(n_fam, per_fam, seed=6, lo=100, hi=10000):
     return sk, np.asarray(lens)
 
 
+def group_mst(sk_flat, off, k, d, gpus):
+    """(upload_s, mst_s, mst) of a G-GPU group: threads of this process, one context per device."""
+    import threading
+    ctxs = [T.Context(r) for r in range(gpus)]
+    n = len(off) - 1
+    handles = [c.mg_export(n) for c in ctxs]
+    out, err, t_up, t_mst = [None] * gpus, [None] * gpus, [0.0] * gpus, [0.0] * gpus
+    bar = threading.Barrier(gpus)
+
+    def work(r):
+        try:
+            ctxs[r].mg_join(r, gpus, handles)
+            bar.wait()
+            t0 = time.time(); ctxs[r].upload(hashes=sk_flat, off=off); t_up[r] = time.time() - t0
+            bar.wait()
+            ctxs[r].mst(k, d)                                  # warm-up (unit lists, buffers)
+            bar.wait()
+            t0 = time.time(); out[r] = ctxs[r].mst(k, d).copy(); t_mst[r] = time.time() - t0
+        except Exception as ex:      # noqa: BLE001
+            bar.abort(); err[r] = ex
+    th = [threading.Thread(target=work, args=(r,)) for r in range(gpus)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    stats = [c.mst_stats() for c in ctxs]
+    for c in ctxs:
+        c.mg_leave(); c.close()
+    for e in err:
+        if e is not None:
+            raise e
+    for r in range(1, gpus):
+        assert np.array_equal(out[0], out[r]), "ranks disagree"
+    return max(t_up), max(t_mst), out[0], stats
+
+
 def main():
+    gpus = 1
+    if "--gpus" in sys.argv:
+        i = sys.argv.index("--gpus"); gpus = int(sys.argv[i + 1]); del sys.argv[i:i + 2]
     what = sys.argv[1]
     res = {"what": what}
     ctx = T.Context(0)
@@ -65,9 +105,21 @@ def main():
         t0 = time.time(); sk = kssd_like(n // per, per); res["gen_s"] = time.time() - t0
         n = len(sk)
         k, d = 18, 0.05
-        t0 = time.time(); ctx.upload(sk); res["upload_s"] = time.time() - t0
-        t0 = time.time(); mst = ctx.mst(k, d); res["mst_s"] = time.time() - t0
+        flat, off = T.pack_sketches(sk)
+        t0 = time.time(); ctx.upload(hashes=flat, off=off); res["upload_s"] = time.time() - t0
+        t0 = time.time(); mst = ctx.mst(k, d); res["mst_first_s"] = time.time() - t0       # may include the edge-buffer growth
+        t0 = time.time(); mst = ctx.mst(k, d).copy(); res["mst_s"] = time.time() - t0
+        res["stats"] = ctx.mst_stats()
         res.update(n=n, pairs=n * (n - 1) // 2, mst_edges=len(mst), pairs_per_s_incl_boruvka=n * (n - 1) / 2 / res["mst_s"])
+        if gpus > 1:
+            ctx.close()
+            up, ms, m2, st = group_mst(flat, off, k, d, gpus)
+            res["multi_gpu"] = {"gpus": gpus, "upload_s": up, "mst_s": ms, "speedup_vs_1gpu": res["mst_s"] / ms,
+                                "equals_1gpu": bool(np.array_equal(m2, mst)),
+                                "pass_ms_per_rank": [x["pass_ms"] for x in st], "boruvka_ms_per_rank": [x["boruvka_ms"] for x in st],
+                                "edges_per_rank": [x["edges"] for x in st]}
+            assert res["multi_gpu"]["equals_1gpu"]
+            ctx = T.Context(0)
         assert (np.diff(mst["dist"]) >= 0).all()
         # union-find over edges <= d
         par = np.arange(n)
@@ -101,6 +153,18 @@ def main():
         t0 = time.time(); ctx.upload(sk); res["upload_s"] = time.time() - t0
         t0 = time.time(); nc, rep = ctx.greedy_cluster(k, d, containment=True); res["greedy_s"] = time.time() - t0
         res.update(n=n, clusters=nc, mean_size=float(np.mean([len(s) for s in sk])))
+        if gpus > 1:
+            import threading
+            flat, off = T.pack_sketches(sk)
+            ctxs = [ctx] + [T.Context(r) for r in range(1, gpus)]
+            th = [threading.Thread(target=lambda c=c: c.upload(hashes=flat, off=off)) for c in ctxs[1:]]
+            t0 = time.time(); [t.start() for t in th]; [t.join() for t in th]; up = time.time() - t0
+            t0 = time.time(); nc2, rep2 = T.greedy_cluster_multi(ctxs, k, d, containment=True); gs = time.time() - t0
+            for c in ctxs[1:]:
+                c.close()
+            res["multi_gpu"] = {"gpus": gpus, "upload_s": up, "greedy_s": gs, "speedup_vs_1gpu": res["greedy_s"] / gs,
+                                "equals_1gpu": bool(nc2 == nc and np.array_equal(rep2, rep))}
+            assert res["multi_gpu"]["equals_1gpu"]
         assert nc == len(set(rep.tolist())) and (rep <= np.arange(n)).all() and (rep[rep] == rep).all()
         L = T.lib()
         rng = np.random.default_rng(1)
