@@ -43,6 +43,9 @@
 #include <queue>
 #include <string>
 #include <mutex>
+#include <memory>
+#include <functional>
+#include <condition_variable>
 #include <thread>
 #include <vector>
 #include <atomic>
@@ -89,6 +92,25 @@ struct Record { string name, comment; bool has_comment = false; uint64_t begin =
 
 bool read_whole_gz(const string &path, string &out)
 {
+    {   // not gzip (magic 1f 8b): one read of the whole file instead of zlib's transparent copy loop
+        FILE *f = fopen(path.c_str(), "rb");
+        if (!f) return false;
+        unsigned char magic[2] = {0, 0};
+        const size_t got = fread(magic, 1, 2, f);
+        if (!(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) {
+            struct stat sb;
+            out.clear();
+            if (fstat(fileno(f), &sb) == 0 && S_ISREG(sb.st_mode)) {
+                out.resize((size_t)sb.st_size);
+                rewind(f);
+                const size_t n = sb.st_size ? fread(&out[0], 1, (size_t)sb.st_size, f) : 0;
+                out.resize(n);
+                fclose(f);
+                return true;
+            }
+        }
+        fclose(f);
+    }
     gzFile fp = gzopen(path.c_str(), "r");
     if (!fp) return false;
     gzbuffer(fp, 1 << 20);
@@ -106,6 +128,7 @@ bool read_whole_gz(const string &path, string &out)
 void parse_fasta(const string &text, bool kseq_mode, vector<uint8_t> &seq, vector<Record> &recs)
 {
     size_t p = 0, n = text.size();
+    seq.reserve(seq.size() + n);                            // one allocation: the sequence is the text minus headers and line ends
     while (p < n && text[p] != '>') {                      // skip anything before the first header
         const char *nl = (const char *)memchr(text.data() + p, '\n', n - p);
         if (!nl) return;
@@ -309,23 +332,35 @@ void make_shuffled_dim(int half_subk)
 }
 
 // ---------------------------------------------------------------------------- sketching
-// page-locked, growable byte buffer (the H2D copies of tc_sketch_* overlap the kernels only from pinned memory)
+// growable byte buffer of a sketch batch: page-locked (tc_host_alloc: the H2D copies of tc_sketch_* then overlap the
+// kernels and run at PCIe speed) when the buffers are reused for many batches, plain memory when the whole input is
+// one or two batches -- page-locking costs ~0.4 ms per MB (470 ms for the 2 x 576 MB of BASELINE configs[0], ten times
+// the copy it would speed up) and needs the CUDA context, which a small run would otherwise not wait for yet
 struct PinnedBuf {
-    uint8_t *p = nullptr; size_t cap = 0, len = 0;
+    uint8_t *p = nullptr; size_t cap = 0, len = 0; bool pinned = true;
     void reserve(size_t need)
     {
         if (need <= cap) return;
-        // page-locking is slow (~0.3 ms per MB): grow geometrically and let the feeder pre-size the buffer
+        // page-locking is slow: grow geometrically and let the feeder pre-size the buffer
         const size_t nc = std::max<size_t>(std::max<size_t>(need, cap * 2), (size_t)16 << 20);
-        uint8_t *q = (uint8_t *)tc_host_alloc(nc);
-        if (!q) { cerr << "ERROR: cannot allocate " << nc << " bytes of page-locked memory, " << tc_last_error() << endl; exit(1); }
+        uint8_t *q = pinned ? (uint8_t *)tc_host_alloc(nc) : (uint8_t *)malloc(nc);
+        if (q && !pinned && nc >= ((size_t)64 << 20)) {
+            // first touch of fresh pages costs the single consumer thread ~0.7 s per GB: fault them in on all cores
+            const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            vector<std::thread> th;
+            for (unsigned t = 0; t < nt; t++)
+                th.emplace_back([=]() { const size_t a = nc * t / nt, b = nc * (t + 1) / nt; for (size_t x = a; x < b; x += 4096) q[x] = 0; });
+            for (std::thread &x : th) x.join();
+        }
+        if (!q) { cerr << "ERROR: cannot allocate " << nc << " bytes of " << (pinned ? "page-locked " : "") << "memory" << (pinned ? string(", ") + tc_last_error() : string()) << endl; exit(1); }
         if (len) memcpy(q, p, len);
-        tc_host_free(p);
+        release();
         p = q; cap = nc;
     }
+    void release() { if (p) { if (pinned) tc_host_free(p); else free(p); } p = nullptr; }
     void append(const uint8_t *src, size_t n) { reserve(len + n + 64); memcpy(p + len, src, n); len += n; }
     size_t size() const { return len; }
-    ~PinnedBuf() { tc_host_free(p); }
+    ~PinnedBuf() { release(); }
 };
 
 struct Batch {
@@ -338,6 +373,8 @@ struct Batch {
 void flush_batch(tc_ctx *ctx, const Options &o, Batch &b, vector<Genome> &out)
 {
     if (b.genomes.empty()) return;
+    const double t_flush = now_s();
+    struct Report { double t0; size_t bytes, ng; ~Report() { if (getenv("TCLUST_TIMING")) cerr << "[tclust timing] sketch batch: " << ng << " genomes, " << bytes / 1e6 << " MB in " << (now_s() - t0) * 1e3 << " ms" << endl; } } report{t_flush, b.seq.len, b.genomes.size()};
     const uint32_t ng = (uint32_t)b.genomes.size();
     b.seq.reserve(b.seq.len + 64);
     memset(b.seq.p + b.seq.len, 0, 64);
@@ -372,10 +409,12 @@ void flush_batch(tc_ctx *ctx, const Options &o, Batch &b, vector<Genome> &out)
 // two batches: one is being filled by the parser while the other is sketched by a background thread
 struct Feeder {
     tc_ctx *ctx; const Options &o; vector<Genome> &out;
+    std::function<tc_ctx *()> late_ctx;       // set when the feeder was built before the context (pageable buffers)
     Batch batch[2]; int cur = 0; std::thread worker; bool running = false;
-    Feeder(tc_ctx *c, const Options &opt, vector<Genome> &dst, uint64_t expect_bytes, uint64_t batch_bytes)
+    Feeder(tc_ctx *c, const Options &opt, vector<Genome> &dst, uint64_t expect_bytes, uint64_t batch_bytes, bool pinned = true)
         : ctx(c), o(opt), out(dst)
     {
+        batch[0].seq.pinned = batch[1].seq.pinned = pinned;
         // one allocation per buffer: the whole input if it fits a batch, else a full batch (+ the largest overshoot)
         const uint64_t first = std::min<uint64_t>(expect_bytes + (1u << 20), batch_bytes + (batch_bytes >> 3));
         batch[0].seq.reserve(first);
@@ -386,6 +425,7 @@ struct Feeder {
     void submit()                      // hand the filled batch to the GPU, continue in the other one
     {
         wait();                        // results are appended in submission order
+        if (!ctx && late_ctx) ctx = late_ctx();
         Batch *b = &batch[cur];
         worker = std::thread([this, b]() { flush_batch(ctx, o, *b, out); });
         running = true;
@@ -395,7 +435,7 @@ struct Feeder {
 };
 
 // list mode: one genome per file (sketchFiles)
-void sketch_files(tc_ctx *ctx, const Options &o, vector<Genome> &out)
+void sketch_files(const std::function<tc_ctx *()> &get_ctx, const Options &o, vector<Genome> &out)
 {
     fprintf(stderr, "-----input fileList, sketch by file\n");
     vector<string> files = read_list(o.input);
@@ -410,36 +450,68 @@ void sketch_files(tc_ctx *ctx, const Options &o, vector<Genome> &out)
         make_shuffled_dim(g_kssd.half_subk);
     }
     const uint64_t batch_bytes = 1ull << 29;
-    struct Parsed { vector<uint8_t> seq; vector<Record> recs; int file_len = 0; bool ok = false; };
-    size_t next = 0;
-    Feeder feeder(ctx, o, out, g_input_bytes, batch_bytes);
-    while (next < nfiles) {
-        // read + parse a window of files on the host threads, then append them in list order
-        const size_t win = std::min(nfiles - next, (size_t)std::max(o.threads * 4, 16));
-        vector<Parsed> parsed(win);
-        std::atomic<size_t> cursor{0};
-        auto worker = [&]() {
-            for (;;) {
-                size_t i = cursor.fetch_add(1);
-                if (i >= win) break;
-                string text;
-                if (!read_whole_gz(files[next + i], text)) continue;
-                parse_fasta(text, true, parsed[i].seq, parsed[i].recs);
-                if (o.containment && !o.fast) { uint64_t u; file_size_like_reference(files[next + i], u, parsed[i].file_len); }
-                parsed[i].ok = true;
+    // Producer / consumer (RabbitFX's producer thread + kseq consumers, FastxStream.cpp:45-71,
+    // SketchInfo.cpp:878-948): the host threads read and parse files ahead of the consumer -- up to `ahead` files in
+    // flight -- while the consumer appends them, in list order, to the page-locked batch the GPU sketches next.  The
+    // CUDA context (seconds to come up) is only waited for when the first batch buffer is allocated, so its start-up
+    // overlaps reading and parsing.
+    struct Parsed { vector<uint8_t> seq; vector<Record> recs; int file_len = 0; bool ok = false, ready = false; };
+    vector<Parsed> parsed(nfiles);
+    std::mutex mu;
+    std::condition_variable cv_ready, cv_room;
+    size_t consumed = 0, cursor = 0;
+    // run-ahead of the parsers: about 2 GB of input in flight (average file size from cal_size), at least a few files per thread
+    const size_t avg_file = std::max<uint64_t>(g_input_bytes / std::max<size_t>(nfiles, 1), 1);
+    const size_t ahead = std::max<size_t>(std::max<size_t>((size_t)o.threads * 4, 16), (size_t)((2ull << 30) / avg_file));
+    auto worker = [&]() {
+        for (;;) {
+            size_t i;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_room.wait(lk, [&]() { return cursor >= nfiles || cursor < consumed + ahead; });
+                if (cursor >= nfiles) return;
+                i = cursor++;
             }
-        };
-        vector<std::thread> th;
-        for (int t = 0; t < std::max(1, std::min<int>(o.threads, (int)win)); t++) th.emplace_back(worker);
-        for (auto &t : th) t.join();
-        for (size_t i = 0; i < win; i++) {
             Parsed &p = parsed[i];
-            if (!p.ok) { fprintf(stderr, "cannot open the genome file: %s\n", files[next + i].c_str()); exit(1); }
-            uint64_t total_len = 0;
-            for (const Record &r : p.recs) total_len += r.end - r.begin;
-            if (total_len < o.min_len) continue;                       // SketchInfo.cpp:963
+            static thread_local string text;                    // reused from file to file: no fresh pages per file
+            if (read_whole_gz(files[i], text)) {
+                parse_fasta(text, true, p.seq, p.recs);
+                if (o.containment && !o.fast) { uint64_t u; file_size_like_reference(files[i], u, p.file_len); }
+                p.ok = true;
+            }
+            { std::lock_guard<std::mutex> lk(mu); p.ready = true; }
+            cv_ready.notify_all();
+        }
+    };
+    vector<std::thread> pool;
+    for (int t = 0; t < std::max(1, std::min<int>(o.threads, (int)nfiles)); t++) pool.emplace_back(worker);
+    std::unique_ptr<Feeder> feeder_p;
+    for (size_t i = 0; i < nfiles; i++) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_ready.wait(lk, [&]() { return parsed[i].ready; });
+        }
+        Parsed &p = parsed[i];
+        if (!p.ok) { fprintf(stderr, "cannot open the genome file: %s\n", files[i].c_str()); exit(1); }
+        uint64_t total_len = 0;
+        for (const Record &r : p.recs) total_len += r.end - r.begin;
+        if (total_len >= o.min_len) {                                  // SketchInfo.cpp:963
+            if (!feeder_p) {
+                // an input of at most two batches goes through plain memory and does not wait for the context before
+                // its first batch is complete; larger inputs reuse two page-locked buffers
+                const bool pinned = g_input_bytes > 2 * batch_bytes;
+                const double tw = now_s();
+                tc_ctx *c = pinned ? get_ctx() : nullptr;
+                const double ta = now_s();
+                feeder_p.reset(new Feeder(c, o, out, g_input_bytes, batch_bytes, pinned));
+                feeder_p->late_ctx = get_ctx;
+                if (getenv("TCLUST_TIMING") && pinned)
+                    cerr << "[tclust timing] feeder: waited " << (ta - tw) * 1e3 << " ms for the context, page-locked batch buffers "
+                         << (now_s() - ta) * 1e3 << " ms" << endl;
+            }
+            Feeder &feeder = *feeder_p;
             Genome g;
-            g.file_name = files[next + i];
+            g.file_name = files[i];
             g.name = "noName"; g.comment = "noName";                    // :934-939
             if (!p.recs.empty()) { g.name = p.recs[0].name; if (p.recs[0].has_comment) g.comment = p.recs[0].comment; }
             g.total_len = total_len;
@@ -453,8 +525,13 @@ void sketch_files(tc_ctx *ctx, const Options &o, vector<Genome> &out)
             b.genomes.push_back(std::move(g));
             if (b.seq.size() >= batch_bytes) feeder.submit();
         }
-        next += win;
+        vector<uint8_t>().swap(p.seq); vector<Record>().swap(p.recs);
+        { std::lock_guard<std::mutex> lk(mu); consumed = i + 1; }
+        cv_room.notify_all();
     }
+    for (std::thread &t : pool) t.join();
+    if (!feeder_p) { get_ctx(); return; }
+    Feeder &feeder = *feeder_p;
     feeder.finish();
     for (size_t i = 0; i < out.size(); i++) out[i].id = (int)i;
 }
@@ -1199,7 +1276,7 @@ int main(int argc, char **argv)
         if (ctx_ready.get()) die("tc_ctx_create: " + ctx_err);
         if (timing) cerr << "[tclust timing] CUDA context ready " << (now_s() - t_ctx) * 1e3 << " ms after start" << endl;
     };
-    if (!(o.presketched && !o.append)) need_ctx();
+    if (o.append || o.premsted) need_ctx();          // the other flows wait for it where they first need it
     vector<Genome> g;
     if (o.append) {
         // classic append (no saved cluster state): append_clust_mst (sub_command.cpp:1578-1757) and
@@ -1230,7 +1307,7 @@ int main(int argc, char **argv)
             cerr << "---the thread number is: " << o.threads << endl;
             cerr << "---the threshold is: " << o.threshold << endl;
             vector<Genome> add;
-            sketch_files(ctx, o, add);                                   // sets g_kssd from o.kmer / o.drlevel
+            sketch_files([&]() { return ctx; }, o, add);                                   // sets g_kssd from o.kmer / o.drlevel
             if (g_kssd.half_k != pre_info.half_k || g_kssd.half_subk != pre_info.half_subk || g_kssd.drlevel != pre_info.drlevel)
                 die("append_clust_mst_fast(), the KSSD parameters of " + o.folder + " cannot be reproduced for the new genomes");
             g_kssd = pre_info;
@@ -1275,7 +1352,7 @@ int main(int argc, char **argv)
         cerr << "---the thread number is: " << o.threads << endl;
         cerr << "---the threshold is: " << o.threshold << endl;
         vector<Genome> add;
-        if (o.by_file) sketch_files(ctx, o, add); else sketch_sequences(ctx, o, add);
+        if (o.by_file) sketch_files([&]() { return ctx; }, o, add); else sketch_sequences(ctx, o, add);
         const uint32_t n_pre = (uint32_t)pre.size();
         g = std::move(pre);
         for (Genome &x : add) g.push_back(std::move(x));
@@ -1358,7 +1435,8 @@ int main(int argc, char **argv)
                 "(SURVEY.md 8a-9) and is out of scope");
         if (!(o.fast ? tune_kssd_parameters(o) : tune_parameters(o))) return 1;
         double t0 = now_s();
-        if (o.by_file) sketch_files(ctx, o, g); else sketch_sequences(ctx, o, g);
+        if (o.by_file) sketch_files([&]() { need_ctx(); return ctx; }, o, g); else { need_ctx(); sketch_sequences(ctx, o, g); }
+        need_ctx();
         if (o.fast) o.kmer = 2 * g_kssd.half_k;                          // SketchInfo.cpp:1019-1020, MST.cpp:219
         cerr << "-----the size of sketches (number of genomes or sequences) is: " << g.size() << endl;
         double t1 = now_s();

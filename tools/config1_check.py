@@ -3,7 +3,9 @@
 rates cycled over 0.001..0.05), k=21 s=1000 -d 0.05, list mode.  Runs the UNMODIFIED reference
 (oracle/_ref/clust-mst -t 1) and our binary on the same files and compares: hash.sketch / info.sketch byte-identical,
 sorted MST weights bit-identical, same partition.  Prints one JSON line with the phase times of both.
-usage: python tools/config1_check.py [workdir] [n_families] [per_family] [length]"""
+With --ref-threads T the reference also runs with -t T (its sketch order then depends on the thread schedule, so only
+its wall/phase times are recorded from that run, not compared).
+usage: python tools/config1_check.py [workdir] [n_families] [per_family] [length] [--ref-threads T]"""
 import glob
 import json
 import os
@@ -34,6 +36,9 @@ def run(exe, args, cwd):
 
 
 def main():
+    ref_threads = 0
+    if "--ref-threads" in sys.argv:
+        i = sys.argv.index("--ref-threads"); ref_threads = int(sys.argv[i + 1]); del sys.argv[i:i + 2]
     work = sys.argv[1] if len(sys.argv) > 1 else "/tmp/config1"
     nf = int(sys.argv[2]) if len(sys.argv) > 2 else 50
     per = int(sys.argv[3]) if len(sys.argv) > 3 else 20
@@ -69,6 +74,12 @@ def main():
            "partition_identical": part(os.path.join(work, "ref", "out.txt")) == part(os.path.join(work, "ours", "out.txt")),
            "clusters": len(part(os.path.join(work, "ours", "out.txt"))),
            "reference_t1": {"wall_s": rt, "phases_s": rph}, "ours": {"wall_s": ot, "phases_s": oph}}
+    res["ours"]["timing_lines"] = [l for l in oerr.splitlines() if l.startswith("[tclust timing]")]
+    if ref_threads > 1:
+        _, rt2, rph2, _ = run(os.path.join(ROOT, "oracle", "_ref", "clust-mst"), ["-t", str(ref_threads)] + args, os.path.join(work, "ref_mt"))
+        res["reference_mt"] = {"threads": ref_threads, "wall_s": rt2, "phases_s": rph2}
+        _, ot2, oph2, _ = run(os.path.join(ROOT, "rabbittclust_b200", "host", "bin", "clust-mst"), args, os.path.join(work, "ours2"))
+        res["ours_second_run"] = {"wall_s": ot2, "phases_s": oph2}
     print(json.dumps(res))
     assert res["hash_sketch_identical"] and res["info_sketch_identical"] and res["mst_weights_identical"] and res["partition_identical"]
 

@@ -8,7 +8,8 @@ import sys
 src = sys.argv[1]
 pairs = float(sys.argv[2]) if len(sys.argv) > 2 else 100000 * 99999 / 2
 d = json.load(open(src))
-k = [l for l in d["launches"] if "k3j_block_kernel" in l["kernel"]][0]
+kname = sys.argv[3] if len(sys.argv) > 3 else "k3s_tile_kernel"
+k = [l for l in d["launches"] if kname in l["kernel"]][0]
 
 
 def val(name):
@@ -19,7 +20,7 @@ def val(name):
 rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
 inst = val("smsp__inst_executed.sum")
 out = {
-    "kernel": "k3j_block_kernel",
+    "kernel": kname,
     "source": "%s (ncu --set full --clock-control none, bench.py --steps 1 --warmup 3 --no-sketch --no-semb --no-cpu, "
               "one launch = one dense pass over %.6g pairs, generation order)" % (src, pairs),
     "dram_bytes_per_launch": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr,
