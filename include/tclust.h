@@ -91,10 +91,14 @@ int tc_sketch_minhash_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const uint64_t *
  * shuffled_dim: host table of 1<<(4*half_subk) ints (generate_shuffle_dim,
  * SketchInfo.cpp:60-102; glibc rand() -- host-only by construction; tc_kssd_shuffled_dim
  * builds it, half_subk = 6 unless drlevel > 4, SketchInfo.cpp:1022).
- * out: ngenomes rows of out_stride u64, ascending, distinct; out_n[g] = count (an error is
- * returned if a genome yields more than out_stride hashes).
+ * out: ngenomes rows of out_stride u64, ascending, distinct; out_n[g] = count.  If a genome yields more than out_stride
+ * hashes the call returns TC_ERR_KSSD_STRIDE (nothing is truncated silently).
  */
+#define TC_ERR_KSSD_STRIDE 2   /* tc_sketch_kssd*: some genome needs a longer output row; tc_kssd_needed_stride() says how long */
 int tc_kssd_shuffled_dim(int half_subk, int32_t *out /* 1 << (4*half_subk) ints */);
+/* after tc_sketch_kssd* returned TC_ERR_KSSD_STRIDE on this thread: the largest number of hashes (before deduplication)
+ * any genome of that call produced -- retry with out_stride >= it */
+uint32_t tc_kssd_needed_stride(void);
 int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off,
                    const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes,
                    int kmer_size, int drlevel, const int32_t *shuffled_dim,

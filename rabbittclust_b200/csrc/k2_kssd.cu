@@ -296,13 +296,18 @@ int k2_enqueue(tc_ctx *ctx, K2Workspace *ws, K2Slot &sl, cudaStream_t st, K2Args
     return 0;
 }
 
+static thread_local uint32_t g_kssd_needed = 0;
+
 int k2_check_overflow(K2Workspace *ws, cudaStream_t st, uint64_t out_stride)
 {
     unsigned int ovf = 0;
     TC_CUDA(cudaMemcpyAsync(&ovf, ws->d_overflow, 4, cudaMemcpyDeviceToHost, st));
     TC_CUDA(cudaStreamSynchronize(st));
-    TC_CHECK(ovf == 0, "tc_sketch_kssd: a genome produced %u hashes, more than out_stride=%llu", ovf,
-             (unsigned long long)out_stride);
+    if (ovf != 0) {      // distinct return code; the needed row length is in the message AND in tc_kssd_needed_stride()
+        tc_set_error("tc_sketch_kssd: a genome produced %u hashes, more than out_stride=%llu", ovf, (unsigned long long)out_stride);
+        g_kssd_needed = ovf;
+        return TC_ERR_KSSD_STRIDE;
+    }
     return 0;
 }
 
@@ -435,3 +440,5 @@ extern "C" int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *
     if (!rc && e1 != cudaSuccess) { tc_set_error("tc_sketch_kssd: %s", cudaGetErrorString(e1)); rc = 1; }
     return rc;
 }
+
+extern "C" uint32_t tc_kssd_needed_stride(void) { return g_kssd_needed; }

@@ -390,7 +390,10 @@ void flush_batch(tc_ctx *ctx, const Options &o, Batch &b, vector<Genome> &out)
             const int rc = tc_sketch_kssd(ctx, b.seq.p, b.rec_off.data(), b.rec2genome.data(), b.rec2genome.size(), ng, o.kmer,
                                           o.drlevel, g_shuffled_dim.data(), hashes.data(), stride, out_n.data());
             if (!rc) break;
-            if (strstr(tc_last_error(), "more than out_stride") && stride < b.longest + 1024) { stride = std::min<uint64_t>(stride * 8, b.longest + 1024); continue; }
+            if (rc == TC_ERR_KSSD_STRIDE && stride < b.longest + 1024) {      // grow to the reported need, not by a guess
+                stride = std::min<uint64_t>(std::max<uint64_t>((uint64_t)tc_kssd_needed_stride() + 64, stride + 1024), b.longest + 1024);
+                continue;
+            }
             tc_or_die(rc, "kssd sketch generation");
         }
     } else {
