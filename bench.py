@@ -414,9 +414,11 @@ def run_pairs(args):
         if dist is None:
             ctx.upload(hashes=hp, off=off)
             return int(h.nbytes + off.nbytes)
-        # every rank copies only its 1/world share from the host; the shares are all-gathered over NVLink
+        # every rank copies and sorts only its 1/world share; the sorted runs are all-gathered over NVLink and merged
         from rabbittclust_b200 import mst_dist
-        return mst_dist.upload_sharded(ctx, h_pin, off, dist, dev) + int(off.nbytes)
+        if os.environ.get("TCLUST_BENCH_UPLOAD") == "allgather_raw":      # round 1's scheme: all-gather the raw hashes, every rank sorts all
+            return mst_dist.upload_sharded(ctx, h_pin, off, dist, dev) + int(off.nbytes)
+        return mst_dist.upload_sharded_runs(ctx, h_pin, off, dist, dev) + int(off.nbytes)
 
     # ---- value: the whole operation on resident sketches -- dense pass (this rank's units) + every Boruvka round +
     #      the sorted MST on the host (tc_mst), CUDA events on the library's stream

@@ -124,6 +124,19 @@ int tc_sketches_upload_dev(tc_ctx *ctx, const uint64_t *hashes_dev, const uint64
  * staging buffers while earlier chunks are already on their way to the device, so the caller needs no flat copy. */
 int tc_sketches_upload_rows(tc_ctx *ctx, const uint64_t *const *rows, const uint64_t *sizes, uint32_t n);
 
+/*
+ * Multi-GPU upload (every GPU of a group needs all sketches resident, but each should move and sort only its share):
+ * rank r copies its contiguous share [pos_base, pos_base + len) of the flat hash array to its device and calls
+ * tc_upload_sort_share_dev, which sorts the share by hash and pairs every hash with its position in the flat array; the
+ * ranks all-gather the sorted runs (keys + positions; NCCL, plumbing) and every rank calls tc_sketches_upload_runs_dev,
+ * which merges the runs instead of sorting everything again and then proceeds exactly like tc_sketches_upload.  The
+ * original u64 hashes are not kept (tc_pair_common impl 1 is unavailable after it).  Used by bench.py (e2e, N > 1).
+ */
+int tc_upload_sort_share_dev(tc_ctx *ctx, const uint64_t *hashes_dev, uint64_t len, uint64_t pos_base,
+                             uint64_t *keys_out_dev, uint32_t *pos_out_dev);
+int tc_sketches_upload_runs_dev(tc_ctx *ctx, const uint64_t *keys_dev, const uint32_t *pos_dev, const uint64_t *run_off,
+                                uint32_t nruns, const uint64_t *off, uint32_t n);
+
 /* validation: common[i-i0][j-j0] = |sketch_i n sketch_j| for i in [i0,i1), j in [j0,j1)
  * (semantic A: the counts of src/MST.cpp:1409-1435).  impl 0 = tiled merge kernel (k3_tile.cu),
  * 1 = independent u64 global-memory merge kernel, 2 = hash-join kernel (k3h_join.cu). */

@@ -63,7 +63,8 @@ struct tc_ctx {
     // resident sketches (HP-2)
     uint32_t n = 0;               // number of sketches
     uint64_t total = 0;           // total hashes
-    uint64_t *d_hashes = nullptr; // original u64 hashes, ragged row-major (validation kernel, greedy first-hit)
+    uint64_t *d_hashes = nullptr; // original u64 hashes, ragged row-major (independent validation kernel only)
+    bool hashes_resident = false; // false after an upload from sorted runs (tc_sketches_upload_runs_dev)
     uint64_t *d_off = nullptr;    // n+1 offsets
     uint32_t *d_size = nullptr;   // n sizes
     uint32_t *d_ranks = nullptr;  // order-preserving dense u32 ranks of the hashes, same layout as d_hashes

@@ -157,6 +157,11 @@ __global__ void iota_kernel(uint32_t *p, uint64_t n)
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = (uint32_t)i;
 }
+__global__ void iota_base_kernel(uint32_t *p, uint64_t n, uint32_t base)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = base + (uint32_t)i;
+}
 __global__ void head_flag_kernel(const uint64_t *keys, uint32_t *flag, uint64_t n)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -362,7 +367,65 @@ int tc_ensure_interleaved(tc_ctx *ctx)
     return 0;
 }
 
-static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_device, const uint64_t *off, uint32_t n)
+// the hashes arrive as `nruns` runs already sorted by hash (keys ascending inside run r = [run_off[r], run_off[r+1])),
+// each with the position its hash has in the flat array (tc_sketches_upload_runs_dev)
+struct SortedRuns { const uint64_t *keys; const uint32_t *pos; const uint64_t *run_off; uint32_t nruns; };
+
+__global__ void check_sorted_ranks_kernel(const uint32_t *r, const unsigned long long *off, uint32_t n, unsigned int *bad)
+{
+    const uint32_t g = blockIdx.x;
+    if (g >= n) return;
+    const unsigned long long o = off[g], len = off[g + 1] - o;
+    for (unsigned long long i = threadIdx.x + 1; i < len; i += blockDim.x)
+        if (r[o + i] <= r[o + i - 1]) { atomicMin(bad, g); return; }
+}
+
+// merge the runs pairwise (level by level, ping-pong between the caller's buffers and the workspace) into one sorted run
+static int merge_sorted_runs(tc_ctx *ctx, const SortedRuns &r, uint64_t total, UploadSort *us)
+{
+    cudaStream_t st = ctx->stream;
+    uint64_t longest = 0;
+    for (uint32_t i = 0; i < r.nruns; i++) longest = std::max(longest, r.run_off[i + 1] - r.run_off[i]);
+    if (upload_sort_workspace(ctx, total, std::max<uint64_t>(longest, 1024), us)) return 1;
+    std::vector<uint64_t> bounds(r.run_off, r.run_off + r.nruns + 1);
+    const uint64_t *ks = r.keys; const uint32_t *vs = r.pos;
+    uint64_t *kd = us->k_a; uint32_t *vd = us->v_a;
+    int level = 0;
+    if (bounds.size() == 2) {          // one run: it is the sorted array already; copy (the caller's buffer is not ours to keep)
+        TC_CUDA(cudaMemcpyAsync(us->k_a, ks, total * 8, cudaMemcpyDeviceToDevice, st));
+        TC_CUDA(cudaMemcpyAsync(us->v_a, vs, total * 4, cudaMemcpyDeviceToDevice, st));
+        us->keys = us->k_a; us->vals = us->v_a; us->spare = us->v_b;
+        return 0;
+    }
+    while (bounds.size() > 2) {
+        std::vector<uint64_t> nb{bounds[0]};
+        for (size_t i = 0; i + 1 < bounds.size(); i += 2) {
+            const uint64_t a0 = bounds[i], a1 = bounds[i + 1], b1 = i + 2 < bounds.size() ? bounds[i + 2] : a1;
+            if (b1 == a1) {
+                if (a1 > a0) {
+                    TC_CUDA(cudaMemcpyAsync(kd + a0, ks + a0, (a1 - a0) * 8, cudaMemcpyDeviceToDevice, st));
+                    TC_CUDA(cudaMemcpyAsync(vd + a0, vs + a0, (a1 - a0) * 4, cudaMemcpyDeviceToDevice, st));
+                }
+            } else {
+                size_t tb = us->tmp_bytes;
+                TC_CUDA(cub::DeviceMerge::MergePairs(us->tmp, tb, ks + a0, vs + a0, (int)(a1 - a0), ks + a1, vs + a1, (int)(b1 - a1),
+                                                     kd + a0, vd + a0, ::cuda::std::less<>{}, st));
+                ctx->launches += 2;
+            }
+            nb.push_back(b1);
+        }
+        bounds.swap(nb);
+        ks = kd; vs = vd;
+        level++;
+        kd = (level & 1) ? us->k_b : us->k_a; vd = (level & 1) ? us->v_b : us->v_a;
+    }
+    us->keys = ks; us->vals = vs;
+    us->spare = const_cast<uint32_t *>(vs) == us->v_a ? us->v_b : us->v_a;
+    return 0;
+}
+
+static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_device, const uint64_t *off, uint32_t n,
+                         const SortedRuns *runs = nullptr)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     PhaseTimer pt(ctx->stream);
@@ -373,7 +436,7 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     // (cub's merge and scan entry points used by the rank transform count items in an int)
     TC_CHECK(total <= 0x7FFFFFFFull, "tc_sketches_upload: %llu hashes exceed the 2^31 - 1 one context ranks at once",
              (unsigned long long)total);
-    ctx->n = n; ctx->total = total;
+    ctx->n = n; ctx->total = total; ctx->hashes_resident = true;
     ctx->h_off.assign(off, off + n + 1);
     ctx->h_size.resize(n);
     uint32_t max_size = 0;
@@ -384,7 +447,7 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     }
     cudaStream_t st = ctx->stream;
     const uint64_t tot1 = std::max<uint64_t>(total, 1);
-    if (ensure_cap(&ctx->d_hashes, &ctx->cap_hashes, tot1) || ensure_cap(&ctx->d_ranks, &ctx->cap_ranks, tot1)) return 1;
+    if ((!runs && ensure_cap(&ctx->d_hashes, &ctx->cap_hashes, tot1)) || ensure_cap(&ctx->d_ranks, &ctx->cap_ranks, tot1)) return 1;
     if (n + 1 > ctx->cap_n) {
         cudaFree(ctx->d_off); cudaFree(ctx->d_size);
         ctx->d_off = nullptr; ctx->d_size = nullptr; ctx->cap_n = 0;
@@ -398,10 +461,14 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     // the last merges run under the PCIe copy (upload_sorted_runs below).  TCLUST_UPLOAD_OVERLAP=0: one copy, one sort; =1: pieces whatever the size.
     const char *ov = getenv("TCLUST_UPLOAD_OVERLAP");
     const bool ov_off = ov && !strcmp(ov, "0"), ov_force = ov && !strcmp(ov, "1");   // 1: whatever the size (tests)
-    const bool chunked = !hashes_on_device && hashes != ctx->d_hashes && !ov_off &&
+    const bool chunked = !runs && !hashes_on_device && hashes != ctx->d_hashes && !ov_off &&
                          (total >= (16ull << 20) || (ov_force && total >= 2));
     UploadSort us;
-    if (chunked) {
+    if (runs) {
+        // sorted runs from the ranks of a multi-GPU upload: no copy of the flat hashes (d_hashes stays empty: only the
+        // independent validation kernel reads it), the order check runs on the ranks below
+        ctx->hashes_resident = false;
+    } else if (chunked) {
         if (upload_sorted_runs(ctx, hashes, total, &us)) return 1;
     } else if (hashes != ctx->d_hashes)   // tc_sketches_upload_rows has staged them in place already
         TC_CUDA(cudaMemcpyAsync(ctx->d_hashes, hashes, total * 8,
@@ -409,7 +476,7 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     TC_CUDA(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     sizes_kernel<<<nblk(n, 256), 256, 0, st>>>(reinterpret_cast<unsigned long long *>(ctx->d_off), ctx->d_size, n);
     ctx->launches++;
-    {   // input contract check (0.8 GB read at N = 100k: ~0.2 ms)
+    if (!runs) {   // input contract check (0.8 GB read at N = 100k: ~0.2 ms)
         unsigned int *d_bad = reinterpret_cast<unsigned int *>(ctx->d_edge_count + 3), h_bad = 0xFFFFFFFFu;
         TC_CUDA(cudaMemsetAsync(d_bad, 0xFF, 4, st));
         check_sorted_kernel<<<n, 128, 0, st>>>(ctx->d_hashes, reinterpret_cast<unsigned long long *>(ctx->d_off), n, d_bad);
@@ -432,7 +499,9 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
         TC_CUDA(cudaMemsetAsync(ctx->d_multi, 0, 4, ctx->stream));
     }
     if (total > 0) {
-        if (!chunked) {
+        if (runs) {
+            if (merge_sorted_runs(ctx, *runs, total, &us)) return 1;
+        } else if (!chunked) {
             // sort workspace: kept in the context's scratch between uploads (24 B per hash + cub's temporary storage)
             if (upload_sort_workspace(ctx, total, 0, &us)) return 1;
             pt.mark("sort workspace");
@@ -458,6 +527,21 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
         TC_CUDA(cudaStreamSynchronize(st));
         pt.mark("flags + scan + scatter");
     }
+    if (runs && total > 0) {      // the contract check on the ranks (order-preserving: same verdict as on the hashes)
+        unsigned int *d_bad = reinterpret_cast<unsigned int *>(ctx->d_edge_count + 3), h_bad = 0xFFFFFFFFu;
+        TC_CUDA(cudaMemsetAsync(d_bad, 0xFF, 4, st));
+        check_sorted_ranks_kernel<<<n, 128, 0, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off), n, d_bad);
+        ctx->launches++;
+        TC_CUDA(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+        TC_CUDA(cudaStreamSynchronize(st));
+        if (h_bad != 0xFFFFFFFFu) {
+            const uint32_t g = h_bad;
+            reset_sketches(ctx);
+            tc_set_error("tc_sketches_upload: sketch %u is not strictly ascending (sketches must be sorted and duplicate-free, "
+                         "as Sketch::MinHash::storeMinHashes returns them)", g);
+            return 1;
+        }
+    }
 
     // ---- group-interleaved layout: only the first-generation merge kernel (semantic B, validation) reads it; built
     //      on first use (tc_ensure_interleaved)
@@ -477,6 +561,41 @@ extern "C" int tc_sketches_upload(tc_ctx *ctx, const uint64_t *hashes, const uin
 extern "C" int tc_sketches_upload_dev(tc_ctx *ctx, const uint64_t *hashes_dev, const uint64_t *off, uint32_t n)
 {
     return upload_common(ctx, hashes_dev, true, off, n);
+}
+
+// ---- multi-GPU upload: every rank sorts its share of the hashes, the sorted runs are all-gathered, every rank merges
+extern "C" int tc_upload_sort_share_dev(tc_ctx *ctx, const uint64_t *hashes_dev, uint64_t len, uint64_t pos_base,
+                                        uint64_t *keys_out_dev, uint32_t *pos_out_dev)
+{
+    TC_CHECK(ctx && (len == 0 || (hashes_dev && keys_out_dev && pos_out_dev)), "tc_upload_sort_share_dev: bad arguments");
+    TC_CHECK(pos_base + len <= 0x7FFFFFFFull, "tc_upload_sort_share_dev: positions exceed 2^31 - 1");
+    TC_CUDA(cudaSetDevice(ctx->device));
+    if (!len) return 0;
+    cudaStream_t st = ctx->stream;
+    size_t tmp_bytes = 0;
+    TC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr,
+                                            (uint32_t *)nullptr, (int)len, 0, 64, st));
+    void *ws = nullptr;
+    const size_t o_tmp = (len * 4 + 255) & ~(size_t)255;
+    if (tc_scratch(ctx, o_tmp + tmp_bytes, &ws)) return 1;
+    uint32_t *iota = static_cast<uint32_t *>(ws);
+    iota_base_kernel<<<nblk(len, 256), 256, 0, st>>>(iota, len, (uint32_t)pos_base);
+    TC_CUDA(cub::DeviceRadixSort::SortPairs(static_cast<uint8_t *>(ws) + o_tmp, tmp_bytes, hashes_dev, keys_out_dev, (const uint32_t *)iota,
+                                            pos_out_dev, (int)len, 0, 64, st));
+    ctx->launches += 10;
+    TC_CUDA(cudaStreamSynchronize(st));          // the outputs are handed to the caller's collective next
+    return 0;
+}
+
+extern "C" int tc_sketches_upload_runs_dev(tc_ctx *ctx, const uint64_t *keys_dev, const uint32_t *pos_dev, const uint64_t *run_off,
+                                           uint32_t nruns, const uint64_t *off, uint32_t n)
+{
+    TC_CHECK(ctx && keys_dev && pos_dev && run_off && off && nruns >= 1, "tc_sketches_upload_runs_dev: bad arguments");
+    TC_CHECK(run_off[0] == 0 && run_off[nruns] == off[n], "tc_sketches_upload_runs_dev: the runs hold %llu hashes, the offsets %llu",
+             (unsigned long long)run_off[nruns], (unsigned long long)off[n]);
+    for (uint32_t r = 0; r < nruns; r++) TC_CHECK(run_off[r + 1] >= run_off[r], "tc_sketches_upload_runs_dev: run offsets not monotone");
+    const SortedRuns runs{keys_dev, pos_dev, run_off, nruns};
+    return upload_common(ctx, nullptr, true, off, n, &runs);
 }
 
 // rows -> d_hashes through two page-locked staging buffers: host threads gather chunk c+1 while chunk c is copied
@@ -531,6 +650,7 @@ extern "C" int tc_pair_common(tc_ctx *ctx, uint32_t i0, uint32_t i1, uint32_t j0
     TC_CUDA(cudaSetDevice(ctx->device));
     TC_CHECK(ctx->n > 0, "tc_pair_common: no sketches uploaded");
     TC_CHECK(i0 <= i1 && i1 <= ctx->n && j0 <= j1 && j1 <= ctx->n, "tc_pair_common: range out of bounds");
+    TC_CHECK(impl != 1 || ctx->hashes_resident, "tc_pair_common: impl 1 reads the original hashes, which an upload from sorted runs does not keep");
     const size_t cells = (size_t)(i1 - i0) * (j1 - j0);
     if (!cells) return 0;
     uint32_t *d_out = nullptr;

@@ -190,6 +190,49 @@ def upload_sharded(ctx, hashes_pinned, off, dist, device):
     return (per + tail) * 8
 
 
+def upload_sharded_runs(ctx, hashes_pinned, off, dist, device):
+    """Like upload_sharded, but no rank sorts more than its share: every rank copies 1/world of the raw hashes over its
+    own PCIe link and sorts it with the positions (tc_upload_sort_share_dev); the sorted runs -- not the raw hashes --
+    are all-gathered over NVLink (12 B per hash) and every rank MERGES them (tc_sketches_upload_runs_dev) instead of
+    radix-sorting all N*s hashes again.  Returns the bytes this rank copied from the host."""
+    import torch
+    import rabbittclust_b200 as T
+    L = T.lib()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    h = hashes_pinned.view(torch.int64)
+    total = int(off[-1])
+    per = (total // world) // 2 * 2
+    tail = total - per * world                                   # remainder: one more (tiny) run, sorted by every rank
+    lo = rank * per
+    share = torch.empty(max(per, 1), dtype=torch.int64, device=device)
+    keys = torch.empty(max(per, 1), dtype=torch.int64, device=device)
+    pos = torch.empty(max(per, 1), dtype=torch.int32, device=device)
+    all_keys = torch.empty(per * world + tail + 1, dtype=torch.int64, device=device)
+    all_pos = torch.empty(per * world + tail + 1, dtype=torch.int32, device=device)
+    if per:
+        share[:per].copy_(h[lo:lo + per], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        T._chk(L.tc_upload_sort_share_dev(ctx._h, share.data_ptr(), per, lo, keys.data_ptr(), pos.data_ptr()))
+        dist.all_gather_into_tensor(all_keys[:per * world], keys[:per])
+        dist.all_gather_into_tensor(all_pos[:per * world], pos[:per])
+    if tail:
+        t_in = torch.empty(tail, dtype=torch.int64, device=device)
+        t_in.copy_(h[per * world:total], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        T._chk(L.tc_upload_sort_share_dev(ctx._h, t_in.data_ptr(), tail, per * world, all_keys[per * world:].data_ptr(),
+                                          all_pos[per * world:].data_ptr()))
+    torch.cuda.current_stream().synchronize()
+    run_off = np.array([r * per for r in range(world + 1)] + ([total] if tail else []), np.uint64)
+    if not per:
+        run_off = np.array([0, total], np.uint64)
+    off = np.ascontiguousarray(off, np.uint64)
+    ctx.n = len(off) - 1
+    ctx.sizes = np.diff(off).astype(np.int64)
+    T._chk(L.tc_sketches_upload_runs_dev(ctx._h, all_keys.data_ptr(), all_pos.data_ptr(), T._p(run_off, C.c_uint64),
+                                         len(run_off) - 1, T._p(off, C.c_uint64), ctx.n))
+    return (per + tail) * 8
+
+
 def distributed_mst(ctx, k, threshold, containment=False, dist=None):
     """Full multi-GPU MST of the sketches uploaded (replicated) on every rank's ctx."""
     import rabbittclust_b200 as T

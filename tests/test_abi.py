@@ -64,3 +64,47 @@ def test_premsted_tree_outputs_match_reference_golden(tmp_path):
     assert r.returncode == 0, r.stderr.decode()[-1000:]
     for suffix in ("", ".newick.tree", ".phylip.tree", ".nexus.tree", ".linkage.txt"):
         assert open(os.path.join(gold, "trees", "mst.txt" + suffix)).read() == open(tmp_path / ("mst.txt" + suffix)).read(), suffix
+
+
+def test_labels_merge_host_helper(tc):
+    """tc_labels_merge (host side of the sharded threshold-only clustering): union of partial partitions given as
+    smallest-id labels, checked against a plain union-find."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    n = 500
+
+    def random_partition():
+        p = np.arange(n)
+        for a, b in rng.integers(0, n, (180, 2)):
+            ra, rb = a, b
+            while p[ra] != ra:
+                ra = p[ra]
+            while p[rb] != rb:
+                rb = p[rb]
+            if ra != rb:
+                p[max(ra, rb)] = min(ra, rb)
+        lab = np.array([v for v in range(n)])
+        for v in range(n):
+            r = v
+            while p[r] != r:
+                r = p[r]
+            lab[v] = r
+        return lab.astype(np.int32)
+
+    a, b = random_partition(), random_partition()
+    nc, m = tc.labels_merge(a, b)
+    # reference: components of the graph {v - a[v]} u {v - b[v]}
+    p = np.arange(n)
+    def find(x):
+        while p[x] != x:
+            x = p[x]
+        return x
+    for lab in (a, b):
+        for v in range(n):
+            ra, rb = find(v), find(int(lab[v]))
+            if ra != rb:
+                p[max(ra, rb)] = min(ra, rb)
+    want = np.array([find(v) for v in range(n)], np.int32)
+    assert np.array_equal(m, want) and nc == len(set(want.tolist()))
+    with pytest.raises(tc.TclustError):
+        tc.labels_merge(np.array([0, 5], np.int32), np.array([0, 0], np.int32))     # label out of range
