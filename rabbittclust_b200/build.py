@@ -42,6 +42,12 @@ def build(force=False, verbose=False):
         if p.returncode:
             raise RuntimeError("nvcc failed on " + src)
     subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"])
+    # a shared library links with unresolved references: make an internal function that lost its definition a build error
+    und = subprocess.run(["nm", "-D", "--undefined-only", LIB], stdout=subprocess.PIPE).stdout.decode()
+    missing = [l.split()[-1] for l in und.splitlines() if "tc_" in l]
+    if missing:
+        os.remove(LIB)
+        raise RuntimeError("libtclust_cuda.so has undefined internal symbols: " + ", ".join(missing))
     return LIB
 
 

@@ -543,6 +543,25 @@ void sketch_files(const std::function<tc_ctx *()> &get_ctx, const Options &o, ve
 void sketch_sequences(tc_ctx *ctx, const Options &o, vector<Genome> &out)
 {
     fprintf(stderr, "-----input one file, sketch by sequence: \n");
+    if (o.fast) {
+        // sketchSequencesWithKssd + consumer_fasta_task_with_kssd (src/SketchInfo.cpp:554-642, 274-433): one KSSD sketch per
+        // record.  For an even k-mer size its window rule (`base > kmerSize`, no tuple reset on a non-ACGT byte) selects
+        // exactly the windows of the list-mode loop, because a window is only used once 2*half_k = kmerSize fresh bases
+        // have been shifted in; the hash SETS are therefore the ones K2 computes per record.  (The reference leaves
+        // them in hash-set iteration order; every consumer treats them as sets, we store them ascending.)
+        const size_t dot = o.input.find_last_of('.');
+        const string suf = dot == string::npos ? "" : o.input.substr(dot + 1);
+        if (suf != "fasta" && suf != "fna" && suf != "fa") {           // SketchInfo.cpp:555-562
+            cerr << "error input format file: " << o.input << endl << "Only support FASTA files" << endl;
+            exit(0);
+        }
+        const int half_k = (o.kmer + 1) / 2;
+        g_kssd.half_k = half_k;
+        g_kssd.half_subk = 6 - o.drlevel >= 2 ? 6 : o.drlevel + 2;
+        g_kssd.drlevel = o.drlevel;
+        g_kssd.id = (half_k << 8) + (g_kssd.half_subk << 4) + o.drlevel;
+        make_shuffled_dim(g_kssd.half_subk);
+    }
     string text;
     if (!read_whole_gz(o.input, text)) die("cannot open the genome file, " + o.input);
     vector<uint8_t> seq; vector<Record> recs;
@@ -565,6 +584,7 @@ void sketch_sequences(tc_ctx *ctx, const Options &o, vector<Genome> &out)
     }
     feeder.finish();
     for (size_t i = 0; i < out.size(); i++) out[i].id = (int)i;
+    if (o.fast) g_kssd.genome_number = (int)out.size();
 }
 
 // ---------------------------------------------------------------------------- on-disk formats
@@ -783,6 +803,9 @@ bool load_kssd_sketches(vector<Genome> &g, const string &folder)
             if (n && fread(tmp.data(), 4, n, fp) != n) die("loadKssdSketches(), truncated " + path);
             std::copy(tmp.begin(), tmp.end(), x.hashes.begin());
         }
+        // a folder the reference wrote from ONE multi-FASTA holds every sketch in hash-set iteration order
+        // (consumer_fasta_task_with_kssd, SketchInfo.cpp:396-410); its consumers treat the arrays as sets
+        if (!std::is_sorted(x.hashes.begin(), x.hashes.end())) std::sort(x.hashes.begin(), x.hashes.end());
     }
     fclose(fp);
     return by_file;
@@ -1433,10 +1456,11 @@ int main(int argc, char **argv)
         run_clustering(ctx, g, o, by_file, false, o.folder);
     } else {
         if (!o.has_input) { usage(argv[0]); die("option -i/--input or --presketched is required"); }
-        if (o.fast && !o.by_file)
-            die("--fast needs -l/--list in this build: the reference's single-file KSSD consumer is a different variant "
-                "(SURVEY.md 8a-9) and is out of scope");
         if (!(o.fast ? tune_kssd_parameters(o) : tune_parameters(o))) return 1;
+        if (o.fast && !o.by_file && (o.kmer & 1))
+            die("--fast on a single multi-FASTA needs an even k-mer size in this build (k = " + std::to_string(o.kmer) + "): for odd k the "
+                "reference's single-file KSSD consumer keeps one stale base in its window (SURVEY.md 8a-9); use -l/--list or -k " +
+                std::to_string(o.kmer + 1));
         double t0 = now_s();
         if (o.by_file) sketch_files([&]() { need_ctx(); return ctx; }, o, g); else { need_ctx(); sketch_sequences(ctx, o, g); }
         need_ctx();

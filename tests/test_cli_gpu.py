@@ -315,3 +315,50 @@ def test_clust_mst_threshold_only(genomes, tmp_path):
     assert first(a) == first(b)
     assert open(a).read().splitlines()[:3] == open(b).read().splitlines()[:3]
     assert os.path.exists(os.path.join(f1, "edge.mst")) and not os.path.exists(os.path.join(f2, "edge.mst"))
+
+
+def _read_kssd_hash_sketch(path):
+    """kssd.hash.sketch: KssdParameters{id, half_k, half_subk, drlevel, genomeNumber} then per genome size_t n + n hashes
+    (u32 unless half_k - drlevel > 8)."""
+    import struct
+    data = open(path, "rb").read()
+    pid, half_k, half_subk, drlevel, ng = struct.unpack_from("<5i", data, 0)
+    w = 8 if half_k - drlevel > 8 else 4
+    pos, out = 20, []
+    while pos < len(data):
+        (n,) = struct.unpack_from("<Q", data, pos)
+        pos += 8
+        out.append(np.frombuffer(data, "<u8" if w == 8 else "<u4", n, pos).astype(np.uint64))
+        pos += n * w
+    return (pid, half_k, half_subk, drlevel, ng), out
+
+
+def test_clust_mst_fast_single_file_matches_reference(genomes, tmp_path):
+    """--fast with ONE multi-FASTA (-i without -l; reference: sketchSequencesWithKssd / consumer_fasta_task_with_kssd,
+    src/SketchInfo.cpp:274-433,554-642): one KSSD sketch per record.  Same parameter block, same hash SET per record (the
+    reference stores them in hash-set iteration order, we ascending), kssd.info.* byte-identical, same MST weights and
+    partition; each binary reads the folder the other wrote."""
+    _, multi = genomes
+    args = ["--fast", "-i", multi, "-d", "0.05", "-o", "out.txt"]
+    rf, rerr = _run(os.path.join(REF, "clust-mst"), ["-t", "1"] + args, str(tmp_path / "ref"))
+    of, oerr = _run(os.path.join(OURS, "clust-mst"), args, str(tmp_path / "ours"))
+    pr, hr = _read_kssd_hash_sketch(os.path.join(rf, "kssd.hash.sketch"))
+    po, ho = _read_kssd_hash_sketch(os.path.join(of, "kssd.hash.sketch"))
+    assert pr == po and len(hr) == len(ho) == pr[4]
+    for a, b in zip(hr, ho):
+        assert np.array_equal(np.sort(a), b), "hash set of a record differs"
+    for fn in ("kssd.info.sketch", "kssd.info.mst"):
+        assert _same_bytes(os.path.join(rf, fn), os.path.join(of, fn)), fn
+    a = sketch_io.read_edge_mst(os.path.join(rf, "edge.mst"))
+    b = sketch_io.read_edge_mst(os.path.join(of, "edge.mst"))
+    assert np.array_equal(np.sort(a["dist"]), np.sort(b["dist"]))
+    ref_out, our_out = str(tmp_path / "ref" / "out.txt"), str(tmp_path / "ours" / "out.txt")
+    assert _partition(ref_out) == _partition(our_out)
+    _run(os.path.join(REF, "clust-mst"), ["-t", "1", "--fast", "--presketched", of, "-d", "0.05", "-o", "x.txt"], str(tmp_path / "ref"))
+    assert _partition(str(tmp_path / "ref" / "x.txt")) == _partition(ref_out)
+    _run(os.path.join(OURS, "clust-mst"), ["--fast", "--presketched", rf, "-d", "0.05", "-o", "pre.txt"], str(tmp_path / "ours"))
+    assert _partition(str(tmp_path / "ours" / "pre.txt")) == _partition(ref_out)
+    # an odd k is refused with an explanation (the reference's consumer is off by one base there)
+    r = subprocess.run([os.path.join(OURS, "clust-mst"), "--fast", "-i", multi, "-k", "17", "-d", "0.05", "-o", "odd.txt"],
+                       cwd=str(tmp_path / "ours"), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"even k-mer size" in r.stderr

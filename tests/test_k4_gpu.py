@@ -242,3 +242,28 @@ def test_bounded_memory_mst(tc, order, monkeypatch):
         c.upload(hashes=h, off=off)
         with pytest.raises(tc.TclustError, match="one work unit"):
             c.mst(21, 0.05)
+
+
+def test_k3s_long_union_lists(tc, oracle):
+    """Union lists of ~14,000 entries per block: K3S streams them in several stages on both sides (4096 row entries,
+    2048 column entries per stage, advanced like the inputs of a merge).  Every candidate edge against the oracle."""
+    rng = np.random.default_rng(77)
+    universe = rng.choice(2**40, 30000, replace=False).astype(np.uint64)
+    sk = [np.sort(rng.choice(universe, int(rng.integers(300, 900)), replace=False)) for _ in range(200)]
+    sk[17] = sk[16].copy()
+    n = len(sk)
+    want = np.tril(oracle.common_matrix(sk), -1)
+    with tc.Context(0) as c:
+        c.upload(sk)
+        npairs, nedges = c.allpairs_pass(1 << 30)
+        e = c.edges()
+        st_tiles = None
+        got = np.zeros((n, n), np.uint32)
+        got[e["i"], e["j"]] = e["common"]
+        assert nedges == len(e) == int((want > 0).sum())
+        assert np.array_equal(got, want)
+        m = c.mst(21, 0.2)
+        st_tiles = c.mst_stats()
+    ref = oracle.mst(sk, 21, 0.2)
+    _same_forest(oracle, m, ref, n, 0.2)
+    assert st_tiles["tiles_flagged"] == st_tiles["tiles_total"] == 28
