@@ -98,12 +98,14 @@ def measure(args, local_rank=0, rank=0, world=1, dist=None):
     torch.cuda.synchronize()
     e2e_ms = (time.time() - t0) * 1e3 / n_e2e
     assert np.array_equal(h_out.numpy().view(np.uint64), o[:ne]), "host-buffer path differs from device path"
+    pcie_bytes = int(L.tc_last_h2d_bytes(ctx._h))      # what the last call moved over PCIe (packed 2-bit batches count packed)
     ctx.close()
     del seq
     return {"genomes": ng, "genome_len": glen, "k": k, "s": s, "ms_per_step": dev_ms,
             "genomes_per_s": ng / (dev_ms / 1e3), "gbp_per_s": ng * glen / (dev_ms / 1e3) / 1e9,
             "launches": int(launches), "e2e_genomes": ne, "e2e_ms_per_step": e2e_ms,
-            "e2e_genomes_per_s": ne / (e2e_ms / 1e3), "h2d_bytes": ne * glen, "d2h_bytes": ne * s * 8 + ne * 4}
+            "e2e_genomes_per_s": ne / (e2e_ms / 1e3), "h2d_bytes": ne * glen, "d2h_bytes": ne * s * 8 + ne * 4,
+            "pcie_bytes": pcie_bytes}
 
 
 def measure_kssd(args, local_rank=0, rank=0):
@@ -208,7 +210,11 @@ def sketch_block(args, m, world, clocks=None, with_cpu=True):
                                 "(Murmur3 = ten 64-bit multiplies per window), not HBM bound: see DESIGN.md K1"},
            "e2e": {"value": world * m["e2e_genomes_per_s"], "unit": "genomes/s",
                    "h2d_bytes_per_step": m["h2d_bytes"] * world, "d2h_bytes_per_step": m["d2h_bytes"] * world,
-                   "genomes_per_step": m["e2e_genomes"] * world, "ms_per_step": m["e2e_ms_per_step"]},
+                   "genomes_per_step": m["e2e_genomes"] * world, "ms_per_step": m["e2e_ms_per_step"],
+                   "pcie_bytes_per_step": m.get("pcie_bytes", m["h2d_bytes"]) * world,
+                   "transport": ("host ASCII buffers; the library packs each batch to 2 bits per base on the host threads "
+                                 "(+ exception list), the device rebuilds the bytes" if m.get("pcie_bytes", m["h2d_bytes"]) < m["h2d_bytes"]
+                                 else "host ASCII buffers copied as they are (1 byte per base)")},
            "gpu_launches": m["launches"]}
     if clocks is not None:
         blk["clocks"] = clocks

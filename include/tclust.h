@@ -78,6 +78,11 @@ int tc_sketch_minhash(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off,
                       const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes, int k,
                       const uint32_t *sketch_size, uint32_t seed,
                       uint64_t *out_hashes, uint64_t out_stride, uint32_t *out_n);
+/* Transport: when the host has cores to spare (>= 12 threads per visible GPU; TCLUST_SKETCH_PACK=0|1 forces it off/on,
+ * TCLUST_PACK_THREADS sets the thread count) every batch is packed on the host to 2 bits per base plus an exception list
+ * of the bytes that are not ACGTacgt, a quarter of the bytes crosses PCIe, and the device rebuilds the exact byte stream
+ * before sketching -- same hashes, bit for bit.  tc_last_h2d_bytes: sequence bytes the last call moved over PCIe. */
+uint64_t tc_last_h2d_bytes(const tc_ctx *ctx);
 /* same with all buffers already resident on the device (timed "value" leg of bench.py);
  * seqs_dev must be readable 16 bytes past its end. */
 int tc_sketch_minhash_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const uint64_t *rec_off,

@@ -19,7 +19,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + \
+    deps = sources() + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + glob.glob(os.path.join(HERE, "csrc", "*.cpp")) + \
         glob.glob(os.path.join(HERE, "..", "include", "*.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -33,6 +33,11 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(HERE, "csrc", "build", os.path.basename(src)[:-3] + ".o")
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(obj)
+    for src in sorted(glob.glob(os.path.join(HERE, "csrc", "*.cpp"))):     # host-only sources (AVX2 packer): plain g++
+        obj = os.path.join(HERE, "csrc", "build", os.path.basename(src)[:-4] + ".o")
+        cmd = [os.environ.get("CXX", "/usr/bin/g++"), "-O3", "-std=c++17", "-fPIC", "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(obj)
     for src, p in procs:

@@ -56,6 +56,7 @@ struct tc_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
+    uint64_t last_h2d_bytes = 0;          // sequence bytes the last tc_sketch_minhash moved over PCIe (packed batches count packed)
     cudaEvent_t ev_pass0 = nullptr, ev_pass1 = nullptr;   // around the last dense-pass kernel
     uint32_t attr_set = 0;                // dynamic shared-memory opt-ins done on this context's device (bit per file)
     bool boruvka_async = false;           // tc_boruvka_set_async: the Boruvka phases do not synchronise the stream

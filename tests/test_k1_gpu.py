@@ -106,3 +106,37 @@ def test_sketch_pipelined_batches(ctx, oracle, monkeypatch):
     monkeypatch.setenv("TCLUST_SKETCH_CHUNK_MB", "4096")
     again = ctx.sketch_minhash(g, k=21, s=500)
     assert all(np.array_equal(a, b) for a, b in zip(got, again))
+
+
+def test_packed_transport_is_exact(tc, oracle, monkeypatch):
+    """TCLUST_SKETCH_PACK=1: the host packs every batch to 2 bits per base + an exception list, the device rebuilds the
+    bytes (pack2bit.cpp, k1_unpack_kernel).  Lower case, N runs, IUPAC codes, arbitrary bytes, several records per genome
+    and several batches: the sketches are the ones of the ASCII transport and of the oracle."""
+    rng = np.random.default_rng(9)
+    genomes = []
+    for g in range(5):
+        recs = []
+        for r in range(1 + g % 3):
+            b = bytearray(synth.random_genome(int(rng.integers(200000, 500000)), rng))
+            if g % 2:
+                b[1000:5000] = bytes(b[1000:5000]).lower()
+            for p in rng.integers(0, len(b) - 100, 6):
+                b[p:p + int(rng.integers(1, 60))] = b"N" * 1
+            for p in rng.integers(0, len(b), 40):
+                b[p] = b"RYKMSWnxz*-\x00\xff"[int(rng.integers(0, 13))]
+            recs.append(bytes(b))
+        genomes.append(recs)
+    monkeypatch.setenv("TCLUST_SKETCH_CHUNK_MB", "1")
+    monkeypatch.setenv("TCLUST_SKETCH_PACK", "0")
+    with tc.Context(0) as c:
+        plain = c.sketch_minhash(genomes, k=21, s=1000)
+    monkeypatch.setenv("TCLUST_SKETCH_PACK", "1")
+    monkeypatch.setenv("TCLUST_PACK_THREADS", "3")
+    with tc.Context(0) as c:
+        l0 = c.launches
+        packed = c.sketch_minhash(genomes, k=21, s=1000)
+        assert c.launches > l0
+    for a, b in zip(plain, packed):
+        assert np.array_equal(a, b)
+    for recs, h in list(zip(genomes, packed))[:2]:
+        assert np.array_equal(h, oracle.minhash_sketch(recs, 21, 1000))
