@@ -24,6 +24,7 @@
 // entry point pipelines batches of genomes over two staging slots (H2D of batch c+1 under the kernels of c).
 #include "tc_common.cuh"
 #include "k_sort.cuh"
+#include "k_stage.cuh"
 #include <algorithm>
 #include <thread>
 #include <cstdlib>
@@ -374,10 +375,7 @@ struct K1Slot {
     uint8_t *d_meta = nullptr; size_t d_meta_cap = 0;   // the same on the device + partial sketches, counters
     cudaEvent_t copied = nullptr, done = nullptr;
     bool used = false;
-    // packed 2-bit transport (host-buffer path, TCLUST_SKETCH_PACK): pinned staging of the packed batch and its exception
-    // list, and their device copies
-    uint8_t *h_pack = nullptr, *d_pack = nullptr; size_t pack_cap = 0;
-    uint32_t *h_exc_pos = nullptr, *d_exc_pos = nullptr; uint8_t *h_exc_byte = nullptr, *d_exc_byte = nullptr; size_t exc_cap = 0;
+    TcPackBuf pack;                                      // packed 2-bit transport (k_stage.cuh)
 };
 struct K1Workspace {
     K1Slot slot[2];
@@ -551,77 +549,6 @@ int k1_validate(const uint64_t *rec_off, const uint32_t *rec2genome, uint64_t nr
     return 0;
 }
 
-// ---- packed 2-bit transport: rebuild the ASCII batch on the device.  One thread = 16 bases = one 32-bit word of the
-// packed stream -> one 16-byte store; code -> byte through PRMT look-ups in the word 'A','C','T','G' (pack2bit.cpp).
-__global__ void k1_unpack_kernel(const uint32_t *packed, uint64_t nwords, uint8_t *out)
-{
-    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nwords) return;
-    const uint32_t p = packed[w];
-    const uint32_t table = 0x47544341u;                 // bytes: [0]='A' [1]='C' [2]='T' [3]='G'
-    uint32_t o[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const uint32_t c = (p >> (8 * q)) & 0xFFu;      // 4 bases
-        const uint32_t sel = (c & 3u) | (((c >> 2) & 3u) << 4) | (((c >> 4) & 3u) << 8) | (((c >> 6) & 3u) << 12);
-        o[q] = __byte_perm(table, 0u, sel);
-    }
-    reinterpret_cast<uint4 *>(out)[w] = make_uint4(o[0], o[1], o[2], o[3]);
-}
-__global__ void k1_patch_kernel(const uint32_t *pos, const uint8_t *byte, uint32_t n, uint8_t *out)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[pos[i]] = byte[i];
-}
-
-}  // namespace
-
-extern "C" size_t tc_pack2bit_range(const uint8_t *seq, uint64_t i0, uint64_t i1, uint64_t origin, uint8_t *out,
-                                    uint32_t *exc_pos, uint8_t *exc_byte, size_t exc_cap);     // pack2bit.cpp
-
-namespace {
-
-// threads the host packer may use: all cores divided by the visible GPUs (one process per GPU shares the host);
-// packing pays only when it outruns the PCIe link (~50 GB/s of ASCII): from about 12 threads up
-int k1_pack_threads()
-{
-    const char *e = getenv("TCLUST_SKETCH_PACK");
-    if (e && !strcmp(e, "0")) return 0;
-    int ndev = 1;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); ndev = 1; }
-    int t = (int)std::thread::hardware_concurrency() / ndev;
-    if (const char *pt = getenv("TCLUST_PACK_THREADS")) t = atoi(pt);
-    if (e && !strcmp(e, "1")) return std::max(t, 1);
-    return t >= 12 ? t : 0;
-}
-
-// pack seqs[base, base + nbytes) (base a multiple of 16) into the slot's pinned staging with `threads` host threads;
-// false: too many non-ACGT bytes for the exception list (the batch then goes over as ASCII)
-bool k1_pack_batch(K1Slot &sl, const uint8_t *seqs, uint64_t base, size_t nbytes, int threads, uint32_t *n_exc)
-{
-    const size_t per = ((nbytes + threads - 1) / threads + 63) & ~(size_t)63;
-    const size_t cap_t = sl.exc_cap / threads;
-    std::vector<size_t> cnt(threads, 0);
-    std::vector<std::thread> th;
-    for (int t = 0; t < threads; t++)
-        th.emplace_back([&, t]() {
-            const size_t a = std::min(nbytes, per * t), b = std::min(nbytes, per * (t + 1));
-            if (b > a) cnt[t] = tc_pack2bit_range(seqs + base, a, b, 0, sl.h_pack + a / 4, sl.h_exc_pos + cap_t * t, sl.h_exc_byte + cap_t * t, cap_t);
-        });
-    for (std::thread &x : th) x.join();
-    size_t total = 0;
-    for (int t = 0; t < threads; t++) {
-        if (cnt[t] > cap_t) return false;
-        if (t && cnt[t] && total != cap_t * t) {
-            memmove(sl.h_exc_pos + total, sl.h_exc_pos + cap_t * t, cnt[t] * 4);
-            memmove(sl.h_exc_byte + total, sl.h_exc_byte + cap_t * t, cnt[t]);
-        }
-        total += cnt[t];
-    }
-    *n_exc = (uint32_t)total;
-    return true;
-}
-
 }  // namespace
 
 void tc_k1_free(tc_ctx *ctx)
@@ -630,10 +557,7 @@ void tc_k1_free(tc_ctx *ctx)
     if (!w) return;
     for (K1Slot &sl : w->slot) {
         cudaFree(sl.d_seq); cudaFree(sl.d_meta);
-        cudaFree(sl.d_pack); cudaFree(sl.d_exc_pos); cudaFree(sl.d_exc_byte);
-        if (sl.h_pack) cudaFreeHost(sl.h_pack);
-        if (sl.h_exc_pos) cudaFreeHost(sl.h_exc_pos);
-        if (sl.h_exc_byte) cudaFreeHost(sl.h_exc_byte);
+        sl.pack.release();
         if (sl.h_meta) cudaFreeHost(sl.h_meta);
         if (sl.copied) cudaEventDestroy(sl.copied);
         if (sl.done) cudaEventDestroy(sl.done);
@@ -700,7 +624,7 @@ extern "C" int tc_sketch_minhash(tc_ctx *ctx, const uint8_t *seqs, const uint64_
     // segment pays its own bottom-s warm-up: 25 genomes per launch run at a third of the full-size rate; measured,
     // profiles/r1m_sketch_chunk_sweep.txt)
     const uint64_t seq_bytes = nrec ? rec_off[nrec] : 0;
-    const int pack_threads = k1_pack_threads();
+    const int pack_threads = tc_pack_threads();
     // (with the packed transport the host packer of batch c+1 runs beside the GPU work of batch c: a sixth of the call,
     //  measured 42.2 ms per 2.56 GB at 448 MB batches against 44.5 at 640 and 47.8 at 768)
     uint64_t chunk_bytes = std::min<uint64_t>(1ull << 30, std::max<uint64_t>(128ull << 20, seq_bytes / (pack_threads > 0 ? 6 : 4)));
@@ -733,54 +657,8 @@ extern "C" int tc_sketch_minhash(tc_ctx *ctx, const uint8_t *seqs, const uint64_
             if (cudaMalloc(&sl.d_seq, nbytes + 64 + nbytes / 8) != cudaSuccess) { tc_set_error("tc_sketch_minhash: out of device memory (%zu bytes of sequence per batch)", nbytes); rc = 1; break; }
             sl.seq_cap = nbytes + 64 + nbytes / 8;
         }
-        bool packed = false;
-        uint32_t n_exc = 0;
-        if (pack_threads > 0 && nbytes >= (1u << 20) && nbytes < (1ull << 32)) {
-            // packed 2-bit transport: the host threads pack this batch (while the GPU works on the previous one), a
-            // quarter of the bytes crosses PCIe, the device rebuilds the exact ASCII batch in the staging slot
-            const size_t pbytes = ((nbytes + 63) & ~(size_t)63) / 4;
-            if (pbytes + 64 > sl.pack_cap) {
-                if (sl.h_pack) cudaFreeHost(sl.h_pack);
-                cudaFree(sl.d_pack);
-                sl.h_pack = nullptr; sl.d_pack = nullptr; sl.pack_cap = 0;
-                const size_t cap = pbytes + 64 + pbytes / 8;
-                if (cudaMallocHost(&sl.h_pack, cap) != cudaSuccess || cudaMalloc(&sl.d_pack, cap) != cudaSuccess) { cudaGetLastError(); sl.pack_cap = 0; }
-                else sl.pack_cap = cap;
-            }
-            if (!sl.exc_cap) {
-                const size_t cap = 1u << 20;
-                if (cudaMallocHost(&sl.h_exc_pos, cap * 4) == cudaSuccess && cudaMallocHost(&sl.h_exc_byte, cap) == cudaSuccess &&
-                    cudaMalloc(&sl.d_exc_pos, cap * 4) == cudaSuccess && cudaMalloc(&sl.d_exc_byte, cap) == cudaSuccess) sl.exc_cap = cap;
-                else cudaGetLastError();
-            }
-            if (sl.pack_cap && sl.exc_cap) {
-                // (the slot's previous H2D copy has completed: its `done` event, waited for above, follows it)
-                packed = k1_pack_batch(sl, seqs, base, nbytes, pack_threads, &n_exc);
-                if (packed) {
-                    const uint64_t nwords = (nbytes + 15) / 16;
-                    ctx->last_h2d_bytes += pbytes + (uint64_t)n_exc * 5;
-                    bool ok = cudaMemcpyAsync(sl.d_pack, sl.h_pack, pbytes, cudaMemcpyHostToDevice, cs) == cudaSuccess;
-                    if (ok && n_exc) ok = cudaMemcpyAsync(sl.d_exc_pos, sl.h_exc_pos, (size_t)n_exc * 4, cudaMemcpyHostToDevice, cs) == cudaSuccess &&
-                                          cudaMemcpyAsync(sl.d_exc_byte, sl.h_exc_byte, n_exc, cudaMemcpyHostToDevice, cs) == cudaSuccess;
-                    ok = ok && cudaEventRecord(sl.copied, cs) == cudaSuccess && cudaStreamWaitEvent(st, sl.copied, 0) == cudaSuccess;
-                    if (ok) {
-                        k1_unpack_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(sl.d_pack), nwords, sl.d_seq);
-                        if (n_exc) k1_patch_kernel<<<(n_exc + 255) / 256, 256, 0, st>>>(sl.d_exc_pos, sl.d_exc_byte, n_exc, sl.d_seq);
-                        ctx->launches += n_exc ? 2 : 1;
-                        ok = cudaMemsetAsync(sl.d_seq + nbytes, 0, 64, st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
-                    }
-                    if (!ok) { tc_set_error("tc_sketch_minhash: packed H2D copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; break; }
-                }
-            }
-        }
-        if (!packed) ctx->last_h2d_bytes += nbytes;
-        if (!packed &&
-            ((nbytes && cudaMemcpyAsync(sl.d_seq, seqs + base, nbytes, cudaMemcpyHostToDevice, cs) != cudaSuccess) ||
-             cudaMemsetAsync(sl.d_seq + nbytes, 0, 64, cs) != cudaSuccess ||
-             cudaEventRecord(sl.copied, cs) != cudaSuccess || cudaStreamWaitEvent(st, sl.copied, 0) != cudaSuccess)) {
-            tc_set_error("tc_sketch_minhash: H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-            rc = 1; break;
-        }
+        // (packed 2-bit transport or plain ASCII copy: k_stage.cuh)
+        if (tc_stage_batch(ctx, sl.pack, seqs, base, nbytes, sl.d_seq, cs, st, sl.copied, pack_threads, "tc_sketch_minhash")) { rc = 1; break; }
         k1_plan(ctx, rec_off, rec2genome, r0, r1, g0, g1, k, sketch_size, base, pl);
         rc = k1_enqueue(ctx, sl, st, sl.d_seq, pl, g1 - g0, k, seed, sketch_size + g0, ws->d_out + (size_t)g0 * out_stride,
                         out_stride, ws->d_n + g0);

@@ -16,6 +16,7 @@
 // at half_subk = 6) is read through L2 (it fits the 126 MB L2).
 #include "tc_common.cuh"
 #include "k_sort.cuh"
+#include "k_stage.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -147,6 +148,7 @@ struct K2Slot {
     uint8_t *d_meta = nullptr; size_t d_meta_cap = 0;   // segments, per-genome counters, segment counter, scratch
     cudaEvent_t copied = nullptr, done = nullptr;
     bool used = false;
+    TcPackBuf pack;                                      // packed 2-bit transport (k_stage.cuh)
 };
 struct K2Workspace {
     K2Slot slot[2];
@@ -319,6 +321,7 @@ void tc_k2_free(tc_ctx *ctx)
     if (!w) return;
     for (K2Slot &sl : w->slot) {
         cudaFree(sl.d_seq); cudaFree(sl.d_meta);
+        sl.pack.release();
         if (sl.h_meta) cudaFreeHost(sl.h_meta);
         if (sl.copied) cudaEventDestroy(sl.copied);
         if (sl.done) cudaEventDestroy(sl.done);
@@ -390,6 +393,8 @@ extern "C" int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *
         ws->n_cap = ngenomes;
     }
     TC_CUDA(cudaMemsetAsync(ws->d_overflow, 0, 4, st));
+    const int pack_threads = tc_pack_threads();
+    ctx->last_h2d_bytes = 0;
     uint64_t chunk_bytes = 128ull << 20;
     if (const char *e = getenv("TCLUST_SKETCH_CHUNK_MB")) chunk_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 1) << 20;
     const uint64_t end_off = nrec ? rec_off[nrec] : 0;
@@ -416,12 +421,7 @@ extern "C" int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *
             if (cudaMalloc(&sl.d_seq, nbytes + 64 + nbytes / 8) != cudaSuccess) { tc_set_error("tc_sketch_kssd: out of device memory (%zu bytes of sequence per batch)", nbytes); rc = 1; break; }
             sl.seq_cap = nbytes + 64 + nbytes / 8;
         }
-        if ((nbytes && cudaMemcpyAsync(sl.d_seq, seqs + base, nbytes, cudaMemcpyHostToDevice, cs) != cudaSuccess) ||
-            cudaMemsetAsync(sl.d_seq + nbytes, 0, 64, cs) != cudaSuccess ||
-            cudaEventRecord(sl.copied, cs) != cudaSuccess || cudaStreamWaitEvent(st, sl.copied, 0) != cudaSuccess) {
-            tc_set_error("tc_sketch_kssd: H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-            rc = 1; break;
-        }
+        if (tc_stage_batch(ctx, sl.pack, seqs, base, nbytes, sl.d_seq, cs, st, sl.copied, pack_threads, "tc_sketch_kssd")) { rc = 1; break; }
         rc = k2_enqueue(ctx, ws, sl, st, a, sl.d_seq, rec_off, rec2genome, r0, r1, g0, g1 - g0, base,
                         ws->d_out + (size_t)g0 * out_stride, out_stride, ws->d_n + g0);
         if (!rc && cudaEventRecord(sl.done, st) != cudaSuccess) { tc_set_error("tc_sketch_kssd: event record failed"); rc = 1; }

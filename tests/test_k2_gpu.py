@@ -73,3 +73,34 @@ def test_kssd_overflow_is_an_error(ctx, oracle, tc):
     g = [[synth.random_genome(400000, rng)]]
     with pytest.raises(tc.TclustError):
         ctx.sketch_kssd(g, 18, 3, oracle.kssd_shuffled_dim(6), max_hashes=16)
+
+
+def test_kssd_packed_transport_is_exact(tc, oracle, monkeypatch):
+    """TCLUST_SKETCH_PACK=1 (2 bits per base over PCIe + exception list, rebuilt on the device): lower case, N runs (which
+    reset the KSSD window), other bytes, several batches -- same sketches as the ASCII transport and as the oracle."""
+    rng = np.random.default_rng(19)
+    genomes = []
+    for g in range(4):
+        recs = []
+        for r in range(1 + g % 2):
+            b = bytearray(synth.random_genome(int(rng.integers(400000, 700000)), rng))
+            if g % 2 == 0:
+                b[2000:9000] = bytes(b[2000:9000]).lower()
+            for p in rng.integers(0, len(b) - 200, 8):
+                b[p:p + int(rng.integers(1, 120))] = b"N" * 1
+            for p in rng.integers(0, len(b), 30):
+                b[p] = b"RYKMnx-\x00\xff"[int(rng.integers(0, 9))]
+            recs.append(bytes(b))
+        genomes.append(recs)
+    sd = oracle.kssd_shuffled_dim(6)
+    monkeypatch.setenv("TCLUST_SKETCH_CHUNK_MB", "1")
+    monkeypatch.setenv("TCLUST_SKETCH_PACK", "0")
+    with tc.Context(0) as c:
+        plain = c.sketch_kssd(genomes, 18, 3, sd)
+    monkeypatch.setenv("TCLUST_SKETCH_PACK", "1")
+    monkeypatch.setenv("TCLUST_PACK_THREADS", "5")
+    with tc.Context(0) as c:
+        packed = c.sketch_kssd(genomes, 18, 3, sd)
+    for a, b in zip(plain, packed):
+        assert np.array_equal(a, b)
+    assert np.array_equal(packed[0], oracle.kssd_sketch(genomes[0], 18, 3))
