@@ -227,14 +227,15 @@ __device__ __forceinline__ void kd_pass_low(uint32_t *buf, uint8_t *rowof, uint3
 // candidates for (P,q) = (2,1) (3,1) (3,2) (4,1) (4,2) (4,3), out[rb*8+7] = elements that entered the sort.
 __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint32_t *ranks, const unsigned long long *off,
                                                                       const uint32_t *size, uint32_t n, const uint32_t *multi,
-                                                                      uint32_t *out, uint32_t *ukeys, uint32_t *umask, int blocked)
+                                                                      uint32_t *out, uint32_t *ukeys, uint32_t *umask, int blocked,
+                                                                      const uint32_t *block_list)
 {
     extern __shared__ __align__(16) uint8_t kh_smem[];
     uint32_t *buf = reinterpret_cast<uint32_t *>(kh_smem);
     uint8_t *rowof = kh_smem + (size_t)KH_SORT_CAP * 4;          // which of the 32 sketches an element came from
     __shared__ uint32_t s_pos[33], s_warp[32], s_d, s_cnt[32];
     __shared__ unsigned long long s_raw;
-    const uint32_t rb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rb = block_list ? block_list[blockIdx.x] : blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         unsigned long long raw = 0;
         for (uint32_t l = 0; l < 32; l++) { const uint32_t id = rb * 32 + l; raw += id < n ? size[id] : 0u; }
@@ -382,6 +383,122 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_kernel(const uint3
             ukeys[base + d] = key;
             umask[base + d] = m;
         }
+    }
+}
+
+// ---- union lists through a hash table (round 2; the sort above is the fall-back).  The 32 sketches of a block of related
+// genomes hold ~24,000 shared elements but only ~1,300 DISTINCT ranks: instead of sorting all elements (65 bitonic stages
+// over 32,768 slots) every element is inserted into a shared-memory table rank -> mask of the rows holding it (the very
+// table K3H/K3J build), the occupied slots are compacted and only the distinct keys are sorted (66 stages over 2,048
+// slots).  Blocks with more than KDH_CAP distinct shared ranks answer 0xFFFFFFFE and are redone by k3h_distinct_kernel.
+// Same outputs: out[rb*8] = D, [1..6] pivot candidates, [7] = shared elements; (key, mask) lists at off[rb*32].
+constexpr uint32_t KDH_SLOTS = 16384;
+constexpr uint32_t KDH_CAP = 8192;
+constexpr size_t KDH_SMEM = (size_t)KDH_SLOTS * 8 + (size_t)KDH_CAP * 8;
+constexpr uint32_t KDH_RETRY = 0xFFFFFFFEu;
+
+__global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_hash_kernel(const uint32_t *ranks, const unsigned long long *off,
+                                                                           const uint32_t *size, uint32_t n, const uint32_t *multi,
+                                                                           uint32_t *out, uint32_t *ukeys, uint32_t *umask)
+{
+    extern __shared__ __align__(16) uint8_t kh_smem[];
+    uint2 *table = reinterpret_cast<uint2 *>(kh_smem);
+    unsigned long long *sk = reinterpret_cast<unsigned long long *>(kh_smem + (size_t)KDH_SLOTS * 8);
+    __shared__ uint32_t s_elems, s_distinct, s_over, s_warp[32];
+    const uint32_t rb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        uint4 *t4 = reinterpret_cast<uint4 *>(kh_smem);
+        const uint4 e = make_uint4(KH_EMPTY, 0u, KH_EMPTY, 0u);
+        for (uint32_t i = tid; i < KDH_SLOTS / 2; i += KH_THREADS) t4[i] = e;
+        if (tid == 0) { s_elems = 0; s_distinct = 0; s_over = 0; }
+    }
+    __syncthreads();
+    {   // warp w inserts the shared elements of row w
+        const uint32_t id = rb * 32 + warp;
+        const uint32_t len = id < n ? size[id] : 0u;
+        const uint32_t *row = ranks + (id < n ? off[id] : 0ULL);
+        const uint32_t bit = 1u << warp;
+        uint32_t mine = 0;
+        for (uint32_t e0 = 0; e0 < len; e0 += 128) {
+            uint32_t x[4]; bool keep[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {                          // four independent loads and bitmap look-ups in flight
+                const uint32_t e = e0 + 32 * q + lane;
+                x[q] = e < len ? __ldg(row + e) : 0u;
+                keep[q] = e < len;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) keep[q] = keep[q] && kh_multi(multi, x[q]);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (!keep[q] || *(volatile uint32_t *)&s_over) continue;
+                mine++;
+                uint32_t slot = kh_slot(x[q]);
+                for (;;) {
+                    const uint32_t old = atomicCAS(&table[slot].x, KH_EMPTY, x[q]);
+                    if (old == KH_EMPTY && atomicAdd(&s_distinct, 1u) + 1u > KDH_CAP) s_over = 1u;
+                    if (old == KH_EMPTY || old == x[q]) { atomicOr(&table[slot].y, bit); break; }
+                    slot = (slot + 1) & (KDH_SLOTS - 1);
+                }
+            }
+        }
+        for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0 && mine) atomicAdd(&s_elems, mine);
+    }
+    __syncthreads();
+    if (s_over) { if (tid == 0) out[rb * KH_DREC] = KDH_RETRY; return; }
+    const uint32_t D = s_distinct;
+    // compact the occupied slots: thread t owns slots [16t, 16t+16)
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) cnt += table[tid * 16 + q].x != KH_EMPTY;
+    uint32_t incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = s_warp[lane];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, v, o); if ((int)lane >= o) v += u; }
+        s_warp[lane] = v;
+    }
+    __syncthreads();
+    uint32_t pos = incl - cnt + (warp ? s_warp[warp - 1] : 0u);
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const uint2 e = table[tid * 16 + q];
+        if (e.x != KH_EMPTY) sk[pos++] = ((unsigned long long)e.x << 32) | e.y;
+    }
+    uint32_t npad = 32;
+    while (npad < D) npad <<= 1;
+    for (uint32_t i = D + tid; i < npad; i += KH_THREADS) sk[i] = 0xFFFFFFFFFFFFFFFFull;
+    __syncthreads();
+    // bitonic sort of the distinct keys (key in the high word)
+    for (uint32_t sz = 2; sz <= npad; sz <<= 1)
+        for (uint32_t stride = sz >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = tid; t < (npad >> 1); t += KH_THREADS) {
+                const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const unsigned long long x = sk[lo], y = sk[hi];
+                if ((x > y) == ((lo & sz) == 0)) { sk[lo] = y; sk[hi] = x; }
+            }
+            __syncthreads();
+        }
+    const unsigned long long base = rb * 32 < n ? off[rb * 32] : 0ULL;
+    for (uint32_t d = tid; d < D; d += KH_THREADS) {
+        const unsigned long long v = sk[d];
+        ukeys[base + d] = (uint32_t)(v >> 32);
+        umask[base + d] = (uint32_t)v;
+    }
+    if (tid < 8) {
+        uint32_t v;
+        if (tid == 0) v = D;
+        else if (tid == 7) v = s_elems;
+        else {
+            const uint32_t num = tid == 1 ? 1 : tid == 2 ? 1 : tid == 3 ? 2 : tid == 4 ? 1 : tid == 5 ? 2 : 3;
+            const uint32_t den = tid == 1 ? 2 : tid <= 3 ? 3 : 4;
+            const uint32_t w = (uint32_t)((unsigned long long)D * num / den);
+            v = w < D ? (uint32_t)(sk[w] >> 32) : 0u;
+        }
+        out[rb * KH_DREC + tid] = v;
     }
 }
 
@@ -1290,15 +1407,44 @@ int tc_kh_prepare(tc_ctx *ctx)
     TC_CHECK(ctx->d_multi, "tc_kh_prepare: no multiplicity bitmap");
     const char *sort_env = getenv("TCLUST_DISTINCT_SORT");       // "plain": one pass per stride (the first version)
     const int blocked = !(sort_env && !strcmp(sort_env, "plain"));
-    k3h_distinct_kernel<<<nrb, KH_THREADS, KH_SORT_CAP * 5, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
-                                                                 ctx->d_size, ctx->n, ctx->d_multi, d_dist, ctx->d_bu_keys, ctx->d_bu_mask,
-                                                                 blocked);
-    ctx->launches++;
+    const char *dist_env = getenv("TCLUST_DISTINCT");            // "sort": the block sort for every block (round 1)
+    const bool hash_first = !(dist_env && !strcmp(dist_env, "sort"));
     std::vector<uint32_t> dist((size_t)nrb * KH_DREC);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dist.data(), d_dist, dist.size() * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { tc_set_error("tc_kh_prepare: %s", cudaGetErrorString(e)); return 1; }
+    cudaError_t e = cudaSuccess;
+    if (hash_first) {
+        if (!(ctx->attr_set & 8u)) {
+            TC_CUDA(cudaFuncSetAttribute(k3h_distinct_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KDH_SMEM));
+            ctx->attr_set |= 8u;
+        }
+        k3h_distinct_hash_kernel<<<nrb, KH_THREADS, KDH_SMEM, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off),
+                                                                   ctx->d_size, ctx->n, ctx->d_multi, d_dist, ctx->d_bu_keys, ctx->d_bu_mask);
+        ctx->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dist.data(), d_dist, dist.size() * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { tc_set_error("tc_kh_prepare: %s", cudaGetErrorString(e)); return 1; }
+    }
+    // blocks the hash kernel could not hold (more than KDH_CAP distinct shared ranks), or all of them: the block sort
+    std::vector<uint32_t> redo;
+    for (uint32_t rb = 0; rb < nrb; rb++)
+        if (!hash_first || dist[(size_t)rb * KH_DREC] == KDH_RETRY) redo.push_back(rb);
+    if (!redo.empty()) {
+        uint32_t *d_list = nullptr;
+        if (redo.size() < nrb) {
+            void *ws = nullptr;
+            if (tc_scratch(ctx, redo.size() * 4, &ws)) return 1;
+            d_list = static_cast<uint32_t *>(ws);
+            TC_CUDA(cudaMemcpyAsync(d_list, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
+        }
+        k3h_distinct_kernel<<<(unsigned)redo.size(), KH_THREADS, KH_SORT_CAP * 5, st>>>(
+            ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off), ctx->d_size, ctx->n, ctx->d_multi, d_dist, ctx->d_bu_keys,
+            ctx->d_bu_mask, blocked, d_list);
+        ctx->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dist.data(), d_dist, dist.size() * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { tc_set_error("tc_kh_prepare: %s", cudaGetErrorString(e)); return 1; }
+    }
     // ---- partitions: by distinct keys where known, else by the multiset total
     std::vector<uint32_t> pivoff(nrb + 1, 0);
     bool any_fallback = false;
