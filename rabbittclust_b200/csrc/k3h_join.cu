@@ -435,9 +435,15 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_hash_kernel(const 
                 mine++;
                 uint32_t slot = kh_slot(x[q]);
                 for (;;) {
-                    const uint32_t old = atomicCAS(&table[slot].x, KH_EMPTY, x[q]);
-                    if (old == KH_EMPTY && atomicAdd(&s_distinct, 1u) + 1u > KDH_CAP) s_over = 1u;
-                    if (old == KH_EMPTY || old == x[q]) { atomicOr(&table[slot].y, bit); break; }
+                    // most elements find their key in place already (24 of the 32 rows hold it): a plain read first, the
+                    // compare-and-swap only for an empty slot
+                    uint32_t old = *(volatile uint32_t *)&table[slot].x;
+                    if (old == KH_EMPTY) {
+                        old = atomicCAS(&table[slot].x, KH_EMPTY, x[q]);
+                        if (old == KH_EMPTY && atomicAdd(&s_distinct, 1u) + 1u > KDH_CAP) s_over = 1u;
+                        if (old == KH_EMPTY) old = x[q];
+                    }
+                    if (old == x[q]) { atomicOr(&table[slot].y, bit); break; }
                     slot = (slot + 1) & (KDH_SLOTS - 1);
                 }
             }
@@ -448,10 +454,11 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_hash_kernel(const 
     __syncthreads();
     if (s_over) { if (tid == 0) out[rb * KH_DREC] = KDH_RETRY; return; }
     const uint32_t D = s_distinct;
-    // compact the occupied slots: thread t owns slots [16t, 16t+16)
+    // compact the occupied slots: thread t owns slots t, t + 1024, ... (consecutive lanes read consecutive slots: no bank
+    // conflicts; the order of the compacted entries does not matter, they are sorted next)
     uint32_t cnt = 0;
 #pragma unroll
-    for (int q = 0; q < 16; q++) cnt += table[tid * 16 + q].x != KH_EMPTY;
+    for (int q = 0; q < 16; q++) cnt += table[q * KH_THREADS + tid].x != KH_EMPTY;
     uint32_t incl = cnt;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
     if (lane == 31) s_warp[warp] = incl;
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(KH_THREADS, 1) k3h_distinct_hash_kernel(const 
     uint32_t pos = incl - cnt + (warp ? s_warp[warp - 1] : 0u);
 #pragma unroll
     for (int q = 0; q < 16; q++) {
-        const uint2 e = table[tid * 16 + q];
+        const uint2 e = table[q * KH_THREADS + tid];
         if (e.x != KH_EMPTY) sk[pos++] = ((unsigned long long)e.x << 32) | e.y;
     }
     uint32_t npad = 32;
