@@ -142,6 +142,32 @@ int tc_upload_sort_share_dev(tc_ctx *ctx, const uint64_t *hashes_dev, uint64_t l
 int tc_sketches_upload_runs_dev(tc_ctx *ctx, const uint64_t *keys_dev, const uint32_t *pos_dev, const uint64_t *run_off,
                                 uint32_t nruns, const uint64_t *off, uint32_t n);
 
+/*
+ * Multi-GPU upload, second form: the rank transform itself is sharded by hash VALUE RANGE, so that no rank sorts more than
+ * its 1/G of the hashes and only 4-byte ranks (not 12-byte sorted runs) are gathered.  Per rank (exchanges = the caller's
+ * all-to-all / all-gather; rabbittclust_b200/mst_dist.py:upload_sharded_vr is the orchestration bench.py uses):
+ *   1. copy the own contiguous share of the flat hash array to the device; agree on G-1 splitters (a sorted sample);
+ *   2. tc_vr_partition_dev(mode 0): (hash, position) pairs grouped by value range -> all-to-all;
+ *   3. tc_vr_local_ranks_dev: sort the received pairs, dense local ranks + "occurs more than once" flag (bit 31);
+ *      all-gather the distinct counts -> base of every range;
+ *   4. tc_vr_partition32_dev: (rank, position) grouped by the rank that owns the position -> all-to-all back;
+ *   5. tc_vr_scatter_ranks_dev: own slice of the position-ordered rank array (base of the source range added);
+ *      all-gather the slices;
+ *   6. tc_sketches_upload_ranks_dev: resident set from the finished ranks (as tc_sketches_upload from there on).
+ * Same resident state as tc_sketches_upload (identical ranks, since the ranges are ordered and ranks are dense).
+ */
+int tc_vr_partition_dev(tc_ctx *ctx, const uint64_t *a_dev, const uint32_t *b_dev /* NULL: pos_base + index */, uint64_t m, int mode,
+                        const uint64_t *splitters /* host, nb - 1, ascending (mode 0) */, uint64_t per /* mode 1 */, uint32_t nb,
+                        uint32_t pos_base, uint64_t *a_out_dev, uint32_t *b_out_dev, uint64_t *counts /* host, nb */);
+int tc_vr_partition32_dev(tc_ctx *ctx, const uint32_t *a_dev, const uint32_t *b_dev, uint64_t m, uint64_t per, uint32_t nb,
+                          uint32_t *a_out_dev, uint32_t *b_out_dev, uint64_t *counts);
+int tc_vr_local_ranks_dev(tc_ctx *ctx, const uint64_t *keys_dev, const uint32_t *pos_dev, uint64_t m,
+                          uint32_t *pos_out_dev, uint32_t *rank_out_dev, uint64_t *n_distinct);
+int tc_vr_scatter_ranks_dev(tc_ctx *ctx, const uint32_t *pos_dev, const uint32_t *rank_dev, const uint64_t *seg_off /* host, nseg + 1 */,
+                            const uint64_t *seg_base /* host, nseg */, uint32_t nseg, uint32_t pos_lo, uint64_t share_len,
+                            uint32_t *out_dev);
+int tc_sketches_upload_ranks_dev(tc_ctx *ctx, const uint32_t *ranks_flag_dev, const uint64_t *off, uint32_t n);
+
 /* validation: common[i-i0][j-j0] = |sketch_i n sketch_j| for i in [i0,i1), j in [j0,j1)
  * (semantic A: the counts of src/MST.cpp:1409-1435).  impl 0 = tiled merge kernel (k3_tile.cu),
  * 1 = independent u64 global-memory merge kernel, 2 = hash-join kernel (k3h_join.cu). */

@@ -26,7 +26,8 @@ SYMBOLS = [
     "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce", "tc_greedy_cluster_kssd", "tc_dense_ani", "tc_allpairs_pass_from", "tc_mst_append",
     "tc_jaccard_b", "tc_distance_b", "tc_contain_distance",
     "tc_mash_dist", "tc_aaf_dist", "tc_dist_from_key", "tc_radio", "tc_greedy_common_min", "tc_greedy_dist",
-    "tc_mg_export", "tc_mg_join", "tc_mg_leave", "tc_mg_rank", "tc_mst_stats", "tc_mst_of_edges", "tc_cluster_threshold", "tc_labels_merge", "tc_greedy_cluster_multi", "tc_kssd_needed_stride", "tc_upload_sort_share_dev", "tc_sketches_upload_runs_dev", "tc_last_h2d_bytes",
+    "tc_mg_export", "tc_mg_join", "tc_mg_leave", "tc_mg_rank", "tc_mst_stats", "tc_mst_of_edges", "tc_cluster_threshold", "tc_labels_merge", "tc_greedy_cluster_multi", "tc_kssd_needed_stride", "tc_upload_sort_share_dev", "tc_sketches_upload_runs_dev", "tc_last_h2d_bytes", "tc_vr_partition_dev", "tc_vr_partition32_dev", "tc_vr_local_ranks_dev", "tc_vr_scatter_ranks_dev",
+    "tc_sketches_upload_ranks_dev",
 ]
 MG_HANDLE_BYTES = 128
 
@@ -116,6 +117,11 @@ def lib():
     L.tc_cluster_threshold.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_uint32, C.c_uint32, i32p, u32p]
     L.tc_labels_merge.argtypes = [i32p, i32p, C.c_uint32, u32p]
     L.tc_kssd_needed_stride.restype = C.c_uint32
+    L.tc_vr_partition_dev.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, u64p, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, u64p]
+    L.tc_vr_partition32_dev.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, u64p]
+    L.tc_vr_local_ranks_dev.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, u64p]
+    L.tc_vr_scatter_ranks_dev.argtypes = [vp, vp, vp, u64p, u64p, C.c_uint32, C.c_uint32, C.c_uint64, vp]
+    L.tc_sketches_upload_ranks_dev.argtypes = [vp, vp, u64p, C.c_uint32]
     L.tc_last_h2d_bytes.argtypes = [vp]
     L.tc_last_h2d_bytes.restype = C.c_uint64
     L.tc_upload_sort_share_dev.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, vp]

@@ -440,8 +440,19 @@ static int merge_sorted_runs(tc_ctx *ctx, const SortedRuns &r, uint64_t total, U
     return 0;
 }
 
+// ranks_flag: the rank transform is done already (value-range sharded upload): per element its global dense rank with bit 31
+// set when the rank occurs in more than one sketch
+__global__ void ranks_from_flagged_kernel(const uint32_t *rf, uint64_t n, uint32_t *ranks, uint32_t *multi)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = rf[i], r = v & 0x7FFFFFFFu;
+    ranks[i] = r;
+    if (v >> 31) atomicOr(&multi[r >> 5], 1u << (r & 31));
+}
+
 static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_device, const uint64_t *off, uint32_t n,
-                         const SortedRuns *runs = nullptr)
+                         const SortedRuns *runs = nullptr, const uint32_t *ranks_flag = nullptr)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     PhaseTimer pt(ctx->stream);
@@ -463,7 +474,8 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     }
     cudaStream_t st = ctx->stream;
     const uint64_t tot1 = std::max<uint64_t>(total, 1);
-    if ((!runs && ensure_cap(&ctx->d_hashes, &ctx->cap_hashes, tot1)) || ensure_cap(&ctx->d_ranks, &ctx->cap_ranks, tot1)) return 1;
+    const bool no_hashes = runs || ranks_flag;      // the flat u64 hashes are not brought to this device
+    if ((!no_hashes && ensure_cap(&ctx->d_hashes, &ctx->cap_hashes, tot1)) || ensure_cap(&ctx->d_ranks, &ctx->cap_ranks, tot1)) return 1;
     if (n + 1 > ctx->cap_n) {
         cudaFree(ctx->d_off); cudaFree(ctx->d_size);
         ctx->d_off = nullptr; ctx->d_size = nullptr; ctx->cap_n = 0;
@@ -477,11 +489,11 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     // the last merges run under the PCIe copy (upload_sorted_runs below).  TCLUST_UPLOAD_OVERLAP=0: one copy, one sort; =1: pieces whatever the size.
     const char *ov = getenv("TCLUST_UPLOAD_OVERLAP");
     const bool ov_off = ov && !strcmp(ov, "0"), ov_force = ov && !strcmp(ov, "1");   // 1: whatever the size (tests)
-    const bool chunked = !runs && !hashes_on_device && hashes != ctx->d_hashes && !ov_off &&
+    const bool chunked = !no_hashes && !hashes_on_device && hashes != ctx->d_hashes && !ov_off &&
                          (total >= (16ull << 20) || (ov_force && total >= 2));
     UploadSort us;
-    if (runs) {
-        // sorted runs from the ranks of a multi-GPU upload: no copy of the flat hashes (d_hashes stays empty: only the
+    if (no_hashes) {
+        // sorted runs / finished ranks from a multi-GPU upload: no copy of the flat hashes (d_hashes stays empty: only the
         // independent validation kernel reads it), the order check runs on the ranks below
         ctx->hashes_resident = false;
     } else if (chunked) {
@@ -492,7 +504,7 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     TC_CUDA(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     sizes_kernel<<<nblk(n, 256), 256, 0, st>>>(reinterpret_cast<unsigned long long *>(ctx->d_off), ctx->d_size, n);
     ctx->launches++;
-    if (!runs) {   // input contract check (0.8 GB read at N = 100k: ~0.2 ms)
+    if (!no_hashes) {   // input contract check (0.8 GB read at N = 100k: ~0.2 ms)
         unsigned int *d_bad = reinterpret_cast<unsigned int *>(ctx->d_edge_count + 3), h_bad = 0xFFFFFFFFu;
         TC_CUDA(cudaMemsetAsync(d_bad, 0xFF, 4, st));
         check_sorted_kernel<<<n, 128, 0, st>>>(ctx->d_hashes, reinterpret_cast<unsigned long long *>(ctx->d_off), n, d_bad);
@@ -514,7 +526,14 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
         if (ensure_cap(&ctx->d_multi, &ctx->cap_multi, 1)) return 1;
         TC_CUDA(cudaMemsetAsync(ctx->d_multi, 0, 4, ctx->stream));
     }
-    if (total > 0) {
+    if (total > 0 && ranks_flag) {
+        const uint64_t mwords = total / 32 + 1;
+        if (ensure_cap(&ctx->d_multi, &ctx->cap_multi, mwords)) return 1;
+        TC_CUDA(cudaMemsetAsync(ctx->d_multi, 0, mwords * 4, st));
+        ranks_from_flagged_kernel<<<nblk(total, 256), 256, 0, st>>>(ranks_flag, total, ctx->d_ranks, ctx->d_multi);
+        ctx->launches++;
+        pt.mark("ranks + bitmap from the sharded transform");
+    } else if (total > 0) {
         if (runs) {
             if (merge_sorted_runs(ctx, *runs, total, &us)) return 1;
         } else if (!chunked) {
@@ -545,7 +564,7 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
         TC_CUDA(cudaStreamSynchronize(st));
         pt.mark("flags + scan + scatter");
     }
-    if (runs && total > 0) {      // the contract check on the ranks (order-preserving: same verdict as on the hashes)
+    if (no_hashes && total > 0) {      // the contract check on the ranks (order-preserving: same verdict as on the hashes)
         unsigned int *d_bad = reinterpret_cast<unsigned int *>(ctx->d_edge_count + 3), h_bad = 0xFFFFFFFFu;
         TC_CUDA(cudaMemsetAsync(d_bad, 0xFF, 4, st));
         check_sorted_ranks_kernel<<<n, 128, 0, st>>>(ctx->d_ranks, reinterpret_cast<unsigned long long *>(ctx->d_off), n, d_bad);
@@ -614,6 +633,191 @@ extern "C" int tc_sketches_upload_runs_dev(tc_ctx *ctx, const uint64_t *keys_dev
     for (uint32_t r = 0; r < nruns; r++) TC_CHECK(run_off[r + 1] >= run_off[r], "tc_sketches_upload_runs_dev: run offsets not monotone");
     const SortedRuns runs{keys_dev, pos_dev, run_off, nruns};
     return upload_common(ctx, nullptr, true, off, n, &runs);
+}
+
+// ---- value-range sharded rank transform (multi-GPU upload, second form): no rank sorts or gathers more than it must.
+// Pieces (the exchanges between them are the caller's: all-to-all / all-gather, plumbing):
+//   tc_vr_partition_dev   pairs (a, b) -> grouped by bucket: mode 0 bucket = number of splitters <= a (a = hash, b = its
+//                         position, generated as pos_base + index when b_dev is NULL); mode 1 bucket = b / per (a = rank).
+//   tc_vr_local_ranks_dev sort the (hash, position) pairs of this rank's value range, dense local ranks (bit 31 = the hash
+//                         occurs more than once, i.e. in more than one sketch) in sorted order next to the positions
+//   tc_vr_scatter_ranks_dev  received (position, local rank) segments, one per source range -> this rank's slice of the
+//                         position-ordered rank array, the source range's base added
+//   tc_sketches_upload_ranks_dev  the all-gathered rank array -> resident set (bitmap, union lists, tile flags ...)
+namespace {
+template <typename A>
+__global__ void vr_count_kernel(const A *a, const uint32_t *b, uint64_t m, int mode, const unsigned long long *spl, uint32_t nspl,
+                                unsigned long long per, uint32_t nb, unsigned long long *counts)
+{
+    __shared__ unsigned long long s_c[64];
+    if (threadIdx.x < 64) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t k = 0;
+        if (mode == 0) { const unsigned long long x = (unsigned long long)a[i]; for (uint32_t q = 0; q < nspl; q++) k += spl[q] <= x; }
+        else k = (uint32_t)(b[i] / per);
+        atomicAdd(&s_c[min(k, nb - 1)], 1ULL);
+    }
+    __syncthreads();
+    if (threadIdx.x < nb && s_c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_c[threadIdx.x]);
+}
+// every block owns a contiguous chunk: bucket histogram in shared memory, ONE global atomic per bucket and block to reserve
+// the block's slice of every bucket, then the elements are placed through shared-memory cursors (the order inside a
+// bucket is free: the receiver sorts / scatters)
+template <typename A>
+__global__ void vr_scatter_kernel(const A *a, const uint32_t *b, uint64_t m, int mode, const unsigned long long *spl, uint32_t nspl,
+                                  unsigned long long per, uint32_t nb, uint32_t pos_base, unsigned long long *cursor, A *a_out, uint32_t *b_out)
+{
+    __shared__ unsigned long long s_c[64], s_base[64];
+    const uint64_t chunk = (m + gridDim.x - 1) / gridDim.x, lo = (uint64_t)blockIdx.x * chunk, hi = min(m, lo + chunk);
+    auto bucket = [&](A x, uint32_t y) -> uint32_t {
+        uint32_t k = 0;
+        if (mode == 0) { for (uint32_t q = 0; q < nspl; q++) k += spl[q] <= (unsigned long long)x; }
+        else k = (uint32_t)(y / per);
+        return min(k, nb - 1);
+    };
+    if (threadIdx.x < 64) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_c[bucket(a[i], b ? b[i] : pos_base + (uint32_t)i)], 1ULL);
+    __syncthreads();
+    if (threadIdx.x < nb) { s_base[threadIdx.x] = s_c[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], s_c[threadIdx.x]) : 0ULL; s_c[threadIdx.x] = 0; }
+    __syncthreads();
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const A x = a[i];
+        const uint32_t y = b ? b[i] : pos_base + (uint32_t)i;
+        const uint32_t k = bucket(x, y);
+        const unsigned long long at = s_base[k] + atomicAdd(&s_c[k], 1ULL);
+        a_out[at] = x; b_out[at] = y;
+    }
+}
+__global__ void vr_rank_kernel(const uint32_t *scan, const uint64_t *keys, uint64_t m, uint32_t *rank_out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const bool multi = (i > 0 && keys[i - 1] == keys[i]) || (i + 1 < m && keys[i + 1] == keys[i]);
+    rank_out[i] = (scan[i] - 1u) | (multi ? 0x80000000u : 0u);
+}
+__global__ void vr_place_kernel(const uint32_t *pos, const uint32_t *rank, uint64_t m, const unsigned long long *seg_off, const unsigned long long *seg_base,
+                                uint32_t nseg, uint32_t pos_lo, uint64_t share_len, uint32_t *out, unsigned int *bad)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint32_t sg = 0;
+    while (sg + 1 < nseg && seg_off[sg + 1] <= i) sg++;
+    const uint32_t v = rank[i], p = pos[i];
+    if (p < pos_lo || (uint64_t)(p - pos_lo) >= share_len) { atomicExch(bad, 1u); return; }
+    out[p - pos_lo] = (uint32_t)((v & 0x7FFFFFFFu) + seg_base[sg]) | (v & 0x80000000u);
+}
+template <typename A>
+int vr_partition(tc_ctx *ctx, const A *a_dev, const uint32_t *b_dev, uint64_t m, int mode, const uint64_t *splitters, uint64_t per,
+                 uint32_t nb, uint32_t pos_base, A *a_out, uint32_t *b_out, uint64_t *counts)
+{
+    TC_CHECK(nb >= 1 && nb <= 64, "tc_vr_partition_dev: %u buckets (1..64)", nb);
+    TC_CHECK(mode == 0 || (mode == 1 && per > 0 && b_dev), "tc_vr_partition_dev: bad mode / arguments");
+    cudaStream_t st = ctx->stream;
+    void *ws = nullptr;
+    if (tc_scratch(ctx, 3 * 64 * 8, &ws)) return 1;
+    unsigned long long *d_spl = static_cast<unsigned long long *>(ws), *d_cnt = d_spl + 64, *d_cur = d_cnt + 64;
+    TC_CUDA(cudaMemsetAsync(d_cnt, 0, 64 * 8, st));
+    if (mode == 0 && nb > 1) TC_CUDA(cudaMemcpyAsync(d_spl, splitters, (size_t)(nb - 1) * 8, cudaMemcpyHostToDevice, st));
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((m + 255) / 256, (uint64_t)ctx->num_sms * 8));
+    vr_count_kernel<A><<<grid, 256, 0, st>>>(a_dev, b_dev, m, mode, d_spl, nb - 1, per, nb, d_cnt);
+    unsigned long long h_cnt[64];
+    TC_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+    TC_CUDA(cudaStreamSynchronize(st));
+    unsigned long long h_cur[64], acc = 0;
+    for (uint32_t k = 0; k < nb; k++) { h_cur[k] = acc; acc += h_cnt[k]; counts[k] = h_cnt[k]; }
+    TC_CUDA(cudaMemcpyAsync(d_cur, h_cur, (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+    vr_scatter_kernel<A><<<grid, 256, 0, st>>>(a_dev, b_dev, m, mode, d_spl, nb - 1, per, nb, pos_base, d_cur, a_out, b_out);
+    ctx->launches += 2;
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+}  // namespace
+
+extern "C" int tc_vr_partition_dev(tc_ctx *ctx, const uint64_t *a_dev, const uint32_t *b_dev, uint64_t m, int mode,
+                                   const uint64_t *splitters, uint64_t per, uint32_t nb, uint32_t pos_base,
+                                   uint64_t *a_out_dev, uint32_t *b_out_dev, uint64_t *counts)
+{
+    TC_CHECK(ctx && counts && (m == 0 || (a_dev && a_out_dev && b_out_dev)), "tc_vr_partition_dev: bad arguments");
+    TC_CUDA(cudaSetDevice(ctx->device));
+    if (m == 0) { for (uint32_t k = 0; k < nb; k++) counts[k] = 0; return 0; }
+    return vr_partition<uint64_t>(ctx, a_dev, b_dev, m, mode, splitters, per, nb, pos_base, a_out_dev, b_out_dev, counts);
+}
+extern "C" int tc_vr_partition32_dev(tc_ctx *ctx, const uint32_t *a_dev, const uint32_t *b_dev, uint64_t m, uint64_t per, uint32_t nb,
+                                     uint32_t *a_out_dev, uint32_t *b_out_dev, uint64_t *counts)
+{
+    TC_CHECK(ctx && counts && (m == 0 || (a_dev && b_dev && a_out_dev && b_out_dev)), "tc_vr_partition32_dev: bad arguments");
+    TC_CUDA(cudaSetDevice(ctx->device));
+    if (m == 0) { for (uint32_t k = 0; k < nb; k++) counts[k] = 0; return 0; }
+    return vr_partition<uint32_t>(ctx, a_dev, b_dev, m, 1, nullptr, per, nb, 0, a_out_dev, b_out_dev, counts);
+}
+
+extern "C" int tc_vr_local_ranks_dev(tc_ctx *ctx, const uint64_t *keys_dev, const uint32_t *pos_dev, uint64_t m,
+                                     uint32_t *pos_out_dev, uint32_t *rank_out_dev, uint64_t *n_distinct)
+{
+    TC_CHECK(ctx && n_distinct && (m == 0 || (keys_dev && pos_dev && pos_out_dev && rank_out_dev)), "tc_vr_local_ranks_dev: bad arguments");
+    TC_CHECK(m <= 0x7FFFFFFFull, "tc_vr_local_ranks_dev: %llu hashes exceed 2^31 - 1", (unsigned long long)m);
+    TC_CUDA(cudaSetDevice(ctx->device));
+    *n_distinct = 0;
+    if (!m) return 0;
+    cudaStream_t st = ctx->stream;
+    size_t t1 = 0, t2 = 0;
+    TC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr,
+                                            (uint32_t *)nullptr, (int)m, 0, 64, st));
+    TC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, t2, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)m, st));
+    const size_t tmp_bytes = (std::max(t1, t2) + 255) & ~(size_t)255;
+    const size_t o_scan = (m * 8 + 255) & ~(size_t)255, o_tmp = o_scan + ((m * 4 + 255) & ~(size_t)255);
+    void *ws = nullptr;
+    if (tc_scratch(ctx, o_tmp + tmp_bytes, &ws)) return 1;
+    uint8_t *w8 = static_cast<uint8_t *>(ws);
+    uint64_t *skeys = reinterpret_cast<uint64_t *>(w8);
+    uint32_t *scan = reinterpret_cast<uint32_t *>(w8 + o_scan);
+    size_t tb = tmp_bytes;
+    TC_CUDA(cub::DeviceRadixSort::SortPairs(w8 + o_tmp, tb, keys_dev, skeys, pos_dev, pos_out_dev, (int)m, 0, 64, st));
+    cub::CountingInputIterator<uint64_t> counting(0);
+    cub::TransformInputIterator<uint32_t, HeadFlagOp, cub::CountingInputIterator<uint64_t>> heads(counting, HeadFlagOp{skeys});
+    tb = tmp_bytes;
+    TC_CUDA(cub::DeviceScan::InclusiveSum(w8 + o_tmp, tb, heads, scan, (int)m, st));
+    vr_rank_kernel<<<nblk(m, 256), 256, 0, st>>>(scan, skeys, m, rank_out_dev);
+    uint32_t last = 0;
+    TC_CUDA(cudaMemcpyAsync(&last, scan + (m - 1), 4, cudaMemcpyDeviceToHost, st));
+    ctx->launches += 12;
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(st));
+    *n_distinct = last;
+    return 0;
+}
+
+extern "C" int tc_vr_scatter_ranks_dev(tc_ctx *ctx, const uint32_t *pos_dev, const uint32_t *rank_dev, const uint64_t *seg_off,
+                                       const uint64_t *seg_base, uint32_t nseg, uint32_t pos_lo, uint64_t share_len, uint32_t *out_dev)
+{
+    TC_CHECK(ctx && seg_off && seg_base && nseg >= 1 && nseg <= 64, "tc_vr_scatter_ranks_dev: bad arguments");
+    TC_CUDA(cudaSetDevice(ctx->device));
+    const uint64_t m = seg_off[nseg];
+    if (!m) return 0;
+    cudaStream_t st = ctx->stream;
+    void *ws = nullptr;
+    if (tc_scratch(ctx, 3 * 64 * 8, &ws)) return 1;
+    unsigned long long *d_off = static_cast<unsigned long long *>(ws), *d_base = d_off + 65;
+    unsigned int *d_bad = reinterpret_cast<unsigned int *>(d_base + 65), h_bad = 0;
+    TC_CUDA(cudaMemcpyAsync(d_off, seg_off, (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, st));
+    TC_CUDA(cudaMemcpyAsync(d_base, seg_base, (size_t)nseg * 8, cudaMemcpyHostToDevice, st));
+    TC_CUDA(cudaMemsetAsync(d_bad, 0, 4, st));
+    vr_place_kernel<<<nblk(m, 256), 256, 0, st>>>(pos_dev, rank_dev, m, d_off, d_base, nseg, pos_lo, share_len, out_dev, d_bad);
+    TC_CUDA(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    ctx->launches++;
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(st));
+    TC_CHECK(!h_bad, "tc_vr_scatter_ranks_dev: a position outside [%u, %u + %llu) arrived", pos_lo, pos_lo, (unsigned long long)share_len);
+    return 0;
+}
+
+extern "C" int tc_sketches_upload_ranks_dev(tc_ctx *ctx, const uint32_t *ranks_flag_dev, const uint64_t *off, uint32_t n)
+{
+    TC_CHECK(ctx && ranks_flag_dev && off, "tc_sketches_upload_ranks_dev: bad arguments");
+    return upload_common(ctx, nullptr, true, off, n, nullptr, ranks_flag_dev);
 }
 
 // rows -> d_hashes through two page-locked staging buffers: host threads gather chunk c+1 while chunk c is copied

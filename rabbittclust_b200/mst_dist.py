@@ -233,6 +233,134 @@ def upload_sharded_runs(ctx, hashes_pinned, off, dist, device):
     return (per + tail) * 8
 
 
+class VrRank:
+    """One rank of the value-range sharded rank transform (include/tclust.h, "Multi-GPU upload, second form").  The
+    methods are the per-rank steps; whoever drives them performs the exchanges in between -- upload_sharded_vr with
+    torch.distributed, tests/test_upload_runs_gpu.py by hand between simulated ranks on one GPU."""
+    SAMPLE = 2048
+
+    def __init__(self, ctx, rank, world, total, device):
+        import torch
+        import rabbittclust_b200 as T
+        self.T, self.torch, self.L = T, torch, T.lib()
+        self.ctx, self.rank, self.world, self.total, self.dev = ctx, rank, world, int(total), device
+        self.per = max(2, -(-self.total // world))                       # share length (the last share is shorter)
+        self.lo = min(self.total, rank * self.per)
+        self.len = min(self.total, self.lo + self.per) - self.lo
+
+    def load_share(self, hashes_host):
+        """H2D of the own share; returns its sample (numpy u64) for the splitters."""
+        torch = self.torch
+        self.share = torch.empty(max(self.len, 1), dtype=torch.int64, device=self.dev)
+        if self.len:
+            self.share[:self.len].copy_(hashes_host[self.lo:self.lo + self.len], non_blocking=True)
+        step = max(1, self.len // self.SAMPLE)
+        smp = self.share[:self.len:step][:self.SAMPLE]
+        out = torch.full((self.SAMPLE,), -1, dtype=torch.int64, device=self.dev)      # all-ones = "no sample"
+        out[:len(smp)] = smp
+        return out
+
+    @staticmethod
+    def splitters(samples_u64, world):
+        """G-1 ascending splitters from the gathered samples (numpy u64, all-ones entries = padding)."""
+        v = np.sort(samples_u64[samples_u64 != U64_MAX])
+        if len(v) == 0:
+            return np.zeros(world - 1, np.uint64)
+        return np.ascontiguousarray(v[[min(len(v) - 1, (i * len(v)) // world) for i in range(1, world)]], np.uint64)
+
+    def partition_by_value(self, spl):
+        torch, T = self.torch, self.T
+        self.pk = torch.empty(max(self.len, 1), dtype=torch.int64, device=self.dev)
+        self.pp = torch.empty(max(self.len, 1), dtype=torch.int32, device=self.dev)
+        cnt = np.zeros(self.world, np.uint64)
+        torch.cuda.current_stream().synchronize()
+        T._chk(self.L.tc_vr_partition_dev(self.ctx._h, self.share.data_ptr(), None, self.len, 0, T._p(spl, C.c_uint64), 0, self.world,
+                                          self.lo, self.pk.data_ptr(), self.pp.data_ptr(), T._p(cnt, C.c_uint64)))
+        return cnt.astype(np.int64)
+
+    def local_ranks(self, keys, pos):
+        """keys/pos: the (hash, position) pairs of this rank's value range (device tensors).  Returns the distinct count."""
+        torch, T = self.torch, self.T
+        m = int(keys.numel())
+        self.m = m
+        self.rpos = torch.empty(max(m, 1), dtype=torch.int32, device=self.dev)
+        self.rrank = torch.empty(max(m, 1), dtype=torch.int32, device=self.dev)
+        nd = C.c_uint64(0)
+        torch.cuda.current_stream().synchronize()
+        T._chk(self.L.tc_vr_local_ranks_dev(self.ctx._h, keys.data_ptr(), pos.data_ptr(), m, self.rpos.data_ptr(), self.rrank.data_ptr(), C.byref(nd)))
+        return int(nd.value)
+
+    def partition_by_owner(self):
+        torch, T = self.torch, self.T
+        self.qr = torch.empty(max(self.m, 1), dtype=torch.int32, device=self.dev)
+        self.qp = torch.empty(max(self.m, 1), dtype=torch.int32, device=self.dev)
+        cnt = np.zeros(self.world, np.uint64)
+        T._chk(self.L.tc_vr_partition32_dev(self.ctx._h, self.rrank.data_ptr(), self.rpos.data_ptr(), self.m, self.per, self.world,
+                                            self.qr.data_ptr(), self.qp.data_ptr(), T._p(cnt, C.c_uint64)))
+        return cnt.astype(np.int64)
+
+    def place(self, pos, rank, seg_counts, seg_base):
+        """pos/rank: the pairs that came back, grouped by source range; returns this rank's slice (length per) of the rank array."""
+        torch, T = self.torch, self.T
+        out = torch.zeros(self.per, dtype=torch.int32, device=self.dev)
+        seg_off = np.zeros(self.world + 1, np.uint64)
+        seg_off[1:] = np.cumsum(np.asarray(seg_counts, np.uint64))
+        base = np.ascontiguousarray(seg_base, np.uint64)
+        torch.cuda.current_stream().synchronize()
+        T._chk(self.L.tc_vr_scatter_ranks_dev(self.ctx._h, pos.data_ptr(), rank.data_ptr(), T._p(seg_off, C.c_uint64), T._p(base, C.c_uint64),
+                                              self.world, self.lo, self.len, out.data_ptr()))
+        return out
+
+    def finish(self, ranks_full, off):
+        torch, T = self.torch, self.T
+        off = np.ascontiguousarray(off, np.uint64)
+        self.ctx.n = len(off) - 1
+        self.ctx.sizes = np.diff(off).astype(np.int64)
+        torch.cuda.current_stream().synchronize()
+        T._chk(self.L.tc_sketches_upload_ranks_dev(self.ctx._h, ranks_full.data_ptr(), T._p(off, C.c_uint64), self.ctx.n))
+
+
+def upload_sharded_vr(ctx, hashes_pinned, off, dist, device):
+    """Multi-GPU upload with the rank transform sharded by hash value range (see VrRank): every rank copies 1/world of the
+    hashes, sorts 1/world of them, and only 4-byte ranks are all-gathered.  Returns the bytes this rank copied from the host."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    total = int(off[-1])
+    r = VrRank(ctx, rank, world, total, device)
+    smp = r.load_share(hashes_pinned.view(torch.int64))
+    allsmp = torch.empty(world * VrRank.SAMPLE, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allsmp, smp)
+    spl = VrRank.splitters(allsmp.cpu().numpy().view(np.uint64), world)
+    send = r.partition_by_value(spl)
+    cnts = torch.empty(world * world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(cnts, torch.from_numpy(send).to(device))
+    cm = cnts.cpu().numpy().reshape(world, world)                     # cm[s][d]: pairs rank s sends to range d
+    recv = cm[:, rank]
+    m = int(recv.sum())
+    keys = torch.empty(max(m, 1), dtype=torch.int64, device=device)
+    pos = torch.empty(max(m, 1), dtype=torch.int32, device=device)
+    dist.all_to_all_single(keys[:m], r.pk[:r.len], recv.tolist(), send.tolist())
+    dist.all_to_all_single(pos[:m], r.pp[:r.len], recv.tolist(), send.tolist())
+    nd = r.local_ranks(keys[:m], pos[:m])
+    nds = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(nds, torch.tensor([nd], dtype=torch.int64, device=device))
+    base = np.concatenate([[0], np.cumsum(nds.cpu().numpy())[:-1]])
+    back = r.partition_by_owner()
+    dist.all_gather_into_tensor(cnts, torch.from_numpy(back).to(device))
+    bm = cnts.cpu().numpy().reshape(world, world)                     # bm[s][d]: pairs range s sends back to owner d
+    rb = bm[:, rank]
+    mb = int(rb.sum())
+    bpos = torch.empty(max(mb, 1), dtype=torch.int32, device=device)
+    brank = torch.empty(max(mb, 1), dtype=torch.int32, device=device)
+    dist.all_to_all_single(bpos[:mb], r.qp[:r.m], rb.tolist(), back.tolist())
+    dist.all_to_all_single(brank[:mb], r.qr[:r.m], rb.tolist(), back.tolist())
+    mine = r.place(bpos, brank, rb, base)
+    full = torch.empty(r.per * world, dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(full, mine)
+    r.finish(full, off)
+    return r.len * 8
+
+
 def distributed_mst(ctx, k, threshold, containment=False, dist=None):
     """Full multi-GPU MST of the sketches uploaded (replicated) on every rank's ctx."""
     import rabbittclust_b200 as T

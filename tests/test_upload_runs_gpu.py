@@ -55,3 +55,57 @@ def test_upload_from_sorted_runs(tc, shares):
         one = np.array([0, total], np.uint64)
         rc = L.tc_sketches_upload_runs_dev(c._h, keys.data_ptr(), pos.data_ptr(), tc._p(one, C.c_uint64), 1, tc._p(off, C.c_uint64), n)
         assert rc != 0 and b"sketch 0 is not strictly ascending" in L.tc_last_error()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_value_range_sharded_transform(tc, world):
+    """The value-range sharded rank transform (mst_dist.VrRank) with `world` simulated ranks on one GPU, the exchanges done
+    by hand: the resident set equals the one of the plain upload (pair counts, MST, edges)."""
+    import torch
+    from rabbittclust_b200.mst_dist import VrRank
+    sk = synth.family_sketches(7, 12, s=250, seed=61) + synth.family_sketches(3, 9, seed=62, ragged=(30, 700))
+    sk.insert(5, np.zeros(0, np.uint64))
+    flat, off = tc.pack_sketches(sk)
+    total, n = int(off[-1]), len(sk)
+    dev = torch.device("cuda", 0)
+    with tc.Context(0) as ref:
+        ref.upload(sk)
+        want = ref.pair_common(0, n, 0, n, impl=2)
+        want_mst = ref.mst(21, 0.05).copy()
+    hosts = torch.from_numpy(flat[:total].view(np.int64).copy())
+    ctxs = [tc.Context(0) for _ in range(world)]
+    try:
+        rs = [VrRank(c, r, world, total, dev) for r, c in enumerate(ctxs)]
+        smp = torch.cat([r.load_share(hosts) for r in rs]).cpu().numpy().view(np.uint64)
+        spl = VrRank.splitters(smp, world)
+        send = np.stack([r.partition_by_value(spl) for r in rs])             # send[s][d]
+        nds = []
+        for d, r in enumerate(rs):                                              # all-to-all by hand
+            ks, ps = [], []
+            for s_, src in enumerate(rs):
+                o = int(send[s_, :d].sum())
+                ks.append(src.pk[o:o + int(send[s_, d])]); ps.append(src.pp[o:o + int(send[s_, d])])
+            nds.append(r.local_ranks(torch.cat(ks).contiguous(), torch.cat(ps).contiguous()))
+        base = np.concatenate([[0], np.cumsum(nds)[:-1]])
+        back = np.stack([r.partition_by_owner() for r in rs])                  # back[s][d]
+        slices = []
+        for d, r in enumerate(rs):
+            ps, rk = [], []
+            for s_, src in enumerate(rs):
+                o = int(back[s_, :d].sum())
+                ps.append(src.qp[o:o + int(back[s_, d])]); rk.append(src.qr[o:o + int(back[s_, d])])
+            slices.append(r.place(torch.cat(ps).contiguous(), torch.cat(rk).contiguous(), back[:, d], base))
+        full = torch.cat(slices).contiguous()
+        for r in rs:
+            r.finish(full, off)
+        for c in ctxs:
+            assert np.array_equal(c.pair_common(0, n, 0, n, impl=2), want)
+            assert np.array_equal(c.mst(21, 0.05), want_mst)
+        # the ranks are the dense ranks of the plain transform: compare through the union of all hashes
+        ranks = (full[:total].cpu().numpy().view(np.uint32) & np.uint32(0x7FFFFFFF)).astype(np.int64)
+        uniq, inv, cnt = np.unique(flat[:total], return_inverse=True, return_counts=True)
+        assert np.array_equal(ranks, inv)
+        assert np.array_equal((full[:total].cpu().numpy().view(np.uint32) >> np.uint32(31)).astype(bool), cnt[inv] > 1)
+    finally:
+        for c in ctxs:
+            c.close()
