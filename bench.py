@@ -414,13 +414,13 @@ def run_pairs(args):
         if dist is None:
             ctx.upload(hashes=hp, off=off)
             return int(h.nbytes + off.nbytes)
-        # every rank copies 1/world of the hashes and sorts 1/world of them (by value range); 4-byte ranks are all-gathered
+        # every rank copies and sorts only its 1/world share; the sorted runs are all-gathered over NVLink and merged
         from rabbittclust_b200 import mst_dist
         if os.environ.get("TCLUST_BENCH_UPLOAD") == "allgather_raw":      # round 1's scheme: all-gather the raw hashes, every rank sorts all
             return mst_dist.upload_sharded(ctx, h_pin, off, dist, dev) + int(off.nbytes)
-        if os.environ.get("TCLUST_BENCH_UPLOAD") == "runs":               # every rank sorts its share, the sorted runs are gathered and merged
-            return mst_dist.upload_sharded_runs(ctx, h_pin, off, dist, dev) + int(off.nbytes)
-        return mst_dist.upload_sharded_vr(ctx, h_pin, off, dist, dev) + int(off.nbytes)
+        if os.environ.get("TCLUST_BENCH_UPLOAD") == "vr":                 # rank transform sharded by hash value range (measured: not faster up to 8 GPUs)
+            return mst_dist.upload_sharded_vr(ctx, h_pin, off, dist, dev) + int(off.nbytes)
+        return mst_dist.upload_sharded_runs(ctx, h_pin, off, dist, dev) + int(off.nbytes)
 
     # ---- value: the whole operation on resident sketches -- dense pass (this rank's units) + every Boruvka round +
     #      the sorted MST on the host (tc_mst), CUDA events on the library's stream
