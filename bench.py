@@ -475,6 +475,7 @@ def run_pairs(args):
         nd = len(od) - 1
         if dist is not None:
             ctx.mg_leave()
+            sync_all()                     # every rank has unmapped its peers before any exchange buffer is re-created
             mine = torch.frombuffer(bytearray(ctx.mg_export(max(n, nd))), dtype=torch.uint8).to(dev)
             allh = torch.empty(world * T.MG_HANDLE_BYTES, dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(allh, mine)

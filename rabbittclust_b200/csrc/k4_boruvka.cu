@@ -33,6 +33,7 @@ namespace {
 
 constexpr int K4_THREADS = 512;
 constexpr unsigned long long K4_NONE = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned long long K4_CHUNK = 1024;               // candidate edges per liveness flag (one warp, 32 coalesced steps)
 constexpr long long K4_SPIN_LIMIT_NS = 10000000000ll;       // a grid barrier that waits longer gives up (error, no hang)
 constexpr long long K4_SYS_SPIN_LIMIT_NS = 30000000000ll;   // same for the multi-GPU barrier (a peer may still be in its dense pass)
 
@@ -57,6 +58,7 @@ struct K4Args {
     unsigned long long *red;          // 2 x n: reduced key / edge of this round (multi-GPU only)
     int rank, nranks;
     unsigned long long sys_base;      // epoch of the multi-GPU barrier at launch (flags only ever grow: no reset between launches)
+    unsigned char *live;              // per chunk of K4_CHUNK candidate edges: 0 = every edge of it lies inside one component (for good)
     unsigned long long *out_key, *out_id;      // forest, n entries each (preset to all ones)
     uint32_t *ctl;                    // [0] forest count, [1] grid barrier, [2..3] merged per round parity, [4] abort, [5] rounds, [6] some rank's edges overflowed
 };
@@ -137,6 +139,8 @@ __global__ void __launch_bounds__(K4_THREADS) k4_boruvka_kernel(const K4Args a)
     unsigned long long m = *a.edge_counter;
     if (m > a.edge_cap) m = a.edge_cap;
     unsigned long long *mine = a.xbuf[a.rank];
+    const unsigned long long gwarp = gtid >> 5, nwarps = gsize >> 5, nchunks = (m + K4_CHUNK - 1) / K4_CHUNK;
+    const unsigned int lane = threadIdx.x & 31;
 
     for (unsigned long long v = gtid; v < n; v += gsize) { a.comp[v] = (int32_t)v; a.parent[v] = (uint32_t)v; }
     // a rank whose candidate edges did not fit tells every peer (note slot 8 + rank = this launch's epoch), so that all
@@ -152,14 +156,32 @@ __global__ void __launch_bounds__(K4_THREADS) k4_boruvka_kernel(const K4Args a)
         for (unsigned long long c = gtid; c < n; c += gsize) { bkey[c] = K4_NONE; bedge[c] = K4_NONE; }
         if (gtid == 0) { a.ctl[2 + par] = 0u; a.ctl[5] = round + 1; }
         k4_grid_sync(a.ctl, epoch);
-        // ---- phase 1: smallest key leaving every component
-        for (unsigned long long e = gtid; e < m; e += gsize) {
-            const tc_pair p = a.edges[e];
-            const int32_t ci = a.comp[p.i], cj = a.comp[p.j];
-            if (ci == cj) continue;
-            const unsigned long long k = k4_edge_key(p, a.size, a.mode, a.semb);
-            if (k < bkey[ci]) atomicMin(&bkey[ci], k);
-            if (k < bkey[cj]) atomicMin(&bkey[cj], k);
+        // ---- phase 1: smallest key leaving every component.  A warp takes a chunk of K4_CHUNK consecutive edges; the pass
+        //      appends a tile's edges together, so most chunks lie inside one family and are dead after the first merges:
+        //      a dead chunk costs one flag byte instead of 12 KB in every later phase
+        for (unsigned long long c = gwarp; c < nchunks; c += nwarps) {
+            if (round > 0 && !a.live[c]) continue;
+            bool any = false;
+            const unsigned long long e1 = min(m, (c + 1) * K4_CHUNK);
+            for (unsigned long long e = c * K4_CHUNK + lane; e < e1; e += 64) {       // two edges per lane in flight
+                const bool two = e + 32 < e1;
+                const tc_pair p = a.edges[e], q = a.edges[two ? e + 32 : e];
+                const int32_t ci = a.comp[p.i], cj = a.comp[p.j], di = a.comp[q.i], dj = a.comp[q.j];
+                if (ci != cj) {
+                    any = true;
+                    const unsigned long long k = k4_edge_key(p, a.size, a.mode, a.semb);
+                    if (k < bkey[ci]) atomicMin(&bkey[ci], k);
+                    if (k < bkey[cj]) atomicMin(&bkey[cj], k);
+                }
+                if (two && di != dj) {
+                    any = true;
+                    const unsigned long long k = k4_edge_key(q, a.size, a.mode, a.semb);
+                    if (k < bkey[di]) atomicMin(&bkey[di], k);
+                    if (k < bkey[dj]) atomicMin(&bkey[dj], k);
+                }
+            }
+            const bool alive = __any_sync(0xffffffffu, any);
+            if (lane == 0) a.live[c] = alive ? 1 : 0;
         }
         for (unsigned long long e = gtid; e < a.nfin; e += gsize) {
             const unsigned long long id = a.fin_id[e], k = a.fin_key[e];
@@ -183,14 +205,18 @@ __global__ void __launch_bounds__(K4_THREADS) k4_boruvka_kernel(const K4Args a)
         }
         k4_grid_sync(a.ctl, epoch);
         // ---- phase 2: smallest (i, j) among the edges that carry a component's best key
-        for (unsigned long long e = gtid; e < m; e += gsize) {
-            const tc_pair p = a.edges[e];
-            const int32_t ci = a.comp[p.i], cj = a.comp[p.j];
-            if (ci == cj) continue;
-            const unsigned long long k = k4_edge_key(p, a.size, a.mode, a.semb);
-            const unsigned long long id = ((unsigned long long)p.i << 32) | p.j;
-            if (k == rkey[ci] && id < bedge[ci]) atomicMin(&bedge[ci], id);
-            if (k == rkey[cj] && id < bedge[cj]) atomicMin(&bedge[cj], id);
+        for (unsigned long long c = gwarp; c < nchunks; c += nwarps) {
+            if (!a.live[c]) continue;
+            const unsigned long long e1 = min(m, (c + 1) * K4_CHUNK);
+            for (unsigned long long e = c * K4_CHUNK + lane; e < e1; e += 32) {
+                const tc_pair p = a.edges[e];
+                const int32_t ci = a.comp[p.i], cj = a.comp[p.j];
+                if (ci == cj) continue;
+                const unsigned long long k = k4_edge_key(p, a.size, a.mode, a.semb);
+                const unsigned long long id = ((unsigned long long)p.i << 32) | p.j;
+                if (k == rkey[ci] && id < bedge[ci]) atomicMin(&bedge[ci], id);
+                if (k == rkey[cj] && id < bedge[cj]) atomicMin(&bedge[cj], id);
+            }
         }
         for (unsigned long long e = gtid; e < a.nfin; e += gsize) {
             const unsigned long long id = a.fin_id[e], k = a.fin_key[e];
@@ -260,7 +286,7 @@ void tc_k4_free(tc_ctx *ctx)
     tc_k4_state &k = ctx->k4;
     for (int g = 0; g < 8; g++)
         if (k.peer_opened[g]) { cudaIpcCloseMemHandle(k.peer_xbuf[g]); k.peer_opened[g] = false; }
-    cudaFree(k.d_xbuf); cudaFree(k.d_red); cudaFree(k.d_parent); cudaFree(k.d_out); cudaFree(k.d_fin); cudaFree(k.d_ctl); cudaFree(k.d_sort_tmp);
+    cudaFree(k.d_xbuf); cudaFree(k.d_red); cudaFree(k.d_parent); cudaFree(k.d_out); cudaFree(k.d_fin); cudaFree(k.d_live); cudaFree(k.d_ctl); cudaFree(k.d_sort_tmp);
     if (k.h_out) cudaFreeHost(k.h_out);
     for (int e = 0; e < 3; e++) if (k.ev[e]) cudaEventDestroy(k.ev[e]);
     k = tc_k4_state();
@@ -328,6 +354,11 @@ int tc_k4_enqueue(tc_ctx *ctx, int mode, const unsigned long long *d_fin_key, co
     else a.xbuf[0] = k.d_xbuf;
     a.red = k.d_red;
     a.out_key = o_key; a.out_id = o_id; a.ctl = k.d_ctl;
+    {   // liveness flags of the edge chunks (written in round 0 before they are read)
+        const uint64_t chunks = (ctx->edge_cap + K4_CHUNK - 1) / K4_CHUNK + 1;
+        if (k4_grow(&k.d_live, &k.cap_live, chunks)) return 1;
+        a.live = k.d_live;
+    }
     a.xstride = k.xbuf_n;
     if (a.nranks > 1) {
         // The epoch flags are zeroed once, when the group is formed, and only grow: every rank launches the same

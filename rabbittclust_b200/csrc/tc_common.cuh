@@ -39,6 +39,7 @@ struct tc_k4_state {
     unsigned long long *d_out = nullptr;  uint64_t cap_out = 0;      // forest (key, id) + sort alternates: 4 x n
     unsigned long long *d_fin = nullptr;  uint64_t cap_fin = 0;      // forest of the edge batches seen so far (bounded-memory MST): 2 x n
     uint32_t *d_ctl = nullptr;
+    unsigned char *d_live = nullptr;      uint64_t cap_live = 0;     // liveness flag per chunk of candidate edges
     void *d_sort_tmp = nullptr;           uint64_t cap_sort_tmp = 0;
     void *h_out = nullptr;                uint64_t h_out_bytes = 0;  // page-locked read-back buffer
     int grid = 0;
