@@ -237,6 +237,42 @@ void cal_size(const Options &o, uint64_t &max_size, uint64_t &min_size, uint64_t
     cerr << "\t===the averageSize is: " << avg_size << endl;
 }
 
+// the two steps tune_parameters (src/sub_command.cpp:2383-2467) and tune_kssd_parameters (:2317-2382) share: the k-mer size
+// rule (k is replaced when it is too small for the largest genome or more than 3 above the recommendation) and
+// the check of the threshold against the largest distance the sketches can resolve.  The stderr lines are the reference's.
+void tune_kmer_size(Options &o, uint64_t max_size)
+{
+    const double warning_rate = 0.01, recommend_rate = 0.0001;
+    const int recommended = ceil(log(max_size * (1 - recommend_rate) / recommend_rate) / log(4));
+    const int warning = ceil(log(max_size * (1 - warning_rate) / warning_rate) / log(4));
+    if (!o.set_kmer) o.kmer = recommended;
+    else if (o.kmer < warning) {
+        cerr << "the kmerSize " << o.kmer << " is too small for the maximum genome size of " << max_size << endl;
+        cerr << "replace the kmerSize to the: " << recommended << " for reducing the random collision of kmers" << endl;
+        o.kmer = recommended;
+    } else if (o.kmer > recommended + 3) {
+        cerr << "the kmerSize " << o.kmer << " maybe too large for the maximum genome size of " << max_size << endl;
+        cerr << "replace the kmerSize to the " << recommended << " for increasing the sensitivity of genome comparison" << endl;
+        o.kmer = recommended;
+    }
+}
+
+bool check_threshold_and_report(const Options &o, double min_jaccard)
+{
+    const double max_dist = min_jaccard >= 1.0 ? 1.0 : -1.0 / o.kmer * log(2 * min_jaccard / (1.0 + min_jaccard));
+    cerr << "-----the max recommand distance threshold is: " << max_dist << endl;
+    if (o.threshold > max_dist) {
+        cerr << "ERROR: tune_parameters(), the threshold: " << o.threshold << " is out of the valid distance range estimated by Mash distance or AAF distance" << endl;
+        cerr << "Please set a distance threshold with -d option" << endl;
+        return false;
+    }
+    cerr << (o.by_file ? "-----sketch by file!" : "-----sketch by sequence!") << endl;
+    cerr << "-----the kmerSize is: " << o.kmer << endl;
+    cerr << "-----the thread number is: " << o.threads << endl;
+    cerr << "-----the threshold is: " << o.threshold << endl;
+    return true;
+}
+
 bool tune_parameters(Options &o)
 {
     uint64_t max_size, min_size, avg_size;
@@ -253,31 +289,8 @@ bool tune_parameters(Options &o)
         cerr << "set the containCompress to: " << o.compress << endl;
     }
 #endif
-    const double warning_rate = 0.01, recommend_rate = 0.0001;
-    int recommended = ceil(log(max_size * (1 - recommend_rate) / recommend_rate) / log(4));
-    int warning = ceil(log(max_size * (1 - warning_rate) / warning_rate) / log(4));
-    if (!o.set_kmer) o.kmer = recommended;
-    else if (o.kmer < warning) {
-        cerr << "the kmerSize " << o.kmer << " is too small for the maximum genome size of " << max_size << endl;
-        cerr << "replace the kmerSize to the: " << recommended << " for reducing the random collision of kmers" << endl;
-        o.kmer = recommended;
-    } else if (o.kmer > recommended + 3) {
-        cerr << "the kmerSize " << o.kmer << " maybe too large for the maximum genome size of " << max_size << endl;
-        cerr << "replace the kmerSize to the " << recommended << " for increasing the sensitivity of genome comparison" << endl;
-        o.kmer = recommended;
-    }
-    double min_jaccard = !o.containment ? 1.0 / o.sketch_size : 1.0 / (min_size / o.compress);
-    double max_dist = min_jaccard >= 1.0 ? 1.0 : -1.0 / o.kmer * log(2 * min_jaccard / (1.0 + min_jaccard));
-    cerr << "-----the max recommand distance threshold is: " << max_dist << endl;
-    if (o.threshold > max_dist) {
-        cerr << "ERROR: tune_parameters(), the threshold: " << o.threshold << " is out of the valid distance range estimated by Mash distance or AAF distance" << endl;
-        cerr << "Please set a distance threshold with -d option" << endl;
-        return false;
-    }
-    cerr << (o.by_file ? "-----sketch by file!" : "-----sketch by sequence!") << endl;
-    cerr << "-----the kmerSize is: " << o.kmer << endl;
-    cerr << "-----the thread number is: " << o.threads << endl;
-    cerr << "-----the threshold is: " << o.threshold << endl;
+    tune_kmer_size(o, max_size);
+    if (!check_threshold_and_report(o, !o.containment ? 1.0 / o.sketch_size : 1.0 / (min_size / o.compress))) return false;
     if (o.containment) cerr << "-----use the AAF distance (variable-sketch-size), the sketchSize is in proportion with 1/" << o.compress << endl;
     else cerr << "-----use the Mash distance (fixed-sketch-size), the sketchSize is: " << o.sketch_size << endl;
     return true;
@@ -294,31 +307,8 @@ bool tune_kssd_parameters(Options &o)
     cal_size(o, max_size, min_size, avg_size);
     const int compression = 1 << (4 * o.drlevel);
     const int sketch_size = avg_size / compression;
-    const double warning_rate = 0.01, recommend_rate = 0.0001;
-    int recommended = ceil(log(max_size * (1 - recommend_rate) / recommend_rate) / log(4));
-    int warning = ceil(log(max_size * (1 - warning_rate) / warning_rate) / log(4));
-    if (!o.set_kmer) o.kmer = recommended;
-    else if (o.kmer < warning) {
-        cerr << "the kmerSize " << o.kmer << " is too small for the maximum genome size of " << max_size << endl;
-        cerr << "replace the kmerSize to the: " << recommended << " for reducing the random collision of kmers" << endl;
-        o.kmer = recommended;
-    } else if (o.kmer > recommended + 3) {
-        cerr << "the kmerSize " << o.kmer << " maybe too large for the maximum genome size of " << max_size << endl;
-        cerr << "replace the kmerSize to the " << recommended << " for increasing the sensitivity of genome comparison" << endl;
-        o.kmer = recommended;
-    }
-    double min_jaccard = !o.containment ? 1.0 / sketch_size : 1.0 / (min_size / compression);
-    double max_dist = min_jaccard >= 1.0 ? 1.0 : -1.0 / o.kmer * log(2 * min_jaccard / (1.0 + min_jaccard));
-    cerr << "-----the max recommand distance threshold is: " << max_dist << endl;
-    if (o.threshold > max_dist) {
-        cerr << "ERROR: tune_parameters(), the threshold: " << o.threshold << " is out of the valid distance range estimated by Mash distance or AAF distance" << endl;
-        cerr << "Please set a distance threshold with -d option" << endl;
-        return false;
-    }
-    cerr << (o.by_file ? "-----sketch by file!" : "-----sketch by sequence!") << endl;
-    cerr << "-----the kmerSize is: " << o.kmer << endl;
-    cerr << "-----the thread number is: " << o.threads << endl;
-    cerr << "-----the threshold is: " << o.threshold << endl;
+    tune_kmer_size(o, max_size);
+    if (!check_threshold_and_report(o, !o.containment ? 1.0 / sketch_size : 1.0 / (min_size / compression))) return false;
     if (o.containment) cerr << "-----use the AAF distance, the sketchSize is approximately in proportion with 1/" << compression << endl;
     else cerr << "-----use the Mash distance, the sketchSize is about: " << sketch_size << endl;
     return true;

@@ -74,3 +74,21 @@ def test_shard_bounds_cover_everything():
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert all((hi - lo) % 2 == 0 for lo, hi in spans[:-1])
+
+
+def test_value_range_splitters_partition_evenly():
+    """VrRank.splitters (host side of the value-range sharded upload): G-1 ascending splitters from the gathered samples;
+    bucket = number of splitters <= hash is monotone in the hash and balances the sample."""
+    from rabbittclust_b200.mst_dist import VrRank, U64_MAX
+    rng = np.random.default_rng(5)
+    smp = rng.integers(0, 2**63, 5000, dtype=np.uint64)
+    smp[::7] = U64_MAX                                  # padding entries of short shares
+    for world in (1, 2, 5, 8):
+        spl = VrRank.splitters(smp, world)
+        assert len(spl) == world - 1 and np.all(np.diff(spl.astype(np.float64)) >= 0)
+        real = np.sort(smp[smp != U64_MAX])
+        bucket = np.searchsorted(spl, real, side="right")          # = number of splitters <= x
+        assert np.all(np.diff(bucket) >= 0)
+        counts = np.bincount(bucket, minlength=world)
+        assert counts.max() - counts.min() <= 2
+    assert np.array_equal(VrRank.splitters(np.full(10, U64_MAX), 4), np.zeros(3, np.uint64))
