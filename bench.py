@@ -643,7 +643,11 @@ def run_pairs(args):
             "e2e": {"value": pairs_per_step / (e2e_ms / 1e3), "unit": "pairs/s",
                     "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "ms_per_step": e2e_ms,
-                    "what": "host hashes -> tc_sketches_upload -> tc_mst -> sorted MST edges on the host (all Boruvka rounds)"},
+                    "what": "host hashes -> tc_sketches_upload -> tc_mst -> sorted MST edges on the host (all Boruvka rounds)",
+                    "pcie": {"h2d_gb_per_rank": round(h2d / 1e9, 3),
+                             "copy_ms_at_55_gbs": round(h2d / 55e9 * 1e3, 2),
+                             "note": "the host->device copy of the u64 hashes is the floor of this step: at the ~55 GB/s a "
+                                     "PCIe Gen5 x16 link sustains it alone takes copy_ms_at_55_gbs of ms_per_step"}},
             "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
         }
         if same_as_single is not None:

@@ -267,3 +267,25 @@ def test_k3s_long_union_lists(tc, oracle):
     ref = oracle.mst(sk, 21, 0.2)
     _same_forest(oracle, m, ref, n, 0.2)
     assert st_tiles["tiles_flagged"] == st_tiles["tiles_total"] == 28
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 33])
+def test_tiny_sets(tc, oracle, n):
+    """One, two, three sketches and one sketch more than a block: MST, threshold clustering and a group of one."""
+    rng = np.random.default_rng(n)
+    base = np.unique(rng.integers(0, 2**40, 300, dtype=np.uint64))
+    sk = [np.sort(rng.choice(base, 200, replace=False)) for _ in range(n)]
+    if n >= 3:
+        sk[2] = np.unique(rng.integers(2**41, 2**42, 150, dtype=np.uint64))      # shares nothing with the others
+    with tc.Context(0) as c:
+        c.upload(sk)
+        m = c.mst(21, 0.5)
+        ref = oracle.mst(sk, 21, 0.5)
+        _same_forest(oracle, m, ref, n, 0.5)
+        nc, lab = c.cluster_threshold(21, 0.5)
+        _, lab_ref, _ = oracle.clusters_from_mst(ref, n, 0.5)
+        assert _labels_partition(lab) == _labels_partition(lab_ref)
+        h = c.mg_export(n)
+        c.mg_join(0, 1, [h])
+        assert np.array_equal(c.mst(21, 0.5), m)
+        c.mg_leave()
