@@ -466,6 +466,28 @@ def run_pairs(args):
     e2e_ms = (time.time() - t0) * 1e3 / e2e_steps
     d2h = int(mst.nbytes)
 
+    # ---- threshold-only clustering: the clusters at d straight from the pass, no edges, no MST
+    thr_only = None
+    if not args.no_robust:
+        sync_all()
+        ctx.cluster_threshold(k, thr, False, rank, world)
+        t_c = time.time()
+        nc_t, lab_t = ctx.cluster_threshold(k, thr, False, rank, world)
+        thr_ms = (time.time() - t_c) * 1e3
+        if dist is not None:                     # the parts' labels are merged on the host (tc_labels_merge)
+            allab = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(world)]
+            dist.all_gather(allab, torch.from_numpy(lab_t.copy()).to(dev))
+            merged = allab[0].cpu().numpy()
+            for x in allab[1:]:
+                nc_t, merged = T.labels_merge(merged, x.cpu().numpy())
+            lab_t = merged
+        if rank == 0:
+            want_lab = partition_labels(n, mst["pre"], mst["suf"], mst["dist"], thr)
+            thr_only = {"what": "tc_cluster_threshold: connected components of the candidate pairs within the threshold (device "
+                                "union-find epilogue of the pass, O(n) memory); this rank's part of the pass",
+                        "ms": round(thr_ms, 3), "clusters": int(len(np.unique(lab_t))),
+                        "equals_mst_partition": bool(np.array_equal(lab_t, want_lab))}
+
     # ---- a set large enough to scale: one species of --dense-n sketches (every pair is a candidate, every tile dense).
     #      configs[2] itself is ~1 ms of work for one GPU, of which only the dense pass shards; this leg shows the same
     #      collective tc_mst where the sharded part dominates.  Same code path, every rank, device-timed like `value`.
@@ -656,6 +678,8 @@ def run_pairs(args):
             line["robustness"] = robust
         if large is not None:
             line["large_set"] = large
+        if thr_only is not None:
+            line["threshold_only"] = thr_only
         if semb_ms is not None:
             line["semantic_b"] = {"what": "the same pass with Mash union-limited counts (MinHash::jaccard stop rule, "
                                           "sketchSize 1000) on the step-budget merge kernel k3_tile_kernel<EDGES,SEMB>; "

@@ -53,6 +53,18 @@ __global__ void k3t_flag_kernel(const uint32_t *key, const uint32_t *blk, unsign
     }
 }
 
+// work of k3t_flag_kernel = sum over the posting lists of L(L-1)/2: the last entry of every list walks back to its start
+// (O(postings) in total) and adds its list's share
+__global__ void k3t_work_kernel(const uint32_t *key, unsigned long long m, unsigned long long *work)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (i + 1 < m && key[i + 1] == key[i]) return;
+    unsigned long long L = 1;
+    for (unsigned long long j = i; j-- > 0 && key[j] == key[i];) L++;
+    if (L > 1) atomicAdd(work, L * (L - 1) / 2);
+}
+
 // diagonal tiles, and the row + column of every block without a union list (K3H streams those without a list)
 __global__ void k3t_fixed_kernel(const uint32_t *bu_count, uint32_t nrb, uint32_t *flags, uint32_t words)
 {
@@ -119,7 +131,7 @@ int tc_tile_flags_build(tc_ctx *ctx, const std::vector<uint32_t> &dist)
         TC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
                                                 (uint32_t *)nullptr, (int)m, 0, end_bit, st));
         const size_t a256 = 255;
-        const size_t o_pref = 0, o_k0 = (o_pref + (nrb + 1) * 8 + a256) & ~a256, o_b0 = (o_k0 + m * 4 + a256) & ~a256;
+        const size_t o_pref = 0, o_k0 = (o_pref + (nrb + 2) * 8 + a256) & ~a256, o_b0 = (o_k0 + m * 4 + a256) & ~a256;
         const size_t o_k1 = (o_b0 + m * 4 + a256) & ~a256, o_b1 = (o_k1 + m * 4 + a256) & ~a256, o_tmp = (o_b1 + m * 4 + a256) & ~a256;
         void *ws = nullptr;
         if (tc_scratch(ctx, o_tmp + tmp_bytes, &ws)) return 1;
@@ -131,8 +143,21 @@ int tc_tile_flags_build(tc_ctx *ctx, const std::vector<uint32_t> &dist)
         k3t_gather_kernel<<<nrb, 256, 0, st>>>(ctx->d_bu_keys, ctx->d_bu_count, reinterpret_cast<const unsigned long long *>(ctx->d_off),
                                               d_pref, nrb, k0, b0);
         TC_CUDA(cub::DeviceRadixSort::SortPairs(w8 + o_tmp, tmp_bytes, (const uint32_t *)k0, k1, (const uint32_t *)b0, b1, (int)m, 0, end_bit, st));
-        k3t_flag_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(k1, b1, m, ctx->d_tile_flags, words);
-        ctx->launches += 2 + (end_bit + 7) / 8;
+        // The flag kernel visits every pair of blocks of every posting list.  A rank held by most blocks (one species: every
+        // shared rank is in every block) makes that quadratic in the number of blocks; when the visits exceed what a pass over
+        // ALL tiles would cost anyway, every tile is flagged instead (a superset is always correct).
+        unsigned long long *d_work = reinterpret_cast<unsigned long long *>(w8 + o_pref) + (nrb + 1), h_work = 0;
+        TC_CUDA(cudaMemsetAsync(d_work, 0, 8, st));
+        k3t_work_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(k1, m, d_work);
+        TC_CUDA(cudaMemcpyAsync(&h_work, d_work, 8, cudaMemcpyDeviceToHost, st));
+        TC_CUDA(cudaStreamSynchronize(st));
+        const unsigned long long tiles = (unsigned long long)nrb * (nrb + 1) / 2;
+        if (h_work > std::max<unsigned long long>(64ull * tiles, 1ull << 28)) {
+            TC_CUDA(cudaMemsetAsync(ctx->d_tile_flags, 0xFF, fwords * 4, st));
+            if (getenv("TCLUST_TIMING")) fprintf(stderr, "[tclust timing] tile flags: %llu block-pair visits for %llu tiles: every tile flagged\n", h_work, tiles);
+        } else
+            k3t_flag_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(k1, b1, m, ctx->d_tile_flags, words);
+        ctx->launches += 3 + (end_bit + 7) / 8;
     }
     k3t_fixed_kernel<<<nrb, 128, 0, st>>>(ctx->d_bu_count, nrb, ctx->d_tile_flags, words);
     k3t_rowcount_kernel<<<(nrb * 32 + 255) / 256, 256, 0, st>>>(ctx->d_tile_flags, nrb, words, ctx->d_tile_rowcount);
