@@ -48,6 +48,10 @@ __device__ __forceinline__ unsigned long long k4_edge_key(const tc_pair &e, cons
     return ~(unsigned long long)__double_as_longlong(J);
 }
 
+struct K4Less {
+    __host__ __device__ bool operator()(const ulonglong2 &x, const ulonglong2 &y) const { return x.x < y.x || (x.x == y.x && x.y < y.y); }
+};
+
 struct K4Args {
     const tc_pair *edges; const unsigned long long *edge_counter; unsigned long long edge_cap;   // m = min(*counter, cap)
     const unsigned long long *fin_key, *fin_id; uint32_t nfin;    // extra edges given as (key, i<<32|j) (forest of an earlier batch)
@@ -59,7 +63,7 @@ struct K4Args {
     int rank, nranks;
     unsigned long long sys_base;      // epoch of the multi-GPU barrier at launch (flags only ever grow: no reset between launches)
     unsigned char *live;              // per chunk of K4_CHUNK candidate edges: 0 = every edge of it lies inside one component (for good)
-    unsigned long long *out_key, *out_id;      // forest, n entries each (preset to all ones)
+    ulonglong2 *out;                  // forest: (key, i<<32|j), n entries (preset to all ones)
     uint32_t *ctl;                    // [0] forest count, [1] grid barrier, [2..3] merged per round parity, [4] abort, [5] rounds, [6] some rank's edges overflowed
 };
 
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_boruvka_kernel(const K4Args a)
             if (redge[other] == id && (uint32_t)c < other) continue;
             a.parent[c] = other;
             const uint32_t slot = atomicAdd(&a.ctl[0], 1u);
-            if (slot < n) { a.out_key[slot] = rkey[c]; a.out_id[slot] = id; }
+            if (slot < n) a.out[slot] = make_ulonglong2(rkey[c], id);
             atomicAdd(&a.ctl[2 + par], 1u);
         }
         k4_grid_sync(a.ctl, epoch);
@@ -264,6 +268,12 @@ __global__ void __launch_bounds__(K4_THREADS) k4_boruvka_kernel(const K4Args a)
         for (unsigned long long v = gtid; v < n; v += gsize) a.comp[v] = (int32_t)a.parent[a.comp[v]];
         k4_grid_sync(a.ctl, epoch);
     }
+}
+
+__global__ void k4_split_kernel(const ulonglong2 *f, uint32_t nf, unsigned long long *key, unsigned long long *id)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nf) { const ulonglong2 v = f[i]; key[i] = v.x; id[i] = v.y; }
 }
 
 template <typename T>
@@ -337,11 +347,10 @@ int tc_k4_enqueue(tc_ctx *ctx, int mode, const unsigned long long *d_fin_key, co
         k.grid = ctx->num_sms * per_sm;
     }
     size_t tmp_bytes = 0;
-    TC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
-                                            (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)n, 0, 64, st));
+    ulonglong2 *forest = reinterpret_cast<ulonglong2 *>(k.d_out);
+    TC_CUDA(cub::DeviceMergeSort::SortKeys(nullptr, tmp_bytes, forest, (int)n, K4Less{}, st));
     if (k4_grow(&k.d_sort_tmp, &k.cap_sort_tmp, tmp_bytes + 256)) return 1;
-    unsigned long long *o_key = k.d_out, *o_id = k.d_out + n, *t_key = k.d_out + 2 * (size_t)n, *t_id = k.d_out + 3 * (size_t)n;
-    TC_CUDA(cudaMemsetAsync(k.d_out, 0xFF, (size_t)2 * n * 8, st));
+    TC_CUDA(cudaMemsetAsync(k.d_out, 0xFF, (size_t)n * 16, st));
     TC_CUDA(cudaMemsetAsync(k.d_ctl, 0, 16 * sizeof(uint32_t), st));
     K4Args a{};
     a.edges = ctx->d_edges; a.edge_counter = ctx->d_edge_count; a.edge_cap = ctx->edge_cap;
@@ -353,7 +362,7 @@ int tc_k4_enqueue(tc_ctx *ctx, int mode, const unsigned long long *d_fin_key, co
     if (a.nranks > 1) { for (int g = 0; g < a.nranks; g++) a.xbuf[g] = g == a.rank ? k.d_xbuf : k.peer_xbuf[g]; }
     else a.xbuf[0] = k.d_xbuf;
     a.red = k.d_red;
-    a.out_key = o_key; a.out_id = o_id; a.ctl = k.d_ctl;
+    a.out = forest; a.ctl = k.d_ctl;
     {   // liveness flags of the edge chunks (written in round 0 before they are read)
         const uint64_t chunks = (ctx->edge_cap + K4_CHUNK - 1) / K4_CHUNK + 1;
         if (k4_grow(&k.d_live, &k.cap_live, chunks)) return 1;
@@ -373,15 +382,10 @@ int tc_k4_enqueue(tc_ctx *ctx, int mode, const unsigned long long *d_fin_key, co
     TC_CUDA(cudaLaunchCooperativeKernel((const void *)k4_boruvka_kernel, dim3(k.grid), dim3(K4_THREADS), params, 0, st));
     TC_CUDA(cudaEventRecord(k.ev[1], st));
     ctx->launches++;
-    // forest sorted by (key, i, j): stable sort by id, then by key; the unused tail (all ones) stays at the end
-    // (ids are (i << 32 | j) with i, j < n; the all-ones padding also sorts last on the low id_bits bits alone only if those
-    //  bits are all ones there too, which they are)
-    int id_bits = 33;
-    while (id_bits < 64 && ((unsigned long long)n >> (id_bits - 32))) id_bits++;
+    // forest sorted by (key, i, j) in one merge sort of the 16-byte entries (round 2, first version: two radix sorts of the
+    // split arrays, 15 passes of ~13 us each for 10^5 entries); the unused tail (all ones) stays at the end
     size_t tb = tmp_bytes;
-    TC_CUDA(cub::DeviceRadixSort::SortPairs(k.d_sort_tmp, tb, (const unsigned long long *)o_id, t_id, (const unsigned long long *)o_key, t_key, (int)n, 0, id_bits, st));
-    tb = tmp_bytes;
-    TC_CUDA(cub::DeviceRadixSort::SortPairs(k.d_sort_tmp, tb, (const unsigned long long *)t_key, o_key, (const unsigned long long *)t_id, o_id, (int)n, 0, 64, st));
+    TC_CUDA(cub::DeviceMergeSort::SortKeys(k.d_sort_tmp, tb, forest, (int)n, K4Less{}, st));
     TC_CUDA(cudaEventRecord(k.ev[2], st));
     ctx->launches += 2;
     return 0;
@@ -400,10 +404,10 @@ int tc_k4_collect(tc_ctx *ctx, int mode, int kmer_size, std::vector<tc_edge> &ms
     uint8_t *h = static_cast<uint8_t *>(k.h_out);
     uint32_t *h_ctl = reinterpret_cast<uint32_t *>(h);
     unsigned long long *h_cnt = reinterpret_cast<unsigned long long *>(h + 64 - 16);
-    unsigned long long *h_key = reinterpret_cast<unsigned long long *>(h + 64), *h_id = h_key + n;
+    const ulonglong2 *h_f = reinterpret_cast<const ulonglong2 *>(h + 64);
     TC_CUDA(cudaMemcpyAsync(h_ctl, k.d_ctl, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     TC_CUDA(cudaMemcpyAsync(h_cnt, ctx->d_edge_count, 16, cudaMemcpyDeviceToHost, st));
-    TC_CUDA(cudaMemcpyAsync(h_key, k.d_out, (size_t)2 * n * 8, cudaMemcpyDeviceToHost, st));     // keys and ids are adjacent
+    TC_CUDA(cudaMemcpyAsync(h + 64, k.d_out, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
     if (comp_out) {
         comp_out->resize(n);
         TC_CUDA(cudaMemcpyAsync(comp_out->data(), ctx->d_comp, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -426,8 +430,8 @@ int tc_k4_collect(tc_ctx *ctx, int mode, int kmer_size, std::vector<tc_edge> &ms
     uint32_t run0 = 0;                 // first edge of the current run of equal distances
     bool mixed = false, monotone = true;
     for (uint32_t e = 0; e < nf; e++) {
-        if (e == 0 || h_key[e] != h_key[e - 1]) {
-            d = tc_dist_from_key(h_key[e], mode, kmer_size);
+        if (e == 0 || h_f[e].x != h_f[e - 1].x) {
+            d = tc_dist_from_key(h_f[e].x, mode, kmer_size);
             if (e > 0 && d == prev_d) mixed = true;
             else {
                 if (mixed) std::sort(mst.begin() + run0, mst.begin() + e, by_weight);
@@ -436,7 +440,7 @@ int tc_k4_collect(tc_ctx *ctx, int mode, int kmer_size, std::vector<tc_edge> &ms
             }
             prev_d = d;
         }
-        mst[e] = tc_edge{(int32_t)(h_id[e] >> 32), (int32_t)(h_id[e] & 0xFFFFFFFFull), d};
+        mst[e] = tc_edge{(int32_t)(h_f[e].y >> 32), (int32_t)(h_f[e].y & 0xFFFFFFFFull), d};
     }
     if (mixed) std::sort(mst.begin() + run0, mst.end(), by_weight);
     if (!monotone) std::sort(mst.begin(), mst.end(), by_weight);   // distances not monotone in the key (never for the valid modes)
@@ -459,8 +463,8 @@ int tc_k4_fold(tc_ctx *ctx, uint32_t *nfin)
     const uint32_t nf = std::min(h_ctl[0], n);
     if (k4_grow(&k.d_fin, &k.cap_fin, (uint64_t)2 * n)) return 1;
     if (nf) {
-        TC_CUDA(cudaMemcpyAsync(k.d_fin, k.d_out, (size_t)nf * 8, cudaMemcpyDeviceToDevice, st));
-        TC_CUDA(cudaMemcpyAsync(k.d_fin + n, k.d_out + n, (size_t)nf * 8, cudaMemcpyDeviceToDevice, st));
+        k4_split_kernel<<<(nf + 255) / 256, 256, 0, st>>>(reinterpret_cast<const ulonglong2 *>(k.d_out), nf, k.d_fin, k.d_fin + n);
+        TC_CUDA(cudaGetLastError());
     }
     TC_CUDA(cudaMemsetAsync(ctx->d_edge_count, 0, 2 * sizeof(unsigned long long), st));
     *nfin = nf;
