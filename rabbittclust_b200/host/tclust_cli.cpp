@@ -46,6 +46,7 @@
 #include <memory>
 #include <functional>
 #include <condition_variable>
+#include <deque>
 #include <thread>
 #include <vector>
 #include <atomic>
@@ -411,13 +412,17 @@ struct Feeder {
         // one allocation per buffer: the whole input if it fits a batch, else a full batch (+ the largest overshoot)
         const uint64_t first = std::min<uint64_t>(expect_bytes + (1u << 20), batch_bytes + (batch_bytes >> 3));
         batch[0].seq.reserve(first);
-        if (expect_bytes > batch_bytes) batch[1].seq.reserve(first);
+        // the second buffer is page-locked in the background while the first one fills
+        if (expect_bytes > batch_bytes) second = std::thread([this, first]() { batch[1].seq.reserve(first); });
     }
+    ~Feeder() { if (second.joinable()) second.join(); }
+    std::thread second;
     Batch &fill() { return batch[cur]; }
     void wait() { if (running) { worker.join(); running = false; } }
     void submit()                      // hand the filled batch to the GPU, continue in the other one
     {
         wait();                        // results are appended in submission order
+        if (second.joinable()) second.join();
         if (!ctx && late_ctx) ctx = late_ctx();
         Batch *b = &batch[cur];
         worker = std::thread([this, b]() { flush_batch(ctx, o, *b, out); });
@@ -478,14 +483,62 @@ void sketch_files(const std::function<tc_ctx *()> &get_ctx, const Options &o, ve
     };
     vector<std::thread> pool;
     for (int t = 0; t < std::max(1, std::min<int>(o.threads, (int)nfiles)); t++) pool.emplace_back(worker);
+    // The consumer only assigns offsets in the batch; a few copy threads move the parsed bytes there (one thread copies
+    // into fresh page-locked memory at ~3 GB/s, which was the feeder's limit on inputs of several GB).  All copies of a
+    // batch are drained before the batch is submitted or its buffer grows.
+    struct CopyTask { uint8_t *dst; vector<uint8_t> src; };
+    std::deque<CopyTask> copy_q;
+    std::mutex cmu;
+    std::condition_variable cv_copy, cv_drained;
+    size_t copies_pending = 0;
+    bool copy_stop = false;
+    auto copier = [&]() {
+        for (;;) {
+            CopyTask t;
+            {
+                std::unique_lock<std::mutex> lk(cmu);
+                cv_copy.wait(lk, [&]() { return copy_stop || !copy_q.empty(); });
+                if (copy_q.empty()) return;
+                t = std::move(copy_q.front());
+                copy_q.pop_front();
+            }
+            memcpy(t.dst, t.src.data(), t.src.size());
+            vector<uint8_t>().swap(t.src);
+            { std::lock_guard<std::mutex> lk(cmu); copies_pending--; }
+            cv_drained.notify_all();
+        }
+    };
+    auto drain_copies = [&]() { std::unique_lock<std::mutex> lk(cmu); cv_drained.wait(lk, [&]() { return copies_pending == 0; }); };
+    vector<std::thread> copiers;
+    const int n_copiers = g_input_bytes > ((uint64_t)256 << 20) ? std::max(1, std::min(6, o.threads / 2)) : 0;
+    for (int t = 0; t < n_copiers; t++) copiers.emplace_back(copier);
     std::unique_ptr<Feeder> feeder_p;
+    const bool feeder_dry = getenv("TCLUST_FEEDER_DRY") != nullptr;
+    const double t_feed0 = now_s();
+    uint64_t dry_bytes = 0;
+    double t_wait_parse = 0, t_wait_gpu = 0;
     for (size_t i = 0; i < nfiles; i++) {
         {
+            const double tw = now_s();
             std::unique_lock<std::mutex> lk(mu);
             cv_ready.wait(lk, [&]() { return parsed[i].ready; });
+            t_wait_parse += now_s() - tw;
         }
         Parsed &p = parsed[i];
         if (!p.ok) { fprintf(stderr, "cannot open the genome file: %s\n", files[i].c_str()); exit(1); }
+        if (feeder_dry) {                                               // producer rate alone (tools/feeder_check.py --dry)
+            dry_bytes += p.seq.size();
+            vector<uint8_t>().swap(p.seq); vector<Record>().swap(p.recs);
+            { std::lock_guard<std::mutex> lk(mu); consumed = i + 1; }
+            cv_room.notify_all();
+            if (i + 1 == nfiles) {
+                cerr << "[tclust timing] feeder dry run: " << dry_bytes / 1e9 << " Gbp parsed in " << (now_s() - t_feed0) << " s with "
+                     << pool.size() << " threads" << endl;
+                for (std::thread &t : pool) t.join();
+                exit(0);
+            }
+            continue;
+        }
         uint64_t total_len = 0;
         for (const Record &r : p.recs) total_len += r.end - r.begin;
         if (total_len >= o.min_len) {                                  // SketchInfo.cpp:963
@@ -511,21 +564,39 @@ void sketch_files(const std::function<tc_ctx *()> &get_ctx, const Options &o, ve
             Batch &b = feeder.fill();
             const uint32_t gi = (uint32_t)b.genomes.size();
             const uint64_t base = b.seq.size();
-            b.seq.append(p.seq.data(), p.seq.size());
+            if (n_copiers && p.seq.size() >= ((size_t)256 << 10)) {
+                if (b.seq.len + p.seq.size() + 64 > b.seq.cap) { drain_copies(); b.seq.reserve(b.seq.len + p.seq.size() + 64); }
+                CopyTask t{b.seq.p + b.seq.len, std::move(p.seq)};
+                b.seq.len += t.src.size();
+                { std::lock_guard<std::mutex> lk(cmu); copy_q.push_back(std::move(t)); copies_pending++; }
+                cv_copy.notify_one();
+            } else {
+                if (b.seq.len + p.seq.size() + 64 > b.seq.cap) drain_copies();
+                b.seq.append(p.seq.data(), p.seq.size());
+            }
             for (const Record &r : p.recs) { b.rec_off.push_back(base + r.end); b.rec2genome.push_back(gi); }
             b.ssize.push_back(o.containment ? (uint32_t)std::max(p.file_len / o.compress, 100) : (uint32_t)o.sketch_size);
             b.longest = std::max<uint64_t>(b.longest, total_len);
             b.genomes.push_back(std::move(g));
-            if (b.seq.size() >= batch_bytes) feeder.submit();
+            if (b.seq.size() >= batch_bytes) { const double tw = now_s(); drain_copies(); feeder.submit(); t_wait_gpu += now_s() - tw; }
         }
         vector<uint8_t>().swap(p.seq); vector<Record>().swap(p.recs);
         { std::lock_guard<std::mutex> lk(mu); consumed = i + 1; }
         cv_room.notify_all();
     }
     for (std::thread &t : pool) t.join();
+    drain_copies();
+    { std::lock_guard<std::mutex> lk(cmu); copy_stop = true; }
+    cv_copy.notify_all();
+    for (std::thread &t : copiers) t.join();
     if (!feeder_p) { get_ctx(); return; }
     Feeder &feeder = *feeder_p;
+    const double t_fin = now_s();
     feeder.finish();
+    if (getenv("TCLUST_TIMING"))
+        cerr << "[tclust timing] feeder: " << (now_s() - t_feed0) * 1e3 << " ms in all; the consumer waited " << t_wait_parse * 1e3
+             << " ms for parsed files, " << t_wait_gpu * 1e3 << " ms for copies and the previous batch on the GPU, "
+             << (now_s() - t_fin) * 1e3 << " ms for the last batch" << endl;
     for (size_t i = 0; i < out.size(); i++) out[i].id = (int)i;
 }
 
@@ -1224,6 +1295,10 @@ int main(int argc, char **argv)
 {
     Options o;
     if (o.threads < 1) o.threads = 1;
+    // The host packer of the 2-bit transport (tc_sketch_* packs on spare cores when there are >= 12 per GPU) would take its
+    // cores from the file parsers here, and one GPU's PCIe link (~40 GB/s) is never what limits this feeder (~9 GB/s):
+    // measured 3.7 s packed vs 1.7 s plain on 6 Gbp.  The library default still applies to callers with resident buffers.
+    setenv("TCLUST_SKETCH_PACK", "0", 0);
     for (int a = 1; a < argc; a++) {
         string f = argv[a];
         auto need = [&](const char *what) -> const char * { if (a + 1 >= argc) die(string("option ") + what + " needs a value"); return argv[++a]; };
