@@ -325,6 +325,17 @@ int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, double thresh
  * per-pair common_min, the representative with the largest Jaccard wins, ties -> first in `touched` order. */
 int tc_greedy_cluster_kssd(tc_ctx *ctx, int kmer_size, double threshold, int32_t *rep_of, uint32_t *n_clusters);
 
+/* KssdIncrementalCluster (src/greedy.cpp:1736-1880; caller: append_clust_greedy_fast, src/sub_command.cpp:192-276): the
+ * uploaded sketches [0, start_index) are already clustered and rep_ids[0..n_reps) are their representatives in creation
+ * order (KssdClusterState::representative_ids); every sketch q >= start_index, in order, joins the representative with the
+ * smallest Mash distance <= threshold among those passing the two-sided size-ratio filter (2*exp(d*k)-1) and the
+ * floor()ed common-hash filter, or becomes the next representative.  rep_of has n entries; only [start_index, n) are
+ * written: the sketch id of the chosen representative, or q itself.  *n_clusters = representatives afterwards.
+ * Equal distances: the reference takes whichever candidate its phmap::flat_hash_map<int,int> yields first (depends
+ * on the table's heap address, not reproducible); this call takes the earliest-created representative. */
+int tc_greedy_incremental_kssd(tc_ctx *ctx, int kmer_size, double threshold, uint32_t start_index, const uint32_t *rep_ids,
+                               uint32_t n_reps, int32_t *rep_of, uint32_t *n_clusters);
+
 /* The same two rules with the representative scan sharded over several GPUs (the outer loop over the
  * genomes is serial, the scan of one batch against the representatives is not): ctxs[0..nctx) are contexts, one per
  * device, that all hold the SAME uploaded sketch set; representative number c is kept by context c mod nctx, every

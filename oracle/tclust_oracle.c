@@ -453,6 +453,52 @@ int oc_greedy_inverted(const uint64_t *hashes, const uint64_t *off, int N, int k
     return nrep;
 }
 
+/* KssdIncrementalCluster (greedy.cpp:1736-1880) with one thread: sketches [0, start) are clustered, seed[0..n_seed) are
+ * their representatives in creation order; sketch q >= start joins the representative of smallest distance or becomes
+ * the next one.  The reference walks its candidates in the iteration order of a phmap::flat_hash_map<int,int> (it
+ * depends on the table's heap address), so among EQUAL distances its choice is not reproducible; here, as in the
+ * product, the earliest-created representative wins.  rep_of[q] is written for q >= start only.  Returns #reps. */
+int oc_greedy_incremental_kssd(const uint64_t *hashes, const uint64_t *off, int N, int k, double threshold,
+                               int start, const int32_t *seed, int n_seed, int32_t *rep_of)
+{
+    int *reps = (int *)malloc(sizeof(int) * (size_t)(N > 0 ? N : 1)), nrep = 0;
+    for (int r = 0; r < n_seed; r++) reps[nrep++] = seed[r];
+    const double radio = 2.0 * exp(threshold * k) - 1.0;              /* calculateMaxSizeRatio, greedy.cpp:162-173 */
+    const double x = exp(-threshold * k);                             /* greedy.cpp:1751-1752 */
+    const double jaccard_min = x / (2.0 - x);
+    for (int q = start; q < N; q++) {
+        const uint64_t *hq = hashes + off[q];
+        const int sizeQry = (int)(off[q + 1] - off[q]);
+        double best_dist = 1.7976931348623157e308;
+        int best = -1;
+        for (int r = 0; r < nrep; r++) {
+            const int id = reps[r];
+            const int sizeRef = (int)(off[id + 1] - off[id]);
+            uint32_t fh;
+            const int common = (int)oc_intersect_u64(hq, sizeQry, hashes + off[id], sizeRef, &fh);
+            if (common == 0) continue;                                /* only representatives met in the index are candidates */
+            const double ratio = (double)sizeQry / sizeRef;           /* :1818-1821 */
+            if (ratio > radio || ratio < 1.0 / radio) continue;
+            const int min_common_needed = (int)(jaccard_min * (sizeQry + sizeRef) / (1.0 + jaccard_min));   /* :1825 */
+            if (common < min_common_needed) continue;
+            /* calculate_mash_distance, greedy.cpp:72-119 */
+            const uint64_t uni = (uint64_t)sizeRef + sizeQry - common;
+            const double jaccard_ = uni == 0 ? 0.0 : (double)common / uni;
+            double dist;
+            if (jaccard_ == 1.0) dist = 0.0;
+            else {
+                dist = -log(2 * jaccard_ / (1.0 + jaccard_)) / (double)k;
+                if (dist > 1.0) dist = 1.0;
+            }
+            if (dist <= threshold && dist < best_dist) { best_dist = dist; best = r; }   /* :1840-1848 */
+        }
+        if (best != -1) rep_of[q] = reps[best];
+        else { reps[nrep++] = q; rep_of[q] = q; }
+    }
+    free(reps);
+    return nrep;
+}
+
 /* ------------------------------------------------- semantic B brute-force callers */
 /* MinHash::jaccard as integers: common among the first sketch_size union elements and the
  * completed denominator (MinHash.cpp:982-1101, scalar form :1199-1229). */

@@ -87,6 +87,12 @@ int oc_clusters_from_mst(const oc_edge *mst, size_t n_edges, int N, double thres
 int oc_greedy_inverted(const uint64_t *hashes, const uint64_t *off, int N, int k,
                        int containment, double threshold, int32_t *rep_of);
 
+/* KssdIncrementalCluster with -t 1 (greedy.cpp:1736-1880): sketches [0,start) clustered with representatives
+ * seed[0..n_seed) (creation order); rep_of[q], q >= start: chosen representative or q.  Ties -> earliest created
+ * (the reference's tie order is a hash-map iteration order). Returns #representatives. */
+int oc_greedy_incremental_kssd(const uint64_t *hashes, const uint64_t *off, int N, int k, double threshold,
+                               int start, const int32_t *seed, int n_seed, int32_t *rep_of);
+
 /* ---- semantic B (the brute-force fallbacks) ---------------------------------------- */
 /* integer form of MinHash::jaccard (MinHash.cpp:982-1101): common among the first
  * sketch_size union elements; *denom_out = completed/capped denominator. */

@@ -193,8 +193,17 @@ extern "C" int tc_greedy_scan(tc_ctx *ctx, uint32_t q0, uint32_t q1, const uint3
 // context c mod G), every context scans the batch against its share on its own host thread, the candidate lists are
 // concatenated and the serial replay below runs unchanged -- it depends only on the union of the candidates, so the
 // result is the single-GPU (= one-thread reference) result whatever G.
+//
+// incr = true  : KssdIncrementalCluster (greedy.cpp:1736-1880): the sketches [0, incr_start) are already clustered, their
+//                representatives are seed[0..n_seed) in creation order; each later sketch joins the nearest
+//                representative (two-sided size-ratio filter, floor()ed common filter, Mash distance <= threshold,
+//                strictly smaller distance wins) or founds a cluster.  The reference walks its candidates in the
+//                iteration order of a phmap::flat_hash_map<int,int>, which depends on the table's heap address, so
+//                its choice among EQUAL distances is not reproducible even by itself; here the earliest-created
+//                representative wins a tie.
 static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment, double threshold, bool brute, uint32_t semb_size,
-                       int32_t *rep_of, uint32_t *n_clusters, bool kssd = false)
+                       int32_t *rep_of, uint32_t *n_clusters, bool kssd = false, bool incr = false, uint32_t incr_start = 0,
+                       const uint32_t *seed = nullptr, uint32_t n_seed = 0)
 {
     tc_ctx *ctx = cs[0];
     TC_CUDA(cudaSetDevice(ctx->device));
@@ -212,6 +221,7 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
     const int cmin_fixed = all_fixed ? tc_greedy_common_min(threshold, kmer_size, fixed_size, fixed_size, 0) : -1;
     const double x = std::exp(-threshold * kmer_size);
     const double jmin = x / (2.0 - x);
+    const double max_ratio = 2.0 * std::exp(threshold * kmer_size) - 1.0;        // calculateMaxSizeRatio, greedy.cpp:162-173
 
     uint64_t cap = 1ull << 24;
     if (const char *s = getenv("TCLUST_CAND_CAP")) cap = std::max<uint64_t>(strtoull(s, nullptr, 10), 1024);
@@ -269,8 +279,34 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
     std::vector<tc_cand> sorted;
     std::vector<uint32_t> new_reps;
     uint32_t nrep_total = 0;
+    // creation number c of a representative lives on context c mod G
+    auto append_reps = [&](const std::vector<uint32_t> &reps) -> int {
+        if (G == 1) return tc_rep_table_append(ctx, reps.data(), (uint32_t)reps.size());
+        std::vector<std::vector<uint32_t>> share(G);
+        for (uint32_t q : reps) share[(uint32_t)order_of[q] % (uint32_t)G].push_back(q);
+        std::vector<std::thread> th;
+        for (int r = 0; r < G; r++)
+            th.emplace_back([&, r]() {
+                if (share[r].empty()) return;
+                if (cudaSetDevice(cs[r]->device) != cudaSuccess || tc_rep_table_append(cs[r], share[r].data(), (uint32_t)share[r].size()))
+                    part_err[r] = std::string("representative table: ") + tc_last_error();
+            });
+        for (std::thread &t : th) t.join();
+        for (int r = 0; r < G; r++) TC_CHECK(part_err[r].empty(), "tc_greedy_cluster: GPU %d: %s", cs[r]->device, part_err[r].c_str());
+        return 0;
+    };
+    if (incr) {
+        TC_CHECK(incr_start <= n && n_seed <= incr_start && (seed || !n_seed), "tc_greedy_incremental_kssd: bad representative list");
+        for (uint32_t c = 0; c < n_seed; c++) {
+            TC_CHECK(seed[c] < incr_start && order_of[seed[c]] < 0, "tc_greedy_incremental_kssd: representative %u (sketch %u) is out of "
+                     "range or listed twice", c, seed[c]);
+            order_of[seed[c]] = (int32_t)c;
+        }
+        nrep_total = n_seed;
+        if (append_reps(std::vector<uint32_t>(seed, seed + n_seed))) return 1;
+    }
 
-    for (uint32_t b0 = 0; b0 < n;) {
+    for (uint32_t b0 = incr ? incr_start : 0; b0 < n;) {
         const uint32_t b1 = std::min<uint64_t>(n, (uint64_t)b0 + batch);
         if (G == 1) scan_part(0, b0, b1);
         else {
@@ -313,7 +349,7 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
             // representative creation order)  -- greedy.cpp:1148-1164
             tc_cand *end = std::remove_if(lo, hi, [&](const tc_cand &c) { return order_of[c.rep] < 0; });
             std::sort(lo, end, [&](const tc_cand &a, const tc_cand &b) {
-                if (!brute && a.first_hit != b.first_hit) return a.first_hit < b.first_hit;
+                if (!brute && !incr && a.first_hit != b.first_hit) return a.first_hit < b.first_hit;
                 return order_of[a.rep] < order_of[b.rep];
             });
             const int size_ref = (int)ctx->h_size[q];
@@ -324,6 +360,16 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
                 if (brute) {   // greedy.cpp:297-334: dist <= threshold, smallest distance, first inserted wins
                     const double dist = containment ? tc_contain_distance(common, size_qry, size_ref, kmer_size)
                                                     : tc_distance_b(common, size_qry, size_ref, (int)semb_size, kmer_size);
+                    if (dist <= threshold && dist < best_dist) { best_dist = dist; best_rep = (int)c->rep; }
+                    continue;
+                }
+                if (incr) {   // greedy.cpp:1812-1846; sizeQry = the new sketch, sizeRef = the representative
+                    const int sizeQry = size_ref, sizeRef = size_qry;
+                    const double ratio = (double)sizeQry / sizeRef;
+                    if (ratio > max_ratio || ratio < 1.0 / max_ratio) continue;
+                    const int min_common_needed = (int)(jmin * (sizeQry + sizeRef) / (1.0 + jmin));
+                    if (common < min_common_needed) continue;
+                    const double dist = tc_greedy_dist(common, sizeRef, sizeQry, 0, kmer_size);   // calculate_mash_distance, :103-160
                     if (dist <= threshold && dist < best_dist) { best_dist = dist; best_rep = (int)c->rep; }
                     continue;
                 }
@@ -351,21 +397,8 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
                 new_reps.push_back(q);
             }
         }
-        // the new representatives join the tables: creation number c goes to context c mod G
-        if (G == 1) { if (tc_rep_table_append(ctx, new_reps.data(), (uint32_t)new_reps.size())) return 1; }
-        else {
-            std::vector<std::vector<uint32_t>> share(G);
-            for (uint32_t q : new_reps) share[(uint32_t)order_of[q] % (uint32_t)G].push_back(q);
-            std::vector<std::thread> th;
-            for (int r = 0; r < G; r++)
-                th.emplace_back([&, r]() {
-                    if (share[r].empty()) return;
-                    if (cudaSetDevice(cs[r]->device) != cudaSuccess || tc_rep_table_append(cs[r], share[r].data(), (uint32_t)share[r].size()))
-                        part_err[r] = std::string("representative table: ") + tc_last_error();
-                });
-            for (std::thread &t : th) t.join();
-            for (int r = 0; r < G; r++) TC_CHECK(part_err[r].empty(), "tc_greedy_cluster: GPU %d: %s", cs[r]->device, part_err[r].c_str());
-        }
+        // the new representatives join the tables
+        if (append_reps(new_reps)) return 1;
         b0 = b1;
     }
     cudaSetDevice(ctx->device);
@@ -382,6 +415,13 @@ extern "C" int tc_greedy_cluster(tc_ctx *ctx, int kmer_size, int containment, do
 extern "C" int tc_greedy_cluster_kssd(tc_ctx *ctx, int kmer_size, double threshold, int32_t *rep_of, uint32_t *n_clusters)
 {
     return greedy_impl(&ctx, 1, kmer_size, 0, threshold, false, 0, rep_of, n_clusters, true);
+}
+
+extern "C" int tc_greedy_incremental_kssd(tc_ctx *ctx, int kmer_size, double threshold, uint32_t start_index, const uint32_t *rep_ids,
+                                          uint32_t n_reps, int32_t *rep_of, uint32_t *n_clusters)
+{
+    TC_CHECK(rep_of, "tc_greedy_incremental_kssd: rep_of is null");
+    return greedy_impl(&ctx, 1, kmer_size, 0, threshold, false, 0, rep_of, n_clusters, true, true, start_index, rep_ids, n_reps);
 }
 
 extern "C" int tc_greedy_cluster_multi(tc_ctx *const *ctxs, int nctx, int kmer_size, int containment, double threshold, int kssd,

@@ -76,7 +76,7 @@ struct Options {
     int threads = (int)std::thread::hardware_concurrency();
     bool by_file = false, containment = false, jaccard = false, set_kmer = false, no_save = false, fast = false;
     bool has_output = false, has_input = false, presketched = false, premsted = false, has_threshold = false;
-    bool append = false;
+    bool append = false, save_rep = false;
     bool dense = false, newick = false, phylip = false, nexus = false, linkage = false;
     double threshold = 0.05;
     int kmer = 19, sketch_size = 1000, compress = 1000, drlevel = 3, device = 0;
@@ -1080,6 +1080,224 @@ string newick_of(const vector<Genome> &g, const vector<tc_edge> &mst, bool by_fi
     }
 }
 
+#ifdef GREEDY_CLUST
+// ------------------------------------------------------------------ clust-greedy --fast --append (cluster state)
+// KssdClusterState (src/greedy.h:47-72) and its file cluster_state.bin (KssdClusterState::save / load,
+// src/greedy.cpp:1545-1734): threshold, kmer_size, half_k, half_subk, drlevel, genomeNumber; representative ids; every
+// sketch {int id, u64 totalSeqLength, bool use64, u32 sketchsize, size_t n32, size_t n64, hashes, size_t nameLen, fileName};
+// the clusters; "KSSI02\0\0" + the hash -> representative-number index.  The reference writes the index in the iteration
+// order of its hash map (it differs from run to run); this writer emits ascending hashes, the reader builds a map either way.
+struct KssdState {
+    double threshold = 0.0; int kmer_size = 0; KssdParams params;
+    vector<int> rep_ids; vector<Genome> all; vector<vector<int>> clusters;
+};
+
+bool save_kssd_state(const KssdState &s, const string &path)
+{
+    FILE *fp = fopen(path.c_str(), "wb");
+    if (!fp) { cerr << "ERROR: Cannot open file for writing: " << path << endl; return false; }
+    const bool use64 = kssd_use64(s.params);
+    wr(fp, s.threshold); wr(fp, s.kmer_size);
+    wr(fp, s.params.half_k); wr(fp, s.params.half_subk); wr(fp, s.params.drlevel); wr(fp, s.params.genome_number);
+    wr(fp, (size_t)s.rep_ids.size());
+    fwrite(s.rep_ids.data(), sizeof(int), s.rep_ids.size(), fp);
+    wr(fp, (size_t)s.all.size());
+    vector<uint32_t> tmp;
+    for (const Genome &x : s.all) {
+        wr(fp, x.id); wr(fp, (uint64_t)x.total_len); wr(fp, use64); wr(fp, (uint32_t)x.hashes.size());
+        wr(fp, use64 ? (size_t)0 : (size_t)x.hashes.size());
+        wr(fp, use64 ? (size_t)x.hashes.size() : (size_t)0);
+        if (use64) fwrite(x.hashes.data(), 8, x.hashes.size(), fp);
+        else { tmp.assign(x.hashes.begin(), x.hashes.end()); fwrite(tmp.data(), 4, tmp.size(), fp); }
+        wr(fp, (size_t)x.file_name.size());
+        fwrite(x.file_name.data(), 1, x.file_name.size(), fp);
+    }
+    wr(fp, (size_t)s.clusters.size());
+    for (const vector<int> &c : s.clusters) { wr(fp, (size_t)c.size()); fwrite(c.data(), sizeof(int), c.size(), fp); }
+    vector<std::pair<uint64_t, int>> post;
+    for (size_t r = 0; r < s.rep_ids.size(); r++) for (uint64_t h : s.all[s.rep_ids[r]].hashes) post.emplace_back(h, (int)r);
+    std::sort(post.begin(), post.end());
+    size_t distinct = 0;
+    for (size_t a = 0; a < post.size(); a++) distinct += a == 0 || post[a].first != post[a - 1].first;
+    const char magic[8] = {'K', 'S', 'S', 'I', '0', '2', '\0', '\0'};
+    fwrite(magic, 1, 8, fp);
+    wr(fp, distinct);
+    cerr << "Saving inverted index: " << distinct << " unique hashes..." << endl;
+    for (size_t a = 0; a < post.size();) {
+        size_t b = a;
+        while (b < post.size() && post[b].first == post[a].first) b++;
+        wr(fp, post[a].first); wr(fp, (size_t)(b - a));
+        for (size_t e = a; e < b; e++) wr(fp, post[e].second);
+        a = b;
+    }
+    const bool ok = !ferror(fp);
+    fclose(fp);
+    cerr << "Saved clustering state to: " << path << endl;
+    cerr << "  - " << s.all.size() << " genomes" << endl;
+    cerr << "  - " << s.rep_ids.size() << " clusters (representatives)" << endl;
+    cerr << "  - " << distinct << " unique hashes in inverted index" << endl;
+    return ok;
+}
+
+bool load_kssd_state(KssdState &s, const string &path)
+{
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (!fp) { cerr << "ERROR: Cannot open file for reading: " << path << endl; return false; }
+    auto bad = [&]() { fclose(fp); cerr << "ERROR: " << path << " is truncated or not a KSSD cluster state" << endl; return false; };
+    if (!rd(fp, s.threshold) || !rd(fp, s.kmer_size) || !rd(fp, s.params.half_k) || !rd(fp, s.params.half_subk) ||
+        !rd(fp, s.params.drlevel) || !rd(fp, s.params.genome_number)) return bad();
+    s.params.id = (s.params.half_k << 8) + (s.params.half_subk << 4) + s.params.drlevel;
+    size_t nrep = 0, nsk = 0, ncl = 0;
+    if (!rd(fp, nrep) || nrep > ((size_t)1 << 31)) return bad();
+    s.rep_ids.resize(nrep);
+    if (nrep && fread(s.rep_ids.data(), sizeof(int), nrep, fp) != nrep) return bad();
+    if (!rd(fp, nsk) || nsk > ((size_t)1 << 31)) return bad();
+    s.all.assign(nsk, Genome());
+    vector<uint32_t> tmp;
+    for (Genome &x : s.all) {
+        bool use64 = false; uint32_t sketchsize = 0; uint64_t len = 0; size_t n32 = 0, n64 = 0, nl = 0;
+        if (!rd(fp, x.id) || !rd(fp, len) || !rd(fp, use64) || !rd(fp, sketchsize) || !rd(fp, n32) || !rd(fp, n64)) return bad();
+        if (n32 > ((size_t)1 << 32) || n64 > ((size_t)1 << 32) || (n32 && n64)) return bad();
+        x.total_len = len;
+        if (n32) {
+            tmp.resize(n32);
+            if (fread(tmp.data(), 4, n32, fp) != n32) return bad();
+            x.hashes.assign(tmp.begin(), tmp.end());
+        }
+        if (n64) { x.hashes.resize(n64); if (fread(x.hashes.data(), 8, n64, fp) != n64) return bad(); }
+        if (!std::is_sorted(x.hashes.begin(), x.hashes.end())) std::sort(x.hashes.begin(), x.hashes.end());
+        if (!rd(fp, nl) || nl > ((size_t)1 << 20)) return bad();
+        x.file_name.resize(nl);
+        if (nl && fread(&x.file_name[0], 1, nl, fp) != nl) return bad();
+        x.name = "N/A"; x.comment = "N/A";           // the state keeps no record names: printKssdResult prints N/A (MST_IO.cpp:99-104)
+    }
+    for (int r : s.rep_ids) if (r < 0 || (size_t)r >= nsk) return bad();
+    if (!rd(fp, ncl) || ncl > nsk) return bad();
+    s.clusters.assign(ncl, vector<int>());
+    for (vector<int> &c : s.clusters) {
+        size_t m = 0;
+        if (!rd(fp, m) || m > nsk) return bad();
+        c.resize(m);
+        if (m && fread(c.data(), sizeof(int), m, fp) != m) return bad();
+    }
+    // the hash -> representative index that follows is rebuilt on the device from the representatives' sketches
+    fclose(fp);
+    if (ncl != nrep) { cerr << "ERROR: " << path << " holds " << ncl << " clusters for " << nrep << " representatives" << endl; return false; }
+    cerr << "Loaded clustering state from: " << path << endl;
+    cerr << "  - " << nsk << " genomes" << endl;
+    cerr << "  - " << nrep << " clusters (representatives)" << endl;
+    return true;
+}
+
+// append_clust_greedy_fast (src/sub_command.cpp:192-276)
+int append_greedy_fast(tc_ctx *ctx, Options &o)
+{
+    const string state_file = o.folder + "/cluster_state.bin";
+    const bool save = !o.no_save;
+    KssdState st;
+    struct stat sb;
+    bool has_state = stat(state_file.c_str(), &sb) == 0;
+    if (has_state) {
+        cerr << "===== Incremental Update Mode (KSSD) =====" << endl;
+        cerr << "Found existing cluster state, loading..." << endl;
+        has_state = load_kssd_state(st, state_file);
+    }
+    auto sketch_new = [&](vector<Genome> &add, const KssdParams &want) {
+        if (!o.by_file && (o.kmer & 1))
+            die("--fast on a single multi-FASTA needs an even k-mer size in this build (SURVEY.md 8a-9)");
+        double t0 = now_s();
+        if (o.by_file) sketch_files([&]() { return ctx; }, o, add); else sketch_sequences(ctx, o, add);
+        if (g_kssd.half_k != want.half_k || g_kssd.half_subk != want.half_subk || g_kssd.drlevel != want.drlevel)
+            die("append_clust_greedy_fast(), the KSSD parameters of " + o.folder + " cannot be reproduced for the new genomes");
+        cerr << "-----the size of sketches (number of genomes or sequences) is: " << add.size() << endl;
+        cerr << "========time of computing sketch is: " << now_s() - t0 << "========" << endl;
+        if (save) {                                              // compute_kssd_sketches: the new sketches get a folder of their own
+            const string folder = current_date_time();
+            if (system(("mkdir -p " + folder).c_str()) != 0) die("cannot create " + folder);
+            save_kssd_sketches(add, folder, o.by_file);
+        }
+    };
+    vector<Genome> add;
+    if (!has_state) {
+        cerr << "===== Initial State Building Mode (KSSD) =====" << endl;
+        cerr << "No existing state found, building state from pre-sketched genomes..." << endl;
+        vector<Genome> pre;
+        const bool pre_by_file = load_kssd_sketches(pre, o.folder);
+        const KssdParams pre_info = g_kssd;
+        if (pre_by_file != o.by_file) cerr << "Warning: the input format of append genomes and pre-sketched genome is not same" << endl;
+        if (pre.empty()) die("no sketches in " + o.folder);
+        o.kmer = 2 * pre_info.half_k;
+        o.drlevel = pre_info.drlevel;
+        cerr << "-----use the same sketch parameters with pre-generated sketches" << endl;
+        cerr << "---use the KSSD sketches" << endl;
+        cerr << "---the half_k is: " << pre_info.half_k << endl;
+        cerr << "---the half_subk is: " << pre_info.half_subk << endl;
+        cerr << "---the drlevel is: " << o.drlevel << endl;
+        cerr << "---the threshold is: " << o.threshold << endl;
+        sketch_new(add, pre_info);
+        g_kssd = pre_info;
+        // KssdInitialClusterWithState (greedy.cpp:902-957): the greedy pass of clust-greedy --fast, its sorted sketch
+        // order kept as the order of the state
+        std::sort(pre.begin(), pre.end(), [](const Genome &a, const Genome &b) { return a.hashes.size() > b.hashes.size(); });
+        upload(ctx, pre);
+        vector<int32_t> rep_of(pre.size());
+        uint32_t nclust = 0;
+        tc_or_die(tc_greedy_cluster_kssd(ctx, o.kmer, o.threshold, rep_of.data(), &nclust), "greedy clustering");
+        vector<int> cid(pre.size(), -1);
+        for (int j = 0; j < (int)pre.size(); j++) {
+            if (rep_of[j] == j) { cid[j] = (int)st.clusters.size(); st.clusters.push_back({j}); st.rep_ids.push_back(j); }
+            else st.clusters[cid[rep_of[j]]].push_back(j);
+        }
+        st.all = std::move(pre);
+        st.params = pre_info; st.threshold = o.threshold; st.kmer_size = o.kmer;
+    } else {
+        cerr << "---the threshold is: " << o.threshold << endl;
+        cerr << "---the thread number is: " << o.threads << endl;
+        o.kmer = st.kmer_size;
+        o.drlevel = st.params.drlevel;
+        sketch_new(add, st.params);
+        g_kssd = st.params;
+        cerr << "New genomes sketched: " << add.size() << endl;
+    }
+    // KssdIncrementalCluster (greedy.cpp:1736-1880) with the state's own threshold and k-mer size
+    const uint32_t n_old = (uint32_t)st.all.size();
+    for (Genome &x : add) st.all.push_back(std::move(x));
+    const uint32_t n = (uint32_t)st.all.size();
+    upload(ctx, st.all);
+    vector<uint32_t> seeds(st.rep_ids.begin(), st.rep_ids.end());
+    vector<int32_t> rep_of(n, -1);
+    uint32_t nclust = 0;
+    tc_or_die(tc_greedy_incremental_kssd(ctx, st.kmer_size, st.threshold, n_old, seeds.data(), (uint32_t)seeds.size(), rep_of.data(), &nclust),
+              "incremental greedy clustering");
+    vector<int> cid(n, -1);
+    for (size_t r = 0; r < st.rep_ids.size(); r++) cid[st.rep_ids[r]] = (int)r;
+    int n_new = 0, n_assigned = 0;
+    for (uint32_t q = n_old; q < n; q++) {
+        if (rep_of[q] == (int32_t)q) {
+            // a new representative opens an EMPTY cluster: the reference does not list it among its own members
+            // (greedy.cpp:1851-1856), so it never appears in the cluster file
+            cid[q] = (int)st.clusters.size();
+            st.rep_ids.push_back((int)q);
+            st.clusters.emplace_back();
+            n_new++;
+        } else {
+            st.clusters[cid[rep_of[q]]].push_back((int)q);
+            n_assigned++;
+        }
+    }
+    cerr << "\n===== Incremental Clustering Results =====" << endl;
+    cerr << "Assigned to existing clusters: " << n_assigned << endl;
+    cerr << "New clusters created: " << n_new << endl;
+    cerr << "Total clusters now: " << st.clusters.size() << endl;
+    if (save && o.save_rep) save_kssd_state(st, state_file);
+    print_result(st.clusters, st.all, o.by_file, o.output, -1.0);
+    cerr << "-----write the cluster result into: " << o.output << endl;
+    cerr << "-----the cluster number of " << o.output << " is: " << st.clusters.size() << endl;
+    cerr << (has_state ? "-----updated cluster state saved" : "-----saved cluster state (with inverted index) for future incremental updates") << endl;
+    return 0;
+}
+#endif
+
 void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_file, bool save, const string &folder)
 {
     if (g.empty()) die("no sketches to cluster");
@@ -1124,11 +1342,20 @@ void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_fi
         if (rep_of[j] == j) { cid[j] = (int)cluster.size(); cluster.push_back({j}); }
         else cluster[cid[rep_of[j]]].push_back(j);
     }
+    if (o.fast && o.save_rep && (save || o.presketched)) {
+        // KssdInitialClusterWithState + state.save (sub_command.cpp:1962-1968, 2485-2490): the clusters just built, in the
+        // sorted sketch order, as the starting point of later clust-greedy --fast --append runs on this folder
+        KssdState st;
+        st.threshold = o.threshold; st.kmer_size = o.kmer; st.params = g_kssd;
+        st.all = g; st.clusters = cluster;
+        for (const vector<int> &c : cluster) st.rep_ids.push_back(c[0]);
+        const string state_file = folder + "/cluster_state.bin";
+        if (save_kssd_state(st, state_file)) cerr << "-----saved cluster state (with inverted index) to: " << state_file << endl;
+    }
     print_result(cluster, g, by_file, o.output, -1.0);
     cerr << "-----write the cluster result into: " << o.output << endl;
     cerr << "-----the cluster number of " << o.output << " is: " << cluster.size() << endl;
     cerr << "========time of greedyCluster is: " << now_s() - t2 << "========" << endl;
-    (void)save; (void)folder;
 #else
     if (o.threshold_only) {
         // connected components of the candidate pairs within the threshold, straight from the dense pass
@@ -1285,7 +1512,7 @@ void usage(const char *prog)
 #ifndef GREEDY_CLUST
             " | --premsted DIR"
 #endif
-            ") [--append FILE] [--fast [--drlevel N]] [--dense]\n"
+            ") [--append FILE] [--fast [--drlevel N]] [--dense] [--save-rep]\n"
             "          [--newick-tree] [--phylip-tree] [--nexus-tree] [--linkage-matrix] [--device N] [--gpus G] [--threshold-only]\n", prog);
 }
 
@@ -1315,6 +1542,7 @@ int main(int argc, char **argv)
         else if (f == "-i" || f == "--input") { o.input = need("-i"); o.has_input = true; }
         else if (f == "--presketched") { o.folder = need("--presketched"); o.presketched = true; }
         else if (f == "--append") { o.input = need("--append"); o.append = true; }
+        else if (f == "--save-rep") o.save_rep = true;
 #ifndef GREEDY_CLUST
         else if (f == "--premsted") { o.folder = need("--premsted"); o.premsted = true; }
 #endif
@@ -1337,6 +1565,14 @@ int main(int argc, char **argv)
     fprintf(stderr, "-----set the thread number %d\n", o.threads);
     if (!o.has_threshold) cerr << "-----use default threshold: " << o.threshold << endl;
     if (o.fast && (o.drlevel < 0 || o.drlevel > 8)) { cerr << "ERROR: invalid drlevel " << o.drlevel << ", should be in [0, 8]" << endl; return 1; }
+#ifdef GREEDY_CLUST
+    if (o.save_rep && !o.fast)
+        die("--save-rep without --fast is not part of this build: the MinHash cluster state (MinHashClusterState, src/greedy.cpp:1904-2130) "
+            "is not built; see DESIGN.md section 8");
+#else
+    if (o.save_rep)
+        die("clust-mst --save-rep is not part of this build: the MST medoid state (src/mst_state.cpp) is not built; see DESIGN.md section 8");
+#endif
 
 #ifndef GREEDY_CLUST
     if (o.premsted && !o.append) {          // clust_from_mst: host only, no GPU needed
@@ -1374,8 +1610,12 @@ int main(int argc, char **argv)
         // append_clust_greedy (:22-96).  The folder's sketch parameters are reused, tune_parameters is not called.
         if (o.dense) die("--append with --dense is not part of this build");
 #ifdef GREEDY_CLUST
-        if (o.fast) die("clust-greedy --append with --fast is not part of this build: the reference clusters it incrementally "
-                        "from a cluster_state.bin (KssdIncrementalCluster), see DESIGN.md section 7");
+        if (o.fast) {
+            if (!o.presketched) { cerr << "ERROR option --append, option --presketched needed" << endl; return 1; }
+            const int rc = append_greedy_fast(ctx, o);
+            tc_ctx_destroy(ctx);
+            return rc;
+        }
 #else
         if (o.fast) {
             // append_clust_mst_fast, the path without a saved mst_cluster_state.bin (sub_command.cpp:1317-1477): KSSD

@@ -103,6 +103,90 @@ def read_info_sketch(path):
     return bool(by_file), out
 
 
+def read_kssd_hash_sketch(path):
+    """kssd.hash.sketch (Sketch_IO.cpp:136-167) -> dict(id, half_k, half_subk, drlevel, genome_number, use64, sketches)."""
+    with open(path, "rb") as f:
+        data = f.read()
+    kid, half_k, half_subk, drlevel, gn = struct.unpack_from("<5i", data, 0)
+    use64 = half_k - drlevel > 8
+    pos, sk = 20, []
+    while pos < len(data):
+        (m,) = struct.unpack_from("<Q", data, pos)
+        pos += 8
+        a = np.frombuffer(data, "<u8" if use64 else "<u4", m, pos)
+        pos += (8 if use64 else 4) * m
+        sk.append(np.sort(a.astype(np.uint64)))
+    return {"id": kid, "half_k": half_k, "half_subk": half_subk, "drlevel": drlevel, "genome_number": gn, "use64": use64,
+            "sketches": sk}
+
+
+def read_kssd_info_sketch(path):
+    """kssd.info.sketch (Sketch_IO.cpp:36-86): info.sketch plus one trailing bool use64 per genome -> (by_file, [dict])."""
+    with open(path, "rb") as f:
+        data = f.read()
+    by_file, n = struct.unpack_from("<?Q", data, 0)
+    pos, out = 9, []
+    for _ in range(n):
+        if by_file:
+            lf, ls, lc, strand, tot = struct.unpack_from("<iiiiQ", data, pos)
+            pos += 24
+            fn = data[pos:pos + lf]; pos += lf
+            sn = data[pos:pos + ls]; pos += ls
+            cm = data[pos:pos + lc]; pos += lc
+            out.append({"file": fn.decode(), "name": sn.decode(), "comment": cm.decode(), "strand": strand, "length": tot})
+        else:
+            ls, lc, strand, length = struct.unpack_from("<iiii", data, pos)
+            pos += 16
+            sn = data[pos:pos + ls]; pos += ls
+            cm = data[pos:pos + lc]; pos += lc
+            out.append({"file": "", "name": sn.decode(), "comment": cm.decode(), "strand": strand, "length": length})
+        pos += 1
+    return bool(by_file), out
+
+
+def read_kssd_cluster_state(path):
+    """cluster_state.bin of clust-greedy --fast --save-rep (KssdClusterState::save, greedy.cpp:1545-1625) ->
+    dict(threshold, kmer_size, half_k, half_subk, drlevel, genome_number, rep_ids, sketches=[dict(id, length, use64,
+    hashes, file)], clusters, index={hash: [representative numbers]})."""
+    with open(path, "rb") as f:
+        data = f.read()
+    thr, k, half_k, half_subk, drlevel, gn = struct.unpack_from("<d5i", data, 0)
+    pos = 28
+    (nrep,) = struct.unpack_from("<Q", data, pos); pos += 8
+    rep_ids = list(struct.unpack_from("<%di" % nrep, data, pos)); pos += 4 * nrep
+    (nsk,) = struct.unpack_from("<Q", data, pos); pos += 8
+    sk = []
+    for _ in range(nsk):
+        gid, length, use64, ssize, n32, n64 = struct.unpack_from("<iQ?IQQ", data, pos)
+        pos += struct.calcsize("<iQ?IQQ")
+        h32 = np.frombuffer(data, "<u4", n32, pos); pos += 4 * n32
+        h64 = np.frombuffer(data, "<u8", n64, pos); pos += 8 * n64
+        (nl,) = struct.unpack_from("<Q", data, pos); pos += 8
+        fn = data[pos:pos + nl].decode(); pos += nl
+        sk.append({"id": gid, "length": length, "use64": bool(use64), "file": fn,
+                   "hashes": np.sort((h64 if n64 else h32).astype(np.uint64))})
+    (ncl,) = struct.unpack_from("<Q", data, pos); pos += 8
+    clusters = []
+    for _ in range(ncl):
+        (m,) = struct.unpack_from("<Q", data, pos); pos += 8
+        clusters.append(list(struct.unpack_from("<%di" % m, data, pos))); pos += 4 * m
+    index = {}
+    wide = data[pos:pos + 6] == b"KSSI02"
+    if wide:
+        pos += 8
+    (nidx,) = struct.unpack_from("<Q", data, pos); pos += 8
+    for _ in range(nidx):
+        if wide:
+            (h,) = struct.unpack_from("<Q", data, pos); pos += 8
+        else:
+            (h,) = struct.unpack_from("<I", data, pos); pos += 4
+        (m,) = struct.unpack_from("<Q", data, pos); pos += 8
+        index[h] = list(struct.unpack_from("<%di" % m, data, pos)); pos += 4 * m
+    assert pos == len(data), "trailing bytes in " + path
+    return {"threshold": thr, "kmer_size": k, "half_k": half_k, "half_subk": half_subk, "drlevel": drlevel,
+            "genome_number": gn, "rep_ids": rep_ids, "sketches": sk, "clusters": clusters, "index": index}
+
+
 def read_edge_mst(path):
     with open(path, "rb") as f:
         data = f.read()

@@ -195,3 +195,43 @@ def test_greedy_sharded_representatives(tc, mode, monkeypatch):
             for c in ctxs:
                 c.close()
         assert got[0] == want[0] and np.array_equal(got[1], want[1]), (mode, g)
+
+
+def _kssd_like_families(seed, n_fam=12, per_fam=10):
+    rng = np.random.default_rng(seed)
+    sk = []
+    for f in range(n_fam):
+        pool = rng.choice(1 << 24, 480, replace=False)
+        for m in range(per_fam):
+            keep = rng.choice(pool, int(480 * rng.uniform(0.3, 1.0)), replace=False)      # some pairs of a family fall below the threshold
+            priv = rng.integers(0, 1 << 24, int(rng.integers(0, 60)))
+            sk.append(np.unique(np.concatenate([keep, priv])).astype(np.uint64))
+    return [sk[i] for i in rng.permutation(len(sk))]
+
+
+@pytest.mark.parametrize("batch", ["32", "4096"])
+@pytest.mark.parametrize("split", [0, 1, 50, 119])
+def test_greedy_incremental_kssd_vs_oracle(ctx, oracle, monkeypatch, batch, split):
+    """tc_greedy_incremental_kssd (KssdIncrementalCluster, greedy.cpp:1736-1880) against the oracle's restatement (pinned
+    to the reference's saved states, tests/test_oracle_golden.py): the first `split` sketches are clustered by the oracle
+    from scratch, their representatives seed the increment over the rest -- new representatives inside a batch included."""
+    monkeypatch.setenv("TCLUST_GREEDY_BATCH", batch)
+    sk = _kssd_like_families(21)
+    n = len(sk)
+    _, rep0 = oracle.greedy_incremental_kssd(sk[:split], 18, 0.05, 0, [])
+    seeds = [q for q in range(split) if rep0[q] == q]
+    want_n, want = oracle.greedy_incremental_kssd(sk, 18, 0.05, split, seeds)
+    ctx.upload(sk)
+    got_n, got = ctx.greedy_incremental_kssd(18, 0.05, split, seeds)
+    assert got_n == want_n
+    assert np.array_equal(got, want)
+    assert got_n >= len(seeds) and (split > 1 or got_n > 12)       # families split: several representatives per family
+
+
+def test_greedy_incremental_kssd_rejects_bad_seeds(ctx, tc):
+    sk = _kssd_like_families(3, 2, 4)
+    ctx.upload(sk)
+    with pytest.raises(tc.TclustError):
+        ctx.greedy_incremental_kssd(18, 0.05, 4, [5])          # a representative must lie before start_index
+    with pytest.raises(tc.TclustError):
+        ctx.greedy_incremental_kssd(18, 0.05, 4, [1, 1])       # listed twice

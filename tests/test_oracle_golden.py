@@ -278,3 +278,88 @@ def test_append_golden_minhash(oracle):
     assert np.array_equal(np.sort(oracle.mst(res["sketches"], 15, 0.05)["dist"]), np.sort(e_res["dist"]))
     assert partition(sketch_io.parse_cluster_file(os.path.join(d, "result", "app.txt"))) == \
         partition(sketch_io.parse_cluster_file(os.path.join(GOLD, "mst_list", "clusters.txt")))
+
+
+def _clusters_after_increment(clusters, rep_ids, start, rep_of):
+    """KssdIncrementalCluster's bookkeeping (greedy.cpp:1851-1870): a new representative opens an EMPTY cluster."""
+    clusters = [list(c) for c in clusters]
+    rep_ids = list(rep_ids)
+    cid = {r: i for i, r in enumerate(rep_ids)}
+    for q, r in enumerate(rep_of, start):
+        if int(r) == q:
+            cid[q] = len(clusters)
+            rep_ids.append(q)
+            clusters.append([])
+        else:
+            clusters[cid[int(r)]].append(q)
+    return clusters, rep_ids
+
+
+def test_append_golden_greedy_kssd_state(oracle):
+    """clust-greedy --fast --append --save-rep of the unmodified reference (tools/make_golden_append.py): 9 genomes
+    clustered, 4 appended without a state (the state is built and saved), 3 more appended from the saved state.  The
+    oracle's restatement of KssdIncrementalCluster reproduces both increments from the saved states, and the reader of
+    cluster_state.bin sees a consistent file (representatives, clusters, hash -> representative index)."""
+    d = os.path.join(GOLD, "append", "greedy_kssd")
+    base = sketch_io.read_kssd_hash_sketch(os.path.join(d, "base", "kssd.hash.sketch"))
+    _, base_info = sketch_io.read_kssd_info_sketch(os.path.join(d, "base", "kssd.info.sketch"))
+    s1 = sketch_io.read_kssd_cluster_state(os.path.join(d, "step1", "cluster_state.bin"))
+    s2 = sketch_io.read_kssd_cluster_state(os.path.join(d, "step2", "cluster_state.bin"))
+    assert (s1["kmer_size"], s1["half_k"], s1["drlevel"], s1["threshold"]) == (2 * base["half_k"], base["half_k"], base["drlevel"], 0.05)
+    # the state keeps the base sketches in the processing order of the initial clustering (size descending) ...
+    by_file = {i["file"]: h for i, h in zip(base_info, base["sketches"])}
+    assert [len(x["hashes"]) for x in s1["sketches"][:9]] == sorted((len(h) for h in base["sketches"]), reverse=True)
+    assert all(np.array_equal(by_file[x["file"]], x["hashes"]) for x in s1["sketches"][:9])
+    # ... followed by the appended ones in list order
+    for st, step, lo in ((s1, "step1", 9), (s2, "step2", 13)):
+        new = sketch_io.read_kssd_hash_sketch(os.path.join(d, step, "new", "kssd.hash.sketch"))
+        assert all(np.array_equal(a, x["hashes"]) for a, x in zip(new["sketches"], st["sketches"][lo:]))
+        assert len(new["sketches"]) == len(st["sketches"]) - lo
+        # index section: hash -> numbers of the representatives holding it
+        want = {}
+        for r, gid in enumerate(st["rep_ids"]):
+            for h in st["sketches"][gid]["hashes"]:
+                want.setdefault(int(h), []).append(r)
+        assert want == st["index"]
+    # increment 1: clusters of the base run (base.txt) + 4 new genomes
+    base_clusters = [[gid for gid, _ in c] for c in sketch_io.parse_cluster_file(os.path.join(d, "base", "base.txt"))]
+    seeds = [c[0] for c in base_clusters]
+    k = s1["kmer_size"]
+    nrep, rep_of = oracle.greedy_incremental_kssd([x["hashes"] for x in s1["sketches"]], k, 0.05, 9, seeds)
+    cl, reps = _clusters_after_increment(base_clusters, seeds, 9, rep_of)
+    assert (cl, reps, nrep) == (s1["clusters"], s1["rep_ids"], len(s1["rep_ids"]))
+    # increment 2 from the saved state
+    nrep, rep_of = oracle.greedy_incremental_kssd([x["hashes"] for x in s2["sketches"]], k, s1["threshold"], 13, s1["rep_ids"])
+    cl, reps = _clusters_after_increment(s1["clusters"], s1["rep_ids"], 13, rep_of)
+    assert (cl, reps, nrep) == (s2["clusters"], s2["rep_ids"], len(s2["rep_ids"]))
+    # the cluster files list exactly the clusters of the states (a founder is not a member of its own new cluster)
+    for st, step in ((s1, "step1"), (s2, "step2")):
+        got = [[gid for gid, _ in c] for c in sketch_io.parse_cluster_file(os.path.join(d, step, "app.txt"))]
+        assert got == st["clusters"]
+
+
+def test_greedy_incremental_oracle_properties(oracle):
+    """the restated rule on a synthetic set: starting from no representatives it is a plain greedy pass in which every
+    sketch is within the threshold of its representative, and splitting the run in two gives the same result."""
+    rng = np.random.default_rng(11)
+    sk = []
+    for f in range(8):
+        pool = rng.choice(1 << 24, 400, replace=False)
+        for m in range(8):
+            keep = rng.choice(pool, int(400 * rng.uniform(0.6, 1.0)), replace=False)
+            sk.append(np.unique(np.concatenate([keep, rng.integers(0, 1 << 24, 20)])).astype(np.uint64))
+    order = rng.permutation(len(sk))
+    sk = [sk[i] for i in order]
+    n = len(sk)
+    nrep, rep = oracle.greedy_incremental_kssd(sk, 18, 0.05, 0, [])
+    reps = [q for q in range(n) if rep[q] == q]
+    assert nrep == len(reps) >= 8
+    for q in range(n):
+        if rep[q] != q:
+            assert rep[q] < q and rep[rep[q]] == rep[q]
+            c = len(np.intersect1d(sk[q], sk[rep[q]]))
+            assert oracle.lib().oc_greedy_dist(c, len(sk[rep[q]]), len(sk[q]), 0, 18) <= 0.05
+    half = n // 2
+    reps_half = [q for q in reps if q < half]
+    nrep2, rep2 = oracle.greedy_incremental_kssd(sk, 18, 0.05, half, reps_half)
+    assert nrep2 == nrep and np.array_equal(rep2, rep[half:])

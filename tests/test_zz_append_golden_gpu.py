@@ -31,3 +31,89 @@ def test_clust_mst_append_golden_folders(tmp_path, name):
     ref_out, our_out = os.path.join(gold, "result", "app.txt"), str(tmp_path / "app.txt")
     assert open(ref_out).read().splitlines()[:3] == open(our_out).read().splitlines()[:3]
     assert _partition(ref_out) == _partition(our_out)
+
+
+def _state_without_index_order(path):
+    s = sketch_io.read_kssd_cluster_state(path)
+    s["sketches"] = [(x["id"], x["length"], x["use64"], x["file"], x["hashes"].tolist()) for x in s["sketches"]]
+    return s
+
+
+def test_clust_greedy_fast_append_state_golden(tmp_path):
+    """clust-greedy --fast --append --save-rep (append_clust_greedy_fast, sub_command.cpp:192-276) on the committed
+    reference runs: increment 1 builds the state from the pre-sketched folder, increment 2 continues from the saved
+    cluster_state.bin.  Cluster files byte-identical; state files equal field by field (the hash -> representative index is
+    compared as a map: the reference writes it in hash-map iteration order)."""
+    _need_bins()
+    import shutil
+    os.symlink(os.path.join(ROOT, "tests"), str(tmp_path / "tests"))
+    gold = os.path.join(ROOT, "tests", "golden", "append", "greedy_kssd")
+    base = str(tmp_path / "base")
+    shutil.copytree(os.path.join(gold, "base"), base)
+    exe = os.path.join(OURS, "clust-greedy")
+    for step, lst in (("step1", "second_a.txt"), ("step2", "second_b.txt")):
+        _, err = _run(exe, ["--fast", "-l", "--append", "tests/golden/append/" + lst, "--presketched", base, "--save-rep",
+                            "-d", "0.05", "-o", step + ".txt"], str(tmp_path))
+        assert ("Initial State Building Mode" if step == "step1" else "Incremental Update Mode") in err
+        assert _same_bytes(os.path.join(gold, step, "app.txt"), str(tmp_path / (step + ".txt"))), step
+        assert _state_without_index_order(os.path.join(gold, step, "cluster_state.bin")) == \
+            _state_without_index_order(os.path.join(base, "cluster_state.bin")), step
+    # the sketches of the appended genomes were saved to folders of their own, as compute_kssd_sketches does
+    new = sorted(p for p in os.listdir(str(tmp_path)) if p.startswith("20"))
+    assert len(new) == 2
+    for folder, step in zip(new, ("step1", "step2")):
+        for fn in ("kssd.hash.sketch", "kssd.info.sketch"):
+            assert _same_bytes(os.path.join(gold, step, "new", fn), str(tmp_path / folder / fn)), (step, fn)
+
+
+def test_clust_greedy_fast_append_without_save_rep(tmp_path):
+    """without --save-rep the same result is printed and no state file is left behind (sub_command.cpp:235-243)"""
+    _need_bins()
+    import shutil
+    os.symlink(os.path.join(ROOT, "tests"), str(tmp_path / "tests"))
+    gold = os.path.join(ROOT, "tests", "golden", "append", "greedy_kssd")
+    base = str(tmp_path / "base")
+    shutil.copytree(os.path.join(gold, "base"), base)
+    _run(os.path.join(OURS, "clust-greedy"), ["--fast", "-l", "--append", "tests/golden/append/second_a.txt", "--presketched", base,
+                                               "-d", "0.05", "-o", "app.txt"], str(tmp_path))
+    assert _same_bytes(os.path.join(gold, "step1", "app.txt"), str(tmp_path / "app.txt"))
+    assert not os.path.exists(os.path.join(base, "cluster_state.bin"))
+
+
+def test_reference_continues_from_our_cluster_state_live(tmp_path):
+    """live: a larger synthetic set (several candidates per query).  clust-greedy --fast --save-rep writes the state next
+    to the sketches; the unmodified reference appends to OUR state file and we append to ITS state file: all four
+    combinations give the same cluster file."""
+    _need_bins()
+    import shutil
+    from test_cli_gpu import REF, _make_genomes
+    d = str(tmp_path / "genomes")
+    os.makedirs(d)
+    lst, _ = _make_genomes(d, n_fam=5, per_fam=6, length=600000, seed=77)
+    files = open(lst).read().split()
+    rng = np.random.default_rng(5)
+    files = [files[i] for i in rng.permutation(len(files))]
+    first, second = str(tmp_path / "first.txt"), str(tmp_path / "second.txt")
+    open(first, "w").write("\n".join(files[:18]) + "\n")
+    open(second, "w").write("\n".join(files[18:]) + "\n")
+    out = {}
+    for who, exe, t1 in (("ref", os.path.join(REF, "clust-greedy"), ["-t", "1"]), ("ours", os.path.join(OURS, "clust-greedy"), [])):
+        cwd = str(tmp_path / who)
+        folder, _ = _run(exe, t1 + ["--fast", "-l", "-i", first, "-d", "0.05", "--save-rep", "-o", "base.txt"], cwd)
+        assert os.path.exists(os.path.join(folder, "cluster_state.bin")), who
+        out[who] = folder
+    assert _same_bytes(str(tmp_path / "ref" / "base.txt"), str(tmp_path / "ours" / "base.txt"))
+    a = _state_without_index_order(os.path.join(out["ref"], "cluster_state.bin"))
+    b = _state_without_index_order(os.path.join(out["ours"], "cluster_state.bin"))
+    assert a == b
+    results = {}
+    for state_of in ("ref", "ours"):
+        for who, exe, t1 in (("ref", os.path.join(REF, "clust-greedy"), ["-t", "1"]), ("ours", os.path.join(OURS, "clust-greedy"), [])):
+            cwd = str(tmp_path / ("app_%s_on_%s" % (who, state_of)))
+            folder = os.path.join(cwd, "state")
+            os.makedirs(cwd)
+            shutil.copytree(out[state_of], folder)
+            _run(exe, t1 + ["--fast", "-l", "--append", second, "--presketched", folder, "--save-rep", "-d", "0.05", "-o", "app.txt"], cwd)
+            results[(who, state_of)] = open(os.path.join(cwd, "app.txt"), "rb").read()
+            assert os.path.getsize(os.path.join(folder, "cluster_state.bin")) > os.path.getsize(os.path.join(out[state_of], "cluster_state.bin"))
+    assert len(set(results.values())) == 1, {k: len(v) for k, v in results.items()}

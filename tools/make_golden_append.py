@@ -4,6 +4,9 @@ the first 9 genomes of tests/golden/mst_genomes are clustered, the other 4 appen
   tests/golden/append/first.txt, second.txt          the two genome lists (paths relative to the repo root)
   tests/golden/append/kssd/base, .../result          clust-mst --fast, then --fast --append   (sub_command.cpp:1286-1477)
   tests/golden/append/minhash/base, .../result       clust-mst -k 15 -s 1000, then --append   (sub_command.cpp:1578-1757)
+  tests/golden/append/greedy_kssd/base, step1, step2 clust-greedy --fast on the first 9, then --fast --append --save-rep of
+                                                     second_a.txt (4 genomes; builds cluster_state.bin) and of second_b.txt
+                                                     (3 genomes; continues from the state)   (sub_command.cpp:192-276)
 usage: python tools/make_golden_append.py   (needs oracle/_ref; rewrites tests/golden/append)"""
 import glob
 import json
@@ -74,6 +77,36 @@ def main():
             meta[name] = {"base_cmd": " ".join(["oracle/_ref/clust-mst"] + base_cmd[1:]),
                           "append_cmd": " ".join(["oracle/_ref/clust-mst"] + app_cmd[1:]).replace(base, "<base folder>"),
                           "stderr_tail": p.stderr.decode()[-400:]}
+    # ---- clust-greedy --fast --append with the cluster state (append_clust_greedy_fast, KssdIncrementalCluster)
+    open(os.path.join(GOLD, "second_a.txt"), "w").write("\n".join(files[N_FIRST:N_FIRST + 4]) + "\n")
+    open(os.path.join(GOLD, "second_b.txt"), "w").write("\n".join(files[N_FIRST + 4:]) + "\n")
+    with tempfile.TemporaryDirectory() as tmp:
+        os.symlink(os.path.join(ROOT, "tests"), os.path.join(tmp, "tests"))
+        exe = os.path.join(REF, "clust-greedy")
+        base_cmd = [exe, "-t", "1", "--fast", "-l", "-i", "tests/golden/append/first.txt", "-d", "0.05", "-o", "base.txt"]
+        run(base_cmd, tmp)
+        base = newest_dir(tmp, [])
+        out = os.path.join(GOLD, "greedy_kssd")
+        os.makedirs(os.path.join(out, "base"))
+        for fn in ("kssd.hash.sketch", "kssd.info.sketch"):
+            shutil.copy(os.path.join(base, fn), os.path.join(out, "base"))
+        shutil.copy(os.path.join(tmp, "base.txt"), os.path.join(out, "base"))
+        known = [base]
+        cmds = []
+        for step, lst in (("step1", "second_a.txt"), ("step2", "second_b.txt")):
+            cmd = [exe, "-t", "1", "--fast", "-l", "--append", "tests/golden/append/" + lst, "--presketched", base, "--save-rep",
+                   "-d", "0.05", "-o", step + ".txt"]
+            p = run(cmd, tmp)
+            new = newest_dir(tmp, known)            # the sketches of the appended genomes (compute_kssd_sketches saves them)
+            known.append(new)
+            os.makedirs(os.path.join(out, step, "new"))
+            for fn in ("kssd.hash.sketch", "kssd.info.sketch"):
+                shutil.copy(os.path.join(new, fn), os.path.join(out, step, "new"))
+            shutil.copy(os.path.join(base, "cluster_state.bin"), os.path.join(out, step))
+            shutil.copy(os.path.join(tmp, step + ".txt"), os.path.join(out, step, "app.txt"))
+            cmds.append(" ".join(["oracle/_ref/clust-greedy"] + cmd[1:]).replace(base, "<base folder>"))
+        meta["greedy_kssd"] = {"base_cmd": " ".join(["oracle/_ref/clust-greedy"] + base_cmd[1:]), "append_cmds": cmds,
+                               "stderr_tail": p.stderr.decode()[-400:]}
     json.dump(meta, open(os.path.join(GOLD, "MANIFEST.json"), "w"), indent=1)
     subprocess.call(["du", "-sh", GOLD])
 
