@@ -108,6 +108,18 @@ int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off,
                    const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes,
                    int kmer_size, int drlevel, const int32_t *shuffled_dim,
                    uint64_t *out_hashes, uint64_t out_stride, uint32_t *out_n);
+/* One KSSD sketch per RECORD of a multi-FASTA: the single-file consumer consumer_fasta_task_with_kssd
+ * (src/SketchInfo.cpp:274-433; caller sketchSequencesWithKssd, :554-642).  nrec == ngenomes, rec2genome[r] == r.  For an even
+ * kmer_size the hash sets are those of tc_sketch_kssd.  For an ODD one the reference does not round kmerSize up to
+ * 2*half_k here (:296 vs :1019-1020): a window is used after kmer_size valid bases while the rolling tuple holds
+ * kmer_size+1, a non-ACGT byte restarts the count without clearing the tuple (:368-371), so the first window after every
+ * gap keeps the last valid base from before it (nothing at the start of a record), and the outer-context bits are packed
+ * with the un-rounded size (:386).  All of that is reproduced on the device.  The reference leaves each set in hash-set
+ * iteration order; rows come back ascending. */
+int tc_sketch_kssd_seq(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off,
+                       const uint32_t *rec2genome, uint64_t nrec, uint32_t ngenomes,
+                       int kmer_size, int drlevel, const int32_t *shuffled_dim,
+                       uint64_t *out_hashes, uint64_t out_stride, uint32_t *out_n);
 /* same with sequence and outputs resident on the device (shuffled_dim stays a host pointer; the
  * table is uploaded once per context and pointer) */
 int tc_sketch_kssd_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const uint64_t *rec_off,

@@ -42,6 +42,8 @@ def lib():
         L.oc_kssd_shuffled_dim.argtypes = [C.c_int, i32p]
         L.oc_kssd_sketch.restype = C.c_size_t
         L.oc_kssd_sketch.argtypes = [u8p, u64p, C.c_int, C.c_int, C.c_int, i32p, u64p, C.c_size_t]
+        L.oc_kssd_sketch_seq.restype = C.c_size_t
+        L.oc_kssd_sketch_seq.argtypes = [u8p, C.c_uint64, C.c_int, C.c_int, i32p, u64p, C.c_size_t]
         L.oc_intersect_u64.restype = C.c_uint32
         L.oc_intersect_u64.argtypes = [u64p, C.c_size_t, u64p, C.c_size_t, u32p]
         L.oc_jaccard_B.restype = C.c_double
@@ -130,10 +132,21 @@ def kssd_sketch(records, kmer_size, drlevel=3):
     seq, off, n = _pack_records(records)
     _, half_subk, _ = kssd_params(kmer_size, drlevel)
     sd = kssd_shuffled_dim(half_subk)
-    cap = max(1024, int(off[-1]) // 8 + 1024)
+    cap = max(1024, int(off[-1]) // (8 if drlevel else 1) + 1024)      # drlevel 0 keeps every window
     out = np.zeros(cap, np.uint64)
     m = lib().oc_kssd_sketch(_p(seq, C.c_uint8), _p(off, C.c_uint64), n, kmer_size, drlevel,
                              _p(sd, C.c_int32), _p(out, C.c_uint64), cap)
+    return out[:m].copy()
+
+
+def kssd_sketch_seq(record, kmer_size, drlevel=3):
+    """one record of a multi-FASTA through the single-file consumer (odd k: stale-base windows, un-rounded shift)"""
+    seq = np.frombuffer(bytes(record), np.uint8).copy() if len(record) else np.zeros(1, np.uint8)
+    _, half_subk, _ = kssd_params(kmer_size, drlevel)
+    sd = kssd_shuffled_dim(half_subk)
+    cap = len(record) + 16
+    out = np.zeros(cap, np.uint64)
+    m = lib().oc_kssd_sketch_seq(_p(seq, C.c_uint8), len(record), kmer_size, drlevel, _p(sd, C.c_int32), _p(out, C.c_uint64), cap)
     return out[:m].copy()
 
 

@@ -205,6 +205,70 @@ size_t oc_kssd_sketch(const uint8_t *seq, const uint64_t *rec_off, int nrec,
     return m;
 }
 
+/* The per-record consumer of the single-file mode (consumer_fasta_task_with_kssd, SketchInfo.cpp:274-433).  It differs
+ * from the list-mode loop above in three ways, all of which matter only for an ODD kmer_size: kmerSize is NOT rounded up
+ * to 2*half_k (:296 vs :1019-1020), so a window is used once kmer_size valid bases have been seen (`base > kmerSize`,
+ * :372) while the tuple still holds 2*half_k bases; a non-ACGT byte restarts the count but does NOT clear tuple /
+ * rvs_tuple (:368-371), so the first window after it carries one base from before the gap (or the zero initial state at
+ * the start of the record); and the outer-context shift uses the un-rounded kmerSize (:386).  One sketch per record;
+ * the reference stores the set in hash-set iteration order, returned here ascending. */
+size_t oc_kssd_sketch_seq(const uint8_t *seq, uint64_t len, int kmer_size, int drlevel, const int32_t *shuffled_dim,
+                          uint64_t *out, size_t out_cap)
+{
+    int half_k = (kmer_size + 1) / 2;
+    int use64 = half_k - drlevel > 8;
+    int half_subk = 6 - drlevel >= 2 ? 6 : drlevel + 2;
+    int dim_end = 1 << (4 * (half_subk - drlevel));
+    int comp_bittl = 64 - 4 * half_k;
+    int half_outctx_len = half_k - half_subk;
+    int rev_add_move = 4 * half_k - 2;
+    uint64_t tupmask = UINT64_MAX >> comp_bittl;
+    uint64_t domask = (tupmask >> (4 * half_outctx_len)) << (2 * half_outctx_len);
+    uint64_t undomask = (tupmask ^ domask) & tupmask;
+    uint64_t undomask1 = undomask & (tupmask >> ((half_k + half_subk) * 2));
+    uint64_t undomask0 = undomask ^ undomask1;
+    size_t n = 0, cap = 1 << 12;
+    uint64_t *buf = (uint64_t *)malloc(cap * 8);
+    uint64_t tuple = 0, rvs = 0;
+    int base = 1;
+    for (uint64_t p = 0; p < len; p++) {                           /* :358-394 */
+        int bn;
+        switch (seq[p]) {
+            case 'A': case 'a': bn = 0; break;
+            case 'C': case 'c': bn = 1; break;
+            case 'G': case 'g': bn = 2; break;
+            case 'T': case 't': bn = 3; break;
+            default: bn = -1;
+        }
+        if (bn >= 0) {
+            tuple = ((tuple << 2) | (uint64_t)bn) & tupmask;
+            rvs = (rvs >> 2) + (((uint64_t)bn ^ 3ULL) << rev_add_move);
+            base++;
+        } else {
+            base = 1;
+        }
+        if (base > kmer_size) {            /* also true at a non-ACGT byte?  no: base was just set to 1 */
+            uint64_t uni = tuple < rvs ? tuple : rvs;
+            uint32_t dim_id = (uint32_t)((uni & domask) >> (half_outctx_len * 2));
+            int pf = shuffled_dim[dim_id];
+            if (pf >= dim_end) continue;
+            uint64_t dr = (((uni & undomask0) | ((uni & undomask1) << (kmer_size * 2 - half_outctx_len * 4)))
+                           >> (drlevel * 4)) | (uint64_t)pf;
+            if (!use64) dr &= 0xffffffffULL;                       /* stored in a uint32 set */
+            if (n == cap) { cap *= 2; buf = (uint64_t *)realloc(buf, cap * 8); }
+            buf[n++] = dr;
+        }
+    }
+    qsort(buf, n, 8, cmp_u64);
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++)
+        if (m == 0 || buf[i] != buf[m - 1]) buf[m++] = buf[i];
+    if (m > out_cap) m = out_cap;
+    memcpy(out, buf, m * 8);
+    free(buf);
+    return m;
+}
+
 /* --------------------------------------------------------------- distances */
 uint32_t oc_intersect_u64(const uint64_t *a, size_t na, const uint64_t *b, size_t nb,
                           uint32_t *first_hit)

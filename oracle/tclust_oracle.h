@@ -48,6 +48,11 @@ size_t oc_kssd_sketch(const uint8_t *seq, const uint64_t *rec_off, int nrec,
                       int kmer_size, int drlevel, const int32_t *shuffled_dim,
                       uint64_t *out, size_t out_cap);
 
+/* the single-file (-i) consumer, one record: consumer_fasta_task_with_kssd (SketchInfo.cpp:274-433); equals
+ * oc_kssd_sketch for an even kmer_size, keeps one stale base per reset and the un-rounded shift for an odd one */
+size_t oc_kssd_sketch_seq(const uint8_t *seq, uint64_t len, int kmer_size, int drlevel, const int32_t *shuffled_dim,
+                          uint64_t *out, size_t out_cap);
+
 /* semantic A: |A n B| over the whole sorted sketches (src/MST.cpp:1409-1435 counts,
  * scalar merge form src/greedy.cpp:125-147). first_hit (may be NULL) = index in `a`
  * of the first shared hash, or UINT32_MAX. */

@@ -19,7 +19,7 @@ PAIR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("common", "<u4")])
 # every symbol include/tclust.h declares (tests check the built library exports all of them)
 SYMBOLS = [
     "tc_version", "tc_last_error", "tc_ctx_create", "tc_ctx_destroy", "tc_kernel_launches", "tc_last_pass_kernel_ms", "tc_stream",
-    "tc_host_alloc", "tc_host_free", "tc_sketch_minhash", "tc_sketch_minhash_dev", "tc_kssd_shuffled_dim", "tc_sketch_kssd", "tc_sketch_kssd_dev",
+    "tc_host_alloc", "tc_host_free", "tc_sketch_minhash", "tc_sketch_minhash_dev", "tc_kssd_shuffled_dim", "tc_sketch_kssd", "tc_sketch_kssd_seq", "tc_sketch_kssd_dev",
     "tc_sketches_upload", "tc_sketches_upload_dev", "tc_sketches_upload_rows", "tc_pair_common", "tc_allpairs_pass",
     "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_boruvka_set_async", "tc_mst",
     "tc_greedy_scan", "tc_greedy_cluster",
@@ -72,6 +72,7 @@ def lib():
     L.tc_sketch_kssd.argtypes = [vp, vp, u64p, u32p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, i32p,
                                  vp, C.c_uint64, vp]
     L.tc_sketch_kssd_dev.argtypes = L.tc_sketch_kssd.argtypes
+    L.tc_sketch_kssd_seq.argtypes = L.tc_sketch_kssd.argtypes
     L.tc_sketches_upload.argtypes = [vp, vp, u64p, C.c_uint32]
     L.tc_sketches_upload_dev.argtypes = [vp, vp, u64p, C.c_uint32]
     L.tc_sketches_upload_rows.argtypes = [vp, vp, u64p, C.c_uint32]
@@ -222,7 +223,9 @@ class Context:
                                      out.ctypes.data, stride, out_n.ctypes.data))
         return [out[g, :out_n[g]].copy() for g in range(ng)]
 
-    def sketch_kssd(self, genomes, kmer_size, drlevel, shuffled_dim, max_hashes=None):
+    def sketch_kssd(self, genomes, kmer_size, drlevel, shuffled_dim, max_hashes=None, per_record=False):
+        """per_record=True: every genome is one record of a multi-FASTA, sketched by the rule of the single-file
+        consumer (tc_sketch_kssd_seq: differs from the list-mode rule for an odd kmer_size)."""
         seq, off, r2g = pack_records(genomes)
         ng = len(genomes)
         if max_hashes is None:
@@ -231,9 +234,10 @@ class Context:
         out = np.zeros((ng, max_hashes), np.uint64)
         out_n = np.zeros(ng, np.uint32)
         sd = np.ascontiguousarray(shuffled_dim, np.int32)
-        _chk(lib().tc_sketch_kssd(self._h, seq.ctypes.data, _p(off, C.c_uint64), _p(r2g, C.c_uint32),
-                                  len(off) - 1, ng, kmer_size, drlevel, _p(sd, C.c_int32),
-                                  out.ctypes.data, max_hashes, out_n.ctypes.data))
+        fn = lib().tc_sketch_kssd_seq if per_record else lib().tc_sketch_kssd
+        _chk(fn(self._h, seq.ctypes.data, _p(off, C.c_uint64), _p(r2g, C.c_uint32),
+                len(off) - 1, ng, kmer_size, drlevel, _p(sd, C.c_int32),
+                out.ctypes.data, max_hashes, out_n.ctypes.data))
         return [out[g, :out_n[g]].copy() for g in range(ng)]
 
     # ---- HP-2 ----

@@ -47,6 +47,8 @@ struct K2Args {
     const int32_t *shuffled_dim;
     const uint32_t *dim_filter;     // K2_FILTER_BITS-bit presence bitmap of the slots that pass (see k2_setup)
     int kmer, drlevel, half_outctx_len, dim_end, use64, rev_add_move;
+    int odd;          // 1: per-record mode of the single-file consumer with an odd k-mer size (see tc_sketch_kssd_seq)
+    int dr_shift;     // left shift of the low outer-context bits: 2*kmerSize - 4*half_outctx_len
     unsigned long long tupmask, domask, undomask0, undomask1;
     uint64_t *out; unsigned long long out_stride; uint32_t *cnt;
 };
@@ -90,15 +92,37 @@ __global__ void __launch_bounds__(K2_THREADS) k2_kssd_kernel(const K2Args a)
             tuple = ((tuple << 2) | bn) & a.tupmask;
             rvs = (rvs >> 2) + ((unsigned long long)(bn ^ 3u) << a.rev_add_move);
             run++;
-            if (run >= a.kmer && pos >= e0) {
-                const unsigned long long uni = tuple < rvs ? tuple : rvs;
+            unsigned long long t_use = tuple, r_use = rvs;
+            bool use = run >= a.kmer && pos >= e0;
+            if (a.odd && run == a.kmer - 1 && pos >= e0) {
+                // consumer_fasta_task_with_kssd with kmerSize = a.kmer - 1 (SketchInfo.cpp:358-372): the window is used
+                // after kmerSize valid bases while the tuple holds a.kmer, and a non-ACGT byte does not clear the tuple:
+                // the oldest slot still holds the last valid base before the gap (nothing at the start of the record).
+                // This thread saw the byte in front of the run (priming starts a.kmer-1 bytes before e0), so the run
+                // really began at a reset; walk back over the gap for that base -- once per reset.
+                unsigned long long q = pos - (unsigned long long)(a.kmer - 2);         // first base of the run
+                int stale = -1;
+                while (q > seg.rec_start && stale < 0) {
+                    q--;
+                    const uint32_t cc = (uint32_t)__ldg(a.seq + q) & 0xDFu;
+                    const uint32_t xx = cc - 0x41u;
+                    if (xx < 20u && ((0x80045u >> xx) & 1u)) { uint32_t b = (cc >> 1) & 3u; b ^= b >> 1; stale = (int)b; }
+                }
+                if (stale >= 0) {
+                    t_use = tuple | ((unsigned long long)stale << (2 * (a.kmer - 1)));
+                    r_use = rvs | (unsigned long long)(stale ^ 3);
+                }
+                use = true;
+            }
+            if (use) {
+                const unsigned long long uni = t_use < r_use ? t_use : r_use;
                 const uint32_t dim_id = (uint32_t)((uni & a.domask) >> (a.half_outctx_len * 2));
                 const uint32_t fb = dim_id & (K2_FILTER_BITS - 1);
                 const bool maybe = (s_filter[fb >> 5] >> (fb & 31u)) & 1u;
                 const int pf = maybe ? __ldg(a.shuffled_dim + dim_id) : a.dim_end;
                 if (pf < a.dim_end) {
                     unsigned long long dr = (((uni & a.undomask0) |
-                                              ((uni & a.undomask1) << (a.kmer * 2 - a.half_outctx_len * 4)))
+                                              ((uni & a.undomask1) << a.dr_shift))
                                              >> (a.drlevel * 4)) | (unsigned long long)pf;
                     if (!a.use64) dr &= 0xffffffffULL;
                     const uint32_t idx = atomicAdd(&a.cnt[seg.genome], 1u);
@@ -176,7 +200,7 @@ K2Workspace *k2_ws(tc_ctx *ctx)
 inline size_t k2_al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // constants of the scheme (SketchInfo.cpp:1019-1048) + the resident shuffled_dim table
-int k2_setup(tc_ctx *ctx, int kmer_size, int drlevel, const int32_t *shuffled_dim, uint64_t out_stride, K2Args &a)
+int k2_setup(tc_ctx *ctx, int kmer_size, int drlevel, const int32_t *shuffled_dim, uint64_t out_stride, K2Args &a, bool seq_mode = false)
 {
     TC_CHECK(kmer_size >= 2 && kmer_size <= 32, "tc_sketch_kssd: kmer_size=%d unsupported (2..32)", kmer_size);
     TC_CHECK(out_stride > 0 && out_stride < (1ull << 31), "tc_sketch_kssd: bad out_stride");
@@ -187,6 +211,9 @@ int k2_setup(tc_ctx *ctx, int kmer_size, int drlevel, const int32_t *shuffled_di
     const int half_outctx_len = half_k - half_subk;
     const int comp_bittl = 64 - 4 * half_k;
     a.kmer = kmer; a.drlevel = drlevel; a.half_outctx_len = half_outctx_len;
+    // list mode rounds kmerSize up to 2*half_k (SketchInfo.cpp:1019-1020); the single-file consumer does not (:296, :386)
+    a.odd = seq_mode && (kmer_size & 1);
+    a.dr_shift = (a.odd ? kmer_size : kmer) * 2 - half_outctx_len * 4;
     a.dim_end = 1 << (4 * (half_subk - drlevel));
     a.use64 = half_k - drlevel > 8;
     a.rev_add_move = 4 * half_k - 2;
@@ -232,9 +259,10 @@ int k2_enqueue(tc_ctx *ctx, K2Workspace *ws, K2Slot &sl, cudaStream_t st, K2Args
                uint64_t base_off, uint64_t *out_dev, uint64_t out_stride, uint32_t *out_n_dev)
 {
     uint64_t total = 0;
+    const int kmin = a.kmer - a.odd;                     // shortest run of valid bases that yields a window
     for (uint64_t r = r0; r < r1; r++) {
         const uint64_t len = rec_off[r + 1] - rec_off[r];
-        if (len >= (uint64_t)a.kmer) total += len - a.kmer + 1;
+        if (len >= (uint64_t)kmin) total += len - kmin + 1;
     }
     const uint64_t want_ctas = (uint64_t)ctx->num_sms * 32;
     uint64_t segw = std::min<uint64_t>(std::max<uint64_t>(total / std::max<uint64_t>(want_ctas, 1), 1u << 14), 1u << 20);
@@ -242,9 +270,9 @@ int k2_enqueue(tc_ctx *ctx, K2Workspace *ws, K2Slot &sl, cudaStream_t st, K2Args
     std::vector<K2Seg> segs;
     for (uint64_t r = r0; r < r1; r++) {
         const uint64_t len = rec_off[r + 1] - rec_off[r];
-        if (len < (uint64_t)a.kmer) continue;
+        if (len < (uint64_t)kmin) continue;
         const uint64_t start = rec_off[r] - base_off;
-        const uint64_t first = start + a.kmer - 1, last = start + len;      // end-positions [first, last)
+        const uint64_t first = start + kmin - 1, last = start + len;        // end-positions [first, last)
         for (uint64_t e = first; e < last; e += segw) {
             K2Seg sg{};
             sg.rec_start = start; sg.emit_begin = e; sg.emit_end = std::min(e + segw, last); sg.genome = rec2genome[r] - g0;
@@ -370,16 +398,16 @@ extern "C" int tc_sketch_kssd_dev(tc_ctx *ctx, const uint8_t *seqs_dev, const ui
     return k2_check_overflow(ws, ctx->stream, out_stride);
 }
 
-extern "C" int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off, const uint32_t *rec2genome,
-                              uint64_t nrec, uint32_t ngenomes, int kmer_size, int drlevel, const int32_t *shuffled_dim,
-                              uint64_t *out_hashes, uint64_t out_stride, uint32_t *out_n)
+static int k2_sketch_host(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off, const uint32_t *rec2genome,
+                          uint64_t nrec, uint32_t ngenomes, int kmer_size, int drlevel, const int32_t *shuffled_dim,
+                          uint64_t *out_hashes, uint64_t out_stride, uint32_t *out_n, bool seq_mode)
 {
     TC_CUDA(cudaSetDevice(ctx->device));
     if (k2_validate(rec_off, rec2genome, nrec, ngenomes)) return 1;
     K2Workspace *ws = k2_ws(ctx);
     TC_CHECK(ws, "tc_sketch_kssd: cannot create the workspace");
     K2Args a{};
-    if (k2_setup(ctx, kmer_size, drlevel, shuffled_dim, out_stride, a)) return 1;
+    if (k2_setup(ctx, kmer_size, drlevel, shuffled_dim, out_stride, a, seq_mode)) return 1;
     cudaStream_t st = ctx->stream, cs = ws->copy_stream;
     const size_t out_elems = std::max<uint64_t>((uint64_t)ngenomes * out_stride, 1);
     if (out_elems > ws->out_cap) {
@@ -439,6 +467,24 @@ extern "C" int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *
     else cudaStreamSynchronize(st);
     if (!rc && e1 != cudaSuccess) { tc_set_error("tc_sketch_kssd: %s", cudaGetErrorString(e1)); rc = 1; }
     return rc;
+}
+
+extern "C" int tc_sketch_kssd(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off, const uint32_t *rec2genome,
+                              uint64_t nrec, uint32_t ngenomes, int kmer_size, int drlevel, const int32_t *shuffled_dim,
+                              uint64_t *out_hashes, uint64_t out_stride, uint32_t *out_n)
+{
+    return k2_sketch_host(ctx, seqs, rec_off, rec2genome, nrec, ngenomes, kmer_size, drlevel, shuffled_dim, out_hashes, out_stride,
+                          out_n, false);
+}
+
+// one sketch per record of a multi-FASTA: consumer_fasta_task_with_kssd (SketchInfo.cpp:274-433).  rec2genome[r] == r.
+extern "C" int tc_sketch_kssd_seq(tc_ctx *ctx, const uint8_t *seqs, const uint64_t *rec_off, const uint32_t *rec2genome,
+                                  uint64_t nrec, uint32_t ngenomes, int kmer_size, int drlevel, const int32_t *shuffled_dim,
+                                  uint64_t *out_hashes, uint64_t out_stride, uint32_t *out_n)
+{
+    TC_CHECK(nrec == ngenomes, "tc_sketch_kssd_seq: one record per sketch (nrec=%llu, ngenomes=%u)", (unsigned long long)nrec, ngenomes);
+    return k2_sketch_host(ctx, seqs, rec_off, rec2genome, nrec, ngenomes, kmer_size, drlevel, shuffled_dim, out_hashes, out_stride,
+                          out_n, true);
 }
 
 extern "C" uint32_t tc_kssd_needed_stride(void) { return g_kssd_needed; }

@@ -378,8 +378,9 @@ void flush_batch(tc_ctx *ctx, const Options &o, Batch &b, vector<Genome> &out)
         stride = std::max<uint64_t>(1024, (b.longest >> (4 * o.drlevel)) * 2 + 1024);
         for (;;) {
             hashes.assign((size_t)ng * stride, 0);
-            const int rc = tc_sketch_kssd(ctx, b.seq.p, b.rec_off.data(), b.rec2genome.data(), b.rec2genome.size(), ng, o.kmer,
-                                          o.drlevel, g_shuffled_dim.data(), hashes.data(), stride, out_n.data());
+            // list mode: sketchFileWithKssd; one multi-FASTA: the per-record consumer, which treats an odd k differently
+            const int rc = (o.by_file ? tc_sketch_kssd : tc_sketch_kssd_seq)(ctx, b.seq.p, b.rec_off.data(), b.rec2genome.data(),
+                                          b.rec2genome.size(), ng, o.kmer, o.drlevel, g_shuffled_dim.data(), hashes.data(), stride, out_n.data());
             if (!rc) break;
             if (rc == TC_ERR_KSSD_STRIDE && stride < b.longest + 1024) {      // grow to the reported need, not by a guess
                 stride = std::min<uint64_t>(std::max<uint64_t>((uint64_t)tc_kssd_needed_stride() + 64, stride + 1024), b.longest + 1024);
@@ -606,10 +607,10 @@ void sketch_sequences(tc_ctx *ctx, const Options &o, vector<Genome> &out)
     fprintf(stderr, "-----input one file, sketch by sequence: \n");
     if (o.fast) {
         // sketchSequencesWithKssd + consumer_fasta_task_with_kssd (src/SketchInfo.cpp:554-642, 274-433): one KSSD sketch per
-        // record.  For an even k-mer size its window rule (`base > kmerSize`, no tuple reset on a non-ACGT byte) selects
-        // exactly the windows of the list-mode loop, because a window is only used once 2*half_k = kmerSize fresh bases
-        // have been shifted in; the hash SETS are therefore the ones K2 computes per record.  (The reference leaves
-        // them in hash-set iteration order; every consumer treats them as sets, we store them ascending.)
+        // record (tc_sketch_kssd_seq).  For an even k-mer size its window rule (`base > kmerSize`, no tuple reset on a
+        // non-ACGT byte) selects exactly the windows of the list-mode loop; for an odd one the first window after every
+        // gap keeps one stale base and the hash is packed with the un-rounded size -- K2 reproduces both.  (The
+        // reference leaves the sets in hash-set iteration order; every consumer treats them as sets, we store them ascending.)
         const size_t dot = o.input.find_last_of('.');
         const string suf = dot == string::npos ? "" : o.input.substr(dot + 1);
         if (suf != "fasta" && suf != "fna" && suf != "fa") {           // SketchInfo.cpp:555-562
@@ -1203,8 +1204,6 @@ int append_greedy_fast(tc_ctx *ctx, Options &o)
         has_state = load_kssd_state(st, state_file);
     }
     auto sketch_new = [&](vector<Genome> &add, const KssdParams &want) {
-        if (!o.by_file && (o.kmer & 1))
-            die("--fast on a single multi-FASTA needs an even k-mer size in this build (SURVEY.md 8a-9)");
         double t0 = now_s();
         if (o.by_file) sketch_files([&]() { return ctx; }, o, add); else sketch_sequences(ctx, o, add);
         if (g_kssd.half_k != want.half_k || g_kssd.half_subk != want.half_subk || g_kssd.drlevel != want.drlevel)
@@ -1762,10 +1761,6 @@ int main(int argc, char **argv)
     } else {
         if (!o.has_input) { usage(argv[0]); die("option -i/--input or --presketched is required"); }
         if (!(o.fast ? tune_kssd_parameters(o) : tune_parameters(o))) return 1;
-        if (o.fast && !o.by_file && (o.kmer & 1))
-            die("--fast on a single multi-FASTA needs an even k-mer size in this build (k = " + std::to_string(o.kmer) + "): for odd k the "
-                "reference's single-file KSSD consumer keeps one stale base in its window (SURVEY.md 8a-9); use -l/--list or -k " +
-                std::to_string(o.kmer + 1));
         double t0 = now_s();
         if (o.by_file) sketch_files([&]() { need_ctx(); return ctx; }, o, g); else { need_ctx(); sketch_sequences(ctx, o, g); }
         need_ctx();

@@ -333,13 +333,15 @@ def _read_kssd_hash_sketch(path):
     return (pid, half_k, half_subk, drlevel, ng), out
 
 
-def test_clust_mst_fast_single_file_matches_reference(genomes, tmp_path):
+@pytest.mark.parametrize("kflag", [[], ["-k", "17"], ["-k", "15", "--drlevel", "2"]])
+def test_clust_mst_fast_single_file_matches_reference(genomes, tmp_path, kflag):
     """--fast with ONE multi-FASTA (-i without -l; reference: sketchSequencesWithKssd / consumer_fasta_task_with_kssd,
     src/SketchInfo.cpp:274-433,554-642): one KSSD sketch per record.  Same parameter block, same hash SET per record (the
     reference stores them in hash-set iteration order, we ascending), kssd.info.* byte-identical, same MST weights and
-    partition; each binary reads the folder the other wrote."""
+    partition; each binary reads the folder the other wrote.  The tuned k is even (16); -k 17 and -k 15 take the odd-k
+    rule of that consumer (one stale base per reset, un-rounded shift)."""
     _, multi = genomes
-    args = ["--fast", "-i", multi, "-d", "0.05", "-o", "out.txt"]
+    args = ["--fast", "-i", multi, "-d", "0.05", "-o", "out.txt"] + kflag
     rf, rerr = _run(os.path.join(REF, "clust-mst"), ["-t", "1"] + args, str(tmp_path / "ref"))
     of, oerr = _run(os.path.join(OURS, "clust-mst"), args, str(tmp_path / "ours"))
     pr, hr = _read_kssd_hash_sketch(os.path.join(rf, "kssd.hash.sketch"))
@@ -358,7 +360,3 @@ def test_clust_mst_fast_single_file_matches_reference(genomes, tmp_path):
     assert _partition(str(tmp_path / "ref" / "x.txt")) == _partition(ref_out)
     _run(os.path.join(OURS, "clust-mst"), ["--fast", "--presketched", rf, "-d", "0.05", "-o", "pre.txt"], str(tmp_path / "ours"))
     assert _partition(str(tmp_path / "ours" / "pre.txt")) == _partition(ref_out)
-    # an odd k is refused with an explanation (the reference's consumer is off by one base there)
-    r = subprocess.run([os.path.join(OURS, "clust-mst"), "--fast", "-i", multi, "-k", "17", "-d", "0.05", "-o", "odd.txt"],
-                       cwd=str(tmp_path / "ours"), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-    assert r.returncode != 0 and b"even k-mer size" in r.stderr

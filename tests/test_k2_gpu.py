@@ -6,7 +6,7 @@ import struct
 import numpy as np
 import pytest
 
-from rabbittclust_b200 import fasta, synth
+from rabbittclust_b200 import fasta, sketch_io, synth
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -104,3 +104,66 @@ def test_kssd_packed_transport_is_exact(tc, oracle, monkeypatch):
     for a, b in zip(plain, packed):
         assert np.array_equal(a, b)
     assert np.array_equal(packed[0], oracle.kssd_sketch(genomes[0], 18, 3))
+
+
+def _fasta_records(path):
+    recs, cur = [], None
+    for line in open(path, "rb").read().split(b"\n"):
+        if line.startswith(b">"):
+            cur = []
+            recs.append(cur)
+        elif cur is not None:
+            cur.append(line)
+    return [b"".join(r) for r in recs]
+
+
+@pytest.mark.parametrize("k", [13, 15, 16])
+def test_kssd_per_record_mode_matches_reference_golden(ctx, oracle, k):
+    """tc_sketch_kssd_seq against the reference's own clust-mst --fast -i run (tools/make_golden_kssd_seq.py, --drlevel 0:
+    every window is in the sketch): N runs of many lengths, valid runs of k-2..k+2 bases, records shorter than k.  For
+    the odd sizes the first window after every reset keeps one stale base and the shift uses the un-rounded k."""
+    d = os.path.join(GOLD, "kssd_seq")
+    gold = sketch_io.read_kssd_hash_sketch(os.path.join(d, "k%d" % k, "kssd.hash.sketch"))
+    recs = _fasta_records(os.path.join(d, "multi.fa"))
+    assert len(recs) == len(gold["sketches"])
+    got = ctx.sketch_kssd([[r] for r in recs], k, 0, oracle.kssd_shuffled_dim(6), max_hashes=4096, per_record=True)
+    for r, a, b in zip(recs, got, gold["sketches"]):
+        assert np.array_equal(a, b), (len(r), len(a), len(b))
+
+
+@pytest.mark.parametrize("k,drlevel", [(17, 3), (19, 3), (21, 2), (15, 0), (31, 3), (18, 3)])
+def test_kssd_per_record_mode_vs_oracle(ctx, oracle, monkeypatch, k, drlevel):
+    """larger records (several segments per record, several batches): gaps at segment borders, at the start and the end of
+    records, long gaps (the stale base lies far back), lower case, other codes; odd and even k"""
+    monkeypatch.setenv("TCLUST_SKETCH_CHUNK_MB", "1")
+    rng = np.random.default_rng(100 + k)
+    recs = []
+    for r in range(5):
+        b = bytearray(synth.random_genome(int(rng.integers(300000, 900000)), rng))
+        for p in rng.integers(0, len(b) - 5000, 60):
+            L = int(rng.choice([1, 2, k - 1, k, k + 1, 100, 3000]))
+            b[p:p + L] = b"N" * L
+        for p in rng.integers(0, len(b), 40):
+            b[p] = b"RYKMnx-"[int(rng.integers(0, 7))]
+        if r % 2:
+            b[1000:50000] = bytes(b[1000:50000]).lower()
+        if r == 1:
+            b[:7] = b"NNNNNNN"
+        if r == 2:
+            b[-9:] = b"N" * 9
+        # gaps exactly around multiples of the segment width the planner uses (>= 16384 positions, 2048-aligned)
+        for q in (16384, 32768, 65536, 131072, 262144):
+            if q + 40 < len(b):
+                b[q - 3:q - 1] = b"NN"
+                b[q + k - 2:q + k - 1] = b"N"
+        recs.append(bytes(b))
+    recs += [b"ACGT" * 3, synth.random_genome(k - 1, rng), synth.random_genome(k, rng), synth.random_genome(k + 1, rng), b"N" * 50]
+    _, half_subk, _ = oracle.kssd_params(k, drlevel)
+    cap = 1 << 20 if drlevel == 0 else 1 << 16
+    got = ctx.sketch_kssd([[r] for r in recs], k, drlevel, oracle.kssd_shuffled_dim(half_subk), max_hashes=cap, per_record=True)
+    for i, (r, a) in enumerate(zip(recs, got)):
+        want = oracle.kssd_sketch_seq(r, k, drlevel)
+        assert np.array_equal(a, want), (i, len(r), len(a), len(want))
+    if k % 2 == 0:
+        same = ctx.sketch_kssd([[r] for r in recs], k, drlevel, oracle.kssd_shuffled_dim(half_subk), max_hashes=cap)
+        assert all(np.array_equal(a, b) for a, b in zip(got, same))

@@ -363,3 +363,42 @@ def test_greedy_incremental_oracle_properties(oracle):
     reps_half = [q for q in reps if q < half]
     nrep2, rep2 = oracle.greedy_incremental_kssd(sk, 18, 0.05, half, reps_half)
     assert nrep2 == nrep and np.array_equal(rep2, rep[half:])
+
+
+def _multi_fasta_records(path):
+    recs, name, cur = [], None, []
+    for line in open(path, "rb").read().split(b"\n"):
+        if line.startswith(b">"):
+            if name is not None:
+                recs.append((name, b"".join(cur)))
+            name, cur = line[1:].split(b" ")[0].decode(), []
+        else:
+            cur.append(line)
+    recs.append((name, b"".join(cur)))
+    return recs
+
+
+@pytest.mark.parametrize("k", [13, 15, 16])
+def test_kssd_single_file_consumer_golden(oracle, k):
+    """clust-mst --fast -i of the unmodified reference (tools/make_golden_kssd_seq.py): per-record KSSD sketches of one
+    multi-FASTA at --drlevel 0 (every window visible).  k = 13 and 15 are ODD: one stale base in the first window after
+    every reset and the un-rounded shift; k = 16 equals the list-mode loop."""
+    d = os.path.join(GOLD, "kssd_seq")
+    gold = sketch_io.read_kssd_hash_sketch(os.path.join(d, "k%d" % k, "kssd.hash.sketch"))
+    by_file, info = sketch_io.read_kssd_info_sketch(os.path.join(d, "k%d" % k, "kssd.info.sketch"))
+    assert not by_file and gold["half_k"] == (k + 1) // 2 and gold["drlevel"] == 0
+    recs = dict(_multi_fasta_records(os.path.join(d, "multi.fa")))
+    assert len(info) == len(recs) == len(gold["sketches"])
+    nonempty = 0
+    for i, g in zip(info, gold["sketches"]):
+        seq = recs[i["name"]]
+        assert i["length"] == len(seq)
+        mine = oracle.kssd_sketch_seq(seq, k, 0)
+        assert np.array_equal(mine, g), (i["name"], len(mine), len(g))
+        nonempty += len(g) > 0
+        if k % 2 == 0:
+            assert np.array_equal(mine, oracle.kssd_sketch([seq], k, 0))
+    assert nonempty >= 6
+    if k % 2:
+        # the quirk is visible: the list-mode rule on the same records gives different sets
+        assert any(not np.array_equal(oracle.kssd_sketch([recs[i["name"]]], k, 0), g) for i, g in zip(info, gold["sketches"]))
