@@ -347,6 +347,11 @@ int tc_greedy_cluster_kssd(tc_ctx *ctx, int kmer_size, double threshold, int32_t
  * on the table's heap address, not reproducible); this call takes the earliest-created representative. */
 int tc_greedy_incremental_kssd(tc_ctx *ctx, int kmer_size, double threshold, uint32_t start_index, const uint32_t *rep_ids,
                                uint32_t n_reps, int32_t *rep_of, uint32_t *n_clusters);
+/* MinHashIncrementalCluster (src/greedy.cpp:1963-2130; caller: append_clust_greedy with a saved state,
+ * src/sub_command.cpp:97-190): as above for MinHash sketches -- no size-ratio filter; containment != 0 uses
+ * floor(jmin * min(|A|,|B|)) as the common-hash filter and common / min(|A|,|B|) as the Jaccard. */
+int tc_greedy_incremental(tc_ctx *ctx, int kmer_size, int containment, double threshold, uint32_t start_index,
+                          const uint32_t *rep_ids, uint32_t n_reps, int32_t *rep_of, uint32_t *n_clusters);
 
 /* The same two rules with the representative scan sharded over several GPUs (the outer loop over the
  * genomes is serial, the scan of one batch against the representatives is not): ctxs[0..nctx) are contexts, one per

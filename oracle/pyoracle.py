@@ -69,6 +69,8 @@ def lib():
         L.oc_greedy_inverted.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_int, C.c_double, i32p]
         L.oc_greedy_incremental_kssd.restype = C.c_int
         L.oc_greedy_incremental_kssd.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_double, C.c_int, i32p, C.c_int, i32p]
+        L.oc_greedy_incremental_minhash.restype = C.c_int
+        L.oc_greedy_incremental_minhash.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, i32p, C.c_int, i32p]
         L.oc_common_B.restype = C.c_uint32
         L.oc_common_B.argtypes = [u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint64, u32p]
         L.oc_contain_distance.restype = C.c_double
@@ -274,6 +276,17 @@ def greedy_incremental_kssd(sketches, k, threshold, start, seeds):
     sd = np.ascontiguousarray(seeds, np.int32)
     nc = lib().oc_greedy_incremental_kssd(_p(h, C.c_uint64), _p(off, C.c_uint64), n, k, threshold, start,
                                           _p(sd, C.c_int32), len(sd), _p(rep, C.c_int32))
+    return nc, rep[start:n]
+
+
+def greedy_incremental_minhash(sketches, k, threshold, start, seeds, containment=False):
+    """MinHashIncrementalCluster: (number of representatives afterwards, rep_of[start:])."""
+    h, off = pack_sketches(sketches)
+    n = len(sketches)
+    rep = np.full(max(n, 1), -1, np.int32)
+    sd = np.ascontiguousarray(seeds, np.int32)
+    nc = lib().oc_greedy_incremental_minhash(_p(h, C.c_uint64), _p(off, C.c_uint64), n, k, int(containment), threshold, start,
+                                             _p(sd, C.c_int32), len(sd), _p(rep, C.c_int32))
     return nc, rep[start:n]
 
 

@@ -563,6 +563,59 @@ int oc_greedy_incremental_kssd(const uint64_t *hashes, const uint64_t *off, int 
     return nrep;
 }
 
+/* MinHashIncrementalCluster (greedy.cpp:1963-2130) with one thread: as oc_greedy_incremental_kssd without the size-ratio
+ * filter and with the containment forms (:2057-2077).  Same tie rule (earliest-created representative). */
+int oc_greedy_incremental_minhash(const uint64_t *hashes, const uint64_t *off, int N, int k, int containment,
+                                  double threshold, int start, const int32_t *seed, int n_seed, int32_t *rep_of)
+{
+    int *reps = (int *)malloc(sizeof(int) * (size_t)(N > 0 ? N : 1)), nrep = 0;
+    for (int r = 0; r < n_seed; r++) reps[nrep++] = seed[r];
+    const double x = exp(-threshold * k);                             /* :2000-2001 */
+    const double jaccard_min = x / (2.0 - x);
+    for (int q = start; q < N; q++) {
+        const uint64_t *hq = hashes + off[q];
+        const int sizeQry = (int)(off[q + 1] - off[q]);
+        double best_dist = 1.7976931348623157e308;
+        int best = -1;
+        for (int r = 0; r < nrep; r++) {
+            const int id = reps[r];
+            const int sizeRef = (int)(off[id + 1] - off[id]);
+            uint32_t fh;
+            const int common = (int)oc_intersect_u64(hq, sizeQry, hashes + off[id], sizeRef, &fh);
+            if (common == 0 || sizeRef == 0) continue;
+            int min_common_needed;
+            if (containment) {
+                const int minSz = sizeQry < sizeRef ? sizeQry : sizeRef;
+                min_common_needed = (int)(jaccard_min * minSz);
+            } else {
+                min_common_needed = (int)(jaccard_min * (sizeQry + sizeRef) / (1.0 + jaccard_min));
+            }
+            if (common < min_common_needed) continue;
+            double jaccard;
+            if (containment) {
+                const int minSz = sizeQry < sizeRef ? sizeQry : sizeRef;
+                jaccard = (double)common / minSz;
+            } else {
+                const int denom = sizeQry + sizeRef - common;
+                if (denom == 0) continue;
+                jaccard = (double)common / denom;
+            }
+            double dist;
+            if (jaccard >= 1.0) dist = 0.0;
+            else if (jaccard <= 0.0) dist = 1.0;
+            else {
+                dist = -log(2.0 * jaccard / (1.0 + jaccard)) / k;
+                if (dist > 1.0) dist = 1.0;
+            }
+            if (dist <= threshold && dist < best_dist) { best_dist = dist; best = r; }
+        }
+        if (best != -1) rep_of[q] = reps[best];
+        else { reps[nrep++] = q; rep_of[q] = q; }
+    }
+    free(reps);
+    return nrep;
+}
+
 /* ------------------------------------------------- semantic B brute-force callers */
 /* MinHash::jaccard as integers: common among the first sketch_size union elements and the
  * completed denominator (MinHash.cpp:982-1101, scalar form :1199-1229). */

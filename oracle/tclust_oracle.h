@@ -98,6 +98,10 @@ int oc_greedy_inverted(const uint64_t *hashes, const uint64_t *off, int N, int k
 int oc_greedy_incremental_kssd(const uint64_t *hashes, const uint64_t *off, int N, int k, double threshold,
                                int start, const int32_t *seed, int n_seed, int32_t *rep_of);
 
+/* MinHashIncrementalCluster with -t 1 (greedy.cpp:1963-2130): no size-ratio filter, containment forms */
+int oc_greedy_incremental_minhash(const uint64_t *hashes, const uint64_t *off, int N, int k, int containment,
+                                  double threshold, int start, const int32_t *seed, int n_seed, int32_t *rep_of);
+
 /* ---- semantic B (the brute-force fallbacks) ---------------------------------------- */
 /* integer form of MinHash::jaccard (MinHash.cpp:982-1101): common among the first
  * sketch_size union elements; *denom_out = completed/capped denominator. */

@@ -23,7 +23,7 @@ SYMBOLS = [
     "tc_sketches_upload", "tc_sketches_upload_dev", "tc_sketches_upload_rows", "tc_pair_common", "tc_allpairs_pass",
     "tc_edges_download", "tc_boruvka_upload_comp", "tc_boruvka_phase1", "tc_boruvka_phase2", "tc_boruvka_set_async", "tc_mst",
     "tc_greedy_scan", "tc_greedy_cluster",
-    "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce", "tc_greedy_cluster_kssd", "tc_greedy_incremental_kssd", "tc_dense_ani", "tc_allpairs_pass_from", "tc_mst_append",
+    "tc_pair_common_b", "tc_allpairs_pass_b", "tc_mst_bruteforce", "tc_greedy_cluster_bruteforce", "tc_greedy_cluster_kssd", "tc_greedy_incremental_kssd", "tc_greedy_incremental", "tc_dense_ani", "tc_allpairs_pass_from", "tc_mst_append",
     "tc_jaccard_b", "tc_distance_b", "tc_contain_distance",
     "tc_mash_dist", "tc_aaf_dist", "tc_dist_from_key", "tc_radio", "tc_greedy_common_min", "tc_greedy_dist",
     "tc_mg_export", "tc_mg_join", "tc_mg_leave", "tc_mg_rank", "tc_mst_stats", "tc_mst_of_edges", "tc_cluster_threshold", "tc_labels_merge", "tc_greedy_cluster_multi", "tc_kssd_needed_stride", "tc_upload_sort_share_dev", "tc_sketches_upload_runs_dev", "tc_last_h2d_bytes", "tc_vr_partition_dev", "tc_vr_partition32_dev", "tc_vr_local_ranks_dev", "tc_vr_scatter_ranks_dev",
@@ -92,6 +92,7 @@ def lib():
     L.tc_greedy_cluster_bruteforce.argtypes = [vp, C.c_int, C.c_uint32, C.c_int, C.c_double, i32p, u32p]
     L.tc_greedy_cluster_kssd.argtypes = [vp, C.c_int, C.c_double, i32p, u32p]
     L.tc_greedy_incremental_kssd.argtypes = [vp, C.c_int, C.c_double, C.c_uint32, u32p, C.c_uint32, i32p, u32p]
+    L.tc_greedy_incremental.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_uint32, u32p, C.c_uint32, i32p, u32p]
     L.tc_allpairs_pass_from.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u64p]
     L.tc_mst_append.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_uint32, vp, C.c_uint64, vp, u64p]
     L.tc_dense_ani.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, u64p]
@@ -323,6 +324,15 @@ class Context:
         ids = np.ascontiguousarray(rep_ids, np.uint32)
         nc = C.c_uint32(0)
         _chk(lib().tc_greedy_incremental_kssd(self._h, k, threshold, start_index, _p(ids, C.c_uint32), len(ids), _p(rep, C.c_int32), C.byref(nc)))
+        return int(nc.value), rep[start_index:self.n].copy()
+
+    def greedy_incremental(self, k, threshold, start_index, rep_ids, containment=False):
+        """MinHashIncrementalCluster: (#representatives afterwards, rep_of[start_index:n])."""
+        rep = np.full(max(self.n, 1), -1, np.int32)
+        ids = np.ascontiguousarray(rep_ids, np.uint32)
+        nc = C.c_uint32(0)
+        _chk(lib().tc_greedy_incremental(self._h, k, int(containment), threshold, start_index, _p(ids, C.c_uint32), len(ids),
+                                         _p(rep, C.c_int32), C.byref(nc)))
         return int(nc.value), rep[start_index:self.n].copy()
 
     def allpairs_pass(self, radio, part=0, nparts=1):

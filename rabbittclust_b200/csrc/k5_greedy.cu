@@ -200,7 +200,8 @@ extern "C" int tc_greedy_scan(tc_ctx *ctx, uint32_t q0, uint32_t q1, const uint3
 //                strictly smaller distance wins) or founds a cluster.  The reference walks its candidates in the
 //                iteration order of a phmap::flat_hash_map<int,int>, which depends on the table's heap address, so
 //                its choice among EQUAL distances is not reproducible even by itself; here the earliest-created
-//                representative wins a tie.
+//                representative wins a tie.  kssd = false with incr: MinHashIncrementalCluster (greedy.cpp:1963-2130), the
+//                same walk without the size-ratio filter and with the containment forms of the filter and the distance.
 static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment, double threshold, bool brute, uint32_t semb_size,
                        int32_t *rep_of, uint32_t *n_clusters, bool kssd = false, bool incr = false, uint32_t incr_start = 0,
                        const uint32_t *seed = nullptr, uint32_t n_seed = 0)
@@ -214,7 +215,7 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
                  "tc_greedy_cluster_multi: context %d does not hold the same sketch set as context 0", r);
     // fixed-size fast path detection over the first 100 sketches (greedy.cpp:1092-1103)
     const int fixed_size = (int)ctx->h_size[0];
-    bool all_fixed = !containment && !brute && !kssd;
+    bool all_fixed = !containment && !brute && !kssd && !incr;
     if (brute && containment) semb_size = 0;   // containDistance counts the full intersection
     for (uint32_t i = 1; i < std::min<uint32_t>(100, n) && all_fixed; i++)
         if ((int)ctx->h_size[i] != fixed_size) all_fixed = false;
@@ -363,13 +364,18 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
                     if (dist <= threshold && dist < best_dist) { best_dist = dist; best_rep = (int)c->rep; }
                     continue;
                 }
-                if (incr) {   // greedy.cpp:1812-1846; sizeQry = the new sketch, sizeRef = the representative
+                if (incr) {   // greedy.cpp:1812-1846 (KSSD), :2049-2094 (MinHash); sizeQry = the new sketch, sizeRef = the representative
                     const int sizeQry = size_ref, sizeRef = size_qry;
-                    const double ratio = (double)sizeQry / sizeRef;
-                    if (ratio > max_ratio || ratio < 1.0 / max_ratio) continue;
-                    const int min_common_needed = (int)(jmin * (sizeQry + sizeRef) / (1.0 + jmin));
+                    if (sizeRef == 0) continue;
+                    if (kssd) {
+                        const double ratio = (double)sizeQry / sizeRef;
+                        if (ratio > max_ratio || ratio < 1.0 / max_ratio) continue;
+                    }
+                    const int min_common_needed = containment ? (int)(jmin * std::min(sizeQry, sizeRef))
+                                                              : (int)(jmin * (sizeQry + sizeRef) / (1.0 + jmin));
                     if (common < min_common_needed) continue;
-                    const double dist = tc_greedy_dist(common, sizeRef, sizeQry, 0, kmer_size);   // calculate_mash_distance, :103-160
+                    // calculate_mash_distance (:103-160) / the inline form of :2069-2085: the same expression
+                    const double dist = tc_greedy_dist(common, sizeRef, sizeQry, containment, kmer_size);
                     if (dist <= threshold && dist < best_dist) { best_dist = dist; best_rep = (int)c->rep; }
                     continue;
                 }
@@ -422,6 +428,14 @@ extern "C" int tc_greedy_incremental_kssd(tc_ctx *ctx, int kmer_size, double thr
 {
     TC_CHECK(rep_of, "tc_greedy_incremental_kssd: rep_of is null");
     return greedy_impl(&ctx, 1, kmer_size, 0, threshold, false, 0, rep_of, n_clusters, true, true, start_index, rep_ids, n_reps);
+}
+
+extern "C" int tc_greedy_incremental(tc_ctx *ctx, int kmer_size, int containment, double threshold, uint32_t start_index,
+                                     const uint32_t *rep_ids, uint32_t n_reps, int32_t *rep_of, uint32_t *n_clusters)
+{
+    TC_CHECK(rep_of, "tc_greedy_incremental: rep_of is null");
+    TC_CHECK(containment == 0 || containment == 1, "tc_greedy_incremental: containment must be 0 or 1");
+    return greedy_impl(&ctx, 1, kmer_size, containment, threshold, false, 0, rep_of, n_clusters, false, true, start_index, rep_ids, n_reps);
 }
 
 extern "C" int tc_greedy_cluster_multi(tc_ctx *const *ctxs, int nctx, int kmer_size, int containment, double threshold, int kssd,

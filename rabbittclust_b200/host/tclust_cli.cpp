@@ -69,6 +69,7 @@ struct Genome {          // SketchInfo (src/SketchInfo.h:23-36) without the owni
     uint64_t total_len = 0;   // list mode: sum of record lengths; single-file mode: record length
     vector<uint64_t> hashes;
     int id = 0;
+    uint32_t ssize = 0;       // the sketch-size argument its MinHash object was built with (getSketchSize(): state files)
 };
 
 struct Options {
@@ -577,6 +578,7 @@ void sketch_files(const std::function<tc_ctx *()> &get_ctx, const Options &o, ve
             }
             for (const Record &r : p.recs) { b.rec_off.push_back(base + r.end); b.rec2genome.push_back(gi); }
             b.ssize.push_back(o.containment ? (uint32_t)std::max(p.file_len / o.compress, 100) : (uint32_t)o.sketch_size);
+            g.ssize = b.ssize.back();
             b.longest = std::max<uint64_t>(b.longest, total_len);
             b.genomes.push_back(std::move(g));
             if (b.seq.size() >= batch_bytes) { const double tw = now_s(); drain_copies(); feeder.submit(); t_wait_gpu += now_s() - tw; }
@@ -640,6 +642,7 @@ void sketch_sequences(tc_ctx *ctx, const Options &o, vector<Genome> &out)
         b.seq.append(seq.data() + r.begin, len);
         b.rec_off.push_back(b.seq.size()); b.rec2genome.push_back(gi);
         b.ssize.push_back(o.containment ? (uint32_t)std::max((int)len / o.compress, 100) : (uint32_t)o.sketch_size);
+        g.ssize = b.ssize.back();
         b.longest = std::max<uint64_t>(b.longest, len);
         b.genomes.push_back(std::move(g));
         if (b.seq.size() >= (1ull << 29)) feeder.submit();
@@ -736,6 +739,7 @@ bool load_sketches(vector<Genome> &g, const string &folder, Options &o)
         if (!rd(fp, n)) die("loadSketches(), truncated " + path);
         x.hashes.resize(n);
         if (n && fread(x.hashes.data(), 8, n, fp) != n) die("loadSketches(), truncated " + path);
+        x.ssize = (uint32_t)param;               // new MinHash(kmer_size, contain_compress | sketch_size), Sketch_IO.cpp:333-340
     }
     fclose(fp);
     return by_file;
@@ -1190,6 +1194,168 @@ bool load_kssd_state(KssdState &s, const string &path)
     return true;
 }
 
+// MinHashClusterState (src/greedy.h:84-112) and its cluster_state.bin (MinHashClusterState::save / load,
+// src/greedy.cpp:2134-2290): "MINHASH\0", threshold, kmer_size, sketch_size, bool is_containment; representative ids; every
+// sketch {int id, u64 totalSeqLength, size_t n, u64 hashes[n], size_t nameLen, fileName} (the loader skips them: the
+// sketches are reloaded from the folder); the clusters; the hash -> representative-number index (no marker here).
+struct MinHashState {
+    double threshold = 0.0; int kmer_size = 0, sketch_size = 0; bool containment = false;
+    vector<int> rep_ids; vector<vector<int>> clusters;
+};
+
+bool save_minhash_state(const MinHashState &s, const vector<Genome> &all, const string &path)
+{
+    FILE *fp = fopen(path.c_str(), "wb");
+    if (!fp) { cerr << "ERROR: Cannot open file for writing: " << path << endl; return false; }
+    const char magic[8] = {'M', 'I', 'N', 'H', 'A', 'S', 'H', '\0'};
+    fwrite(magic, 1, 8, fp);
+    wr(fp, s.threshold); wr(fp, s.kmer_size); wr(fp, s.sketch_size); wr(fp, s.containment);
+    wr(fp, (size_t)s.rep_ids.size());
+    fwrite(s.rep_ids.data(), sizeof(int), s.rep_ids.size(), fp);
+    wr(fp, (size_t)all.size());
+    for (const Genome &x : all) {
+        wr(fp, x.id); wr(fp, (uint64_t)x.total_len);
+        wr(fp, (size_t)x.hashes.size());
+        fwrite(x.hashes.data(), 8, x.hashes.size(), fp);
+        wr(fp, (size_t)x.file_name.size());
+        fwrite(x.file_name.data(), 1, x.file_name.size(), fp);
+    }
+    wr(fp, (size_t)s.clusters.size());
+    for (const vector<int> &c : s.clusters) { wr(fp, (size_t)c.size()); fwrite(c.data(), sizeof(int), c.size(), fp); }
+    vector<std::pair<uint64_t, int>> post;
+    for (size_t r = 0; r < s.rep_ids.size(); r++) for (uint64_t h : all[s.rep_ids[r]].hashes) post.emplace_back(h, (int)r);
+    std::sort(post.begin(), post.end());
+    size_t distinct = 0;
+    for (size_t a = 0; a < post.size(); a++) distinct += a == 0 || post[a].first != post[a - 1].first;
+    wr(fp, distinct);
+    cerr << "Saving inverted index: " << distinct << " unique hashes..." << endl;
+    for (size_t a = 0; a < post.size();) {
+        size_t b = a;
+        while (b < post.size() && post[b].first == post[a].first) b++;
+        wr(fp, post[a].first); wr(fp, (size_t)(b - a));
+        for (size_t e = a; e < b; e++) wr(fp, post[e].second);
+        a = b;
+    }
+    const bool ok = !ferror(fp);
+    fclose(fp);
+    cerr << "Saved clustering state to: " << path << endl;
+    cerr << "  - " << all.size() << " genomes" << endl;
+    cerr << "  - " << s.rep_ids.size() << " clusters (representatives)" << endl;
+    cerr << "  - " << distinct << " unique hashes in inverted index" << endl;
+    return ok;
+}
+
+bool load_minhash_state(MinHashState &s, const string &path)
+{
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (!fp) { cerr << "ERROR: Cannot open file for reading: " << path << endl; return false; }
+    auto bad = [&]() { fclose(fp); cerr << "ERROR: " << path << " is truncated or not a MinHash cluster state" << endl; return false; };
+    char magic[8];
+    if (fread(magic, 1, 8, fp) != 8 || strncmp(magic, "MINHASH", 8) != 0) {
+        fclose(fp);
+        cerr << "ERROR: Invalid file format (not a MinHash cluster state)" << endl;
+        return false;
+    }
+    if (!rd(fp, s.threshold) || !rd(fp, s.kmer_size) || !rd(fp, s.sketch_size) || !rd(fp, s.containment)) return bad();
+    size_t nrep = 0, nsk = 0, ncl = 0;
+    if (!rd(fp, nrep) || nrep > ((size_t)1 << 31)) return bad();
+    s.rep_ids.resize(nrep);
+    if (nrep && fread(s.rep_ids.data(), sizeof(int), nrep, fp) != nrep) return bad();
+    if (!rd(fp, nsk) || nsk > ((size_t)1 << 31)) return bad();
+    for (size_t i = 0; i < nsk; i++) {                     // skipped: the sketches are reloaded from the folder (greedy.cpp:2232-2250)
+        int id; uint64_t len; size_t nh = 0, nl = 0;
+        if (!rd(fp, id) || !rd(fp, len) || !rd(fp, nh) || nh > ((size_t)1 << 32) || fseek(fp, (long)(nh * 8), SEEK_CUR) != 0) return bad();
+        if (!rd(fp, nl) || nl > ((size_t)1 << 20) || fseek(fp, (long)nl, SEEK_CUR) != 0) return bad();
+    }
+    if (!rd(fp, ncl) || ncl > ((size_t)1 << 31)) return bad();
+    s.clusters.assign(ncl, vector<int>());
+    for (vector<int> &c : s.clusters) {
+        size_t m = 0;
+        if (!rd(fp, m) || m > ((size_t)1 << 31)) return bad();
+        c.resize(m);
+        if (m && fread(c.data(), sizeof(int), m, fp) != m) return bad();
+    }
+    fclose(fp);
+    cerr << "Loaded clustering state from: " << path << endl;
+    cerr << "  - " << nsk << " genomes" << endl;
+    cerr << "  - " << nrep << " clusters (representatives)" << endl;
+    return true;
+}
+
+// append_clust_greedy with a saved state (src/sub_command.cpp:97-190): true when the state was found and used
+bool append_greedy_minhash_state(tc_ctx *ctx, Options &o)
+{
+    const string state_file = o.folder + "/cluster_state.bin";
+    struct stat sb;
+    if (stat(state_file.c_str(), &sb) != 0) return false;
+    cerr << "===== Incremental Update Mode (MinHash) =====" << endl;
+    cerr << "Found existing cluster state, loading..." << endl;
+    MinHashState st;
+    if (!load_minhash_state(st, state_file)) return false;          // the reference falls back to the classic append
+    cerr << "---the threshold is: " << o.threshold << endl;
+    cerr << "---the thread number is: " << o.threads << endl;
+    // the sketches come from the folder again, in the folder's order (:101-104); the representatives must lie in it
+    vector<Genome> all;
+    const bool pre_by_file = load_sketches(all, o.folder, o);        // also sets o.kmer / o.containment / o.compress / o.sketch_size
+    if (pre_by_file != o.by_file) cerr << "Warning: the input format of append genomes and pre-sketched genome is not same" << endl;
+    for (int r : st.rep_ids)
+        if (r < 0 || (size_t)r >= all.size()) {
+            cerr << "ERROR: Representative ID " << r << " out of range [0, " << all.size() << "), cannot continue" << endl;
+            exit(1);
+        }
+    cerr << "Successfully loaded " << st.rep_ids.size() << " representatives" << endl;
+    if (st.kmer_size <= 0 || st.sketch_size <= 0) {
+        cerr << "ERROR: Invalid kmer_size or sketch_size: kmer=" << st.kmer_size << ", sketch=" << st.sketch_size << endl;
+        exit(1);
+    }
+    if (st.containment && o.compress <= 0) { cerr << "ERROR: is_containment is true but contain_compress is " << o.compress << endl; exit(1); }
+    if (st.clusters.size() != st.rep_ids.size()) die(state_file + " holds " + std::to_string(st.clusters.size()) + " clusters for " +
+                                                     std::to_string(st.rep_ids.size()) + " representatives");
+    cerr << "Computing sketches for new genomes..." << endl;
+    cerr << "  Parameters: kmer_size=" << st.kmer_size << ", sketch_size=" << st.sketch_size << ", is_containment=" << st.containment
+         << ", contain_compress=" << o.compress << endl;
+    o.kmer = st.kmer_size; o.sketch_size = st.sketch_size; o.containment = st.containment;
+    vector<Genome> add;
+    if (o.by_file) sketch_files([&]() { return ctx; }, o, add); else sketch_sequences(ctx, o, add);
+    cerr << "New genomes sketched: " << add.size() << endl;
+    if (add.empty()) { cerr << "ERROR: No new sketches generated" << endl; return true; }
+    cerr << "Starting incremental clustering..." << endl;
+    const uint32_t n_old = (uint32_t)all.size();
+    for (Genome &x : add) all.push_back(std::move(x));
+    const uint32_t n = (uint32_t)all.size();
+    upload(ctx, all);
+    vector<uint32_t> seeds(st.rep_ids.begin(), st.rep_ids.end());
+    vector<int32_t> rep_of(n, -1);
+    uint32_t nclust = 0;
+    tc_or_die(tc_greedy_incremental(ctx, st.kmer_size, st.containment, st.threshold, n_old, seeds.data(), (uint32_t)seeds.size(),
+                                    rep_of.data(), &nclust), "incremental greedy clustering");
+    vector<int> cid(n, -1);
+    for (size_t r = 0; r < st.rep_ids.size(); r++) cid[st.rep_ids[r]] = (int)r;
+    int n_new = 0, n_assigned = 0;
+    for (uint32_t q = n_old; q < n; q++) {
+        if (rep_of[q] == (int32_t)q) {          // opens an EMPTY cluster, as in the KSSD flow (greedy.cpp:2099-2104)
+            cid[q] = (int)st.clusters.size();
+            st.rep_ids.push_back((int)q);
+            st.clusters.emplace_back();
+            n_new++;
+        } else {
+            st.clusters[cid[rep_of[q]]].push_back((int)q);
+            n_assigned++;
+        }
+    }
+    cerr << "\n===== Incremental Clustering Results =====" << endl;
+    cerr << "Assigned to existing clusters: " << n_assigned << endl;
+    cerr << "New clusters created: " << n_new << endl;
+    cerr << "Total clusters now: " << st.clusters.size() << endl;
+    cerr << "Incremental clustering completed" << endl;
+    if (!o.no_save && o.save_rep) save_minhash_state(st, all, state_file);
+    print_result(st.clusters, all, o.by_file, o.output, -1.0);
+    cerr << "-----write the cluster result into: " << o.output << endl;
+    cerr << "-----the cluster number of " << o.output << " is: " << st.clusters.size() << endl;
+    cerr << "-----updated cluster state saved" << endl;
+    return true;
+}
+
 // append_clust_greedy_fast (src/sub_command.cpp:192-276)
 int append_greedy_fast(tc_ctx *ctx, Options &o)
 {
@@ -1340,6 +1506,15 @@ void run_clustering(tc_ctx *ctx, vector<Genome> &g, const Options &o, bool by_fi
     for (int j = 0; j < (int)g.size(); j++) {
         if (rep_of[j] == j) { cid[j] = (int)cluster.size(); cluster.push_back({j}); }
         else cluster[cid[rep_of[j]]].push_back(j);
+    }
+    if (!o.fast && o.save_rep && (save || o.presketched)) {
+        // MinHashInitialClusterWithState + state.save (sub_command.cpp:2673-2679, 2904-2910)
+        MinHashState st;
+        st.threshold = o.threshold; st.kmer_size = o.kmer; st.sketch_size = (int)g[0].ssize; st.containment = o.containment;
+        st.clusters = cluster;
+        for (const vector<int> &c : cluster) st.rep_ids.push_back(c[0]);
+        const string state_file = folder + "/cluster_state.bin";
+        if (save_minhash_state(st, g, state_file)) cerr << "-----saved cluster state (with inverted index) to: " << state_file << endl;
     }
     if (o.fast && o.save_rep && (save || o.presketched)) {
         // KssdInitialClusterWithState + state.save (sub_command.cpp:1962-1968, 2485-2490): the clusters just built, in the
@@ -1565,9 +1740,6 @@ int main(int argc, char **argv)
     if (!o.has_threshold) cerr << "-----use default threshold: " << o.threshold << endl;
     if (o.fast && (o.drlevel < 0 || o.drlevel > 8)) { cerr << "ERROR: invalid drlevel " << o.drlevel << ", should be in [0, 8]" << endl; return 1; }
 #ifdef GREEDY_CLUST
-    if (o.save_rep && !o.fast)
-        die("--save-rep without --fast is not part of this build: the MinHash cluster state (MinHashClusterState, src/greedy.cpp:1904-2130) "
-            "is not built; see DESIGN.md section 8");
 #else
     if (o.save_rep)
         die("clust-mst --save-rep is not part of this build: the MST medoid state (src/mst_state.cpp) is not built; see DESIGN.md section 8");
@@ -1670,6 +1842,7 @@ int main(int argc, char **argv)
 #endif
 #ifdef GREEDY_CLUST
         if (!o.presketched) { cerr << "ERROR option --append, option --presketched needed" << endl; return 1; }
+        if (append_greedy_minhash_state(ctx, o)) { tc_ctx_destroy(ctx); return 0; }      // a saved cluster_state.bin: incremental
 #else
         if (!o.presketched && !o.premsted) { cerr << "ERROR option --append, option --presketched or --premsted needed" << endl; return 1; }
 #endif

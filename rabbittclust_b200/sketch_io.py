@@ -187,6 +187,40 @@ def read_kssd_cluster_state(path):
             "genome_number": gn, "rep_ids": rep_ids, "sketches": sk, "clusters": clusters, "index": index}
 
 
+def read_minhash_cluster_state(path):
+    """cluster_state.bin of clust-greedy --save-rep (MinHashClusterState::save, greedy.cpp:2134-2205) ->
+    dict(threshold, kmer_size, sketch_size, containment, rep_ids, sketches=[dict(id, length, hashes, file)], clusters,
+    index={hash: [representative numbers]})."""
+    with open(path, "rb") as f:
+        data = f.read()
+    assert data[:8] == b"MINHASH\0", "not a MinHash cluster state: " + path
+    thr, k, ssz, cont = struct.unpack_from("<dii?", data, 8)
+    pos = 8 + 17
+    (nrep,) = struct.unpack_from("<Q", data, pos); pos += 8
+    rep_ids = list(struct.unpack_from("<%di" % nrep, data, pos)); pos += 4 * nrep
+    (nsk,) = struct.unpack_from("<Q", data, pos); pos += 8
+    sk = []
+    for _ in range(nsk):
+        gid, length, nh = struct.unpack_from("<iQQ", data, pos); pos += 20
+        h = np.frombuffer(data, "<u8", nh, pos).copy(); pos += 8 * nh
+        (nl,) = struct.unpack_from("<Q", data, pos); pos += 8
+        fn = data[pos:pos + nl].decode(); pos += nl
+        sk.append({"id": gid, "length": length, "hashes": h, "file": fn})
+    (ncl,) = struct.unpack_from("<Q", data, pos); pos += 8
+    clusters = []
+    for _ in range(ncl):
+        (m,) = struct.unpack_from("<Q", data, pos); pos += 8
+        clusters.append(list(struct.unpack_from("<%di" % m, data, pos))); pos += 4 * m
+    (nidx,) = struct.unpack_from("<Q", data, pos); pos += 8
+    index = {}
+    for _ in range(nidx):
+        h, m = struct.unpack_from("<QQ", data, pos); pos += 16
+        index[h] = list(struct.unpack_from("<%di" % m, data, pos)); pos += 4 * m
+    assert pos == len(data), "trailing bytes in " + path
+    return {"threshold": thr, "kmer_size": k, "sketch_size": ssz, "containment": bool(cont), "rep_ids": rep_ids,
+            "sketches": sk, "clusters": clusters, "index": index}
+
+
 def read_edge_mst(path):
     with open(path, "rb") as f:
         data = f.read()

@@ -235,3 +235,27 @@ def test_greedy_incremental_kssd_rejects_bad_seeds(ctx, tc):
         ctx.greedy_incremental_kssd(18, 0.05, 4, [5])          # a representative must lie before start_index
     with pytest.raises(tc.TclustError):
         ctx.greedy_incremental_kssd(18, 0.05, 4, [1, 1])       # listed twice
+
+
+@pytest.mark.parametrize("contain", [False, True])
+@pytest.mark.parametrize("batch", ["32", "4096"])
+def test_greedy_incremental_minhash_vs_oracle(ctx, oracle, monkeypatch, contain, batch):
+    """tc_greedy_incremental (MinHashIncrementalCluster, greedy.cpp:1963-2130) against the oracle's restatement (pinned to
+    the reference's saved states): fixed-size Mash sketches and ragged containment sketches, seeded with the
+    representatives of a plain greedy pass over the first half."""
+    monkeypatch.setenv("TCLUST_GREEDY_BATCH", batch)
+    if contain:
+        sk = synth.family_sketches(10, 20, seed=8, ragged=(100, 4000), keep_lo=0.3, keep_hi=1.0)
+    else:
+        sk = synth.family_sketches(12, 25, s=1000, seed=5, keep_lo=0.3, keep_hi=1.0)
+    rng = np.random.default_rng(2)
+    sk = [sk[i] for i in rng.permutation(len(sk))]
+    n, half = len(sk), len(sk) // 2
+    _, rep0 = oracle.greedy(sk[:half], 21, 0.05, contain)
+    seeds = [q for q in range(half) if rep0[q] == q]
+    want_n, want = oracle.greedy_incremental_minhash(sk, 21, 0.05, half, seeds, contain)
+    ctx.upload(sk)
+    got_n, got = ctx.greedy_incremental(21, 0.05, half, seeds, contain)
+    assert got_n == want_n
+    assert np.array_equal(got, want)
+    assert (got != np.arange(half, n)).any() and got_n >= len(seeds)

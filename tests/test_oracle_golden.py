@@ -402,3 +402,33 @@ def test_kssd_single_file_consumer_golden(oracle, k):
     if k % 2:
         # the quirk is visible: the list-mode rule on the same records gives different sets
         assert any(not np.array_equal(oracle.kssd_sketch([recs[i["name"]]], k, 0), g) for i, g in zip(info, gold["sketches"]))
+
+
+@pytest.mark.parametrize("tag,contain", [("s", False), ("c", True)])
+def test_append_golden_greedy_minhash_state(oracle, tag, contain):
+    """clust-greedy --save-rep on 9 genomes, then --append --save-rep of 7 from the saved state (append_clust_greedy,
+    sub_command.cpp:97-190; MinHashIncrementalCluster, greedy.cpp:1963-2130), both by the unmodified reference
+    (tools/make_golden_append.py).  The oracle's restatement reproduces the increment from the saved state."""
+    import json
+    d = os.path.join(GOLD, "append", "greedy_minhash", tag)
+    s0 = json.load(open(os.path.join(d, "state_base.json")))
+    s1 = json.load(open(os.path.join(d, "state_app.json")))
+    base = sketch_io.read_hash_sketch(os.path.join(d, "hash.sketch"))
+    assert base["containment"] == contain and s0["containment"] == contain and s0["kmer_size"] == base["k"] == 15
+    assert len(base["sketches"]) == 9 == len(s0["sketches"]) and len(s1["sketches"]) == 16
+    # the state of the base run: the clusters of base.txt, first member = representative
+    base_clusters = [[gid for gid, _ in c] for c in sketch_io.parse_cluster_file(os.path.join(d, "base.txt"))]
+    assert s0["clusters"] == base_clusters and s0["rep_ids"] == [c[0] for c in base_clusters]
+    # all 16 sketches at these parameters: the committed all-at-once runs of the same genome list
+    full = sketch_io.read_hash_sketch(os.path.join(GOLD, "greedy_list_%s" % tag, "hash.sketch"))
+    by_len = {}
+    _, info = sketch_io.read_info_sketch(os.path.join(GOLD, "greedy_list_%s" % tag, "info.sketch"))
+    sk_of = {i["file"]: h for i, h in zip(info, full["sketches"])}
+    allsk = [sk_of[x[3]] for x in s1["sketches"]]
+    assert [len(h) for h in allsk] == [x[2] for x in s1["sketches"]]
+    assert all(np.array_equal(a, b) for a, b in zip(allsk[:9], base["sketches"]))
+    nrep, rep_of = oracle.greedy_incremental_minhash(allsk, 15, s0["threshold"], 9, s0["rep_ids"], contain)
+    cl, reps = _clusters_after_increment(s0["clusters"], s0["rep_ids"], 9, rep_of)
+    assert (cl, reps, nrep) == (s1["clusters"], s1["rep_ids"], len(s1["rep_ids"]))
+    got = [[gid for gid, _ in c] for c in sketch_io.parse_cluster_file(os.path.join(d, "app.txt"))]
+    assert got == s1["clusters"]

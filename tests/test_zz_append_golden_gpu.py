@@ -117,3 +117,73 @@ def test_reference_continues_from_our_cluster_state_live(tmp_path):
             results[(who, state_of)] = open(os.path.join(cwd, "app.txt"), "rb").read()
             assert os.path.getsize(os.path.join(folder, "cluster_state.bin")) > os.path.getsize(os.path.join(out[state_of], "cluster_state.bin"))
     assert len(set(results.values())) == 1, {k: len(v) for k, v in results.items()}
+
+
+@pytest.mark.parametrize("tag,flags", [("s", ["-s", "1000"]), ("c", ["-c", "100"])])
+def test_clust_greedy_minhash_state_golden(tmp_path, tag, flags):
+    """clust-greedy --save-rep from genomes, then --append --save-rep from the saved MinHash state (append_clust_greedy,
+    sub_command.cpp:97-190) against the committed reference runs: cluster files byte-identical, states equal field by
+    field (hashes of the sketches included, through the folder's hash.sketch)."""
+    _need_bins()
+    import json
+    os.symlink(os.path.join(ROOT, "tests"), str(tmp_path / "tests"))
+    gold = os.path.join(ROOT, "tests", "golden", "append", "greedy_minhash", tag)
+    exe = os.path.join(OURS, "clust-greedy")
+
+    def summary(path):
+        st = sketch_io.read_minhash_cluster_state(path)
+        want = {}
+        for r, gid in enumerate(st["rep_ids"]):
+            for h in st["sketches"][gid]["hashes"]:
+                want.setdefault(int(h), []).append(r)
+        assert want == st["index"]
+        return {"threshold": st["threshold"], "kmer_size": st["kmer_size"], "sketch_size": st["sketch_size"],
+                "containment": st["containment"], "rep_ids": st["rep_ids"], "clusters": st["clusters"],
+                "sketches": [[x["id"], x["length"], len(x["hashes"]), x["file"]] for x in st["sketches"]]}
+    folder, _ = _run(exe, ["-l", "-i", "tests/golden/append/first.txt", "-k", "15"] + flags + ["-d", "0.05", "--save-rep", "-o", "base.txt"],
+                     str(tmp_path))
+    for fn in ("hash.sketch", "info.sketch"):
+        assert _same_bytes(os.path.join(gold, fn), os.path.join(folder, fn)), fn
+    assert _same_bytes(os.path.join(gold, "base.txt"), str(tmp_path / "base.txt"))
+    assert summary(os.path.join(folder, "cluster_state.bin")) == json.load(open(os.path.join(gold, "state_base.json")))
+    _, err = _run(exe, ["-l", "--append", "tests/golden/append/second.txt", "--presketched", folder, "--save-rep", "-d", "0.05", "-o", "app.txt"],
+                  str(tmp_path))
+    assert "Incremental Update Mode (MinHash)" in err
+    assert _same_bytes(os.path.join(gold, "app.txt"), str(tmp_path / "app.txt"))
+    assert summary(os.path.join(folder, "cluster_state.bin")) == json.load(open(os.path.join(gold, "state_app.json")))
+
+
+def test_reference_continues_from_our_minhash_state_live(tmp_path):
+    """live, a larger set: the reference appends to OUR MinHash state and we append to ITS state -- same cluster file"""
+    _need_bins()
+    import shutil
+    from test_cli_gpu import REF, _make_genomes
+    d = str(tmp_path / "genomes")
+    os.makedirs(d)
+    lst, _ = _make_genomes(d, n_fam=5, per_fam=6, length=150000, seed=78)
+    files = open(lst).read().split()
+    rng = np.random.default_rng(6)
+    files = [files[i] for i in rng.permutation(len(files))]
+    first, second = str(tmp_path / "first.txt"), str(tmp_path / "second.txt")
+    open(first, "w").write("\n".join(files[:18]) + "\n")
+    open(second, "w").write("\n".join(files[18:]) + "\n")
+    out = {}
+    bins = (("ref", os.path.join(REF, "clust-greedy"), ["-t", "1"]), ("ours", os.path.join(OURS, "clust-greedy"), []))
+    for who, exe, t1 in bins:
+        folder, _ = _run(exe, t1 + ["-l", "-i", first, "-k", "21", "-s", "1000", "-d", "0.05", "--save-rep", "-o", "base.txt"], str(tmp_path / who))
+        assert os.path.exists(os.path.join(folder, "cluster_state.bin")), who
+        out[who] = folder
+    assert _same_bytes(str(tmp_path / "ref" / "base.txt"), str(tmp_path / "ours" / "base.txt"))
+    results = {}
+    for state_of in ("ref", "ours"):
+        for who, exe, t1 in bins:
+            cwd = str(tmp_path / ("app_%s_on_%s" % (who, state_of)))
+            folder = os.path.join(cwd, "state")
+            os.makedirs(cwd)
+            shutil.copytree(out[state_of], folder)
+            idx = os.path.join(folder, "minhash.sketch.index")          # cache file of the reference's normal run (DESIGN 8: upstream bug)
+            if os.path.exists(idx):
+                os.remove(idx)
+            _run(exe, t1 + ["-l", "--append", second, "--presketched", folder, "--save-rep", "-d", "0.05", "-o", "app.txt"], cwd)
+            results[(who, state_of)] = open(os.path.join(cwd, "app.txt"), "rb").read()
+    assert len(set(results.values())) == 1, {k: len(v) for k, v in results.items()}

@@ -7,6 +7,10 @@ the first 9 genomes of tests/golden/mst_genomes are clustered, the other 4 appen
   tests/golden/append/greedy_kssd/base, step1, step2 clust-greedy --fast on the first 9, then --fast --append --save-rep of
                                                      second_a.txt (4 genomes; builds cluster_state.bin) and of second_b.txt
                                                      (3 genomes; continues from the state)   (sub_command.cpp:192-276)
+  tests/golden/append/greedy_minhash/{s,c}           clust-greedy -k 15 (-s 1000 | -c 100) --save-rep on the first 9, then
+                                                     --append --save-rep of second.txt from the saved state
+                                                     (sub_command.cpp:97-190, MinHashIncrementalCluster); the states are kept as
+                                                     JSON summaries (the sketches are those of tests/golden/append/minhash)
 usage: python tools/make_golden_append.py   (needs oracle/_ref; rewrites tests/golden/append)"""
 import glob
 import json
@@ -107,6 +111,41 @@ def main():
             cmds.append(" ".join(["oracle/_ref/clust-greedy"] + cmd[1:]).replace(base, "<base folder>"))
         meta["greedy_kssd"] = {"base_cmd": " ".join(["oracle/_ref/clust-greedy"] + base_cmd[1:]), "append_cmds": cmds,
                                "stderr_tail": p.stderr.decode()[-400:]}
+    # ---- clust-greedy --append from a saved MinHash cluster state (append_clust_greedy, MinHashIncrementalCluster)
+    sys.path.insert(0, ROOT)
+    from rabbittclust_b200 import sketch_io
+
+    def summary(path):
+        st = sketch_io.read_minhash_cluster_state(path)
+        want = {}
+        for r, gid in enumerate(st["rep_ids"]):
+            for h in st["sketches"][gid]["hashes"]:
+                want.setdefault(int(h), []).append(r)
+        assert want == st["index"]                  # the index section is what the representatives' sketches imply
+        return {"threshold": st["threshold"], "kmer_size": st["kmer_size"], "sketch_size": st["sketch_size"],
+                "containment": st["containment"], "rep_ids": st["rep_ids"], "clusters": st["clusters"],
+                "sketches": [[x["id"], x["length"], len(x["hashes"]), x["file"]] for x in st["sketches"]]}
+    for tag, flags in (("s", ["-s", "1000"]), ("c", ["-c", "100"])):
+        with tempfile.TemporaryDirectory() as tmp:
+            os.symlink(os.path.join(ROOT, "tests"), os.path.join(tmp, "tests"))
+            exe = os.path.join(REF, "clust-greedy")
+            base_cmd = [exe, "-t", "1", "-l", "-i", "tests/golden/append/first.txt", "-k", "15"] + flags + ["-d", "0.05", "--save-rep", "-o", "base.txt"]
+            run(base_cmd, tmp)
+            base = newest_dir(tmp, [])
+            out = os.path.join(GOLD, "greedy_minhash", tag)
+            os.makedirs(out)
+            for fn in ("hash.sketch", "info.sketch"):
+                shutil.copy(os.path.join(base, fn), out)
+            shutil.copy(os.path.join(tmp, "base.txt"), out)
+            json.dump(summary(os.path.join(base, "cluster_state.bin")), open(os.path.join(out, "state_base.json"), "w"))
+            app_cmd = [exe, "-t", "1", "-l", "--append", "tests/golden/append/second.txt", "--presketched", base, "--save-rep",
+                       "-d", "0.05", "-o", "app.txt"]
+            p = run(app_cmd, tmp)
+            shutil.copy(os.path.join(tmp, "app.txt"), out)
+            json.dump(summary(os.path.join(base, "cluster_state.bin")), open(os.path.join(out, "state_app.json"), "w"))
+            meta["greedy_minhash_" + tag] = {"base_cmd": " ".join(["oracle/_ref/clust-greedy"] + base_cmd[1:]),
+                                             "append_cmd": " ".join(["oracle/_ref/clust-greedy"] + app_cmd[1:]).replace(base, "<base folder>"),
+                                             "stderr_tail": p.stderr.decode()[-300:]}
     json.dump(meta, open(os.path.join(GOLD, "MANIFEST.json"), "w"), indent=1)
     subprocess.call(["du", "-sh", GOLD])
 
