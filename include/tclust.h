@@ -343,8 +343,11 @@ int tc_greedy_cluster_kssd(tc_ctx *ctx, int kmer_size, double threshold, int32_t
  * smallest Mash distance <= threshold among those passing the two-sided size-ratio filter (2*exp(d*k)-1) and the
  * floor()ed common-hash filter, or becomes the next representative.  rep_of has n entries; only [start_index, n) are
  * written: the sketch id of the chosen representative, or q itself.  *n_clusters = representatives afterwards.
- * Equal distances: the reference takes whichever candidate its phmap::flat_hash_map<int,int> yields first (depends
- * on the table's heap address, not reproducible); this call takes the earliest-created representative. */
+ * Equal distances: the reference walks its candidates in the iteration order of its
+ * `phmap::flat_hash_map<int,int> candidate_counts` (reserve(1000)) and keeps the first of the smallest distance; that
+ * order is a function of the touched representatives in first-touch order and is reproduced exactly (the device
+ * returns every touched representative for these rules).  Input sketches of the reference's single-file KSSD mode are
+ * stored there in hash-set order, here ascending: first-touch order, hence a tie, can differ for such folders only. */
 int tc_greedy_incremental_kssd(tc_ctx *ctx, int kmer_size, double threshold, uint32_t start_index, const uint32_t *rep_ids,
                                uint32_t n_reps, int32_t *rep_of, uint32_t *n_clusters);
 /* MinHashIncrementalCluster (src/greedy.cpp:1963-2130; caller: append_clust_greedy with a saved state,

@@ -69,6 +69,8 @@ def lib():
         L.oc_greedy_inverted.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_int, C.c_double, i32p]
         L.oc_greedy_incremental_kssd.restype = C.c_int
         L.oc_greedy_incremental_kssd.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_double, C.c_int, i32p, C.c_int, i32p]
+        L.oc_phmap_iteration_order.restype = None
+        L.oc_phmap_iteration_order.argtypes = [i32p, C.c_int, i32p]
         L.oc_greedy_incremental_minhash.restype = C.c_int
         L.oc_greedy_incremental_minhash.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, i32p, C.c_int, i32p]
         L.oc_common_B.restype = C.c_uint32
@@ -277,6 +279,14 @@ def greedy_incremental_kssd(sketches, k, threshold, start, seeds):
     nc = lib().oc_greedy_incremental_kssd(_p(h, C.c_uint64), _p(off, C.c_uint64), n, k, threshold, start,
                                           _p(sd, C.c_int32), len(sd), _p(rep, C.c_int32))
     return nc, rep[start:n]
+
+
+def phmap_iteration_order(keys):
+    """iteration order of the reference's candidate table for distinct int keys given in insertion order"""
+    k = np.ascontiguousarray(keys, np.int32)
+    out = np.zeros(max(len(k), 1), np.int32)
+    lib().oc_phmap_iteration_order(_p(k, C.c_int32), len(k), _p(out, C.c_int32))
+    return out[:len(k)]
 
 
 def greedy_incremental_minhash(sketches, k, threshold, start, seeds, containment=False):

@@ -28,6 +28,19 @@
  *                                                   Kruskal); out.bin: u64 n, {i32,i32,f64}[n].  clust-mst --presketched
  *                                                   itself never writes edge.mst, so this is how the full-size MST weights
  *                                                   of the unmodified reference are obtained (bench.py parity)
+ *   ref_harness phorder <keys.bin> <out.bin>        the iteration order of the reference's candidate table: the int32 keys of
+ *                                                   keys.bin go, in order, through `phmap::flat_hash_map<int,int> m;
+ *                                                   m.reserve(1000); m[key]++` (KssdIncrementalCluster / MinHashIncrementalCluster,
+ *                                                   src/greedy.cpp:1771-1803, 2014-2036, with the reference's own phmap.h);
+ *                                                   out.bin: the keys in iteration order
+ *   ref_harness kssdinc <kssd folder> <n_old> <threshold>
+ *   ref_harness minhashinc <folder> <n_old> <threshold>
+ *                                                   the reference's incremental greedy rules on a pre-sketched folder: the
+ *                                                   first n_old sketches go through KssdInitialClusterWithState /
+ *                                                   MinHashInitialClusterWithState, the rest through KssdIncrementalCluster /
+ *                                                   MinHashIncrementalCluster (src/greedy.cpp:902-957, 1736-1880, 1904-2130), one
+ *                                                   thread.  text: line 1 = folder index of every sketch in state order, line 2 =
+ *                                                   representative ids, then one cluster per line ("-" = empty)
  *   ref_harness greedyb <hash.sketch> <nmax> <threads> <threshold> [contain]
  *                                                   the reference's brute-force greedyCluster
  *                                                   (src/greedy.cpp:285-351); text: one cluster per line
@@ -253,8 +266,79 @@ static int cmd_greedyb(int argc, char **argv)
     return 0;
 }
 
+template <typename State>
+static void print_state(const State &st, const std::vector<std::vector<int>> &cl)
+{
+    for (size_t i = 0; i < st.all_sketches.size(); i++) printf(i ? " %d" : "%d", st.all_sketches[i].id);
+    printf("\n");
+    for (size_t i = 0; i < st.representative_ids.size(); i++) printf(i ? " %d" : "%d", st.representative_ids[i]);
+    printf("\n");
+    for (const auto &c : cl) {
+        if (c.empty()) printf("-");
+        for (size_t i = 0; i < c.size(); i++) printf(i ? " %d" : "%d", c[i]);
+        printf("\n");
+    }
+}
+
+static int cmd_kssdinc(int argc, char **argv)
+{
+    std::vector<KssdSketchInfo> all;
+    KssdParameters info;
+    loadKssdSketches(argv[2], 1, all, info);
+    const size_t n_old = strtoull(argv[3], 0, 10);
+    const double thr = atof(argv[4]);
+    if (n_old == 0 || n_old > all.size()) { fprintf(stderr, "kssdinc: bad n_old\n"); return 1; }
+    for (size_t i = 0; i < all.size(); i++) all[i].id = (int)i;
+    std::vector<KssdSketchInfo> pre(all.begin(), all.begin() + n_old), add(all.begin() + n_old, all.end());
+    const int kmer_size = info.half_k * 2;
+    KssdClusterState st = KssdInitialClusterWithState(pre, info, thr, 1, kmer_size);
+    std::vector<std::vector<int>> cl = KssdIncrementalCluster(st, add, 1);
+    print_state(st, cl);
+    return 0;
+}
+
+static int cmd_minhashinc(int argc, char **argv)
+{
+    std::vector<SketchInfo> all;
+    int func_id = 0;
+    loadSketches(argv[2], 1, all, func_id);
+    const size_t n_old = strtoull(argv[3], 0, 10);
+    const double thr = atof(argv[4]);
+    if (n_old == 0 || n_old > all.size() || func_id != 0) { fprintf(stderr, "minhashinc: bad input\n"); return 1; }
+    for (size_t i = 0; i < all.size(); i++) all[i].id = (int)i;
+    std::vector<SketchInfo> pre(all.begin(), all.begin() + n_old), add(all.begin() + n_old, all.end());
+    const int kmer_size = pre[0].minHash->getKmerSize();
+    const int sketch_size = pre[0].minHash->getSketchSize();
+    const bool contain = pre[0].isContainment;
+    MinHashClusterState st = MinHashInitialClusterWithState(pre, thr, 1, kmer_size, sketch_size, contain);
+    std::vector<std::vector<int>> cl = MinHashIncrementalCluster(st, add, 1);
+    print_state(st, cl);
+    return 0;
+}
+
+static int cmd_phorder(int argc, char **argv)
+{
+    FILE *fi = fopen(argv[2], "rb");
+    if (!fi) { perror(argv[2]); return 1; }
+    std::vector<int> keys;
+    int k;
+    while (fread(&k, 4, 1, fi) == 1) keys.push_back(k);
+    fclose(fi);
+    phmap::flat_hash_map<int, int> m;
+    m.reserve(1000);
+    for (int x : keys) m[x]++;
+    FILE *fo = fopen(argv[3], "wb");
+    if (!fo) { perror(argv[3]); return 1; }
+    for (const auto &pr : m) fwrite(&pr.first, 4, 1, fo);
+    fclose(fo);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc >= 4 && !strcmp(argv[1], "phorder")) return cmd_phorder(argc, argv);
+    if (argc >= 5 && !strcmp(argv[1], "kssdinc")) return cmd_kssdinc(argc, argv);
+    if (argc >= 5 && !strcmp(argv[1], "minhashinc")) return cmd_minhashinc(argc, argv);
     if (argc >= 4 && !strcmp(argv[1], "pairsdump")) return cmd_pairsdump(argc, argv);
     if (argc >= 5 && !strcmp(argv[1], "mstb")) return cmd_mstb(argc, argv);
     if (argc >= 6 && !strcmp(argv[1], "msti")) return cmd_msti(argc, argv);

@@ -517,73 +517,111 @@ int oc_greedy_inverted(const uint64_t *hashes, const uint64_t *off, int N, int k
     return nrep;
 }
 
-/* KssdIncrementalCluster (greedy.cpp:1736-1880) with one thread: sketches [0, start) are clustered, seed[0..n_seed) are
- * their representatives in creation order; sketch q >= start joins the representative of smallest distance or becomes
- * the next one.  The reference walks its candidates in the iteration order of a phmap::flat_hash_map<int,int> (it
- * depends on the table's heap address), so among EQUAL distances its choice is not reproducible; here, as in the
- * product, the earliest-created representative wins.  rep_of[q] is written for q >= start only.  Returns #reps. */
-int oc_greedy_incremental_kssd(const uint64_t *hashes, const uint64_t *off, int N, int k, double threshold,
-                               int start, const int32_t *seed, int n_seed, int32_t *rep_of)
+/* ---- iteration order of the reference's candidate table ----------------------------------------------------------
+ * Both incremental rules collect the touched representatives in `phmap::flat_hash_map<int,int> candidate_counts;
+ * candidate_counts.reserve(1000)` (greedy.cpp:1771-1772, 2014-2015), copy the table into a vector in ITERATION order and
+ * walk that vector with a strict `dist < best_dist` (:1805-1848, 2038-2094): among equal distances the candidate that comes
+ * first in the table wins.  The table is the vendored parallel-hashmap (src/phmap.h, deterministic build: H1 = hash >> 7,
+ * no per-table seed): hash = hi64 + lo64 of key * 0xde5fb9d2630458e9 (phmap_utils.h:67-77), 16-wide groups, triangular
+ * probing (phmap.h:145-167), first empty slot of the first group that has one (:2196-2207), capacity 2047 after
+ * reserve(1000) (NormalizeCapacity(1000 + 999/7), :573-609, :1698-1714), growth to 2*cap+1 when cap - cap/8 entries are in,
+ * re-inserting in slot order (:2054-2079, :2144-2154, :2252-2269).  Checked against the real container through
+ * `ref_harness phorder` (tests/test_oracle_golden.py). */
+typedef struct { int cap, size, growth; unsigned char *full; int *key; } phtab;
+static uint64_t ph_mix(uint64_t a)
 {
-    int *reps = (int *)malloc(sizeof(int) * (size_t)(N > 0 ? N : 1)), nrep = 0;
-    for (int r = 0; r < n_seed; r++) reps[nrep++] = seed[r];
-    const double radio = 2.0 * exp(threshold * k) - 1.0;              /* calculateMaxSizeRatio, greedy.cpp:162-173 */
-    const double x = exp(-threshold * k);                             /* greedy.cpp:1751-1752 */
-    const double jaccard_min = x / (2.0 - x);
-    for (int q = start; q < N; q++) {
-        const uint64_t *hq = hashes + off[q];
-        const int sizeQry = (int)(off[q + 1] - off[q]);
-        double best_dist = 1.7976931348623157e308;
-        int best = -1;
-        for (int r = 0; r < nrep; r++) {
-            const int id = reps[r];
-            const int sizeRef = (int)(off[id + 1] - off[id]);
-            uint32_t fh;
-            const int common = (int)oc_intersect_u64(hq, sizeQry, hashes + off[id], sizeRef, &fh);
-            if (common == 0) continue;                                /* only representatives met in the index are candidates */
-            const double ratio = (double)sizeQry / sizeRef;           /* :1818-1821 */
-            if (ratio > radio || ratio < 1.0 / radio) continue;
-            const int min_common_needed = (int)(jaccard_min * (sizeQry + sizeRef) / (1.0 + jaccard_min));   /* :1825 */
-            if (common < min_common_needed) continue;
-            /* calculate_mash_distance, greedy.cpp:72-119 */
-            const uint64_t uni = (uint64_t)sizeRef + sizeQry - common;
-            const double jaccard_ = uni == 0 ? 0.0 : (double)common / uni;
-            double dist;
-            if (jaccard_ == 1.0) dist = 0.0;
-            else {
-                dist = -log(2 * jaccard_ / (1.0 + jaccard_)) / (double)k;
-                if (dist > 1.0) dist = 1.0;
-            }
-            if (dist <= threshold && dist < best_dist) { best_dist = dist; best = r; }   /* :1840-1848 */
+    unsigned __int128 p = (unsigned __int128)a * 0xde5fb9d2630458e9ULL;
+    return (uint64_t)(p >> 64) + (uint64_t)p;
+}
+static int ph_first_non_full(const phtab *t, uint64_t h)
+{
+    const uint64_t mask = (uint64_t)t->cap;
+    uint64_t off = (h >> 7) & mask, idx = 0;
+    for (;;) {
+        for (int i = 0; i < 16; i++) {
+            const uint64_t p = off + i;            /* control bytes: [0,cap) slots, cap = sentinel, then clones of the first 16 */
+            if (p == mask) continue;
+            const uint64_t q = p < mask ? p : p - mask - 1;
+            if (!t->full[q]) return (int)((off + i) & mask);
         }
-        if (best != -1) rep_of[q] = reps[best];
-        else { reps[nrep++] = q; rep_of[q] = q; }
+        idx += 16; off = (off + idx) & mask;
     }
-    free(reps);
-    return nrep;
+}
+static void ph_resize(phtab *t, int newcap)
+{
+    unsigned char *of = t->full; int *ok = t->key; const int oc = t->cap;
+    t->cap = newcap;
+    t->full = (unsigned char *)calloc((size_t)newcap, 1);
+    t->key = (int *)malloc(sizeof(int) * (size_t)newcap);
+    t->growth = newcap - newcap / 8 - t->size;
+    for (int i = 0; i < oc; i++)
+        if (of[i]) { const int s = ph_first_non_full(t, ph_mix((uint64_t)ok[i])); t->full[s] = 1; t->key[s] = ok[i]; }
+    free(of); free(ok);
+}
+/* keys: distinct ints in first-insertion order; out: the same keys in iteration order */
+void oc_phmap_iteration_order(const int32_t *keys, int n, int32_t *out)
+{
+    phtab t = {0, 0, 0, NULL, NULL};
+    ph_resize(&t, 2047);
+    for (int i = 0; i < n; i++) {
+        int s = ph_first_non_full(&t, ph_mix((uint64_t)keys[i]));
+        if (t.growth == 0) { ph_resize(&t, t.cap * 2 + 1); s = ph_first_non_full(&t, ph_mix((uint64_t)keys[i])); }
+        t.size++; t.growth--;
+        t.full[s] = 1; t.key[s] = keys[i];
+    }
+    int m = 0;
+    for (int i = 0; i < t.cap; i++) if (t.full[i]) out[m++] = t.key[i];
+    free(t.full); free(t.key);
 }
 
-/* MinHashIncrementalCluster (greedy.cpp:1963-2130) with one thread: as oc_greedy_incremental_kssd without the size-ratio
- * filter and with the containment forms (:2057-2077).  Same tie rule (earliest-created representative). */
-int oc_greedy_incremental_minhash(const uint64_t *hashes, const uint64_t *off, int N, int k, int containment,
-                                  double threshold, int start, const int32_t *seed, int n_seed, int32_t *rep_of)
+/* KssdIncrementalCluster (greedy.cpp:1736-1880, kssd = 1) and MinHashIncrementalCluster (:1963-2130, kssd = 0) with one
+ * thread: sketches [0, start) are clustered, seed[0..n_seed) are their representatives in creation order; sketch
+ * q >= start joins the representative of smallest distance -- the first such one in the iteration order of the candidate
+ * table -- or becomes the next representative.  rep_of[q] is written for q >= start only.  Returns #representatives. */
+typedef struct { uint32_t first_hit; int rep_idx; int common; } inc_touch;
+static int cmp_inc_touch(const void *a, const void *b)
 {
-    int *reps = (int *)malloc(sizeof(int) * (size_t)(N > 0 ? N : 1)), nrep = 0;
+    const inc_touch *x = (const inc_touch *)a, *y = (const inc_touch *)b;
+    if (x->first_hit != y->first_hit) return x->first_hit < y->first_hit ? -1 : 1;
+    return x->rep_idx < y->rep_idx ? -1 : x->rep_idx > y->rep_idx;
+}
+static int greedy_incremental(const uint64_t *hashes, const uint64_t *off, int N, int k, int kssd, int containment,
+                              double threshold, int start, const int32_t *seed, int n_seed, int32_t *rep_of)
+{
+    const size_t cap = (size_t)(N > 0 ? N : 1);
+    int *reps = (int *)malloc(sizeof(int) * cap), nrep = 0;
+    inc_touch *tc = (inc_touch *)malloc(sizeof(inc_touch) * cap);
+    int32_t *ins = (int32_t *)malloc(4 * cap), *ord = (int32_t *)malloc(4 * cap);
+    int *common_of = (int *)malloc(sizeof(int) * cap);
     for (int r = 0; r < n_seed; r++) reps[nrep++] = seed[r];
-    const double x = exp(-threshold * k);                             /* :2000-2001 */
+    const double radio = 2.0 * exp(threshold * k) - 1.0;              /* calculateMaxSizeRatio, greedy.cpp:162-173 */
+    const double x = exp(-threshold * k);                             /* :1751-1752, :2000-2001 */
     const double jaccard_min = x / (2.0 - x);
     for (int q = start; q < N; q++) {
         const uint64_t *hq = hashes + off[q];
         const int sizeQry = (int)(off[q + 1] - off[q]);
-        double best_dist = 1.7976931348623157e308;
-        int best = -1;
+        /* the index probe (:1774-1795, :2017-2024): query hashes in array order, postings in representative order */
+        int nt = 0;
         for (int r = 0; r < nrep; r++) {
             const int id = reps[r];
-            const int sizeRef = (int)(off[id + 1] - off[id]);
             uint32_t fh;
-            const int common = (int)oc_intersect_u64(hq, sizeQry, hashes + off[id], sizeRef, &fh);
-            if (common == 0 || sizeRef == 0) continue;
-            int min_common_needed;
+            const int c = (int)oc_intersect_u64(hq, sizeQry, hashes + off[id], off[id + 1] - off[id], &fh);
+            if (c > 0) { tc[nt].first_hit = fh; tc[nt].rep_idx = r; tc[nt].common = c; nt++; }
+        }
+        qsort(tc, nt, sizeof(inc_touch), cmp_inc_touch);              /* first-insertion order into candidate_counts */
+        for (int t = 0; t < nt; t++) { ins[t] = tc[t].rep_idx; common_of[tc[t].rep_idx] = tc[t].common; }
+        oc_phmap_iteration_order(ins, nt, ord);                       /* `for (const auto& pair : candidate_counts)` */
+        double best_dist = 1.7976931348623157e308;
+        int best = -1;
+        for (int t = 0; t < nt; t++) {
+            const int r = ord[t], common = common_of[r];
+            const int sizeRef = (int)(off[reps[r] + 1] - off[reps[r]]);
+            if (sizeRef == 0) continue;
+            if (kssd) {                                               /* :1818-1821 */
+                const double ratio = (double)sizeQry / sizeRef;
+                if (ratio > radio || ratio < 1.0 / radio) continue;
+            }
+            int min_common_needed;                                    /* :1825, :2057-2063 */
             if (containment) {
                 const int minSz = sizeQry < sizeRef ? sizeQry : sizeRef;
                 min_common_needed = (int)(jaccard_min * minSz);
@@ -591,7 +629,7 @@ int oc_greedy_incremental_minhash(const uint64_t *hashes, const uint64_t *off, i
                 min_common_needed = (int)(jaccard_min * (sizeQry + sizeRef) / (1.0 + jaccard_min));
             }
             if (common < min_common_needed) continue;
-            double jaccard;
+            double jaccard;                                           /* calculate_mash_distance :72-119 / inline :2069-2085 */
             if (containment) {
                 const int minSz = sizeQry < sizeRef ? sizeQry : sizeRef;
                 jaccard = (double)common / minSz;
@@ -607,13 +645,25 @@ int oc_greedy_incremental_minhash(const uint64_t *hashes, const uint64_t *off, i
                 dist = -log(2.0 * jaccard / (1.0 + jaccard)) / k;
                 if (dist > 1.0) dist = 1.0;
             }
-            if (dist <= threshold && dist < best_dist) { best_dist = dist; best = r; }
+            if (dist <= threshold && dist < best_dist) { best_dist = dist; best = r; }   /* :1840-1848, :2087-2094 */
         }
         if (best != -1) rep_of[q] = reps[best];
         else { reps[nrep++] = q; rep_of[q] = q; }
     }
-    free(reps);
+    free(reps); free(tc); free(ins); free(ord); free(common_of);
     return nrep;
+}
+
+int oc_greedy_incremental_kssd(const uint64_t *hashes, const uint64_t *off, int N, int k, double threshold,
+                               int start, const int32_t *seed, int n_seed, int32_t *rep_of)
+{
+    return greedy_incremental(hashes, off, N, k, 1, 0, threshold, start, seed, n_seed, rep_of);
+}
+
+int oc_greedy_incremental_minhash(const uint64_t *hashes, const uint64_t *off, int N, int k, int containment,
+                                  double threshold, int start, const int32_t *seed, int n_seed, int32_t *rep_of)
+{
+    return greedy_incremental(hashes, off, N, k, 0, containment, threshold, start, seed, n_seed, rep_of);
 }
 
 /* ------------------------------------------------- semantic B brute-force callers */

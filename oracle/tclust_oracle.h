@@ -92,9 +92,13 @@ int oc_clusters_from_mst(const oc_edge *mst, size_t n_edges, int N, double thres
 int oc_greedy_inverted(const uint64_t *hashes, const uint64_t *off, int N, int k,
                        int containment, double threshold, int32_t *rep_of);
 
+/* iteration order of `phmap::flat_hash_map<int,int> m; m.reserve(1000); m[key]++` for distinct keys in insertion order
+ * (the reference's candidate table, greedy.cpp:1771-1803; src/phmap.h) */
+void oc_phmap_iteration_order(const int32_t *keys, int n, int32_t *out);
+
 /* KssdIncrementalCluster with -t 1 (greedy.cpp:1736-1880): sketches [0,start) clustered with representatives
- * seed[0..n_seed) (creation order); rep_of[q], q >= start: chosen representative or q.  Ties -> earliest created
- * (the reference's tie order is a hash-map iteration order). Returns #representatives. */
+ * seed[0..n_seed) (creation order); rep_of[q], q >= start: chosen representative or q.  Equal distances: the
+ * candidate that comes first in the iteration order of the reference's candidate table. Returns #representatives. */
 int oc_greedy_incremental_kssd(const uint64_t *hashes, const uint64_t *off, int N, int k, double threshold,
                                int start, const int32_t *seed, int n_seed, int32_t *rep_of);
 

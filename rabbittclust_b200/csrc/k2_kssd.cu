@@ -53,6 +53,9 @@ struct K2Args {
     uint64_t *out; unsigned long long out_stride; uint32_t *cnt;
 };
 
+// ODD: the per-record mode with an odd k-mer size (a.odd); a template parameter so that the list-mode instantiation -- an
+// ALU-bound loop -- carries none of its instructions
+template <bool ODD>
 __global__ void __launch_bounds__(K2_THREADS) k2_kssd_kernel(const K2Args a)
 {
     __shared__ uint32_t s_seg;
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_kssd_kernel(const K2Args a)
             run++;
             unsigned long long t_use = tuple, r_use = rvs;
             bool use = run >= a.kmer && pos >= e0;
-            if (a.odd && run == a.kmer - 1 && pos >= e0) {
+            if (ODD && run == a.kmer - 1 && pos >= e0) {
                 // consumer_fasta_task_with_kssd with kmerSize = a.kmer - 1 (SketchInfo.cpp:358-372): the window is used
                 // after kmerSize valid bases while the tuple holds a.kmer, and a non-ACGT byte does not clear the tuple:
                 // the oldest slot still holds the last valid base before the gap (nothing at the start of the record).
@@ -311,7 +314,8 @@ int k2_enqueue(tc_ctx *ctx, K2Workspace *ws, K2Slot &sl, cudaStream_t st, K2Args
     a.out = out_dev; a.out_stride = out_stride; a.cnt = d_cnt;
     if (nseg) {
         const int grid = (int)std::min<uint64_t>(nseg, (uint64_t)ctx->num_sms * 6);   // 6 CTAs x 32 KB filter per SM
-        k2_kssd_kernel<<<grid, K2_THREADS, 0, st>>>(a);
+        if (a.odd) k2_kssd_kernel<true><<<grid, K2_THREADS, 0, st>>>(a);
+        else k2_kssd_kernel<false><<<grid, K2_THREADS, 0, st>>>(a);
         ctx->launches++;
         TC_CUDA(cudaGetLastError());
     }

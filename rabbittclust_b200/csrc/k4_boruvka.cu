@@ -395,8 +395,9 @@ int tc_k4_enqueue(tc_ctx *ctx, int mode, const unsigned long long *d_fin_key, co
 // tc_dist_from_key (glibc log, the reference's expression order).  *n_edges_dev / *overflow: the candidate-edge counters
 // of the pass that fed it.  comp_out (may be NULL): final component label of every vertex.
 // One wait: control words, counters and the (at most n-1, padded to n) sorted forest entries come back together.
+// direct != nullptr: the forest is written there (room for n edges) instead of into `mst`; *n_direct = its length
 int tc_k4_collect(tc_ctx *ctx, int mode, int kmer_size, std::vector<tc_edge> &mst, uint64_t *n_edges_dev, bool *overflow,
-                  std::vector<int32_t> *comp_out)
+                  std::vector<int32_t> *comp_out, tc_edge *direct, uint64_t *n_direct)
 {
     tc_k4_state &k = ctx->k4;
     const uint32_t n = ctx->n;
@@ -414,11 +415,13 @@ int tc_k4_collect(tc_ctx *ctx, int mode, int kmer_size, std::vector<tc_edge> &ms
     }
     TC_CUDA(cudaStreamSynchronize(st));
     TC_CHECK(h_ctl[4] == 0, "tc_mst: the Boruvka kernel gave up at a barrier (%s)", h_ctl[4] == 2 ? "a peer GPU of the group did not arrive" : "grid barrier");
-    const uint32_t nf = std::min(h_ctl[0], n);
+    const uint32_t nf = std::min(h_ctl[0], direct && n ? n - 1 : n);      // a forest has at most n - 1 edges (the caller's array)
     if (n_edges_dev) *n_edges_dev = h_cnt[0];
     if (overflow) *overflow = h_cnt[1] != 0 || h_cnt[0] > ctx->edge_cap || h_ctl[6] != 0;   // this rank's or (group) any rank's
     ctx->k4.last_rounds = h_ctl[5];
-    mst.resize(nf);
+    if (direct) { mst.clear(); if (n_direct) *n_direct = nf; }
+    else mst.resize(nf);
+    tc_edge *dst = direct ? direct : mst.data();
     auto by_weight = [](const tc_edge &x, const tc_edge &y) {
         if (x.dist != y.dist) return x.dist < y.dist;
         if (x.pre != y.pre) return x.pre < y.pre;
@@ -434,16 +437,16 @@ int tc_k4_collect(tc_ctx *ctx, int mode, int kmer_size, std::vector<tc_edge> &ms
             d = tc_dist_from_key(h_f[e].x, mode, kmer_size);
             if (e > 0 && d == prev_d) mixed = true;
             else {
-                if (mixed) std::sort(mst.begin() + run0, mst.begin() + e, by_weight);
+                if (mixed) std::sort(dst + run0, dst + e, by_weight);
                 if (e > 0 && d < prev_d) monotone = false;
                 run0 = e; mixed = false;
             }
             prev_d = d;
         }
-        mst[e] = tc_edge{(int32_t)(h_f[e].y >> 32), (int32_t)(h_f[e].y & 0xFFFFFFFFull), d};
+        dst[e] = tc_edge{(int32_t)(h_f[e].y >> 32), (int32_t)(h_f[e].y & 0xFFFFFFFFull), d};
     }
-    if (mixed) std::sort(mst.begin() + run0, mst.end(), by_weight);
-    if (!monotone) std::sort(mst.begin(), mst.end(), by_weight);   // distances not monotone in the key (never for the valid modes)
+    if (mixed) std::sort(dst + run0, dst + nf, by_weight);
+    if (!monotone) std::sort(dst, dst + nf, by_weight);            // distances not monotone in the key (never for the valid modes)
     return 0;
 }
 

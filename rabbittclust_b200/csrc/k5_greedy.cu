@@ -180,6 +180,57 @@ extern "C" int tc_greedy_scan(tc_ctx *ctx, uint32_t q0, uint32_t q1, const uint3
     return rc;
 }
 
+// Iteration order of the reference's candidate table (src/phmap.h, vendored parallel-hashmap in its deterministic build):
+// `phmap::flat_hash_map<int,int> m; m.reserve(1000); m[key]++` for distinct keys in insertion order.  hash = high + low
+// 64 bits of key * 0xde5fb9d2630458e9 (phmap_utils.h:67-77); slot search from (hash >> 7) & capacity over 16-wide groups
+// with triangular steps, first empty position of the first group that has one (phmap.h:145-167, 2196-2207; the control
+// array ends with a sentinel and 16 cloned bytes); capacity 2047 after reserve(1000) (:573-609, 1698-1714), growth to
+// 2*capacity+1 once capacity - capacity/8 entries are in, re-inserting in slot order (:2054-2079, 2144-2154, 2252-2269).
+// Checked against the real container in tests (ref_harness phorder -> oracle -> this).
+struct PhmapOrder {
+    std::vector<uint8_t> full; std::vector<int> key;
+    uint64_t cap = 0; size_t size = 0, growth = 0;
+    static uint64_t mix(uint64_t a) { const unsigned __int128 p = (unsigned __int128)a * 0xde5fb9d2630458e9ULL; return (uint64_t)(p >> 64) + (uint64_t)p; }
+    size_t first_non_full(uint64_t h) const
+    {
+        uint64_t off = (h >> 7) & cap, idx = 0;
+        for (;;) {
+            for (uint64_t i = 0; i < 16; i++) {
+                const uint64_t p = off + i;
+                if (p == cap) continue;                                  // the sentinel
+                if (!full[p < cap ? p : p - cap - 1]) return (size_t)((off + i) & cap);
+            }
+            idx += 16; off = (off + idx) & cap;
+        }
+    }
+    void resize(uint64_t ncap)
+    {
+        std::vector<uint8_t> of; std::vector<int> ok;
+        of.swap(full); ok.swap(key);
+        const uint64_t oc = cap;
+        cap = ncap; full.assign(ncap, 0); key.assign(ncap, 0);
+        growth = (size_t)(ncap - ncap / 8) - size;
+        for (uint64_t i = 0; i < oc; i++)
+            if (of[i]) { const size_t t = first_non_full(mix((uint64_t)ok[i])); full[t] = 1; key[t] = ok[i]; }
+    }
+    // keys: distinct, in insertion order; returns them in iteration order
+    std::vector<int> order(const std::vector<int> &keys)
+    {
+        cap = 0; size = 0; full.clear(); key.clear();
+        resize(2047);
+        for (int k : keys) {
+            size_t t = first_non_full(mix((uint64_t)k));
+            if (growth == 0) { resize(cap * 2 + 1); t = first_non_full(mix((uint64_t)k)); }
+            size++; growth--;
+            full[t] = 1; key[t] = k;
+        }
+        std::vector<int> out;
+        out.reserve(keys.size());
+        for (uint64_t i = 0; i < cap; i++) if (full[i]) out.push_back(key[i]);
+        return out;
+    }
+};
+
 // --------------------------------------------------------------------- full greedy clustering
 // brute = false: MinHashGreedyClusterWithInvertedIndex (greedy.cpp:986-1399), semantic A, `touched` tie order.
 // brute = true : greedyCluster (greedy.cpp:285-351): MinHash::distance (semantic B with sketchSize semb_size) or
@@ -198,9 +249,11 @@ extern "C" int tc_greedy_scan(tc_ctx *ctx, uint32_t q0, uint32_t q1, const uint3
 //                representatives are seed[0..n_seed) in creation order; each later sketch joins the nearest
 //                representative (two-sided size-ratio filter, floor()ed common filter, Mash distance <= threshold,
 //                strictly smaller distance wins) or founds a cluster.  The reference walks its candidates in the
-//                iteration order of a phmap::flat_hash_map<int,int>, which depends on the table's heap address, so
-//                its choice among EQUAL distances is not reproducible even by itself; here the earliest-created
-//                representative wins a tie.  kssd = false with incr: MinHashIncrementalCluster (greedy.cpp:1963-2130), the
+//                iteration order of its `phmap::flat_hash_map<int,int> candidate_counts` (reserve(1000)), so among EQUAL
+//                distances the candidate that comes first in that table wins; the order is a pure function of the
+//                touched representatives in first-touch order, reproduced by PhmapOrder below.  For that the device
+//                emits every touched representative (common >= 1), not only those that can pass the filter.
+//                kssd = false with incr: MinHashIncrementalCluster (greedy.cpp:1963-2130), the
 //                same walk without the size-ratio filter and with the containment forms of the filter and the distance.
 static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment, double threshold, bool brute, uint32_t semb_size,
                        int32_t *rep_of, uint32_t *n_clusters, bool kssd = false, bool incr = false, uint32_t incr_start = 0,
@@ -242,6 +295,8 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
     const char *gimpl = getenv("TCLUST_GREEDY_IMPL");
     const bool use_join = semb_size == 0 && !(gimpl && !strcmp(gimpl, "merge"));
     std::vector<int32_t> order_of(n, -1);      // representative creation order, -1 = not a representative
+    std::vector<uint32_t> rep_by_order;        // creation number -> sketch id
+    PhmapOrder phmap_order;
     std::vector<tc_cand> cands;
     std::vector<std::vector<tc_cand>> part_cands(G);
     std::vector<std::string> part_err(G);
@@ -258,8 +313,10 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
         // candidates: the hash-join kernel (first_hit = smallest shared rank, same `touched` order), except for the
         // semantic-B counts of the brute-force rule, which need the ordered merge (TCLUST_GREEDY_IMPL=merge forces it)
         if (use_join) {
-            if (c->nrep > 0 && tc_launch_join_cands(c, b0, b1, 1, cmin_fixed, containment, jmin)) { fail("representative scan"); return; }
-            if (r == 0 && tc_launch_join_cands(c, b0, b1, 0, cmin_fixed, containment, jmin)) { fail("batch scan"); return; }
+            // incremental rules: every touched representative (common >= 1), the tie order depends on all of them
+            const int cmin_dev = incr ? 1 : cmin_fixed;
+            if (c->nrep > 0 && tc_launch_join_cands(c, b0, b1, 1, cmin_dev, containment, jmin)) { fail("representative scan"); return; }
+            if (r == 0 && tc_launch_join_cands(c, b0, b1, 0, cmin_dev, containment, jmin)) { fail("batch scan"); return; }
         } else {
             if (c->nrep > 0 && tc_launch_tiles_cands(c, b0, b1, 1, cmin_fixed, containment, jmin, 0, 1, semb_size)) { fail("representative scan"); return; }
             if (r == 0 && tc_launch_tiles_cands(c, b0, b1, 0, cmin_fixed, containment, jmin, 0, 1, semb_size)) { fail("batch scan"); return; }
@@ -302,6 +359,7 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
             TC_CHECK(seed[c] < incr_start && order_of[seed[c]] < 0, "tc_greedy_incremental_kssd: representative %u (sketch %u) is out of "
                      "range or listed twice", c, seed[c]);
             order_of[seed[c]] = (int32_t)c;
+            rep_by_order.push_back(seed[c]);
         }
         nrep_total = n_seed;
         if (append_reps(std::vector<uint32_t>(seed, seed + n_seed))) return 1;
@@ -350,11 +408,11 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
             // representative creation order)  -- greedy.cpp:1148-1164
             tc_cand *end = std::remove_if(lo, hi, [&](const tc_cand &c) { return order_of[c.rep] < 0; });
             std::sort(lo, end, [&](const tc_cand &a, const tc_cand &b) {
-                if (!brute && !incr && a.first_hit != b.first_hit) return a.first_hit < b.first_hit;
+                if (!brute && a.first_hit != b.first_hit) return a.first_hit < b.first_hit;
                 return order_of[a.rep] < order_of[b.rep];
             });
             const int size_ref = (int)ctx->h_size[q];
-            int best_common = -1, best_rep = -1;
+            int best_common = -1, best_rep = -1, n_tied = 0;
             double best_dist = std::numeric_limits<double>::max(), best_jaccard = -1.0;
             for (tc_cand *c = lo; c < end; c++) {
                 const int common = (int)c->common, size_qry = (int)ctx->h_size[c->rep];
@@ -376,7 +434,10 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
                     if (common < min_common_needed) continue;
                     // calculate_mash_distance (:103-160) / the inline form of :2069-2085: the same expression
                     const double dist = tc_greedy_dist(common, sizeRef, sizeQry, containment, kmer_size);
-                    if (dist <= threshold && dist < best_dist) { best_dist = dist; best_rep = (int)c->rep; }
+                    if (dist <= threshold) {
+                        if (dist < best_dist) { best_dist = dist; best_rep = (int)c->rep; n_tied = 1; }
+                        else if (dist == best_dist) n_tied++;
+                    }
                     continue;
                 }
                 const int common_min = all_fixed ? cmin_fixed
@@ -395,11 +456,31 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
                     if (dist <= threshold && dist < best_dist) { best_dist = dist; best_common = common; best_rep = (int)c->rep; }
                 }
             }
+            if (incr && n_tied > 1) {
+                // several representatives at the smallest distance: the reference takes the one that comes first in the
+                // iteration order of its candidate table, filled in first-touch order = the sorted order of lo..end
+                std::vector<int> keys;
+                keys.reserve(end - lo);
+                for (tc_cand *c = lo; c < end; c++) keys.push_back(order_of[c->rep]);
+                const std::vector<int> it = phmap_order.order(keys);
+                std::vector<char> tied(nrep_total, 0);
+                for (tc_cand *c = lo; c < end; c++) {
+                    const int common = (int)c->common, sizeQry = size_ref, sizeRef = (int)ctx->h_size[c->rep];
+                    if (sizeRef == 0) continue;
+                    if (kssd) { const double ratio = (double)sizeQry / sizeRef; if (ratio > max_ratio || ratio < 1.0 / max_ratio) continue; }
+                    const int need = containment ? (int)(jmin * std::min(sizeQry, sizeRef)) : (int)(jmin * (sizeQry + sizeRef) / (1.0 + jmin));
+                    if (common < need) continue;
+                    if (tc_greedy_dist(common, sizeRef, sizeQry, containment, kmer_size) == best_dist) tied[order_of[c->rep]] = 1;
+                }
+                for (int idx : it)
+                    if (tied[idx]) { best_rep = (int)rep_by_order[idx]; break; }
+            }
             if (best_rep != -1) {
                 rep_of[q] = best_rep;
             } else {
                 rep_of[q] = (int32_t)q;
                 order_of[q] = (int32_t)nrep_total++;
+                rep_by_order.push_back(q);
                 new_reps.push_back(q);
             }
         }

@@ -176,7 +176,7 @@ void tc_k4_free(tc_ctx *ctx);
 int tc_k4_reserve(tc_ctx *ctx, uint32_t n);
 int tc_k4_enqueue(tc_ctx *ctx, int mode, const unsigned long long *d_fin_key, const unsigned long long *d_fin_id, uint32_t nfin);
 int tc_k4_collect(tc_ctx *ctx, int mode, int kmer_size, std::vector<tc_edge> &mst, uint64_t *n_edges_dev, bool *overflow,
-                  std::vector<int32_t> *comp_out);
+                  std::vector<int32_t> *comp_out, tc_edge *direct = nullptr, uint64_t *n_direct = nullptr);
 int tc_k4_fold(tc_ctx *ctx, uint32_t *nfin);     // wait for the queued Boruvka and keep its forest on the device as the next launch's extra edges
 void tc_k2_free(tc_ctx *ctx);
 

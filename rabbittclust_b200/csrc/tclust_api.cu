@@ -1434,6 +1434,11 @@ static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t se
     std::vector<tc_edge> mst;
     std::vector<int32_t> comp;
     ctx->bounded_batches = ctx->bounded_folds = 0;
+    // the plain call (no completion with distance-1 edges, no old MST to merge): the forest is converted straight into the
+    // caller's array (room for n - 1 edges by contract), without a vector in between
+    tc_edge *direct = (out && !complete && !n_pre) ? out : nullptr;
+    uint64_t n_direct = 0;
+    bool is_direct = direct != nullptr;
     for (int attempt = 0;; attempt++) {
         uint64_t cnt = 0;
         bool overflow = false;
@@ -1442,7 +1447,7 @@ static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t se
             if (allpairs_pass_impl(ctx, radio, semb_size, part, nparts, nullptr, nullptr, start_index, true)) return 1;
         }
         if (tc_k4_enqueue(ctx, mode, nullptr, nullptr, 0)) return 1;
-        if (tc_k4_collect(ctx, mode, kmer_size, mst, &cnt, &overflow, complete ? &comp : nullptr)) return 1;
+        if (tc_k4_collect(ctx, mode, kmer_size, mst, &cnt, &overflow, complete ? &comp : nullptr, direct, &n_direct)) return 1;
         ctx->n_edges = std::min<uint64_t>(cnt, ctx->edge_cap);
         if (!overflow) break;
         TC_CHECK(!edges_only, "tc_mst_of_edges: the candidate edges of the last pass overflowed the edge buffer");
@@ -1457,6 +1462,7 @@ static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t se
             TC_CHECK(semb_size == 0 && !edges_only, "tc_mst: %llu candidate edges exceed the device edge buffer (%llu)",
                      (unsigned long long)cnt, (unsigned long long)ctx->edge_cap);
             if (mst_bounded(ctx, kmer_size, mode, radio, start_index, mst, complete ? &comp : nullptr)) return 1;
+            is_direct = false;
             break;
         }
         if (cnt > ctx->edge_cap && ensure_edges(ctx, cnt)) return 1;      // (in a group: only the ranks that overflowed grow)
@@ -1497,6 +1503,7 @@ static int mst_impl(tc_ctx *ctx, int kmer_size, int mode, int radio, uint32_t se
             mst.push_back(e);
         }
     }
+    if (is_direct) { if (n_out) *n_out = n_direct; return 0; }
     if (out) std::copy(mst.begin(), mst.end(), out);
     if (n_out) *n_out = mst.size();
     return 0;

@@ -77,3 +77,56 @@ def genome_families(n_families, per_family, length, seed=12345, rates=(0.001, 0.
         for m in range(1, per_family):
             out.append(mutate(base, rates[m % len(rates)], rng))
     return out
+
+
+def incremental_tie_set(seed=1, n_reps=2000, n_queries=400, size=99, query_size=None, threshold=0.08, kmer=18,
+                        containment=False, hash_bits=31):
+    """Sketch set that stresses the tie rule of the reference's incremental greedy clustering (the winner among equal
+    distances is the first candidate in the iteration order of its phmap candidate table): n_reps mutually unrelated
+    representatives of `size` hashes that all hold one common hash (so every query touches ALL of them and the table
+    grows past its reserved capacity), followed by n_queries sketches that share EXACTLY the same number of hashes with
+    2-4 randomly chosen representatives (equal sizes -> equal distances), sometimes with unequal shares, sometimes with
+    none (they become representatives, and later queries tie between those too).
+    -> (list of ascending np.uint64 sketches, n_reps)"""
+    import math
+    rng = np.random.default_rng(seed)
+    qs = size if query_size is None else query_size
+    x = math.exp(-threshold * kmer)
+    jmin = x / (2.0 - x)
+    common_hash = 7
+    want = n_reps * (size - 1) + n_queries * qs
+    pool = np.unique(rng.integers(100, 1 << hash_bits, size=want + want // 4 + 1000, dtype=np.int64))
+    assert len(pool) >= want
+    pool = rng.permutation(pool)[:want].astype(np.uint64)
+    reps = [np.sort(np.concatenate([[common_hash], pool[i * (size - 1):(i + 1) * (size - 1)]]).astype(np.uint64)) for i in range(n_reps)]
+    priv = pool[n_reps * (size - 1):]
+    out = list(reps)
+    sources = list(range(n_reps))                 # sketches a query may draw from (representatives; later also new ones)
+    p = 0
+    for qi in range(n_queries):
+        m = int(rng.choice([0, 2, 2, 3, 4]))
+        chosen = rng.choice(len(sources), size=m, replace=False) if m else []
+        # smallest share that passes the filter for these sizes (Mash: c / (|q| + |r| - c) >= jmin; containment: c / min)
+        if containment:
+            cmin = int(math.ceil(jmin * min(qs, size))) + 1
+        else:
+            cmin = int(math.ceil(jmin * (qs + size) / (1.0 + jmin))) + 1
+        cmax = (qs - 1) // max(m, 1)
+        parts = [[common_hash]]
+        if m and cmax >= cmin:
+            c = int(rng.integers(cmin, cmax + 1))
+            unequal = rng.random() < 0.25
+            for j, si in enumerate(chosen):
+                src = out[sources[int(si)]]
+                src = src[src != common_hash]
+                cj = c - (j if unequal else 0)
+                parts.append(rng.choice(src, size=min(cj, len(src)), replace=False))
+        have = sum(len(x) for x in parts)
+        need = qs - have
+        parts.append(priv[p:p + need])
+        p += need
+        q = np.unique(np.concatenate([np.asarray(x, np.uint64) for x in parts]))
+        out.append(q)
+        if m == 0:
+            sources.append(len(out) - 1)
+    return out, n_reps

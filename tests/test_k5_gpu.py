@@ -259,3 +259,22 @@ def test_greedy_incremental_minhash_vs_oracle(ctx, oracle, monkeypatch, contain,
     assert got_n == want_n
     assert np.array_equal(got, want)
     assert (got != np.arange(half, n)).any() and got_n >= len(seeds)
+
+
+@pytest.mark.parametrize("batch", ["64", "4096"])
+@pytest.mark.parametrize("name", ["kssd", "minhash_s", "minhash_c"])
+def test_greedy_incremental_tie_rule_golden(ctx, oracle, monkeypatch, name, batch):
+    """the incremental rules on the reference's own runs over sets full of exact distance ties
+    (tests/golden/incremental, tools/make_golden_incremental.py): among equal distances the first candidate in the
+    iteration order of the reference's phmap candidate table wins -- same representative for every sketch."""
+    from test_oracle_golden import _clusters_after_increment, incremental_golden
+    monkeypatch.setenv("TCLUST_GREEDY_BATCH", batch)
+    sk, n_old, seeds, base, want_reps, want_clusters, gen = incremental_golden(name)
+    ctx.upload(sk)
+    if name == "kssd":
+        nrep, rep_of = ctx.greedy_incremental_kssd(gen["kmer"], gen["threshold"], n_old, seeds)
+    else:
+        nrep, rep_of = ctx.greedy_incremental(gen["kmer"], gen["threshold"], n_old, seeds, gen.get("containment", False))
+    cl, reps = _clusters_after_increment(base, seeds, n_old, rep_of)
+    assert reps == want_reps and nrep == len(want_reps)
+    assert cl == want_clusters

@@ -432,3 +432,56 @@ def test_append_golden_greedy_minhash_state(oracle, tag, contain):
     assert (cl, reps, nrep) == (s1["clusters"], s1["rep_ids"], len(s1["rep_ids"]))
     got = [[gid for gid, _ in c] for c in sketch_io.parse_cluster_file(os.path.join(d, "app.txt"))]
     assert got == s1["clusters"]
+
+
+def test_phmap_iteration_order_golden(oracle, tmp_path):
+    """the oracle's model of the reference's candidate table (phmap::flat_hash_map<int,int>, reserve(1000)) against
+    iteration orders recorded from the real container (tools/make_golden_incremental.py: ref_harness phorder), growth past
+    the reserved capacity included; and live against the container when oracle/_ref is built"""
+    import json
+    for case in json.load(open(os.path.join(GOLD, "incremental", "phmap_order.json"))):
+        assert oracle.phmap_iteration_order(case["keys"]).tolist() == case["order"], len(case["keys"])
+    exe = oracle.ref_bin("ref_harness")
+    if exe is not None:
+        rng = np.random.default_rng(77)
+        for n in (1, 17, 1000, 1792, 1793, 4000):
+            keys = rng.choice(1 << 20, n, replace=False).astype(np.int32)
+            keys.tofile(str(tmp_path / "k.bin"))
+            subprocess.check_call([exe, "phorder", str(tmp_path / "k.bin"), str(tmp_path / "o.bin")])
+            assert oracle.phmap_iteration_order(keys).tolist() == np.fromfile(str(tmp_path / "o.bin"), np.int32).tolist()
+
+
+def incremental_golden(name):
+    """-> (sketches in state order, n_old, seeds, base clusters, golden rep ids, golden clusters, generator args)"""
+    import json
+    g = json.load(open(os.path.join(GOLD, "incremental", name + ".json")))
+    sk, n_old = synth.incremental_tie_set(**g["generator"])
+    assert n_old == g["n_old"] and sorted(g["order"]) == list(range(len(sk)))
+    sk = [sk[i] for i in g["order"]]
+    seeds = [r for r in g["rep_ids"] if r < n_old]
+    assert g["rep_ids"][:len(seeds)] == seeds
+    base = [[m for m in cl if m < n_old] for cl in g["clusters"][:len(seeds)]]
+    return sk, n_old, seeds, base, g["rep_ids"], g["clusters"], g["generator"]
+
+
+@pytest.mark.parametrize("name", ["kssd", "minhash_s", "minhash_c"])
+def test_incremental_tie_rule_golden(oracle, name):
+    """KssdIncrementalCluster / MinHashIncrementalCluster of the unmodified reference on sets full of exact distance ties
+    (two to four representatives at the same distance; every query touches every representative, so the candidate table
+    grows past its reserved capacity): the oracle picks the same representative every time."""
+    sk, n_old, seeds, base, want_reps, want_clusters, gen = incremental_golden(name)
+    if name == "kssd":
+        nrep, rep_of = oracle.greedy_incremental_kssd(sk, gen["kmer"], gen["threshold"], n_old, seeds)
+    else:
+        nrep, rep_of = oracle.greedy_incremental_minhash(sk, gen["kmer"], gen["threshold"], n_old, seeds, gen.get("containment", False))
+    cl, reps = _clusters_after_increment(base, seeds, n_old, rep_of)
+    assert reps == want_reps and nrep == len(want_reps)
+    assert cl == want_clusters
+    # the set does contain ties that the creation-order rule would decide differently
+    ties = 0
+    for q, r in enumerate(rep_of, n_old):
+        if int(r) != q:
+            c = len(np.intersect1d(sk[q], sk[int(r)]))
+            same = [s for s in reps if s < q and s != int(r) and len(sk[s]) == len(sk[int(r)]) and len(np.intersect1d(sk[q], sk[s])) == c]
+            ties += any(s < int(r) for s in same)
+    assert ties >= 5, ties
