@@ -58,11 +58,15 @@ __global__ void k3t_flag_kernel(const uint32_t *key, const uint32_t *blk, unsign
 __global__ void k3t_work_kernel(const uint32_t *key, unsigned long long m, unsigned long long *work)
 {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    if (i + 1 < m && key[i + 1] == key[i]) return;
-    unsigned long long L = 1;
-    for (unsigned long long j = i; j-- > 0 && key[j] == key[i];) L++;
-    if (L > 1) atomicAdd(work, L * (L - 1) / 2);
+    unsigned long long v = 0;
+    if (i < m && !(i + 1 < m && key[i + 1] == key[i])) {
+        unsigned long long L = 1;
+        for (unsigned long long j = i; j-- > 0 && key[j] == key[i];) L++;
+        v = L * (L - 1) / 2;
+    }
+    // one atomic per warp: a million single-address atomics cost more than the rest of the flag build
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(work, v);
 }
 
 // diagonal tiles, and the row + column of every block without a union list (K3H streams those without a list)
