@@ -40,10 +40,12 @@ __global__ void k3t_gather_kernel(const uint32_t *bu_keys, const uint32_t *bu_co
 }
 
 // postings sorted by (rank, block): entry i pairs up with every earlier entry of the same rank (an earlier block)
-__global__ void k3t_flag_kernel(const uint32_t *key, const uint32_t *blk, unsigned long long m, uint32_t *flags, uint32_t words)
+// (*work > limit: the guard below has decided to flag every tile instead, nothing to do here)
+__global__ void k3t_flag_kernel(const uint32_t *key, const uint32_t *blk, unsigned long long m, uint32_t *flags, uint32_t words,
+                                const unsigned long long *work, unsigned long long limit)
 {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m || i == 0) return;
+    if (i >= m || i == 0 || *work > limit) return;
     const uint32_t k = key[i], b = blk[i];
     uint32_t *row = flags + (size_t)b * words;
     for (unsigned long long j = i; j-- > 0;) {
@@ -67,6 +69,14 @@ __global__ void k3t_work_kernel(const uint32_t *key, unsigned long long m, unsig
     // one atomic per warp: a million single-address atomics cost more than the rest of the flag build
     for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(work, v);
+}
+
+// the guard's other branch: every tile flagged (a superset is always correct)
+__global__ void k3t_saturate_kernel(uint32_t *flags, unsigned long long fwords, const unsigned long long *work, unsigned long long limit)
+{
+    if (*work <= limit) return;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < fwords;
+         i += (unsigned long long)gridDim.x * blockDim.x) flags[i] = 0xFFFFFFFFu;
 }
 
 // diagonal tiles, and the row + column of every block without a union list (K3H streams those without a list)
@@ -153,14 +163,16 @@ int tc_tile_flags_build(tc_ctx *ctx, const std::vector<uint32_t> &dist)
         unsigned long long *d_work = reinterpret_cast<unsigned long long *>(w8 + o_pref) + (nrb + 1), h_work = 0;
         TC_CUDA(cudaMemsetAsync(d_work, 0, 8, st));
         k3t_work_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(k1, m, d_work);
-        TC_CUDA(cudaMemcpyAsync(&h_work, d_work, 8, cudaMemcpyDeviceToHost, st));
-        TC_CUDA(cudaStreamSynchronize(st));
+        // the decision is taken on the device (both kernels read the estimate): no host round trip in the upload's tail
         const unsigned long long tiles = (unsigned long long)nrb * (nrb + 1) / 2;
-        if (h_work > std::max<unsigned long long>(64ull * tiles, 1ull << 28)) {
-            TC_CUDA(cudaMemsetAsync(ctx->d_tile_flags, 0xFF, fwords * 4, st));
-            if (getenv("TCLUST_TIMING")) fprintf(stderr, "[tclust timing] tile flags: %llu block-pair visits for %llu tiles: every tile flagged\n", h_work, tiles);
-        } else
-            k3t_flag_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(k1, b1, m, ctx->d_tile_flags, words);
+        const unsigned long long limit = std::max<unsigned long long>(64ull * tiles, 1ull << 28);
+        k3t_flag_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(k1, b1, m, ctx->d_tile_flags, words, d_work, limit);
+        k3t_saturate_kernel<<<(unsigned)std::min<unsigned long long>((fwords + 255) / 256, 4096), 256, 0, st>>>(ctx->d_tile_flags, fwords, d_work, limit);
+        if (getenv("TCLUST_TIMING")) {
+            TC_CUDA(cudaMemcpyAsync(&h_work, d_work, 8, cudaMemcpyDeviceToHost, st));
+            TC_CUDA(cudaStreamSynchronize(st));
+            if (h_work > limit) fprintf(stderr, "[tclust timing] tile flags: %llu block-pair visits for %llu tiles: every tile flagged\n", h_work, tiles);
+        }
         ctx->launches += 3 + (end_bit + 7) / 8;
     }
     k3t_fixed_kernel<<<nrb, 128, 0, st>>>(ctx->d_bu_count, nrb, ctx->d_tile_flags, words);

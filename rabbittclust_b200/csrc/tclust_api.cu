@@ -203,6 +203,14 @@ __global__ void check_sorted_kernel(const uint64_t *h, const unsigned long long 
     for (unsigned long long i = threadIdx.x + 1; i < len; i += blockDim.x)
         if (h[o + i] <= h[o + i - 1]) { atomicMin(bad, g); return; }
 }
+// the same check for sketches [g0, g0 + gridDim.x): upload_sorted_runs checks a sketch as soon as its last hash has landed
+__global__ void check_sorted_range_kernel(const uint64_t *h, const unsigned long long *off, uint32_t g0, unsigned int *bad)
+{
+    const uint32_t g = g0 + blockIdx.x;
+    const unsigned long long o = off[g], len = off[g + 1] - o;
+    for (unsigned long long i = threadIdx.x + 1; i < len; i += blockDim.x)
+        if (h[o + i] <= h[o + i - 1]) { atomicMin(bad, g); return; }
+}
 __global__ void sizes_kernel(const unsigned long long *off, uint32_t *size, uint32_t n)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,7 +304,11 @@ static int upload_sort_workspace(tc_ctx *ctx, uint64_t total, uint64_t clen, Upl
 // positions as values) into run c of buffer B as soon as its copy has landed, and whenever two neighbouring runs of one
 // width are complete they are merged into the other buffer (binary-counter order), so the work left when the last
 // byte arrives is one piece's sort and log2(UP_CHUNKS) merges instead of the sort of the whole set.
-static int upload_sorted_runs(tc_ctx *ctx, const uint64_t *hashes, uint64_t total, UploadSort *us)
+// The input contract (every sketch strictly ascending) is checked piece by piece as well: sketch g is checked by the
+// piece that brings its last hash (`off`: host offsets, `d_bad`: smallest offending sketch, read by the caller later), so
+// that only the last piece's sketches are checked after the copy.
+static int upload_sorted_runs(tc_ctx *ctx, const uint64_t *hashes, uint64_t total, UploadSort *us, const uint64_t *off, uint32_t n,
+                              unsigned int *d_bad)
 {
     cudaStream_t st = ctx->stream;
     if (!ctx->up_copy_stream) TC_CUDA(cudaStreamCreateWithFlags(&ctx->up_copy_stream, cudaStreamNonBlocking));
@@ -322,6 +334,16 @@ static int upload_sorted_runs(tc_ctx *ctx, const uint64_t *hashes, uint64_t tota
         if (len) TC_CUDA(cudaMemcpyAsync(ctx->d_hashes + pos, hashes + pos, len * 8, cudaMemcpyHostToDevice, ctx->up_copy_stream));
         TC_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->up_copy_stream));
         TC_CUDA(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
+        if (len) {
+            // sketches whose last hash lies in (pos, pos + len]: off[g + 1] in that range
+            const uint32_t g_lo = (uint32_t)(std::upper_bound(off + 1, off + n + 1, pos) - (off + 1));
+            const uint32_t g_hi = (uint32_t)(std::upper_bound(off + 1, off + n + 1, pos + len) - (off + 1));
+            if (g_hi > g_lo) {
+                check_sorted_range_kernel<<<g_hi - g_lo, 128, 0, st>>>(ctx->d_hashes, reinterpret_cast<const unsigned long long *>(ctx->d_off),
+                                                                        g_lo, d_bad);
+                ctx->launches++;
+            }
+        }
         if (len) {
             size_t tb = us->tmp_bytes;
             TC_CUDA(cub::DeviceRadixSort::SortPairs(us->tmp, tb, (const uint64_t *)(ctx->d_hashes + pos), us->k_b + pos,
@@ -492,19 +514,22 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
     const bool chunked = !no_hashes && !hashes_on_device && hashes != ctx->d_hashes && !ov_off &&
                          (total >= (16ull << 20) || (ov_force && total >= 2));
     UploadSort us;
+    unsigned int *d_bad_chunked = reinterpret_cast<unsigned int *>(ctx->d_edge_count + 3);
     if (no_hashes) {
         // sorted runs / finished ranks from a multi-GPU upload: no copy of the flat hashes (d_hashes stays empty: only the
         // independent validation kernel reads it), the order check runs on the ranks below
         ctx->hashes_resident = false;
     } else if (chunked) {
-        if (upload_sorted_runs(ctx, hashes, total, &us)) return 1;
+        TC_CUDA(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        TC_CUDA(cudaMemsetAsync(d_bad_chunked, 0xFF, 4, st));
+        if (upload_sorted_runs(ctx, hashes, total, &us, off, n, d_bad_chunked)) return 1;
     } else if (hashes != ctx->d_hashes)   // tc_sketches_upload_rows has staged them in place already
         TC_CUDA(cudaMemcpyAsync(ctx->d_hashes, hashes, total * 8,
                                 hashes_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-    TC_CUDA(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (!chunked) TC_CUDA(cudaMemcpyAsync(ctx->d_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     sizes_kernel<<<nblk(n, 256), 256, 0, st>>>(reinterpret_cast<unsigned long long *>(ctx->d_off), ctx->d_size, n);
     ctx->launches++;
-    if (!no_hashes) {   // input contract check (0.8 GB read at N = 100k: ~0.2 ms)
+    if (!no_hashes && !chunked) {   // input contract check (0.8 GB read at N = 100k: ~0.2 ms)
         unsigned int *d_bad = reinterpret_cast<unsigned int *>(ctx->d_edge_count + 3), h_bad = 0xFFFFFFFFu;
         TC_CUDA(cudaMemsetAsync(d_bad, 0xFF, 4, st));
         check_sorted_kernel<<<n, 128, 0, st>>>(ctx->d_hashes, reinterpret_cast<unsigned long long *>(ctx->d_off), n, d_bad);
@@ -561,7 +586,16 @@ static int upload_common(tc_ctx *ctx, const uint64_t *hashes, bool hashes_on_dev
         TC_CUDA(cudaMemsetAsync(ctx->d_multi, 0, mwords * 4, st));
         scatter_rank_multi_kernel<<<nblk(total, 256), 256, 0, st>>>(flag, us.vals, ctx->d_ranks, total, ctx->d_multi);
         ctx->launches += 12;  // iota, sort passes (cub), flags, scan, scatter (approximate; cub internals)
+        unsigned int h_bad = 0xFFFFFFFFu;
+        if (chunked) TC_CUDA(cudaMemcpyAsync(&h_bad, d_bad_chunked, 4, cudaMemcpyDeviceToHost, st));
         TC_CUDA(cudaStreamSynchronize(st));
+        if (h_bad != 0xFFFFFFFFu) {         // verdict of the piece-wise contract check (upload_sorted_runs)
+            const uint32_t g = h_bad;
+            reset_sketches(ctx);
+            tc_set_error("tc_sketches_upload: sketch %u is not strictly ascending (sketches must be sorted and duplicate-free, "
+                         "as Sketch::MinHash::storeMinHashes returns them)", g);
+            return 1;
+        }
         pt.mark("flags + scan + scatter");
     }
     if (no_hashes && total > 0) {      // the contract check on the ranks (order-preserving: same verdict as on the hashes)

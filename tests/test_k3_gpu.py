@@ -252,6 +252,30 @@ def test_edge_buffer_grows_on_overflow(tc, oracle, monkeypatch):
             c.allpairs_pass(1 << 30)
 
 
+def test_piecewise_upload_checks_every_sketch(tc, monkeypatch):
+    """the upload in pieces (TCLUST_UPLOAD_OVERLAP=1 forces it for a small set) checks a sketch when the piece holding its
+    last hash has landed: an offending sketch anywhere -- first piece, a sketch straddling two pieces, last piece -- is named"""
+    monkeypatch.setenv("TCLUST_UPLOAD_OVERLAP", "1")
+    rng = np.random.default_rng(3)
+    base = [np.unique(rng.integers(0, 1 << 40, int(z), dtype=np.uint64)) for z in rng.integers(1, 3000, 40)]
+    base.insert(7, np.zeros(0, np.uint64))                                  # an empty sketch in the middle
+    with tc.Context(0) as c:
+        c.upload(base)
+        want = c.pair_common(0, len(base), 0, len(base), impl=2)
+        total = sum(len(b) for b in base)
+        for idx in (0, 3, 19, 24, len(base) - 1):
+            if len(base[idx]) < 2:
+                continue
+            bad = [b.copy() for b in base]
+            j = len(bad[idx]) // 2
+            bad[idx][j] = bad[idx][j - 1]                                    # a duplicate somewhere inside sketch idx
+            with pytest.raises(tc.TclustError, match="sketch %d is not strictly ascending" % idx):
+                c.upload(bad)
+        c.upload(base)                                                      # the context is usable again afterwards
+        assert np.array_equal(c.pair_common(0, len(base), 0, len(base), impl=2), want)
+        assert total > 8 * 1024                                             # several pieces of >= 1024 hashes
+
+
 def test_upload_rejects_unsorted_or_duplicate_sketches(tc):
     a = np.array([5, 9, 9, 12], np.uint64)           # duplicate
     b = np.array([3, 2, 7], np.uint64)               # not ascending
