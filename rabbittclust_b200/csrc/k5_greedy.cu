@@ -463,17 +463,17 @@ static int greedy_impl(tc_ctx *const *cs, int G, int kmer_size, int containment,
                 keys.reserve(end - lo);
                 for (tc_cand *c = lo; c < end; c++) keys.push_back(order_of[c->rep]);
                 const std::vector<int> it = phmap_order.order(keys);
-                std::vector<char> tied(nrep_total, 0);
+                std::vector<int> tied;                     // creation numbers of the tied candidates (a handful)
                 for (tc_cand *c = lo; c < end; c++) {
                     const int common = (int)c->common, sizeQry = size_ref, sizeRef = (int)ctx->h_size[c->rep];
                     if (sizeRef == 0) continue;
                     if (kssd) { const double ratio = (double)sizeQry / sizeRef; if (ratio > max_ratio || ratio < 1.0 / max_ratio) continue; }
                     const int need = containment ? (int)(jmin * std::min(sizeQry, sizeRef)) : (int)(jmin * (sizeQry + sizeRef) / (1.0 + jmin));
                     if (common < need) continue;
-                    if (tc_greedy_dist(common, sizeRef, sizeQry, containment, kmer_size) == best_dist) tied[order_of[c->rep]] = 1;
+                    if (tc_greedy_dist(common, sizeRef, sizeQry, containment, kmer_size) == best_dist) tied.push_back(order_of[c->rep]);
                 }
                 for (int idx : it)
-                    if (tied[idx]) { best_rep = (int)rep_by_order[idx]; break; }
+                    if (std::find(tied.begin(), tied.end(), idx) != tied.end()) { best_rep = (int)rep_by_order[idx]; break; }
             }
             if (best_rep != -1) {
                 rep_of[q] = best_rep;
