@@ -346,8 +346,9 @@ int tc_greedy_cluster_kssd(tc_ctx *ctx, int kmer_size, double threshold, int32_t
  * Equal distances: the reference walks its candidates in the iteration order of its
  * `phmap::flat_hash_map<int,int> candidate_counts` (reserve(1000)) and keeps the first of the smallest distance; that
  * order is a function of the touched representatives in first-touch order and is reproduced exactly (the device
- * returns every touched representative for these rules).  Input sketches of the reference's single-file KSSD mode are
- * stored there in hash-set order, here ascending: first-touch order, hence a tie, can differ for such folders only. */
+ * returns every touched representative for these rules).  (Sketches of the reference's single-file KSSD mode are
+ * stored there in hash-set order, and its incremental step then merges those unsorted arrays as if they were sorted:
+ * its distances are wrong for such folders; this call always works on ascending sets.) */
 int tc_greedy_incremental_kssd(tc_ctx *ctx, int kmer_size, double threshold, uint32_t start_index, const uint32_t *rep_ids,
                                uint32_t n_reps, int32_t *rep_of, uint32_t *n_clusters);
 /* MinHashIncrementalCluster (src/greedy.cpp:1963-2130; caller: append_clust_greedy with a saved state,

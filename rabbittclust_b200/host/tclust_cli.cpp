@@ -70,6 +70,7 @@ struct Genome {          // SketchInfo (src/SketchInfo.h:23-36) without the owni
     vector<uint64_t> hashes;
     int id = 0;
     uint32_t ssize = 0;       // the sketch-size argument its MinHash object was built with (getSketchSize(): state files)
+    bool from_state = false;  // rebuilt from a KSSD cluster_state.bin: no record names, no per-record length (KssdClusterState::load)
 };
 
 struct Options {
@@ -920,6 +921,8 @@ void print_result(const vector<vector<int>> &cluster, const vector<Genome> &g, b
             if (by_file)
                 fprintf(fp, "\t%5d\t%6d\t%12dnt\t%20s\t%20s\t%s\n", (int)j, id, (int)g[id].total_len, g[id].file_name.c_str(),
                         g[id].name.c_str(), g[id].comment.c_str());
+            else if (g[id].from_state)      // seqInfo of a state-loaded sketch is value-initialised: length 0, empty strings
+                fprintf(fp, "\t%6d\t%6d\t%12dnt\t%20s\t%s\n", (int)j, id, 0, "", "");
             else
                 fprintf(fp, "\t%6d\t%6d\t%12dnt\t%20s\t%s\n", (int)j, id, (int)g[id].total_len, g[id].name.c_str(),
                         g[id].comment.c_str());
@@ -1175,6 +1178,7 @@ bool load_kssd_state(KssdState &s, const string &path)
         x.file_name.resize(nl);
         if (nl && fread(&x.file_name[0], 1, nl, fp) != nl) return bad();
         x.name = "N/A"; x.comment = "N/A";           // the state keeps no record names: printKssdResult prints N/A (MST_IO.cpp:99-104)
+        x.from_state = true;
     }
     for (int r : s.rep_ids) if (r < 0 || (size_t)r >= nsk) return bad();
     if (!rd(fp, ncl) || ncl > nsk) return bad();

@@ -187,3 +187,49 @@ def test_reference_continues_from_our_minhash_state_live(tmp_path):
             _run(exe, t1 + ["-l", "--append", second, "--presketched", folder, "--save-rep", "-d", "0.05", "-o", "app.txt"], cwd)
             results[(who, state_of)] = open(os.path.join(cwd, "app.txt"), "rb").read()
     assert len(set(results.values())) == 1, {k: len(v) for k, v in results.items()}
+
+
+def test_clust_greedy_fast_state_single_file_mode_live(tmp_path, oracle):
+    """live, sketch-by-sequence: clust-greedy --fast -i (one multi-FASTA) --save-rep, then --append of a second multi-FASTA
+    from the saved state.  The initial clustering equals the unmodified reference's byte for byte, and the rows of
+    state-loaded sketches print as the reference prints them (length 0, empty names: its seqInfo is value-initialised).
+    The reference's incremental step itself is broken in this mode: it feeds the UNSORTED hash arrays of the single-file
+    consumer (hash-set iteration order) to a sorted-merge Jaccard (calculate_mash_distance, greedy.cpp:72-119), so its
+    distances are garbage and nearly every new record founds a cluster.  Ours is checked against the oracle instead."""
+    _need_bins()
+    from test_cli_gpu import REF, _make_genomes, _write_fasta
+    from test_oracle_golden import _clusters_after_increment
+    from rabbittclust_b200 import fasta
+    d = str(tmp_path / "genomes")
+    os.makedirs(d)
+    _, multi = _make_genomes(d, n_fam=4, per_fam=6, length=300000, seed=91)
+    recs = fasta.read_fasta(multi)
+    rng = np.random.default_rng(8)
+    order = rng.permutation(len(recs))
+    first, second = str(tmp_path / "first.fna"), str(tmp_path / "second.fna")
+    _write_fasta(first, [("%s %s" % (recs[i][0], recs[i][1] or ""), recs[i][2]) for i in order[:14]])
+    _write_fasta(second, [("%s %s" % (recs[i][0], recs[i][1] or ""), recs[i][2]) for i in order[14:]])
+    out, folders = {}, {}
+    for who, exe, t1 in (("ref", os.path.join(REF, "clust-greedy"), ["-t", "1"]), ("ours", os.path.join(OURS, "clust-greedy"), [])):
+        cwd = str(tmp_path / who)
+        folder, _ = _run(exe, t1 + ["--fast", "-i", first, "-d", "0.05", "--save-rep", "-o", "base.txt"], cwd)
+        assert os.path.exists(os.path.join(folder, "cluster_state.bin")), who
+        if who == "ours":
+            before = sketch_io.read_kssd_cluster_state(os.path.join(folder, "cluster_state.bin"))
+        _run(exe, t1 + ["--fast", "--append", second, "--presketched", folder, "--save-rep", "-d", "0.05", "-o", "app.txt"], cwd)
+        out[who] = (open(os.path.join(cwd, "base.txt"), "rb").read(), open(os.path.join(cwd, "app.txt"), "rb").read())
+        folders[who] = folder
+    assert out["ref"][0] == out["ours"][0]
+    # rows of the 14 state-loaded sketches: same text in both files
+    def old_rows(text):
+        return sorted(l.split(b"\t", 2)[2] for l in text.split(b"\n") if l.startswith(b"\t") and int(l.split(b"\t")[2]) < 14)
+    assert old_rows(out["ref"][1]) == old_rows(out["ours"][1]) and len(old_rows(out["ours"][1])) == 14
+    # our increment = the oracle's on the sketches of our state
+    after = sketch_io.read_kssd_cluster_state(os.path.join(folders["ours"], "cluster_state.bin"))
+    sk = [x["hashes"] for x in after["sketches"]]
+    nrep, rep_of = oracle.greedy_incremental_kssd(sk, after["kmer_size"], after["threshold"], 14, before["rep_ids"])
+    cl, reps = _clusters_after_increment(before["clusters"], before["rep_ids"], 14, rep_of)
+    assert (cl, reps) == (after["clusters"], after["rep_ids"])
+    got = [[gid for gid, _ in c] for c in sketch_io.parse_cluster_file(str(tmp_path / "ours" / "app.txt"))]
+    assert got == after["clusters"]
+    assert sum(len(c) for c in cl) > sum(len(c) for c in before["clusters"]) + 3       # new records do join clusters
