@@ -363,8 +363,12 @@ class Context:
             _chk(lib().tc_edges_download(self._h, out.ctypes.data, m, C.byref(n)))
         return out
 
-    def mst(self, k, threshold, containment=False):
-        out = np.empty(max(self.n, 1), EDGE_DTYPE)
+    def mst(self, k, threshold, containment=False, out=None):
+        """out: optional caller-owned array of >= n EDGE_DTYPE entries (the C ABI writes into the caller's buffer); a view
+        of its first m entries is returned"""
+        if out is None:
+            out = np.empty(max(self.n, 1), EDGE_DTYPE)
+        assert out.dtype == EDGE_DTYPE and len(out) >= max(self.n, 1) and out.flags.c_contiguous
         m = C.c_uint64(0)
         _chk(lib().tc_mst(self._h, k, int(containment), threshold, out.ctypes.data, C.byref(m)))
         return out[:int(m.value)]
