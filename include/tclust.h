@@ -45,9 +45,13 @@ int         tc_version(void);
 const char *tc_last_error(void);
 
 /* ---- context ------------------------------------------------------------------------ */
+/* The reference keeps all state in host vectors owned by its callers (vector<SketchInfo>, SketchInfo.h:23-36) and
+ * has nothing to create; the context is what SURVEY.md 8b-3 introduces for the device-resident copies: one per
+ * device, one caller thread at a time.  Several devices: one context each, joined by tc_mg_join (below). */
 int  tc_ctx_create(int device, tc_ctx **out);
 void tc_ctx_destroy(tc_ctx *ctx);
-/* number of kernels of this library launched on the context so far (bench accounting) */
+/* measurement aids without a counterpart in the reference (its Timer prints, src/sub_command.cpp `#ifdef Timer`, are
+ * what the CLI reproduces): number of kernels of this library launched on the context so far (bench accounting) */
 uint64_t tc_kernel_launches(const tc_ctx *ctx);
 /* duration of the last dense-pass kernel (tc_allpairs_pass*, tc_mst*), CUDA events recorded on the context's stream
  * immediately around the launch; -1 if no pass has completed */
@@ -142,7 +146,9 @@ int tc_sketches_upload_dev(tc_ctx *ctx, const uint64_t *hashes_dev, const uint64
 int tc_sketches_upload_rows(tc_ctx *ctx, const uint64_t *const *rows, const uint64_t *sizes, uint32_t n);
 
 /*
- * Multi-GPU upload (every GPU of a group needs all sketches resident, but each should move and sort only its share):
+ * Multi-GPU upload ("every GPU holds all N sketches for HP-2"; the reference is a single-node OpenMP
+ * program and has no counterpart -- its threads share the one vector<SketchInfo>).  Every GPU of a group needs all sketches
+ * resident, but each should move and sort only its share:
  * rank r copies its contiguous share [pos_base, pos_base + len) of the flat hash array to its device and calls
  * tc_upload_sort_share_dev, which sorts the share by hash and pairs every hash with its position in the flat array; the
  * ranks all-gather the sorted runs (keys + positions; NCCL, plumbing) and every rank calls tc_sketches_upload_runs_dev,
