@@ -69,6 +69,8 @@ def lib():
         L.oc_greedy_inverted.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_int, C.c_double, i32p]
         L.oc_greedy_incremental_kssd.restype = C.c_int
         L.oc_greedy_incremental_kssd.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_double, C.c_int, i32p, C.c_int, i32p]
+        L.oc_greedy_kssd.restype = C.c_int
+        L.oc_greedy_kssd.argtypes = [u64p, u64p, C.c_int, C.c_int, C.c_double, i32p]
         L.oc_phmap_iteration_order.restype = None
         L.oc_phmap_iteration_order.argtypes = [i32p, C.c_int, i32p]
         L.oc_greedy_incremental_minhash.restype = C.c_int
@@ -279,6 +281,15 @@ def greedy_incremental_kssd(sketches, k, threshold, start, seeds):
     nc = lib().oc_greedy_incremental_kssd(_p(h, C.c_uint64), _p(off, C.c_uint64), n, k, threshold, start,
                                           _p(sd, C.c_int32), len(sd), _p(rep, C.c_int32))
     return nc, rep[start:n]
+
+
+def greedy_kssd(sketches, k, threshold):
+    """KssdGreedyClusterWithInvertedIndex on sketches already in the reference's processing order: (#clusters, rep_of)"""
+    h, off = pack_sketches(sketches)
+    n = len(sketches)
+    rep = np.zeros(max(n, 1), np.int32)
+    nc = lib().oc_greedy_kssd(_p(h, C.c_uint64), _p(off, C.c_uint64), n, k, threshold, _p(rep, C.c_int32))
+    return nc, rep[:n]
 
 
 def phmap_iteration_order(keys):

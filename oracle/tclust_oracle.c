@@ -517,6 +517,50 @@ int oc_greedy_inverted(const uint64_t *hashes, const uint64_t *off, int N, int k
     return nrep;
 }
 
+/* KssdGreedyClusterWithInvertedIndex with one thread (greedy.cpp:566-899), for sketches already in its processing order
+ * (hash count descending, its std::sort :592-596): sketch j probes the index of the representatives (:707-735), a touched
+ * representative passes when common >= ceil(jmin * (|A| + |B|) / (1 + jmin)) (:771), the one of largest Jaccard wins, the
+ * first in `touched` order among equals (strict >, :790-793; `touched` = order of first contact: query hashes ascending,
+ * postings in representative order).  The periodic pruning of too-large representatives (:690-704) only removes
+ * representatives that can no longer pass the filter (|rep| > |query| / (0.8 jmin) implies common_min > |query|).
+ * rep_of[j] = representative sketch of j (itself for a representative).  Returns #clusters. */
+int oc_greedy_kssd(const uint64_t *hashes, const uint64_t *off, int N, int k, double threshold, int32_t *rep_of)
+{
+    if (N == 0) return 0;
+    int *reps = (int *)malloc(sizeof(int) * N), nrep = 0;
+    touched_t *tc = (touched_t *)malloc(sizeof(touched_t) * N);
+    const double x = exp(-threshold * k);                    /* :650-652 */
+    const double jaccard_min = x / (2.0 - x);
+    reps[nrep++] = 0; rep_of[0] = 0;
+    for (int j = 1; j < N; j++) {
+        const uint64_t *q = hashes + off[j];
+        const int sizeRef = (int)(off[j + 1] - off[j]);
+        int nt = 0;
+        for (int r = 0; r < nrep; r++) {
+            const int id = reps[r];
+            uint32_t fh;
+            const int c = (int)oc_intersect_u64(q, sizeRef, hashes + off[id], off[id + 1] - off[id], &fh);
+            if (c > 0) { tc[nt].first_hit = fh; tc[nt].order = r; tc[nt].rep = id; tc[nt].common = c; nt++; }
+        }
+        qsort(tc, nt, sizeof(touched_t), cmp_touched);
+        double best_jaccard = -1.0;
+        int best_rep = -1;
+        for (int t = 0; t < nt; t++) {
+            const int id = tc[t].rep, common = tc[t].common;
+            const int sizeQry = (int)(off[id + 1] - off[id]);
+            const int common_min = (int)ceil(jaccard_min * (sizeRef + sizeQry) / (1.0 + jaccard_min));
+            if (common < common_min) continue;
+            const int denom = sizeRef + sizeQry - common;
+            const double jaccard = denom == 0 ? 1.0 : (double)common / denom;
+            if (jaccard > best_jaccard) { best_jaccard = jaccard; best_rep = id; }
+        }
+        if (best_rep != -1) rep_of[j] = best_rep;
+        else { reps[nrep++] = j; rep_of[j] = j; }
+    }
+    free(reps); free(tc);
+    return nrep;
+}
+
 /* ---- iteration order of the reference's candidate table ----------------------------------------------------------
  * Both incremental rules collect the touched representatives in `phmap::flat_hash_map<int,int> candidate_counts;
  * candidate_counts.reserve(1000)` (greedy.cpp:1771-1772, 2014-2015), copy the table into a vector in ITERATION order and

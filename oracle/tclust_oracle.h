@@ -92,6 +92,10 @@ int oc_clusters_from_mst(const oc_edge *mst, size_t n_edges, int N, double thres
 int oc_greedy_inverted(const uint64_t *hashes, const uint64_t *off, int N, int k,
                        int containment, double threshold, int32_t *rep_of);
 
+/* KssdGreedyClusterWithInvertedIndex with -t 1 (greedy.cpp:566-899) on sketches in its processing order (size
+ * descending): per-pair ceil()ed common filter, largest Jaccard wins, first in touched order among equals. */
+int oc_greedy_kssd(const uint64_t *hashes, const uint64_t *off, int N, int k, double threshold, int32_t *rep_of);
+
 /* iteration order of `phmap::flat_hash_map<int,int> m; m.reserve(1000); m[key]++` for distinct keys in insertion order
  * (the reference's candidate table, greedy.cpp:1771-1803; src/phmap.h) */
 void oc_phmap_iteration_order(const int32_t *keys, int n, int32_t *out);

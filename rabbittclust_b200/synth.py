@@ -130,3 +130,18 @@ def incremental_tie_set(seed=1, n_reps=2000, n_queries=400, size=99, query_size=
         if m == 0:
             sources.append(len(out) - 1)
     return out, n_reps
+
+
+def kssd_like_families(seed=3, n_fam=12, per_fam=10, pool=480, keep_lo=0.5, keep_hi=1.0, hash_bits=24):
+    """KSSD-like sketch families in a small hash space (2^24, as k = 18 / drlevel 3 gives): members keep a random
+    keep_lo..keep_hi share of a family pool of `pool` hashes plus up to 60 private ones -- many equal sizes and equal
+    Jaccard values, i.e. ties for the greedy rules.  -> list of ascending np.uint64 sketches, family by family"""
+    rng = np.random.default_rng(seed)
+    sk = []
+    for f in range(n_fam):
+        p = rng.choice(1 << hash_bits, pool, replace=False)
+        for m in range(per_fam):
+            keep = rng.choice(p, int(pool * rng.uniform(keep_lo, keep_hi)), replace=False)
+            priv = rng.integers(0, 1 << hash_bits, int(rng.integers(0, 60)))
+            sk.append(np.unique(np.concatenate([keep, priv])).astype(np.uint64))
+    return sk

@@ -278,3 +278,22 @@ def test_greedy_incremental_tie_rule_golden(ctx, oracle, monkeypatch, name, batc
     cl, reps = _clusters_after_increment(base, seeds, n_old, rep_of)
     assert reps == want_reps and nrep == len(want_reps)
     assert cl == want_clusters
+
+
+@pytest.mark.parametrize("case", range(3))
+def test_greedy_kssd_rule_golden_and_oracle(ctx, oracle, case):
+    """tc_greedy_cluster_kssd against the committed runs of the unmodified clust-greedy --fast --presketched
+    (tests/golden/incremental/greedy_kssd_full.json) and against the oracle's restatement of the rule"""
+    from test_oracle_golden import kssd_greedy_goldens
+    g = kssd_greedy_goldens()[case]
+    sk = synth.kssd_like_families(**g["generator"])
+    sk = [sk[i] for i in g["order"]]
+    ctx.upload(sk)
+    nc, rep = ctx.greedy_cluster_kssd(g["kmer"], g["threshold"])
+    nc_o, rep_o = oracle.greedy_kssd(sk, g["kmer"], g["threshold"])
+    assert nc == nc_o == len(g["clusters"])
+    assert np.array_equal(rep, rep_o)
+    want = np.zeros(len(sk), np.int32)
+    for c in g["clusters"]:
+        want[c] = c[0]
+    assert np.array_equal(rep, want)

@@ -485,3 +485,28 @@ def test_incremental_tie_rule_golden(oracle, name):
             same = [s for s in reps if s < q and s != int(r) and len(sk[s]) == len(sk[int(r)]) and len(np.intersect1d(sk[q], sk[s])) == c]
             ties += any(s < int(r) for s in same)
     assert ties >= 5, ties
+
+
+def kssd_greedy_goldens():
+    import json
+    return json.load(open(os.path.join(GOLD, "incremental", "greedy_kssd_full.json")))
+
+
+@pytest.mark.parametrize("case", range(3))
+def test_greedy_kssd_rule_golden(oracle, case):
+    """KssdGreedyClusterWithInvertedIndex through the unmodified clust-greedy --fast --presketched (-t 1) on sets with many
+    equal sizes and equal Jaccard values (tools/make_golden_incremental.py): the oracle's restatement gives the same
+    clusters in the same order, members in arrival order."""
+    g = kssd_greedy_goldens()[case]
+    sk = synth.kssd_like_families(**g["generator"])
+    sk = [sk[i] for i in g["order"]]
+    assert all(len(sk[i]) >= len(sk[i + 1]) for i in range(len(sk) - 1))          # the reference's processing order
+    nc, rep = oracle.greedy_kssd(sk, g["kmer"], g["threshold"])
+    clusters, cid = [], {}
+    for j, r in enumerate(rep):
+        if int(r) == j:
+            cid[j] = len(clusters)
+            clusters.append([j])
+        else:
+            clusters[cid[int(r)]].append(j)
+    assert nc == len(g["clusters"]) and clusters == g["clusters"]

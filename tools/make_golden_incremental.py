@@ -6,6 +6,9 @@ order of the reference's `phmap::flat_hash_map<int,int> candidate_counts` -- rep
   tests/golden/incremental/minhash_s.json   MinHash..., Mash mode                                   (ref_harness minhashinc)
   tests/golden/incremental/minhash_c.json   MinHash..., containment mode
   tests/golden/incremental/phmap_order.json insertion sequences -> iteration order of the real container (ref_harness phorder)
+  tests/golden/incremental/greedy_kssd_full.json   the whole-set rule KssdGreedyClusterWithInvertedIndex: the unmodified
+                                            clust-greedy --fast --presketched (-t 1) on synth.kssd_like_families sets
+                                            (many equal sizes and Jaccard values): processing order + clusters
 Each file holds the generator arguments (the sketches are regenerated from the seed), the state order, the representative
 ids and the clusters the UNMODIFIED reference produced with one thread.
 usage: python tools/make_golden_incremental.py   (needs oracle/_ref; rewrites tests/golden/incremental)"""
@@ -81,6 +84,28 @@ def main():
                    "n_old": n_old, "order": order, "rep_ids": reps, "clusters": clusters},
                   open(os.path.join(GOLD, name + ".json"), "w"))
         print(name, "sketches", len(sk), "representatives", len(reps), "(new: %d)" % n_new_reps, "clusters with members", multi)
+    # ---- KssdGreedyClusterWithInvertedIndex through the unmodified binary
+    full = []
+    for gen in (dict(seed=3, n_fam=12, per_fam=10), dict(seed=4, n_fam=30, per_fam=12, keep_lo=0.3), dict(seed=5, n_fam=6, per_fam=40, pool=200, keep_lo=0.4)):
+        sk = synth.kssd_like_families(**gen)
+        with tempfile.TemporaryDirectory() as tmp:
+            folder = os.path.join(tmp, "kssd")
+            write_kssd_folder(folder, sk)
+            p = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "clust-greedy"), "-t", "1", "--fast", "--presketched", folder, "-d", "0.05",
+                                "-o", "out.txt"], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            if p.returncode:
+                sys.exit("FAILED clust-greedy --fast --presketched\n" + p.stderr.decode()[-2000:])
+            ref = sketch_io.parse_cluster_file(os.path.join(tmp, "out.txt"))
+        # the cluster file carries (position in the processing order, name s<folder index>): the std::sort by size is not stable
+        pos_of = {}
+        for c in ref:
+            for gid, nm in c:
+                pos_of[gid] = int(nm[1:])
+        assert sorted(pos_of) == list(range(len(sk)))
+        full.append({"generator": gen, "cmd": "oracle/_ref/clust-greedy -t 1 --fast --presketched <folder> -d 0.05 -o out.txt", "kmer": 18,
+                     "threshold": 0.05, "order": [pos_of[p] for p in range(len(sk))], "clusters": [[gid for gid, _ in c] for c in ref]})
+        print("greedy_kssd_full", gen, "clusters", len(ref))
+    json.dump(full, open(os.path.join(GOLD, "greedy_kssd_full.json"), "w"))
     # the candidate table itself
     rng = np.random.default_rng(5)
     seqs = []
