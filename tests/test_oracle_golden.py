@@ -510,3 +510,24 @@ def test_greedy_kssd_rule_golden(oracle, case):
         else:
             clusters[cid[int(r)]].append(j)
     assert nc == len(g["clusters"]) and clusters == g["clusters"]
+
+
+@pytest.mark.parametrize("k,drlevel", [(14, 0), (16, 1), (18, 3), (20, 2)])
+def test_kssd_per_record_rule_equals_list_rule_for_even_k(oracle, k, drlevel):
+    """for an even k the single-file consumer (tuple not cleared at a gap, window after k valid bases) selects exactly the
+    windows of the list-mode loop: random records with gaps of every length, lower case and other codes"""
+    rng = np.random.default_rng(k * 10 + drlevel)
+    for trial in range(6):
+        b = bytearray(synth.random_genome(int(rng.integers(2000, 30000)), rng))
+        for p in rng.integers(0, len(b) - 300, 25):
+            L = int(rng.choice([1, 2, k - 1, k, k + 1, 60, 250]))
+            b[p:p + L] = b"N" * L
+        for p in rng.integers(0, len(b), 10):
+            b[p] = b"RYKMnx-"[int(rng.integers(0, 7))]
+        if trial % 2:
+            b[100:900] = bytes(b[100:900]).lower()
+        rec = bytes(b)
+        assert np.array_equal(oracle.kssd_sketch_seq(rec, k, drlevel), oracle.kssd_sketch([rec], k, drlevel))
+    # and for an odd k the two rules differ on a record with gaps
+    rec = bytes(synth.random_genome(4000, rng)[:2000]) + b"N" + bytes(synth.random_genome(2000, rng))
+    assert not np.array_equal(oracle.kssd_sketch_seq(rec, k - 1, 0), oracle.kssd_sketch([rec], k - 1, 0))
